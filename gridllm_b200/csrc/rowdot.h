@@ -1,0 +1,256 @@
+// Per-lane block-decode arithmetic of the decode GEMV and the engine's HBM row layouts.
+//
+// Everything here is __host__ __device__ so that tests/hostcheck can run the exact lane
+// program on the CPU (layout / bit-twiddling bugs are found without a GPU).  The CUDA kernels
+// in gemv.cu call these same functions; nothing in the product path runs them on the host.
+//
+// A "unit" is the slice of one weight row that one lane owns: 128 consecutive columns
+// (half a K-quant super-block, or four Q8_0 blocks).  The lane keeps the matching 128
+// activations in registers as two int8 planes (hi, lo) + per-32-column scales for the whole
+// kernel, so every weight byte staged in shared memory is touched exactly once.
+//
+// Engine row layouts in HBM (size-preserving permutations of the GGUF row):
+//   Q4_K   : native GGUF (144-B super-blocks; block b at 144*b).  Conflict-free as is because
+//            144 = 128 + 16 rotates consecutive blocks across the 16-B shared-memory slots.
+//   Q6_K-T : per row of nb super-blocks / nu = 2*nb units:
+//              [ql : 4 x nu x 16 B, chunk(i4,u) at (i4*nu+u)*16 ]   bytes h*64+16*i4.. of block b
+//              [qh : 2 x nu x 16 B, chunk(i2,u) at (i2*nu+u)*16 ]   bytes h*32+16*i2.. of block b
+//              [sc : nu x 8 B ]                                      scales[8h..8h+8) of block b
+//              [d  : nb x 2 B ]                                      (u = 2*b + h)
+//   Q8_0-T : per row of nu = cols/128 units (4 blocks each):
+//              [qs : 8 x nu x 16 B, chunk(i,u) at (i*nu+u)*16 ] [d : nu x 8 B]
+//   rows are padded to a multiple of 16 B (TMA bulk-copy granularity).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+namespace gl {
+
+constexpr int UNIT_COLS = 128;
+constexpr float ACT16_RANGE = 16256.0f;   // 127*128
+constexpr float ACT8_RANGE = 127.0f;
+
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+
+GL_HD int dp4a_s(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a((int)a, (int)b, c);
+#else
+    for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+    return c;
+#endif
+}
+
+GL_HD float half_bits_to_float(uint16_t h) {
+#if defined(__CUDA_ARCH__)
+    return __half2float(__ushort_as_half(h));
+#else
+    uint32_t sign = (uint32_t)(h & 0x8000) << 16, exp = (h >> 10) & 0x1F, man = h & 0x3FF, out;
+    if (exp == 0) {
+        if (man == 0) out = sign;
+        else { int e = -1; do { ++e; man <<= 1; } while (!(man & 0x400)); out = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FF) << 13); }
+    } else if (exp == 31) out = sign | 0x7F800000u | (man << 13);
+    else out = sign | ((exp + 112) << 23) | (man << 13);
+    float f; memcpy(&f, &out, 4); return f;
+#endif
+}
+
+// One lane's activation slice (128 columns).  Unused members are dead-code-eliminated per type.
+struct XUnit {
+    uint32_t hi[32];   // int8x4 words, plane "hi" (v = 128*hi + lo when ABITS==16; v = hi when 8)
+    uint32_t lo[32];
+    float sx[4];       // fixed-point step of each 32-column block
+    float sm[4];       // sx * sum(v) of each 32-column block      (Q4_K "mins" term)
+    int s16[8];        // sum(v) of each 16-column group           (Q6_K -32 offset)
+};
+
+template <int ABITS> GL_HD int combine(int acc_hi, int acc_lo) { return ABITS == 16 ? acc_hi * 128 + acc_lo : acc_hi; }
+
+// Snap 16 consecutive activations (half of a 32-column block) to the fixed point.  amax is the
+// max |x| over the WHOLE 32-column block.  Produces 4 hi words, 4 lo words and sum(v).
+// Spec (oracle/llama_oracle.py snap_i16 / snap_q8): sx = amax/RANGE, v = rint(x * (RANGE/amax)).
+template <int ABITS>
+GL_HD void snap16(const float* x, float amax, uint32_t* hi4, uint32_t* lo4, int* vsum) {
+    const float range = ABITS == 16 ? ACT16_RANGE : ACT8_RANGE;
+    const float inv = amax > 0.f ? range / amax : 0.f;
+    int s = 0;
+    for (int w = 0; w < 4; ++w) {
+        uint32_t h = 0, l = 0;
+        for (int b = 0; b < 4; ++b) {
+#if defined(__CUDA_ARCH__)
+            int v = __float2int_rn(x[4 * w + b] * inv);
+#else
+            int v = (int)__builtin_rintf(x[4 * w + b] * inv);
+#endif
+            s += v;
+            if (ABITS == 16) {
+                int lo = ((v + 64) & 127) - 64;
+                int hh = (v - lo) >> 7;
+                h |= (uint32_t)(hh & 0xFF) << (8 * b);
+                l |= (uint32_t)(lo & 0xFF) << (8 * b);
+            } else {
+                h |= (uint32_t)(v & 0xFF) << (8 * b);
+            }
+        }
+        hi4[w] = h;
+        lo4[w] = l;
+    }
+    *vsum = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q4_K, native layout.  blk -> 144-B super-block; hb = which half (columns 128*hb .. +127).
+// ---------------------------------------------------------------------------------------------
+template <int ABITS>
+GL_HD float unit_dot_q4k(const uint8_t* blk, int hb, const XUnit& x) {
+    const U4 hdr = *reinterpret_cast<const U4*>(blk);
+    const float d = half_bits_to_float((uint16_t)(hdr.x & 0xFFFF));
+    const float dmin = half_bits_to_float((uint16_t)(hdr.x >> 16));
+    const uint32_t s0 = hdr.y, s1 = hdr.z, s2 = hdr.w;
+    // 6-bit scale / min of the unit's four 32-column sub-blocks, one per byte
+    const uint32_t sc4 = hb ? ((s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u)) : (s0 & 0x3F3F3F3Fu);
+    const uint32_t mn4 = hb ? (((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u)) : (s1 & 0x3F3F3F3Fu);
+    const U4* q = reinterpret_cast<const U4*>(blk + 16 + 64 * hb);
+    float val = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {            // 32-byte chunk: low nibbles -> sub-block 2c, high -> 2c+1
+        int ah = 0, al = 0, bh = 0, bl = 0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const U4 qq = q[2 * c + v];
+            const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t lo4 = w[k] & 0x0F0F0F0Fu;
+                const uint32_t hi4 = (w[k] >> 4) & 0x0F0F0F0Fu;
+                const int xa = 8 * (2 * c) + 4 * v + k, xb = 8 * (2 * c + 1) + 4 * v + k;
+                ah = dp4a_s(lo4, x.hi[xa], ah);
+                bh = dp4a_s(hi4, x.hi[xb], bh);
+                if (ABITS == 16) {
+                    al = dp4a_s(lo4, x.lo[xa], al);
+                    bl = dp4a_s(hi4, x.lo[xb], bl);
+                }
+            }
+        }
+        const int sa = 2 * c, sb = 2 * c + 1;
+        const float sca = (float)((sc4 >> (8 * sa)) & 0xFF), scb = (float)((sc4 >> (8 * sb)) & 0xFF);
+        const float mna = (float)((mn4 >> (8 * sa)) & 0xFF), mnb = (float)((mn4 >> (8 * sb)) & 0xFF);
+        val += d * (sca * ((float)combine<ABITS>(ah, al) * x.sx[sa]) + scb * ((float)combine<ABITS>(bh, bl) * x.sx[sb]))
+             - dmin * (mna * x.sm[sa] + mnb * x.sm[sb]);
+    }
+    return val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q6_K-T.  row -> start of the (transposed) row in shared memory; nb blocks, nu = 2*nb units.
+// ---------------------------------------------------------------------------------------------
+template <int ABITS>
+GL_HD float unit_dot_q6k(const uint8_t* row, int nb, int u, const XUnit& x) {
+    const int nu = 2 * nb;
+    const uint8_t* qlp = row;
+    const uint8_t* qhp = row + (size_t)nb * 128;
+    const uint8_t* scp = row + (size_t)nb * 192 + (size_t)u * 8;
+    const uint16_t dbits = *reinterpret_cast<const uint16_t*>(row + (size_t)nb * 208 + (size_t)(u >> 1) * 2);
+    const float d = half_bits_to_float(dbits);
+    const uint32_t scw[2] = {reinterpret_cast<const uint32_t*>(scp)[0], reinterpret_cast<const uint32_t*>(scp)[1]};
+    U4 qh[2];
+    qh[0] = *reinterpret_cast<const U4*>(qhp + ((size_t)0 * nu + u) * 16);
+    qh[1] = *reinterpret_cast<const U4*>(qhp + ((size_t)1 * nu + u) * 16);
+    float val = 0.f;
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+        const U4 ql = *reinterpret_cast<const U4*>(qlp + ((size_t)i4 * nu + u) * 16);
+        const uint32_t qlw[4] = {ql.x, ql.y, ql.z, ql.w};
+        const U4 qhc = qh[i4 & 1];
+        const uint32_t qhw[4] = {qhc.x, qhc.y, qhc.z, qhc.w};
+        const int t = i4 >> 1;
+        int ah = 0, al = 0, bh = 0, bl = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a4 = (qlw[k] & 0x0F0F0F0Fu) | (((qhw[k] >> (2 * t)) & 0x03030303u) << 4);
+            const uint32_t b4 = ((qlw[k] >> 4) & 0x0F0F0F0Fu) | (((qhw[k] >> (4 + 2 * t)) & 0x03030303u) << 4);
+            const int xa = 4 * i4 + k, xb = 16 + 4 * i4 + k;
+            ah = dp4a_s(a4, x.hi[xa], ah);
+            bh = dp4a_s(b4, x.hi[xb], bh);
+            if (ABITS == 16) {
+                al = dp4a_s(a4, x.lo[xa], al);
+                bl = dp4a_s(b4, x.lo[xb], bl);
+            }
+        }
+        const int ga = i4, gb = 4 + i4;                       // 16-column groups inside the unit
+        const float sca = (float)(int8_t)(scw[ga >> 2] >> (8 * (ga & 3)));
+        const float scb = (float)(int8_t)(scw[gb >> 2] >> (8 * (gb & 3)));
+        const int ia = combine<ABITS>(ah, al) - 32 * x.s16[ga];
+        const int ib = combine<ABITS>(bh, bl) - 32 * x.s16[gb];
+        val += sca * ((float)ia * x.sx[ga >> 1]) + scb * ((float)ib * x.sx[gb >> 1]);
+    }
+    return d * val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q8_0-T.  row -> transposed row; cols = K; nu = K/128.
+// ---------------------------------------------------------------------------------------------
+template <int ABITS>
+GL_HD float unit_dot_q80(const uint8_t* row, int cols, int u, const XUnit& x) {
+    const int nu = cols / UNIT_COLS;
+    const uint32_t* dp = reinterpret_cast<const uint32_t*>(row + (size_t)cols + (size_t)u * 8);
+    const uint32_t dw[2] = {dp[0], dp[1]};
+    float val = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {            // 32-column block j of the unit
+        int ah = 0, al = 0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int i = 2 * j + v;
+            const U4 qq = *reinterpret_cast<const U4*>(row + ((size_t)i * nu + u) * 16);
+            const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ah = dp4a_s(w[k], x.hi[4 * i + k], ah);
+                if (ABITS == 16) al = dp4a_s(w[k], x.lo[4 * i + k], al);
+            }
+        }
+        const float dj = half_bits_to_float((uint16_t)(dw[j >> 1] >> (16 * (j & 1))));
+        val += dj * ((float)combine<ABITS>(ah, al) * x.sx[j]);
+    }
+    return val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side row repackers (loader) -- GGUF row -> engine row.  dst has engine_row_stride bytes.
+// ---------------------------------------------------------------------------------------------
+inline size_t align16(size_t n) { return (n + 15) & ~(size_t)15; }
+
+inline void repack_row_q6k(const uint8_t* src, uint8_t* dst, int nb) {
+    const int nu = 2 * nb;
+    for (int b = 0; b < nb; ++b) {
+        const uint8_t* blk = src + (size_t)b * 210;
+        for (int h = 0; h < 2; ++h) {
+            const int u = 2 * b + h;
+            for (int i4 = 0; i4 < 4; ++i4) memcpy(dst + ((size_t)i4 * nu + u) * 16, blk + h * 64 + 16 * i4, 16);
+            for (int i2 = 0; i2 < 2; ++i2) memcpy(dst + (size_t)nb * 128 + ((size_t)i2 * nu + u) * 16, blk + 128 + h * 32 + 16 * i2, 16);
+            memcpy(dst + (size_t)nb * 192 + (size_t)u * 8, blk + 192 + 8 * h, 8);
+        }
+        memcpy(dst + (size_t)nb * 208 + (size_t)b * 2, blk + 208, 2);
+    }
+}
+
+inline void repack_row_q80(const uint8_t* src, uint8_t* dst, int cols) {
+    const int nu = cols / UNIT_COLS;
+    for (int u = 0; u < nu; ++u) {
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t* blk = src + (size_t)(4 * u + j) * 34;
+            memcpy(dst + ((size_t)(2 * j) * nu + u) * 16, blk + 2, 16);
+            memcpy(dst + ((size_t)(2 * j + 1) * nu + u) * 16, blk + 18, 16);
+            memcpy(dst + (size_t)cols + (size_t)u * 8 + 2 * j, blk, 2);
+        }
+    }
+}
+
+}  // namespace gl

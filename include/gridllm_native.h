@@ -1,0 +1,157 @@
+/*
+ * gridllm_native.h -- C ABI of libgridllm_native.so, the B200-native inference engine that
+ * replaces the GridLLM worker's Ollama HTTP call-out.
+ *
+ * The reference has no FFI today: the seam is the TypeScript class OllamaService
+ * (/root/reference/client/src/services/OllamaService.ts) as consumed by WorkerClientService
+ * (client/src/services/WorkerClientService.ts:32,43,133,520,548,554,596,602,645).  Each entry
+ * point below names the reference call it stands in for.  Host bindings that sit on this ABI:
+ *   - gridllm_b200/native.py          (ctypes; what the tests and bench run)
+ *   - host/napi/addon.cc              (N-API shim, compiled where node_api.h exists)
+ *   - host/src/NativeInferenceService.ts (the drop-in for OllamaService)
+ *
+ * Conventions: every function returns 0 (GL_OK) or a negative gl_status; gl_last_error()
+ * returns a thread-local message owned by the library.  All buffers are caller-owned plain
+ * pointers + sizes; no torch / CUDA types cross the boundary.  One gl_engine = one GPU = one
+ * CUDA stream; calls on the same engine must be serialised by the caller, different engines are
+ * independent (8 engines <-> 8 worker ids in one process).
+ * There is NO CPU fallback: without a usable CUDA device gl_engine_create fails with
+ * GL_ERR_NO_DEVICE.
+ */
+#ifndef GRIDLLM_NATIVE_H
+#define GRIDLLM_NATIVE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_ABI_VERSION 1
+
+typedef enum gl_status {
+    GL_OK = 0,
+    GL_ERR_INVALID = -1,      /* bad argument */
+    GL_ERR_IO = -2,           /* file missing / unreadable */
+    GL_ERR_FORMAT = -3,       /* not a GGUF v2/v3 file, or missing tensor / key */
+    GL_ERR_UNSUPPORTED = -4,  /* architecture / tensor type / shape outside the hot path */
+    GL_ERR_CUDA = -5,         /* CUDA runtime error (message has the cudaError string) */
+    GL_ERR_NOMEM = -6,
+    GL_ERR_CANCELLED = -7,    /* token callback asked to stop */
+    GL_ERR_NO_DEVICE = -8,    /* no CUDA device: the product path never falls back to CPU */
+    GL_ERR_CONTEXT = -9       /* prompt + num_predict exceeds the engine's context */
+} gl_status;
+
+/* ggml tensor type ids the engine understands (public ggml enum values). */
+enum { GL_TYPE_F32 = 0, GL_TYPE_F16 = 1, GL_TYPE_Q8_0 = 8, GL_TYPE_Q4_K = 12, GL_TYPE_Q6_K = 14, GL_TYPE_BF16 = 30 };
+
+typedef struct gl_engine gl_engine;
+
+typedef struct gl_engine_opts {
+    int32_t max_ctx;          /* tokens of KV cache to provision; 0 = min(model ctx, 8192) */
+    int32_t act_bits;         /* GEMV activation fixed point: 16 (default, 2x int8 planes) or 8 (ggml-like) */
+    int32_t use_graph;        /* 1 (default): decode step replayed as a CUDA graph; 0: plain launches */
+    int32_t use_pdl;          /* 1 (default): programmatic dependent launch between step kernels */
+    int32_t prefill_mode;     /* 0 auto, 1 sequential decode steps, 2 batched tensor-core prefill */
+    int32_t reserved[11];
+} gl_engine_opts;
+
+typedef struct gl_model_info {
+    char     arch[32];
+    char     name[96];
+    char     quantization[24];   /* "Q4_K_M", "Q8_0", "BF16", ... from general.file_type */
+    int32_t  n_layer, n_embd, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx_train, n_ctx;
+    float    rope_base, rms_eps;
+    int32_t  bos_id, eos_id, eot_id, has_tokenizer;
+    uint64_t n_params;
+    uint64_t file_bytes;
+    uint64_t weight_bytes;       /* matrix payload resident in HBM */
+    uint64_t decode_bytes_per_token; /* algorithmic weight bytes one decode token must read */
+    int32_t  device;
+    int32_t  sm_count;
+} gl_model_info;
+
+typedef struct gl_sample_opts {
+    int32_t  num_predict;     /* OllamaService.ts:105  max_tokens = options.num_predict || 128 */
+    float    temperature;     /* 0 = greedy (the parity configuration) */
+    int32_t  top_k;           /* 0 = off */
+    float    top_p;           /* 1 = off */
+    uint64_t seed;
+    int32_t  ignore_eos;      /* 1: fixed-length generation (bench workloads) */
+    int32_t  n_stop_ids;
+    const int32_t* stop_ids;  /* extra stop token ids (host resolves stop strings) */
+    int32_t  want_logits;     /* 1: keep per-step logits for gl_last_logits (parity tests) */
+    int32_t  reserved[6];
+} gl_sample_opts;
+
+typedef struct gl_gen_stats {
+    int32_t prompt_eval_count;     /* InferenceResponse.prompt_eval_count (client/src/types/index.ts:61) */
+    int32_t eval_count;            /* InferenceResponse.eval_count */
+    int64_t prompt_eval_duration_ns; /* device time (cudaEvent) */
+    int64_t eval_duration_ns;      /* device time (cudaEvent) */
+    int64_t total_duration_ns;     /* host wall time of the call */
+    int64_t load_duration_ns;
+    int32_t done_reason;           /* 0 "stop" (eos / stop id), 1 "length", 2 cancelled */
+    int32_t kernel_launches;       /* kernels of this library launched by the call */
+} gl_gen_stats;
+
+/* Return non-zero to cancel (job_cancellation, JobScheduler.ts:530-536). piece may be NULL when the
+ * model carries no tokenizer. */
+typedef int (*gl_token_cb)(void* user, int32_t id, float logprob, const char* piece, int32_t piece_len);
+
+/* ---- library / device ---------------------------------------------------------------- */
+int         gl_abi_version(void);
+const char* gl_last_error(void);
+int         gl_device_count(int* n);                       /* checkHealth(): OllamaService.ts:65-83 */
+
+/* ---- engine lifetime (constructor / model load: OllamaService.ts:17-25, Ollama model load) */
+int  gl_engine_create(const char* gguf_path, int device, const gl_engine_opts* opts, gl_engine** out);
+void gl_engine_destroy(gl_engine* e);
+int  gl_engine_info(const gl_engine* e, gl_model_info* out); /* getAvailableModels(): OllamaService.ts:85-95 */
+
+/* ---- tokenizer (inside Ollama for the reference; needed by every generate*/
+int  gl_tokenize(const gl_engine* e, const char* utf8, int32_t n_bytes, int add_bos, int parse_special,
+                 int32_t* ids, int32_t cap, int32_t* n_out);
+int  gl_detokenize(const gl_engine* e, const int32_t* ids, int32_t n, char* buf, int32_t cap, int32_t* len_out);
+
+/* ---- the hot path ---------------------------------------------------------------------
+ * gl_generate: generateResponse / generateStreamResponse / generateChat*Response
+ *   (OllamaService.ts:97-184, 186-284, 353-449, 451-599): prefill the prompt, then decode up to
+ *   num_predict tokens; cb (may be NULL) is invoked once per generated token in order.
+ *   out_ids / out_logprobs (may be NULL) receive up to num_predict entries. */
+int  gl_generate(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_sample_opts* opts,
+                 gl_token_cb cb, void* user, int32_t* out_ids, float* out_logprobs, gl_gen_stats* stats);
+/* gl_embed: generateEmbedding (OllamaService.ts:601-665): prefill only, output_norm, mean-pool,
+ *   L2-normalise. seq_offsets has n_seq+1 entries into ids. out is [n_seq][n_embd]. */
+int  gl_embed(gl_engine* e, const int32_t* ids, const int32_t* seq_offsets, int32_t n_seq,
+              float* out, gl_gen_stats* stats);
+/* logits of generation step i of the last gl_generate that ran with want_logits=1 */
+int  gl_last_logits(gl_engine* e, int32_t step, float* out, int32_t n_vocab);
+
+/* ---- kernel-level entry points (parity tests and roofline measurement) ------------------ */
+/* y[rows] = W[rows x cols] (GGUF-layout blocks of ggml_type, host memory) * x[cols].
+ * iters>=1 timed launches after 2 warm-ups; kernel_ms = mean device time of one launch. */
+int  gl_gemv(gl_engine* e, int ggml_type, const void* w_host, int32_t rows, int32_t cols,
+             const float* x, float* y, int32_t iters, float* kernel_ms);
+/* device-resident GEMV bandwidth probe on matrix `tensor_name` of the loaded model (no H2D in the
+ * timed region); flush_l2!=0 writes a >L2 buffer between iterations. */
+int  gl_gemv_model_tensor(gl_engine* e, const char* tensor_name, const float* x, float* y,
+                          int32_t iters, int32_t flush_l2, float* kernel_ms, uint64_t* weight_bytes);
+/* y = rmsnorm(x) * w (the fused-prologue arithmetic, exposed stand-alone) */
+int  gl_rmsnorm(gl_engine* e, const float* x, const float* w, int32_t n, float eps, float* y);
+/* one decode step at the engine's current position: feeds `token`, returns logits (may be NULL),
+ * greedy id and its logprob.  gl_kv_reset() rewinds the sequence. */
+int  gl_decode_step(gl_engine* e, int32_t token, float* logits, int32_t* argmax, float* logprob);
+int  gl_kv_reset(gl_engine* e);
+int  gl_position(const gl_engine* e, int32_t* pos);
+/* batched prefill of n tokens from the current position; logits of the LAST token (may be NULL) */
+int  gl_prefill(gl_engine* e, const int32_t* ids, int32_t n, float* last_logits);
+/* mean device time (ms) of one decode step replayed `iters` times at context length ctx_len
+ * (KV content is whatever is resident; used for the roofline line) */
+int  gl_time_decode(gl_engine* e, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDLLM_NATIVE_H */

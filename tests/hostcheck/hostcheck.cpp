@@ -1,0 +1,76 @@
+// TEST INFRASTRUCTURE: runs the GEMV lane program (gridllm_b200/csrc/rowdot.h) on the CPU so the
+// layout / bit-twiddling logic can be checked against the oracle without a GPU.  Never linked
+// into libgridllm_native.so.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include "../../gridllm_b200/csrc/rowdot.h"
+#include "../../gridllm_b200/csrc/gguf_file.h"
+
+using namespace gl;
+
+template <int AB>
+static void build_xunits(const float* x, int cols, std::vector<XUnit>& xs) {
+    int nu = cols / UNIT_COLS;
+    xs.resize(nu);
+    for (int u = 0; u < nu; ++u) {
+        XUnit& xu = xs[u];
+        for (int b = 0; b < 4; ++b) {
+            const float* xb = x + u * 128 + b * 32;
+            float amax = 0.f;
+            for (int i = 0; i < 32; ++i) amax = std::fmax(amax, std::fabs(xb[i]));
+            int s0, s1;
+            snap16<AB>(xb, amax, &xu.hi[8 * b], &xu.lo[8 * b], &s0);
+            snap16<AB>(xb + 16, amax, &xu.hi[8 * b + 4], &xu.lo[8 * b + 4], &s1);
+            xu.sx[b] = amax / (AB == 16 ? ACT16_RANGE : ACT8_RANGE);
+            xu.sm[b] = xu.sx[b] * (float)(s0 + s1);
+            xu.s16[2 * b] = s0;
+            xu.s16[2 * b + 1] = s1;
+        }
+    }
+}
+
+template <int AB>
+static int run(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
+    std::vector<XUnit> xs;
+    build_xunits<AB>(x, cols, xs);
+    int nu = cols / UNIT_COLS;
+    size_t rb = row_bytes(type, cols), rs = align16(rb);
+    std::vector<uint8_t> row(rs + 16);
+    uint8_t* r = row.data() + ((16 - ((uintptr_t)row.data() & 15)) & 15);
+    for (int i = 0; i < rows; ++i) {
+        const uint8_t* src = w + (size_t)i * rb;
+        float acc = 0.f;
+        if (type == T_Q4_K) {
+            memcpy(r, src, rb);
+            for (int u = 0; u < nu; ++u) acc += unit_dot_q4k<AB>(r + (size_t)(u >> 1) * 144, u & 1, xs[u]);
+        } else if (type == T_Q6_K) {
+            repack_row_q6k(src, r, cols / 256);
+            for (int u = 0; u < nu; ++u) acc += unit_dot_q6k<AB>(r, cols / 256, u, xs[u]);
+        } else if (type == T_Q8_0) {
+            repack_row_q80(src, r, cols);
+            for (int u = 0; u < nu; ++u) acc += unit_dot_q80<AB>(r, cols, u, xs[u]);
+        } else return -1;
+        y[i] = acc;
+    }
+    return 0;
+}
+
+extern "C" int hc_gemv(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
+    if (cols % 128) return -2;
+    if (type == T_Q4_K || type == T_Q6_K) { if (cols % 256) return -2; }
+    return abits == 16 ? run<16>(type, w, rows, cols, x, y) : run<8>(type, w, rows, cols, x, y);
+}
+
+// GGUF reader check: returns number of tensors or -1; fills a few fields
+extern "C" int hc_gguf_probe(const char* path, char* arch, int cap, uint64_t* n_kv, uint64_t* total_bytes) {
+    GGUFFile f;
+    std::string err = f.open(path);
+    if (!err.empty()) { snprintf(arch, cap, "%s", err.c_str()); return -1; }
+    snprintf(arch, cap, "%s", f.get_s("general.architecture", "").c_str());
+    *n_kv = f.kv.size();
+    uint64_t tot = 0;
+    for (auto& t : f.tensors) tot += t.nbytes;
+    *total_bytes = tot;
+    return (int)f.tensors.size();
+}
