@@ -1,0 +1,154 @@
+// extern "C" surface of libgridllm_native.so -- see include/gridllm_native.h for the reference
+// call site each entry point stands in for.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "../../include/gridllm_native.h"
+#include "engine.h"
+
+using gl::Engine;
+using gl::Status;
+
+struct gl_engine {
+    Engine* impl;
+};
+
+namespace {
+int ret(const Status& s) {
+    if (!s.ok()) gl::set_last_error(s.msg);
+    return s.code;
+}
+int bad(const char* m) {
+    gl::set_last_error(m);
+    return GL_ERR_INVALID;
+}
+}  // namespace
+
+extern "C" {
+
+int gl_abi_version(void) { return GL_ABI_VERSION; }
+const char* gl_last_error(void) { return gl::get_last_error(); }
+
+int gl_device_count(int* n) {
+    if (!n) return bad("gl_device_count: null");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        gl::set_last_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        return GL_ERR_NO_DEVICE;
+    }
+    *n = c;
+    return GL_OK;
+}
+
+int gl_engine_create(const char* gguf_path, int device, const gl_engine_opts* opts, gl_engine** out) {
+    if (!gguf_path || !out) return bad("gl_engine_create: null argument");
+    *out = nullptr;
+    Engine* e = nullptr;
+    Status s = Engine::create(gguf_path, device, opts, &e);
+    if (!s.ok()) return ret(s);
+    *out = new gl_engine{e};
+    return GL_OK;
+}
+
+void gl_engine_destroy(gl_engine* e) {
+    if (!e) return;
+    delete e->impl;
+    delete e;
+}
+
+int gl_engine_info(const gl_engine* e, gl_model_info* out) {
+    if (!e || !out) return bad("gl_engine_info: null argument");
+    return ret(e->impl->info(out));
+}
+
+int gl_tokenize(const gl_engine* e, const char* utf8, int32_t n_bytes, int add_bos, int parse_special, int32_t* ids, int32_t cap,
+                int32_t* n_out) {
+    if (!e || !utf8 || !n_out) return bad("gl_tokenize: null argument");
+    const gl::Tokenizer& t = e->impl->tokenizer();
+    if (!t.ok()) { gl::set_last_error("model carries no supported tokenizer (tokenizer.ggml.model != gpt2)"); return GL_ERR_UNSUPPORTED; }
+    std::string text(utf8, n_bytes >= 0 ? (size_t)n_bytes : std::strlen(utf8));
+    std::vector<int32_t> v = t.encode(text, add_bos != 0, parse_special != 0);
+    *n_out = (int32_t)v.size();
+    if ((int32_t)v.size() > cap || (!ids && !v.empty())) { gl::set_last_error("gl_tokenize: output buffer too small"); return ids ? GL_ERR_INVALID : GL_OK; }
+    if (!v.empty()) std::memcpy(ids, v.data(), v.size() * sizeof(int32_t));
+    return GL_OK;
+}
+
+int gl_detokenize(const gl_engine* e, const int32_t* ids, int32_t n, char* buf, int32_t cap, int32_t* len_out) {
+    if (!e || (!ids && n > 0) || !len_out) return bad("gl_detokenize: null argument");
+    const gl::Tokenizer& t = e->impl->tokenizer();
+    if (!t.ok()) { gl::set_last_error("model carries no supported tokenizer"); return GL_ERR_UNSUPPORTED; }
+    std::string s = t.decode(ids, n);
+    *len_out = (int32_t)s.size();
+    if ((int32_t)s.size() > cap || !buf) { gl::set_last_error("gl_detokenize: output buffer too small"); return buf ? GL_ERR_INVALID : GL_OK; }
+    std::memcpy(buf, s.data(), s.size());
+    return GL_OK;
+}
+
+int gl_generate(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_sample_opts* opts, gl_token_cb cb, void* user,
+                int32_t* out_ids, float* out_logprobs, gl_gen_stats* stats) {
+    if (!e || !prompt) return bad("gl_generate: null argument");
+    gl_sample_opts so{};
+    if (opts) so = *opts;
+    else { so.num_predict = 128; so.top_p = 1.f; }
+    return ret(e->impl->generate(prompt, n_prompt, so, cb, user, out_ids, out_logprobs, stats));
+}
+
+int gl_embed(gl_engine* e, const int32_t* ids, const int32_t* seq_offsets, int32_t n_seq, float* out, gl_gen_stats* stats) {
+    if (!e || !ids || !seq_offsets || !out || n_seq <= 0) return bad("gl_embed: bad argument");
+    return ret(e->impl->embed(ids, seq_offsets, n_seq, out, stats));
+}
+
+int gl_last_logits(gl_engine* e, int32_t step, float* out, int32_t n_vocab) {
+    if (!e || !out) return bad("gl_last_logits: null argument");
+    return ret(e->impl->last_logits(step, out, n_vocab));
+}
+
+int gl_gemv(gl_engine* e, int ggml_type, const void* w_host, int32_t rows, int32_t cols, const float* x, float* y, int32_t iters,
+            float* kernel_ms) {
+    if (!e) return bad("gl_gemv: null engine");
+    return ret(e->impl->gemv_host(ggml_type, w_host, rows, cols, x, y, iters, kernel_ms));
+}
+
+int gl_gemv_model_tensor(gl_engine* e, const char* tensor_name, const float* x, float* y, int32_t iters, int32_t flush_l2,
+                         float* kernel_ms, uint64_t* weight_bytes) {
+    if (!e || !tensor_name || !x || !y) return bad("gl_gemv_model_tensor: null argument");
+    return ret(e->impl->gemv_tensor(tensor_name, x, y, iters, flush_l2, kernel_ms, weight_bytes));
+}
+
+int gl_rmsnorm(gl_engine* e, const float* x, const float* w, int32_t n, float eps, float* y) {
+    if (!e || !x || !w || !y || n <= 0) return bad("gl_rmsnorm: bad argument");
+    return ret(e->impl->rmsnorm(x, w, n, eps, y));
+}
+
+int gl_decode_step(gl_engine* e, int32_t token, float* logits, int32_t* argmax, float* logprob) {
+    if (!e) return bad("gl_decode_step: null engine");
+    return ret(e->impl->decode_step(token, logits, argmax, logprob));
+}
+
+int gl_kv_reset(gl_engine* e) {
+    if (!e) return bad("gl_kv_reset: null engine");
+    return ret(e->impl->kv_reset());
+}
+
+int gl_position(const gl_engine* e, int32_t* pos) {
+    if (!e || !pos) return bad("gl_position: null argument");
+    *pos = e->impl->position();
+    return GL_OK;
+}
+
+int gl_prefill(gl_engine* e, const int32_t* ids, int32_t n, float* last_logits) {
+    if (!e || !ids) return bad("gl_prefill: null argument");
+    return ret(e->impl->prefill(ids, n, last_logits));
+}
+
+int gl_time_decode(gl_engine* e, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step) {
+    if (!e) return bad("gl_time_decode: null engine");
+    return ret(e->impl->time_decode(ctx_len, iters, ms_per_step, launches_per_step));
+}
+
+}  // extern "C"

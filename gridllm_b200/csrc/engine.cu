@@ -1,0 +1,814 @@
+// Engine implementation: GGUF -> HBM upload (engine row layouts), paged KV pool, decode-step
+// construction (fused sm_100a kernels, PDL, CUDA graph) and the generate / embed drivers.
+// See engine.h / include/gridllm_native.h for the reference call sites this replaces.
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "common.cuh"
+#include "rowdot.h"
+
+namespace gl {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+namespace {
+
+Status fail(int code, const std::string& m) { return Status{code, m}; }
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(GL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+#define ST(expr)                          \
+    do {                                  \
+        Status _s = (expr);               \
+        if (!_s.ok()) return _s;          \
+    } while (0)
+
+int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+const char* ftype_name(uint64_t ft) {
+    switch (ft) {
+        case 0: return "F32";
+        case 1: return "F16";
+        case 7: return "Q8_0";
+        case 14: return "Q4_K_S";
+        case 15: return "Q4_K_M";
+        case 18: return "Q6_K";
+        case 32: return "BF16";
+        default: return "unknown";
+    }
+}
+
+}  // namespace
+
+Status Engine::create(const std::string& path, int device, const gl_engine_opts* opts, Engine** out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(GL_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) +
+                                          "): the native worker has no CPU fallback");
+    if (device < 0 || device >= n) return fail(GL_ERR_INVALID, "device index out of range");
+    Engine* eng = new Engine();
+    Status s = eng->load(path, device, opts);
+    if (!s.ok()) { delete eng; return s; }
+    *out = eng;
+    return {};
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    if (g_nohead_) cudaGraphExecDestroy(g_nohead_);
+    if (g_head_) cudaGraphExecDestroy(g_head_);
+    if (g_head_keep_) cudaGraphExecDestroy(g_head_keep_);
+    for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
+    for (void* p : allocs_) cudaFree(p);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+Status Engine::upload_f32(const GGUFTensor& t, float** out, int expect) {
+    if (t.type != T_F32 || t.cols() * t.rows() != expect) return fail(GL_ERR_FORMAT, "tensor '" + t.name + "': expected F32[" + std::to_string(expect) + "]");
+    CU(cudaMalloc((void**)out, (size_t)expect * 4));
+    allocs_.push_back(*out);
+    CU(cudaMemcpy(*out, t.data, (size_t)expect * 4, cudaMemcpyHostToDevice));
+    return {};
+}
+
+Status Engine::upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layout) {
+    BlockGeom g = block_geom(t.type);
+    if (!g.weights) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': ggml type " + std::to_string(t.type) + " is outside the hot path (F32/F16/BF16/Q8_0/Q4_K/Q6_K)");
+    m.type = (int)t.type;
+    m.rows = (int)t.rows();
+    m.cols = (int)t.cols();
+    m.gguf_bytes = t.nbytes;
+    const size_t rb = row_bytes(t.type, t.cols());
+    const bool repack = !native_layout && (t.type == T_Q6_K || t.type == T_Q8_0);
+    if (!native_layout && m.quantized() && (m.cols % UNIT_COLS)) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': cols must be a multiple of 128 for the quantised GEMV");
+    m.row_stride = (int)(native_layout ? rb : align16(rb));
+    const size_t total = (size_t)m.row_stride * m.rows;
+    CU(cudaMalloc((void**)&m.w, total + 256));
+    allocs_.push_back(m.w);
+    if (!repack && (size_t)m.row_stride == rb) {
+        CU(cudaMemcpy(m.w, t.data, total, cudaMemcpyHostToDevice));
+    } else {
+        // repack rows on the host (parallel over rows), in slabs through one staging buffer
+        const size_t slab_rows = std::max<size_t>(1, (size_t)(64u << 20) / m.row_stride);
+        std::vector<uint8_t> stage(slab_rows * m.row_stride);
+        for (size_t r0 = 0; r0 < (size_t)m.rows; r0 += slab_rows) {
+            const size_t nr = std::min(slab_rows, (size_t)m.rows - r0);
+            const int nthreads = (int)std::min<size_t>(8, std::max<size_t>(1, nr / 64));
+            std::vector<std::thread> th;
+            for (int ti = 0; ti < nthreads; ++ti) {
+                th.emplace_back([&, ti]() {
+                    for (size_t r = ti; r < nr; r += nthreads) {
+                        const uint8_t* src = t.data + (r0 + r) * rb;
+                        uint8_t* dst = stage.data() + r * m.row_stride;
+                        if (t.type == T_Q6_K && repack) { repack_row_q6k(src, dst, m.cols / 256); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
+                        else if (t.type == T_Q8_0 && repack) { repack_row_q80(src, dst, m.cols); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
+                        else { memcpy(dst, src, rb); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
+                    }
+                });
+            }
+            for (auto& x : th) x.join();
+            CU(cudaMemcpy(m.w + r0 * m.row_stride, stage.data(), nr * m.row_stride, cudaMemcpyHostToDevice));
+        }
+    }
+    return {};
+}
+
+Status Engine::load(const std::string& path, int device, const gl_engine_opts* opts) {
+    const int64_t t0 = now_ns();
+    device_ = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(GL_ERR_UNSUPPORTED, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a (B200) only");
+    sm_count_ = prop.multiProcessorCount;
+
+    abits_ = (opts && opts->act_bits == 8) ? 8 : 16;
+    use_graph_ = !(opts && opts->use_graph == 0) && env_int("GL_GRAPH", 1) != 0;
+    use_pdl_ = !(opts && opts->use_pdl == 0) && env_int("GL_PDL", 1) != 0;
+    fused_ = env_int("GL_FUSE", 1) != 0;
+    abits_ = env_int("GL_ACT_BITS", abits_) == 8 ? 8 : 16;
+    stage_kb_ = env_int("GL_STAGE_KB", 24);
+    smem_kb_ = env_int("GL_SMEM_KB", 110);
+    attn_splits_ = std::max(1, std::min(64, env_int("GL_ATTN_SPLITS", 16)));
+
+    std::string err = gguf_.open(path);
+    if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);
+    const std::string arch = gguf_.get_s("general.architecture", "");
+    if (arch != "llama") return fail(GL_ERR_UNSUPPORTED, "architecture '" + arch + "' is outside the hot path (llama-family GGUF only)");
+    auto key = [&](const char* k) { return arch + "." + k; };
+    n_layer_ = (int)gguf_.get_u(key("block_count"), 0);
+    n_embd_ = (int)gguf_.get_u(key("embedding_length"), 0);
+    n_head_ = (int)gguf_.get_u(key("attention.head_count"), 0);
+    n_kv_ = (int)gguf_.get_u(key("attention.head_count_kv"), n_head_);
+    n_ff_ = (int)gguf_.get_u(key("feed_forward_length"), 0);
+    eps_ = (float)gguf_.get_f(key("attention.layer_norm_rms_epsilon"), 1e-5);
+    rope_base_ = (float)gguf_.get_f(key("rope.freq_base"), 10000.0);
+    const int n_ctx_train = (int)gguf_.get_u(key("context_length"), 2048);
+    if (!n_layer_ || !n_embd_ || !n_head_ || !n_ff_) return fail(GL_ERR_FORMAT, "missing llama hyper-parameters in GGUF metadata");
+    hd_ = (int)gguf_.get_u(key("rope.dimension_count"), n_embd_ / n_head_);
+    if (hd_ * n_head_ != n_embd_ || (hd_ != 64 && hd_ != 128)) return fail(GL_ERR_UNSUPPORTED, "head_dim must be 64 or 128 and n_head*head_dim == n_embd");
+    if (n_head_ % n_kv_ || n_head_ / n_kv_ > 8) return fail(GL_ERR_UNSUPPORTED, "GQA group must divide n_head and be <= 8");
+    n_ctx_ = (opts && opts->max_ctx > 0) ? opts->max_ctx : std::min(n_ctx_train, 8192);
+    n_ctx_ = (n_ctx_ + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS * KV_PAGE_TOKENS;
+
+    const GGUFTensor* te = gguf_.tensor("token_embd.weight");
+    if (!te) return fail(GL_ERR_FORMAT, "missing token_embd.weight");
+    n_vocab_ = (int)te->rows();
+    if (te->cols() != n_embd_) return fail(GL_ERR_FORMAT, "token_embd.weight has wrong width");
+
+    CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& ev : ev_) CU(cudaEventCreate(&ev));
+    CU(gemv_configure());
+
+    // ---- weights -> HBM -------------------------------------------------------------------------
+    ST(upload_matrix(*te, tok_embd_, /*native=*/true));
+    const GGUFTensor* tout = gguf_.tensor("output.weight");
+    ST(upload_matrix(tout ? *tout : *te, output_, false));
+    const GGUFTensor* ton = gguf_.tensor("output_norm.weight");
+    if (!ton) return fail(GL_ERR_FORMAT, "missing output_norm.weight");
+    ST(upload_f32(*ton, &output_norm_, n_embd_));
+    layers_.resize(n_layer_);
+    uint64_t layer_bytes = 0;
+    n_params_ = (uint64_t)te->rows() * te->cols() + (tout ? (uint64_t)tout->rows() * tout->cols() : 0);
+    for (int il = 0; il < n_layer_; ++il) {
+        LayerWeights& L = layers_[il];
+        const std::string p = "blk." + std::to_string(il) + ".";
+        struct Item { const char* n; DevMatrix* m; int rows, cols; };
+        Item items[] = {{"attn_q.weight", &L.wq, n_head_ * hd_, n_embd_},  {"attn_k.weight", &L.wk, n_kv_ * hd_, n_embd_},
+                        {"attn_v.weight", &L.wv, n_kv_ * hd_, n_embd_},    {"attn_output.weight", &L.wo, n_embd_, n_head_ * hd_},
+                        {"ffn_gate.weight", &L.wgate, n_ff_, n_embd_},     {"ffn_up.weight", &L.wup, n_ff_, n_embd_},
+                        {"ffn_down.weight", &L.wdown, n_embd_, n_ff_}};
+        for (auto& it : items) {
+            const GGUFTensor* t = gguf_.tensor(p + it.n);
+            if (!t) return fail(GL_ERR_FORMAT, "missing tensor " + p + it.n);
+            if (t->rows() != it.rows || t->cols() != it.cols) return fail(GL_ERR_FORMAT, "tensor " + p + it.n + " has unexpected shape");
+            ST(upload_matrix(*t, *it.m, false));
+            layer_bytes += t->nbytes;
+            n_params_ += (uint64_t)t->rows() * t->cols();
+            if (!it.m->quantized()) all_quant_ = false;
+        }
+        const GGUFTensor* an = gguf_.tensor(p + "attn_norm.weight");
+        const GGUFTensor* fn = gguf_.tensor(p + "ffn_norm.weight");
+        if (!an || !fn) return fail(GL_ERR_FORMAT, "missing norm weights in layer " + std::to_string(il));
+        ST(upload_f32(*an, &L.attn_norm, n_embd_));
+        ST(upload_f32(*fn, &L.ffn_norm, n_embd_));
+    }
+    if (!output_.quantized()) all_quant_ = false;
+    if (!all_quant_) fused_ = false;
+    weight_bytes_ = layer_bytes + output_.gguf_bytes + tok_embd_.gguf_bytes;
+    decode_bytes_ = layer_bytes + output_.gguf_bytes + (uint64_t)(2 * n_layer_ + 1) * n_embd_ * 4 + row_bytes(tok_embd_.type, n_embd_);
+
+    // ---- activations, KV pool, state ------------------------------------------------------------
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) { allocs_.push_back(*p); e = cudaMemset(*p, 0, bytes); }
+        return e;
+    };
+    const int qdim = n_head_ * hd_, kvdim = n_kv_ * hd_;
+    CU(dalloc((void**)&x_, (size_t)n_embd_ * 4));
+    CU(dalloc((void**)&xn_, (size_t)std::max(n_embd_, n_ff_) * 4));
+    CU(dalloc((void**)&q_, (size_t)qdim * 4));
+    CU(dalloc((void**)&ktmp_, (size_t)kvdim * 4));
+    CU(dalloc((void**)&vtmp_, (size_t)kvdim * 4));
+    CU(dalloc((void**)&attn_, (size_t)qdim * 4));
+    CU(dalloc((void**)&h_, (size_t)n_ff_ * 4));
+    CU(dalloc((void**)&gate_, (size_t)n_ff_ * 4));
+    CU(dalloc((void**)&up_, (size_t)n_ff_ * 4));
+    CU(dalloc((void**)&ytmp_, (size_t)std::max(n_embd_, n_ff_) * 4));
+    CU(dalloc((void**)&logits_, (size_t)n_vocab_ * 4));
+    CU(dalloc((void**)&part_o_, (size_t)n_head_ * attn_splits_ * hd_ * 4));
+    CU(dalloc((void**)&part_ml_, (size_t)n_head_ * attn_splits_ * 2 * 4));
+    CU(dalloc((void**)&counters_, (size_t)n_kv_ * 4));
+    n_pages_ = n_ctx_ / KV_PAGE_TOKENS;
+    kv_layer_elems_ = (size_t)n_pages_ * n_kv_ * KV_PAGE_TOKENS * hd_;
+    CU(dalloc((void**)&kcache_, kv_layer_elems_ * n_layer_ * sizeof(__half)));
+    CU(dalloc((void**)&vcache_, kv_layer_elems_ * n_layer_ * sizeof(__half)));
+    CU(dalloc((void**)&page_table_, (size_t)n_pages_ * 4));
+    CU(dalloc((void**)&st_, sizeof(StepState)));
+    CU(dalloc((void**)&prompt_ids_, (size_t)n_ctx_ * 4));
+    max_out_ = n_ctx_;
+    CU(dalloc((void**)&out_ids_, (size_t)max_out_ * 4));
+    CU(dalloc((void**)&out_lp_, (size_t)max_out_ * 4));
+    // physical pages are handed out in reverse order so that the page table is a real indirection
+    free_pages_.resize(n_pages_);
+    for (int i = 0; i < n_pages_; ++i) free_pages_[i] = i;
+
+    // RoPE tables (oracle/llama_oracle.py rope_table): inv_freq rounded to fp32, angle formed in fp32,
+    // cos/sin evaluated in double, rounded to fp32.
+    {
+        std::vector<float> c((size_t)n_ctx_ * hd_ / 2), s((size_t)n_ctx_ * hd_ / 2);
+        std::vector<float> inv(hd_ / 2);
+        for (int i = 0; i < hd_ / 2; ++i) inv[i] = (float)std::pow((double)rope_base_, -2.0 * i / hd_);
+        for (int pos = 0; pos < n_ctx_; ++pos)
+            for (int i = 0; i < hd_ / 2; ++i) {
+                const float ang = (float)pos * inv[i];
+                c[(size_t)pos * hd_ / 2 + i] = (float)std::cos((double)ang);
+                s[(size_t)pos * hd_ / 2 + i] = (float)std::sin((double)ang);
+            }
+        CU(dalloc((void**)&rope_cos_, c.size() * 4));
+        CU(dalloc((void**)&rope_sin_, s.size() * 4));
+        CU(cudaMemcpy(rope_cos_, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(rope_sin_, s.data(), s.size() * 4, cudaMemcpyHostToDevice));
+    }
+    tok_.load(gguf_);
+
+    // ---- info -----------------------------------------------------------------------------------
+    std::memset(&info_, 0, sizeof(info_));
+    std::snprintf(info_.arch, sizeof(info_.arch), "%s", arch.c_str());
+    std::snprintf(info_.name, sizeof(info_.name), "%s", gguf_.get_s("general.name", "unnamed").c_str());
+    std::snprintf(info_.quantization, sizeof(info_.quantization), "%s", ftype_name(gguf_.get_u("general.file_type", 9999)));
+    info_.n_layer = n_layer_; info_.n_embd = n_embd_; info_.n_head = n_head_; info_.n_head_kv = n_kv_; info_.head_dim = hd_;
+    info_.n_ff = n_ff_; info_.n_vocab = n_vocab_; info_.n_ctx_train = n_ctx_train; info_.n_ctx = n_ctx_;
+    info_.rope_base = rope_base_; info_.rms_eps = eps_;
+    info_.bos_id = tok_.bos; info_.eos_id = tok_.eos; info_.eot_id = tok_.eot; info_.has_tokenizer = tok_.ok() ? 1 : 0;
+    info_.n_params = n_params_; info_.file_bytes = gguf_.file_bytes; info_.weight_bytes = weight_bytes_;
+    info_.decode_bytes_per_token = decode_bytes_; info_.device = device_; info_.sm_count = sm_count_;
+
+    ST(kv_reset());
+    if (use_graph_) ST(build_graphs());
+    CU(cudaStreamSynchronize(stream_));
+    load_ns_ = now_ns() - t0;
+    return {};
+}
+
+Status Engine::info(gl_model_info* out) const {
+    *out = info_;
+    return {};
+}
+
+const DevMatrix* Engine::find_matrix(const std::string& name) const {
+    if (name == "output.weight") return &output_;
+    if (name.rfind("blk.", 0) == 0) {
+        const size_t dot = name.find('.', 4);
+        if (dot == std::string::npos) return nullptr;
+        const int il = std::atoi(name.substr(4, dot - 4).c_str());
+        if (il < 0 || il >= n_layer_) return nullptr;
+        const std::string rest = name.substr(dot + 1);
+        const LayerWeights& L = layers_[il];
+        if (rest == "attn_q.weight") return &L.wq;
+        if (rest == "attn_k.weight") return &L.wk;
+        if (rest == "attn_v.weight") return &L.wv;
+        if (rest == "attn_output.weight") return &L.wo;
+        if (rest == "ffn_gate.weight") return &L.wgate;
+        if (rest == "ffn_up.weight") return &L.wup;
+        if (rest == "ffn_down.weight") return &L.wdown;
+    }
+    return nullptr;
+}
+
+// -------------------------------------------------------------------------------------------------
+// KV pages
+// -------------------------------------------------------------------------------------------------
+Status Engine::kv_reset() {
+    for (int p : seq_pages_) free_pages_.push_back(p);
+    seq_pages_.clear();
+    host_pos_ = 0;
+    return set_state(0, 0, 0, 0, nullptr);
+}
+
+Status Engine::ensure_pages(int n_tokens) {
+    if (n_tokens > n_ctx_) return fail(GL_ERR_CONTEXT, "sequence of " + std::to_string(n_tokens) + " tokens exceeds the engine context " + std::to_string(n_ctx_));
+    const int need = (n_tokens + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+    bool grew = false;
+    while ((int)seq_pages_.size() < need) {
+        if (free_pages_.empty()) return fail(GL_ERR_NOMEM, "KV page pool exhausted");
+        seq_pages_.push_back(free_pages_.back());
+        free_pages_.pop_back();
+        grew = true;
+    }
+    if (grew) CU(cudaMemcpyAsync(page_table_, seq_pages_.data(), seq_pages_.size() * 4, cudaMemcpyHostToDevice, stream_));
+    return {};
+}
+
+Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so) {
+    StepState h{};
+    h.pos = pos; h.token = token; h.n_prompt = n_prompt; h.out_idx = out_idx; h.done = 0;
+    h.ignore_eos = so ? so->ignore_eos : 1;
+    h.n_stop = 0;
+    if (so && !so->ignore_eos) {
+        if (tok_.eos >= 0) h.stop_ids[h.n_stop++] = tok_.eos;
+        if (tok_.eot >= 0 && tok_.eot != tok_.eos) h.stop_ids[h.n_stop++] = tok_.eot;
+        for (int i = 0; i < so->n_stop_ids && h.n_stop < 9; ++i) h.stop_ids[h.n_stop++] = so->stop_ids[i];
+    }
+    CU(cudaMemcpyAsync(st_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
+    CU(cudaStreamSynchronize(stream_));     // h is on the stack
+    return {};
+}
+
+// -------------------------------------------------------------------------------------------------
+// decode step
+// -------------------------------------------------------------------------------------------------
+Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch) {
+    p.n_stages = 3;
+    p.stage_bytes = stage_kb_ * 1024;
+    if (!gemv_plan(p)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(p.cols) + ")");
+    // shrink the stage to what the plan needs, then spend the shared-memory budget on depth
+    int need = 0;
+    for (int i = 0; i < p.nseg; ++i) need = std::max(need, p.seg[i].rows_per_stage * p.seg[i].row_stride * (p.pair ? 2 : 1));
+    p.stage_bytes = (need + 127) & ~127;
+    const size_t fixed = gemv_smem_bytes(p.cols, 0, 0);
+    int ns = (int)(((size_t)smem_kb_ * 1024 - fixed) / p.stage_bytes);
+    p.n_stages = std::max(2, std::min(GEMV_MAX_STAGES, ns));
+    if (gemv_smem_bytes(p.cols, p.n_stages, p.stage_bytes) > 227 * 1024) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
+    CU(gemv_launch(p, abits_, sm_count_, use_pdl_, s));
+    ++*n_launch;
+    return {};
+}
+
+Status Engine::plain_gemv(cudaStream_t s, const DevMatrix& m, const float* x, float* y, int* n_launch) {
+    if (m.quantized()) {
+        GemvParams p{};
+        p.seg[0] = GemvSeg{m.w, m.type, m.rows, m.row_stride, 0};
+        p.nseg = 1; p.cols = m.cols; p.x = x; p.epi = EPI_STORE; p.out = y; p.st = st_;
+        return enqueue_gemv(s, p, n_launch);
+    }
+    CU(gemv_fp_launch(m.w, m.type, m.rows, m.cols, x, y, s));
+    ++*n_launch;
+    return {};
+}
+
+Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, int* n_launch) {
+    const bool pdl = use_pdl_;
+    {
+        EmbedParams ep{tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, st_, prompt_ids_, x_};
+        CU(embed_launch(ep, pdl, s));
+        ++*n_launch;
+    }
+    const float scale = 1.0f / std::sqrt((float)hd_);
+    for (int il = 0; il < n_layer_; ++il) {
+        const LayerWeights& L = layers_[il];
+        __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
+        __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
+        if (fused_) {
+            GemvParams p{};
+            p.seg[0] = GemvSeg{L.wq.w, L.wq.type, L.wq.rows, L.wq.row_stride, 0};
+            p.seg[1] = GemvSeg{L.wk.w, L.wk.type, L.wk.rows, L.wk.row_stride, 0};
+            p.seg[2] = GemvSeg{L.wv.w, L.wv.type, L.wv.rows, L.wv.row_stride, 0};
+            p.nseg = 3; p.cols = n_embd_; p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
+            p.rope_cos = rope_cos_; p.rope_sin = rope_sin_; p.head_dim = hd_; p.n_kv_heads = n_kv_;
+            p.k_cache = kc; p.v_cache = vc; p.page_table = page_table_; p.st = st_;
+            ST(enqueue_gemv(s, p, n_launch));
+        } else {
+            CU(rmsnorm_launch(x_, L.attn_norm, n_embd_, eps_, xn_, s)); ++*n_launch;
+            ST(plain_gemv(s, L.wq, xn_, q_, n_launch));
+            ST(plain_gemv(s, L.wk, xn_, ktmp_, n_launch));
+            ST(plain_gemv(s, L.wv, xn_, vtmp_, n_launch));
+            CU(rope_kv_launch(q_, ktmp_, vtmp_, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, st_, kc, vc, page_table_, s)); ++*n_launch;
+        }
+        {
+            AttnParams a{};
+            a.q = q_; a.k_cache = kc; a.v_cache = vc; a.page_table = page_table_; a.st = st_; a.out = attn_;
+            a.part_o = part_o_; a.part_ml = part_ml_; a.counters = counters_;
+            a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = attn_splits_; a.scale = scale;
+            CU(attn_decode_launch(a, pdl && fused_, s));
+            ++*n_launch;
+        }
+        if (fused_) {
+            GemvParams p{};
+            p.seg[0] = GemvSeg{L.wo.w, L.wo.type, L.wo.rows, L.wo.row_stride, 0};
+            p.nseg = 1; p.cols = n_head_ * hd_; p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
+            ST(enqueue_gemv(s, p, n_launch));
+            GemvParams g{};
+            g.seg[0] = GemvSeg{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.row_stride, 0};
+            g.seg[1] = GemvSeg{L.wup.w, L.wup.type, L.wup.rows, L.wup.row_stride, 0};
+            g.nseg = 2; g.pair = 1; g.cols = n_embd_; g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
+            if (L.wgate.type != L.wup.type) return fail(GL_ERR_UNSUPPORTED, "ffn_gate / ffn_up with different types");
+            ST(enqueue_gemv(s, g, n_launch));
+            GemvParams d{};
+            d.seg[0] = GemvSeg{L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.row_stride, 0};
+            d.nseg = 1; d.cols = n_ff_; d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
+            ST(enqueue_gemv(s, d, n_launch));
+        } else {
+            ST(plain_gemv(s, L.wo, attn_, ytmp_, n_launch));
+            CU(add_launch(x_, ytmp_, n_embd_, x_, s)); ++*n_launch;
+            CU(rmsnorm_launch(x_, L.ffn_norm, n_embd_, eps_, xn_, s)); ++*n_launch;
+            ST(plain_gemv(s, L.wgate, xn_, gate_, n_launch));
+            ST(plain_gemv(s, L.wup, xn_, up_, n_launch));
+            CU(silu_mul_launch(gate_, up_, n_ff_, h_, s)); ++*n_launch;
+            ST(plain_gemv(s, L.wdown, h_, ytmp_, n_launch));
+            CU(add_launch(x_, ytmp_, n_embd_, x_, s)); ++*n_launch;
+        }
+    }
+    if (with_head) {
+        if (fused_) {
+            GemvParams p{};
+            p.seg[0] = GemvSeg{output_.w, output_.type, output_.rows, output_.row_stride, 0};
+            p.nseg = 1; p.cols = n_embd_; p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
+            ST(enqueue_gemv(s, p, n_launch));
+        } else {
+            CU(rmsnorm_launch(x_, output_norm_, n_embd_, eps_, xn_, s)); ++*n_launch;
+            ST(plain_gemv(s, output_, xn_, logits_, n_launch));
+        }
+        SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_};
+        CU(sample_greedy_launch(sp, pdl && fused_, s));
+        ++*n_launch;
+    } else {
+        CU(advance_launch(st_, pdl && fused_, s));
+        ++*n_launch;
+    }
+    return {};
+}
+
+Status Engine::build_graphs() {
+    for (int which = 0; which < 2; ++which) {
+        cudaGraph_t g = nullptr;
+        int n = 0;
+        CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        Status s = enqueue_step(stream_, which == 1, false, &n);
+        cudaError_t e = cudaStreamEndCapture(stream_, &g);
+        if (!s.ok()) { if (g) cudaGraphDestroy(g); return s; }
+        if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+        if (which == 0) { g_nohead_ = ge; launches_nohead_ = n; } else { g_head_ = ge; launches_head_ = n; }
+    }
+    return {};
+}
+
+Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
+    int dummy = 0;
+    if (keep_logits && use_graph_ && !g_head_keep_) {
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        Status s = enqueue_step(stream_, true, true, &dummy);
+        cudaError_t e = cudaStreamEndCapture(stream_, &g);
+        if (!s.ok()) { if (g) cudaGraphDestroy(g); return s; }
+        if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&g_head_keep_, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    }
+    for (int i = 0; i < n_nohead; ++i) {
+        if (use_graph_) CU(cudaGraphLaunch(g_nohead_, stream_));
+        else ST(enqueue_step(stream_, false, false, &dummy));
+    }
+    for (int i = 0; i < n_head; ++i) {
+        if (use_graph_) CU(cudaGraphLaunch(keep_logits ? g_head_keep_ : g_head_, stream_));
+        else ST(enqueue_step(stream_, true, keep_logits, &dummy));
+    }
+    return {};
+}
+
+// -------------------------------------------------------------------------------------------------
+// drivers
+// -------------------------------------------------------------------------------------------------
+Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, gl_token_cb cb, void* user,
+                        int32_t* out_ids, float* out_lp, gl_gen_stats* stats) {
+    CU(cudaSetDevice(device_));
+    const int64_t t0 = now_ns();
+    if (n_prompt <= 0 || !prompt) return fail(GL_ERR_INVALID, "empty prompt");
+    const int n_pred = so.num_predict > 0 ? so.num_predict : 128;     // OllamaService.ts:105
+    if (so.temperature > 0.f) return fail(GL_ERR_UNSUPPORTED, "only greedy decoding (temperature 0) is on the hot path");
+    for (int i = 0; i < n_prompt; ++i)
+        if (prompt[i] < 0 || prompt[i] >= n_vocab_) return fail(GL_ERR_INVALID, "prompt token id out of range");
+    ST(kv_reset());
+    ST(ensure_pages(n_prompt + n_pred));
+    if (so.want_logits) {
+        if (keep_cap_ < n_pred) {
+            float* p = nullptr;
+            CU(cudaMalloc((void**)&p, (size_t)n_pred * n_vocab_ * 4));
+            allocs_.push_back(p);
+            logits_keep_ = p;
+            keep_cap_ = n_pred;
+            if (g_head_keep_) { cudaGraphExecDestroy(g_head_keep_); g_head_keep_ = nullptr; }
+        }
+    }
+    CU(cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_));
+    ST(set_state(0, prompt[0], n_prompt, 0, &so));
+
+    // prefill: n_prompt-1 positions without a head, then the last prompt token produces token 0
+    CU(cudaEventRecord(ev_[0], stream_));
+    ST(run_steps(n_prompt - 1, 0, false));
+    CU(cudaEventRecord(ev_[1], stream_));
+
+    std::vector<int32_t> ids(n_pred);
+    std::vector<float> lps(n_pred);
+    int produced = 0, done_reason = 1;
+    bool cancelled = false;
+    const int chunk = cb ? 8 : 32;
+    StepState hs{};
+    while (produced < n_pred && !cancelled) {
+        const int n = std::min(chunk, n_pred - produced);
+        ST(run_steps(0, n, so.want_logits != 0));
+        CU(cudaMemcpyAsync(ids.data() + produced, out_ids_ + produced, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+        CU(cudaMemcpyAsync(lps.data() + produced, out_lp_ + produced, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+        CU(cudaMemcpyAsync(&hs, st_, sizeof(hs), cudaMemcpyDeviceToHost, stream_));
+        CU(cudaStreamSynchronize(stream_));
+        const int upto = std::min(hs.out_idx, produced + n);
+        for (int i = produced; i < upto && !cancelled; ++i) {
+            const bool is_stop = hs.done && i == hs.out_idx - 1;
+            if (is_stop) break;                  // the stop token itself is not part of the response
+            if (cb) {
+                const std::string pc = tok_.ok() ? tok_.piece(ids[i]) : std::string();
+                if (cb(user, ids[i], lps[i], tok_.ok() ? pc.c_str() : nullptr, (int32_t)pc.size()) != 0) cancelled = true;
+            }
+            if (out_ids) out_ids[i] = ids[i];
+            if (out_lp) out_lp[i] = lps[i];
+            ++produced;
+        }
+        if (hs.done) { done_reason = 0; break; }
+    }
+    CU(cudaEventRecord(ev_[2], stream_));
+    CU(cudaEventSynchronize(ev_[2]));
+    if (cancelled) done_reason = 2;
+    host_pos_ = n_prompt + produced;
+    if (stats) {
+        float ms_p = 0.f, ms_d = 0.f;
+        cudaEventElapsedTime(&ms_p, ev_[0], ev_[1]);
+        cudaEventElapsedTime(&ms_d, ev_[1], ev_[2]);
+        stats->prompt_eval_count = n_prompt;
+        stats->eval_count = produced;
+        stats->prompt_eval_duration_ns = (int64_t)(ms_p * 1e6);
+        stats->eval_duration_ns = (int64_t)(ms_d * 1e6);
+        stats->total_duration_ns = now_ns() - t0;
+        stats->load_duration_ns = load_ns_;
+        stats->done_reason = done_reason;
+        stats->kernel_launches = (n_prompt - 1) * launches_nohead_ + std::max(produced, 1) * launches_head_;
+    }
+    return cancelled ? fail(GL_ERR_CANCELLED, "cancelled by token callback") : Status{};
+}
+
+Status Engine::last_logits(int step, float* out, int n_vocab) {
+    if (!logits_keep_ || step < 0 || step >= keep_cap_ || n_vocab != n_vocab_) return fail(GL_ERR_INVALID, "no kept logits for that step");
+    CU(cudaMemcpy(out, logits_keep_ + (size_t)step * n_vocab_, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost));
+    return {};
+}
+
+Status Engine::decode_step(int token, float* logits, int* argmax, float* logprob) {
+    CU(cudaSetDevice(device_));
+    if (token < 0 || token >= n_vocab_) return fail(GL_ERR_INVALID, "token id out of range");
+    ST(ensure_pages(host_pos_ + 1));
+    gl_sample_opts so{};
+    so.ignore_eos = 1;
+    ST(set_state(host_pos_, token, 0, 0, &so));
+    ST(run_steps(0, 1, false));
+    int id = 0;
+    float lp = 0.f;
+    CU(cudaMemcpyAsync(&id, out_ids_, 4, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaMemcpyAsync(&lp, out_lp_, 4, cudaMemcpyDeviceToHost, stream_));
+    if (logits) CU(cudaMemcpyAsync(logits, logits_, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaStreamSynchronize(stream_));
+    if (argmax) *argmax = id;
+    if (logprob) *logprob = lp;
+    ++host_pos_;
+    return {};
+}
+
+Status Engine::prefill(const int32_t* ids, int n, float* last_logits) {
+    CU(cudaSetDevice(device_));
+    if (n <= 0) return fail(GL_ERR_INVALID, "empty prefill");
+    for (int i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= n_vocab_) return fail(GL_ERR_INVALID, "token id out of range");
+    ST(ensure_pages(host_pos_ + n));
+    // sequential prefill: tokens are fed from prompt_ids_ indexed by absolute position
+    CU(cudaMemcpyAsync(prompt_ids_ + host_pos_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+    gl_sample_opts so{};
+    so.ignore_eos = 1;
+    ST(set_state(host_pos_, ids[0], host_pos_ + n, 0, &so));
+    ST(run_steps(n - 1, 1, false));
+    if (last_logits) CU(cudaMemcpyAsync(last_logits, logits_, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaStreamSynchronize(stream_));
+    host_pos_ += n;
+    return {};
+}
+
+Status Engine::embed(const int32_t* ids, const int32_t* offs, int n_seq, float* out, gl_gen_stats* stats) {
+    CU(cudaSetDevice(device_));
+    const int64_t t0 = now_ns();
+    int total = 0;
+    std::vector<float> hid(n_embd_), nw(n_embd_);
+    CU(cudaMemcpy(nw.data(), output_norm_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost));
+    CU(cudaEventRecord(ev_[0], stream_));
+    for (int sidx = 0; sidx < n_seq; ++sidx) {
+        const int n = offs[sidx + 1] - offs[sidx];
+        if (n <= 0) return fail(GL_ERR_INVALID, "empty sequence in gl_embed");
+        const int32_t* sid = ids + offs[sidx];
+        for (int i = 0; i < n; ++i)
+            if (sid[i] < 0 || sid[i] >= n_vocab_) return fail(GL_ERR_INVALID, "token id out of range");
+        ST(kv_reset());
+        ST(ensure_pages(n));
+        CU(cudaMemcpyAsync(prompt_ids_, sid, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+        gl_sample_opts so{};
+        so.ignore_eos = 1;
+        ST(set_state(0, sid[0], n, 0, &so));
+        // mean pooling of output_norm(hidden) over positions, accumulated on the host in double
+        std::vector<double> acc(n_embd_, 0.0);
+        for (int i = 0; i < n; ++i) {
+            ST(run_steps(1, 0, false));
+            CU(cudaMemcpyAsync(hid.data(), x_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost, stream_));
+            CU(cudaStreamSynchronize(stream_));
+            double ss = 0;
+            for (int d = 0; d < n_embd_; ++d) ss += (double)hid[d] * hid[d];
+            const double rstd = 1.0 / std::sqrt(ss / n_embd_ + (double)eps_);
+            for (int d = 0; d < n_embd_; ++d) acc[d] += hid[d] * rstd * nw[d];
+        }
+        double nrm = 0;
+        for (int d = 0; d < n_embd_; ++d) { acc[d] /= n; nrm += acc[d] * acc[d]; }
+        nrm = std::max(std::sqrt(nrm), 1e-12);
+        for (int d = 0; d < n_embd_; ++d) out[(size_t)sidx * n_embd_ + d] = (float)(acc[d] / nrm);
+        total += n;
+    }
+    CU(cudaEventRecord(ev_[1], stream_));
+    CU(cudaEventSynchronize(ev_[1]));
+    if (stats) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+        std::memset(stats, 0, sizeof(*stats));
+        stats->prompt_eval_count = total;
+        stats->prompt_eval_duration_ns = (int64_t)(ms * 1e6);
+        stats->total_duration_ns = now_ns() - t0;
+        stats->load_duration_ns = load_ns_;
+        stats->kernel_launches = total * launches_nohead_;
+    }
+    return {};
+}
+
+Status Engine::rmsnorm(const float* x, const float* w, int n, float eps, float* y) {
+    CU(cudaSetDevice(device_));
+    float *dx, *dw, *dy;
+    CU(cudaMalloc((void**)&dx, (size_t)n * 4));
+    CU(cudaMalloc((void**)&dw, (size_t)n * 4));
+    CU(cudaMalloc((void**)&dy, (size_t)n * 4));
+    cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dw, w, (size_t)n * 4, cudaMemcpyHostToDevice);
+    cudaError_t e = rmsnorm_launch(dx, dw, n, eps, dy, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    if (e == cudaSuccess) e = cudaMemcpy(y, dy, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dw); cudaFree(dy);
+    CU(e);
+    return {};
+}
+
+Status Engine::gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms) {
+    CU(cudaSetDevice(device_));
+    if (rows <= 0 || cols <= 0 || !w_host || !x || !y) return fail(GL_ERR_INVALID, "bad gl_gemv arguments");
+    GGUFTensor t;
+    t.name = "<gl_gemv>";
+    t.type = (uint32_t)type;
+    t.ne = {cols, rows};
+    BlockGeom g = block_geom(t.type);
+    if (!g.weights || cols % g.weights) return fail(GL_ERR_UNSUPPORTED, "gl_gemv: unsupported type / cols");
+    t.data = static_cast<const uint8_t*>(w_host);
+    t.nbytes = row_bytes(t.type, cols) * (size_t)rows;
+    DevMatrix m;
+    const size_t mark = allocs_.size();
+    Status s = upload_matrix(t, m, false);
+    float *dx = nullptr, *dy = nullptr;
+    auto cleanup = [&]() {
+        if (dx) cudaFree(dx);
+        if (dy) cudaFree(dy);
+        while (allocs_.size() > mark) { cudaFree(allocs_.back()); allocs_.pop_back(); }
+    };
+    if (!s.ok()) { cleanup(); return s; }
+    cudaError_t e = cudaMalloc((void**)&dx, (size_t)cols * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dy, (size_t)rows * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, (size_t)cols * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cleanup(); CU(e); }
+    int nl = 0;
+    const int warm = iters > 1 ? 2 : 0;
+    for (int i = 0; i < warm && s.ok(); ++i) s = plain_gemv(stream_, m, dx, dy, &nl);
+    if (s.ok()) {
+        cudaEventRecord(ev_[0], stream_);
+        for (int i = 0; i < std::max(1, iters) && s.ok(); ++i) s = plain_gemv(stream_, m, dx, dy, &nl);
+        cudaEventRecord(ev_[1], stream_);
+        e = cudaStreamSynchronize(stream_);
+        if (s.ok() && e != cudaSuccess) s = fail(GL_ERR_CUDA, std::string("gl_gemv: ") + cudaGetErrorString(e));
+    }
+    if (s.ok()) {
+        float t_ms = 0.f;
+        cudaEventElapsedTime(&t_ms, ev_[0], ev_[1]);
+        if (ms) *ms = t_ms / std::max(1, iters);
+        e = cudaMemcpy(y, dy, (size_t)rows * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) s = fail(GL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cleanup();
+    return s;
+}
+
+Status Engine::gemv_tensor(const std::string& name, const float* x, float* y, int iters, int flush, float* ms, uint64_t* wbytes) {
+    CU(cudaSetDevice(device_));
+    const DevMatrix* m = find_matrix(name);
+    if (!m) return fail(GL_ERR_INVALID, "no such matrix: " + name);
+    float *dx = nullptr, *dy = nullptr;
+    CU(cudaMalloc((void**)&dx, (size_t)m->cols * 4));
+    CU(cudaMalloc((void**)&dy, (size_t)m->rows * 4));
+    CU(cudaMemcpy(dx, x, (size_t)m->cols * 4, cudaMemcpyHostToDevice));
+    if (flush && !flush_buf_) {
+        flush_elems_ = (size_t)64 << 20;     // 256 MB > 126 MB L2
+        CU(cudaMalloc((void**)&flush_buf_, flush_elems_ * 4));
+        allocs_.push_back(flush_buf_);
+        CU(cudaMemset(flush_buf_, 0, flush_elems_ * 4));
+    }
+    int nl = 0;
+    Status s;
+    for (int i = 0; i < 3 && s.ok(); ++i) s = plain_gemv(stream_, *m, dx, dy, &nl);
+    double tot = 0;
+    for (int i = 0; i < std::max(1, iters) && s.ok(); ++i) {
+        if (flush) l2_flush_launch(flush_buf_, flush_elems_, stream_);
+        cudaEventRecord(ev_[0], stream_);
+        s = plain_gemv(stream_, *m, dx, dy, &nl);
+        cudaEventRecord(ev_[1], stream_);
+        cudaError_t e = cudaStreamSynchronize(stream_);
+        if (s.ok() && e != cudaSuccess) s = fail(GL_ERR_CUDA, cudaGetErrorString(e));
+        float t_ms = 0.f;
+        cudaEventElapsedTime(&t_ms, ev_[0], ev_[1]);
+        tot += t_ms;
+    }
+    if (s.ok()) {
+        if (ms) *ms = (float)(tot / std::max(1, iters));
+        if (wbytes) *wbytes = m->gguf_bytes;
+        cudaError_t e = cudaMemcpy(y, dy, (size_t)m->rows * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) s = fail(GL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dx);
+    cudaFree(dy);
+    return s;
+}
+
+Status Engine::time_decode(int ctx_len, int iters, float* ms, int* launches) {
+    CU(cudaSetDevice(device_));
+    if (ctx_len < 1 || iters < 1) return fail(GL_ERR_INVALID, "bad arguments");
+    ST(kv_reset());
+    ST(ensure_pages(ctx_len + iters + 4));
+    gl_sample_opts so{};
+    so.ignore_eos = 1;
+    ST(set_state(ctx_len - 1, 1 % n_vocab_, 0, 0, &so));
+    ST(run_steps(0, 3, false));                       // warm-up
+    ST(set_state(ctx_len - 1, 1 % n_vocab_, 0, 0, &so));
+    CU(cudaEventRecord(ev_[0], stream_));
+    ST(run_steps(0, iters, false));
+    CU(cudaEventRecord(ev_[1], stream_));
+    CU(cudaEventSynchronize(ev_[1]));
+    float t_ms = 0.f;
+    cudaEventElapsedTime(&t_ms, ev_[0], ev_[1]);
+    if (ms) *ms = t_ms / iters;
+    if (launches) *launches = launches_head_;
+    ST(kv_reset());
+    return {};
+}
+
+}  // namespace gl

@@ -1,0 +1,127 @@
+// Engine: one loaded GGUF model on one B200.  Owns the weights in HBM (engine row layouts), the
+// paged KV pool, the device-resident step state and the captured decode-step CUDA graphs.
+// This is the native replacement for what sits behind OllamaService in the reference
+// (/root/reference/client/src/services/OllamaService.ts) -- see include/gridllm_native.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gridllm_native.h"
+#include "gguf_file.h"
+#include "kernels.h"
+#include "tokenizer.h"
+
+namespace gl {
+
+struct DevMatrix {
+    uint8_t* w = nullptr;      // device
+    int type = 0;
+    int rows = 0, cols = 0;
+    int row_stride = 0;        // engine layout stride (bytes)
+    size_t gguf_bytes = 0;     // algorithmic bytes (GGUF payload)
+    bool quantized() const { return type == T_Q4_K || type == T_Q6_K || type == T_Q8_0; }
+};
+
+struct LayerWeights {
+    float* attn_norm = nullptr;
+    float* ffn_norm = nullptr;
+    DevMatrix wq, wk, wv, wo, wgate, wup, wdown;
+};
+
+struct Status {
+    int code = GL_OK;
+    std::string msg;
+    bool ok() const { return code == GL_OK; }
+};
+
+class Engine {
+public:
+    static Status create(const std::string& path, int device, const gl_engine_opts* opts, Engine** out);
+    ~Engine();
+
+    Status info(gl_model_info* out) const;
+    Status generate(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, gl_token_cb cb, void* user,
+                    int32_t* out_ids, float* out_lp, gl_gen_stats* stats);
+    Status embed(const int32_t* ids, const int32_t* offs, int n_seq, float* out, gl_gen_stats* stats);
+    Status last_logits(int step, float* out, int n_vocab);
+    Status gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms);
+    Status gemv_tensor(const std::string& name, const float* x, float* y, int iters, int flush, float* ms, uint64_t* wbytes);
+    Status rmsnorm(const float* x, const float* w, int n, float eps, float* y);
+    Status decode_step(int token, float* logits, int* argmax, float* logprob);
+    Status kv_reset();
+    Status prefill(const int32_t* ids, int n, float* last_logits);
+    Status time_decode(int ctx_len, int iters, float* ms, int* launches);
+    int position() const { return host_pos_; }
+    const Tokenizer& tokenizer() const { return tok_; }
+
+private:
+    Engine() = default;
+    Status load(const std::string& path, int device, const gl_engine_opts* opts);
+    Status upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layout);
+    Status upload_f32(const GGUFTensor& t, float** out, int expect);
+    Status ensure_pages(int n_tokens);
+    Status enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, int* n_launch);
+    Status enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch);
+    Status plain_gemv(cudaStream_t s, const DevMatrix& m, const float* x, float* y, int* n_launch);
+    Status build_graphs();
+    Status set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so);
+    Status run_steps(int n_nohead, int n_head, bool keep_logits);
+    const DevMatrix* find_matrix(const std::string& name) const;
+
+    // model
+    GGUFFile gguf_;
+    Tokenizer tok_;
+    gl_model_info info_{};
+    int n_layer_ = 0, n_embd_ = 0, n_head_ = 0, n_kv_ = 0, hd_ = 0, n_ff_ = 0, n_vocab_ = 0, n_ctx_ = 0;
+    float eps_ = 1e-5f, rope_base_ = 10000.f;
+    std::vector<LayerWeights> layers_;
+    DevMatrix tok_embd_;       // native layout (row gather)
+    DevMatrix output_;         // engine layout (GEMV)
+    float* output_norm_ = nullptr;
+    bool all_quant_ = true;
+
+    // options
+    int device_ = 0, sm_count_ = 148;
+    int abits_ = 16;
+    bool use_graph_ = true, use_pdl_ = true, fused_ = true;
+    int stage_kb_ = 24, smem_kb_ = 110, attn_splits_ = 16;
+
+    // device state
+    cudaStream_t stream_ = nullptr;
+    std::vector<void*> allocs_;
+    float *x_ = nullptr, *xn_ = nullptr, *q_ = nullptr, *ktmp_ = nullptr, *vtmp_ = nullptr, *attn_ = nullptr, *h_ = nullptr,
+          *gate_ = nullptr, *up_ = nullptr, *ytmp_ = nullptr, *logits_ = nullptr;
+    float *rope_cos_ = nullptr, *rope_sin_ = nullptr;
+    float *part_o_ = nullptr, *part_ml_ = nullptr;
+    unsigned* counters_ = nullptr;
+    __half *kcache_ = nullptr, *vcache_ = nullptr;    // [layer][page][kv][16][hd]
+    size_t kv_layer_elems_ = 0;
+    int n_pages_ = 0;
+    int* page_table_ = nullptr;                      // device
+    std::vector<int> free_pages_;
+    std::vector<int> seq_pages_;
+    StepState* st_ = nullptr;
+    int* prompt_ids_ = nullptr;
+    int* out_ids_ = nullptr;
+    float* out_lp_ = nullptr;
+    float* logits_keep_ = nullptr;
+    int keep_cap_ = 0;
+    float* flush_buf_ = nullptr;
+    size_t flush_elems_ = 0;
+    int max_out_ = 0;
+    int host_pos_ = 0;
+
+    cudaGraphExec_t g_nohead_ = nullptr, g_head_ = nullptr, g_head_keep_ = nullptr;
+    int launches_nohead_ = 0, launches_head_ = 0;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t load_ns_ = 0;
+    uint64_t weight_bytes_ = 0, decode_bytes_ = 0, n_params_ = 0;
+};
+
+void set_last_error(const std::string& s);
+const char* get_last_error();
+
+}  // namespace gl

@@ -1,0 +1,120 @@
+// Launcher interface of the sm_100a kernels (implemented in gemv.cu, attention.cu, misc.cu,
+// prefill.cu).  Host code (engine.cu) only sees plain structs and cudaStream_t.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gl {
+
+struct StepState;
+
+constexpr int GEMV_CONSUMER_WARPS = 8;
+constexpr int GEMV_THREADS = (GEMV_CONSUMER_WARPS + 1) * 32;
+constexpr int GEMV_MAX_PASSES = 4;
+constexpr int GEMV_MAX_STAGES = 8;
+constexpr int KV_PAGE_TOKENS = 16;
+
+enum GemvEpilogue : int {
+    EPI_STORE = 0,   // out[r] = y[r]
+    EPI_ADD = 1,     // out[r] = resid[r] + y[r]                (attn_output / ffn_down + residual)
+    EPI_QKV = 2,     // seg0 -> RoPE -> q fp32; seg1 -> RoPE -> K page (fp16); seg2 -> V page (fp16)
+    EPI_SILU = 3,    // pair mode: out[r] = silu(gate[r]) * up[r]
+};
+
+struct GemvSeg {
+    const uint8_t* w;      // engine row layout (rowdot.h), row stride = row_stride bytes
+    int type;              // ggml type id
+    int rows;
+    int row_stride;
+    int rows_per_stage;    // host-chosen: multiple of rows-per-pass where possible
+};
+
+struct GemvParams {
+    GemvSeg seg[3];
+    int nseg;
+    int pair;              // 1: seg[0] / seg[1] are gate / up, staged together, EPI_SILU
+    int cols;              // K, multiple of 128, <= 32768
+    const float* x;        // [cols] fp32 activations (produced by the previous kernel)
+    const float* norm_w;   // fused RMSNorm prologue when non-null
+    float eps;
+    int epi;
+    float* out;            // STORE / ADD / SILU: [rows]; QKV: q fp32 [seg0.rows]
+    const float* resid;    // ADD
+    // EPI_QKV
+    const float* rope_cos; // [n_ctx][head_dim/2]
+    const float* rope_sin;
+    int head_dim;
+    int n_kv_heads;
+    __half* k_cache;       // this layer: [n_pages][n_kv][KV_PAGE_TOKENS][head_dim]
+    __half* v_cache;
+    const int* page_table; // logical page -> physical page
+    const StepState* st;   // position (EPI_QKV) / done flag
+    // staging
+    int n_stages;
+    int stage_bytes;
+};
+
+// host helpers
+size_t gemv_smem_bytes(int cols, int n_stages, int stage_bytes);
+// fills seg[i].rows_per_stage; returns false if the shape is outside the kernel's envelope
+bool gemv_plan(GemvParams& p);
+cudaError_t gemv_configure();   // opt-in to large dynamic shared memory (once per process)
+cudaError_t gemv_launch(const GemvParams& p, int abits, int n_ctas, bool pdl, cudaStream_t s);
+
+// plain fp weights (F32/F16/BF16): y = W x, fp32 accumulate, no fusion
+cudaError_t gemv_fp_launch(const void* w, int type, int rows, int cols, const float* x, float* y, cudaStream_t s);
+
+// ---- small kernels ---------------------------------------------------------------------------
+// x[n_embd] = dequant(token_embd[row token]); also publishes the token for this step.
+struct EmbedParams {
+    const uint8_t* w;       // token_embd in NATIVE GGUF layout (row gather)
+    int type;
+    int cols;
+    int row_bytes;
+    StepState* st;
+    const int* prompt_ids;  // sequential prefill: token = prompt_ids[pos] while pos < n_prompt
+    float* x;
+};
+cudaError_t embed_launch(const EmbedParams& p, bool pdl, cudaStream_t s);
+
+struct AttnParams {
+    const float* q;         // [n_head][head_dim] (already rotated)
+    const __half* k_cache;  // layer base
+    const __half* v_cache;
+    const int* page_table;
+    const StepState* st;    // attends to positions 0..st->pos
+    float* out;             // [n_head][head_dim]
+    float* part_o;          // [n_head][n_splits][head_dim]
+    float* part_ml;         // [n_head][n_splits][2]
+    unsigned* counters;     // [n_kv_heads], zero between launches
+    int n_head, n_kv_heads, head_dim, n_splits;
+    float scale;
+};
+cudaError_t attn_decode_launch(const AttnParams& p, bool pdl, cudaStream_t s);
+
+struct SampleParams {
+    const float* logits;
+    int n_vocab;
+    StepState* st;
+    int* out_ids;
+    float* out_logprobs;
+    float* logits_keep;     // optional [max_steps][n_vocab] copy for parity tests
+    int max_out;
+};
+// greedy: argmax + log-softmax of the winner; advances StepState (pos+1, token=argmax, out_idx+1).
+cudaError_t sample_greedy_launch(const SampleParams& p, bool pdl, cudaStream_t s);
+// sequential-prefill step without sampling: pos += 1
+cudaError_t advance_launch(StepState* st, bool pdl, cudaStream_t s);
+
+// standalone pieces (used for fp-weight models and as unfused cross-checks)
+cudaError_t rmsnorm_launch(const float* x, const float* w, int n, float eps, float* y, cudaStream_t s);
+cudaError_t rope_kv_launch(float* q, const float* k, const float* v, int n_head, int n_kv, int head_dim,
+                           const float* cos_t, const float* sin_t, const StepState* st, __half* k_cache,
+                           __half* v_cache, const int* page_table, cudaStream_t s);
+cudaError_t silu_mul_launch(const float* g, const float* u, int n, float* out, cudaStream_t s);
+cudaError_t add_launch(const float* a, const float* b, int n, float* out, cudaStream_t s);
+cudaError_t l2_flush_launch(float* buf, size_t n, cudaStream_t s);
+
+}  // namespace gl

@@ -1,0 +1,230 @@
+// Small kernels of the decode step: token-embedding row gather (dequantise one row), greedy sampler
+// (argmax + log-softmax, advances the device-resident StepState), and the standalone RMSNorm / RoPE+KV
+// append / SiLU*mul / add pieces used for fp-weight models and as unfused cross-checks of the fused
+// GEMV prologue / epilogues.  Reference call sites: see gemv.cu header.
+#include "common.cuh"
+#include "kernels.h"
+#include "rowdot.h"
+#include "gguf_file.h"
+
+namespace gl {
+
+namespace {
+
+__device__ __forceinline__ float dequant_native(const uint8_t* row, int type, int c) {
+    switch (type) {
+        case T_F32: return reinterpret_cast<const float*>(row)[c];
+        case T_F16: return __half2float(reinterpret_cast<const __half*>(row)[c]);
+        case T_BF16: return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(row)[c] << 16);
+        case T_Q8_0: {
+            const uint8_t* b = row + (size_t)(c >> 5) * 34;
+            return half_bits_to_float(*reinterpret_cast<const uint16_t*>(b)) * (float)(int8_t)b[2 + (c & 31)];
+        }
+        case T_Q4_K: {
+            const uint8_t* b = row + (size_t)(c >> 8) * 144;
+            const int e = c & 255, sub = e >> 5, l = e & 31;
+            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b));
+            const float dmin = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 2));
+            const uint8_t* sc = b + 4;
+            int s, m;
+            if (sub < 4) { s = sc[sub] & 63; m = sc[4 + sub] & 63; }
+            else { s = (sc[4 + sub] & 0xF) | ((sc[sub - 4] >> 6) << 4); m = (sc[4 + sub] >> 4) | ((sc[sub] >> 6) << 4); }
+            const uint8_t qb = b[16 + (sub >> 1) * 32 + l];
+            const int q = (sub & 1) ? (qb >> 4) : (qb & 0xF);
+            return d * (float)s * (float)q - dmin * (float)m;
+        }
+        case T_Q6_K: {
+            const uint8_t* b = row + (size_t)(c >> 8) * 210;
+            const int e = c & 255, h = e >> 7, r = e & 127;
+            const int s = r >> 6, i = r & 63;            // ql nibble s of byte h*64+i
+            const int t = r >> 5, j = r & 31;            // qh bits 2t of byte h*32+j
+            const int qlv = (b[h * 64 + i] >> (4 * s)) & 0xF;
+            const int qhv = (b[128 + h * 32 + j] >> (2 * t)) & 3;
+            const int q = (qlv | (qhv << 4)) - 32;
+            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 208));
+            return d * (float)(int8_t)b[192 + (e >> 4)] * (float)q;
+        }
+        default: return 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ EmbedParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ int tok_s;
+    if (threadIdx.x == 0) {
+        const int pos = __ldcg(&p.st->pos);
+        const int np = __ldcg(&p.st->n_prompt);
+        int tok = __ldcg(&p.st->token);
+        if (pos < np) tok = __ldcg(p.prompt_ids + pos);
+        p.st->token = tok;
+        tok_s = tok;
+    }
+    __syncthreads();
+    const uint8_t* row = p.w + (size_t)tok_s * p.row_bytes;
+    for (int c = threadIdx.x; c < p.cols; c += blockDim.x) p.x[c] = dequant_native(row, p.type, c);
+}
+
+__global__ void __launch_bounds__(1024) sample_greedy_kernel(const __grid_constant__ SampleParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float smax[32];
+    __shared__ int sidx[32];
+    __shared__ float ssum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    StepState* st = p.st;
+    const int done = __ldcg(&st->done);
+    const int out_idx = __ldcg(&st->out_idx);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < p.n_vocab; i += 1024) {
+        const float v = __ldcg(p.logits + i);
+        if (v > best) { best = v; bi = i; }       // strided scan keeps the lowest index per thread on ties
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { smax[warp] = best; sidx[warp] = bi; }
+    __syncthreads();
+    best = smax[0]; bi = sidx[0];
+    for (int w = 1; w < 32; ++w) {
+        if (smax[w] > best || (smax[w] == best && sidx[w] < bi)) { best = smax[w]; bi = sidx[w]; }
+    }
+    float s = 0.f;
+    for (int i = tid; i < p.n_vocab; i += 1024) s += expf(__ldcg(p.logits + i) - best);
+    s = warp_sum(s);
+    if (lane == 0) ssum[warp] = s;
+    __syncthreads();
+    if (p.logits_keep != nullptr && !done && out_idx < p.max_out) {
+        float* dst = p.logits_keep + (size_t)out_idx * p.n_vocab;
+        for (int i = tid; i < p.n_vocab; i += 1024) dst[i] = __ldcg(p.logits + i);
+    }
+    if (tid == 0 && !done) {
+        float tot = 0.f;
+        for (int w = 0; w < 32; ++w) tot += ssum[w];
+        if (out_idx < p.max_out) {
+            p.out_ids[out_idx] = bi;
+            p.out_logprobs[out_idx] = -logf(tot);
+        }
+        st->token = bi;
+        st->pos = st->pos + 1;
+        st->out_idx = out_idx + 1;
+        if (!st->ignore_eos) {
+            for (int k = 0; k < st->n_stop; ++k)
+                if (st->stop_ids[k] == bi) st->done = 1;
+        }
+    }
+}
+
+__global__ void advance_kernel(StepState* st) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) st->pos = st->pos + 1;
+}
+
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, int n, float eps,
+                                                      float* __restrict__ y) {
+    __shared__ float red[8];
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) { const float v = x[i]; ss += v * v; }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    const float rstd = 1.0f / sqrtf(tot / (float)n + eps);
+    for (int i = threadIdx.x; i < n; i += 256) y[i] = (x[i] * rstd) * w[i];
+}
+
+__global__ void rope_kv_kernel(float* q, const float* k, const float* v, int n_head, int n_kv, int hd, const float* cos_t,
+                               const float* sin_t, const StepState* st, __half* k_cache, __half* v_cache, const int* page_table) {
+    const int pos = st->pos;
+    const int page = page_table[pos / KV_PAGE_TOKENS];
+    const int tok = pos % KV_PAGE_TOKENS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // pair index
+    const int nq = n_head * hd / 2, nk = n_kv * hd / 2;
+    if (i < nq) {
+        const int d = (2 * i) % hd;
+        const float c = cos_t[(size_t)pos * (hd / 2) + d / 2], s = sin_t[(size_t)pos * (hd / 2) + d / 2];
+        const float a = q[2 * i], b = q[2 * i + 1];
+        q[2 * i] = a * c - b * s;
+        q[2 * i + 1] = a * s + b * c;
+    } else if (i < nq + nk) {
+        const int j = i - nq;
+        const int r = 2 * j, kvh = r / hd, d = r % hd;
+        const float c = cos_t[(size_t)pos * (hd / 2) + d / 2], s = sin_t[(size_t)pos * (hd / 2) + d / 2];
+        const float a = k[r], b = k[r + 1];
+        const size_t off = (((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d;
+        k_cache[off] = __float2half_rn(a * c - b * s);
+        k_cache[off + 1] = __float2half_rn(a * s + b * c);
+        v_cache[off] = __float2half_rn(v[r]);
+        v_cache[off + 1] = __float2half_rn(v[r + 1]);
+    }
+}
+
+__global__ void silu_mul_kernel(const float* g, const float* u, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float a = g[i]; out[i] = (a / (1.0f + expf(-a))) * u[i]; }
+}
+__global__ void add_kernel(const float* a, const float* b, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+__global__ void l2_flush_kernel(float* buf, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = buf[i] * 0.5f + 1.0f;
+}
+
+template <typename... Args>
+cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, bool pdl, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+}  // namespace
+
+cudaError_t embed_launch(const EmbedParams& p, bool pdl, cudaStream_t s) {
+    return launch_pdl(embed_kernel, dim3(1), dim3(256), pdl, s, p);
+}
+cudaError_t sample_greedy_launch(const SampleParams& p, bool pdl, cudaStream_t s) {
+    return launch_pdl(sample_greedy_kernel, dim3(1), dim3(1024), pdl, s, p);
+}
+cudaError_t advance_launch(StepState* st, bool pdl, cudaStream_t s) {
+    return launch_pdl(advance_kernel, dim3(1), dim3(32), pdl, s, st);
+}
+cudaError_t rmsnorm_launch(const float* x, const float* w, int n, float eps, float* y, cudaStream_t s) {
+    rmsnorm_kernel<<<1, 256, 0, s>>>(x, w, n, eps, y);
+    return cudaGetLastError();
+}
+cudaError_t rope_kv_launch(float* q, const float* k, const float* v, int n_head, int n_kv, int head_dim, const float* cos_t,
+                           const float* sin_t, const StepState* st, __half* k_cache, __half* v_cache, const int* page_table,
+                           cudaStream_t s) {
+    const int n = (n_head + n_kv) * head_dim / 2;
+    rope_kv_kernel<<<(n + 255) / 256, 256, 0, s>>>(q, k, v, n_head, n_kv, head_dim, cos_t, sin_t, st, k_cache, v_cache, page_table);
+    return cudaGetLastError();
+}
+cudaError_t silu_mul_launch(const float* g, const float* u, int n, float* out, cudaStream_t s) {
+    silu_mul_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, u, n, out);
+    return cudaGetLastError();
+}
+cudaError_t add_launch(const float* a, const float* b, int n, float* out, cudaStream_t s) {
+    add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, out);
+    return cudaGetLastError();
+}
+cudaError_t l2_flush_launch(float* buf, size_t n, cudaStream_t s) {
+    l2_flush_kernel<<<148 * 4, 256, 0, s>>>(buf, n);
+    return cudaGetLastError();
+}
+
+}  // namespace gl

@@ -1,0 +1,242 @@
+// Byte-level BPE (GPT-2 style) from GGUF metadata.  See tokenizer.h.
+#include "tokenizer.h"
+
+#include <algorithm>
+#include <climits>
+
+namespace gl {
+
+namespace {
+
+std::string cp_to_utf8(uint32_t cp) {
+    std::string s;
+    if (cp < 0x80) s += (char)cp;
+    else if (cp < 0x800) { s += (char)(0xC0 | (cp >> 6)); s += (char)(0x80 | (cp & 0x3F)); }
+    else if (cp < 0x10000) { s += (char)(0xE0 | (cp >> 12)); s += (char)(0x80 | ((cp >> 6) & 0x3F)); s += (char)(0x80 | (cp & 0x3F)); }
+    else { s += (char)(0xF0 | (cp >> 18)); s += (char)(0x80 | ((cp >> 12) & 0x3F)); s += (char)(0x80 | ((cp >> 6) & 0x3F)); s += (char)(0x80 | (cp & 0x3F)); }
+    return s;
+}
+
+// split a UTF-8 string into code-point substrings
+std::vector<std::string> utf8_chars(const std::string& s) {
+    std::vector<std::string> out;
+    for (size_t i = 0; i < s.size();) {
+        unsigned char c = (unsigned char)s[i];
+        size_t n = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+        if (i + n > s.size()) n = 1;
+        out.push_back(s.substr(i, n));
+        i += n;
+    }
+    return out;
+}
+
+uint32_t utf8_decode1(const std::string& ch) {
+    unsigned char c = (unsigned char)ch[0];
+    if (c < 0x80 || ch.size() == 1) return c;
+    if (ch.size() == 2) return ((c & 0x1F) << 6) | (ch[1] & 0x3F);
+    if (ch.size() == 3) return ((c & 0x0F) << 12) | ((ch[1] & 0x3F) << 6) | (ch[2] & 0x3F);
+    return ((c & 0x07) << 18) | ((ch[1] & 0x3F) << 12) | ((ch[2] & 0x3F) << 6) | (ch[3] & 0x3F);
+}
+
+inline bool is_letter(unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80; }
+inline bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
+inline bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+inline bool is_nl(unsigned char c) { return c == '\n' || c == '\r'; }
+
+// llama-bpe pre-tokeniser restated over bytes:
+//  (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n L N]? L+ | N{1,3} | ' '? [^\s L N]+ [\r\n]* | \s*[\r\n]+ | \s+(?!\S) | \s+
+std::vector<std::string> pretokenize(const std::string& t) {
+    std::vector<std::string> out;
+    const size_t n = t.size();
+    size_t i = 0;
+    auto lower = [](unsigned char c) { return (c >= 'A' && c <= 'Z') ? (unsigned char)(c + 32) : c; };
+    while (i < n) {
+        const unsigned char c = (unsigned char)t[i];
+        // contractions
+        if (c == '\'' && i + 1 < n) {
+            const unsigned char a = lower((unsigned char)t[i + 1]);
+            const unsigned char b = i + 2 < n ? lower((unsigned char)t[i + 2]) : 0;
+            size_t len = 0;
+            if (a == 's' || a == 't' || a == 'm' || a == 'd') len = 2;
+            if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e') || (a == 'l' && b == 'l')) len = 3;
+            if (len) { out.push_back(t.substr(i, len)); i += len; continue; }
+        }
+        // [^\r\n L N]? L+
+        {
+            size_t j = i;
+            if (!is_nl(c) && !is_letter(c) && !is_digit(c) && j + 1 < n && is_letter((unsigned char)t[j + 1])) ++j;
+            if (j < n && is_letter((unsigned char)t[j])) {
+                size_t k = j;
+                while (k < n && is_letter((unsigned char)t[k])) ++k;
+                out.push_back(t.substr(i, k - i));
+                i = k;
+                continue;
+            }
+        }
+        // N{1,3}
+        if (is_digit(c)) {
+            size_t k = i;
+            while (k < n && k - i < 3 && is_digit((unsigned char)t[k])) ++k;
+            out.push_back(t.substr(i, k - i));
+            i = k;
+            continue;
+        }
+        // ' '? [^\s L N]+ [\r\n]*
+        {
+            size_t j = i;
+            if (c == ' ' && j + 1 < n) ++j;
+            auto punct = [&](size_t p) { unsigned char d = (unsigned char)t[p]; return !is_space(d) && !is_letter(d) && !is_digit(d); };
+            if (j < n && punct(j)) {
+                size_t k = j;
+                while (k < n && punct(k)) ++k;
+                while (k < n && is_nl((unsigned char)t[k])) ++k;
+                out.push_back(t.substr(i, k - i));
+                i = k;
+                continue;
+            }
+        }
+        // whitespace runs
+        if (is_space(c)) {
+            size_t k = i;
+            while (k < n && is_space((unsigned char)t[k])) ++k;
+            // \s*[\r\n]+ : take through the last newline in the run
+            size_t last_nl = std::string::npos;
+            for (size_t p = i; p < k; ++p) if (is_nl((unsigned char)t[p])) last_nl = p;
+            if (last_nl != std::string::npos) { out.push_back(t.substr(i, last_nl + 1 - i)); i = last_nl + 1; continue; }
+            // \s+(?!\S): leave the last space for the next word if something follows
+            if (k < n && k - i > 1) { out.push_back(t.substr(i, k - 1 - i)); i = k - 1; continue; }
+            if (k < n && k - i == 1) {
+                // single space followed by non-space that is not letter/punct-start (e.g. digit): emit alone
+                out.push_back(t.substr(i, 1)); i = k; continue;
+            }
+            out.push_back(t.substr(i, k - i));
+            i = k;
+            continue;
+        }
+        out.push_back(t.substr(i, 1));
+        ++i;
+    }
+    return out;
+}
+
+}  // namespace
+
+bool Tokenizer::load(const GGUFFile& f) {
+    ok_ = false;
+    const GGUFValue* toks = f.find("tokenizer.ggml.tokens");
+    if (!toks || toks->arr_s.empty()) return false;
+    if (f.get_s("tokenizer.ggml.model", "") != "gpt2") return false;
+    tokens_ = toks->arr_s;
+    const GGUFValue* ty = f.find("tokenizer.ggml.token_type");
+    types_.assign(tokens_.size(), 1);
+    if (ty && ty->arr_i.size() == tokens_.size())
+        for (size_t i = 0; i < tokens_.size(); ++i) types_[i] = (int)ty->arr_i[i];
+    tok2id_.reserve(tokens_.size() * 2);
+    for (size_t i = 0; i < tokens_.size(); ++i) tok2id_.emplace(tokens_[i], (int32_t)i);
+    const GGUFValue* mg = f.find("tokenizer.ggml.merges");
+    if (mg)
+        for (size_t i = 0; i < mg->arr_s.size(); ++i) merge_rank_.emplace(mg->arr_s[i], (int)i);
+    bos = (int)f.get_u("tokenizer.ggml.bos_token_id", (uint64_t)-1);
+    eos = (int)f.get_u("tokenizer.ggml.eos_token_id", (uint64_t)-1);
+    eot = (int)f.get_u("tokenizer.ggml.eot_token_id", (uint64_t)-1);
+    add_bos_default = f.get_u("tokenizer.ggml.add_bos_token", 1) != 0;
+    chat_template = f.get_s("tokenizer.chat_template", "");
+    // GPT-2 byte <-> unicode table
+    std::vector<int> bs;
+    for (int b = 33; b <= 126; ++b) bs.push_back(b);
+    for (int b = 161; b <= 172; ++b) bs.push_back(b);
+    for (int b = 174; b <= 255; ++b) bs.push_back(b);
+    std::vector<int> cs(bs.begin(), bs.end());
+    int extra = 0;
+    for (int b = 0; b < 256; ++b)
+        if (std::find(bs.begin(), bs.end(), b) == bs.end()) { bs.push_back(b); cs.push_back(256 + extra++); }
+    for (size_t i = 0; i < bs.size(); ++i) {
+        byte2u_[bs[i]] = cp_to_utf8((uint32_t)cs[i]);
+        cp2byte_[(uint32_t)cs[i]] = (uint8_t)bs[i];
+    }
+    for (size_t i = 0; i < tokens_.size(); ++i)
+        if (types_[i] == 3 || types_[i] == 4) specials_.emplace_back(tokens_[i], (int32_t)i);
+    std::sort(specials_.begin(), specials_.end(), [](auto& a, auto& b) { return a.first.size() > b.first.size(); });
+    ok_ = true;
+    return true;
+}
+
+void Tokenizer::bpe_word(const std::string& word_u, std::vector<int32_t>& out) const {
+    std::vector<std::string> sym = utf8_chars(word_u);
+    while (sym.size() > 1) {
+        int best = INT_MAX;
+        size_t bi = 0;
+        for (size_t i = 0; i + 1 < sym.size(); ++i) {
+            auto it = merge_rank_.find(sym[i] + " " + sym[i + 1]);
+            if (it != merge_rank_.end() && it->second < best) { best = it->second; bi = i; }
+        }
+        if (best == INT_MAX) break;
+        sym[bi] += sym[bi + 1];
+        sym.erase(sym.begin() + (long)bi + 1);
+    }
+    for (auto& s : sym) {
+        auto it = tok2id_.find(s);
+        if (it != tok2id_.end()) { out.push_back(it->second); continue; }
+        for (auto& ch : utf8_chars(s)) {      // unknown merge result: fall back to byte tokens
+            auto jt = tok2id_.find(ch);
+            if (jt != tok2id_.end()) out.push_back(jt->second);
+        }
+    }
+}
+
+std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos, bool parse_special) const {
+    std::vector<int32_t> out;
+    if (!ok_) return out;
+    if (add_bos && bos >= 0) out.push_back(bos);
+    // split on control tokens first
+    std::vector<std::pair<std::string, int32_t>> parts;   // (text, -1) or ("", special id)
+    if (parse_special && !specials_.empty()) {
+        size_t i = 0, start = 0;
+        while (i < text.size()) {
+            bool hit = false;
+            for (auto& sp : specials_) {
+                if (!sp.first.empty() && text.compare(i, sp.first.size(), sp.first) == 0) {
+                    if (i > start) parts.emplace_back(text.substr(start, i - start), -1);
+                    parts.emplace_back(std::string(), sp.second);
+                    i += sp.first.size();
+                    start = i;
+                    hit = true;
+                    break;
+                }
+            }
+            if (!hit) ++i;
+        }
+        if (start < text.size()) parts.emplace_back(text.substr(start), -1);
+    } else {
+        parts.emplace_back(text, -1);
+    }
+    for (auto& pr : parts) {
+        if (pr.second >= 0) { out.push_back(pr.second); continue; }
+        for (auto& w : pretokenize(pr.first)) {
+            std::string wu;
+            for (unsigned char c : w) wu += byte2u_[c];
+            bpe_word(wu, out);
+        }
+    }
+    return out;
+}
+
+std::string Tokenizer::piece(int32_t id) const {
+    if (!ok_ || id < 0 || id >= (int)tokens_.size()) return {};
+    if (types_[id] == 3) return {};     // control tokens render as nothing
+    std::string out;
+    for (auto& ch : utf8_chars(tokens_[id])) {
+        auto it = cp2byte_.find(utf8_decode1(ch));
+        if (it != cp2byte_.end()) out += (char)it->second;
+        else out += ch;
+    }
+    return out;
+}
+
+std::string Tokenizer::decode(const int32_t* ids, int n) const {
+    std::string out;
+    for (int i = 0; i < n; ++i) out += piece(ids[i]);
+    return out;
+}
+
+}  // namespace gl

@@ -1,0 +1,41 @@
+// Byte-level BPE tokenizer driven by GGUF metadata (tokenizer.ggml.{model,tokens,merges,...}).
+// In the reference the tokenizer lives inside Ollama; OllamaService only ever ships prompt TEXT
+// (/root/reference/client/src/services/OllamaService.ts:101-104, 190-195), so a native worker needs
+// its own.  Supports tokenizer.ggml.model == "gpt2" (Llama-3 family).  The pre-tokeniser is the
+// llama-bpe split restated for ASCII classes with every non-ASCII UTF-8 sequence treated as a
+// letter (documented limitation).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gguf_file.h"
+
+namespace gl {
+
+class Tokenizer {
+public:
+    bool load(const GGUFFile& f);
+    bool ok() const { return ok_; }
+    std::vector<int32_t> encode(const std::string& text, bool add_bos, bool parse_special) const;
+    std::string decode(const int32_t* ids, int n) const;
+    std::string piece(int32_t id) const;     // raw bytes of one token ("" for control tokens)
+    int n_vocab() const { return (int)tokens_.size(); }
+    int bos = -1, eos = -1, eot = -1;
+    bool add_bos_default = true;
+    std::string chat_template;
+
+private:
+    void bpe_word(const std::string& word_u, std::vector<int32_t>& out) const;
+    bool ok_ = false;
+    std::vector<std::string> tokens_;                 // in "unicode-escaped bytes" form (GPT-2)
+    std::vector<int> types_;
+    std::unordered_map<std::string, int32_t> tok2id_;
+    std::unordered_map<std::string, int> merge_rank_;  // "a b" -> rank
+    std::vector<std::pair<std::string, int32_t>> specials_;  // control tokens, longest first
+    std::string byte2u_[256];                         // byte -> UTF-8 of its GPT-2 code point
+    std::unordered_map<uint32_t, uint8_t> cp2byte_;
+};
+
+}  // namespace gl

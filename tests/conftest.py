@@ -1,0 +1,72 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def tmp_models(tmp_path_factory):
+    return tmp_path_factory.mktemp("models")
+
+
+@pytest.fixture(scope="session")
+def tiny_gguf(tmp_models):
+    """2-layer d=256 Llama (head_dim 64, GQA 2:1), q4_K_M recipe (Q4_K + Q6_K), properly quantised."""
+    from oracle import gguf_synth as S
+    p = str(tmp_models / "tiny_q4km.gguf")
+    S.build_model(p, S.TINY, "q4_k_m", seed=1234)
+    return p
+
+
+@pytest.fixture(scope="session")
+def tiny128_gguf(tmp_models):
+    """2-layer d=512 Llama with head_dim 128, GQA 4:1, n_ff 768, q4_K_M recipe."""
+    from oracle import gguf_synth as S
+    p = str(tmp_models / "tiny128_q4km.gguf")
+    S.build_model(p, S.TINY128, "q4_k_m", seed=4321)
+    return p
+
+
+@pytest.fixture(scope="session")
+def tiny_q8_gguf(tmp_models):
+    from oracle import gguf_synth as S
+    p = str(tmp_models / "tiny_q8.gguf")
+    S.build_model(p, S.TINY, "q8_0", seed=99)
+    return p
+
+
+@pytest.fixture(scope="session")
+def tiny_f16_gguf(tmp_models):
+    from oracle import gguf_synth as S
+    p = str(tmp_models / "tiny_f16.gguf")
+    S.build_model(p, S.TINY, "f16", seed=77)
+    return p
+
+
+@pytest.fixture(scope="session")
+def hostcheck_lib():
+    """CPU build of the GEMV lane program (tests/hostcheck) -- test infrastructure only."""
+    import ctypes
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
+    out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
+    deps = [src, os.path.join(ROOT, "gridllm_b200", "csrc", "rowdot.h"), os.path.join(ROOT, "gridllm_b200", "csrc", "gguf_file.cpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src,
+                               os.path.join(ROOT, "gridllm_b200", "csrc", "gguf_file.cpp")])
+    return ctypes.CDLL(out)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
