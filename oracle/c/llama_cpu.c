@@ -1,0 +1,436 @@
+/*
+ * TEST INFRASTRUCTURE / CPU BASELINE -- plain-C restatement of the decode step the native worker
+ * replaces.  Not part of the product: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.
+ *
+ * What it restates: the per-token forward that, for the reference, runs inside the Ollama daemon
+ * reached from OllamaService.generateResponse / generateStreamResponse
+ * (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237).  Ollama (llama.cpp/ggml)
+ * is not vendored in /root/reference and is un-pinned (docs/deployment/docker-compose.dependencies.yml:14,
+ * image ollama/ollama:latest), so this follows the published GGUF block formats and Llama
+ * architecture, and is pinned against oracle/llama_oracle.py (tests/test_c_oracle.py), which is in
+ * turn pinned against gguf-py and transformers.  PARITY UNPINNED w.r.t. the reference itself.
+ *
+ * act_mode 0: exact -- dequantised fp32 weights x fp32 activations ("mode A", the specification).
+ * act_mode 1: ggml-style -- activations quantised to int8 per 32-column block, integer dot
+ *             products ("mode B"); this is the fair stand-in for llama.cpp's CPU kernels and is what
+ *             bench.py times as the CPU baseline (label: "CPU restatement, not Ollama").
+ * K/V are rounded to fp16 when cached, like the engine.
+ */
+#define _GNU_SOURCE
+#include <fcntl.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+enum { T_F32 = 0, T_F16 = 1, T_Q8_0 = 8, T_Q4_K = 12, T_Q6_K = 14, T_BF16 = 30 };
+
+typedef struct { const uint8_t* data; int type; int rows, cols; size_t row_bytes; } mat_t;
+typedef struct { const float* attn_norm; const float* ffn_norm; mat_t wq, wk, wv, wo, wg, wu, wd; } layer_t;
+
+typedef struct {
+    void* map; size_t map_len;
+    int n_layer, n_embd, n_head, n_kv, hd, n_ff, n_vocab, n_ctx;
+    float eps, rope_base;
+    mat_t tok_embd, output; const float* output_norm;
+    layer_t* layers;
+    float *kc, *vc;            /* [layer][pos][n_kv*hd], values already fp16-rounded */
+    float *cos_t, *sin_t;      /* [n_ctx][hd/2] */
+    int pos;
+    float *x, *xn, *q, *k, *v, *att, *g, *u, *h, *y, *sc;
+    int8_t* xq; float* xs;     /* int8 activations + per-32 scale */
+} model_t;
+
+static float h2f(uint16_t h) { _Float16 f; memcpy(&f, &h, 2); return (float)f; }
+static float f16_round(float v) { _Float16 f = (_Float16)v; return (float)f; }
+
+static size_t type_row_bytes(int t, int cols) {
+    switch (t) {
+        case T_F32: return (size_t)cols * 4;
+        case T_F16: case T_BF16: return (size_t)cols * 2;
+        case T_Q8_0: return (size_t)cols / 32 * 34;
+        case T_Q4_K: return (size_t)cols / 256 * 144;
+        case T_Q6_K: return (size_t)cols / 256 * 210;
+        default: return 0;
+    }
+}
+
+/* ---- GGUF v3 container (public layout) ------------------------------------------------------- */
+typedef struct { const uint8_t* p; const uint8_t* end; int ok; } cur_t;
+static uint64_t rd(cur_t* c, int n) { uint64_t v = 0; if (c->end - c->p < n) { c->ok = 0; return 0; } memcpy(&v, c->p, n); c->p += n; return v; }
+static void rd_str(cur_t* c, char* out, int cap) {
+    uint64_t n = rd(c, 8);
+    if (!c->ok || (uint64_t)(c->end - c->p) < n) { c->ok = 0; return; }
+    if (out) { int m = (int)(n < (uint64_t)cap - 1 ? n : (uint64_t)cap - 1); memcpy(out, c->p, m); out[m] = 0; }
+    c->p += n;
+}
+static const int scalar_size[13] = {1, 1, 2, 2, 4, 4, 4, 1, 0, 0, 8, 8, 8};
+static double rd_num(cur_t* c, uint32_t t) {
+    switch (t) {
+        case 0: return (double)(uint8_t)rd(c, 1);
+        case 1: return (double)(int8_t)rd(c, 1);
+        case 2: return (double)(uint16_t)rd(c, 2);
+        case 3: return (double)(int16_t)rd(c, 2);
+        case 4: return (double)(uint32_t)rd(c, 4);
+        case 5: return (double)(int32_t)rd(c, 4);
+        case 6: { uint32_t b = (uint32_t)rd(c, 4); float f; memcpy(&f, &b, 4); return f; }
+        case 7: return (double)(uint8_t)rd(c, 1);
+        case 10: return (double)rd(c, 8);
+        case 11: return (double)(int64_t)rd(c, 8);
+        case 12: { uint64_t b = rd(c, 8); double f; memcpy(&f, &b, 8); return f; }
+        default: c->ok = 0; return 0;
+    }
+}
+
+typedef struct { char name[128]; uint32_t type; int64_t ne[4]; int nd; uint64_t off; } tinfo_t;
+
+static const tinfo_t* find_t(const tinfo_t* ti, uint64_t n, const char* name) {
+    for (uint64_t i = 0; i < n; ++i) if (!strcmp(ti[i].name, name)) return &ti[i];
+    return NULL;
+}
+
+static int bind_mat(mat_t* m, const tinfo_t* t, const uint8_t* data_base) {
+    if (!t) return -1;
+    m->type = (int)t->type; m->cols = (int)t->ne[0]; m->rows = t->nd > 1 ? (int)t->ne[1] : 1;
+    m->row_bytes = type_row_bytes(m->type, m->cols);
+    if (!m->row_bytes) return -1;
+    m->data = data_base + t->off;
+    return 0;
+}
+
+void oc_free(void* vm);
+
+void* oc_load(const char* path, int n_ctx) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return NULL;
+    struct stat st; fstat(fd, &st);
+    void* map = mmap(NULL, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return NULL;
+    model_t* m = calloc(1, sizeof(model_t));
+    m->map = map; m->map_len = st.st_size;
+    cur_t c = {(const uint8_t*)map, (const uint8_t*)map + st.st_size, 1};
+    if ((uint32_t)rd(&c, 4) != 0x46554747u) { oc_free(m); return NULL; }
+    rd(&c, 4);
+    uint64_t nt = rd(&c, 8), nkv = rd(&c, 8);
+    uint64_t align = 32;
+    m->eps = 1e-5f; m->rope_base = 10000.f;
+    int n_ctx_train = 2048, rope_dim = 0;
+    for (uint64_t i = 0; i < nkv && c.ok; ++i) {
+        char key[256]; rd_str(&c, key, sizeof key);
+        uint32_t t = (uint32_t)rd(&c, 4);
+        if (t == 8) { rd_str(&c, NULL, 0); continue; }
+        if (t == 9) {
+            uint32_t et = (uint32_t)rd(&c, 4); uint64_t n = rd(&c, 8);
+            if (et == 8) { for (uint64_t j = 0; j < n && c.ok; ++j) rd_str(&c, NULL, 0); }
+            else if (et < 13 && scalar_size[et]) { c.p += n * scalar_size[et]; if (c.p > c.end) c.ok = 0; }
+            else c.ok = 0;
+            continue;
+        }
+        double v = rd_num(&c, t);
+        const char* k = strchr(key, '.'); k = k ? k + 1 : key;
+        if (!strcmp(key, "general.alignment")) align = (uint64_t)v;
+        else if (!strcmp(k, "block_count")) m->n_layer = (int)v;
+        else if (!strcmp(k, "embedding_length")) m->n_embd = (int)v;
+        else if (!strcmp(k, "feed_forward_length")) m->n_ff = (int)v;
+        else if (!strcmp(k, "attention.head_count")) m->n_head = (int)v;
+        else if (!strcmp(k, "attention.head_count_kv")) m->n_kv = (int)v;
+        else if (!strcmp(k, "attention.layer_norm_rms_epsilon")) m->eps = (float)v;
+        else if (!strcmp(k, "rope.freq_base")) m->rope_base = (float)v;
+        else if (!strcmp(k, "rope.dimension_count")) rope_dim = (int)v;
+        else if (!strcmp(k, "context_length")) n_ctx_train = (int)v;
+    }
+    tinfo_t* ti = calloc(nt, sizeof(tinfo_t));
+    for (uint64_t i = 0; i < nt && c.ok; ++i) {
+        rd_str(&c, ti[i].name, sizeof ti[i].name);
+        ti[i].nd = (int)rd(&c, 4);
+        for (int d = 0; d < ti[i].nd && d < 4; ++d) ti[i].ne[d] = (int64_t)rd(&c, 8);
+        ti[i].type = (uint32_t)rd(&c, 4);
+        ti[i].off = rd(&c, 8);
+    }
+    if (!c.ok || !m->n_layer || !m->n_embd || !m->n_head) { free(ti); oc_free(m); return NULL; }
+    if (!m->n_kv) m->n_kv = m->n_head;
+    m->hd = rope_dim ? rope_dim : m->n_embd / m->n_head;
+    m->n_ctx = n_ctx > 0 ? n_ctx : n_ctx_train;
+    size_t off = (size_t)(c.p - (const uint8_t*)map);
+    off = (off + align - 1) / align * align;
+    const uint8_t* base = (const uint8_t*)map + off;
+    int bad = 0;
+    bad |= bind_mat(&m->tok_embd, find_t(ti, nt, "token_embd.weight"), base);
+    const tinfo_t* to = find_t(ti, nt, "output.weight");
+    bad |= bind_mat(&m->output, to ? to : find_t(ti, nt, "token_embd.weight"), base);
+    const tinfo_t* on = find_t(ti, nt, "output_norm.weight");
+    if (!on) bad = 1; else m->output_norm = (const float*)(base + on->off);
+    m->n_vocab = m->tok_embd.rows;
+    m->layers = calloc(m->n_layer, sizeof(layer_t));
+    for (int il = 0; il < m->n_layer && !bad; ++il) {
+        char nm[160];
+        layer_t* L = &m->layers[il];
+        struct { const char* n; mat_t* mm; } it[] = {{"attn_q", &L->wq}, {"attn_k", &L->wk}, {"attn_v", &L->wv}, {"attn_output", &L->wo},
+                                                    {"ffn_gate", &L->wg}, {"ffn_up", &L->wu}, {"ffn_down", &L->wd}};
+        for (int j = 0; j < 7; ++j) { snprintf(nm, sizeof nm, "blk.%d.%s.weight", il, it[j].n); bad |= bind_mat(it[j].mm, find_t(ti, nt, nm), base); }
+        snprintf(nm, sizeof nm, "blk.%d.attn_norm.weight", il);
+        const tinfo_t* a = find_t(ti, nt, nm);
+        snprintf(nm, sizeof nm, "blk.%d.ffn_norm.weight", il);
+        const tinfo_t* f = find_t(ti, nt, nm);
+        if (!a || !f) bad = 1; else { L->attn_norm = (const float*)(base + a->off); L->ffn_norm = (const float*)(base + f->off); }
+    }
+    free(ti);
+    if (bad) { oc_free(m); return NULL; }
+    const int kvd = m->n_kv * m->hd, qd = m->n_head * m->hd;
+    m->kc = malloc((size_t)m->n_layer * m->n_ctx * kvd * 4);
+    m->vc = malloc((size_t)m->n_layer * m->n_ctx * kvd * 4);
+    m->cos_t = malloc((size_t)m->n_ctx * m->hd / 2 * 4);
+    m->sin_t = malloc((size_t)m->n_ctx * m->hd / 2 * 4);
+    for (int p = 0; p < m->n_ctx; ++p)
+        for (int i = 0; i < m->hd / 2; ++i) {
+            float inv = (float)pow((double)m->rope_base, -2.0 * i / m->hd);
+            float ang = (float)p * inv;
+            m->cos_t[(size_t)p * m->hd / 2 + i] = (float)cos((double)ang);
+            m->sin_t[(size_t)p * m->hd / 2 + i] = (float)sin((double)ang);
+        }
+    int big = m->n_ff > m->n_embd ? m->n_ff : m->n_embd;
+    if (qd > big) big = qd;
+    m->x = malloc(m->n_embd * 4); m->xn = malloc(big * 4); m->q = malloc(qd * 4); m->k = malloc(kvd * 4); m->v = malloc(kvd * 4);
+    m->att = malloc(qd * 4); m->g = malloc(m->n_ff * 4); m->u = malloc(m->n_ff * 4); m->h = malloc(m->n_ff * 4); m->y = malloc(big * 4);
+    m->sc = malloc((size_t)m->n_ctx * 4 * 64);
+    m->xq = malloc(big); m->xs = malloc((big / 32 + 1) * 4);
+    return m;
+}
+
+void oc_free(void* vm) {
+    model_t* m = vm;
+    if (!m) return;
+    if (m->map) munmap(m->map, m->map_len);
+    free(m->layers); free(m->kc); free(m->vc); free(m->cos_t); free(m->sin_t);
+    free(m->x); free(m->xn); free(m->q); free(m->k); free(m->v); free(m->att); free(m->g); free(m->u); free(m->h); free(m->y); free(m->sc);
+    free(m->xq); free(m->xs);
+    free(m);
+}
+
+void oc_reset(void* vm) { ((model_t*)vm)->pos = 0; }
+int oc_pos(void* vm) { return ((model_t*)vm)->pos; }
+void oc_info(void* vm, int* o) {
+    model_t* m = vm;
+    o[0] = m->n_layer; o[1] = m->n_embd; o[2] = m->n_head; o[3] = m->n_kv; o[4] = m->hd; o[5] = m->n_ff; o[6] = m->n_vocab; o[7] = m->n_ctx;
+}
+int oc_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---- block decoders (public ggml formats) ------------------------------------------------------ */
+static void q4k_scale_min(const uint8_t* s, int j, int* sc, int* mn) {
+    if (j < 4) { *sc = s[j] & 63; *mn = s[j + 4] & 63; }
+    else { *sc = (s[j + 4] & 0xF) | ((s[j - 4] >> 6) << 4); *mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4); }
+}
+
+static void dequant_row(const uint8_t* row, int type, int cols, float* out) {
+    if (type == T_F32) { memcpy(out, row, (size_t)cols * 4); return; }
+    if (type == T_F16) { for (int i = 0; i < cols; ++i) out[i] = h2f(((const uint16_t*)row)[i]); return; }
+    if (type == T_BF16) { for (int i = 0; i < cols; ++i) { uint32_t b = (uint32_t)((const uint16_t*)row)[i] << 16; memcpy(&out[i], &b, 4); } return; }
+    if (type == T_Q8_0) {
+        for (int b = 0; b < cols / 32; ++b) {
+            const uint8_t* p = row + (size_t)b * 34; float d = h2f(*(const uint16_t*)p);
+            for (int i = 0; i < 32; ++i) out[b * 32 + i] = d * (float)(int8_t)p[2 + i];
+        }
+        return;
+    }
+    if (type == T_Q4_K) {
+        for (int b = 0; b < cols / 256; ++b) {
+            const uint8_t* p = row + (size_t)b * 144; float d = h2f(*(const uint16_t*)p), dm = h2f(*(const uint16_t*)(p + 2));
+            for (int j = 0; j < 8; ++j) {
+                int sc, mn; q4k_scale_min(p + 4, j, &sc, &mn);
+                const uint8_t* qs = p + 16 + (j >> 1) * 32;
+                for (int l = 0; l < 32; ++l) { int q = (j & 1) ? (qs[l] >> 4) : (qs[l] & 0xF); out[b * 256 + j * 32 + l] = d * (float)sc * (float)q - dm * (float)mn; }
+            }
+        }
+        return;
+    }
+    if (type == T_Q6_K) {
+        for (int b = 0; b < cols / 256; ++b) {
+            const uint8_t* p = row + (size_t)b * 210; float d = h2f(*(const uint16_t*)(p + 208));
+            for (int e = 0; e < 256; ++e) {
+                int h = e >> 7, r = e & 127;
+                int ql = (p[h * 64 + (r & 63)] >> (4 * (r >> 6))) & 0xF;
+                int qh = (p[128 + h * 32 + (r & 31)] >> (2 * (r >> 5))) & 3;
+                out[b * 256 + e] = d * (float)(int8_t)p[192 + (e >> 4)] * (float)((ql | (qh << 4)) - 32);
+            }
+        }
+    }
+}
+
+/* exact mode: fp32 dot against the dequantised row (double accumulate) */
+static float row_dot_exact(const uint8_t* row, int type, int cols, const float* x, float* tmp) {
+    dequant_row(row, type, cols, tmp);
+    double a = 0;
+    for (int i = 0; i < cols; ++i) a += (double)tmp[i] * x[i];
+    return (float)a;
+}
+
+/* ggml-style mode: integer dots against int8 activations (per-32 scale xs, sums derived on the fly) */
+static float row_dot_q8(const uint8_t* row, int type, int cols, const int8_t* xq, const float* xs, const float* x) {
+    float acc = 0.f;
+    if (type == T_Q8_0) {
+        for (int b = 0; b < cols / 32; ++b) {
+            const uint8_t* p = row + (size_t)b * 34; const int8_t* w = (const int8_t*)(p + 2); const int8_t* a = xq + b * 32;
+            int s = 0; for (int i = 0; i < 32; ++i) s += (int)w[i] * (int)a[i];
+            acc += h2f(*(const uint16_t*)p) * xs[b] * (float)s;
+        }
+    } else if (type == T_Q4_K) {
+        for (int b = 0; b < cols / 256; ++b) {
+            const uint8_t* p = row + (size_t)b * 144; float d = h2f(*(const uint16_t*)p), dm = h2f(*(const uint16_t*)(p + 2));
+            float sd = 0.f, sm = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                const uint8_t* qs = p + 16 + c * 32; const int8_t* a0 = xq + b * 256 + (2 * c) * 32; const int8_t* a1 = a0 + 32;
+                int s0 = 0, s1 = 0, t0 = 0, t1 = 0;
+                for (int l = 0; l < 32; ++l) { s0 += (int)(qs[l] & 0xF) * a0[l]; s1 += (int)(qs[l] >> 4) * a1[l]; t0 += a0[l]; t1 += a1[l]; }
+                int sc0, mn0, sc1, mn1; q4k_scale_min(p + 4, 2 * c, &sc0, &mn0); q4k_scale_min(p + 4, 2 * c + 1, &sc1, &mn1);
+                const float x0 = xs[b * 8 + 2 * c], x1 = xs[b * 8 + 2 * c + 1];
+                sd += (float)sc0 * x0 * (float)s0 + (float)sc1 * x1 * (float)s1;
+                sm += (float)mn0 * x0 * (float)t0 + (float)mn1 * x1 * (float)t1;
+            }
+            acc += d * sd - dm * sm;
+        }
+    } else if (type == T_Q6_K) {
+        for (int b = 0; b < cols / 256; ++b) {
+            const uint8_t* p = row + (size_t)b * 210; float d = h2f(*(const uint16_t*)(p + 208));
+            const int8_t* sc = (const int8_t*)(p + 192);
+            float sd = 0.f;
+            for (int g = 0; g < 16; ++g) {       /* 16-column groups */
+                int s = 0;
+                for (int i = 0; i < 16; ++i) {
+                    int e = g * 16 + i, h = e >> 7, r = e & 127;
+                    int ql = (p[h * 64 + (r & 63)] >> (4 * (r >> 6))) & 0xF;
+                    int qh = (p[128 + h * 32 + (r & 31)] >> (2 * (r >> 5))) & 3;
+                    s += ((ql | (qh << 4)) - 32) * (int)xq[b * 256 + e];
+                }
+                sd += (float)sc[g] * xs[b * 8 + (g >> 1)] * (float)s;
+            }
+            acc += d * sd;
+        }
+    } else {                                     /* fp weights: plain float dot */
+        if (type == T_F32) { const float* w = (const float*)row; for (int i = 0; i < cols; ++i) acc += w[i] * x[i]; }
+        else if (type == T_F16) { const uint16_t* w = (const uint16_t*)row; for (int i = 0; i < cols; ++i) acc += h2f(w[i]) * x[i]; }
+        else { const uint16_t* w = (const uint16_t*)row; for (int i = 0; i < cols; ++i) { uint32_t bb = (uint32_t)w[i] << 16; float f; memcpy(&f, &bb, 4); acc += f * x[i]; } }
+    }
+    return acc;
+}
+
+static void quant_act(model_t* m, const float* x, int n) {
+    for (int b = 0; b < n / 32; ++b) {
+        float amax = 0.f;
+        for (int i = 0; i < 32; ++i) { float a = fabsf(x[b * 32 + i]); if (a > amax) amax = a; }
+        const float inv = amax > 0.f ? 127.0f / amax : 0.f;
+        m->xs[b] = amax / 127.0f;
+        for (int i = 0; i < 32; ++i) m->xq[b * 32 + i] = (int8_t)lrintf(x[b * 32 + i] * inv);
+    }
+}
+
+static void matvec(model_t* m, const mat_t* w, const float* x, float* y, int mode) {
+    if (mode == 1) quant_act(m, x, w->cols);
+#pragma omp parallel
+    {
+        float* tmp = mode == 0 ? malloc((size_t)w->cols * 4) : NULL;
+#pragma omp for schedule(static)
+        for (int r = 0; r < w->rows; ++r) {
+            const uint8_t* row = w->data + (size_t)r * w->row_bytes;
+            y[r] = mode == 0 ? row_dot_exact(row, w->type, w->cols, x, tmp) : row_dot_q8(row, w->type, w->cols, m->xq, m->xs, x);
+        }
+        free(tmp);
+    }
+}
+
+static void rmsnorm(const float* x, const float* w, int n, float eps, float* y) {
+    double ss = 0; for (int i = 0; i < n; ++i) ss += (double)x[i] * x[i];
+    const float r = (float)(1.0 / sqrt(ss / n + eps));
+    for (int i = 0; i < n; ++i) y[i] = (x[i] * r) * w[i];
+}
+
+static void rope(float* v, int n_heads, int hd, const float* c, const float* s) {
+    for (int h = 0; h < n_heads; ++h)
+        for (int i = 0; i < hd / 2; ++i) {
+            float a = v[h * hd + 2 * i], b = v[h * hd + 2 * i + 1];
+            v[h * hd + 2 * i] = a * c[i] - b * s[i];
+            v[h * hd + 2 * i + 1] = a * s[i] + b * c[i];
+        }
+}
+
+/* one token through all layers; returns 0; logits (may be NULL) get n_vocab floats; hidden (may be
+ * NULL) gets the final residual stream */
+int oc_step(void* vm, int token, int mode, float* logits, float* hidden) {
+    model_t* m = vm;
+    if (token < 0 || token >= m->n_vocab || m->pos >= m->n_ctx) return -1;
+    const int E = m->n_embd, H = m->n_head, KV = m->n_kv, hd = m->hd, kvd = KV * hd, grp = H / KV, pos = m->pos;
+    dequant_row(m->tok_embd.data + (size_t)token * m->tok_embd.row_bytes, m->tok_embd.type, E, m->x);
+    const float* c = m->cos_t + (size_t)pos * hd / 2; const float* s = m->sin_t + (size_t)pos * hd / 2;
+    for (int il = 0; il < m->n_layer; ++il) {
+        layer_t* L = &m->layers[il];
+        rmsnorm(m->x, L->attn_norm, E, m->eps, m->xn);
+        matvec(m, &L->wq, m->xn, m->q, mode);
+        matvec(m, &L->wk, m->xn, m->k, mode);
+        matvec(m, &L->wv, m->xn, m->v, mode);
+        rope(m->q, H, hd, c, s);
+        rope(m->k, KV, hd, c, s);
+        float* kc = m->kc + ((size_t)il * m->n_ctx) * kvd; float* vc = m->vc + ((size_t)il * m->n_ctx) * kvd;
+        for (int i = 0; i < kvd; ++i) { kc[(size_t)pos * kvd + i] = f16_round(m->k[i]); vc[(size_t)pos * kvd + i] = f16_round(m->v[i]); }
+        const float scale = 1.0f / sqrtf((float)hd);
+#pragma omp parallel for schedule(static)
+        for (int h = 0; h < H; ++h) {
+            const int kvh = h / grp;
+            float* sc = m->sc + (size_t)h * m->n_ctx;
+            float mx = -INFINITY;
+            for (int p = 0; p <= pos; ++p) {
+                const float* kr = kc + (size_t)p * kvd + kvh * hd; double a = 0;
+                for (int d = 0; d < hd; ++d) a += (double)m->q[h * hd + d] * kr[d];
+                sc[p] = (float)a * scale; if (sc[p] > mx) mx = sc[p];
+            }
+            double den = 0; for (int p = 0; p <= pos; ++p) { sc[p] = expf(sc[p] - mx); den += sc[p]; }
+            for (int d = 0; d < hd; ++d) {
+                double a = 0; for (int p = 0; p <= pos; ++p) a += (double)sc[p] * vc[(size_t)p * kvd + kvh * hd + d];
+                m->att[h * hd + d] = (float)(a / den);
+            }
+        }
+        matvec(m, &L->wo, m->att, m->y, mode);
+        for (int i = 0; i < E; ++i) m->x[i] += m->y[i];
+        rmsnorm(m->x, L->ffn_norm, E, m->eps, m->xn);
+        matvec(m, &L->wg, m->xn, m->g, mode);
+        matvec(m, &L->wu, m->xn, m->u, mode);
+        for (int i = 0; i < m->n_ff; ++i) m->h[i] = (m->g[i] / (1.0f + expf(-m->g[i]))) * m->u[i];
+        matvec(m, &L->wd, m->h, m->y, mode);
+        for (int i = 0; i < E; ++i) m->x[i] += m->y[i];
+    }
+    if (hidden) memcpy(hidden, m->x, (size_t)E * 4);
+    if (logits) {
+        rmsnorm(m->x, m->output_norm, E, m->eps, m->xn);
+        matvec(m, &m->output, m->xn, logits, mode);
+    }
+    m->pos++;
+    return 0;
+}
+
+/* greedy generate; returns number generated.  logits_buf must hold n_vocab floats. */
+int oc_generate(void* vm, const int* prompt, int n_prompt, int n_predict, int mode, int* out_ids, float* out_lp, float* logits_buf) {
+    model_t* m = vm;
+    m->pos = 0;
+    for (int i = 0; i < n_prompt; ++i)
+        if (oc_step(m, prompt[i], mode, i == n_prompt - 1 ? logits_buf : NULL, NULL)) return -1;
+    for (int g = 0; g < n_predict; ++g) {
+        int best = 0; for (int i = 1; i < m->n_vocab; ++i) if (logits_buf[i] > logits_buf[best]) best = i;
+        double se = 0; for (int i = 0; i < m->n_vocab; ++i) se += exp((double)logits_buf[i] - logits_buf[best]);
+        out_ids[g] = best; if (out_lp) out_lp[g] = (float)(-log(se));
+        if (g + 1 < n_predict && oc_step(m, best, mode, logits_buf, NULL)) return g + 1;
+    }
+    return n_predict;
+}
