@@ -12,9 +12,11 @@
  * turn pinned against gguf-py and transformers.  PARITY UNPINNED w.r.t. the reference itself.
  *
  * act_mode 0: exact -- dequantised fp32 weights x fp32 activations ("mode A", the specification).
- * act_mode 1: ggml-style -- activations quantised to int8 per 32-column block, integer dot
- *             products ("mode B"); this is the fair stand-in for llama.cpp's CPU kernels and is what
- *             bench.py times as the CPU baseline (label: "CPU restatement, not Ollama").
+ * act_mode 1: ggml-style ("mode B") -- activations quantised to int8 the way ggml's CPU backend does
+ *             it ([external] ggml vec_dot pairing: K-quant weights x Q8_K = one scale per 256 columns
+ *             + per-16 sums; Q8_0 weights x Q8_0 = one scale per 32), integer dot products (AVX2
+ *             maddubs/madd when available).  This is the fair stand-in for llama.cpp's CPU kernels and
+ *             is what bench.py times as the CPU baseline (label: "CPU restatement, not Ollama").
  * K/V are rounded to fp16 when cached, like the engine.
  */
 #define _GNU_SOURCE
@@ -29,6 +31,9 @@
 #include <unistd.h>
 #ifdef _OPENMP
 #include <omp.h>
+#endif
+#ifdef __AVX2__
+#include <immintrin.h>
 #endif
 
 enum { T_F32 = 0, T_F16 = 1, T_Q8_0 = 8, T_Q4_K = 12, T_Q6_K = 14, T_BF16 = 30 };
@@ -46,7 +51,8 @@ typedef struct {
     float *cos_t, *sin_t;      /* [n_ctx][hd/2] */
     int pos;
     float *x, *xn, *q, *k, *v, *att, *g, *u, *h, *y, *sc;
-    int8_t* xq; float* xs;     /* int8 activations + per-32 scale */
+    int8_t* xq; float* xs;     /* int8 activations + per-block scale (per 32, or per 256 for K-quants) */
+    int* bs;                   /* per-16 sums of xq (Q8_K bsums) */
 } model_t;
 
 static float h2f(uint16_t h) { _Float16 f; memcpy(&f, &h, 2); return (float)f; }
@@ -202,7 +208,7 @@ void* oc_load(const char* path, int n_ctx) {
     m->x = malloc(m->n_embd * 4); m->xn = malloc(big * 4); m->q = malloc(qd * 4); m->k = malloc(kvd * 4); m->v = malloc(kvd * 4);
     m->att = malloc(qd * 4); m->g = malloc(m->n_ff * 4); m->u = malloc(m->n_ff * 4); m->h = malloc(m->n_ff * 4); m->y = malloc(big * 4);
     m->sc = malloc((size_t)m->n_ctx * 4 * 64);
-    m->xq = malloc(big); m->xs = malloc((big / 32 + 1) * 4);
+    m->xq = malloc(big + 64); m->xs = malloc((big / 32 + 1) * 4); m->bs = malloc((big / 16 + 1) * 4);
     return m;
 }
 
@@ -212,7 +218,7 @@ void oc_free(void* vm) {
     if (m->map) munmap(m->map, m->map_len);
     free(m->layers); free(m->kc); free(m->vc); free(m->cos_t); free(m->sin_t);
     free(m->x); free(m->xn); free(m->q); free(m->k); free(m->v); free(m->att); free(m->g); free(m->u); free(m->h); free(m->y); free(m->sc);
-    free(m->xq); free(m->xs);
+    free(m->xq); free(m->xs); free(m->bs);
     free(m);
 }
 
@@ -279,46 +285,100 @@ static float row_dot_exact(const uint8_t* row, int type, int cols, const float* 
     return (float)a;
 }
 
-/* ggml-style mode: integer dots against int8 activations (per-32 scale xs, sums derived on the fly) */
-static float row_dot_q8(const uint8_t* row, int type, int cols, const int8_t* xq, const float* xs, const float* x) {
+/* ggml-style mode: integer dots against int8 activations.
+ * K-quants: xq quantised per 256 columns (scale xs[b], per-16 sums bs[]); Q8_0: per 32 columns. */
+#ifdef __AVX2__
+static inline int hsum_i32(__m256i v) {
+    __m128i s = _mm_add_epi32(_mm256_castsi256_si128(v), _mm256_extracti128_si256(v, 1));
+    s = _mm_add_epi32(s, _mm_shuffle_epi32(s, 0x4E));
+    s = _mm_add_epi32(s, _mm_shuffle_epi32(s, 0xB1));
+    return _mm_cvtsi128_si32(s);
+}
+#endif
+
+static float row_dot_q8(const uint8_t* row, int type, int cols, const int8_t* xq, const float* xs, const int* bs, const float* x) {
     float acc = 0.f;
     if (type == T_Q8_0) {
         for (int b = 0; b < cols / 32; ++b) {
             const uint8_t* p = row + (size_t)b * 34; const int8_t* w = (const int8_t*)(p + 2); const int8_t* a = xq + b * 32;
-            int s = 0; for (int i = 0; i < 32; ++i) s += (int)w[i] * (int)a[i];
+            int s;
+#ifdef __AVX2__
+            const __m256i wv = _mm256_loadu_si256((const __m256i*)w), av = _mm256_loadu_si256((const __m256i*)a);
+            const __m256i pr = _mm256_maddubs_epi16(_mm256_sign_epi8(wv, wv), _mm256_sign_epi8(av, wv));
+            s = hsum_i32(_mm256_madd_epi16(pr, _mm256_set1_epi16(1)));
+#else
+            s = 0; for (int i = 0; i < 32; ++i) s += (int)w[i] * (int)a[i];
+#endif
             acc += h2f(*(const uint16_t*)p) * xs[b] * (float)s;
         }
     } else if (type == T_Q4_K) {
         for (int b = 0; b < cols / 256; ++b) {
-            const uint8_t* p = row + (size_t)b * 144; float d = h2f(*(const uint16_t*)p), dm = h2f(*(const uint16_t*)(p + 2));
-            float sd = 0.f, sm = 0.f;
+            const uint8_t* p = row + (size_t)b * 144; const float d = h2f(*(const uint16_t*)p), dm = h2f(*(const uint16_t*)(p + 2));
+            const int8_t* a = xq + b * 256; const int* bsum = bs + b * 16;
+            int sumi, summ = 0;
+            int sc[8], mn[8];
+            for (int j = 0; j < 8; ++j) { q4k_scale_min(p + 4, j, &sc[j], &mn[j]); summ += mn[j] * (bsum[2 * j] + bsum[2 * j + 1]); }
+#ifdef __AVX2__
+            __m256i accv = _mm256_setzero_si256();
+            const __m256i m4 = _mm256_set1_epi8(0x0F);
             for (int c = 0; c < 4; ++c) {
-                const uint8_t* qs = p + 16 + c * 32; const int8_t* a0 = xq + b * 256 + (2 * c) * 32; const int8_t* a1 = a0 + 32;
-                int s0 = 0, s1 = 0, t0 = 0, t1 = 0;
-                for (int l = 0; l < 32; ++l) { s0 += (int)(qs[l] & 0xF) * a0[l]; s1 += (int)(qs[l] >> 4) * a1[l]; t0 += a0[l]; t1 += a1[l]; }
-                int sc0, mn0, sc1, mn1; q4k_scale_min(p + 4, 2 * c, &sc0, &mn0); q4k_scale_min(p + 4, 2 * c + 1, &sc1, &mn1);
-                const float x0 = xs[b * 8 + 2 * c], x1 = xs[b * 8 + 2 * c + 1];
-                sd += (float)sc0 * x0 * (float)s0 + (float)sc1 * x1 * (float)s1;
-                sm += (float)mn0 * x0 * (float)t0 + (float)mn1 * x1 * (float)t1;
+                const __m256i q = _mm256_loadu_si256((const __m256i*)(p + 16 + c * 32));
+                const __m256i lo = _mm256_and_si256(q, m4), hi = _mm256_and_si256(_mm256_srli_epi16(q, 4), m4);
+                const __m256i a0 = _mm256_loadu_si256((const __m256i*)(a + 64 * c)), a1 = _mm256_loadu_si256((const __m256i*)(a + 64 * c + 32));
+                accv = _mm256_add_epi32(accv, _mm256_madd_epi16(_mm256_maddubs_epi16(lo, a0), _mm256_set1_epi16((short)sc[2 * c])));
+                accv = _mm256_add_epi32(accv, _mm256_madd_epi16(_mm256_maddubs_epi16(hi, a1), _mm256_set1_epi16((short)sc[2 * c + 1])));
             }
-            acc += d * sd - dm * sm;
+            sumi = hsum_i32(accv);
+#else
+            sumi = 0;
+            for (int c = 0; c < 4; ++c) {
+                const uint8_t* qs = p + 16 + c * 32; const int8_t* a0 = a + 64 * c; const int8_t* a1 = a0 + 32;
+                int s0 = 0, s1 = 0;
+                for (int l = 0; l < 32; ++l) { s0 += (int)(qs[l] & 0xF) * a0[l]; s1 += (int)(qs[l] >> 4) * a1[l]; }
+                sumi += sc[2 * c] * s0 + sc[2 * c + 1] * s1;
+            }
+#endif
+            acc += xs[b] * (d * (float)sumi - dm * (float)summ);
         }
     } else if (type == T_Q6_K) {
         for (int b = 0; b < cols / 256; ++b) {
-            const uint8_t* p = row + (size_t)b * 210; float d = h2f(*(const uint16_t*)(p + 208));
-            const int8_t* sc = (const int8_t*)(p + 192);
-            float sd = 0.f;
-            for (int g = 0; g < 16; ++g) {       /* 16-column groups */
+            const uint8_t* p = row + (size_t)b * 210; const float d = h2f(*(const uint16_t*)(p + 208));
+            const int8_t* sc = (const int8_t*)(p + 192); const int8_t* a = xq + b * 256; const int* bsum = bs + b * 16;
+            int sumi, off = 0;
+            for (int g = 0; g < 16; ++g) off += (int)sc[g] * bsum[g];
+#ifdef __AVX2__
+            __m256i accv = _mm256_setzero_si256();
+            const __m256i m4 = _mm256_set1_epi8(0x0F), m2 = _mm256_set1_epi8(0x03);
+            for (int h = 0; h < 2; ++h) {
+                const __m256i ql0 = _mm256_loadu_si256((const __m256i*)(p + h * 64)), ql1 = _mm256_loadu_si256((const __m256i*)(p + h * 64 + 32));
+                const __m256i qh = _mm256_loadu_si256((const __m256i*)(p + 128 + h * 32));
+                __m256i qv[4];
+                qv[0] = _mm256_or_si256(_mm256_and_si256(ql0, m4), _mm256_slli_epi16(_mm256_and_si256(qh, m2), 4));
+                qv[1] = _mm256_or_si256(_mm256_and_si256(ql1, m4), _mm256_slli_epi16(_mm256_and_si256(_mm256_srli_epi16(qh, 2), m2), 4));
+                qv[2] = _mm256_or_si256(_mm256_and_si256(_mm256_srli_epi16(ql0, 4), m4), _mm256_slli_epi16(_mm256_and_si256(_mm256_srli_epi16(qh, 4), m2), 4));
+                qv[3] = _mm256_or_si256(_mm256_and_si256(_mm256_srli_epi16(ql1, 4), m4), _mm256_slli_epi16(_mm256_and_si256(_mm256_srli_epi16(qh, 6), m2), 4));
+                for (int t = 0; t < 4; ++t) {
+                    const __m256i av = _mm256_loadu_si256((const __m256i*)(a + h * 128 + t * 32));
+                    const short s0 = sc[h * 8 + 2 * t], s1 = sc[h * 8 + 2 * t + 1];
+                    const __m256i scv = _mm256_set_m128i(_mm_set1_epi16(s1), _mm_set1_epi16(s0));
+                    accv = _mm256_add_epi32(accv, _mm256_madd_epi16(_mm256_maddubs_epi16(qv[t], av), scv));
+                }
+            }
+            sumi = hsum_i32(accv);
+#else
+            sumi = 0;
+            for (int g = 0; g < 16; ++g) {
                 int s = 0;
                 for (int i = 0; i < 16; ++i) {
                     int e = g * 16 + i, h = e >> 7, r = e & 127;
                     int ql = (p[h * 64 + (r & 63)] >> (4 * (r >> 6))) & 0xF;
                     int qh = (p[128 + h * 32 + (r & 31)] >> (2 * (r >> 5))) & 3;
-                    s += ((ql | (qh << 4)) - 32) * (int)xq[b * 256 + e];
+                    s += (ql | (qh << 4)) * (int)a[e];
                 }
-                sd += (float)sc[g] * xs[b * 8 + (g >> 1)] * (float)s;
+                sumi += (int)sc[g] * s;
             }
-            acc += d * sd;
+#endif
+            acc += d * xs[b] * (float)(sumi - 32 * off);
         }
     } else {                                     /* fp weights: plain float dot */
         if (type == T_F32) { const float* w = (const float*)row; for (int i = 0; i < cols; ++i) acc += w[i] * x[i]; }
@@ -328,25 +388,28 @@ static float row_dot_q8(const uint8_t* row, int type, int cols, const int8_t* xq
     return acc;
 }
 
-static void quant_act(model_t* m, const float* x, int n) {
-    for (int b = 0; b < n / 32; ++b) {
+/* blk = 32 (Q8_0 pairing) or 256 (Q8_K pairing): d = amax/127, q = rint(x/d); per-16 sums */
+static void quant_act(model_t* m, const float* x, int n, int blk) {
+    for (int b = 0; b < n / blk; ++b) {
         float amax = 0.f;
-        for (int i = 0; i < 32; ++i) { float a = fabsf(x[b * 32 + i]); if (a > amax) amax = a; }
+        for (int i = 0; i < blk; ++i) { float a = fabsf(x[b * blk + i]); if (a > amax) amax = a; }
         const float inv = amax > 0.f ? 127.0f / amax : 0.f;
         m->xs[b] = amax / 127.0f;
-        for (int i = 0; i < 32; ++i) m->xq[b * 32 + i] = (int8_t)lrintf(x[b * 32 + i] * inv);
+        for (int i = 0; i < blk; ++i) m->xq[b * blk + i] = (int8_t)lrintf(x[b * blk + i] * inv);
     }
+    for (int g = 0; g < n / 16; ++g) { int s = 0; for (int i = 0; i < 16; ++i) s += m->xq[g * 16 + i]; m->bs[g] = s; }
 }
 
 static void matvec(model_t* m, const mat_t* w, const float* x, float* y, int mode) {
-    if (mode == 1) quant_act(m, x, w->cols);
+    if (mode == 1 && (w->type == T_Q4_K || w->type == T_Q6_K)) quant_act(m, x, w->cols, 256);
+    else if (mode == 1 && w->type == T_Q8_0) quant_act(m, x, w->cols, 32);
 #pragma omp parallel
     {
         float* tmp = mode == 0 ? malloc((size_t)w->cols * 4) : NULL;
 #pragma omp for schedule(static)
         for (int r = 0; r < w->rows; ++r) {
             const uint8_t* row = w->data + (size_t)r * w->row_bytes;
-            y[r] = mode == 0 ? row_dot_exact(row, w->type, w->cols, x, tmp) : row_dot_q8(row, w->type, w->cols, m->xq, m->xs, x);
+            y[r] = mode == 0 ? row_dot_exact(row, w->type, w->cols, x, tmp) : row_dot_q8(row, w->type, w->cols, m->xq, m->xs, m->bs, x);
         }
         free(tmp);
     }

@@ -18,8 +18,10 @@ Numerics modes
   act="i16"   : x is first snapped to the engine's per-32-block 15-bit fixed point
                 (x ~ sx*(128*hi+lo), hi/lo int8) -- what the CUDA GEMV consumes.  Lets the
                 tests separate "kernel arithmetic wrong" from "activation rounding".
-  act="q8"    : x snapped to int8 per 32-block -- ggml-style activation quantisation
-                ("mode B"); used only to QUANTIFY the divergence a real Ollama would show.
+  act="q8"    : x snapped to int8 per 32-block (the engine's act_bits=8 option).
+  act="ggml"  : x snapped the way ggml's CPU backend pairs activations with each weight type
+                (K-quants: Q8_K, one scale per 256 columns; Q8_0: one per 32) -- "mode B", used
+                to pin the C baseline and to QUANTIFY the divergence a real Ollama would show.
   kv_f16=True : K/V rounded to fp16 when written to the cache, as the engine stores them.
 """
 from __future__ import annotations
@@ -142,7 +144,24 @@ def snap_q8(x: np.ndarray) -> np.ndarray:
     return (v.astype(np.float64) * sx.astype(np.float64)).reshape(np.shape(x))
 
 
-def _snap(x: np.ndarray, act: str) -> np.ndarray:
+def snap_q8k(x: np.ndarray) -> np.ndarray:
+    """ggml Q8_K-style: one int8 scale per 256 columns (d = amax/127)."""
+    x32 = np.asarray(x, dtype=np.float32).reshape(-1, 256)
+    amax = np.abs(x32).max(axis=1, keepdims=True)
+    sx = (amax / np.float32(127.0)).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = np.where(amax > 0, np.float32(127.0) / amax, np.float32(0)).astype(np.float32)
+    v = np.rint(x32 * inv)
+    return (v.astype(np.float64) * sx.astype(np.float64)).reshape(np.shape(x))
+
+
+def _snap(x: np.ndarray, act: str, wtype: Optional[int] = None) -> np.ndarray:
+    if act == "ggml":      # the activation format ggml's CPU backend pairs with each weight type
+        if wtype in (S.Q4_K, S.Q6_K):
+            return snap_q8k(x)
+        if wtype == S.Q8_0:
+            return snap_q8(x)
+        return np.asarray(x, dtype=np.float64)
     if act == "exact":
         return np.asarray(x, dtype=np.float64)
     if act == "i16":
@@ -152,9 +171,9 @@ def _snap(x: np.ndarray, act: str) -> np.ndarray:
     raise ValueError(act)
 
 
-def gemv(w: np.ndarray, x: np.ndarray, act: str = "exact") -> np.ndarray:
+def gemv(w: np.ndarray, x: np.ndarray, act: str = "exact", wtype: Optional[int] = None) -> np.ndarray:
     """y = W @ snap(x); W fp32 exact dequantised values, float64 accumulate."""
-    return w.astype(np.float64) @ _snap(x, act)
+    return w.astype(np.float64) @ _snap(x, act, wtype)
 
 
 # --------------------------------------------------------------------------------------
@@ -217,12 +236,15 @@ class LlamaOracle:
         H, KV, hd = m.n_head, m.n_head_kv, m.head_dim
         x = m.w("token_embd.weight")[token].astype(np.float64)
         pos = self.pos
+
+        def mv(name, vec):
+            return gemv(m.w(name), vec, act, m.raw[name][0])
         for il in range(m.n_layer):
             p = f"blk.{il}."
             h = rmsnorm(x, m.w(p + "attn_norm.weight"), m.rms_eps)
-            q = gemv(m.w(p + "attn_q.weight"), h, act)
-            k = gemv(m.w(p + "attn_k.weight"), h, act)
-            v = gemv(m.w(p + "attn_v.weight"), h, act)
+            q = mv(p + "attn_q.weight", h)
+            k = mv(p + "attn_k.weight", h)
+            v = mv(p + "attn_v.weight", h)
             q = apply_rope(q, pos, H, hd, self.cos, self.sin)
             k = apply_rope(k, pos, KV, hd, self.cos, self.sin)
             self.k[il].append(self._kv_round(k))
@@ -239,11 +261,11 @@ class LlamaOracle:
                 pw = np.exp(s)
                 pw /= pw.sum()
                 att[hh] = pw @ Vc[:, kvh, :]
-            x = x + gemv(m.w(p + "attn_output.weight"), att.reshape(-1), act)
+            x = x + mv(p + "attn_output.weight", att.reshape(-1))
             h2 = rmsnorm(x, m.w(p + "ffn_norm.weight"), m.rms_eps)
-            g = gemv(m.w(p + "ffn_gate.weight"), h2, act)
-            u = gemv(m.w(p + "ffn_up.weight"), h2, act)
-            x = x + gemv(m.w(p + "ffn_down.weight"), silu(g) * u, act)
+            g = mv(p + "ffn_gate.weight", h2)
+            u = mv(p + "ffn_up.weight", h2)
+            x = x + mv(p + "ffn_down.weight", silu(g) * u)
         self.pos += 1
         return x
 
@@ -251,7 +273,7 @@ class LlamaOracle:
         m = self.m
         h = rmsnorm(x, m.w("output_norm.weight"), m.rms_eps)
         wname = "output.weight" if m.has("output.weight") else "token_embd.weight"
-        return gemv(m.w(wname), h, self.act)
+        return gemv(m.w(wname), h, self.act, m.raw[wname][0])
 
     def step(self, token: int) -> np.ndarray:
         return self.logits_from_hidden(self.hidden_step(token))

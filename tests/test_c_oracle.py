@@ -34,9 +34,7 @@ def test_c_port_matches_numpy_oracle(oc, fixture, request):
     h = oc.oc_load(path.encode(), 128)
     assert h
     toks = np.random.Generator(np.random.PCG64(5)).integers(0, om.n_vocab - 3, size=20)
-    for mode, act in ((0, "exact"), (1, "q8")):
-        if fixture == "tiny_f16_gguf" and mode == 1:
-            act = "exact"       # fp weights take the float path in both modes
+    for mode, act in ((0, "exact"), (1, "ggml")):
         oc.oc_reset(h)
         orc = O.LlamaOracle(om, act=act)
         for t in toks:
