@@ -82,6 +82,7 @@ Engine::~Engine() {
     if (g_head_keep_) cudaGraphExecDestroy(g_head_keep_);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     for (void* p : allocs_) cudaFree(p);
+    for (void* p : pf_allocs_) cudaFree(p);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -152,6 +153,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     stage_kb_ = env_int("GL_STAGE_KB", 24);
     smem_kb_ = env_int("GL_SMEM_KB", 110);
     attn_splits_ = std::max(1, std::min(64, env_int("GL_ATTN_SPLITS", 16)));
+    prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
+    prefill_min_ = env_int("GL_PREFILL_MIN", 8);
 
     std::string err = gguf_.open(path);
     if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);
@@ -181,6 +184,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& ev : ev_) CU(cudaEventCreate(&ev));
     CU(gemv_configure());
+    CU(prefill_configure());
 
     // ---- weights -> HBM -------------------------------------------------------------------------
     ST(upload_matrix(*te, tok_embd_, /*native=*/true));
@@ -287,6 +291,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     info_.decode_bytes_per_token = decode_bytes_; info_.device = device_; info_.sm_count = sm_count_;
 
     ST(kv_reset());
+    if (prefill_mode_ != 1) ST(build_prefill_weights());
     if (use_graph_) ST(build_graphs());
     CU(cudaStreamSynchronize(stream_));
     load_ns_ = now_ns() - t0;
@@ -452,22 +457,28 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
         }
     }
     if (with_head) {
-        if (fused_) {
-            GemvParams p{};
-            p.seg[0] = GemvSeg{output_.w, output_.type, output_.rows, output_.row_stride, 0};
-            p.nseg = 1; p.cols = n_embd_; p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
-            ST(enqueue_gemv(s, p, n_launch));
-        } else {
-            CU(rmsnorm_launch(x_, output_norm_, n_embd_, eps_, xn_, s)); ++*n_launch;
-            ST(plain_gemv(s, output_, xn_, logits_, n_launch));
-        }
-        SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_};
-        CU(sample_greedy_launch(sp, pdl && fused_, s));
-        ++*n_launch;
+        ST(enqueue_head(s, keep_logits, n_launch));
     } else {
         CU(advance_launch(st_, pdl && fused_, s));
         ++*n_launch;
     }
+    return {};
+}
+
+Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
+    const bool pdl = use_pdl_;
+    if (fused_) {
+        GemvParams p{};
+        p.seg[0] = GemvSeg{output_.w, output_.type, output_.rows, output_.row_stride, 0};
+        p.nseg = 1; p.cols = n_embd_; p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
+        ST(enqueue_gemv(s, p, n_launch));
+    } else {
+        CU(rmsnorm_launch(x_, output_norm_, n_embd_, eps_, xn_, s)); ++*n_launch;
+        ST(plain_gemv(s, output_, xn_, logits_, n_launch));
+    }
+    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_};
+    CU(sample_greedy_launch(sp, pdl && fused_, s));
+    ++*n_launch;
     return {};
 }
 
@@ -538,12 +549,23 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
         }
     }
     CU(cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_));
-    ST(set_state(0, prompt[0], n_prompt, 0, &so));
-
-    // prefill: n_prompt-1 positions without a head, then the last prompt token produces token 0
-    CU(cudaEventRecord(ev_[0], stream_));
-    ST(run_steps(n_prompt - 1, 0, false));
-    CU(cudaEventRecord(ev_[1], stream_));
+    const bool batched = can_batch_prefill(n_prompt);
+    int prefill_launches = 0;
+    if (batched) {
+        // whole prompt through the tensor-core path; the sampler then moves pos from T-1 to T
+        ST(set_state(n_prompt - 1, prompt[n_prompt - 1], n_prompt, 0, &so));
+        CU(cudaEventRecord(ev_[0], stream_));
+        ST(prefill_batched(n_prompt, &prefill_launches));
+        CU(cudaEventRecord(ev_[1], stream_));
+    } else {
+        // sequential prefill: n_prompt-1 positions without a head, then the last prompt token produces token 0
+        ST(set_state(0, prompt[0], n_prompt, 0, &so));
+        CU(cudaEventRecord(ev_[0], stream_));
+        ST(run_steps(n_prompt - 1, 0, false));
+        CU(cudaEventRecord(ev_[1], stream_));
+        prefill_launches = (n_prompt - 1) * launches_nohead_;
+    }
+    bool first_head_only = batched;
 
     std::vector<int32_t> ids(n_pred);
     std::vector<float> lps(n_pred);
@@ -553,7 +575,14 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
     StepState hs{};
     while (produced < n_pred && !cancelled) {
         const int n = std::min(chunk, n_pred - produced);
-        ST(run_steps(0, n, so.want_logits != 0));
+        int full = n;
+        if (first_head_only) {
+            int dummy = 0;
+            ST(enqueue_head(stream_, so.want_logits != 0, &dummy));
+            full = n - 1;
+            first_head_only = false;
+        }
+        ST(run_steps(0, full, so.want_logits != 0));
         CU(cudaMemcpyAsync(ids.data() + produced, out_ids_ + produced, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
         CU(cudaMemcpyAsync(lps.data() + produced, out_lp_ + produced, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
         CU(cudaMemcpyAsync(&hs, st_, sizeof(hs), cudaMemcpyDeviceToHost, stream_));
@@ -587,7 +616,7 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
         stats->total_duration_ns = now_ns() - t0;
         stats->load_duration_ns = load_ns_;
         stats->done_reason = done_reason;
-        stats->kernel_launches = (n_prompt - 1) * launches_nohead_ + std::max(produced, 1) * launches_head_;
+        stats->kernel_launches = prefill_launches + std::max(produced, 1) * launches_head_;
     }
     return cancelled ? fail(GL_ERR_CANCELLED, "cancelled by token callback") : Status{};
 }
@@ -624,12 +653,20 @@ Status Engine::prefill(const int32_t* ids, int n, float* last_logits) {
     for (int i = 0; i < n; ++i)
         if (ids[i] < 0 || ids[i] >= n_vocab_) return fail(GL_ERR_INVALID, "token id out of range");
     ST(ensure_pages(host_pos_ + n));
-    // sequential prefill: tokens are fed from prompt_ids_ indexed by absolute position
-    CU(cudaMemcpyAsync(prompt_ids_ + host_pos_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
     gl_sample_opts so{};
     so.ignore_eos = 1;
-    ST(set_state(host_pos_, ids[0], host_pos_ + n, 0, &so));
-    ST(run_steps(n - 1, 1, false));
+    if (can_batch_prefill(n)) {
+        int dummy = 0;
+        CU(cudaMemcpyAsync(prompt_ids_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+        ST(set_state(n - 1, ids[n - 1], n, 0, &so));
+        ST(prefill_batched(n, &dummy));
+        ST(enqueue_head(stream_, false, &dummy));
+    } else {
+        // sequential prefill: tokens are fed from prompt_ids_ indexed by absolute position
+        CU(cudaMemcpyAsync(prompt_ids_ + host_pos_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+        ST(set_state(host_pos_, ids[0], host_pos_ + n, 0, &so));
+        ST(run_steps(n - 1, 1, false));
+    }
     if (last_logits) CU(cudaMemcpyAsync(last_logits, logits_, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost, stream_));
     CU(cudaStreamSynchronize(stream_));
     host_pos_ += n;
@@ -639,7 +676,7 @@ Status Engine::prefill(const int32_t* ids, int n, float* last_logits) {
 Status Engine::embed(const int32_t* ids, const int32_t* offs, int n_seq, float* out, gl_gen_stats* stats) {
     CU(cudaSetDevice(device_));
     const int64_t t0 = now_ns();
-    int total = 0;
+    int total = 0, launches = 0;
     std::vector<float> hid(n_embd_), nw(n_embd_);
     CU(cudaMemcpy(nw.data(), output_norm_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost));
     CU(cudaEventRecord(ev_[0], stream_));
@@ -657,14 +694,28 @@ Status Engine::embed(const int32_t* ids, const int32_t* offs, int n_seq, float* 
         ST(set_state(0, sid[0], n, 0, &so));
         // mean pooling of output_norm(hidden) over positions, accumulated on the host in double
         std::vector<double> acc(n_embd_, 0.0);
-        for (int i = 0; i < n; ++i) {
-            ST(run_steps(1, 0, false));
-            CU(cudaMemcpyAsync(hid.data(), x_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost, stream_));
-            CU(cudaStreamSynchronize(stream_));
+        auto pool_row = [&](const float* hrow) {
             double ss = 0;
-            for (int d = 0; d < n_embd_; ++d) ss += (double)hid[d] * hid[d];
+            for (int d = 0; d < n_embd_; ++d) ss += (double)hrow[d] * hrow[d];
             const double rstd = 1.0 / std::sqrt(ss / n_embd_ + (double)eps_);
-            for (int d = 0; d < n_embd_; ++d) acc[d] += hid[d] * rstd * nw[d];
+            for (int d = 0; d < n_embd_; ++d) acc[d] += hrow[d] * rstd * nw[d];
+        };
+        if (can_batch_prefill(n)) {
+            int nl = 0;
+            ST(prefill_batched(n, &nl));
+            launches += nl;
+            std::vector<float> all((size_t)n * n_embd_);
+            CU(cudaMemcpyAsync(all.data(), pf_x_, all.size() * 4, cudaMemcpyDeviceToHost, stream_));
+            CU(cudaStreamSynchronize(stream_));
+            for (int i = 0; i < n; ++i) pool_row(all.data() + (size_t)i * n_embd_);
+        } else {
+            for (int i = 0; i < n; ++i) {
+                ST(run_steps(1, 0, false));
+                CU(cudaMemcpyAsync(hid.data(), x_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost, stream_));
+                CU(cudaStreamSynchronize(stream_));
+                pool_row(hid.data());
+            }
+            launches += n * launches_nohead_;
         }
         double nrm = 0;
         for (int d = 0; d < n_embd_; ++d) { acc[d] /= n; nrm += acc[d] * acc[d]; }
@@ -682,7 +733,7 @@ Status Engine::embed(const int32_t* ids, const int32_t* offs, int n_seq, float* 
         stats->prompt_eval_duration_ns = (int64_t)(ms * 1e6);
         stats->total_duration_ns = now_ns() - t0;
         stats->load_duration_ns = load_ns_;
-        stats->kernel_launches = total * launches_nohead_;
+        stats->kernel_launches = launches;
     }
     return {};
 }

@@ -12,6 +12,7 @@
 #include "../../include/gridllm_native.h"
 #include "gguf_file.h"
 #include "kernels.h"
+#include "prefill.h"
 #include "tokenizer.h"
 
 namespace gl {
@@ -29,6 +30,11 @@ struct LayerWeights {
     float* attn_norm = nullptr;
     float* ffn_norm = nullptr;
     DevMatrix wq, wk, wv, wo, wgate, wup, wdown;
+    // resident 16-bit copies for the batched tensor-core prefill (built on the GPU at load)
+    void* wqkv16 = nullptr;   // [(qd + 2 kvd) x n_embd]
+    void* wo16 = nullptr;     // [n_embd x qd]
+    void* wgu16 = nullptr;    // [2 n_ff x n_embd], rows interleaved 8 gate / 8 up
+    void* wd16 = nullptr;     // [n_embd x n_ff]
 };
 
 struct Status {
@@ -69,6 +75,11 @@ private:
     Status build_graphs();
     Status set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so);
     Status run_steps(int n_nohead, int n_head, bool keep_logits);
+    Status enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch);
+    Status build_prefill_weights();
+    Status ensure_prefill_scratch(int t_pad);
+    Status prefill_batched(int n, int* n_launch);     // tokens already in prompt_ids_[0..n)
+    bool can_batch_prefill(int n) const { return have_w16_ && prefill_mode_ != 1 && host_pos_ == 0 && n >= prefill_min_ && n <= 4096; }
     const DevMatrix* find_matrix(const std::string& name) const;
 
     // model
@@ -88,6 +99,15 @@ private:
     int abits_ = 16;
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
     int stage_kb_ = 24, smem_kb_ = 110, attn_splits_ = 16;
+    int prefill_mode_ = 0, prefill_min_ = 8;
+    bool have_w16_ = false, prefill_bf16_ = false;
+    // prefill scratch (grown on demand)
+    int pf_cap_ = 0;
+    float *pf_x_ = nullptr, *pf_qkv_ = nullptr, *pf_s_ = nullptr;
+    void *pf_xn_ = nullptr, *pf_attn_ = nullptr, *pf_h_ = nullptr;
+    __half *pf_q_ = nullptr, *pf_k_ = nullptr, *pf_vt_ = nullptr, *pf_p_ = nullptr;
+    std::vector<void*> pf_allocs_;
+    int last_prefill_launches_ = 0;
 
     // device state
     cudaStream_t stream_ = nullptr;

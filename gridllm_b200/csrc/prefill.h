@@ -1,0 +1,44 @@
+// Launchers of the batched-prefill kernels (prefill.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gl {
+
+enum GemmEpilogue : int {
+    GEMM_EPI_F32 = 0,      // C fp32 = acc
+    GEMM_EPI_ADD_F32 = 1,  // C fp32 += acc                 (residual add in place)
+    GEMM_EPI_T16 = 2,      // C 16-bit = acc
+    GEMM_EPI_SILU = 3,     // B rows interleaved [8 gate | 8 up]: C16[m][col] = silu(gate) * up
+};
+
+// C[M x N] = A[M x K] * B[N x K]^T, 16-bit inputs (fp16 or bf16), fp32 accumulate; strides in ELEMENTS.
+struct GemmParams {
+    const void* a;
+    const void* b;
+    void* c;
+    int m, n, k;
+    int lda, ldb, ldc;
+    int batch;                 // blockIdx.z
+    long long a_batch_stride;  // elements of A per batch
+    long long b_batch_stride;  // elements of B per (batch / b_batch_div)   (GQA: several query heads share one KV head)
+    long long c_batch_stride;
+    int b_batch_div;
+    int epi;
+    int causal_skip;           // 1: skip tiles entirely above the diagonal (S = Q K^T)
+    int causal_k;              // 1: limit K to the last row of the tile + 1 (O = P V, P lower-triangular)
+};
+
+cudaError_t prefill_configure();   // per device: opt in to the GEMM's dynamic shared memory
+cudaError_t gemm_tn_launch(const GemmParams& p, bool bf16, cudaStream_t s);
+cudaError_t dequant_rows_launch(const uint8_t* src, int type, int rows, int cols, int row_stride, void* dst, int dst_ld, int dst_row0,
+                                int interleave, bool bf16, cudaStream_t s);
+cudaError_t rmsnorm_rows_launch(const float* x, const float* w, int rows, int rows_pad, int n, float eps, void* y, bool bf16, cudaStream_t s);
+cudaError_t rope_split_launch(const float* qkv, int t_rows, int t_pad, int pos0, int n_head, int n_kv, int hd, const float* cos_t,
+                              const float* sin_t, __half* qo, __half* ko, __half* vt, __half* k_cache, __half* v_cache,
+                              const int* page_table, cudaStream_t s);
+cudaError_t softmax_causal_launch(const float* sc, int n_head, int t_rows, int t_pad, float scale, __half* p, cudaStream_t s);
+cudaError_t embed_rows_launch(const uint8_t* w, int type, int cols, int row_bytes, const int* ids, int t_rows, float* x, cudaStream_t s);
+
+}  // namespace gl

@@ -136,11 +136,12 @@ class Engine:
     """One GGUF model resident on one GPU (gl_engine)."""
 
     def __init__(self, gguf_path: str, device: int = 0, max_ctx: int = 0, act_bits: int = 16, use_graph: bool = True,
-                 use_pdl: bool = True):
+                 use_pdl: bool = True, prefill_mode: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         o = EngineOpts()
         o.max_ctx, o.act_bits, o.use_graph, o.use_pdl = max_ctx, act_bits, int(use_graph), int(use_pdl)
+        o.prefill_mode = prefill_mode   # 0 auto (batched tensor-core prefill), 1 sequential decode steps
         _check(self._lib.gl_engine_create(gguf_path.encode(), device, C.byref(o), C.byref(self._h)))
         self.info = ModelInfo()
         _check(self._lib.gl_engine_info(self._h, C.byref(self.info)))
