@@ -17,7 +17,8 @@ struct StepState {
     int done;          // 1 once a stop token was sampled (and !ignore_eos): later steps are no-ops
     int ignore_eos;
     int n_stop;
-    int stop_ids[9];
+    int stop_ids[8];
+    unsigned bar_base;  // epoch of the persistent kernel's grid barrier (decode_mega.cu)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

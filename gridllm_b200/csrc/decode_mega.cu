@@ -1,0 +1,384 @@
+// Persistent decode kernel: the WHOLE decode step (and several steps back to back) in one cooperative
+// launch, one CTA per SM.  Replaces the 163 dependent launches of the per-op path: at ~0.7 ms of HBM
+// traffic per token, launch + ramp + drain of every small kernel was costing more than the traffic.
+//
+//   producer warp : walks the phase table of the token (QKV, O, gate/up, down of every layer, lm_head) and
+//                   streams this CTA's weight rows into the shared-memory ring with 1-D TMA bulk copies.  It
+//                   never waits for a grid barrier -- weights do not depend on activations -- so while the
+//                   consumers synchronise, the ring fills with the NEXT phase's rows and HBM stays busy.
+//   consumer warps: phase by phase: fused prologue (RMSNorm + activation snap), dp4a block decode from the
+//                   ring, fused epilogue; split-KV paged attention; greedy sampling; a grid-wide barrier
+//                   (one atomic + acquire spin per CTA) between phases.
+//
+// Reference call site replaced: the decode loop inside Ollama behind OllamaService.generate*Response
+// (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237).
+#include "decode_mega.h"
+#include "gemv_core.cuh"
+
+namespace gl {
+
+namespace {
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all consumer threads of every CTA call this the same number of times
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int tid) {
+    named_bar_sync(1, NCT);
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned spins = 0;
+        while ((int)(ld_acquire_u32(counter) - target) < 0) {
+            if (++spins > (1u << 28)) __trap();
+        }
+        __threadfence();
+    }
+    named_bar_sync(1, NCT);
+}
+
+__device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int type, int c) {
+    switch (type) {
+        case T_F32: return reinterpret_cast<const float*>(row)[c];
+        case T_F16: return __half2float(reinterpret_cast<const __half*>(row)[c]);
+        case T_BF16: return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(row)[c] << 16);
+        case T_Q8_0: {
+            const uint8_t* b = row + (size_t)(c >> 5) * 34;
+            return half_bits_to_float(*reinterpret_cast<const uint16_t*>(b)) * (float)(int8_t)b[2 + (c & 31)];
+        }
+        case T_Q4_K: {
+            const uint8_t* b = row + (size_t)(c >> 8) * 144;
+            const int e = c & 255, sub = e >> 5, l = e & 31;
+            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b));
+            const float dmin = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 2));
+            const uint8_t* sc = b + 4;
+            int s, m;
+            if (sub < 4) { s = sc[sub] & 63; m = sc[4 + sub] & 63; }
+            else { s = (sc[4 + sub] & 0xF) | ((sc[sub - 4] >> 6) << 4); m = (sc[4 + sub] >> 4) | ((sc[sub] >> 6) << 4); }
+            const uint8_t qb = b[16 + (sub >> 1) * 32 + l];
+            const int q = (sub & 1) ? (qb >> 4) : (qb & 0xF);
+            return d * (float)s * (float)q - dmin * (float)m;
+        }
+        case T_Q6_K: {
+            const uint8_t* b = row + (size_t)(c >> 8) * 210;
+            const int e = c & 255, h = e >> 7, r = e & 127;
+            const int qlv = (b[h * 64 + (r & 63)] >> (4 * (r >> 6))) & 0xF;
+            const int qhv = (b[128 + h * 32 + (r & 31)] >> (2 * (r >> 5))) & 3;
+            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 208));
+            return d * (float)(int8_t)b[192 + (e >> 4)] * (float)((qlv | (qhv << 4)) - 32);
+        }
+        default: return 0.f;
+    }
+}
+
+// ---- split-KV paged attention for one (kv head, split) item; K/V rows read straight from HBM/L2 ----------
+template <int DPL>
+__device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc, const __half* vc, int item, int warp, int lane,
+                                          int tid, int* smem_flag) {
+    constexpr int HD = DPL * 32;
+    const int n_splits = mp.attn_splits;
+    const int kvh = item / n_splits, split = item % n_splits;
+    const int grp = mp.n_head / mp.n_kv;
+    const int head = kvh * grp + warp;
+    const bool active = warp < grp;
+    const int L = __ldcg(&mp.st->pos) + 1;
+    const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+    const int pps = (n_pages + n_splits - 1) / n_splits;
+    const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
+    if (active) {
+        float q[DPL], o[DPL];
+        const float* qp = mp.q + (size_t)head * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) { q[d] = __ldcg(qp + d) * mp.attn_scale; o[d] = 0.f; }
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int pg = pg0; pg < pg1; ++pg) {
+            const int page = __ldcg(mp.page_table + pg);
+            const size_t base = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD + lane * DPL;
+            const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
+            float sc[KV_PAGE_TOKENS];
+#pragma unroll
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {       // 16 independent loads in flight per lane
+                float a = 0.f;
+                if (j < npos) {
+                    if (DPL == 4) {
+                        const uint2 kk = __ldcg(reinterpret_cast<const uint2*>(kc + base + (size_t)j * HD));
+                        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk.x));
+                        const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk.y));
+                        a = q[0] * k0.x + q[1] * k0.y + q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
+                    } else {
+                        const unsigned kk = __ldcg(reinterpret_cast<const unsigned*>(kc + base + (size_t)j * HD));
+                        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk));
+                        a = q[0] * k0.x + q[1] * k0.y;
+                    }
+                }
+                sc[j] = a;
+            }
+            float m_t = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+                sc[j] = warp_sum(sc[j]);
+                if (j < npos) m_t = fmaxf(m_t, sc[j]);
+            }
+            const float m_new = fmaxf(m_run, m_t);
+            const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+            l_run *= corr;
+#pragma unroll
+            for (int d = 0; d < DPL; ++d) o[d] *= corr;
+#pragma unroll
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+                if (j < npos) {
+                    const float w = expf(sc[j] - m_new);
+                    l_run += w;
+                    if (DPL == 4) {
+                        const uint2 vv = __ldcg(reinterpret_cast<const uint2*>(vc + base + (size_t)j * HD));
+                        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x));
+                        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
+                        o[0] += w * v0.x; o[1] += w * v0.y; o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
+                    } else {
+                        const unsigned vv = __ldcg(reinterpret_cast<const unsigned*>(vc + base + (size_t)j * HD));
+                        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv));
+                        o[0] += w * v0.x; o[1] += w * v0.y;
+                    }
+                }
+            }
+            m_run = m_new;
+        }
+        float* po = mp.part_o + ((size_t)head * n_splits + split) * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) po[d] = o[d];
+        if (lane == 0) {
+            mp.part_ml[((size_t)head * n_splits + split) * 2] = m_run;
+            mp.part_ml[((size_t)head * n_splits + split) * 2 + 1] = l_run;
+        }
+    }
+    __threadfence();
+    named_bar_sync(1, NCT);
+    if (tid == 0) {
+        const unsigned ticket = atomicAdd(mp.attn_counters + kvh, 1u);
+        const int last = (ticket == (unsigned)n_splits - 1);
+        if (last) mp.attn_counters[kvh] = 0;
+        *smem_flag = last;
+    }
+    named_bar_sync(1, NCT);
+    if (*smem_flag && active) {
+        __threadfence();
+        float M = -INFINITY;
+        for (int s = 0; s < n_splits; ++s) M = fmaxf(M, __ldcg(mp.part_ml + ((size_t)head * n_splits + s) * 2));
+        float den = 0.f, acc[DPL];
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
+        for (int s = 0; s < n_splits; ++s) {
+            const float ms = __ldcg(mp.part_ml + ((size_t)head * n_splits + s) * 2);
+            if (ms == -INFINITY) continue;
+            const float ls = __ldcg(mp.part_ml + ((size_t)head * n_splits + s) * 2 + 1);
+            const float w = expf(ms - M);
+            den += w * ls;
+            const float* po = mp.part_o + ((size_t)head * n_splits + s) * HD + lane * DPL;
+#pragma unroll
+            for (int d = 0; d < DPL; ++d) acc[d] += w * __ldcg(po + d);
+        }
+        const float inv = 1.0f / den;
+        float* out = mp.attn_out + (size_t)head * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) out[d] = acc[d] * inv;
+    }
+}
+
+template <int ABITS>
+__global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaParams mp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int fixed = gemv_fixed_smem(mp.max_cols);
+    GemvParams* sdesc = reinterpret_cast<GemvParams*>(smem + fixed);            // phase descriptor, consumer copy
+    int* sflag = reinterpret_cast<int*>(smem + fixed + 256);
+    float* sstat = reinterpret_cast<float*>(smem + fixed + 256 + 16);            // 3 x NCW floats
+    Ring ring;
+    ring.full = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+    ring.empty = ring.full + GEMV_MAX_STAGES;
+    ring.slots = smem + fixed + 512;
+    ring.n_slots = mp.n_slots;
+    ring.slot_bytes = mp.slot_bytes;
+    ring.st = 0;
+    ring.ph = 0;
+    if (tid == 0) {
+        for (int i = 0; i < mp.n_slots; ++i) {
+            mbar_init(&ring.full[i], 1);
+            mbar_init(&ring.empty[i], NCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ============ producer: every weight phase of every step, never blocked by grid barriers ============
+        if (lane == 0) {
+            for (int step = 0; step < mp.n_steps; ++step)
+                for (int ph = 0; ph < mp.n_phases; ++ph) {
+                    const MegaPhase& P = mp.phases[ph];
+                    if (P.kind == PH_GEMV) gemv_produce(P.g, ring, cta, G);
+                }
+        }
+        return;
+    }
+
+    // ============ consumers ==================================================================================
+    StepState* st = mp.st;
+    const unsigned bar_base = __ldcg(&st->bar_base);
+    unsigned nbar = 0;
+    XUnit xr;
+    for (int step = 0; step < mp.n_steps; ++step) {
+        // ---- token embedding (CTA 0) ----------------------------------------------------------------------
+        if (cta == 0) {
+            int tok;
+            {
+                const int pos = __ldcg(&st->pos), np = __ldcg(&st->n_prompt);
+                tok = __ldcg(&st->token);
+                if (pos < np) tok = __ldcg(mp.prompt_ids + pos);
+            }
+            const uint8_t* row = mp.embd_w + (size_t)tok * mp.embd_row_bytes;
+            for (int c = tid; c < mp.n_embd; c += NCT) mp.x[c] = dequant_native_elem(row, mp.embd_type, c);
+        }
+        ++nbar;
+        grid_barrier(mp.bar_counter, bar_base + nbar * G, tid);
+
+        for (int ph = 0; ph < mp.n_phases; ++ph) {
+            const MegaPhase& P = mp.phases[ph];
+            const int kind = P.kind;
+            if (kind == PH_GEMV) {
+                // stage the descriptor in shared memory (it is read many times in the row loop)
+                if (tid < (int)(sizeof(GemvParams) / 4)) reinterpret_cast<uint32_t*>(sdesc)[tid] = reinterpret_cast<const uint32_t*>(&P.g)[tid];
+                named_bar_sync(1, NCT);
+                gemv_prologue<ABITS>(*sdesc, smem, tid, xr);
+                gemv_consume<ABITS>(*sdesc, ring, smem, tid, xr, cta, G);
+                if (P.flags & PHF_HEAD) {
+                    // per-CTA softmax statistics over the logits rows this CTA produced
+                    named_bar_sync(1, NCT);
+                    const WorkRange wr = cta_range(sdesc->seg[0].rows, 1, cta, G);
+                    float best = -INFINITY;
+                    int bi = 0x7fffffff;
+                    for (int i = wr.a + tid; i < wr.b; i += NCT) {
+                        const float v = __ldcg(mp.logits + i);
+                        if (v > best) { best = v; bi = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                    }
+                    if (lane == 0) { sstat[warp] = best; reinterpret_cast<int*>(sstat)[NCW + warp] = bi; }
+                    named_bar_sync(1, NCT);
+                    best = sstat[0]; bi = reinterpret_cast<int*>(sstat)[NCW];
+                    for (int w = 1; w < NCW; ++w) {
+                        const float ov = sstat[w];
+                        const int oi = reinterpret_cast<int*>(sstat)[NCW + w];
+                        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                    }
+                    float s = 0.f;
+                    for (int i = wr.a + tid; i < wr.b; i += NCT) s += expf(__ldcg(mp.logits + i) - best);
+                    s = warp_sum(s);
+                    if (lane == 0) sstat[2 * NCW + warp] = s;
+                    named_bar_sync(1, NCT);
+                    if (tid == 0) {
+                        float tot = 0.f;
+                        for (int w = 0; w < NCW; ++w) tot += sstat[2 * NCW + w];
+                        mp.head_part[cta * 4 + 0] = best;
+                        reinterpret_cast<int*>(mp.head_part)[cta * 4 + 1] = bi;
+                        mp.head_part[cta * 4 + 2] = tot;
+                    }
+                    if (mp.logits_keep != nullptr) {
+                        const int oi = __ldcg(&st->out_idx);
+                        if (!__ldcg(&st->done) && oi < mp.max_out) {
+                            float* dst = mp.logits_keep + (size_t)oi * sdesc->seg[0].rows;
+                            for (int i = wr.a + tid; i < wr.b; i += NCT) dst[i] = __ldcg(mp.logits + i);
+                        }
+                    }
+                }
+            } else if (kind == PH_ATTN) {
+                const int n_items = mp.n_kv * mp.attn_splits;
+                if (cta < n_items) {
+                    if (mp.head_dim == 128) attn_item<4>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
+                    else attn_item<2>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
+                }
+            }
+            ++nbar;
+            grid_barrier(mp.bar_counter, bar_base + nbar * G, tid);
+        }
+
+        // ---- sampling / state advance (CTA 0), published to everyone by the barrier at the top of the next step
+        if (cta == 0 && warp == 0) {
+            if (mp.with_head) {
+                float best = -INFINITY, sum = 0.f;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < G; c += 32) {
+                    const float m = __ldcg(mp.head_part + c * 4);
+                    const int ix = __ldcg(reinterpret_cast<const int*>(mp.head_part) + c * 4 + 1);
+                    if (m > best || (m == best && ix < bi)) { best = m; bi = ix; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                for (int c = lane; c < G; c += 32) {
+                    const float m = __ldcg(mp.head_part + c * 4);
+                    const float sc = __ldcg(mp.head_part + c * 4 + 2);
+                    if (m > -INFINITY) sum += sc * expf(m - best);
+                }
+                sum = warp_sum(sum);
+                if (lane == 0 && !__ldcg(&st->done)) {
+                    const int oi = __ldcg(&st->out_idx);
+                    if (oi < mp.max_out) {
+                        mp.out_ids[oi] = bi;
+                        mp.out_logprobs[oi] = -logf(sum);
+                    }
+                    st->token = bi;
+                    st->pos = __ldcg(&st->pos) + 1;
+                    st->out_idx = oi + 1;
+                    if (!st->ignore_eos) {
+                        for (int k = 0; k < st->n_stop; ++k)
+                            if (st->stop_ids[k] == bi) st->done = 1;
+                    }
+                }
+            } else if (lane == 0) {
+                st->pos = __ldcg(&st->pos) + 1;
+            }
+        }
+        if (cta == 0) named_bar_sync(1, NCT);     // state written before CTA 0 starts the next embedding
+    }
+    if (cta == 0 && tid == 0) st->bar_base = bar_base + nbar * G;
+}
+
+}  // namespace
+
+size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes) {
+    return (size_t)gemv_fixed_smem(max_cols) + 512 + (size_t)n_slots * slot_bytes;
+}
+
+cudaError_t mega_configure() {
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(decode_mega_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t mega_launch(const MegaParams& mp, int abits, int n_ctas, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    cfg.blockDim = dim3(GEMV_THREADS);
+    cfg.dynamicSmemBytes = mega_smem_bytes(mp.max_cols, mp.n_slots, mp.slot_bytes);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barrier depends on it
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (abits == 16) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<16>, mp);
+    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<8>, mp);
+}
+
+}  // namespace gl

@@ -1,0 +1,53 @@
+// Persistent decode-step kernel (decode_mega.cu): phase table + launch interface.
+#pragma once
+#include "kernels.h"
+
+namespace gl {
+
+enum MegaPhaseKind : int { PH_GEMV = 1, PH_ATTN = 2 };
+enum MegaPhaseFlags : int { PHF_HEAD = 1 };   // lm_head: also produce per-CTA softmax statistics
+
+struct alignas(16) MegaPhase {
+    int kind;
+    int flags;
+    int pad[2];
+    GemvParams g;          // PH_GEMV: the whole work description; PH_ATTN: k_cache / v_cache of the layer
+};
+
+struct MegaParams {
+    const MegaPhase* phases;   // device memory, n_phases entries (one token)
+    int n_phases;
+    int n_steps;               // tokens per launch
+    int with_head;             // 1: lm_head + greedy sample each step; 0: sequential-prefill step (pos += 1)
+    StepState* st;
+    unsigned* bar_counter;     // grid barrier, monotonic (StepState::bar_base carries the epoch)
+    const int* prompt_ids;
+    // embedding gather (token_embd in native GGUF layout)
+    const uint8_t* embd_w;
+    int embd_type, embd_row_bytes, n_embd;
+    float* x;                  // residual stream [n_embd]
+    // attention
+    const float* q;
+    float* attn_out;
+    float* part_o;
+    float* part_ml;
+    unsigned* attn_counters;
+    const int* page_table;
+    int n_head, n_kv, head_dim, attn_splits;
+    float attn_scale;
+    // sampling
+    const float* logits;
+    float* head_part;          // [n_ctas][4]: max, argmax (int bits), sum exp
+    int* out_ids;
+    float* out_logprobs;
+    float* logits_keep;
+    int max_out;
+    // ring
+    int n_slots, slot_bytes, max_cols;
+};
+
+size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes);
+cudaError_t mega_configure();
+cudaError_t mega_launch(const MegaParams& mp, int abits, int n_ctas, cudaStream_t s);
+
+}  // namespace gl

@@ -292,7 +292,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
 
     ST(kv_reset());
     if (prefill_mode_ != 1) ST(build_prefill_weights());
-    if (use_graph_) ST(build_graphs());
+    if (fused_ && all_quant_ && env_int("GL_MEGA", 1) != 0) ST(build_mega());
+    if (use_graph_ && !use_mega_) ST(build_graphs());
     CU(cudaStreamSynchronize(stream_));
     load_ns_ = now_ns() - t0;
     return {};
@@ -355,8 +356,10 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
     if (so && !so->ignore_eos) {
         if (tok_.eos >= 0) h.stop_ids[h.n_stop++] = tok_.eos;
         if (tok_.eot >= 0 && tok_.eot != tok_.eos) h.stop_ids[h.n_stop++] = tok_.eot;
-        for (int i = 0; i < so->n_stop_ids && h.n_stop < 9; ++i) h.stop_ids[h.n_stop++] = so->stop_ids[i];
+        for (int i = 0; i < so->n_stop_ids && h.n_stop < 8; ++i) h.stop_ids[h.n_stop++] = so->stop_ids[i];
     }
+    h.bar_base = 0;
+    if (bar_counter_) CU(cudaMemsetAsync(bar_counter_, 0, 4, stream_));
     CU(cudaMemcpyAsync(st_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
     CU(cudaStreamSynchronize(stream_));     // h is on the stack
     return {};
@@ -502,6 +505,11 @@ Status Engine::build_graphs() {
 
 Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
     int dummy = 0;
+    if (use_mega_) {
+        if (n_nohead > 0) ST(launch_mega(n_nohead, false, false));
+        if (n_head > 0) ST(launch_mega(n_head, true, keep_logits));
+        return {};
+    }
     if (keep_logits && use_graph_ && !g_head_keep_) {
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
@@ -521,6 +529,104 @@ Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
         if (use_graph_) CU(cudaGraphLaunch(keep_logits ? g_head_keep_ : g_head_, stream_));
         else ST(enqueue_step(stream_, true, keep_logits, &dummy));
     }
+    return {};
+}
+
+Status Engine::build_mega() {
+    CU(mega_configure());
+    mega_max_cols_ = std::max(n_embd_, std::max(n_ff_, n_head_ * hd_));
+    if (mega_max_cols_ % UNIT_COLS || mega_max_cols_ > 32768) return {};      // outside the kernel envelope: per-op path
+    const int slot_kb = env_int("GL_MEGA_SLOT_KB", 36);
+    mega_slot_bytes_ = slot_kb * 1024;
+    const size_t fixed = mega_smem_bytes(mega_max_cols_, 0, 0);
+    const size_t budget = (size_t)env_int("GL_MEGA_SMEM_KB", 224) * 1024;
+    if (fixed + 2 * (size_t)mega_slot_bytes_ > budget) return {};
+    mega_slots_ = (int)std::min<size_t>(GEMV_MAX_STAGES, (budget - fixed) / mega_slot_bytes_);
+    mega_slots_ = std::min(mega_slots_, env_int("GL_MEGA_SLOTS", GEMV_MAX_STAGES));
+    if (mega_slots_ < 2) return {};
+    std::vector<MegaPhase> ph;
+    auto add_gemv = [&](GemvParams g, int flags) -> bool {
+        g.n_stages = mega_slots_;
+        g.stage_bytes = mega_slot_bytes_;
+        if (!gemv_plan(g)) return false;
+        MegaPhase m{};
+        m.kind = PH_GEMV; m.flags = flags; m.g = g;
+        ph.push_back(m);
+        return true;
+    };
+    for (int il = 0; il < n_layer_; ++il) {
+        const LayerWeights& L = layers_[il];
+        __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
+        __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
+        GemvParams p{};
+        p.seg[0] = GemvSeg{L.wq.w, L.wq.type, L.wq.rows, L.wq.row_stride, 0};
+        p.seg[1] = GemvSeg{L.wk.w, L.wk.type, L.wk.rows, L.wk.row_stride, 0};
+        p.seg[2] = GemvSeg{L.wv.w, L.wv.type, L.wv.rows, L.wv.row_stride, 0};
+        p.nseg = 3; p.cols = n_embd_; p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
+        p.rope_cos = rope_cos_; p.rope_sin = rope_sin_; p.head_dim = hd_; p.n_kv_heads = n_kv_;
+        p.k_cache = kc; p.v_cache = vc; p.page_table = page_table_; p.st = st_;
+        if (!add_gemv(p, 0)) return {};
+        MegaPhase a{};
+        a.kind = PH_ATTN; a.g.k_cache = kc; a.g.v_cache = vc;
+        ph.push_back(a);
+        GemvParams o{};
+        o.seg[0] = GemvSeg{L.wo.w, L.wo.type, L.wo.rows, L.wo.row_stride, 0};
+        o.nseg = 1; o.cols = n_head_ * hd_; o.x = attn_; o.epi = EPI_ADD; o.out = x_; o.resid = x_; o.st = st_;
+        if (!add_gemv(o, 0)) return {};
+        if (L.wgate.type != L.wup.type) return {};
+        GemvParams g{};
+        g.seg[0] = GemvSeg{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.row_stride, 0};
+        g.seg[1] = GemvSeg{L.wup.w, L.wup.type, L.wup.rows, L.wup.row_stride, 0};
+        g.nseg = 2; g.pair = 1; g.cols = n_embd_; g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
+        if (!add_gemv(g, 0)) return {};
+        GemvParams d{};
+        d.seg[0] = GemvSeg{L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.row_stride, 0};
+        d.nseg = 1; d.cols = n_ff_; d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
+        if (!add_gemv(d, 0)) return {};
+    }
+    mega_n_nohead_ = (int)ph.size();
+    {
+        GemvParams p{};
+        p.seg[0] = GemvSeg{output_.w, output_.type, output_.rows, output_.row_stride, 0};
+        p.nseg = 1; p.cols = n_embd_; p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
+        if (!add_gemv(p, PHF_HEAD)) return {};
+    }
+    mega_n_head_ = (int)ph.size();
+    CU(cudaMalloc((void**)&mega_head_, ph.size() * sizeof(MegaPhase)));
+    allocs_.push_back(mega_head_);
+    CU(cudaMemcpy(mega_head_, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    mega_nohead_ = mega_head_;          // same table, shorter count
+    CU(cudaMalloc((void**)&bar_counter_, 64));
+    allocs_.push_back(bar_counter_);
+    CU(cudaMemset(bar_counter_, 0, 64));
+    CU(cudaMalloc((void**)&head_part_, (size_t)sm_count_ * 16));
+    allocs_.push_back(head_part_);
+    CU(cudaMemset(head_part_, 0, (size_t)sm_count_ * 16));
+    use_mega_ = true;
+    launches_head_ = 1;
+    launches_nohead_ = 1;
+    return {};
+}
+
+Status Engine::launch_mega(int n_steps, bool with_head, bool keep_logits) {
+    MegaParams mp{};
+    mp.phases = mega_head_;
+    mp.n_phases = with_head ? mega_n_head_ : mega_n_nohead_;
+    mp.n_steps = n_steps;
+    mp.with_head = with_head ? 1 : 0;
+    mp.st = st_; mp.bar_counter = bar_counter_; mp.prompt_ids = prompt_ids_;
+    mp.embd_w = tok_embd_.w; mp.embd_type = tok_embd_.type; mp.embd_row_bytes = tok_embd_.row_stride; mp.n_embd = n_embd_;
+    mp.x = x_; mp.q = q_; mp.attn_out = attn_; mp.part_o = part_o_; mp.part_ml = part_ml_; mp.attn_counters = counters_;
+    mp.page_table = page_table_;
+    mp.n_head = n_head_; mp.n_kv = n_kv_; mp.head_dim = hd_;
+    mp.attn_splits = std::max(1, std::min(attn_splits_, sm_count_ / n_kv_));
+    mp.attn_scale = 1.0f / std::sqrt((float)hd_);
+    mp.logits = logits_; mp.head_part = head_part_; mp.out_ids = out_ids_; mp.out_logprobs = out_lp_;
+    mp.logits_keep = keep_logits ? logits_keep_ : nullptr;
+    mp.max_out = keep_logits ? keep_cap_ : max_out_;
+    mp.n_slots = mega_slots_; mp.slot_bytes = mega_slot_bytes_; mp.max_cols = mega_max_cols_;
+    CU(mega_launch(mp, abits_, sm_count_, stream_));
+    ++mega_launches_;
     return {};
 }
 
@@ -551,6 +657,7 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
     CU(cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_));
     const bool batched = can_batch_prefill(n_prompt);
     int prefill_launches = 0;
+    const int mega0 = mega_launches_;
     if (batched) {
         // whole prompt through the tensor-core path; the sampler then moves pos from T-1 to T
         ST(set_state(n_prompt - 1, prompt[n_prompt - 1], n_prompt, 0, &so));
@@ -563,7 +670,7 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
         CU(cudaEventRecord(ev_[0], stream_));
         ST(run_steps(n_prompt - 1, 0, false));
         CU(cudaEventRecord(ev_[1], stream_));
-        prefill_launches = (n_prompt - 1) * launches_nohead_;
+        prefill_launches = use_mega_ ? 0 : (n_prompt - 1) * launches_nohead_;
     }
     bool first_head_only = batched;
 
@@ -616,7 +723,8 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
         stats->total_duration_ns = now_ns() - t0;
         stats->load_duration_ns = load_ns_;
         stats->done_reason = done_reason;
-        stats->kernel_launches = prefill_launches + std::max(produced, 1) * launches_head_;
+        stats->kernel_launches = use_mega_ ? prefill_launches + (mega_launches_ - mega0) + (batched ? 2 : 0)
+                                           : prefill_launches + std::max(produced, 1) * launches_head_;
     }
     return cancelled ? fail(GL_ERR_CANCELLED, "cancelled by token callback") : Status{};
 }

@@ -13,6 +13,7 @@
 #include "gguf_file.h"
 #include "kernels.h"
 #include "prefill.h"
+#include "decode_mega.h"
 #include "tokenizer.h"
 
 namespace gl {
@@ -77,6 +78,8 @@ private:
     Status run_steps(int n_nohead, int n_head, bool keep_logits);
     Status enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch);
     Status build_prefill_weights();
+    Status build_mega();
+    Status launch_mega(int n_steps, bool with_head, bool keep_logits);
     Status ensure_prefill_scratch(int t_pad);
     Status prefill_batched(int n, int* n_launch);     // tokens already in prompt_ids_[0..n)
     bool can_batch_prefill(int n) const { return have_w16_ && prefill_mode_ != 1 && host_pos_ == 0 && n >= prefill_min_ && n <= 4096; }
@@ -108,6 +111,13 @@ private:
     __half *pf_q_ = nullptr, *pf_k_ = nullptr, *pf_vt_ = nullptr, *pf_p_ = nullptr;
     std::vector<void*> pf_allocs_;
     int last_prefill_launches_ = 0;
+    // persistent decode kernel
+    bool use_mega_ = false;
+    MegaPhase *mega_head_ = nullptr, *mega_nohead_ = nullptr;
+    int mega_n_head_ = 0, mega_n_nohead_ = 0, mega_slots_ = 0, mega_slot_bytes_ = 0, mega_max_cols_ = 0;
+    unsigned* bar_counter_ = nullptr;
+    float* head_part_ = nullptr;
+    int mega_launches_ = 0;
 
     // device state
     cudaStream_t stream_ = nullptr;

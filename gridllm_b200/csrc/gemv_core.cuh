@@ -1,0 +1,340 @@
+// Device-side building blocks of the weight-streaming GEMV, shared by the stand-alone kernel
+// (gemv.cu) and the persistent decode-step kernel (decode_mega.cu).
+//
+//   producer lane : gemv_produce()  -- 1-D TMA bulk copies of whole rows into an mbarrier ring
+//   consumer warps: gemv_prologue() -- (RMSNorm) + snap x to int8 planes -> this lane's XUnit registers
+//                   gemv_consume()  -- dp4a block decode out of shared memory, warp-shuffle reduction,
+//                                      fused epilogue (store / residual add / RoPE+KV append / SiLU*mul)
+//
+// For K <= 4096 (one warp spans a row) every consumer warp is autonomous: it waits for a stage, reduces its
+// own rows, runs their epilogue from lane 0 with operands prefetched before the dot product, and releases
+// the stage -- there is no CTA-wide barrier in the steady state.  For larger K (ffn_down) the 2/4/8 warps
+// that share a row meet at a named barrier of just those warps.
+#pragma once
+#include "common.cuh"
+#include "gguf_file.h"
+#include "kernels.h"
+#include "rowdot.h"
+
+namespace gl {
+
+constexpr int NCW = GEMV_CONSUMER_WARPS;
+constexpr int NCT = NCW * 32;
+
+// shared-memory carve-up (bytes from the start of dynamic smem)
+constexpr int SM_BARS = 0;                 // full[8], empty[8] mbarriers
+constexpr int SM_RED = 128;                // 32 floats: RMSNorm partials
+constexpr int SM_RES = 256;                // 2 x 256 floats: cross-warp partial sums (K > 4096)
+constexpr int SM_X = 256 + 2 * 256 * 4;    // x planes start (2304)
+
+__host__ __device__ inline int gemv_x_bytes(int cols) { return 2 * cols + cols / 2; }   // hi, lo, sx, sm, s16
+__host__ __device__ inline int gemv_fixed_smem(int cols) { return (SM_X + gemv_x_bytes(cols) + 127) & ~127; }
+
+__host__ __device__ inline int warps_per_row(int cols) {
+    const int w = (cols / UNIT_COLS + 31) / 32;
+    int p = 1;
+    while (p < w) p <<= 1;
+    return p;       // 1,2,4,8
+}
+
+struct Ring {
+    uint64_t* full;
+    uint64_t* empty;
+    uint8_t* slots;
+    int n_slots;
+    int slot_bytes;
+    int st;
+    uint32_t ph;
+    __device__ __forceinline__ void advance() { if (++st == n_slots) { st = 0; ph ^= 1; } }
+    __device__ __forceinline__ uint8_t* slot() const { return slots + (size_t)st * slot_bytes; }
+};
+
+struct WorkRange { int a, b; };
+__device__ __forceinline__ WorkRange cta_range(int rows, int gran, int cta, int n_ctas) {
+    const int units = rows / gran;
+    WorkRange r;
+    r.a = (int)(((long long)cta * units) / n_ctas) * gran;
+    r.b = (int)(((long long)(cta + 1) * units) / n_ctas) * gran;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// producer (one lane): stream this CTA's rows of every segment
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, int cta, int n_ctas) {
+    const int gran = (p.epi == EPI_QKV) ? 2 : 1;
+    const int nwork = p.pair ? 1 : p.nseg;
+    for (int s = 0; s < nwork; ++s) {
+        const GemvSeg sg = p.seg[s];
+        const WorkRange wr = cta_range(sg.rows, gran, cta, n_ctas);
+        for (int r0 = wr.a; r0 < wr.b; r0 += sg.rows_per_stage) {
+            const int n = min(sg.rows_per_stage, wr.b - r0);
+            const uint32_t bytes = (uint32_t)n * (uint32_t)sg.row_stride;
+            mbar_wait(&ring.empty[ring.st], ring.ph ^ 1);
+            uint8_t* dst = ring.slot();
+            if (p.pair) {
+                mbar_expect_tx(&ring.full[ring.st], 2 * bytes);
+                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+                tma_load_1d(dst + bytes, p.seg[1].w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+            } else {
+                mbar_expect_tx(&ring.full[ring.st], bytes);
+                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+            }
+            ring.advance();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// consumer prologue: x -> (RMSNorm) -> int8 planes in smem -> XUnit registers of this lane
+// All NCT consumer threads must call it (named barrier 1).
+// ---------------------------------------------------------------------------------------------------
+template <int ABITS>
+__device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, XUnit& xr) {
+    const int K = p.cols;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* red = reinterpret_cast<float*>(smem + SM_RED);
+    uint8_t* xhi = smem + SM_X;
+    uint8_t* xlo = xhi + K;
+    float* sx_arr = reinterpret_cast<float*>(xlo + K);
+    float* sm_arr = sx_arr + K / 32;
+    int* s16_arr = reinterpret_cast<int*>(sm_arr + K / 32);
+
+    // every read of data produced upstream uses ld.global.cg: this CTA may have been resident (and its
+    // SM's L1 populated) before the producer of x finished.
+    float rstd = 1.f;
+    if (p.norm_w != nullptr) {
+        float ss = 0.f;
+        for (int i = tid * 4; i < K; i += NCT * 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + i));
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        named_bar_sync(1, NCT);
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) tot += red[w];
+        rstd = 1.0f / sqrtf(tot / (float)K + p.eps);
+    }
+    {
+        const int half = tid & 1;
+        const int nblk = K / 32;
+        const int nblk_pad = ((nblk + NCT / 2 - 1) / (NCT / 2)) * (NCT / 2);
+        for (int blk = tid >> 1; blk < nblk_pad; blk += NCT / 2) {
+            const bool live = blk < nblk;
+            float v[16];
+            float amax = 0.f;
+            if (live) {
+                const float* xb = p.x + blk * 32 + half * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = __ldcg(reinterpret_cast<const float4*>(xb + 4 * q));
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+                if (p.norm_w != nullptr) {
+                    const float* wb = p.norm_w + blk * 32 + half * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wb + 4 * q);
+                        v[4 * q] = (v[4 * q] * rstd) * wv.x;
+                        v[4 * q + 1] = (v[4 * q + 1] * rstd) * wv.y;
+                        v[4 * q + 2] = (v[4 * q + 2] * rstd) * wv.z;
+                        v[4 * q + 3] = (v[4 * q + 3] * rstd) * wv.w;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(v[q]));
+            }
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            uint32_t h4[4], l4[4];
+            int vs = 0;
+            if (live) snap16<ABITS>(v, amax, h4, l4, &vs);
+            const int vs_other = __shfl_xor_sync(0xffffffffu, vs, 1);
+            if (live) {
+                const int u = blk >> 2;
+                const int j = 2 * (blk & 3) + half;
+                const int phys = j ^ (u & 7);
+                *reinterpret_cast<uint4*>(xhi + u * 128 + phys * 16) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + u * 128 + phys * 16) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+                s16_arr[2 * blk + half] = vs;
+                if (half == 0) {
+                    const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                    sx_arr[blk] = sx;
+                    sm_arr[blk] = sx * (float)(vs + vs_other);
+                }
+            }
+        }
+    }
+    named_bar_sync(1, NCT);
+
+    const int nu = K / UNIT_COLS;
+    const int wpr = warps_per_row(K);
+    const int u = (warp % wpr) * 32 + lane;
+    if (u < nu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int phys = j ^ (u & 7);
+            const uint4 h = *reinterpret_cast<const uint4*>(xhi + u * 128 + phys * 16);
+            xr.hi[4 * j] = h.x; xr.hi[4 * j + 1] = h.y; xr.hi[4 * j + 2] = h.z; xr.hi[4 * j + 3] = h.w;
+            if (ABITS == 16) {
+                const uint4 l = *reinterpret_cast<const uint4*>(xlo + u * 128 + phys * 16);
+                xr.lo[4 * j] = l.x; xr.lo[4 * j + 1] = l.y; xr.lo[4 * j + 2] = l.z; xr.lo[4 * j + 3] = l.w;
+            }
+        }
+        const float4 a = *reinterpret_cast<const float4*>(sx_arr + 4 * u);
+        const float4 b = *reinterpret_cast<const float4*>(sm_arr + 4 * u);
+        xr.sx[0] = a.x; xr.sx[1] = a.y; xr.sx[2] = a.z; xr.sx[3] = a.w;
+        xr.sm[0] = b.x; xr.sm[1] = b.y; xr.sm[2] = b.z; xr.sm[3] = b.w;
+        const int4 c0 = *reinterpret_cast<const int4*>(s16_arr + 8 * u);
+        const int4 c1 = *reinterpret_cast<const int4*>(s16_arr + 8 * u + 4);
+        xr.s16[0] = c0.x; xr.s16[1] = c0.y; xr.s16[2] = c0.z; xr.s16[3] = c0.w;
+        xr.s16[4] = c1.x; xr.s16[5] = c1.y; xr.s16[6] = c1.z; xr.s16[7] = c1.w;
+    }
+    // the x planes may be overwritten by the next prologue only after every lane has its registers
+    named_bar_sync(1, NCT);
+}
+
+template <int ABITS>
+__device__ __forceinline__ float unit_dot_type(int type, const uint8_t* row, int K, int u, const XUnit& xr) {
+    // type is warp-uniform; each case is a single inlined copy
+    if (type == T_Q4_K) return unit_dot_q4k<ABITS>(row + (size_t)(u >> 1) * 144, u & 1, xr);
+    if (type == T_Q6_K) return unit_dot_q6k<ABITS>(row, K >> 8, u, xr);
+    return unit_dot_q80<ABITS>(row, K, u, xr);
+}
+
+// reduce two per-lane partials over the warp with 6 shuffles; result: .x = sum(a0), .y = sum(a1) on lane 0
+__device__ __forceinline__ float2 warp_sum2(float a0, float a1, int lane) {
+    const bool hi = lane & 16;
+    float v = hi ? a1 : a0;
+    const float t = hi ? a0 : a1;
+    v += __shfl_xor_sync(0xffffffffu, t, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float w = __shfl_sync(0xffffffffu, v, 16);
+    return make_float2(v, w);
+}
+
+struct EpiCtx {      // per-kernel constants of the QKV epilogue, loaded once
+    int pos;
+    int page;
+};
+
+// lane-0 epilogue of one item (1 or 2 rows)
+__device__ __forceinline__ void gemv_epilogue_item(const GemvParams& p, int seg, int r, float v0, float v1, float pre0, float pre1,
+                                                   const EpiCtx& ec) {
+    if (p.epi == EPI_STORE) {
+        p.out[r] = v0;
+    } else if (p.epi == EPI_ADD) {
+        p.out[r] = pre0 + v0;
+    } else if (p.epi == EPI_SILU) {
+        p.out[r] = (v0 / (1.0f + expf(-v0))) * v1;
+    } else {   // EPI_QKV
+        if (seg < 2) {
+            const int d = r % p.head_dim;
+            const float o0 = v0 * pre0 - v1 * pre1, o1 = v0 * pre1 + v1 * pre0;      // pre0 = cos, pre1 = sin
+            if (seg == 0) {
+                *reinterpret_cast<float2*>(p.out + r) = make_float2(o0, o1);
+            } else {
+                const int kvh = r / p.head_dim;
+                const size_t off = (((size_t)ec.page * p.n_kv_heads + kvh) * KV_PAGE_TOKENS + (ec.pos % KV_PAGE_TOKENS)) * p.head_dim + d;
+                *reinterpret_cast<__half2*>(p.k_cache + off) = __floats2half2_rn(o0, o1);
+            }
+        } else {
+            const int kvh = r / p.head_dim, d = r % p.head_dim;
+            const size_t off = (((size_t)ec.page * p.n_kv_heads + kvh) * KV_PAGE_TOKENS + (ec.pos % KV_PAGE_TOKENS)) * p.head_dim + d;
+            p.v_cache[off] = __float2half_rn(v0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// consumer main loop over this CTA's stages.  All consumer warps call it.
+// ---------------------------------------------------------------------------------------------------
+template <int ABITS>
+__device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, const XUnit& xr, int cta, int n_ctas) {
+    const int K = p.cols;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nu = K / UNIT_COLS;
+    const int wpr = warps_per_row(K);
+    const int ngrp = NCW / wpr;              // row groups working in parallel
+    const int grp = warp / wpr, wsub = warp % wpr;
+    const int u = wsub * 32 + lane;
+    const bool valid = u < nu;
+    float* res = reinterpret_cast<float*>(smem + SM_RES);
+    const int gran = (p.epi == EPI_QKV) ? 2 : 1;
+    const int nwork = p.pair ? 1 : p.nseg;
+
+    EpiCtx ec{0, 0};
+    if (p.epi == EPI_QKV) {
+        ec.pos = __ldcg(&p.st->pos);
+        ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
+    }
+    int buf = 0;
+    for (int s = 0; s < nwork; ++s) {
+        const GemvSeg sg = p.seg[s];
+        const WorkRange wr = cta_range(sg.rows, gran, cta, n_ctas);
+        // an "item" is what one epilogue needs: a RoPE pair (2 adjacent rows), a gate/up pair, or a single row
+        const bool pair_adj = (p.epi == EPI_QKV && s < 2);
+        const bool pair_gu = p.pair != 0;
+        for (int r0 = wr.a; r0 < wr.b; r0 += sg.rows_per_stage) {
+            const int n = min(sg.rows_per_stage, wr.b - r0);
+            const int nitems = pair_adj ? n / 2 : n;
+            const uint8_t* base = ring.slot();
+            mbar_wait(&ring.full[ring.st], ring.ph);
+            const bool paired = pair_adj || pair_gu;
+            const int step = paired ? ngrp : 2 * ngrp;      // unpaired rows are processed two at a time
+            for (int it = grp; it < nitems; it += step) {
+                int ra, rb, ga, gb;       // stage-local and global row indices of the (up to) two rows
+                if (pair_adj) { ra = 2 * it; rb = ra + 1; ga = r0 + ra; gb = ga + 1; }
+                else if (pair_gu) { ra = it; rb = n + it; ga = r0 + it; gb = ga; }
+                else { ra = it; rb = (it + ngrp < nitems) ? it + ngrp : -1; ga = r0 + ra; gb = r0 + rb; }
+                // prefetch the epilogue's operands so their latency hides behind the dot products
+                float pre0 = 0.f, pre1 = 0.f;
+                if (lane == 0 && wsub == 0) {
+                    if (p.epi == EPI_ADD) {
+                        pre0 = __ldcg(p.resid + ga);
+                        if (rb >= 0) pre1 = __ldcg(p.resid + gb);
+                    } else if (pair_adj) {
+                        const int d2 = (ga % p.head_dim) >> 1;
+                        pre0 = p.rope_cos[(size_t)ec.pos * (p.head_dim / 2) + d2];
+                        pre1 = p.rope_sin[(size_t)ec.pos * (p.head_dim / 2) + d2];
+                    }
+                }
+                float a0 = 0.f, a1 = 0.f;
+                if (valid) {
+                    a0 = unit_dot_type<ABITS>(sg.type, base + (size_t)ra * sg.row_stride, K, u, xr);
+                    if (rb >= 0) a1 = unit_dot_type<ABITS>(sg.type, base + (size_t)rb * sg.row_stride, K, u, xr);
+                }
+                float2 sum;
+                if (rb >= 0) sum = warp_sum2(a0, a1, lane);
+                else sum = make_float2(warp_sum(a0), 0.f);
+                if (wpr > 1) {
+                    // K > 4096: wpr warps share the row; partials meet in shared memory
+                    float* rbuf = res + buf * 256 + grp * 2 * wpr;
+                    if (lane == 0) { rbuf[wsub] = sum.x; rbuf[wpr + wsub] = sum.y; }
+                    named_bar_sync(2 + grp, 32 * wpr);
+                    if (wsub == 0 && lane == 0) {
+                        float v0 = 0.f, v1 = 0.f;
+                        for (int j = 0; j < wpr; ++j) { v0 += rbuf[j]; v1 += rbuf[wpr + j]; }
+                        sum = make_float2(v0, v1);
+                    }
+                    buf ^= 1;     // double buffer: the next item's partials never race the reader of this one
+                }
+                if (lane == 0 && wsub == 0) {
+                    if (paired) {
+                        gemv_epilogue_item(p, s, ga, sum.x, sum.y, pre0, pre1, ec);
+                    } else {
+                        gemv_epilogue_item(p, s, ga, sum.x, 0.f, pre0, 0.f, ec);
+                        if (rb >= 0) gemv_epilogue_item(p, s, gb, sum.y, 0.f, pre1, 0.f, ec);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[ring.st]);      // this warp is done with the stage's bytes
+            ring.advance();
+        }
+    }
+}
+
+}  // namespace gl

@@ -47,6 +47,18 @@ GL_HD int dp4a_s(uint32_t a, uint32_t b, int c) {
 #endif
 }
 
+// unsigned bytes (a) x signed bytes (b): lets the high nibbles stay in place (value 16*q) -- no shift
+GL_HD int dp4a_us(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    for (int i = 0; i < 4; ++i) c += (int)(uint8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+    return c;
+#endif
+}
+
 GL_HD float half_bits_to_float(uint16_t h) {
 #if defined(__CUDA_ARCH__)
     return __half2float(__ushort_as_half(h));
@@ -128,18 +140,18 @@ GL_HD float unit_dot_q4k(const uint8_t* blk, int hb, const XUnit& x) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t lo4 = w[k] & 0x0F0F0F0Fu;
-                const uint32_t hi4 = (w[k] >> 4) & 0x0F0F0F0Fu;
+                const uint32_t hi4 = w[k] & 0xF0F0F0F0u;          // 16*q, consumed by the unsigned dp4a
                 const int xa = 8 * (2 * c) + 4 * v + k, xb = 8 * (2 * c + 1) + 4 * v + k;
                 ah = dp4a_s(lo4, x.hi[xa], ah);
-                bh = dp4a_s(hi4, x.hi[xb], bh);
+                bh = dp4a_us(hi4, x.hi[xb], bh);
                 if (ABITS == 16) {
                     al = dp4a_s(lo4, x.lo[xa], al);
-                    bl = dp4a_s(hi4, x.lo[xb], bl);
+                    bl = dp4a_us(hi4, x.lo[xb], bl);
                 }
             }
         }
         const int sa = 2 * c, sb = 2 * c + 1;
-        const float sca = (float)((sc4 >> (8 * sa)) & 0xFF), scb = (float)((sc4 >> (8 * sb)) & 0xFF);
+        const float sca = (float)((sc4 >> (8 * sa)) & 0xFF), scb = (float)((sc4 >> (8 * sb)) & 0xFF) * 0.0625f;   // hi nibbles carry 16x
         const float mna = (float)((mn4 >> (8 * sa)) & 0xFF), mnb = (float)((mn4 >> (8 * sb)) & 0xFF);
         val += d * (sca * ((float)combine<ABITS>(ah, al) * x.sx[sa]) + scb * ((float)combine<ABITS>(bh, bl) * x.sx[sb]))
              - dmin * (mna * x.sm[sa] + mnb * x.sm[sb]);

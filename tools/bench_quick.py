@@ -18,11 +18,13 @@ def main():
     t0 = time.time()
     info = S.build_model(path, S.LLAMA3_8B, "q4_k_m", seed=1234, mode="random", with_vocab=False)
     print("build_s", round(time.time() - t0, 1), info, flush=True)
-    for cfg in ({}, {"GL_PDL": "0"}, {"GL_GRAPH": "0"}, {"GL_ACT_BITS": "8"}):
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH"):
+    cfgs = ({}, {"GL_MEGA": "0"}, {"GL_ACT_BITS": "8"}, {"GL_MEGA_SLOT_KB": "24"}, {"GL_MEGA_SLOT_KB": "48"}, {"GL_MEGA_SLOTS": "3"}, {"GL_ATTN_SPLITS": "8"})
+    for cfg in cfgs:
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_KB", "GL_MEGA_SLOTS", "GL_ATTN_SPLITS"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         t0 = time.time()
+        os.environ["GL_PREFILL"] = "1" if cfg else "0"      # only the default config pays for the fp16 prefill copy
         e = N.Engine(path, max_ctx=2048)
         load_s = time.time() - t0
         bpt = e.info.decode_bytes_per_token

@@ -29,12 +29,9 @@ def main():
     configs = [
         {},
         {"GL_ACT_BITS": "8"},
-        {"GL_PDL": "0"},
-        {"GL_STAGE_KB": "16"},
-        {"GL_STAGE_KB": "32"},
-        {"GL_STAGE_KB": "48", "GL_SMEM_KB": "200"},
-        {"GL_SMEM_KB": "200"},
-        {"GL_SMEM_KB": "64"},
+        {"GL_STAGE_KB": "36", "GL_SMEM_KB": "200"},
+        {"GL_STAGE_KB": "36", "GL_SMEM_KB": "200", "GL_ACT_BITS": "8"},
+        {"GL_STAGE_KB": "54", "GL_SMEM_KB": "220"},
     ]
     for cfg in configs:
         for k in ("GL_ACT_BITS", "GL_PDL", "GL_STAGE_KB", "GL_SMEM_KB"):
