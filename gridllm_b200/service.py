@@ -1,0 +1,285 @@
+"""NativeInferenceService -- the drop-in for the reference's ``OllamaService``.
+
+Mirrors /root/reference/client/src/services/OllamaService.ts method for method (same names,
+same request / response dictionaries as client/src/types/index.ts:1-27,39-74, same
+"<Kind> failed: <message>" error convention the worker turns into job:failed), but instead of an
+HTTP call to an Ollama daemon every method calls the in-process native engine through the C ABI
+(gridllm_b200/native.py -> libgridllm_native.so).  The TypeScript twin that a GridLLM
+maintainer would actually ship is host/src/NativeInferenceService.ts over host/napi/addon.cc;
+node is not present in this image, so this Python class is the executable host side.
+
+All generate* calls run the blocking native call on a worker thread (``asyncio.to_thread``) so the
+event loop keeps servicing heartbeats, exactly like napi_create_async_work in the N-API shim.
+"""
+from __future__ import annotations
+
+import asyncio
+import hashlib
+import os
+import queue
+import threading
+import time
+from datetime import datetime, timezone
+from typing import Any, AsyncGenerator, Dict, List, Optional
+
+import numpy as np
+
+from . import native as N
+
+InferenceRequest = Dict[str, Any]
+InferenceResponse = Dict[str, Any]
+StreamResponse = Dict[str, Any]
+
+
+def _now_iso() -> str:
+    return datetime.now(timezone.utc).isoformat(timespec="milliseconds").replace("+00:00", "Z")
+
+
+class NativeInferenceService:
+    """One engine = one GPU = one loaded model (one service per worker id)."""
+
+    def __init__(self, models: Dict[str, str], device: int = 0, max_ctx: int = 0, **engine_kw):
+        """models: Ollama-style model name -> GGUF path."""
+        self._paths = dict(models)
+        self._device = device
+        self._max_ctx = max_ctx
+        self._engine_kw = engine_kw
+        self._engines: Dict[str, N.Engine] = {}
+        self._lock = threading.Lock()          # one engine call at a time (one CUDA stream per engine)
+        self.isConnected = False
+        self.lastHealthCheck = datetime.now(timezone.utc)
+
+    # ---- engine management -------------------------------------------------------------------
+    def _engine(self, name: str) -> N.Engine:
+        if name not in self._paths:
+            raise RuntimeError(f"model '{name}' not found")
+        if name not in self._engines:
+            self._engines[name] = N.Engine(self._paths[name], device=self._device, max_ctx=self._max_ctx, **self._engine_kw)
+        return self._engines[name]
+
+    def close(self):
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()
+
+    # ---- OllamaService.checkHealth (OllamaService.ts:65-83) ------------------------------------
+    async def checkHealth(self) -> bool:
+        try:
+            self.isConnected = N.device_count() > self._device
+        except Exception:
+            self.isConnected = False
+        self.lastHealthCheck = datetime.now(timezone.utc)
+        return self.isConnected
+
+    # ---- OllamaService.getAvailableModels (:85-95); OllamaModel shape client/src/types/index.ts:76-88
+    async def getAvailableModels(self) -> List[Dict[str, Any]]:
+        try:
+            out = []
+            for name, path in self._paths.items():
+                st = os.stat(path)
+                info = self._engines[name].info if name in self._engines else None
+                details = {"format": "gguf", "family": "llama", "families": ["llama"],
+                           "parameter_size": f"{info.n_params / 1e9:.1f}B" if info else "",
+                           "quantization_level": info.quantization.decode() if info else ""}
+                digest = hashlib.sha256(f"{path}:{st.st_size}:{int(st.st_mtime)}".encode()).hexdigest()
+                out.append({"name": name, "digest": digest, "size": st.st_size,
+                            "modified_at": datetime.fromtimestamp(st.st_mtime, timezone.utc).isoformat().replace("+00:00", "Z"),
+                            "details": details})
+            return out
+        except Exception:
+            raise RuntimeError("Failed to retrieve available models from Ollama")
+
+    # ---- OllamaService.validateModel (:340-351): O(1) instead of a /api/tags round trip -----------
+    async def validateModel(self, modelName: str) -> bool:
+        return modelName in self._paths and os.path.exists(self._paths[modelName])
+
+    def getConnectionStatus(self) -> Dict[str, Any]:
+        return {"isConnected": self.isConnected, "lastHealthCheck": self.lastHealthCheck}
+
+    # ---- prompt handling ------------------------------------------------------------------------
+    def _prompt_ids(self, eng: N.Engine, request: InferenceRequest, text: Optional[str]) -> np.ndarray:
+        md = request.get("metadata") or {}
+        if md.get("prompt_token_ids") is not None:      # synthetic workloads: token-id prompts
+            return np.asarray(md["prompt_token_ids"], dtype=np.int32)
+        if not eng.info.has_tokenizer:
+            raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
+        return eng.tokenize(text or "", add_bos=True, parse_special=False)
+
+    def _chat_prompt(self, eng: N.Engine, messages: List[Dict[str, Any]]) -> str:
+        # Llama-3 style header framing when the GGUF has no usable template engine on this side;
+        # the gateway's own /api/chat flattening ("role: content\n...assistant:", ollama.ts:367-370)
+        # reaches generate*, not this method.
+        parts = []
+        for m in messages:
+            parts.append(f"<|start_header_id|>{m.get('role', 'user')}<|end_header_id|>\n\n{m.get('content', '')}<|eot_id|>")
+        parts.append("<|start_header_id|>assistant<|end_header_id|>\n\n")
+        return "".join(parts)
+
+    def _stop_ids(self, eng: N.Engine, request: InferenceRequest) -> List[int]:
+        return []
+
+    def _run(self, model: str, ids: np.ndarray, num_predict: int, options: Dict[str, Any], on_token=None):
+        eng = self._engine(model)
+        temperature = options.get("temperature")
+        if temperature not in (None, 0, 0.0):
+            raise RuntimeError("only greedy decoding (temperature 0) is implemented on the native path")
+        ignore_eos = bool(options.get("ignore_eos", False))
+        with self._lock:
+            return eng, eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token)
+
+    def _response(self, request: InferenceRequest, eng: N.Engine, gen: N.Generation, text: str) -> InferenceResponse:
+        st = gen.stats
+        return {
+            "id": request["id"],
+            "model": request["model"],
+            "created_at": _now_iso(),
+            "response": text,
+            "done": True,
+            "done_reason": "stop" if st.done_reason == 0 else "length",
+            "total_duration": int(st.total_duration_ns),           # real numbers (the reference reports 0, :156-161)
+            "load_duration": int(st.load_duration_ns),
+            "prompt_eval_count": int(st.prompt_eval_count),
+            "prompt_eval_duration": int(st.prompt_eval_duration_ns),
+            "eval_count": int(st.eval_count),
+            "eval_duration": int(st.eval_duration_ns),
+            "system_fingerprint": "fp_gridllm_b200_native",
+            "context": [int(t) for t in gen.ids],                   # token ids: SURVEY.md section 8f.4 (optional field)
+            "logprobs": [float(x) for x in gen.logprobs],
+        }
+
+    def _text(self, eng: N.Engine, ids) -> str:
+        return eng.detokenize(ids) if eng.info.has_tokenizer else ""
+
+    # ---- OllamaService.generateResponse (:97-184) -------------------------------------------------
+    async def generateResponse(self, request: InferenceRequest) -> InferenceResponse:
+        try:
+            options = request.get("options") or {}
+            num_predict = options.get("num_predict") or 128              # OllamaService.ts:105
+            eng = self._engine(request["model"])
+            ids = self._prompt_ids(eng, request, request.get("prompt"))
+            eng, gen = await asyncio.to_thread(self._run, request["model"], ids, num_predict, options)
+            return self._response(request, eng, gen, self._text(eng, gen.ids))
+        except Exception as error:
+            raise RuntimeError(f"Inference failed: {error}")
+
+    # ---- OllamaService.generateStreamResponse (:186-284): async generator of {id, response, done} ----
+    async def generateStreamResponse(self, request: InferenceRequest) -> AsyncGenerator[StreamResponse, None]:
+        try:
+            options = request.get("options") or {}
+            num_predict = options.get("num_predict") or 128
+            eng = self._engine(request["model"])
+            ids = self._prompt_ids(eng, request, request.get("prompt"))
+            q: "queue.Queue" = queue.Queue()
+            cancel = threading.Event()
+
+            def on_token(tid: int, lp: float, piece: bytes) -> bool:
+                q.put(("tok", tid, piece))
+                return cancel.is_set()          # non-zero return cancels (job_cancellation, JobScheduler.ts:530-536)
+
+            def work():
+                try:
+                    _, gen = self._run(request["model"], ids, num_predict, options, on_token)
+                    q.put(("done", gen, None))
+                except Exception as ex:          # surfaced on the consumer side
+                    q.put(("err", ex, None))
+
+            th = threading.Thread(target=work, daemon=True)
+            th.start()
+            pending = b""
+            try:
+                while True:
+                    kind, a, b = await asyncio.to_thread(q.get)
+                    if kind == "tok":
+                        pending += b or b""
+                        try:
+                            text = pending.decode("utf-8")
+                            pending = b""
+                        except UnicodeDecodeError:
+                            text = ""            # wait for the rest of a multi-byte character
+                        yield {"id": request["id"], "response": text, "done": False}
+                    elif kind == "done":
+                        yield {"id": request["id"], "response": pending.decode("utf-8", "replace"), "done": True}
+                        return
+                    else:
+                        raise a
+            finally:
+                cancel.set()
+        except Exception as error:
+            raise RuntimeError(f"Streaming inference failed: {error}")
+
+    # ---- OllamaService.generateChatResponse (:353-449) -------------------------------------------------
+    async def generateChatResponse(self, request: InferenceRequest) -> InferenceResponse:
+        try:
+            md = request.get("metadata") or {}
+            if not md.get("messages"):
+                raise RuntimeError("Chat request must include messages in metadata")
+            options = request.get("options") or {}
+            num_predict = options.get("num_predict") or 128
+            eng = self._engine(request["model"])
+            prompt = self._chat_prompt(eng, md["messages"])
+            if md.get("prompt_token_ids") is not None:
+                ids = np.asarray(md["prompt_token_ids"], dtype=np.int32)
+            else:
+                if not eng.info.has_tokenizer:
+                    raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
+                ids = eng.tokenize(prompt, add_bos=True, parse_special=True)
+            eng, gen = await asyncio.to_thread(self._run, request["model"], ids, num_predict, options)
+            res = self._response(request, eng, gen, "")
+            res.pop("response")
+            res["message"] = {"role": "assistant", "content": self._text(eng, gen.ids)}
+            return res
+        except Exception as error:
+            raise RuntimeError(f"Chat inference failed: {error}")
+
+    # ---- OllamaService.generateChatStreamResponse (:451-599) ---------------------------------------------
+    async def generateChatStreamResponse(self, request: InferenceRequest) -> AsyncGenerator[StreamResponse, None]:
+        try:
+            md = request.get("metadata") or {}
+            if not md.get("messages"):
+                raise RuntimeError("Chat request must include messages in metadata")
+            eng = self._engine(request["model"])
+            sub = dict(request)
+            if md.get("prompt_token_ids") is None:
+                if not eng.info.has_tokenizer:
+                    raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
+                ids = eng.tokenize(self._chat_prompt(eng, md["messages"]), add_bos=True, parse_special=True)
+                sub["metadata"] = dict(md, prompt_token_ids=[int(t) for t in ids])
+            async for chunk in self.generateStreamResponse(sub):
+                yield chunk
+        except Exception as error:
+            raise RuntimeError(f"Chat streaming inference failed: {error}")
+
+    # ---- OllamaService.generateEmbedding (:601-665) ------------------------------------------------------
+    async def generateEmbedding(self, request: InferenceRequest) -> InferenceResponse:
+        try:
+            inp = request.get("input")
+            md = request.get("metadata") or {}
+            if not inp and md.get("input_token_ids") is None:
+                raise RuntimeError("Input is required for embedding requests")
+            eng = self._engine(request["model"])
+            if md.get("input_token_ids") is not None:
+                seqs = [np.asarray(s, dtype=np.int32) for s in md["input_token_ids"]]
+            else:
+                if not eng.info.has_tokenizer:
+                    raise RuntimeError("model carries no tokenizer; supply metadata.input_token_ids")
+                texts = inp if isinstance(inp, list) else [inp]
+                seqs = [eng.tokenize(t, add_bos=True, parse_special=False) for t in texts]
+
+            def work():
+                with self._lock:
+                    return eng.embed(seqs)
+
+            t0 = time.perf_counter_ns()
+            emb, st = await asyncio.to_thread(work)
+            return {"id": request["id"], "model": request["model"], "embeddings": emb.astype(float).tolist(),
+                    "total_duration": time.perf_counter_ns() - t0, "load_duration": int(st.load_duration_ns),
+                    "prompt_eval_count": int(st.prompt_eval_count)}
+        except Exception as error:
+            raise RuntimeError(f"Embedding failed: {error}")
+
+    # ---- pullModel / deleteModel (:286-331): not reachable from WorkerClientService -------------------------
+    async def pullModel(self, modelName: str) -> None:
+        raise RuntimeError(f"Failed to pull model {modelName}: the native worker loads local GGUF files only")
+
+    async def deleteModel(self, modelName: str) -> None:
+        raise RuntimeError(f"Failed to delete model {modelName}: the native worker does not manage model files")

@@ -1,0 +1,156 @@
+"""Worker host around the native engine: the job-dispatch half of the reference's
+``WorkerClientService`` (/root/reference/client/src/services/WorkerClientService.ts), speaking the
+frozen pub/sub wire format to whatever bus the server side uses.
+
+What is mirrored (and what is deliberately not):
+  * registration object + ``worker:registered``                     WorkerClientService.ts:175-206
+  * heartbeat object + ``worker:heartbeat`` / ``heartbeat:<id>``      :330-353   (currentJobs sent as a number,
+                                                                    accepted by WorkerRegistry.ts:269)
+  * ``worker:status_update``                                         :442-472
+  * ``worker:<id>:job`` {type: job_assignment} dispatch by request type, stream chunk re-publish on
+    ``job:stream:<jobId>``, ``job:completed`` / ``job:failed`` / ``job:result:<jobId>``   :497-712
+  * busy-drop of a second assignment                                 :500-505
+  * ``job_cancellation`` IS honoured here (the reference ignores it, :483-491)
+The Redis connection manager, Express health server, Joi config and winston logging of the reference
+client are out of scope: the bus is an interface with an in-process
+implementation; a Redis-backed one plugs in the same way on a box that has Redis.
+"""
+from __future__ import annotations
+
+import asyncio
+import json
+from datetime import datetime, timezone
+from typing import Any, Awaitable, Callable, Dict, List, Optional
+
+from .service import NativeInferenceService
+
+
+def _iso() -> str:
+    return datetime.now(timezone.utc).isoformat(timespec="milliseconds").replace("+00:00", "Z")
+
+
+class LocalBus:
+    """In-process stand-in for the Redis pub/sub + hash/string keys the reference uses
+    (server/src/services/RedisService.ts:111-227).  Channel names travel bare, keys get no prefix."""
+
+    def __init__(self):
+        self.subs: Dict[str, List[Callable[[str], Awaitable[None]]]] = {}
+        self.hashes: Dict[str, Dict[str, str]] = {}
+        self.keys: Dict[str, str] = {}
+        self.log: List[tuple] = []           # (channel, message) in publish order -- golden-fixture tests read this
+
+    async def publish(self, channel: str, message: str) -> None:
+        self.log.append((channel, message))
+        for cb in list(self.subs.get(channel, [])):
+            await cb(message)
+
+    async def subscribe(self, channel: str, cb: Callable[[str], Awaitable[None]]) -> None:
+        self.subs.setdefault(channel, []).append(cb)
+
+    async def hset(self, key: str, field: str, value: str) -> None:
+        self.hashes.setdefault(key, {})[field] = value
+
+    async def set_with_expiry(self, key: str, value: str, ttl_s: float) -> None:
+        self.keys[key] = value
+
+
+class NativeWorker:
+    """One worker id <-> one GPU engine."""
+
+    def __init__(self, worker_id: str, service: NativeInferenceService, bus: LocalBus, heartbeat_interval_ms: int = 5000):
+        self.worker_id = worker_id
+        self.service = service
+        self.bus = bus
+        self.heartbeat_interval_ms = heartbeat_interval_ms
+        self.isProcessingJob = False
+        self.currentJobs = 0
+        self.capabilities: Optional[Dict[str, Any]] = None
+        self._cancelled: set = set()
+
+    # ---- boot (WorkerClientService.initialize/start, :35-89) ----------------------------------------
+    async def start(self) -> None:
+        if not await self.service.checkHealth():
+            raise RuntimeError("Ollama service is not available")      # same message the reference throws (:43-47)
+        models = await self.service.getAvailableModels()
+        self.capabilities = {"workerId": self.worker_id, "availableModels": models, "maxConcurrentTasks": 1,
+                             "supportedFormats": ["json", "text"], "lastUpdated": _iso()}
+        reg = {"workerId": self.worker_id, "capabilities": self.capabilities, "status": "online", "registeredAt": _iso()}
+        await self.bus.hset("workers", self.worker_id, json.dumps(reg))
+        await self.bus.publish("worker:registered", json.dumps(reg))
+        await self.bus.subscribe(f"worker:{self.worker_id}:job", self.handleJobMessage)
+
+    async def sendHeartbeat(self) -> None:
+        hb = {"workerId": self.worker_id, "status": "busy" if self.isProcessingJob else "online", "timestamp": _iso(),
+              "currentJobs": self.currentJobs, "connectionHealth": "healthy"}
+        await self.bus.set_with_expiry(f"heartbeat:{self.worker_id}", json.dumps(hb), self.heartbeat_interval_ms * 2 / 1000)
+        await self.bus.publish("worker:heartbeat", json.dumps(hb))
+
+    async def publishStatusUpdate(self) -> None:
+        await self.bus.publish("worker:status_update", json.dumps(
+            {"workerId": self.worker_id, "status": "busy" if self.isProcessingJob else "online", "currentJobs": self.currentJobs}))
+
+    # ---- message handling (:478-495) -----------------------------------------------------------------
+    async def handleJobMessage(self, message: str) -> None:
+        data = json.loads(message)
+        if data.get("type") == "job_assignment":
+            await self.processJobAssignment(data["job"])
+        elif data.get("type") == "job_cancellation":
+            self._cancelled.add(data.get("jobId"))
+
+    # ---- processJobAssignment (:497-712) ---------------------------------------------------------------
+    async def processJobAssignment(self, assignment: Dict[str, Any]) -> None:
+        request = assignment["request"]
+        if self.isProcessingJob:
+            return                                   # dropped; the server notices via timeout / orphan scan
+        self.isProcessingJob = True
+        self.currentJobs = 1
+        await self.publishStatusUpdate()
+        jid = request["id"]
+        try:
+            if not await self.service.validateModel(request["model"]):
+                raise RuntimeError(f"Model {request['model']} is not available")
+            md = request.get("metadata") or {}
+            rtype = md.get("requestType")
+            result: Optional[Dict[str, Any]] = None
+            if rtype == "embedding":
+                result = await self.service.generateEmbedding(request)
+            elif rtype == "chat":
+                if request.get("stream"):
+                    full = ""
+                    async for chunk in self.service.generateChatStreamResponse(request):
+                        full += chunk["response"]
+                        await self.bus.publish(f"job:stream:{jid}", json.dumps(
+                            {"jobId": jid, "workerId": self.worker_id,
+                             "chunk": dict(chunk, message={"content": chunk["response"]}), "timestamp": _iso()}))
+                        if chunk["done"] or jid in self._cancelled:
+                            result = dict(chunk, id=jid, message={"content": full})
+                            break
+                else:
+                    result = await self.service.generateChatResponse(request)
+            elif request.get("stream"):
+                full = ""
+                async for chunk in self.service.generateStreamResponse(request):
+                    full += chunk["response"]
+                    await self.bus.publish(f"job:stream:{jid}", json.dumps(
+                        {"jobId": jid, "workerId": self.worker_id,
+                         "chunk": {"id": chunk["id"], "response": chunk["response"], "done": chunk["done"]}, "timestamp": _iso()}))
+                    if chunk["done"] or jid in self._cancelled:
+                        result = {"id": jid, "response": full, "done": True}
+                        break
+            else:
+                result = await self.service.generateResponse(request)
+            if not result:
+                raise RuntimeError("No result generated from inference")
+            payload = json.dumps({"jobId": jid, "workerId": self.worker_id, "result": result, "timestamp": _iso()})
+            await self.bus.publish("job:completed", payload)
+            await self.bus.publish(f"job:result:{jid}", payload)
+        except Exception as error:
+            msg = str(error) or "Unknown error"
+            payload = json.dumps({"jobId": jid, "workerId": self.worker_id, "error": msg, "timestamp": _iso()})
+            await self.bus.publish("job:failed", payload)
+            await self.bus.publish(f"job:result:{jid}", payload)
+        finally:
+            self.isProcessingJob = False
+            self.currentJobs = 0
+            self._cancelled.discard(jid)
+            await self.publishStatusUpdate()

@@ -1,0 +1,118 @@
+"""GPU: the reference-facing host layer over the real engine -- NativeInferenceService (drop-in for
+OllamaService) and NativeWorker (WorkerClientService job dispatch), driven by the scheduler stand-in."""
+import asyncio
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(coro):
+    return asyncio.new_event_loop().run_until_complete(coro)
+
+
+@pytest.fixture(scope="module")
+def svc(tiny_gguf):
+    from gridllm_b200.service import NativeInferenceService
+    s = NativeInferenceService({"tiny:latest": tiny_gguf}, device=0)
+    yield s
+    s.close()
+
+
+def test_health_models_validate(svc):
+    assert _run(svc.checkHealth()) is True
+    models = _run(svc.getAvailableModels())
+    assert models[0]["name"] == "tiny:latest" and models[0]["details"]["format"] == "gguf" and models[0]["size"] > 0
+    assert _run(svc.validateModel("tiny:latest")) and not _run(svc.validateModel("other"))
+
+
+def test_generate_text_prompt_roundtrip(svc):
+    from gridllm_b200 import native as N
+    req = {"id": "r1", "model": "tiny:latest", "prompt": "hello world, the rain in spain", "options": {"num_predict": 6, "temperature": 0, "ignore_eos": True},
+           "priority": "medium"}
+    res = _run(svc.generateResponse(req))
+    assert res["id"] == "r1" and res["done"] is True and res["done_reason"] == "length"
+    assert res["eval_count"] == 6 and res["prompt_eval_count"] > 3 and res["eval_duration"] > 0 and res["prompt_eval_duration"] > 0
+    eng = svc._engine("tiny:latest")
+    ids = eng.tokenize(req["prompt"])
+    assert eng.detokenize(ids[1:]) == req["prompt"]                 # byte-level BPE round trip (id 0 is BOS)
+    g = eng.generate(ids, num_predict=6, ignore_eos=True)
+    assert res["context"] == [int(t) for t in g.ids]                # service == direct C-ABI call
+    assert res["response"] == eng.detokenize(g.ids)
+    # default generation length when num_predict is absent: OllamaService.ts:105 -> 128
+    res2 = _run(svc.generateResponse({"id": "r2", "model": "tiny:latest", "prompt": "hi", "options": {"ignore_eos": True}, "priority": "low"}))
+    assert res2["eval_count"] == 128
+
+
+def test_stream_equals_non_stream(svc):
+    req = {"id": "s1", "model": "tiny:latest", "prompt": "in the end", "stream": True, "options": {"num_predict": 9, "ignore_eos": True}, "priority": "medium"}
+
+    async def collect():
+        out = []
+        async for c in svc.generateStreamResponse(req):
+            out.append(c)
+        return out
+    chunks = _run(collect())
+    assert [c["done"] for c in chunks] == [False] * 9 + [True]
+    assert all(set(c) == {"id", "response", "done"} for c in chunks)
+    full = _run(svc.generateResponse(dict(req, stream=False)))
+    assert "".join(c["response"] for c in chunks) == full["response"]
+
+
+def test_chat_and_embedding(svc):
+    chat = {"id": "c1", "model": "tiny:latest", "options": {"num_predict": 4, "ignore_eos": True}, "priority": "high",
+            "metadata": {"requestType": "chat", "messages": [{"role": "user", "content": "hello"}]}}
+    res = _run(svc.generateChatResponse(chat))
+    assert res["message"]["role"] == "assistant" and res["eval_count"] == 4 and "response" not in res
+    emb = _run(svc.generateEmbedding({"id": "e1", "model": "tiny:latest", "input": ["the rain", "hello world"], "priority": "low",
+                                      "metadata": {"requestType": "embedding"}}))
+    e = np.asarray(emb["embeddings"])
+    assert e.shape == (2, 256) and np.allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+    with pytest.raises(RuntimeError, match="Embedding failed: Input is required"):
+        _run(svc.generateEmbedding({"id": "e2", "model": "tiny:latest", "priority": "low"}))
+    with pytest.raises(RuntimeError, match="Chat inference failed: Chat request must include messages"):
+        _run(svc.generateChatResponse({"id": "c2", "model": "tiny:latest", "priority": "low"}))
+    with pytest.raises(RuntimeError, match="Inference failed"):
+        _run(svc.generateResponse({"id": "x", "model": "missing", "prompt": "a", "priority": "low"}))
+
+
+def test_workers_shard_requests_like_the_scheduler(tiny_gguf):
+    """Two in-process workers (two engines on this GPU; one per GPU on a multi-GPU box), sharded by the
+    scheduler stand-in: least-loaded selection spreads jobs, priority is honoured, and every result equals
+    the single-engine answer (replicas are independent: no collective on this path)."""
+    from gridllm_b200.service import NativeInferenceService
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    from sched_standin import SchedulerStandIn
+    from gridllm_b200 import native as N
+    ndev = N.device_count()
+    bus = LocalBus()
+    sched = SchedulerStandIn(bus)
+    svcs = [NativeInferenceService({"tiny:latest": tiny_gguf}, device=i % ndev) for i in range(2)]
+    workers = [NativeWorker(f"b200-{i}", s, bus) for i, s in enumerate(svcs)]
+
+    async def go():
+        await sched.start()
+        for w in workers:
+            await w.start()
+        for i in range(6):
+            ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=20).tolist()
+            sched.add_job({"id": f"job-{i}", "model": "tiny:latest", "prompt": "", "stream": False, "priority": "high" if i == 5 else "medium",
+                           "options": {"num_predict": 5, "ignore_eos": True}, "timeout": 300000, "metadata": {"prompt_token_ids": ids}})
+        await sched.run_until_empty()
+    _run(go())
+    assert len(sched.results) == 6 and all("result" in r for r in sched.results.values())
+    used = set(sched.assigned.values())
+    assert used == {"b200-0", "b200-1"}
+    first_two = [c for c, m in bus.log if c.startswith("worker:b200-") and c.endswith(":job")][:2]
+    assigned_first = json.loads([m for c, m in bus.log if c == first_two[0]][0])["job"]["jobId"]
+    assert assigned_first == "job-5"                                   # priority sort (JobScheduler.ts:145-151)
+    ref = N.Engine(tiny_gguf)
+    for i in range(6):
+        ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=20)
+        g = ref.generate(ids, num_predict=5, ignore_eos=True)
+        assert sched.results[f"job-{i}"]["result"]["context"] == [int(t) for t in g.ids]
+    ref.close()
+    for s in svcs:
+        s.close()
