@@ -26,8 +26,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 
 // all consumer threads of every CTA call this the same number of times
+template <int NT>
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int tid) {
-    named_bar_sync(1, NCT);
+    named_bar_sync(1, NT);
     if (tid == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
@@ -37,7 +38,32 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target,
         }
         __threadfence();
     }
-    named_bar_sync(1, NCT);
+    named_bar_sync(1, NT);
+}
+
+// producer: stream one GEMV phase described by a constant-bank descriptor
+__device__ __forceinline__ void produce_phase(const ProdDesc& d, Ring& ring, int cta, int n_ctas) {
+    const int nwork = d.pair ? 1 : d.nseg;
+    for (int s = 0; s < nwork; ++s) {
+        const ProdSeg sg = d.seg[s];
+        const int rps = d.rps[s];
+        const WorkRange wr = cta_range(sg.rows, d.gran, cta, n_ctas);
+        for (int r0 = wr.a; r0 < wr.b; r0 += rps) {
+            const int n = min(rps, wr.b - r0);
+            const uint32_t bytes = (uint32_t)n * (uint32_t)sg.row_stride;
+            mbar_wait(&ring.empty[ring.st], ring.ph ^ 1);
+            uint8_t* dst = ring.slot();
+            if (d.pair) {
+                mbar_expect_tx(&ring.full[ring.st], 2 * bytes);
+                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+                tma_load_1d(dst + bytes, d.seg[1].w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+            } else {
+                mbar_expect_tx(&ring.full[ring.st], bytes);
+                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+            }
+            ring.advance();
+        }
+    }
 }
 
 __device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int type, int c) {
@@ -75,7 +101,9 @@ __device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int typ
 }
 
 // ---- split-KV paged attention for one (kv head, split) item; K/V rows read straight from HBM/L2 ----------
-template <int DPL>
+// One warp per query head of the GQA group; a lane owns DPL dims.  K and V of a 16-token page are requested
+// together (32 independent loads per lane in flight) before any arithmetic.
+template <int DPL, int NT>
 __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc, const __half* vc, int item, int warp, int lane,
                                           int tid, int* smem_flag) {
     constexpr int HD = DPL * 32;
@@ -98,21 +126,29 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
             const int page = __ldcg(mp.page_table + pg);
             const size_t base = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD + lane * DPL;
             const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
-            float sc[KV_PAGE_TOKENS];
+            uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
 #pragma unroll
-            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {       // 16 independent loads in flight per lane
-                float a = 0.f;
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+                kk[j] = make_uint2(0u, 0u);
+                vv[j] = make_uint2(0u, 0u);
                 if (j < npos) {
                     if (DPL == 4) {
-                        const uint2 kk = __ldcg(reinterpret_cast<const uint2*>(kc + base + (size_t)j * HD));
-                        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk.x));
-                        const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk.y));
-                        a = q[0] * k0.x + q[1] * k0.y + q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
+                        kk[j] = __ldcg(reinterpret_cast<const uint2*>(kc + base + (size_t)j * HD));
+                        vv[j] = __ldcg(reinterpret_cast<const uint2*>(vc + base + (size_t)j * HD));
                     } else {
-                        const unsigned kk = __ldcg(reinterpret_cast<const unsigned*>(kc + base + (size_t)j * HD));
-                        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk));
-                        a = q[0] * k0.x + q[1] * k0.y;
+                        kk[j].x = __ldcg(reinterpret_cast<const unsigned*>(kc + base + (size_t)j * HD));
+                        vv[j].x = __ldcg(reinterpret_cast<const unsigned*>(vc + base + (size_t)j * HD));
                     }
+                }
+            }
+            float sc[KV_PAGE_TOKENS];
+#pragma unroll
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+                const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].x));
+                float a = q[0] * k0.x + q[1] * k0.y;
+                if (DPL == 4) {
+                    const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].y));
+                    a += q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
                 }
                 sc[j] = a;
             }
@@ -132,15 +168,11 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
                 if (j < npos) {
                     const float w = expf(sc[j] - m_new);
                     l_run += w;
+                    const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
+                    o[0] += w * v0.x; o[1] += w * v0.y;
                     if (DPL == 4) {
-                        const uint2 vv = __ldcg(reinterpret_cast<const uint2*>(vc + base + (size_t)j * HD));
-                        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x));
-                        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
-                        o[0] += w * v0.x; o[1] += w * v0.y; o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
-                    } else {
-                        const unsigned vv = __ldcg(reinterpret_cast<const unsigned*>(vc + base + (size_t)j * HD));
-                        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv));
-                        o[0] += w * v0.x; o[1] += w * v0.y;
+                        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
+                        o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
                     }
                 }
             }
@@ -155,27 +187,31 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
         }
     }
     __threadfence();
-    named_bar_sync(1, NCT);
+    named_bar_sync(1, NT);
     if (tid == 0) {
         const unsigned ticket = atomicAdd(mp.attn_counters + kvh, 1u);
         const int last = (ticket == (unsigned)n_splits - 1);
         if (last) mp.attn_counters[kvh] = 0;
         *smem_flag = last;
     }
-    named_bar_sync(1, NCT);
+    named_bar_sync(1, NT);
     if (*smem_flag && active) {
         __threadfence();
-        float M = -INFINITY;
-        for (int s = 0; s < n_splits; ++s) M = fmaxf(M, __ldcg(mp.part_ml + ((size_t)head * n_splits + s) * 2));
-        float den = 0.f, acc[DPL];
+        // lane s holds (m, l) of split s; n_splits <= 32
+        float ms = -INFINITY, ls = 0.f;
+        if (lane < n_splits) {
+            ms = __ldcg(mp.part_ml + ((size_t)head * n_splits + lane) * 2);
+            ls = __ldcg(mp.part_ml + ((size_t)head * n_splits + lane) * 2 + 1);
+        }
+        const float M = warp_max(ms);
+        const float wl = (ms == -INFINITY) ? 0.f : expf(ms - M);
+        const float den = warp_sum(wl * ls);
+        float acc[DPL];
 #pragma unroll
         for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
         for (int s = 0; s < n_splits; ++s) {
-            const float ms = __ldcg(mp.part_ml + ((size_t)head * n_splits + s) * 2);
-            if (ms == -INFINITY) continue;
-            const float ls = __ldcg(mp.part_ml + ((size_t)head * n_splits + s) * 2 + 1);
-            const float w = expf(ms - M);
-            den += w * ls;
+            const float w = __shfl_sync(0xffffffffu, wl, s);
+            if (w == 0.f) continue;
             const float* po = mp.part_o + ((size_t)head * n_splits + s) * HD + lane * DPL;
 #pragma unroll
             for (int d = 0; d < DPL; ++d) acc[d] += w * __ldcg(po + d);
@@ -187,19 +223,20 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
     }
 }
 
-template <int ABITS>
-__global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaParams mp) {
+template <int ABITS, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __grid_constant__ MegaParams mp) {
+    constexpr int NT = NW * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, G = gridDim.x;
     const int fixed = gemv_fixed_smem(mp.max_cols);
-    GemvParams* sdesc = reinterpret_cast<GemvParams*>(smem + fixed);            // phase descriptor, consumer copy
-    int* sflag = reinterpret_cast<int*>(smem + fixed + 256);
-    float* sstat = reinterpret_cast<float*>(smem + fixed + 256 + 16);            // 3 x NCW floats
+    MegaPhase* sdesc = reinterpret_cast<MegaPhase*>(smem + fixed);              // 2 x 256 B: phase descriptors, double-buffered
+    int* sflag = reinterpret_cast<int*>(smem + fixed + 512);
+    float* sstat = reinterpret_cast<float*>(smem + fixed + 512 + 16);            // 3 x NW floats
     Ring ring;
     ring.full = reinterpret_cast<uint64_t*>(smem + SM_BARS);
     ring.empty = ring.full + GEMV_MAX_STAGES;
-    ring.slots = smem + fixed + 512;
+    ring.slots = smem + fixed + 1024;
     ring.n_slots = mp.n_slots;
     ring.slot_bytes = mp.slot_bytes;
     ring.st = 0;
@@ -207,28 +244,32 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __gr
     if (tid == 0) {
         for (int i = 0; i < mp.n_slots; ++i) {
             mbar_init(&ring.full[i], 1);
-            mbar_init(&ring.empty[i], NCW);
+            mbar_init(&ring.empty[i], NW);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (warp == NCW) {
+    if (warp == NW) {
         // ============ producer: every weight phase of every step, never blocked by grid barriers ============
         if (lane == 0) {
             for (int step = 0; step < mp.n_steps; ++step)
-                for (int ph = 0; ph < mp.n_phases; ++ph) {
-                    const MegaPhase& P = mp.phases[ph];
-                    if (P.kind == PH_GEMV) gemv_produce(P.g, ring, cta, G);
-                }
+                for (int i = 0; i < mp.n_prod; ++i) produce_phase(mp.prod[i], ring, cta, G);
         }
         return;
     }
 
     // ============ consumers ==================================================================================
+    static_assert(sizeof(MegaPhase) <= 256 && sizeof(MegaPhase) % 4 == 0, "descriptor slot");
+    constexpr int DESC_WORDS = sizeof(MegaPhase) / 4;
+    auto prefetch_desc = [&](int ph, int slot) {      // static data: plain loads; visible after the next barrier
+        if (tid < DESC_WORDS)
+            reinterpret_cast<uint32_t*>(sdesc)[slot * 64 + tid] = reinterpret_cast<const uint32_t*>(mp.phases + ph)[tid];
+    };
     StepState* st = mp.st;
     const unsigned bar_base = __ldcg(&st->bar_base);
     unsigned nbar = 0;
+    int dslot = 0;
     XUnit xr;
     for (int step = 0; step < mp.n_steps; ++step) {
         // ---- token embedding (CTA 0) ----------------------------------------------------------------------
@@ -240,27 +281,25 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __gr
                 if (pos < np) tok = __ldcg(mp.prompt_ids + pos);
             }
             const uint8_t* row = mp.embd_w + (size_t)tok * mp.embd_row_bytes;
-            for (int c = tid; c < mp.n_embd; c += NCT) mp.x[c] = dequant_native_elem(row, mp.embd_type, c);
+            for (int c = tid; c < mp.n_embd; c += NT) mp.x[c] = dequant_native_elem(row, mp.embd_type, c);
         }
+        prefetch_desc(0, dslot);
         ++nbar;
-        grid_barrier(mp.bar_counter, bar_base + nbar * G, tid);
+        grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
 
         for (int ph = 0; ph < mp.n_phases; ++ph) {
-            const MegaPhase& P = mp.phases[ph];
+            const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<const uint8_t*>(sdesc) + dslot * 256);
             const int kind = P.kind;
             if (kind == PH_GEMV) {
-                // stage the descriptor in shared memory (it is read many times in the row loop)
-                if (tid < (int)(sizeof(GemvParams) / 4)) reinterpret_cast<uint32_t*>(sdesc)[tid] = reinterpret_cast<const uint32_t*>(&P.g)[tid];
-                named_bar_sync(1, NCT);
-                gemv_prologue<ABITS>(*sdesc, smem, tid, xr);
-                gemv_consume<ABITS>(*sdesc, ring, smem, tid, xr, cta, G);
+                gemv_prologue<ABITS, NW>(P.g, smem, tid, xr);
+                gemv_consume<ABITS, NW>(P.g, ring, smem, tid, xr, cta, G);
                 if (P.flags & PHF_HEAD) {
                     // per-CTA softmax statistics over the logits rows this CTA produced
-                    named_bar_sync(1, NCT);
-                    const WorkRange wr = cta_range(sdesc->seg[0].rows, 1, cta, G);
+                    named_bar_sync(1, NT);
+                    const WorkRange wr = cta_range(P.g.seg[0].rows, 1, cta, G);
                     float best = -INFINITY;
                     int bi = 0x7fffffff;
-                    for (int i = wr.a + tid; i < wr.b; i += NCT) {
+                    for (int i = wr.a + tid; i < wr.b; i += NT) {
                         const float v = __ldcg(mp.logits + i);
                         if (v > best) { best = v; bi = i; }
                     }
@@ -270,22 +309,22 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __gr
                         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
                     }
-                    if (lane == 0) { sstat[warp] = best; reinterpret_cast<int*>(sstat)[NCW + warp] = bi; }
-                    named_bar_sync(1, NCT);
-                    best = sstat[0]; bi = reinterpret_cast<int*>(sstat)[NCW];
-                    for (int w = 1; w < NCW; ++w) {
+                    if (lane == 0) { sstat[warp] = best; reinterpret_cast<int*>(sstat)[NW + warp] = bi; }
+                    named_bar_sync(1, NT);
+                    best = sstat[0]; bi = reinterpret_cast<int*>(sstat)[NW];
+                    for (int w = 1; w < NW; ++w) {
                         const float ov = sstat[w];
-                        const int oi = reinterpret_cast<int*>(sstat)[NCW + w];
+                        const int oi = reinterpret_cast<int*>(sstat)[NW + w];
                         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
                     }
                     float s = 0.f;
-                    for (int i = wr.a + tid; i < wr.b; i += NCT) s += expf(__ldcg(mp.logits + i) - best);
+                    for (int i = wr.a + tid; i < wr.b; i += NT) s += expf(__ldcg(mp.logits + i) - best);
                     s = warp_sum(s);
-                    if (lane == 0) sstat[2 * NCW + warp] = s;
-                    named_bar_sync(1, NCT);
+                    if (lane == 0) sstat[2 * NW + warp] = s;
+                    named_bar_sync(1, NT);
                     if (tid == 0) {
                         float tot = 0.f;
-                        for (int w = 0; w < NCW; ++w) tot += sstat[2 * NCW + w];
+                        for (int w = 0; w < NW; ++w) tot += sstat[2 * NW + w];
                         mp.head_part[cta * 4 + 0] = best;
                         reinterpret_cast<int*>(mp.head_part)[cta * 4 + 1] = bi;
                         mp.head_part[cta * 4 + 2] = tot;
@@ -293,20 +332,23 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __gr
                     if (mp.logits_keep != nullptr) {
                         const int oi = __ldcg(&st->out_idx);
                         if (!__ldcg(&st->done) && oi < mp.max_out) {
-                            float* dst = mp.logits_keep + (size_t)oi * sdesc->seg[0].rows;
-                            for (int i = wr.a + tid; i < wr.b; i += NCT) dst[i] = __ldcg(mp.logits + i);
+                            float* dst = mp.logits_keep + (size_t)oi * P.g.seg[0].rows;
+                            for (int i = wr.a + tid; i < wr.b; i += NT) dst[i] = __ldcg(mp.logits + i);
                         }
                     }
                 }
             } else if (kind == PH_ATTN) {
                 const int n_items = mp.n_kv * mp.attn_splits;
                 if (cta < n_items) {
-                    if (mp.head_dim == 128) attn_item<4>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
-                    else attn_item<2>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
+                    if (mp.head_dim == 128) attn_item<4, NT>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
+                    else attn_item<2, NT>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
                 }
             }
+            // the next phase's descriptor travels while this CTA waits at the barrier
+            if (ph + 1 < mp.n_phases) prefetch_desc(ph + 1, dslot ^ 1);
+            dslot ^= 1;
             ++nbar;
-            grid_barrier(mp.bar_counter, bar_base + nbar * G, tid);
+            grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
         }
 
         // ---- sampling / state advance (CTA 0), published to everyone by the barrier at the top of the next step
@@ -349,7 +391,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __gr
                 st->pos = __ldcg(&st->pos) + 1;
             }
         }
-        if (cta == 0) named_bar_sync(1, NCT);     // state written before CTA 0 starts the next embedding
+        if (cta == 0) named_bar_sync(1, NT);     // state written before CTA 0 starts the next embedding
     }
     if (cta == 0 && tid == 0) st->bar_base = bar_base + nbar * G;
 }
@@ -357,19 +399,22 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) decode_mega_kernel(const __gr
 }  // namespace
 
 size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes) {
-    return (size_t)gemv_fixed_smem(max_cols) + 512 + (size_t)n_slots * slot_bytes;
+    return (size_t)gemv_fixed_smem(max_cols) + 1024 + (size_t)n_slots * slot_bytes;
 }
 
 cudaError_t mega_configure() {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(decode_mega_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
 }
 
-cudaError_t mega_launch(const MegaParams& mp, int abits, int n_ctas, cudaStream_t s) {
+cudaError_t mega_launch(const MegaParams& mp, int abits, int nw, int n_ctas, cudaStream_t s) {
+    if (!gemv_variant_ok(abits, nw)) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);
-    cfg.blockDim = dim3(GEMV_THREADS);
+    cfg.blockDim = dim3((unsigned)gemv_threads(nw));
     cfg.dynamicSmemBytes = mega_smem_bytes(mp.max_cols, mp.n_slots, mp.slot_bytes);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -377,8 +422,8 @@ cudaError_t mega_launch(const MegaParams& mp, int abits, int n_ctas, cudaStream_
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (abits == 16) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<16>, mp);
-    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<8>, mp);
+    if (abits == 16) return nw == 8 ? cudaLaunchKernelEx(&cfg, decode_mega_kernel<16, 8>, mp) : cudaLaunchKernelEx(&cfg, decode_mega_kernel<16, 12>, mp);
+    return nw == 8 ? cudaLaunchKernelEx(&cfg, decode_mega_kernel<8, 8>, mp) : cudaLaunchKernelEx(&cfg, decode_mega_kernel<8, 16>, mp);
 }
 
 }  // namespace gl

@@ -14,6 +14,16 @@ struct alignas(16) MegaPhase {
     GemvParams g;          // PH_GEMV: the whole work description; PH_ATTN: k_cache / v_cache of the layer
 };
 
+// What the producer lane needs to stream one GEMV phase.  Lives in the kernel-parameter constant bank so the
+// producer never waits on a global-memory round trip when it crosses a phase boundary.
+struct ProdSeg { const uint8_t* w; int rows; int row_stride; };
+struct alignas(16) ProdDesc {
+    ProdSeg seg[3];
+    short nseg, pair, gran, pad;
+    short rps[4];              // rows per stage of each segment
+};
+constexpr int MEGA_MAX_GEMV_PHASES = 400;     // 80 layers x 4 + head; 400 x 64 B = 25.6 KB of the 32 KB parameter space
+
 struct MegaParams {
     const MegaPhase* phases;   // device memory, n_phases entries (one token)
     int n_phases;
@@ -44,10 +54,12 @@ struct MegaParams {
     int max_out;
     // ring
     int n_slots, slot_bytes, max_cols;
+    int n_prod;                // GEMV phases per token (entries of prod[] in use)
+    ProdDesc prod[MEGA_MAX_GEMV_PHASES];
 };
 
 size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes);
 cudaError_t mega_configure();
-cudaError_t mega_launch(const MegaParams& mp, int abits, int n_ctas, cudaStream_t s);
+cudaError_t mega_launch(const MegaParams& mp, int abits, int consumer_warps, int n_ctas, cudaStream_t s);
 
 }  // namespace gl

@@ -150,6 +150,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     use_pdl_ = !(opts && opts->use_pdl == 0) && env_int("GL_PDL", 1) != 0;
     fused_ = env_int("GL_FUSE", 1) != 0;
     abits_ = env_int("GL_ACT_BITS", abits_) == 8 ? 8 : 16;
+    nw_ = env_int("GL_WARPS", abits_ == 16 ? 12 : 16);
+    if (!gemv_variant_ok(abits_, nw_)) nw_ = 8;
     stage_kb_ = env_int("GL_STAGE_KB", 24);
     smem_kb_ = env_int("GL_SMEM_KB", 110);
     attn_splits_ = std::max(1, std::min(64, env_int("GL_ATTN_SPLITS", 16)));
@@ -242,8 +244,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(dalloc((void**)&up_, (size_t)n_ff_ * 4));
     CU(dalloc((void**)&ytmp_, (size_t)std::max(n_embd_, n_ff_) * 4));
     CU(dalloc((void**)&logits_, (size_t)n_vocab_ * 4));
-    CU(dalloc((void**)&part_o_, (size_t)n_head_ * attn_splits_ * hd_ * 4));
-    CU(dalloc((void**)&part_ml_, (size_t)n_head_ * attn_splits_ * 2 * 4));
+    CU(dalloc((void**)&part_o_, (size_t)n_head_ * std::max(attn_splits_, 32) * hd_ * 4));
+    CU(dalloc((void**)&part_ml_, (size_t)n_head_ * std::max(attn_splits_, 32) * 2 * 4));
     CU(dalloc((void**)&counters_, (size_t)n_kv_ * 4));
     n_pages_ = n_ctx_ / KV_PAGE_TOKENS;
     kv_layer_elems_ = (size_t)n_pages_ * n_kv_ * KV_PAGE_TOKENS * hd_;
@@ -371,7 +373,7 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
 Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch) {
     p.n_stages = 3;
     p.stage_bytes = stage_kb_ * 1024;
-    if (!gemv_plan(p)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(p.cols) + ")");
+    if (!gemv_plan(p, nw_)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(p.cols) + ")");
     // shrink the stage to what the plan needs, then spend the shared-memory budget on depth
     int need = 0;
     for (int i = 0; i < p.nseg; ++i) need = std::max(need, p.seg[i].rows_per_stage * p.seg[i].row_stride * (p.pair ? 2 : 1));
@@ -380,7 +382,7 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch) {
     int ns = (int)(((size_t)smem_kb_ * 1024 - fixed) / p.stage_bytes);
     p.n_stages = std::max(2, std::min(GEMV_MAX_STAGES, ns));
     if (gemv_smem_bytes(p.cols, p.n_stages, p.stage_bytes) > 227 * 1024) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
-    CU(gemv_launch(p, abits_, sm_count_, use_pdl_, s));
+    CU(gemv_launch(p, abits_, nw_, sm_count_, use_pdl_, s));
     ++*n_launch;
     return {};
 }
@@ -545,13 +547,22 @@ Status Engine::build_mega() {
     mega_slots_ = std::min(mega_slots_, env_int("GL_MEGA_SLOTS", GEMV_MAX_STAGES));
     if (mega_slots_ < 2) return {};
     std::vector<MegaPhase> ph;
+    mega_prod_.clear();
+    mega_splits_ = std::max(1, std::min(32, sm_count_ / n_kv_));
     auto add_gemv = [&](GemvParams g, int flags) -> bool {
         g.n_stages = mega_slots_;
         g.stage_bytes = mega_slot_bytes_;
-        if (!gemv_plan(g)) return false;
+        if (!gemv_plan(g, nw_)) return false;
         MegaPhase m{};
         m.kind = PH_GEMV; m.flags = flags; m.g = g;
         ph.push_back(m);
+        ProdDesc d{};
+        for (int i = 0; i < g.nseg; ++i) {
+            d.seg[i] = ProdSeg{g.seg[i].w, g.seg[i].rows, g.seg[i].row_stride};
+            d.rps[i] = (short)g.seg[i].rows_per_stage;
+        }
+        d.nseg = (short)g.nseg; d.pair = (short)g.pair; d.gran = (short)(g.epi == EPI_QKV ? 2 : 1);
+        mega_prod_.push_back(d);
         return true;
     };
     for (int il = 0; il < n_layer_; ++il) {
@@ -592,6 +603,7 @@ Status Engine::build_mega() {
         if (!add_gemv(p, PHF_HEAD)) return {};
     }
     mega_n_head_ = (int)ph.size();
+    if ((int)mega_prod_.size() > MEGA_MAX_GEMV_PHASES) return {};          // too many layers for the parameter bank: per-op path
     CU(cudaMalloc((void**)&mega_head_, ph.size() * sizeof(MegaPhase)));
     allocs_.push_back(mega_head_);
     CU(cudaMemcpy(mega_head_, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
@@ -619,13 +631,16 @@ Status Engine::launch_mega(int n_steps, bool with_head, bool keep_logits) {
     mp.x = x_; mp.q = q_; mp.attn_out = attn_; mp.part_o = part_o_; mp.part_ml = part_ml_; mp.attn_counters = counters_;
     mp.page_table = page_table_;
     mp.n_head = n_head_; mp.n_kv = n_kv_; mp.head_dim = hd_;
-    mp.attn_splits = std::max(1, std::min(attn_splits_, sm_count_ / n_kv_));
+    mp.attn_splits = mega_splits_;
     mp.attn_scale = 1.0f / std::sqrt((float)hd_);
     mp.logits = logits_; mp.head_part = head_part_; mp.out_ids = out_ids_; mp.out_logprobs = out_lp_;
     mp.logits_keep = keep_logits ? logits_keep_ : nullptr;
     mp.max_out = keep_logits ? keep_cap_ : max_out_;
     mp.n_slots = mega_slots_; mp.slot_bytes = mega_slot_bytes_; mp.max_cols = mega_max_cols_;
-    CU(mega_launch(mp, abits_, sm_count_, stream_));
+    // producer descriptors: all GEMV phases of the token; the head phase is the last entry
+    mp.n_prod = with_head ? (int)mega_prod_.size() : (int)mega_prod_.size() - 1;
+    std::memcpy(mp.prod, mega_prod_.data(), mega_prod_.size() * sizeof(ProdDesc));
+    CU(mega_launch(mp, abits_, nw_, sm_count_, stream_));
     ++mega_launches_;
     return {};
 }

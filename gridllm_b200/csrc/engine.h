@@ -100,6 +100,7 @@ private:
     // options
     int device_ = 0, sm_count_ = 148;
     int abits_ = 16;
+    int nw_ = 8;               // consumer warps per CTA of the GEMV / persistent kernels
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
     int stage_kb_ = 24, smem_kb_ = 110, attn_splits_ = 16;
     int prefill_mode_ = 0, prefill_min_ = 8;
@@ -118,6 +119,8 @@ private:
     unsigned* bar_counter_ = nullptr;
     float* head_part_ = nullptr;
     int mega_launches_ = 0;
+    int mega_splits_ = 16;
+    std::vector<ProdDesc> mega_prod_;
 
     // device state
     cudaStream_t stream_ = nullptr;

@@ -23,8 +23,8 @@ namespace gl {
 
 namespace {
 
-template <int ABITS>
-__global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
+template <int ABITS, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
@@ -38,22 +38,22 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const __grid_cons
     if (tid == 0) {
         for (int i = 0; i < p.n_stages; ++i) {
             mbar_init(&ring.full[i], 1);
-            mbar_init(&ring.empty[i], NCW);
+            mbar_init(&ring.empty[i], NW);
         }
         fence_mbar_init();
     }
     __syncthreads();
     pdl_launch_dependents();
 
-    if (warp == NCW) {
+    if (warp == NW) {
         // producer: weights are static, so streaming starts before the upstream kernel has finished
         if (lane == 0) gemv_produce(p, ring, blockIdx.x, gridDim.x);
         return;
     }
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
     XUnit xr;
-    gemv_prologue<ABITS>(p, smem, tid, xr);
-    gemv_consume<ABITS>(p, ring, smem, tid, xr, blockIdx.x, gridDim.x);
+    gemv_prologue<ABITS, NW>(p, smem, tid, xr);
+    gemv_consume<ABITS, NW>(p, ring, smem, tid, xr, blockIdx.x, gridDim.x);
 }
 
 }  // namespace
@@ -62,11 +62,12 @@ size_t gemv_smem_bytes(int cols, int n_stages, int stage_bytes) {
     return (size_t)gemv_fixed_smem(cols) + (size_t)n_stages * stage_bytes;
 }
 
-bool gemv_plan(GemvParams& p) {
+bool gemv_plan(GemvParams& p, int consumer_warps) {
     if (p.cols % UNIT_COLS || p.cols <= 0 || p.cols > 32768) return false;
     if (p.n_stages < 2 || p.n_stages > GEMV_MAX_STAGES || (p.stage_bytes & 127)) return false;
     const int wpr = warps_per_row(p.cols);
-    const int ngrp = NCW / wpr;
+    const int ngrp = consumer_warps / wpr;
+    if (ngrp < 1) return false;
     for (int s = 0; s < p.nseg; ++s) {
         GemvSeg& sg = p.seg[s];
         if (sg.type != T_Q4_K && sg.type != T_Q6_K && sg.type != T_Q8_0) return false;
@@ -79,6 +80,7 @@ bool gemv_plan(GemvParams& p) {
         // a stage should hand every row group the same number of (pairs of) rows
         const int granule = p.pair ? ngrp : 2 * ngrp;
         if (r >= granule) r = r / granule * granule;
+        else if (!p.pair && r >= ngrp) r = ngrp;
         if (pair_adj || p.epi == EPI_QKV) r &= ~1;
         if (r < ((p.epi == EPI_QKV) ? 2 : 1)) return false;
         sg.rows_per_stage = r;
@@ -92,16 +94,21 @@ bool gemv_plan(GemvParams& p) {
     return true;
 }
 
+bool gemv_variant_ok(int abits, int nw) { return (abits == 16 && (nw == 8 || nw == 12)) || (abits == 8 && (nw == 8 || nw == 16)); }
+
 cudaError_t gemv_configure() {
-    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
 }
 
-cudaError_t gemv_launch(const GemvParams& p, int abits, int n_ctas, bool pdl, cudaStream_t s) {
+cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
+    if (!gemv_variant_ok(abits, nw)) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);
-    cfg.blockDim = dim3(GEMV_THREADS);
+    cfg.blockDim = dim3((unsigned)gemv_threads(nw));
     cfg.dynamicSmemBytes = gemv_smem_bytes(p.cols, p.n_stages, p.stage_bytes);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -109,8 +116,8 @@ cudaError_t gemv_launch(const GemvParams& p, int abits, int n_ctas, bool pdl, cu
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (abits == 16) return cudaLaunchKernelEx(&cfg, gemv_kernel<16>, p);
-    return cudaLaunchKernelEx(&cfg, gemv_kernel<8>, p);
+    if (abits == 16) return nw == 8 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<16, 12>, p);
+    return nw == 8 ? cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 16>, p);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -18,8 +18,7 @@
 
 namespace gl {
 
-constexpr int NCW = GEMV_CONSUMER_WARPS;
-constexpr int NCT = NCW * 32;
+constexpr int GEMV_MAX_WARPS = 16;      // consumer warps per CTA are a template parameter (8, 12 or 16)
 
 // shared-memory carve-up (bytes from the start of dynamic smem)
 constexpr int SM_BARS = 0;                 // full[8], empty[8] mbarriers
@@ -89,8 +88,9 @@ __device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, in
 // consumer prologue: x -> (RMSNorm) -> int8 planes in smem -> XUnit registers of this lane
 // All NCT consumer threads must call it (named barrier 1).
 // ---------------------------------------------------------------------------------------------------
-template <int ABITS>
+template <int ABITS, int NW>
 __device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, XUnit& xr) {
+    constexpr int NT = NW * 32;
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -102,71 +102,94 @@ __device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem
 
     // every read of data produced upstream uses ld.global.cg: this CTA may have been resident (and its
     // SM's L1 populated) before the producer of x finished.
+    const int half = tid & 1;
+    const int nblk = K / 32;
+    const int nblk_pad = ((nblk + NT / 2 - 1) / (NT / 2)) * (NT / 2);
+    const int niter = nblk_pad / (NT / 2);
+    const bool keep = niter <= 2;          // x stays in registers between the norm pass and the snap pass
+    float vk[2][16];
     float rstd = 1.f;
     if (p.norm_w != nullptr) {
         float ss = 0.f;
-        for (int i = tid * 4; i < K; i += NCT * 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + i));
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (keep) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int blk = (tid >> 1) + it * (NT / 2);
+                if (it < niter && blk < nblk) {
+                    const float* xb = p.x + blk * 32 + half * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(xb + 4 * q));
+                        vk[it][4 * q] = t.x; vk[it][4 * q + 1] = t.y; vk[it][4 * q + 2] = t.z; vk[it][4 * q + 3] = t.w;
+                        ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+                    }
+                }
+            }
+        } else {
+            for (int i = tid * 4; i < K; i += NT * 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + i));
+                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
         }
         ss = warp_sum(ss);
         if (lane == 0) red[warp] = ss;
-        named_bar_sync(1, NCT);
+        named_bar_sync(1, NT);
         float tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < NCW; ++w) tot += red[w];
+        for (int w = 0; w < NW; ++w) tot += red[w];
         rstd = 1.0f / sqrtf(tot / (float)K + p.eps);
     }
-    {
-        const int half = tid & 1;
-        const int nblk = K / 32;
-        const int nblk_pad = ((nblk + NCT / 2 - 1) / (NCT / 2)) * (NCT / 2);
-        for (int blk = tid >> 1; blk < nblk_pad; blk += NCT / 2) {
-            const bool live = blk < nblk;
-            float v[16];
-            float amax = 0.f;
-            if (live) {
+    for (int it = 0; it < niter; ++it) {
+        const int blk = (tid >> 1) + it * (NT / 2);
+        const bool live = blk < nblk;
+        float v[16];
+        float amax = 0.f;
+        if (live) {
+            if (p.norm_w != nullptr && keep) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = it == 0 ? vk[0][q] : vk[1][q];
+            } else {
                 const float* xb = p.x + blk * 32 + half * 16;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 t = __ldcg(reinterpret_cast<const float4*>(xb + 4 * q));
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
-                if (p.norm_w != nullptr) {
-                    const float* wb = p.norm_w + blk * 32 + half * 16;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 wv = *reinterpret_cast<const float4*>(wb + 4 * q);
-                        v[4 * q] = (v[4 * q] * rstd) * wv.x;
-                        v[4 * q + 1] = (v[4 * q + 1] * rstd) * wv.y;
-                        v[4 * q + 2] = (v[4 * q + 2] * rstd) * wv.z;
-                        v[4 * q + 3] = (v[4 * q + 3] * rstd) * wv.w;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(v[q]));
             }
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            uint32_t h4[4], l4[4];
-            int vs = 0;
-            if (live) snap16<ABITS>(v, amax, h4, l4, &vs);
-            const int vs_other = __shfl_xor_sync(0xffffffffu, vs, 1);
-            if (live) {
-                const int u = blk >> 2;
-                const int j = 2 * (blk & 3) + half;
-                const int phys = j ^ (u & 7);
-                *reinterpret_cast<uint4*>(xhi + u * 128 + phys * 16) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + u * 128 + phys * 16) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-                s16_arr[2 * blk + half] = vs;
-                if (half == 0) {
-                    const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
-                    sx_arr[blk] = sx;
-                    sm_arr[blk] = sx * (float)(vs + vs_other);
+            if (p.norm_w != nullptr) {
+                const float* wb = p.norm_w + blk * 32 + half * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wb + 4 * q);
+                    v[4 * q] = (v[4 * q] * rstd) * wv.x;
+                    v[4 * q + 1] = (v[4 * q + 1] * rstd) * wv.y;
+                    v[4 * q + 2] = (v[4 * q + 2] * rstd) * wv.z;
+                    v[4 * q + 3] = (v[4 * q + 3] * rstd) * wv.w;
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(v[q]));
+        }
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        uint32_t h4[4], l4[4];
+        int vs = 0;
+        if (live) snap16<ABITS>(v, amax, h4, l4, &vs);
+        const int vs_other = __shfl_xor_sync(0xffffffffu, vs, 1);
+        if (live) {
+            const int u = blk >> 2;
+            const int j = 2 * (blk & 3) + half;
+            const int phys = j ^ (u & 7);
+            *reinterpret_cast<uint4*>(xhi + u * 128 + phys * 16) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + u * 128 + phys * 16) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+            s16_arr[2 * blk + half] = vs;
+            if (half == 0) {
+                const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                sx_arr[blk] = sx;
+                sm_arr[blk] = sx * (float)(vs + vs_other);
             }
         }
     }
-    named_bar_sync(1, NCT);
+    named_bar_sync(1, NT);
 
     const int nu = K / UNIT_COLS;
     const int wpr = warps_per_row(K);
@@ -192,7 +215,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem
         xr.s16[4] = c1.x; xr.s16[5] = c1.y; xr.s16[6] = c1.z; xr.s16[7] = c1.w;
     }
     // the x planes may be overwritten by the next prologue only after every lane has its registers
-    named_bar_sync(1, NCT);
+    named_bar_sync(1, NT);
 }
 
 template <int ABITS>
@@ -251,16 +274,17 @@ __device__ __forceinline__ void gemv_epilogue_item(const GemvParams& p, int seg,
 // ---------------------------------------------------------------------------------------------------
 // consumer main loop over this CTA's stages.  All consumer warps call it.
 // ---------------------------------------------------------------------------------------------------
-template <int ABITS>
+template <int ABITS, int NW>
 __device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, const XUnit& xr, int cta, int n_ctas) {
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     const int nu = K / UNIT_COLS;
     const int wpr = warps_per_row(K);
-    const int ngrp = NCW / wpr;              // row groups working in parallel
+    const int ngrp = NW / wpr;               // row groups working in parallel (warps beyond ngrp*wpr only hand stages back)
     const int grp = warp / wpr, wsub = warp % wpr;
     const int u = wsub * 32 + lane;
     const bool valid = u < nu;
+    const bool in_grp = grp < ngrp;
     float* res = reinterpret_cast<float*>(smem + SM_RES);
     const int gran = (p.epi == EPI_QKV) ? 2 : 1;
     const int nwork = p.pair ? 1 : p.nseg;
@@ -284,7 +308,7 @@ __device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, ui
             mbar_wait(&ring.full[ring.st], ring.ph);
             const bool paired = pair_adj || pair_gu;
             const int step = paired ? ngrp : 2 * ngrp;      // unpaired rows are processed two at a time
-            for (int it = grp; it < nitems; it += step) {
+            for (int it = in_grp ? grp : nitems; it < nitems; it += step) {
                 int ra, rb, ga, gb;       // stage-local and global row indices of the (up to) two rows
                 if (pair_adj) { ra = 2 * it; rb = ra + 1; ga = r0 + ra; gb = ga + 1; }
                 else if (pair_gu) { ra = it; rb = n + it; ga = r0 + it; gb = ga; }

@@ -10,9 +10,8 @@ namespace gl {
 
 struct StepState;
 
-constexpr int GEMV_CONSUMER_WARPS = 8;
-constexpr int GEMV_THREADS = (GEMV_CONSUMER_WARPS + 1) * 32;
-constexpr int GEMV_MAX_PASSES = 4;
+// consumer warps per CTA: a launch-time choice among the compiled variants {8, 12, 16}
+inline int gemv_threads(int consumer_warps) { return (consumer_warps + 1) * 32; }
 constexpr int GEMV_MAX_STAGES = 8;
 constexpr int KV_PAGE_TOKENS = 16;
 
@@ -59,9 +58,11 @@ struct GemvParams {
 // host helpers
 size_t gemv_smem_bytes(int cols, int n_stages, int stage_bytes);
 // fills seg[i].rows_per_stage; returns false if the shape is outside the kernel's envelope
-bool gemv_plan(GemvParams& p);
+bool gemv_plan(GemvParams& p, int consumer_warps);
 cudaError_t gemv_configure();   // opt-in to large dynamic shared memory (once per process)
-cudaError_t gemv_launch(const GemvParams& p, int abits, int n_ctas, bool pdl, cudaStream_t s);
+cudaError_t gemv_launch(const GemvParams& p, int abits, int consumer_warps, int n_ctas, bool pdl, cudaStream_t s);
+// (abits, consumer_warps) combinations that are compiled: (16,8) (16,12) (8,8) (8,16)
+bool gemv_variant_ok(int abits, int consumer_warps);
 
 // plain fp weights (F32/F16/BF16): y = W x, fp32 accumulate, no fusion
 cudaError_t gemv_fp_launch(const void* w, int type, int rows, int cols, const float* x, float* y, cudaStream_t s);

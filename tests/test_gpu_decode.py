@@ -195,3 +195,24 @@ def test_generate_with_batched_prefill(tiny128_gguf):
                 assert ref["margins"][i] <= 5e-2
                 break
     e.close()
+
+
+@pytest.mark.parametrize("abits,warps,mega", [(16, 8, 1), (16, 12, 1), (8, 8, 1), (8, 16, 1), (16, 12, 0), (16, 8, 0), (8, 16, 0)])
+def test_kernel_variants_match_oracle(tiny128_gguf, tiny_q8_gguf, abits, warps, mega, monkeypatch):
+    """every compiled (activation bits, consumer warps) variant of the GEMV core, inside the persistent kernel
+    (mega=1) and as stand-alone per-op kernels under a CUDA graph with PDL (mega=0)"""
+    from oracle import llama_oracle as O
+    monkeypatch.setenv("GL_WARPS", str(warps))
+    monkeypatch.setenv("GL_MEGA", str(mega))
+    for path in (tiny128_gguf, tiny_q8_gguf):
+        m = O.load_gguf(path)
+        e = _engine(path, act_bits=abits, prefill_mode=1)
+        orc = O.LlamaOracle(m, act="i16" if abits == 16 else "q8", kv_f16=True)
+        toks = np.random.Generator(np.random.PCG64(77)).integers(0, m.n_vocab - 3, size=20)
+        for t in toks:
+            lg, am, lp = e.decode_step(int(t))
+            ref = orc.step(int(t))
+        assert np.abs(lg - ref).max() <= 2e-3 * np.abs(ref).max(), (path, abits, warps, mega)
+        g = e.generate(toks[:12], num_predict=6, ignore_eos=True)
+        assert g.stats.eval_count == 6
+        e.close()

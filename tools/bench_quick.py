@@ -18,9 +18,10 @@ def main():
     t0 = time.time()
     info = S.build_model(path, S.LLAMA3_8B, "q4_k_m", seed=1234, mode="random", with_vocab=False)
     print("build_s", round(time.time() - t0, 1), info, flush=True)
-    cfgs = ({}, {"GL_MEGA": "0"}, {"GL_ACT_BITS": "8"}, {"GL_MEGA_SLOT_KB": "24"}, {"GL_MEGA_SLOT_KB": "48"}, {"GL_MEGA_SLOTS": "3"}, {"GL_ATTN_SPLITS": "8"})
+    cfgs = ({}, {"GL_WARPS": "8"}, {"GL_ACT_BITS": "8"}, {"GL_ACT_BITS": "8", "GL_WARPS": "8"}, {"GL_MEGA": "0"},
+            {"GL_MEGA_SLOT_KB": "54"}, {"GL_MEGA_SLOT_KB": "27"})
     for cfg in cfgs:
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_KB", "GL_MEGA_SLOTS", "GL_ATTN_SPLITS"):
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_KB", "GL_MEGA_SLOTS", "GL_ATTN_SPLITS", "GL_WARPS"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         t0 = time.time()
