@@ -1,0 +1,330 @@
+// N-API shim over the C ABI (include/gridllm_native.h).  Thin by design: every export forwards to exactly one
+// gl_* call; blocking calls run on the libuv pool (napi_create_async_work) and per-token callbacks reach JS
+// through a napi_threadsafe_function, so the worker's heartbeat timers (WorkerClientService.ts:316-323) keep
+// firing during a long job.  node_api.h is not present in the build image, so this file is compiled only
+// where it exists (see host/napi/binding.gyp); the same ABI is exercised from Python (gridllm_b200/native.py).
+//
+// JS surface (consumed by host/src/NativeInferenceService.ts):
+//   deviceCount(): number
+//   createEngine(path, device, {maxCtx, actBits}) -> external
+//   engineInfo(engine) -> {name, quantization, nParams, fileBytes, nVocab, nCtx, hasTokenizer, ...}
+//   tokenize(engine, text, addBos, parseSpecial) -> Int32Array ; detokenize(engine, Int32Array) -> string
+//   generate(engine, Int32Array prompt, {numPredict, ignoreEos, stopIds}, onToken|null) -> Promise<{ids, logprobs, stats}>
+//   embed(engine, Int32Array ids, Int32Array offsets) -> Promise<{embeddings: Float32Array, stats}>
+//   destroyEngine(engine)
+#include <node_api.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gridllm_native.h"
+
+namespace {
+
+#define NAPI_OK(call)                                                   \
+    do {                                                                \
+        if ((call) != napi_ok) {                                        \
+            napi_throw_error(env, nullptr, "N-API call failed: " #call); \
+            return nullptr;                                             \
+        }                                                               \
+    } while (0)
+
+napi_value throw_gl(napi_env env, const char* what) {
+    std::string m = std::string(what) + ": " + gl_last_error();
+    napi_throw_error(env, nullptr, m.c_str());
+    return nullptr;
+}
+
+gl_engine* unwrap(napi_env env, napi_value v) {
+    void* p = nullptr;
+    napi_get_value_external(env, v, &p);
+    return static_cast<gl_engine*>(p);
+}
+
+napi_value DeviceCount(napi_env env, napi_callback_info) {
+    int n = 0;
+    gl_device_count(&n);
+    napi_value out;
+    NAPI_OK(napi_create_int32(env, n, &out));
+    return out;
+}
+
+napi_value CreateEngine(napi_env env, napi_callback_info info) {
+    size_t argc = 3;
+    napi_value argv[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    char path[4096];
+    size_t len = 0;
+    NAPI_OK(napi_get_value_string_utf8(env, argv[0], path, sizeof path, &len));
+    int32_t device = 0;
+    NAPI_OK(napi_get_value_int32(env, argv[1], &device));
+    gl_engine_opts o{};
+    if (argc > 2) {
+        napi_value v;
+        if (napi_get_named_property(env, argv[2], "maxCtx", &v) == napi_ok) napi_get_value_int32(env, v, &o.max_ctx);
+        if (napi_get_named_property(env, argv[2], "actBits", &v) == napi_ok) napi_get_value_int32(env, v, &o.act_bits);
+    }
+    o.use_graph = 1;
+    o.use_pdl = 1;
+    gl_engine* e = nullptr;
+    if (gl_engine_create(path, device, &o, &e) != GL_OK) return throw_gl(env, "gl_engine_create");
+    napi_value ext;
+    NAPI_OK(napi_create_external(env, e, [](napi_env, void* p, void*) { gl_engine_destroy(static_cast<gl_engine*>(p)); }, nullptr, &ext));
+    return ext;
+}
+
+// ---- generate: async work + threadsafe token callback --------------------------------------------------
+struct GenJob {
+    gl_engine* e;
+    std::vector<int32_t> prompt, stop_ids, ids;
+    std::vector<float> lps;
+    gl_sample_opts so{};
+    gl_gen_stats st{};
+    int rc = 0;
+    std::string err;
+    napi_threadsafe_function tsfn = nullptr;
+    napi_deferred deferred = nullptr;
+    napi_async_work work = nullptr;
+};
+struct Tok { int32_t id; float lp; std::string piece; };
+
+int on_token(void* user, int32_t id, float lp, const char* piece, int32_t n) {
+    GenJob* j = static_cast<GenJob*>(user);
+    if (!j->tsfn) return 0;
+    Tok* t = new Tok{id, lp, piece ? std::string(piece, n) : std::string()};
+    return napi_call_threadsafe_function(j->tsfn, t, napi_tsfn_nonblocking) == napi_ok ? 0 : 1;
+}
+
+void call_js(napi_env env, napi_value cb, void*, void* data) {
+    Tok* t = static_cast<Tok*>(data);
+    if (env && cb) {
+        napi_value argv[3], undef;
+        napi_create_int32(env, t->id, &argv[0]);
+        napi_create_double(env, t->lp, &argv[1]);
+        napi_create_string_utf8(env, t->piece.data(), t->piece.size(), &argv[2]);
+        napi_get_undefined(env, &undef);
+        napi_call_function(env, undef, cb, 3, argv, nullptr);
+    }
+    delete t;
+}
+
+void gen_execute(napi_env, void* data) {
+    GenJob* j = static_cast<GenJob*>(data);
+    j->so.n_stop_ids = (int32_t)j->stop_ids.size();
+    j->so.stop_ids = j->stop_ids.data();
+    j->ids.resize(j->so.num_predict > 0 ? j->so.num_predict : 128);
+    j->lps.resize(j->ids.size());
+    j->rc = gl_generate(j->e, j->prompt.data(), (int32_t)j->prompt.size(), &j->so, on_token, j, j->ids.data(), j->lps.data(), &j->st);
+    if (j->rc != GL_OK) j->err = gl_last_error();
+}
+
+void gen_complete(napi_env env, napi_status, void* data) {
+    GenJob* j = static_cast<GenJob*>(data);
+    if (j->tsfn) napi_release_threadsafe_function(j->tsfn, napi_tsfn_release);
+    if (j->rc != GL_OK && j->rc != GL_ERR_CANCELLED) {
+        napi_value msg, err;
+        napi_create_string_utf8(env, j->err.c_str(), NAPI_AUTO_LENGTH, &msg);
+        napi_create_error(env, nullptr, msg, &err);
+        napi_reject_deferred(env, j->deferred, err);
+    } else {
+        napi_value out, v, ab;
+        napi_create_object(env, &out);
+        void* p;
+        napi_create_arraybuffer(env, j->st.eval_count * 4, &p, &ab);
+        memcpy(p, j->ids.data(), j->st.eval_count * 4);
+        napi_create_typedarray(env, napi_int32_array, j->st.eval_count, ab, 0, &v);
+        napi_set_named_property(env, out, "ids", v);
+        napi_create_arraybuffer(env, j->st.eval_count * 4, &p, &ab);
+        memcpy(p, j->lps.data(), j->st.eval_count * 4);
+        napi_create_typedarray(env, napi_float32_array, j->st.eval_count, ab, 0, &v);
+        napi_set_named_property(env, out, "logprobs", v);
+        napi_value st;
+        napi_create_object(env, &st);
+        auto seti = [&](const char* k, double d) { napi_value x; napi_create_double(env, d, &x); napi_set_named_property(env, st, k, x); };
+        seti("promptEvalCount", j->st.prompt_eval_count); seti("evalCount", j->st.eval_count);
+        seti("promptEvalDurationNs", (double)j->st.prompt_eval_duration_ns); seti("evalDurationNs", (double)j->st.eval_duration_ns);
+        seti("totalDurationNs", (double)j->st.total_duration_ns); seti("loadDurationNs", (double)j->st.load_duration_ns);
+        seti("doneReason", j->st.done_reason);
+        napi_set_named_property(env, out, "stats", st);
+        napi_resolve_deferred(env, j->deferred, out);
+    }
+    napi_delete_async_work(env, j->work);
+    delete j;
+}
+
+napi_value Generate(napi_env env, napi_callback_info info) {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    GenJob* j = new GenJob();
+    j->e = unwrap(env, argv[0]);
+    void* data; size_t n; napi_typedarray_type ty; napi_value ab; size_t off;
+    NAPI_OK(napi_get_typedarray_info(env, argv[1], &ty, &n, &data, &ab, &off));
+    j->prompt.assign(static_cast<int32_t*>(data), static_cast<int32_t*>(data) + n);
+    napi_value v;
+    j->so.top_p = 1.f;
+    if (napi_get_named_property(env, argv[2], "numPredict", &v) == napi_ok) napi_get_value_int32(env, v, &j->so.num_predict);
+    bool b = false;
+    if (napi_get_named_property(env, argv[2], "ignoreEos", &v) == napi_ok && napi_get_value_bool(env, v, &b) == napi_ok) j->so.ignore_eos = b;
+    napi_valuetype vt;
+    if (argc > 3 && napi_typeof(env, argv[3], &vt) == napi_ok && vt == napi_function) {
+        napi_value name;
+        napi_create_string_utf8(env, "gl_token", NAPI_AUTO_LENGTH, &name);
+        NAPI_OK(napi_create_threadsafe_function(env, argv[3], nullptr, name, 0, 1, nullptr, nullptr, nullptr, call_js, &j->tsfn));
+    }
+    napi_value promise, rname;
+    NAPI_OK(napi_create_promise(env, &j->deferred, &promise));
+    napi_create_string_utf8(env, "gl_generate", NAPI_AUTO_LENGTH, &rname);
+    NAPI_OK(napi_create_async_work(env, nullptr, rname, gen_execute, gen_complete, j, &j->work));
+    NAPI_OK(napi_queue_async_work(env, j->work));
+    return promise;
+}
+
+napi_value EngineInfo(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    gl_model_info mi{};
+    if (gl_engine_info(unwrap(env, argv[0]), &mi) != GL_OK) return throw_gl(env, "gl_engine_info");
+    napi_value out, v;
+    NAPI_OK(napi_create_object(env, &out));
+    auto sets = [&](const char* k, const char* s) { napi_create_string_utf8(env, s, NAPI_AUTO_LENGTH, &v); napi_set_named_property(env, out, k, v); };
+    auto setd = [&](const char* k, double d) { napi_create_double(env, d, &v); napi_set_named_property(env, out, k, v); };
+    sets("arch", mi.arch); sets("name", mi.name); sets("quantization", mi.quantization);
+    setd("nParams", (double)mi.n_params); setd("fileBytes", (double)mi.file_bytes); setd("nVocab", mi.n_vocab); setd("nCtx", mi.n_ctx);
+    setd("nLayer", mi.n_layer); setd("nEmbd", mi.n_embd); setd("hasTokenizer", mi.has_tokenizer); setd("device", mi.device);
+    return out;
+}
+
+napi_value Tokenize(napi_env env, napi_callback_info info) {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    size_t len = 0;
+    NAPI_OK(napi_get_value_string_utf8(env, argv[1], nullptr, 0, &len));
+    std::string text(len, '\0');
+    NAPI_OK(napi_get_value_string_utf8(env, argv[1], &text[0], len + 1, &len));
+    bool add_bos = true, special = false;
+    if (argc > 2) napi_get_value_bool(env, argv[2], &add_bos);
+    if (argc > 3) napi_get_value_bool(env, argv[3], &special);
+    std::vector<int32_t> ids(len + 8);
+    int32_t n = 0;
+    if (gl_tokenize(unwrap(env, argv[0]), text.data(), (int32_t)len, add_bos, special, ids.data(), (int32_t)ids.size(), &n) != GL_OK)
+        return throw_gl(env, "gl_tokenize");
+    napi_value ab, out;
+    void* p;
+    NAPI_OK(napi_create_arraybuffer(env, (size_t)n * 4, &p, &ab));
+    memcpy(p, ids.data(), (size_t)n * 4);
+    NAPI_OK(napi_create_typedarray(env, napi_int32_array, n, ab, 0, &out));
+    return out;
+}
+
+napi_value Detokenize(napi_env env, napi_callback_info info) {
+    size_t argc = 2;
+    napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    void* data; size_t n; napi_typedarray_type ty; napi_value ab; size_t off;
+    NAPI_OK(napi_get_typedarray_info(env, argv[1], &ty, &n, &data, &ab, &off));
+    std::string buf(16 * (n + 1), '\0');
+    int32_t len = 0;
+    if (gl_detokenize(unwrap(env, argv[0]), static_cast<int32_t*>(data), (int32_t)n, &buf[0], (int32_t)buf.size(), &len) != GL_OK)
+        return throw_gl(env, "gl_detokenize");
+    napi_value out;
+    NAPI_OK(napi_create_string_utf8(env, buf.data(), len, &out));
+    return out;
+}
+
+// embed: same async-work pattern as generate, without a token callback
+struct EmbJob {
+    gl_engine* e;
+    std::vector<int32_t> ids, offs;
+    std::vector<float> out;
+    gl_gen_stats st{};
+    int rc = 0, n_embd = 0;
+    std::string err;
+    napi_deferred deferred = nullptr;
+    napi_async_work work = nullptr;
+};
+
+void emb_execute(napi_env, void* data) {
+    EmbJob* j = static_cast<EmbJob*>(data);
+    gl_model_info mi{};
+    gl_engine_info(j->e, &mi);
+    j->n_embd = mi.n_embd;
+    const int n_seq = (int)j->offs.size() - 1;
+    j->out.resize((size_t)n_seq * mi.n_embd);
+    j->rc = gl_embed(j->e, j->ids.data(), j->offs.data(), n_seq, j->out.data(), &j->st);
+    if (j->rc != GL_OK) j->err = gl_last_error();
+}
+
+void emb_complete(napi_env env, napi_status, void* data) {
+    EmbJob* j = static_cast<EmbJob*>(data);
+    if (j->rc != GL_OK) {
+        napi_value msg, err;
+        napi_create_string_utf8(env, j->err.c_str(), NAPI_AUTO_LENGTH, &msg);
+        napi_create_error(env, nullptr, msg, &err);
+        napi_reject_deferred(env, j->deferred, err);
+    } else {
+        napi_value out, ab, v, st;
+        void* p;
+        napi_create_object(env, &out);
+        napi_create_arraybuffer(env, j->out.size() * 4, &p, &ab);
+        memcpy(p, j->out.data(), j->out.size() * 4);
+        napi_create_typedarray(env, napi_float32_array, j->out.size(), ab, 0, &v);
+        napi_set_named_property(env, out, "embeddings", v);
+        napi_create_object(env, &st);
+        auto seti = [&](const char* k, double d) { napi_value x; napi_create_double(env, d, &x); napi_set_named_property(env, st, k, x); };
+        seti("promptEvalCount", j->st.prompt_eval_count); seti("totalDurationNs", (double)j->st.total_duration_ns);
+        seti("loadDurationNs", (double)j->st.load_duration_ns);
+        napi_set_named_property(env, out, "stats", st);
+        napi_resolve_deferred(env, j->deferred, out);
+    }
+    napi_delete_async_work(env, j->work);
+    delete j;
+}
+
+napi_value Embed(napi_env env, napi_callback_info info) {
+    size_t argc = 3;
+    napi_value argv[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    EmbJob* j = new EmbJob();
+    j->e = unwrap(env, argv[0]);
+    void* data; size_t n; napi_typedarray_type ty; napi_value ab; size_t off;
+    NAPI_OK(napi_get_typedarray_info(env, argv[1], &ty, &n, &data, &ab, &off));
+    j->ids.assign(static_cast<int32_t*>(data), static_cast<int32_t*>(data) + n);
+    NAPI_OK(napi_get_typedarray_info(env, argv[2], &ty, &n, &data, &ab, &off));
+    j->offs.assign(static_cast<int32_t*>(data), static_cast<int32_t*>(data) + n);
+    napi_value promise, rname;
+    NAPI_OK(napi_create_promise(env, &j->deferred, &promise));
+    napi_create_string_utf8(env, "gl_embed", NAPI_AUTO_LENGTH, &rname);
+    NAPI_OK(napi_create_async_work(env, nullptr, rname, emb_execute, emb_complete, j, &j->work));
+    NAPI_OK(napi_queue_async_work(env, j->work));
+    return promise;
+}
+
+napi_value DestroyEngine(napi_env env, napi_callback_info) {
+    // engines are released by the external's finalizer (CreateEngine); kept for API symmetry
+    napi_value u;
+    napi_get_undefined(env, &u);
+    return u;
+}
+
+napi_value Init(napi_env env, napi_value exports) {
+    napi_property_descriptor d[] = {
+        {"deviceCount", nullptr, DeviceCount, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"createEngine", nullptr, CreateEngine, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"generate", nullptr, Generate, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"engineInfo", nullptr, EngineInfo, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"tokenize", nullptr, Tokenize, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"detokenize", nullptr, Detokenize, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"embed", nullptr, Embed, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"destroyEngine", nullptr, DestroyEngine, nullptr, nullptr, nullptr, napi_default, nullptr},
+    };
+    napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
+    return exports;
+}
+
+}  // namespace
+
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)
