@@ -151,4 +151,10 @@ int gl_time_decode(gl_engine* e, int32_t ctx_len, int32_t iters, float* ms_per_s
     return ret(e->impl->time_decode(ctx_len, iters, ms_per_step, launches_per_step));
 }
 
+// profiling aid (not part of the reference-facing ABI): per-phase globaltimer stamps of the persistent kernel
+int gl_debug_mega_trace(gl_engine* e, unsigned long long* out, int32_t cap, int32_t* n_ctas, int32_t* n_phases) {
+    if (!e || !out) return bad("gl_debug_mega_trace: null argument");
+    return ret(e->impl->mega_trace(out, cap, n_ctas, n_phases));
+}
+
 }  // extern "C"

@@ -19,6 +19,12 @@ namespace gl {
 
 namespace {
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -28,15 +34,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // all consumer threads of every CTA call this the same number of times
 template <int NT>
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int tid) {
+    // bar.sync orders every consumer thread's writes before thread 0's release; the acquire load + bar.sync hand the
+    // other CTAs' writes to every thread of this one.  No full fences.
     named_bar_sync(1, NT);
     if (tid == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned spins = 0;
         while ((int)(ld_acquire_u32(counter) - target) < 0) {
             if (++spins > (1u << 28)) __trap();
         }
-        __threadfence();
     }
     named_bar_sync(1, NT);
 }
@@ -186,17 +192,16 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
             mp.part_ml[((size_t)head * n_splits + split) * 2 + 1] = l_run;
         }
     }
-    __threadfence();
     named_bar_sync(1, NT);
     if (tid == 0) {
-        const unsigned ticket = atomicAdd(mp.attn_counters + kvh, 1u);
+        unsigned ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(mp.attn_counters + kvh) : "memory");
         const int last = (ticket == (unsigned)n_splits - 1);
         if (last) mp.attn_counters[kvh] = 0;
         *smem_flag = last;
     }
     named_bar_sync(1, NT);
     if (*smem_flag && active) {
-        __threadfence();
         // lane s holds (m, l) of split s; n_splits <= 32
         float ms = -INFINITY, ls = 0.f;
         if (lane < n_splits) {
@@ -209,12 +214,22 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
         float acc[DPL];
 #pragma unroll
         for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
-        for (int s = 0; s < n_splits; ++s) {
-            const float w = __shfl_sync(0xffffffffu, wl, s);
-            if (w == 0.f) continue;
-            const float* po = mp.part_o + ((size_t)head * n_splits + s) * HD + lane * DPL;
+        const float* pbase = mp.part_o + (size_t)head * n_splits * HD + lane * DPL;
+        for (int s0 = 0; s0 < n_splits; s0 += 8) {          // 8 splits' partial outputs in flight at a time
+            float po[8][DPL];
 #pragma unroll
-            for (int d = 0; d < DPL; ++d) acc[d] += w * __ldcg(po + d);
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int d = 0; d < DPL; ++d) po[i][d] = (s0 + i < n_splits) ? __ldcg(pbase + (size_t)(s0 + i) * HD + d) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float w = __shfl_sync(0xffffffffu, wl, (s0 + i) & 31);
+                if (s0 + i < n_splits) {
+#pragma unroll
+                    for (int d = 0; d < DPL; ++d) acc[d] += w * po[i][d];
+                }
+            }
         }
         const float inv = 1.0f / den;
         float* out = mp.attn_out + (size_t)head * HD + lane * DPL;
@@ -290,9 +305,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
         for (int ph = 0; ph < mp.n_phases; ++ph) {
             const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<const uint8_t*>(sdesc) + dslot * 256);
             const int kind = P.kind;
+            unsigned long long* tr = (mp.trace != nullptr && tid == 0) ? mp.trace + ((size_t)cta * (mp.n_phases + 1) + ph) * 4 : nullptr;
+            if (tr) tr[0] = gtime();
             if (kind == PH_GEMV) {
-                gemv_prologue<ABITS, NW>(P.g, smem, tid, xr);
-                gemv_consume<ABITS, NW>(P.g, ring, smem, tid, xr, cta, G);
+                const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid, xr);
+                if (tr) tr[1] = gtime();
+                gemv_consume<ABITS, NW>(P.g, ring, smem, tid, xr, scale, cta, G);
                 if (P.flags & PHF_HEAD) {
                     // per-CTA softmax statistics over the logits rows this CTA produced
                     named_bar_sync(1, NT);
@@ -344,11 +362,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
                     else attn_item<2, NT>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
                 }
             }
+            if (tr) tr[2] = gtime();
             // the next phase's descriptor travels while this CTA waits at the barrier
             if (ph + 1 < mp.n_phases) prefetch_desc(ph + 1, dslot ^ 1);
             dslot ^= 1;
             ++nbar;
             grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
+            if (tr) tr[3] = gtime();
         }
 
         // ---- sampling / state advance (CTA 0), published to everyone by the barrier at the top of the next step

@@ -54,6 +54,7 @@ struct MegaParams {
     int max_out;
     // ring
     int n_slots, slot_bytes, max_cols;
+    unsigned long long* trace; // optional [n_ctas][n_phases+1][4] globaltimer stamps of the LAST step (GL_MEGA_TRACE=1)
     int n_prod;                // GEMV phases per token (entries of prod[] in use)
     ProdDesc prod[MEGA_MAX_GEMV_PHASES];
 };

@@ -150,7 +150,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     use_pdl_ = !(opts && opts->use_pdl == 0) && env_int("GL_PDL", 1) != 0;
     fused_ = env_int("GL_FUSE", 1) != 0;
     abits_ = env_int("GL_ACT_BITS", abits_) == 8 ? 8 : 16;
-    nw_ = env_int("GL_WARPS", abits_ == 16 ? 12 : 16);
+    nw_ = env_int("GL_WARPS", 8);          // measured: 8 consumer warps beat 12 / 16 (per-stage costs per warp dominate)
     if (!gemv_variant_ok(abits_, nw_)) nw_ = 8;
     stage_kb_ = env_int("GL_STAGE_KB", 24);
     smem_kb_ = env_int("GL_SMEM_KB", 110);
@@ -614,6 +614,12 @@ Status Engine::build_mega() {
     CU(cudaMalloc((void**)&head_part_, (size_t)sm_count_ * 16));
     allocs_.push_back(head_part_);
     CU(cudaMemset(head_part_, 0, (size_t)sm_count_ * 16));
+    if (env_int("GL_MEGA_TRACE", 0)) {
+        const size_t n = (size_t)sm_count_ * (mega_n_head_ + 1) * 4;
+        CU(cudaMalloc((void**)&mega_trace_, n * 8));
+        allocs_.push_back(mega_trace_);
+        CU(cudaMemset(mega_trace_, 0, n * 8));
+    }
     use_mega_ = true;
     launches_head_ = 1;
     launches_nohead_ = 1;
@@ -637,6 +643,7 @@ Status Engine::launch_mega(int n_steps, bool with_head, bool keep_logits) {
     mp.logits_keep = keep_logits ? logits_keep_ : nullptr;
     mp.max_out = keep_logits ? keep_cap_ : max_out_;
     mp.n_slots = mega_slots_; mp.slot_bytes = mega_slot_bytes_; mp.max_cols = mega_max_cols_;
+    mp.trace = with_head ? mega_trace_ : nullptr;
     // producer descriptors: all GEMV phases of the token; the head phase is the last entry
     mp.n_prod = with_head ? (int)mega_prod_.size() : (int)mega_prod_.size() - 1;
     std::memcpy(mp.prod, mega_prod_.data(), mega_prod_.size() * sizeof(ProdDesc));
@@ -961,6 +968,16 @@ Status Engine::gemv_tensor(const std::string& name, const float* x, float* y, in
     cudaFree(dx);
     cudaFree(dy);
     return s;
+}
+
+Status Engine::mega_trace(unsigned long long* out, int cap, int* n_ctas, int* n_phases) {
+    if (!mega_trace_) return fail(GL_ERR_UNSUPPORTED, "trace not enabled (GL_MEGA_TRACE=1)");
+    const size_t n = (size_t)sm_count_ * (mega_n_head_ + 1) * 4;
+    if ((size_t)cap < n) return fail(GL_ERR_INVALID, "trace buffer too small");
+    CU(cudaMemcpy(out, mega_trace_, n * 8, cudaMemcpyDeviceToHost));
+    *n_ctas = sm_count_;
+    *n_phases = mega_n_head_;
+    return {};
 }
 
 Status Engine::time_decode(int ctx_len, int iters, float* ms, int* launches) {

@@ -61,6 +61,7 @@ public:
     Status kv_reset();
     Status prefill(const int32_t* ids, int n, float* last_logits);
     Status time_decode(int ctx_len, int iters, float* ms, int* launches);
+    Status mega_trace(unsigned long long* out, int cap, int* n_ctas, int* n_phases);
     int position() const { return host_pos_; }
     const Tokenizer& tokenizer() const { return tok_; }
 
@@ -120,6 +121,7 @@ private:
     float* head_part_ = nullptr;
     int mega_launches_ = 0;
     int mega_splits_ = 16;
+    unsigned long long* mega_trace_ = nullptr;
     std::vector<ProdDesc> mega_prod_;
 
     // device state

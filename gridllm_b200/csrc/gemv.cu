@@ -52,8 +52,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     }
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
     XUnit xr;
-    gemv_prologue<ABITS, NW>(p, smem, tid, xr);
-    gemv_consume<ABITS, NW>(p, ring, smem, tid, xr, blockIdx.x, gridDim.x);
+    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, xr);
+    gemv_consume<ABITS, NW>(p, ring, smem, tid, xr, scale, blockIdx.x, gridDim.x);
 }
 
 }  // namespace

@@ -88,9 +88,14 @@ __device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, in
 // consumer prologue: x -> (RMSNorm) -> int8 planes in smem -> XUnit registers of this lane
 // All NCT consumer threads must call it (named barrier 1).
 // ---------------------------------------------------------------------------------------------------
+// Returns the scalar every row sum of this phase must be multiplied by: 1, or the RMSNorm factor
+// rstd = 1/sqrt(mean(x^2)+eps).  The fixed-point integers v = rint(x*w / amax_blk(x*w) * RANGE) do not depend on
+// rstd (it cancels), so the planes are built from x*w while the sum of squares is still being reduced, and rstd is
+// applied once per output row.  One named barrier in total.
 template <int ABITS, int NW>
-__device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, XUnit& xr) {
+__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, XUnit& xr) {
     constexpr int NT = NW * 32;
+    constexpr int MAX_IT = 4;              // K <= MAX_IT * NT/2 * 32 columns stay in registers (16384 at 8 warps)
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -104,92 +109,74 @@ __device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem
     // SM's L1 populated) before the producer of x finished.
     const int half = tid & 1;
     const int nblk = K / 32;
-    const int nblk_pad = ((nblk + NT / 2 - 1) / (NT / 2)) * (NT / 2);
-    const int niter = nblk_pad / (NT / 2);
-    const bool keep = niter <= 2;          // x stays in registers between the norm pass and the snap pass
-    float vk[2][16];
-    float rstd = 1.f;
-    if (p.norm_w != nullptr) {
-        float ss = 0.f;
-        if (keep) {
+    const bool norm = p.norm_w != nullptr;
+    float ss = 0.f;
+    for (int it0 = 0; it0 * (NT / 2) < nblk; it0 += MAX_IT) {
+        float v[MAX_IT][16];
+        // all loads of the batch are issued before anything waits on them: one L2 round trip
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int blk = (tid >> 1) + it * (NT / 2);
-                if (it < niter && blk < nblk) {
-                    const float* xb = p.x + blk * 32 + half * 16;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 t = __ldcg(reinterpret_cast<const float4*>(xb + 4 * q));
-                        vk[it][4 * q] = t.x; vk[it][4 * q + 1] = t.y; vk[it][4 * q + 2] = t.z; vk[it][4 * q + 3] = t.w;
-                        ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
-                    }
-                }
-            }
-        } else {
-            for (int i = tid * 4; i < K; i += NT * 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + i));
-                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            }
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) red[warp] = ss;
-        named_bar_sync(1, NT);
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) tot += red[w];
-        rstd = 1.0f / sqrtf(tot / (float)K + p.eps);
-    }
-    for (int it = 0; it < niter; ++it) {
-        const int blk = (tid >> 1) + it * (NT / 2);
-        const bool live = blk < nblk;
-        float v[16];
-        float amax = 0.f;
-        if (live) {
-            if (p.norm_w != nullptr && keep) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = it == 0 ? vk[0][q] : vk[1][q];
-            } else {
+        for (int it = 0; it < MAX_IT; ++it) {
+            const int blk = (tid >> 1) + (it0 + it) * (NT / 2);
+            if (blk < nblk) {
                 const float* xb = p.x + blk * 32 + half * 16;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 t = __ldcg(reinterpret_cast<const float4*>(xb + 4 * q));
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                    v[it][4 * q] = t.x; v[it][4 * q + 1] = t.y; v[it][4 * q + 2] = t.z; v[it][4 * q + 3] = t.w;
                 }
             }
-            if (p.norm_w != nullptr) {
-                const float* wb = p.norm_w + blk * 32 + half * 16;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wb + 4 * q);
-                    v[4 * q] = (v[4 * q] * rstd) * wv.x;
-                    v[4 * q + 1] = (v[4 * q + 1] * rstd) * wv.y;
-                    v[4 * q + 2] = (v[4 * q + 2] * rstd) * wv.z;
-                    v[4 * q + 3] = (v[4 * q + 3] * rstd) * wv.w;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(v[q]));
         }
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        uint32_t h4[4], l4[4];
-        int vs = 0;
-        if (live) snap16<ABITS>(v, amax, h4, l4, &vs);
-        const int vs_other = __shfl_xor_sync(0xffffffffu, vs, 1);
-        if (live) {
-            const int u = blk >> 2;
-            const int j = 2 * (blk & 3) + half;
-            const int phys = j ^ (u & 7);
-            *reinterpret_cast<uint4*>(xhi + u * 128 + phys * 16) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-            if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + u * 128 + phys * 16) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-            s16_arr[2 * blk + half] = vs;
-            if (half == 0) {
-                const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
-                sx_arr[blk] = sx;
-                sm_arr[blk] = sx * (float)(vs + vs_other);
+#pragma unroll
+        for (int it = 0; it < MAX_IT; ++it) {
+            const int blk = (tid >> 1) + (it0 + it) * (NT / 2);
+            const bool live = blk < nblk;        // uniform over the lane pair that shares a block
+            float amax = 0.f;
+            if (live) {
+                if (norm) {
+                    const float* wb = p.norm_w + blk * 32 + half * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wb + 4 * q);
+                        ss += v[it][4 * q] * v[it][4 * q] + v[it][4 * q + 1] * v[it][4 * q + 1] + v[it][4 * q + 2] * v[it][4 * q + 2] +
+                              v[it][4 * q + 3] * v[it][4 * q + 3];
+                        v[it][4 * q] *= wv.x; v[it][4 * q + 1] *= wv.y; v[it][4 * q + 2] *= wv.z; v[it][4 * q + 3] *= wv.w;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(v[it][q]));
+            }
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            uint32_t h4[4], l4[4];
+            int vs = 0;
+            if (live) snap16<ABITS>(v[it], amax, h4, l4, &vs);
+            const int vs_other = __shfl_xor_sync(0xffffffffu, vs, 1);
+            if (live) {
+                const int u = blk >> 2;
+                const int j = 2 * (blk & 3) + half;
+                const int phys = j ^ (u & 7);
+                *reinterpret_cast<uint4*>(xhi + u * 128 + phys * 16) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + u * 128 + phys * 16) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+                s16_arr[2 * blk + half] = vs;
+                if (half == 0) {
+                    const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                    sx_arr[blk] = sx;
+                    sm_arr[blk] = sx * (float)(vs + vs_other);
+                }
             }
         }
     }
+    if (norm) {
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+    }
     named_bar_sync(1, NT);
+    float scale = 1.f;
+    if (norm) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += red[w];
+        scale = 1.0f / sqrtf(tot / (float)K + p.eps);
+    }
 
     const int nu = K / UNIT_COLS;
     const int wpr = warps_per_row(K);
@@ -214,8 +201,9 @@ __device__ __forceinline__ void gemv_prologue(const GemvParams& p, uint8_t* smem
         xr.s16[0] = c0.x; xr.s16[1] = c0.y; xr.s16[2] = c0.z; xr.s16[3] = c0.w;
         xr.s16[4] = c1.x; xr.s16[5] = c1.y; xr.s16[6] = c1.z; xr.s16[7] = c1.w;
     }
-    // the x planes may be overwritten by the next prologue only after every lane has its registers
-    named_bar_sync(1, NT);
+    // NOTE: the planes (and red[]) are rewritten only by the NEXT prologue, which every caller separates from this
+    // point by a CTA-wide barrier (end of kernel, or the grid barrier of the persistent kernel).
+    return scale;
 }
 
 template <int ABITS>
@@ -275,7 +263,8 @@ __device__ __forceinline__ void gemv_epilogue_item(const GemvParams& p, int seg,
 // consumer main loop over this CTA's stages.  All consumer warps call it.
 // ---------------------------------------------------------------------------------------------------
 template <int ABITS, int NW>
-__device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, const XUnit& xr, int cta, int n_ctas) {
+__device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, const XUnit& xr, float scale, int cta,
+                                             int n_ctas) {
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     const int nu = K / UNIT_COLS;
@@ -346,6 +335,8 @@ __device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, ui
                     buf ^= 1;     // double buffer: the next item's partials never race the reader of this one
                 }
                 if (lane == 0 && wsub == 0) {
+                    sum.x *= scale;          // RMSNorm factor of the fused prologue (1 when there is no norm)
+                    sum.y *= scale;
                     if (paired) {
                         gemv_epilogue_item(p, s, ga, sum.x, sum.y, pre0, pre1, ec);
                     } else {

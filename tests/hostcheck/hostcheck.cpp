@@ -74,3 +74,27 @@ extern "C" int hc_gguf_probe(const char* path, char* arch, int cap, uint64_t* n_
     *total_bytes = tot;
     return (int)f.tensors.size();
 }
+
+// tokenizer (product code, gridllm_b200/csrc/tokenizer.cpp) driven from the CPU tests
+#include "../../gridllm_b200/csrc/tokenizer.h"
+extern "C" int hc_tokenize(const char* gguf_path, const char* text, int add_bos, int parse_special, int32_t* ids, int cap) {
+    GGUFFile f;
+    if (!f.open(gguf_path).empty()) return -1;
+    Tokenizer t;
+    if (!t.load(f)) return -2;
+    std::vector<int32_t> v = t.encode(text, add_bos != 0, parse_special != 0);
+    if ((int)v.size() > cap) return -3;
+    for (size_t i = 0; i < v.size(); ++i) ids[i] = v[i];
+    return (int)v.size();
+}
+extern "C" int hc_detokenize(const char* gguf_path, const int32_t* ids, int n, char* buf, int cap) {
+    GGUFFile f;
+    if (!f.open(gguf_path).empty()) return -1;
+    Tokenizer t;
+    if (!t.load(f)) return -2;
+    std::string s = t.decode(ids, n);
+    if ((int)s.size() >= cap) return -3;
+    memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    return (int)s.size();
+}

@@ -212,7 +212,10 @@ def test_kernel_variants_match_oracle(tiny128_gguf, tiny_q8_gguf, abits, warps, 
         for t in toks:
             lg, am, lp = e.decode_step(int(t))
             ref = orc.step(int(t))
-        assert np.abs(lg - ref).max() <= 2e-3 * np.abs(ref).max(), (path, abits, warps, mega)
+        # int8 activations are discontinuous (a rounding flip moves an activation by 1/127 of its block max): fp32-vs-fp64
+        # differences upstream show at the 1e-2 level after 20 positions; the 15-bit default stays at 2e-3
+        tol = 2e-3 if abits == 16 else 3e-2
+        assert np.abs(lg - ref).max() <= tol * np.abs(ref).max(), (path, abits, warps, mega)
         g = e.generate(toks[:12], num_predict=6, ignore_eos=True)
         assert g.stats.eval_count == 6
         e.close()

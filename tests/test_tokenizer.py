@@ -1,0 +1,50 @@
+"""CPU: the engine's byte-level BPE tokenizer (gridllm_b200/csrc/tokenizer.cpp) on the synthetic GPT-2 style
+vocabulary, cross-checked against a from-scratch Python BPE that applies the same merges."""
+import ctypes
+
+import numpy as np
+import pytest
+
+
+def _py_bpe(word_u, ranks):
+    sym = list(word_u)
+    while len(sym) > 1:
+        best, bi = None, -1
+        for i in range(len(sym) - 1):
+            r = ranks.get(sym[i] + " " + sym[i + 1])
+            if r is not None and (best is None or r < best):
+                best, bi = r, i
+        if best is None:
+            break
+        sym[bi:bi + 2] = [sym[bi] + sym[bi + 1]]
+    return sym
+
+
+@pytest.mark.parametrize("text", ["hello world", "the rain in spain", " hello  world\n\nthe end", "café naïve 中文", "x=42; y=1234567",
+                                  "it's we'll they're", ""])
+def test_encode_decode_roundtrip_and_merges(hostcheck_lib, tiny_gguf, text):
+    from oracle import gguf_synth as S
+    toks, merges, types = S.synth_vocab(S.TINY.n_vocab)
+    ids = np.zeros(4096, np.int32)
+    n = hostcheck_lib.hc_tokenize(tiny_gguf.encode(), text.encode(), 1, 0, ids.ctypes.data_as(ctypes.c_void_p), 4096)
+    assert n >= 1 and ids[0] == S.TINY.n_vocab - 3                  # BOS
+    buf = ctypes.create_string_buffer(8192)
+    m = hostcheck_lib.hc_detokenize(tiny_gguf.encode(), ids[1:].ctypes.data_as(ctypes.c_void_p), n - 1, buf, 8192)
+    assert buf.raw[:m].decode("utf-8") == text                      # lossless
+    # every produced token is a legal BPE symbol of its word under the file's merge table
+    b2u = S.gpt2_byte_to_unicode()
+    ranks = {mg: i for i, mg in enumerate(merges)}
+    produced = [toks[i] for i in ids[1:n]]
+    assert "".join(produced) == "".join(b2u[b] for b in text.encode())
+    if text == "hello world":
+        assert produced == _py_bpe("".join(b2u[b] for b in b"hello"), ranks) + _py_bpe("".join(b2u[b] for b in b" world"), ranks)
+        assert len(produced) < len(text)                            # merges were applied
+
+
+def test_special_tokens(hostcheck_lib, tiny_gguf):
+    from oracle import gguf_synth as S
+    ids = np.zeros(64, np.int32)
+    n = hostcheck_lib.hc_tokenize(tiny_gguf.encode(), b"hi<|eot_id|>", 0, 1, ids.ctypes.data_as(ctypes.c_void_p), 64)
+    assert ids[n - 1] == S.TINY.n_vocab - 1
+    n2 = hostcheck_lib.hc_tokenize(tiny_gguf.encode(), b"hi<|eot_id|>", 0, 0, ids.ctypes.data_as(ctypes.c_void_p), 64)
+    assert n2 > n                                                    # not parsed: spelled out byte by byte
