@@ -285,7 +285,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     const unsigned bar_base = __ldcg(&st->bar_base);
     unsigned nbar = 0;
     int dslot = 0;
-    XUnit xr;
     for (int step = 0; step < mp.n_steps; ++step) {
         // ---- token embedding (CTA 0) ----------------------------------------------------------------------
         if (cta == 0) {
@@ -308,6 +307,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
             unsigned long long* tr = (mp.trace != nullptr && tid == 0) ? mp.trace + ((size_t)cta * (mp.n_phases + 1) + ph) * 4 : nullptr;
             if (tr) tr[0] = gtime();
             if (kind == PH_GEMV) {
+                XUnit xr;      // scoped to the phase: dead (no registers pinned) during attention / barriers
                 const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid, xr);
                 if (tr) tr[1] = gtime();
                 gemv_consume<ABITS, NW>(P.g, ring, smem, tid, xr, scale, cta, G);

@@ -316,8 +316,16 @@ __device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, ui
                 }
                 float a0 = 0.f, a1 = 0.f;
                 if (valid) {
-                    a0 = unit_dot_type<ABITS>(sg.type, base + (size_t)ra * sg.row_stride, K, u, xr);
-                    if (rb >= 0) a1 = unit_dot_type<ABITS>(sg.type, base + (size_t)rb * sg.row_stride, K, u, xr);
+                    const uint8_t* pa = base + (size_t)ra * sg.row_stride;
+                    const uint8_t* pb = base + (size_t)rb * sg.row_stride;
+                    if (rb >= 0 && sg.type == T_Q4_K) {
+                        unit_dot2_q4k<ABITS>(pa + (size_t)(u >> 1) * 144, pb + (size_t)(u >> 1) * 144, u & 1, xr, a0, a1);
+                    } else if (rb >= 0 && sg.type == T_Q6_K) {
+                        unit_dot2_q6k<ABITS>(pa, pb, K >> 8, u, xr, a0, a1);
+                    } else {
+                        a0 = unit_dot_type<ABITS>(sg.type, pa, K, u, xr);
+                        if (rb >= 0) a1 = unit_dot_type<ABITS>(sg.type, pb, K, u, xr);
+                    }
                 }
                 float2 sum;
                 if (rb >= 0) sum = warp_sum2(a0, a1, lane);

@@ -129,13 +129,15 @@ GL_HD float unit_dot_q4k(const uint8_t* blk, int hb, const XUnit& x) {
     const uint32_t sc4 = hb ? ((s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u)) : (s0 & 0x3F3F3F3Fu);
     const uint32_t mn4 = hb ? (((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u)) : (s1 & 0x3F3F3F3Fu);
     const U4* q = reinterpret_cast<const U4*>(blk + 16 + 64 * hb);
+    // all four 16-B chunks are requested before any arithmetic: one shared-memory latency per unit, not four
+    const U4 qall[4] = {q[0], q[1], q[2], q[3]};
     float val = 0.f;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {            // 32-byte chunk: low nibbles -> sub-block 2c, high -> 2c+1
         int ah = 0, al = 0, bh = 0, bl = 0;
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-            const U4 qq = q[2 * c + v];
+            const U4 qq = qall[2 * c + v];
             const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -174,10 +176,13 @@ GL_HD float unit_dot_q6k(const uint8_t* row, int nb, int u, const XUnit& x) {
     U4 qh[2];
     qh[0] = *reinterpret_cast<const U4*>(qhp + ((size_t)0 * nu + u) * 16);
     qh[1] = *reinterpret_cast<const U4*>(qhp + ((size_t)1 * nu + u) * 16);
+    U4 qlall[4];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) qlall[i4] = *reinterpret_cast<const U4*>(qlp + ((size_t)i4 * nu + u) * 16);
     float val = 0.f;
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
-        const U4 ql = *reinterpret_cast<const U4*>(qlp + ((size_t)i4 * nu + u) * 16);
+        const U4 ql = qlall[i4];
         const uint32_t qlw[4] = {ql.x, ql.y, ql.z, ql.w};
         const U4 qhc = qh[i4 & 1];
         const uint32_t qhw[4] = {qhc.x, qhc.y, qhc.z, qhc.w};
@@ -213,6 +218,9 @@ GL_HD float unit_dot_q80(const uint8_t* row, int cols, int u, const XUnit& x) {
     const int nu = cols / UNIT_COLS;
     const uint32_t* dp = reinterpret_cast<const uint32_t*>(row + (size_t)cols + (size_t)u * 8);
     const uint32_t dw[2] = {dp[0], dp[1]};
+    U4 qall[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qall[i] = *reinterpret_cast<const U4*>(row + ((size_t)i * nu + u) * 16);
     float val = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {            // 32-column block j of the unit
@@ -220,7 +228,7 @@ GL_HD float unit_dot_q80(const uint8_t* row, int cols, int u, const XUnit& x) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
             const int i = 2 * j + v;
-            const U4 qq = *reinterpret_cast<const U4*>(row + ((size_t)i * nu + u) * 16);
+            const U4 qq = qall[i];
             const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -232,6 +240,122 @@ GL_HD float unit_dot_q80(const uint8_t* row, int cols, int u, const XUnit& x) {
         val += dj * ((float)combine<ABITS>(ah, al) * x.sx[j]);
     }
     return val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two rows at once.  Same arithmetic as the single-row functions, but the two rows advance word by word in
+// lock-step so that every dp4a has 8-16 independent accumulators around it: the fixed-latency dependency
+// stalls ("wait") that dominated the single-row schedule (profiles/r01_run5) are filled with the other row's work.
+// ---------------------------------------------------------------------------------------------
+template <int ABITS>
+GL_HD void unit_dot2_q4k(const uint8_t* blk0, const uint8_t* blk1, int hb, const XUnit& x, float& out0, float& out1) {
+    const uint8_t* blk[2] = {blk0, blk1};
+    U4 hdr[2], qall[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        hdr[r] = *reinterpret_cast<const U4*>(blk[r]);
+        const U4* q = reinterpret_cast<const U4*>(blk[r] + 16 + 64 * hb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qall[r][i] = q[i];
+    }
+    float val[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        int ah[2] = {0, 0}, al[2] = {0, 0}, bh[2] = {0, 0}, bl[2] = {0, 0};
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const uint32_t w0[4] = {qall[0][2 * c + v].x, qall[0][2 * c + v].y, qall[0][2 * c + v].z, qall[0][2 * c + v].w};
+            const uint32_t w1[4] = {qall[1][2 * c + v].x, qall[1][2 * c + v].y, qall[1][2 * c + v].z, qall[1][2 * c + v].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xa = 8 * (2 * c) + 4 * v + k, xb = 8 * (2 * c + 1) + 4 * v + k;
+                const uint32_t lo0 = w0[k] & 0x0F0F0F0Fu, hi0 = w0[k] & 0xF0F0F0F0u;
+                const uint32_t lo1 = w1[k] & 0x0F0F0F0Fu, hi1 = w1[k] & 0xF0F0F0F0u;
+                ah[0] = dp4a_s(lo0, x.hi[xa], ah[0]);
+                ah[1] = dp4a_s(lo1, x.hi[xa], ah[1]);
+                bh[0] = dp4a_us(hi0, x.hi[xb], bh[0]);
+                bh[1] = dp4a_us(hi1, x.hi[xb], bh[1]);
+                if (ABITS == 16) {
+                    al[0] = dp4a_s(lo0, x.lo[xa], al[0]);
+                    al[1] = dp4a_s(lo1, x.lo[xa], al[1]);
+                    bl[0] = dp4a_us(hi0, x.lo[xb], bl[0]);
+                    bl[1] = dp4a_us(hi1, x.lo[xb], bl[1]);
+                }
+            }
+        }
+        const int sa = 2 * c, sb = 2 * c + 1;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t s0 = hdr[r].y, s1 = hdr[r].z, s2 = hdr[r].w;
+            const uint32_t sc4 = hb ? ((s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u)) : (s0 & 0x3F3F3F3Fu);
+            const uint32_t mn4 = hb ? (((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u)) : (s1 & 0x3F3F3F3Fu);
+            const float d = half_bits_to_float((uint16_t)(hdr[r].x & 0xFFFF));
+            const float dmin = half_bits_to_float((uint16_t)(hdr[r].x >> 16));
+            const float sca = (float)((sc4 >> (8 * sa)) & 0xFF), scb = (float)((sc4 >> (8 * sb)) & 0xFF) * 0.0625f;
+            const float mna = (float)((mn4 >> (8 * sa)) & 0xFF), mnb = (float)((mn4 >> (8 * sb)) & 0xFF);
+            val[r] += d * (sca * ((float)combine<ABITS>(ah[r], al[r]) * x.sx[sa]) + scb * ((float)combine<ABITS>(bh[r], bl[r]) * x.sx[sb]))
+                    - dmin * (mna * x.sm[sa] + mnb * x.sm[sb]);
+        }
+    }
+    out0 = val[0];
+    out1 = val[1];
+}
+
+template <int ABITS>
+GL_HD void unit_dot2_q6k(const uint8_t* row0, const uint8_t* row1, int nb, int u, const XUnit& x, float& out0, float& out1) {
+    const int nu = 2 * nb;
+    const uint8_t* row[2] = {row0, row1};
+    U4 ql[2][4], qh[2][2];
+    uint32_t scw[2][2];
+    float d[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint8_t* qlp = row[r];
+        const uint8_t* qhp = row[r] + (size_t)nb * 128;
+        const uint8_t* scp = row[r] + (size_t)nb * 192 + (size_t)u * 8;
+        d[r] = half_bits_to_float(*reinterpret_cast<const uint16_t*>(row[r] + (size_t)nb * 208 + (size_t)(u >> 1) * 2));
+        scw[r][0] = reinterpret_cast<const uint32_t*>(scp)[0];
+        scw[r][1] = reinterpret_cast<const uint32_t*>(scp)[1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ql[r][i] = *reinterpret_cast<const U4*>(qlp + ((size_t)i * nu + u) * 16);
+        qh[r][0] = *reinterpret_cast<const U4*>(qhp + ((size_t)0 * nu + u) * 16);
+        qh[r][1] = *reinterpret_cast<const U4*>(qhp + ((size_t)1 * nu + u) * 16);
+    }
+    float val[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+        const int t = i4 >> 1;
+        int ah[2] = {0, 0}, al[2] = {0, 0}, bh[2] = {0, 0}, bl[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xa = 4 * i4 + k, xb = 16 + 4 * i4 + k;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t qlw = k == 0 ? ql[r][i4].x : k == 1 ? ql[r][i4].y : k == 2 ? ql[r][i4].z : ql[r][i4].w;
+                const U4& qq = qh[r][i4 & 1];
+                const uint32_t qhw = k == 0 ? qq.x : k == 1 ? qq.y : k == 2 ? qq.z : qq.w;
+                const uint32_t a4 = (qlw & 0x0F0F0F0Fu) | (((qhw >> (2 * t)) & 0x03030303u) << 4);
+                const uint32_t b4 = ((qlw >> 4) & 0x0F0F0F0Fu) | (((qhw >> (4 + 2 * t)) & 0x03030303u) << 4);
+                ah[r] = dp4a_s(a4, x.hi[xa], ah[r]);
+                bh[r] = dp4a_s(b4, x.hi[xb], bh[r]);
+                if (ABITS == 16) {
+                    al[r] = dp4a_s(a4, x.lo[xa], al[r]);
+                    bl[r] = dp4a_s(b4, x.lo[xb], bl[r]);
+                }
+            }
+        }
+        const int ga = i4, gb = 4 + i4;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float sca = (float)(int8_t)(scw[r][ga >> 2] >> (8 * (ga & 3)));
+            const float scb = (float)(int8_t)(scw[r][gb >> 2] >> (8 * (gb & 3)));
+            const int ia = combine<ABITS>(ah[r], al[r]) - 32 * x.s16[ga];
+            const int ib = combine<ABITS>(bh[r], bl[r]) - 32 * x.s16[gb];
+            val[r] += sca * ((float)ia * x.sx[ga >> 1]) + scb * ((float)ib * x.sx[gb >> 1]);
+        }
+    }
+    out0 = d[0] * val[0];
+    out1 = d[1] * val[1];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -30,6 +30,30 @@ static void build_xunits(const float* x, int cols, std::vector<XUnit>& xs) {
     }
 }
 
+// rows taken two at a time through the lock-step functions the GPU consumer uses for row pairs
+template <int AB>
+static int run_pairs(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
+    std::vector<XUnit> xs;
+    build_xunits<AB>(x, cols, xs);
+    int nu = cols / UNIT_COLS;
+    size_t rb = row_bytes(type, cols), rs = align16(rb);
+    std::vector<uint8_t> buf(2 * rs + 16);
+    uint8_t* r0 = buf.data() + ((16 - ((uintptr_t)buf.data() & 15)) & 15);
+    uint8_t* r1 = r0 + rs;
+    for (int i = 0; i + 1 < rows; i += 2) {
+        float acc0 = 0.f, acc1 = 0.f;
+        if (type == T_Q4_K) {
+            memcpy(r0, w + (size_t)i * rb, rb); memcpy(r1, w + (size_t)(i + 1) * rb, rb);
+            for (int u = 0; u < nu; ++u) { float a, b; unit_dot2_q4k<AB>(r0 + (size_t)(u >> 1) * 144, r1 + (size_t)(u >> 1) * 144, u & 1, xs[u], a, b); acc0 += a; acc1 += b; }
+        } else if (type == T_Q6_K) {
+            repack_row_q6k(w + (size_t)i * rb, r0, cols / 256); repack_row_q6k(w + (size_t)(i + 1) * rb, r1, cols / 256);
+            for (int u = 0; u < nu; ++u) { float a, b; unit_dot2_q6k<AB>(r0, r1, cols / 256, u, xs[u], a, b); acc0 += a; acc1 += b; }
+        } else return -1;
+        y[i] = acc0; y[i + 1] = acc1;
+    }
+    return 0;
+}
+
 template <int AB>
 static int run(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
     std::vector<XUnit> xs;
@@ -54,6 +78,11 @@ static int run(int type, const uint8_t* w, int rows, int cols, const float* x, f
         y[i] = acc;
     }
     return 0;
+}
+
+extern "C" int hc_gemv_pairs(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
+    if (cols % 256 || (rows & 1)) return -2;
+    return abits == 16 ? run_pairs<16>(type, w, rows, cols, x, y) : run_pairs<8>(type, w, rows, cols, x, y);
 }
 
 extern "C" int hc_gemv(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {

@@ -46,3 +46,20 @@ def test_edge_activations(hostcheck_lib):
         ref = O.gemv(wd, x, "i16")
         assert np.isfinite(y).all()
         assert np.allclose(y, ref, rtol=1e-5, atol=1e-30 + 1e-6 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("tname", ["Q4_K", "Q6_K"])
+def test_paired_row_functions_equal_single_row(hostcheck_lib, tname):
+    """unit_dot2_* (two rows in lock-step, what the GPU consumer runs for row pairs) == unit_dot_* bit for bit"""
+    from oracle import gguf_synth as S
+    t = {"Q4_K": S.Q4_K, "Q6_K": S.Q6_K}[tname]
+    rng = np.random.Generator(np.random.PCG64(31))
+    for cols in (256, 4096, 14336):
+        blocks = S.random_blocks(rng, t, 10, cols)
+        x = rng.standard_normal(cols).astype(np.float32)
+        for ab in (16, 8):
+            y1 = _run(hostcheck_lib, t, blocks, 10, cols, x, ab)
+            y2 = np.zeros(10, np.float32)
+            rc = hostcheck_lib.hc_gemv_pairs(t, blocks.ctypes.data_as(ctypes.c_void_p), 10, cols, x.ctypes.data_as(ctypes.c_void_p),
+                                             y2.ctypes.data_as(ctypes.c_void_p), ab)
+            assert rc == 0 and np.array_equal(y1, y2)
