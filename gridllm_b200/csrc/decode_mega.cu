@@ -107,18 +107,98 @@ __device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int typ
 }
 
 // ---- split-KV paged attention for one (kv head, split) item; K/V rows read straight from HBM/L2 ----------
-// One warp per query head of the GQA group; a lane owns DPL dims.  K and V of a 16-token page are requested
-// together (32 independent loads per lane in flight) before any arithmetic.
+// One warp per query head of the GQA group; a lane owns DPL dims.
+// The phase is a chain of dependent L2 round trips, so it is cut in two around the grid barrier that follows the
+// QKV phase: K/V rows of OLD positions are final before that barrier, and attn_prefetch() requests up to two
+// 16-token pages of them (64 independent 8-B loads per lane) before the CTA waits; after the barrier only q and
+// the single row of the newest position remain to be fetched.
+constexpr int ATTN_PRE_PAGES = 2;
+struct AttnPre {      // K rows only: V is requested after the barrier together with q (same round trip)
+    uint2 kk[ATTN_PRE_PAGES][KV_PAGE_TOKENS];
+};
+
+// 16 rows of one page of K (or V) for this lane's dims
+template <int DPL>
+__device__ __forceinline__ void attn_load_rows(const MegaParams& mp, const __half* cache, int kvh, int pg, int L, int lane, uint2* rows) {
+    constexpr int HD = DPL * 32;
+    const int page = __ldcg(mp.page_table + pg);
+    const size_t base = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD + lane * DPL;
+    const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
+#pragma unroll
+    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+        rows[j] = make_uint2(0u, 0u);
+        if (j < npos) {
+            if (DPL == 4) rows[j] = __ldcg(reinterpret_cast<const uint2*>(cache + base + (size_t)j * HD));
+            else rows[j].x = __ldcg(reinterpret_cast<const unsigned*>(cache + base + (size_t)j * HD));
+        }
+    }
+}
+
+template <int DPL>
+__device__ __forceinline__ void attn_prefetch(AttnPre& ap, const MegaParams& mp, const __half* kc, const __half* vc, int item, int warp,
+                                              int lane, int pos) {
+    const int n_splits = mp.attn_splits;
+    const int kvh = item / n_splits, split = item % n_splits;
+    if (warp >= mp.n_head / mp.n_kv) return;
+    const int L = pos + 1;
+    const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+    const int pps = (n_pages + n_splits - 1) / n_splits;
+    const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
+#pragma unroll
+    for (int i = 0; i < ATTN_PRE_PAGES; ++i)
+        if (pg0 + i < pg1) attn_load_rows<DPL>(mp, kc, kvh, pg0 + i, L, lane, ap.kk[i]);
+}
+
+template <int DPL>
+__device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv, int npos, const float* q, float* o, float& m_run, float& l_run) {
+    float sc[KV_PAGE_TOKENS];
+#pragma unroll
+    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].x));
+        float a = q[0] * k0.x + q[1] * k0.y;
+        if (DPL == 4) {
+            const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].y));
+            a += q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
+        }
+        sc[j] = a;
+    }
+    float m_t = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+        sc[j] = warp_sum(sc[j]);
+        if (j < npos) m_t = fmaxf(m_t, sc[j]);
+    }
+    const float m_new = fmaxf(m_run, m_t);
+    const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+    l_run *= corr;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) o[d] *= corr;
+#pragma unroll
+    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+        if (j < npos) {
+            const float w = expf(sc[j] - m_new);
+            l_run += w;
+            const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
+            o[0] += w * v0.x; o[1] += w * v0.y;
+            if (DPL == 4) {
+                const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
+                o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
+            }
+        }
+    }
+    m_run = m_new;
+}
+
 template <int DPL, int NT>
-__device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc, const __half* vc, int item, int warp, int lane,
-                                          int tid, int* smem_flag) {
+__device__ __forceinline__ void attn_item(AttnPre& ap, bool prefetched, const MegaParams& mp, const __half* kc, const __half* vc, int item,
+                                          int warp, int lane, int tid, int pos, int* smem_flag) {
     constexpr int HD = DPL * 32;
     const int n_splits = mp.attn_splits;
     const int kvh = item / n_splits, split = item % n_splits;
     const int grp = mp.n_head / mp.n_kv;
     const int head = kvh * grp + warp;
     const bool active = warp < grp;
-    const int L = __ldcg(&mp.st->pos) + 1;
+    const int L = pos + 1;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
     const int pps = (n_pages + n_splits - 1) / n_splits;
     const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
@@ -127,62 +207,39 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
         const float* qp = mp.q + (size_t)head * HD + lane * DPL;
 #pragma unroll
         for (int d = 0; d < DPL; ++d) { q[d] = __ldcg(qp + d) * mp.attn_scale; o[d] = 0.f; }
+        // V of the prefetched pages (and K when nothing was prefetched) travels with q: same round trip
+        uint2 vv[ATTN_PRE_PAGES][KV_PAGE_TOKENS];
+#pragma unroll
+        for (int i = 0; i < ATTN_PRE_PAGES; ++i) {
+            if (pg0 + i < pg1) {
+                attn_load_rows<DPL>(mp, vc, kvh, pg0 + i, L, lane, vv[i]);
+                if (!prefetched) attn_load_rows<DPL>(mp, kc, kvh, pg0 + i, L, lane, ap.kk[i]);
+            }
+        }
+        // the newest position's K row was written by the QKV phase that just ended: patch it in if it is ours
+        const int pg_new = pos / KV_PAGE_TOKENS, j_new = pos % KV_PAGE_TOKENS;
+        if (prefetched && pg_new >= pg0 && pg_new < pg1 && pg_new - pg0 < ATTN_PRE_PAGES) {
+            const int page = __ldcg(mp.page_table + pg_new);
+            const size_t off = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD + (size_t)j_new * HD + lane * DPL;
+            uint2 kn = make_uint2(0u, 0u);
+            if (DPL == 4) kn = __ldcg(reinterpret_cast<const uint2*>(kc + off));
+            else kn.x = __ldcg(reinterpret_cast<const unsigned*>(kc + off));
+#pragma unroll
+            for (int i = 0; i < ATTN_PRE_PAGES; ++i)
+#pragma unroll
+                for (int j = 0; j < KV_PAGE_TOKENS; ++j)
+                    if (i == pg_new - pg0 && j == j_new) ap.kk[i][j] = kn;
+        }
         float m_run = -INFINITY, l_run = 0.f;
-        for (int pg = pg0; pg < pg1; ++pg) {
-            const int page = __ldcg(mp.page_table + pg);
-            const size_t base = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD + lane * DPL;
-            const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
-            uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
 #pragma unroll
-            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-                kk[j] = make_uint2(0u, 0u);
-                vv[j] = make_uint2(0u, 0u);
-                if (j < npos) {
-                    if (DPL == 4) {
-                        kk[j] = __ldcg(reinterpret_cast<const uint2*>(kc + base + (size_t)j * HD));
-                        vv[j] = __ldcg(reinterpret_cast<const uint2*>(vc + base + (size_t)j * HD));
-                    } else {
-                        kk[j].x = __ldcg(reinterpret_cast<const unsigned*>(kc + base + (size_t)j * HD));
-                        vv[j].x = __ldcg(reinterpret_cast<const unsigned*>(vc + base + (size_t)j * HD));
-                    }
-                }
-            }
-            float sc[KV_PAGE_TOKENS];
-#pragma unroll
-            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-                const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].x));
-                float a = q[0] * k0.x + q[1] * k0.y;
-                if (DPL == 4) {
-                    const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].y));
-                    a += q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
-                }
-                sc[j] = a;
-            }
-            float m_t = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-                sc[j] = warp_sum(sc[j]);
-                if (j < npos) m_t = fmaxf(m_t, sc[j]);
-            }
-            const float m_new = fmaxf(m_run, m_t);
-            const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-            l_run *= corr;
-#pragma unroll
-            for (int d = 0; d < DPL; ++d) o[d] *= corr;
-#pragma unroll
-            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-                if (j < npos) {
-                    const float w = expf(sc[j] - m_new);
-                    l_run += w;
-                    const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
-                    o[0] += w * v0.x; o[1] += w * v0.y;
-                    if (DPL == 4) {
-                        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
-                        o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
-                    }
-                }
-            }
-            m_run = m_new;
+        for (int i = 0; i < ATTN_PRE_PAGES; ++i) {
+            const int pg = pg0 + i;
+            if (pg < pg1) attn_page_math<DPL>(ap.kk[i], vv[i], min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
+        }
+        for (int pg = pg0 + ATTN_PRE_PAGES; pg < pg1; ++pg) {       // long contexts: remaining pages one at a time
+            attn_load_rows<DPL>(mp, kc, kvh, pg, L, lane, ap.kk[0]);
+            attn_load_rows<DPL>(mp, vc, kvh, pg, L, lane, vv[0]);
+            attn_page_math<DPL>(ap.kk[0], vv[0], min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
         }
         float* po = mp.part_o + ((size_t)head * n_splits + split) * HD + lane * DPL;
 #pragma unroll
@@ -202,25 +259,28 @@ __device__ __forceinline__ void attn_item(const MegaParams& mp, const __half* kc
     }
     named_bar_sync(1, NT);
     if (*smem_flag && active) {
-        // lane s holds (m, l) of split s; n_splits <= 32
+        // one round trip: (m, l) of split `lane` and the partial outputs of the first 8 splits travel together
         float ms = -INFINITY, ls = 0.f;
         if (lane < n_splits) {
             ms = __ldcg(mp.part_ml + ((size_t)head * n_splits + lane) * 2);
             ls = __ldcg(mp.part_ml + ((size_t)head * n_splits + lane) * 2 + 1);
         }
-        const float M = warp_max(ms);
-        const float wl = (ms == -INFINITY) ? 0.f : expf(ms - M);
-        const float den = warp_sum(wl * ls);
+        const float* pbase = mp.part_o + (size_t)head * n_splits * HD + lane * DPL;
         float acc[DPL];
 #pragma unroll
         for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
-        const float* pbase = mp.part_o + (size_t)head * n_splits * HD + lane * DPL;
-        for (int s0 = 0; s0 < n_splits; s0 += 8) {          // 8 splits' partial outputs in flight at a time
+        float M = 0.f, wl = 0.f, den = 0.f;
+        for (int s0 = 0; s0 < n_splits; s0 += 8) {
             float po[8][DPL];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
 #pragma unroll
                 for (int d = 0; d < DPL; ++d) po[i][d] = (s0 + i < n_splits) ? __ldcg(pbase + (size_t)(s0 + i) * HD + d) : 0.f;
+            }
+            if (s0 == 0) {
+                M = warp_max(ms);
+                wl = (ms == -INFINITY) ? 0.f : expf(ms - M);
+                den = warp_sum(wl * ls);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -300,6 +360,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
         prefetch_desc(0, dslot);
         ++nbar;
         grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
+        const int step_pos = __ldcg(&st->pos);        // fixed for the whole step
 
         for (int ph = 0; ph < mp.n_phases; ++ph) {
             const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<const uint8_t*>(sdesc) + dslot * 256);
@@ -356,11 +417,41 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
                     }
                 }
             } else if (kind == PH_ATTN) {
+                // only reached when the attention phase does not directly follow a QKV phase (never in the current tables)
                 const int n_items = mp.n_kv * mp.attn_splits;
                 if (cta < n_items) {
-                    if (mp.head_dim == 128) attn_item<4, NT>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
-                    else attn_item<2, NT>(mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, sflag);
+                    AttnPre ap;
+                    if (mp.head_dim == 128) attn_item<4, NT>(ap, false, mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, step_pos, sflag);
+                    else attn_item<2, NT>(ap, false, mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, step_pos, sflag);
                 }
+            }
+            if (kind == PH_GEMV && P.g.epi == EPI_QKV && ph + 2 < mp.n_phases) {
+                // QKV -> [barrier] -> attention, fused: request this CTA's K/V pages of the old positions before the
+                // barrier, run the attention item right after it, then skip the table's ATTN entry.
+                const int n_items = mp.n_kv * mp.attn_splits;
+                const __half* kc = P.g.k_cache;
+                const __half* vc = P.g.v_cache;
+                AttnPre ap;
+                if (cta < n_items) {
+                    if (mp.head_dim == 128) attn_prefetch<4>(ap, mp, kc, vc, cta, warp, lane, step_pos);
+                    else attn_prefetch<2>(ap, mp, kc, vc, cta, warp, lane, step_pos);
+                }
+                if (tr) tr[2] = gtime();
+                prefetch_desc(ph + 2, dslot ^ 1);            // descriptor of the phase after attention (attn_output)
+                ++nbar;
+                grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
+                if (tr) { tr[3] = gtime(); tr += 4; tr[0] = tr[1] = gtime(); }
+                if (cta < n_items) {
+                    if (mp.head_dim == 128) attn_item<4, NT>(ap, true, mp, kc, vc, cta, warp, lane, tid, step_pos, sflag);
+                    else attn_item<2, NT>(ap, true, mp, kc, vc, cta, warp, lane, tid, step_pos, sflag);
+                }
+                if (tr) tr[2] = gtime();
+                dslot ^= 1;
+                ++ph;                                         // the ATTN entry is done
+                ++nbar;
+                grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
+                if (tr) tr[3] = gtime();
+                continue;
             }
             if (tr) tr[2] = gtime();
             // the next phase's descriptor travels while this CTA waits at the barrier
