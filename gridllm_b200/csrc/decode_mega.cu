@@ -113,11 +113,9 @@ __device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int typ
 // 16-token pages of them (64 independent 8-B loads per lane) before the CTA waits; after the barrier only q and
 // the single row of the newest position remain to be fetched.
 constexpr int ATTN_PRE_PAGES = 2;
-struct AttnPre {      // K rows only: V is requested after the barrier together with q (same round trip)
-    uint2 kk[ATTN_PRE_PAGES][KV_PAGE_TOKENS];
-};
+constexpr int ATTN_SMEM_BYTES = 2 * ATTN_PRE_PAGES * KV_PAGE_TOKENS * 128 * 2 + 64;   // K + V tiles (head_dim <= 128) + mbarrier
 
-// 16 rows of one page of K (or V) for this lane's dims
+// 16 rows of one page of K (or V) for this lane's dims, straight from global memory
 template <int DPL>
 __device__ __forceinline__ void attn_load_rows(const MegaParams& mp, const __half* cache, int kvh, int pg, int L, int lane, uint2* rows) {
     constexpr int HD = DPL * 32;
@@ -134,19 +132,26 @@ __device__ __forceinline__ void attn_load_rows(const MegaParams& mp, const __hal
     }
 }
 
-template <int DPL>
-__device__ __forceinline__ void attn_prefetch(AttnPre& ap, const MegaParams& mp, const __half* kc, const __half* vc, int item, int warp,
-                                              int lane, int pos) {
+// one thread: TMA-stage up to two KV pages of this CTA's attention item into shared memory (old positions are final)
+__device__ __forceinline__ void attn_prefetch(uint8_t* abuf, const MegaParams& mp, const __half* kc, const __half* vc, int item, int pos) {
+    const int HD = mp.head_dim;
     const int n_splits = mp.attn_splits;
     const int kvh = item / n_splits, split = item % n_splits;
-    if (warp >= mp.n_head / mp.n_kv) return;
     const int L = pos + 1;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
     const int pps = (n_pages + n_splits - 1) / n_splits;
     const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
-#pragma unroll
-    for (int i = 0; i < ATTN_PRE_PAGES; ++i)
-        if (pg0 + i < pg1) attn_load_rows<DPL>(mp, kc, kvh, pg0 + i, L, lane, ap.kk[i]);
+    const int np = min(ATTN_PRE_PAGES, pg1 - pg0);
+    if (np <= 0) return;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(abuf + ATTN_SMEM_BYTES - 64);
+    const uint32_t page_bytes = (uint32_t)(KV_PAGE_TOKENS * HD * sizeof(__half));
+    mbar_expect_tx(bar, 2u * np * page_bytes);
+    for (int i = 0; i < np; ++i) {
+        const int page = __ldcg(mp.page_table + pg0 + i);
+        const size_t off = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD;
+        tma_load_1d(abuf + (size_t)i * page_bytes, kc + off, page_bytes, bar);
+        tma_load_1d(abuf + (size_t)(ATTN_PRE_PAGES + i) * page_bytes, vc + off, page_bytes, bar);
+    }
 }
 
 template <int DPL>
@@ -190,8 +195,8 @@ __device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv,
 }
 
 template <int DPL, int NT>
-__device__ __forceinline__ void attn_item(AttnPre& ap, bool prefetched, const MegaParams& mp, const __half* kc, const __half* vc, int item,
-                                          int warp, int lane, int tid, int pos, int* smem_flag) {
+__device__ __forceinline__ void attn_item(uint8_t* abuf, bool prefetched, uint32_t aparity, const MegaParams& mp, const __half* kc,
+                                          const __half* vc, int item, int warp, int lane, int tid, int pos, int* smem_flag) {
     constexpr int HD = DPL * 32;
     const int n_splits = mp.attn_splits;
     const int kvh = item / n_splits, split = item % n_splits;
@@ -202,44 +207,49 @@ __device__ __forceinline__ void attn_item(AttnPre& ap, bool prefetched, const Me
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
     const int pps = (n_pages + n_splits - 1) / n_splits;
     const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
+    const int npre = prefetched ? max(0, min(ATTN_PRE_PAGES, pg1 - pg0)) : 0;
     if (active) {
         float q[DPL], o[DPL];
         const float* qp = mp.q + (size_t)head * HD + lane * DPL;
 #pragma unroll
         for (int d = 0; d < DPL; ++d) { q[d] = __ldcg(qp + d) * mp.attn_scale; o[d] = 0.f; }
-        // V of the prefetched pages (and K when nothing was prefetched) travels with q: same round trip
-        uint2 vv[ATTN_PRE_PAGES][KV_PAGE_TOKENS];
-#pragma unroll
-        for (int i = 0; i < ATTN_PRE_PAGES; ++i) {
-            if (pg0 + i < pg1) {
-                attn_load_rows<DPL>(mp, vc, kvh, pg0 + i, L, lane, vv[i]);
-                if (!prefetched) attn_load_rows<DPL>(mp, kc, kvh, pg0 + i, L, lane, ap.kk[i]);
-            }
-        }
-        // the newest position's K row was written by the QKV phase that just ended: patch it in if it is ours
+        // the newest position's K/V row was written by the QKV phase that just ended (the staged copy may predate it):
+        // fetch it in the same round trip as q
         const int pg_new = pos / KV_PAGE_TOKENS, j_new = pos % KV_PAGE_TOKENS;
-        if (prefetched && pg_new >= pg0 && pg_new < pg1 && pg_new - pg0 < ATTN_PRE_PAGES) {
+        uint2 kn = make_uint2(0u, 0u), vn = make_uint2(0u, 0u);
+        const bool mine_new = pg_new >= pg0 && pg_new < pg0 + npre;
+        if (mine_new) {
             const int page = __ldcg(mp.page_table + pg_new);
             const size_t off = ((size_t)page * mp.n_kv + kvh) * KV_PAGE_TOKENS * HD + (size_t)j_new * HD + lane * DPL;
-            uint2 kn = make_uint2(0u, 0u);
-            if (DPL == 4) kn = __ldcg(reinterpret_cast<const uint2*>(kc + off));
-            else kn.x = __ldcg(reinterpret_cast<const unsigned*>(kc + off));
-#pragma unroll
-            for (int i = 0; i < ATTN_PRE_PAGES; ++i)
-#pragma unroll
-                for (int j = 0; j < KV_PAGE_TOKENS; ++j)
-                    if (i == pg_new - pg0 && j == j_new) ap.kk[i][j] = kn;
+            if (DPL == 4) { kn = __ldcg(reinterpret_cast<const uint2*>(kc + off)); vn = __ldcg(reinterpret_cast<const uint2*>(vc + off)); }
+            else { kn.x = __ldcg(reinterpret_cast<const unsigned*>(kc + off)); vn.x = __ldcg(reinterpret_cast<const unsigned*>(vc + off)); }
         }
         float m_run = -INFINITY, l_run = 0.f;
-#pragma unroll
-        for (int i = 0; i < ATTN_PRE_PAGES; ++i) {
+        if (npre > 0) mbar_wait(reinterpret_cast<uint64_t*>(abuf + ATTN_SMEM_BYTES - 64), aparity);
+        const uint32_t page_bytes = (uint32_t)(KV_PAGE_TOKENS * HD * sizeof(__half));
+        for (int i = 0; i < npre; ++i) {
             const int pg = pg0 + i;
-            if (pg < pg1) attn_page_math<DPL>(ap.kk[i], vv[i], min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
+            uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
+            const uint8_t* kb = abuf + (size_t)i * page_bytes + lane * DPL * 2;
+            const uint8_t* vb = abuf + (size_t)(ATTN_PRE_PAGES + i) * page_bytes + lane * DPL * 2;
+#pragma unroll
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+                if (DPL == 4) {
+                    kk[j] = *reinterpret_cast<const uint2*>(kb + (size_t)j * HD * 2);
+                    vv[j] = *reinterpret_cast<const uint2*>(vb + (size_t)j * HD * 2);
+                } else {
+                    kk[j] = make_uint2(*reinterpret_cast<const unsigned*>(kb + (size_t)j * HD * 2), 0u);
+                    vv[j] = make_uint2(*reinterpret_cast<const unsigned*>(vb + (size_t)j * HD * 2), 0u);
+                }
+                if (mine_new && pg == pg_new && j == j_new) { kk[j] = kn; vv[j] = vn; }
+            }
+            attn_page_math<DPL>(kk, vv, min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
         }
-        for (int pg = pg0 + ATTN_PRE_PAGES; pg < pg1; ++pg) {       // long contexts: remaining pages one at a time
-            attn_load_rows<DPL>(mp, kc, kvh, pg, L, lane, ap.kk[0]);
-            attn_load_rows<DPL>(mp, vc, kvh, pg, L, lane, vv[0]);
-            attn_page_math<DPL>(ap.kk[0], vv[0], min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
+        for (int pg = pg0 + npre; pg < pg1; ++pg) {       // not staged (long contexts / no prefetch): straight from global memory
+            uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
+            attn_load_rows<DPL>(mp, kc, kvh, pg, L, lane, kk);
+            attn_load_rows<DPL>(mp, vc, kvh, pg, L, lane, vv);
+            attn_page_math<DPL>(kk, vv, min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
         }
         float* po = mp.part_o + ((size_t)head * n_splits + split) * HD + lane * DPL;
 #pragma unroll
@@ -308,10 +318,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     MegaPhase* sdesc = reinterpret_cast<MegaPhase*>(smem + fixed);              // 2 x 256 B: phase descriptors, double-buffered
     int* sflag = reinterpret_cast<int*>(smem + fixed + 512);
     float* sstat = reinterpret_cast<float*>(smem + fixed + 512 + 16);            // 3 x NW floats
+    uint8_t* abuf = smem + fixed + 1024;                                          // attention staging: K/V tiles + mbarrier
+    uint64_t* abar = reinterpret_cast<uint64_t*>(abuf + ATTN_SMEM_BYTES - 64);
+    uint32_t aparity = 0;
     Ring ring;
     ring.full = reinterpret_cast<uint64_t*>(smem + SM_BARS);
     ring.empty = ring.full + GEMV_MAX_STAGES;
-    ring.slots = smem + fixed + 1024;
+    ring.slots = smem + fixed + 1024 + ATTN_SMEM_BYTES;
     ring.n_slots = mp.n_slots;
     ring.slot_bytes = mp.slot_bytes;
     ring.st = 0;
@@ -321,6 +334,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
             mbar_init(&ring.full[i], 1);
             mbar_init(&ring.empty[i], NW);
         }
+        mbar_init(abar, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -420,9 +434,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
                 // only reached when the attention phase does not directly follow a QKV phase (never in the current tables)
                 const int n_items = mp.n_kv * mp.attn_splits;
                 if (cta < n_items) {
-                    AttnPre ap;
-                    if (mp.head_dim == 128) attn_item<4, NT>(ap, false, mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, step_pos, sflag);
-                    else attn_item<2, NT>(ap, false, mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, step_pos, sflag);
+                    if (mp.head_dim == 128) attn_item<4, NT>(abuf, false, 0u, mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, step_pos, sflag);
+                    else attn_item<2, NT>(abuf, false, 0u, mp, P.g.k_cache, P.g.v_cache, cta, warp, lane, tid, step_pos, sflag);
                 }
             }
             if (kind == PH_GEMV && P.g.epi == EPI_QKV && ph + 2 < mp.n_phases) {
@@ -431,19 +444,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
                 const int n_items = mp.n_kv * mp.attn_splits;
                 const __half* kc = P.g.k_cache;
                 const __half* vc = P.g.v_cache;
-                AttnPre ap;
-                if (cta < n_items) {
-                    if (mp.head_dim == 128) attn_prefetch<4>(ap, mp, kc, vc, cta, warp, lane, step_pos);
-                    else attn_prefetch<2>(ap, mp, kc, vc, cta, warp, lane, step_pos);
-                }
+                // (the staging buffer was last read two barriers ago; tid 0's own reads are ordered before these async writes)
+                if (cta < n_items && tid == 0) attn_prefetch(abuf, mp, kc, vc, cta, step_pos);
                 if (tr) tr[2] = gtime();
                 prefetch_desc(ph + 2, dslot ^ 1);            // descriptor of the phase after attention (attn_output)
                 ++nbar;
                 grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
                 if (tr) { tr[3] = gtime(); tr += 4; tr[0] = tr[1] = gtime(); }
                 if (cta < n_items) {
-                    if (mp.head_dim == 128) attn_item<4, NT>(ap, true, mp, kc, vc, cta, warp, lane, tid, step_pos, sflag);
-                    else attn_item<2, NT>(ap, true, mp, kc, vc, cta, warp, lane, tid, step_pos, sflag);
+                    if (mp.head_dim == 128) attn_item<4, NT>(abuf, true, aparity, mp, kc, vc, cta, warp, lane, tid, step_pos, sflag);
+                    else attn_item<2, NT>(abuf, true, aparity, mp, kc, vc, cta, warp, lane, tid, step_pos, sflag);
+                    // the barrier flipped phase only if something was staged for this item
+                    {
+                        const int L = step_pos + 1, npg = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+                        const int pps = (npg + mp.attn_splits - 1) / mp.attn_splits;
+                        const int pg0 = (cta % mp.attn_splits) * pps;
+                        if (min(npg, pg0 + pps) - pg0 > 0) aparity ^= 1;
+                    }
                 }
                 if (tr) tr[2] = gtime();
                 dslot ^= 1;
@@ -510,7 +527,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
 }  // namespace
 
 size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes) {
-    return (size_t)gemv_fixed_smem(max_cols) + 1024 + (size_t)n_slots * slot_bytes;
+    return (size_t)gemv_fixed_smem(max_cols) + 1024 + ATTN_SMEM_BYTES + (size_t)n_slots * slot_bytes;
 }
 
 cudaError_t mega_configure() {

@@ -15,5 +15,5 @@ for cfg in "GL_WARPS=8" "GL_WARPS=8 GL_ACT_BITS=8"; do
 done
 tail -4 gpurun_out/pytest_gpu.log
 cat gpurun_out/mega_trace.log
-timeout 600 python tools/microbench.py > gpurun_out/microbench.log 2>&1
+
 grep -E '"GL_WARPS": "8"|ACT_BITS' gpurun_out/microbench.log | head -12
