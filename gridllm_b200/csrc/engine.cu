@@ -152,8 +152,9 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     abits_ = env_int("GL_ACT_BITS", abits_) == 8 ? 8 : 16;
     nw_ = env_int("GL_WARPS", 8);          // measured: 8 consumer warps beat 12 / 16 (per-stage costs per warp dominate)
     if (!gemv_variant_ok(abits_, nw_)) nw_ = 8;
-    stage_kb_ = env_int("GL_STAGE_KB", 24);
-    smem_kb_ = env_int("GL_SMEM_KB", 110);
+    // measured (profiles/r01_run11): 72 KB stages / 224 KB of shared memory: a CTA's whole slice of a small matrix lands as one bulk copy
+    stage_kb_ = env_int("GL_STAGE_KB", 72);
+    smem_kb_ = env_int("GL_SMEM_KB", 224);
     attn_splits_ = std::max(1, std::min(64, env_int("GL_ATTN_SPLITS", 16)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -294,7 +295,9 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
 
     ST(kv_reset());
     if (prefill_mode_ != 1) ST(build_prefill_weights());
-    if (fused_ && all_quant_ && env_int("GL_MEGA", 1) != 0) ST(build_mega());
+    // the persistent single-launch decode kernel is opt-in: it is correct (same tests) but, as of round 1, slower than
+    // the per-op graph path (3.2 vs 2.3 ms/token; profiles/README.md)
+    if (fused_ && all_quant_ && env_int("GL_MEGA", 0) != 0) ST(build_mega());
     if (use_graph_ && !use_mega_) ST(build_graphs());
     CU(cudaStreamSynchronize(stream_));
     load_ns_ = now_ns() - t0;

@@ -18,21 +18,29 @@ def main():
     t0 = time.time()
     info = S.build_model(path, S.LLAMA3_8B, "q4_k_m", seed=1234, mode="random", with_vocab=False)
     print("build_s", round(time.time() - t0, 1), info, flush=True)
-    cfgs = ({}, {"GL_WARPS": "8"}, {"GL_ACT_BITS": "8"}, {"GL_ACT_BITS": "8", "GL_WARPS": "8"}, {"GL_MEGA": "0"},
-            {"GL_MEGA_SLOT_KB": "54"}, {"GL_MEGA_SLOT_KB": "27"})
+    M = {"GL_MEGA": "0"}
+    cfgs = (dict(M, GL_STAGE_KB="36", GL_SMEM_KB="112"), dict(M, GL_STAGE_KB="36", GL_SMEM_KB="150"), dict(M, GL_STAGE_KB="36", GL_SMEM_KB="224"),
+            dict(M, GL_STAGE_KB="54", GL_SMEM_KB="224"), dict(M, GL_STAGE_KB="72", GL_SMEM_KB="224"),
+            dict(M, GL_STAGE_KB="36", GL_SMEM_KB="224", GL_ATTN_SPLITS="8"), dict(M, GL_STAGE_KB="36", GL_SMEM_KB="224", GL_ATTN_SPLITS="32"),
+            dict(M, GL_STAGE_KB="36", GL_SMEM_KB="224", GL_ACT_BITS="8"), dict(M, GL_STAGE_KB="36", GL_SMEM_KB="224", GL_GRAPH="0"),
+            {"GL_MEGA_SLOT_KB": "36", "GL_MEGA_SLOTS": "4"})
     for cfg in cfgs:
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_KB", "GL_MEGA_SLOTS", "GL_ATTN_SPLITS", "GL_WARPS"):
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_KB", "GL_MEGA_SLOTS", "GL_ATTN_SPLITS", "GL_WARPS", "GL_STAGE_KB", "GL_SMEM_KB"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         t0 = time.time()
-        os.environ["GL_PREFILL"] = "1" if cfg else "0"      # only the default config pays for the fp16 prefill copy
+        os.environ["GL_PREFILL"] = "1"
+        gen = False
         e = N.Engine(path, max_ctx=2048)
         load_s = time.time() - t0
         bpt = e.info.decode_bytes_per_token
-        for ctx in (1, 576, 1024):
+        for ctx in (1, 576):
             ms, nl = e.time_decode(ctx, 32)
             print(json.dumps({"cfg": cfg, "ctx": ctx, "ms_per_token": round(ms, 4), "tok_s": round(1000 / ms, 1), "launches": nl,
                               "weights_GBps": round(bpt / ms / 1e6, 1), "load_s": round(load_s, 1)}), flush=True)
+        if not gen:
+            e.close()
+            continue
         prompt = np.random.Generator(np.random.PCG64(1000)).integers(0, 128000, size=512)
         g = e.generate(prompt, num_predict=128, ignore_eos=True)
         st = g.stats
