@@ -382,10 +382,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
             unsigned long long* tr = (mp.trace != nullptr && tid == 0) ? mp.trace + ((size_t)cta * (mp.n_phases + 1) + ph) * 4 : nullptr;
             if (tr) tr[0] = gtime();
             if (kind == PH_GEMV) {
-                XUnit xr;      // scoped to the phase: dead (no registers pinned) during attention / barriers
-                const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid, xr);
+                const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid);
                 if (tr) tr[1] = gtime();
-                gemv_consume<ABITS, NW>(P.g, ring, smem, tid, xr, scale, cta, G);
+                gemv_consume<ABITS, NW>(P.g, ring, smem, tid, scale, cta, G);
                 if (P.flags & PHF_HEAD) {
                     // per-CTA softmax statistics over the logits rows this CTA produced
                     named_bar_sync(1, NT);
@@ -532,9 +531,7 @@ size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes) {
 
 cudaError_t mega_configure() {
     cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
 }
 
@@ -550,8 +547,7 @@ cudaError_t mega_launch(const MegaParams& mp, int abits, int nw, int n_ctas, cud
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (abits == 16) return nw == 8 ? cudaLaunchKernelEx(&cfg, decode_mega_kernel<16, 8>, mp) : cudaLaunchKernelEx(&cfg, decode_mega_kernel<16, 12>, mp);
-    return nw == 8 ? cudaLaunchKernelEx(&cfg, decode_mega_kernel<8, 8>, mp) : cudaLaunchKernelEx(&cfg, decode_mega_kernel<8, 16>, mp);
+    return abits == 16 ? cudaLaunchKernelEx(&cfg, decode_mega_kernel<16, 8>, mp) : cudaLaunchKernelEx(&cfg, decode_mega_kernel<8, 8>, mp);
 }
 
 }  // namespace gl

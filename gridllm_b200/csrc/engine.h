@@ -102,6 +102,7 @@ private:
     int device_ = 0, sm_count_ = 148;
     int abits_ = 16;
     int nw_ = 8;               // consumer warps per CTA of the GEMV / persistent kernels
+    int ctas_per_sm_ = 2;      // stand-alone GEMV kernels: CTAs per SM (<=112 registers, <=113 KB shared memory each)
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
     int stage_kb_ = 24, smem_kb_ = 110, attn_splits_ = 16;
     int prefill_mode_ = 0, prefill_min_ = 8;

@@ -24,7 +24,7 @@ namespace gl {
 namespace {
 
 template <int ABITS, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
+__global__ void __launch_bounds__((NW + 1) * 32, 2) gemv_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
@@ -51,9 +51,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
         return;
     }
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
-    XUnit xr;
-    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, xr);
-    gemv_consume<ABITS, NW>(p, ring, smem, tid, xr, scale, blockIdx.x, gridDim.x);
+    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid);
+    gemv_consume<ABITS, NW>(p, ring, smem, tid, scale, blockIdx.x, gridDim.x);
 }
 
 }  // namespace
@@ -76,11 +75,11 @@ bool gemv_plan(GemvParams& p, int consumer_warps) {
         const int mult = p.pair ? 2 : 1;
         const bool pair_adj = (p.epi == EPI_QKV && s < 2);
         int r = p.stage_bytes / (sg.row_stride * mult);
-        if (r > 64) r = 64;
-        // a stage should hand every row group the same number of (pairs of) rows
-        const int granule = p.pair ? ngrp : 2 * ngrp;
-        if (r >= granule) r = r / granule * granule;
-        else if (!p.pair && r >= ngrp) r = ngrp;
+        if (r > 128) r = 128;
+        // whole quads per stage: 4 rows (2 gate + 2 up rows in pair mode), and where it fits one quad per row group
+        const int quad = p.pair ? 2 : 4;
+        if (r >= quad * ngrp) r = r / (quad * ngrp) * (quad * ngrp);
+        else if (r >= quad) r = r / quad * quad;
         if (pair_adj || p.epi == EPI_QKV) r &= ~1;
         if (r < ((p.epi == EPI_QKV) ? 2 : 1)) return false;
         sg.rows_per_stage = r;
@@ -94,13 +93,11 @@ bool gemv_plan(GemvParams& p, int consumer_warps) {
     return true;
 }
 
-bool gemv_variant_ok(int abits, int nw) { return (abits == 16 && (nw == 8 || nw == 12)) || (abits == 8 && (nw == 8 || nw == 16)); }
+bool gemv_variant_ok(int abits, int nw) { return (abits == 16 || abits == 8) && nw == 8; }
 
 cudaError_t gemv_configure() {
     cudaError_t e = cudaFuncSetAttribute(gemv_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<16, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
 }
 
@@ -116,8 +113,7 @@ cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (abits == 16) return nw == 8 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<16, 12>, p);
-    return nw == 8 ? cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 16>, p);
+    return abits == 16 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8>, p);
 }
 
 // ------------------------------------------------------------------------------------------------

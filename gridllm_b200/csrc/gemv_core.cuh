@@ -93,7 +93,7 @@ __device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, in
 // rstd (it cancels), so the planes are built from x*w while the sum of squares is still being reduced, and rstd is
 // applied once per output row.  One named barrier in total.
 template <int ABITS, int NW>
-__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, XUnit& xr) {
+__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid) {
     constexpr int NT = NW * 32;
     constexpr int MAX_IT = 4;              // K <= MAX_IT * NT/2 * 32 columns stay in registers (16384 at 8 warps)
     const int K = p.cols;
@@ -178,52 +178,26 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
         scale = 1.0f / sqrtf(tot / (float)K + p.eps);
     }
 
-    const int nu = K / UNIT_COLS;
-    const int wpr = warps_per_row(K);
-    const int u = (warp % wpr) * 32 + lane;
-    if (u < nu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int phys = j ^ (u & 7);
-            const uint4 h = *reinterpret_cast<const uint4*>(xhi + u * 128 + phys * 16);
-            xr.hi[4 * j] = h.x; xr.hi[4 * j + 1] = h.y; xr.hi[4 * j + 2] = h.z; xr.hi[4 * j + 3] = h.w;
-            if (ABITS == 16) {
-                const uint4 l = *reinterpret_cast<const uint4*>(xlo + u * 128 + phys * 16);
-                xr.lo[4 * j] = l.x; xr.lo[4 * j + 1] = l.y; xr.lo[4 * j + 2] = l.z; xr.lo[4 * j + 3] = l.w;
-            }
-        }
-        const float4 a = *reinterpret_cast<const float4*>(sx_arr + 4 * u);
-        const float4 b = *reinterpret_cast<const float4*>(sm_arr + 4 * u);
-        xr.sx[0] = a.x; xr.sx[1] = a.y; xr.sx[2] = a.z; xr.sx[3] = a.w;
-        xr.sm[0] = b.x; xr.sm[1] = b.y; xr.sm[2] = b.z; xr.sm[3] = b.w;
-        const int4 c0 = *reinterpret_cast<const int4*>(s16_arr + 8 * u);
-        const int4 c1 = *reinterpret_cast<const int4*>(s16_arr + 8 * u + 4);
-        xr.s16[0] = c0.x; xr.s16[1] = c0.y; xr.s16[2] = c0.z; xr.s16[3] = c0.w;
-        xr.s16[4] = c1.x; xr.s16[5] = c1.y; xr.s16[6] = c1.z; xr.s16[7] = c1.w;
-    }
     // NOTE: the planes (and red[]) are rewritten only by the NEXT prologue, which every caller separates from this
     // point by a CTA-wide barrier (end of kernel, or the grid barrier of the persistent kernel).
     return scale;
 }
 
-template <int ABITS>
-__device__ __forceinline__ float unit_dot_type(int type, const uint8_t* row, int K, int u, const XUnit& xr) {
-    // type is warp-uniform; each case is a single inlined copy
-    if (type == T_Q4_K) return unit_dot_q4k<ABITS>(row + (size_t)(u >> 1) * 144, u & 1, xr);
-    if (type == T_Q6_K) return unit_dot_q6k<ABITS>(row, K >> 8, u, xr);
-    return unit_dot_q80<ABITS>(row, K, u, xr);
-}
-
-// reduce two per-lane partials over the warp with 6 shuffles; result: .x = sum(a0), .y = sum(a1) on lane 0
-__device__ __forceinline__ float2 warp_sum2(float a0, float a1, int lane) {
-    const bool hi = lane & 16;
-    float v = hi ? a1 : a0;
-    const float t = hi ? a0 : a1;
-    v += __shfl_xor_sync(0xffffffffu, t, 16);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const float w = __shfl_sync(0xffffffffu, v, 16);
-    return make_float2(v, w);
+// reduce four per-lane partials over the warp with 6 shuffles.  On return, lane L holds the warp total of row
+// ((L >> 3) & 3); i.e. lanes 0-7 -> row 0, 8-15 -> row 1, 16-23 -> row 2, 24-31 -> row 3.
+__device__ __forceinline__ float warp_sum4(const float* o, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    float ka = b4 ? o[2] : o[0], kb = b4 ? o[3] : o[1];
+    const float sa = b4 ? o[0] : o[2], sb = b4 ? o[1] : o[3];
+    ka += __shfl_xor_sync(0xffffffffu, sa, 16);
+    kb += __shfl_xor_sync(0xffffffffu, sb, 16);
+    float k = b3 ? kb : ka;
+    const float snd = b3 ? ka : kb;
+    k += __shfl_xor_sync(0xffffffffu, snd, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
 }
 
 struct EpiCtx {      // per-kernel constants of the QKV epilogue, loaded once
@@ -261,10 +235,17 @@ __device__ __forceinline__ void gemv_epilogue_item(const GemvParams& p, int seg,
 
 // ---------------------------------------------------------------------------------------------------
 // consumer main loop over this CTA's stages.  All consumer warps call it.
+//
+// A warp works on a QUAD of rows per iteration (quad_dot_* in rowdot.h): activations come from the shared-memory
+// planes, each x word is reused for four weight rows, 16 independent dp4a chains per lane.  After the 6-shuffle
+// reduction lane 8*r holds row r of the quad and runs that row's epilogue (operands prefetched before the dots).
+// Quad composition per epilogue kind:
+//   STORE / ADD / V rows : rows 4q .. 4q+3 of the stage
+//   RoPE pairs (q, k)    : same (pairs (0,1) and (2,3) are adjacent rows)
+//   gate/up (SiLU*mul)   : gate rows 2q, 2q+1 and the matching up rows (stage holds n gate rows, then n up rows)
 // ---------------------------------------------------------------------------------------------------
 template <int ABITS, int NW>
-__device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, const XUnit& xr, float scale, int cta,
-                                             int n_ctas) {
+__device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, float scale, int cta, int n_ctas) {
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     const int nu = K / UNIT_COLS;
@@ -278,79 +259,92 @@ __device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, ui
     const int gran = (p.epi == EPI_QKV) ? 2 : 1;
     const int nwork = p.pair ? 1 : p.nseg;
 
+    XPlanes xp;
+    {
+        uint8_t* xhi = smem + SM_X;
+        const int uu = valid ? u : 0;
+        xp.hi = xhi + uu * 128;
+        xp.lo = xhi + K + uu * 128;
+        const float* sx_arr = reinterpret_cast<const float*>(xhi + 2 * K);
+        xp.sx = sx_arr + 4 * uu;
+        xp.sm = sx_arr + K / 32 + 4 * uu;
+        xp.s16 = reinterpret_cast<const int*>(sx_arr + 2 * (K / 32)) + 8 * uu;
+        xp.sw = uu & 7;
+    }
     EpiCtx ec{0, 0};
     if (p.epi == EPI_QKV) {
         ec.pos = __ldcg(&p.st->pos);
         ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
     }
+    const int myrow = lane >> 3;             // row of the quad this lane reports after the reduction
+    const bool epi_lane = (lane & 7) == 0 && wsub == 0;
     int buf = 0;
     for (int s = 0; s < nwork; ++s) {
         const GemvSeg sg = p.seg[s];
         const WorkRange wr = cta_range(sg.rows, gran, cta, n_ctas);
-        // an "item" is what one epilogue needs: a RoPE pair (2 adjacent rows), a gate/up pair, or a single row
         const bool pair_adj = (p.epi == EPI_QKV && s < 2);
         const bool pair_gu = p.pair != 0;
         for (int r0 = wr.a; r0 < wr.b; r0 += sg.rows_per_stage) {
             const int n = min(sg.rows_per_stage, wr.b - r0);
-            const int nitems = pair_adj ? n / 2 : n;
+            const int nq = pair_gu ? (n + 1) / 2 : (n + 3) / 4;
             const uint8_t* base = ring.slot();
             mbar_wait(&ring.full[ring.st], ring.ph);
-            const bool paired = pair_adj || pair_gu;
-            const int step = paired ? ngrp : 2 * ngrp;      // unpaired rows are processed two at a time
-            for (int it = in_grp ? grp : nitems; it < nitems; it += step) {
-                int ra, rb, ga, gb;       // stage-local and global row indices of the (up to) two rows
-                if (pair_adj) { ra = 2 * it; rb = ra + 1; ga = r0 + ra; gb = ga + 1; }
-                else if (pair_gu) { ra = it; rb = n + it; ga = r0 + it; gb = ga; }
-                else { ra = it; rb = (it + ngrp < nitems) ? it + ngrp : -1; ga = r0 + ra; gb = r0 + rb; }
-                // prefetch the epilogue's operands so their latency hides behind the dot products
+            for (int qi = in_grp ? grp : nq; qi < nq; qi += ngrp) {
+                // stage-local rows of the quad (clamped: a ragged quad repeats its last row and ignores the result)
+                int lr[4];
+                if (pair_gu) {
+                    const int g0 = 2 * qi, g1 = min(2 * qi + 1, n - 1);
+                    lr[0] = g0; lr[1] = g1; lr[2] = n + g0; lr[3] = n + g1;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) lr[r] = min(4 * qi + r, n - 1);
+                }
+                // this lane's row for the epilogue
+                const int my_local = pair_gu ? (2 * qi + (myrow & 1)) : (4 * qi + myrow);
+                const bool my_ok = epi_lane && my_local < n && (pair_gu ? myrow < 2 : (pair_adj ? (myrow & 1) == 0 : true));
+                const int grow = r0 + my_local;                 // global row (gate row for gate/up)
                 float pre0 = 0.f, pre1 = 0.f;
-                if (lane == 0 && wsub == 0) {
-                    if (p.epi == EPI_ADD) {
-                        pre0 = __ldcg(p.resid + ga);
-                        if (rb >= 0) pre1 = __ldcg(p.resid + gb);
-                    } else if (pair_adj) {
-                        const int d2 = (ga % p.head_dim) >> 1;
+                if (my_ok) {
+                    if (p.epi == EPI_ADD) pre0 = __ldcg(p.resid + grow);
+                    else if (pair_adj) {
+                        const int d2 = (grow % p.head_dim) >> 1;
                         pre0 = p.rope_cos[(size_t)ec.pos * (p.head_dim / 2) + d2];
                         pre1 = p.rope_sin[(size_t)ec.pos * (p.head_dim / 2) + d2];
                     }
                 }
-                float a0 = 0.f, a1 = 0.f;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
                 if (valid) {
-                    const uint8_t* pa = base + (size_t)ra * sg.row_stride;
-                    const uint8_t* pb = base + (size_t)rb * sg.row_stride;
-                    if (rb >= 0 && sg.type == T_Q4_K) {
-                        unit_dot2_q4k<ABITS>(pa + (size_t)(u >> 1) * 144, pb + (size_t)(u >> 1) * 144, u & 1, xr, a0, a1);
-                    } else if (rb >= 0 && sg.type == T_Q6_K) {
-                        unit_dot2_q6k<ABITS>(pa, pb, K >> 8, u, xr, a0, a1);
+                    const uint8_t* rp[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) rp[r] = base + (size_t)lr[r] * sg.row_stride;
+                    if (sg.type == T_Q4_K) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) rp[r] += (size_t)(u >> 1) * 144;
+                        quad_dot_q4k<ABITS>(rp, u & 1, xp, o);
+                    } else if (sg.type == T_Q6_K) {
+                        quad_dot_q6k<ABITS>(rp, K >> 8, u, xp, o);
                     } else {
-                        a0 = unit_dot_type<ABITS>(sg.type, pa, K, u, xr);
-                        if (rb >= 0) a1 = unit_dot_type<ABITS>(sg.type, pb, K, u, xr);
+                        quad_dot_q80<ABITS>(rp, K, u, xp, o);
                     }
                 }
-                float2 sum;
-                if (rb >= 0) sum = warp_sum2(a0, a1, lane);
-                else sum = make_float2(warp_sum(a0), 0.f);
+                float tot = warp_sum4(o, lane);
                 if (wpr > 1) {
-                    // K > 4096: wpr warps share the row; partials meet in shared memory
-                    float* rbuf = res + buf * 256 + grp * 2 * wpr;
-                    if (lane == 0) { rbuf[wsub] = sum.x; rbuf[wpr + wsub] = sum.y; }
+                    // K > 4096: wpr warps share the rows; their partials meet in shared memory
+                    float* rbuf = res + buf * 256 + grp * 4 * wpr;
+                    if ((lane & 7) == 0) rbuf[myrow * wpr + wsub] = tot;
                     named_bar_sync(2 + grp, 32 * wpr);
-                    if (wsub == 0 && lane == 0) {
-                        float v0 = 0.f, v1 = 0.f;
-                        for (int j = 0; j < wpr; ++j) { v0 += rbuf[j]; v1 += rbuf[wpr + j]; }
-                        sum = make_float2(v0, v1);
+                    if (wsub == 0) {
+                        float t = 0.f;
+                        for (int j = 0; j < wpr; ++j) t += rbuf[myrow * wpr + j];
+                        tot = t;
                     }
-                    buf ^= 1;     // double buffer: the next item's partials never race the reader of this one
+                    buf ^= 1;     // double buffer: the next quad's partials never race the readers of this one
                 }
-                if (lane == 0 && wsub == 0) {
-                    sum.x *= scale;          // RMSNorm factor of the fused prologue (1 when there is no norm)
-                    sum.y *= scale;
-                    if (paired) {
-                        gemv_epilogue_item(p, s, ga, sum.x, sum.y, pre0, pre1, ec);
-                    } else {
-                        gemv_epilogue_item(p, s, ga, sum.x, 0.f, pre0, 0.f, ec);
-                        if (rb >= 0) gemv_epilogue_item(p, s, gb, sum.y, 0.f, pre1, 0.f, ec);
-                    }
+                // partner row of a pair: adjacent row (RoPE) or the up row (gate/up)
+                const float other = __shfl_xor_sync(0xffffffffu, tot, pair_gu ? 16 : 8);
+                if (my_ok) {
+                    const float v0 = tot * scale, v1 = other * scale;      // RMSNorm factor of the fused prologue (1 if none)
+                    gemv_epilogue_item(p, s, grow, v0, v1, pre0, pre1, ec);
                 }
             }
             __syncwarp();

@@ -59,6 +59,14 @@ GL_HD int dp4a_us(uint32_t a, uint32_t b, int c) {
 #endif
 }
 
+GL_HD float bits_to_float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
 GL_HD float half_bits_to_float(uint16_t h) {
 #if defined(__CUDA_ARCH__)
     return __half2float(__ushort_as_half(h));
@@ -356,6 +364,186 @@ GL_HD void unit_dot2_q6k(const uint8_t* row0, const uint8_t* row1, int nb, int u
     }
     out0 = d[0] * val[0];
     out1 = d[1] * val[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Four rows at once, activations read from the (swizzled) shared-memory planes instead of registers.
+//
+// Register budget is what limited occupancy: an XUnit is 64-80 registers per lane.  Here a lane keeps only the
+// x words of the 32-byte chunk it is working on (8-16 registers) and amortises each x load over FOUR weight rows,
+// which also gives every dp4a 16 independent accumulator chains around it.  ~100 registers -> two CTAs (16
+// consumer warps) per SM.
+//
+// XPlanes: pointers to this lane's unit inside the planes written by the prologue:
+//   hi/lo  -> 128-byte area of the unit; 16-B chunk j lives at physical chunk (j ^ sw)
+//   sx, sm -> per-32-column scale / scale*sum(v) of the unit (4 floats each); s16 -> per-16-column sums (8 ints)
+// ---------------------------------------------------------------------------------------------
+struct XPlanes {
+    const uint8_t* hi;
+    const uint8_t* lo;
+    const float* sx;
+    const float* sm;
+    const int* s16;
+    int sw;          // u & 7
+};
+
+GL_HD U4 xchunk(const uint8_t* plane, int j, int sw) { return *reinterpret_cast<const U4*>(plane + ((j ^ sw) << 4)); }
+
+// rows[r] -> the 144-B super-block of row r that contains this unit (blk base), r = 0..3
+template <int ABITS>
+GL_HD void quad_dot_q4k(const uint8_t* const* blk, int hb, const XPlanes& xp, float* out) {
+    float val[4] = {0.f, 0.f, 0.f, 0.f};
+    U4 hdr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) hdr[r] = *reinterpret_cast<const U4*>(blk[r]);
+    const U4 sx4 = *reinterpret_cast<const U4*>(xp.sx);
+    const U4 sm4 = *reinterpret_cast<const U4*>(xp.sm);
+    const float sxf[4] = {bits_to_float(sx4.x), bits_to_float(sx4.y), bits_to_float(sx4.z), bits_to_float(sx4.w)};
+    const float smf[4] = {bits_to_float(sm4.x), bits_to_float(sm4.y), bits_to_float(sm4.z), bits_to_float(sm4.w)};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {            // 32-byte chunk pair: low nibbles -> sub-block 2c, high nibbles -> 2c+1
+        int ah[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0}, bh[4] = {0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            // x words of sub-block 2c (chunk 2*(2c)+v) and sub-block 2c+1 (chunk 2*(2c+1)+v) of the unit
+            const U4 xah = xchunk(xp.hi, 4 * c + v, xp.sw), xbh = xchunk(xp.hi, 4 * c + 2 + v, xp.sw);
+            U4 xal = {0, 0, 0, 0}, xbl = {0, 0, 0, 0};
+            if (ABITS == 16) { xal = xchunk(xp.lo, 4 * c + v, xp.sw); xbl = xchunk(xp.lo, 4 * c + 2 + v, xp.sw); }
+            const uint32_t xa_h[4] = {xah.x, xah.y, xah.z, xah.w}, xb_h[4] = {xbh.x, xbh.y, xbh.z, xbh.w};
+            const uint32_t xa_l[4] = {xal.x, xal.y, xal.z, xal.w}, xb_l[4] = {xbl.x, xbl.y, xbl.z, xbl.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const U4 qq = *reinterpret_cast<const U4*>(blk[r] + 16 + 64 * hb + 16 * (2 * c + v));
+                const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t lo4 = w[k] & 0x0F0F0F0Fu, hi4 = w[k] & 0xF0F0F0F0u;
+                    ah[r] = dp4a_s(lo4, xa_h[k], ah[r]);
+                    bh[r] = dp4a_us(hi4, xb_h[k], bh[r]);
+                    if (ABITS == 16) {
+                        al[r] = dp4a_s(lo4, xa_l[k], al[r]);
+                        bl[r] = dp4a_us(hi4, xb_l[k], bl[r]);
+                    }
+                }
+            }
+        }
+        const int sa = 2 * c, sb = 2 * c + 1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t s0 = hdr[r].y, s1 = hdr[r].z, s2 = hdr[r].w;
+            const uint32_t sc4 = hb ? ((s2 & 0x0F0F0F0Fu) | ((s0 >> 2) & 0x30303030u)) : (s0 & 0x3F3F3F3Fu);
+            const uint32_t mn4 = hb ? (((s2 >> 4) & 0x0F0F0F0Fu) | ((s1 >> 2) & 0x30303030u)) : (s1 & 0x3F3F3F3Fu);
+            const float d = half_bits_to_float((uint16_t)(hdr[r].x & 0xFFFF));
+            const float dmin = half_bits_to_float((uint16_t)(hdr[r].x >> 16));
+            const float sca = (float)((sc4 >> (8 * sa)) & 0xFF), scb = (float)((sc4 >> (8 * sb)) & 0xFF) * 0.0625f;
+            const float mna = (float)((mn4 >> (8 * sa)) & 0xFF), mnb = (float)((mn4 >> (8 * sb)) & 0xFF);
+            val[r] += d * (sca * ((float)combine<ABITS>(ah[r], al[r]) * sxf[sa]) + scb * ((float)combine<ABITS>(bh[r], bl[r]) * sxf[sb]))
+                    - dmin * (mna * smf[sa] + mnb * smf[sb]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = val[r];
+}
+
+// rows[r] -> start of the Q6_K-T row r
+template <int ABITS>
+GL_HD void quad_dot_q6k(const uint8_t* const* row, int nb, int u, const XPlanes& xp, float* out) {
+    const int nu = 2 * nb;
+    float val[4] = {0.f, 0.f, 0.f, 0.f};
+    const U4 sx4 = *reinterpret_cast<const U4*>(xp.sx);
+    const float sxf[4] = {bits_to_float(sx4.x), bits_to_float(sx4.y), bits_to_float(sx4.z), bits_to_float(sx4.w)};
+    const U4 g0 = *reinterpret_cast<const U4*>(xp.s16), g1 = *reinterpret_cast<const U4*>(xp.s16 + 4);
+    const int s16[8] = {(int)g0.x, (int)g0.y, (int)g0.z, (int)g0.w, (int)g1.x, (int)g1.y, (int)g1.z, (int)g1.w};
+    uint32_t scw[4][2];
+    float d[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint8_t* scp = row[r] + (size_t)nb * 192 + (size_t)u * 8;
+        scw[r][0] = reinterpret_cast<const uint32_t*>(scp)[0];
+        scw[r][1] = reinterpret_cast<const uint32_t*>(scp)[1];
+        d[r] = half_bits_to_float(*reinterpret_cast<const uint16_t*>(row[r] + (size_t)nb * 208 + (size_t)(u >> 1) * 2));
+    }
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+        const int t = i4 >> 1;
+        // x words of the A elements (columns 16*i4..) and B elements (columns 64+16*i4..): chunk i4 and chunk 4+i4
+        const U4 xah = xchunk(xp.hi, i4, xp.sw), xbh = xchunk(xp.hi, 4 + i4, xp.sw);
+        U4 xal = {0, 0, 0, 0}, xbl = {0, 0, 0, 0};
+        if (ABITS == 16) { xal = xchunk(xp.lo, i4, xp.sw); xbl = xchunk(xp.lo, 4 + i4, xp.sw); }
+        const uint32_t xa_h[4] = {xah.x, xah.y, xah.z, xah.w}, xb_h[4] = {xbh.x, xbh.y, xbh.z, xbh.w};
+        const uint32_t xa_l[4] = {xal.x, xal.y, xal.z, xal.w}, xb_l[4] = {xbl.x, xbl.y, xbl.z, xbl.w};
+        const int ga = i4, gb = 4 + i4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const U4 ql = *reinterpret_cast<const U4*>(row[r] + ((size_t)i4 * nu + u) * 16);
+            const U4 qh = *reinterpret_cast<const U4*>(row[r] + (size_t)nb * 128 + ((size_t)(i4 & 1) * nu + u) * 16);
+            const uint32_t qlw[4] = {ql.x, ql.y, ql.z, ql.w}, qhw[4] = {qh.x, qh.y, qh.z, qh.w};
+            int ah = 0, al = 0, bh = 0, bl = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a4 = (qlw[k] & 0x0F0F0F0Fu) | (((qhw[k] >> (2 * t)) & 0x03030303u) << 4);
+                const uint32_t b4 = ((qlw[k] >> 4) & 0x0F0F0F0Fu) | (((qhw[k] >> (4 + 2 * t)) & 0x03030303u) << 4);
+                ah = dp4a_s(a4, xa_h[k], ah);
+                bh = dp4a_s(b4, xb_h[k], bh);
+                if (ABITS == 16) {
+                    al = dp4a_s(a4, xa_l[k], al);
+                    bl = dp4a_s(b4, xb_l[k], bl);
+                }
+            }
+            const float sca = (float)(int8_t)(scw[r][ga >> 2] >> (8 * (ga & 3)));
+            const float scb = (float)(int8_t)(scw[r][gb >> 2] >> (8 * (gb & 3)));
+            const int ia = combine<ABITS>(ah, al) - 32 * s16[ga];
+            const int ib = combine<ABITS>(bh, bl) - 32 * s16[gb];
+            val[r] += sca * ((float)ia * sxf[ga >> 1]) + scb * ((float)ib * sxf[gb >> 1]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = d[r] * val[r];
+}
+
+// rows[r] -> start of the Q8_0-T row r
+template <int ABITS>
+GL_HD void quad_dot_q80(const uint8_t* const* row, int cols, int u, const XPlanes& xp, float* out) {
+    const int nu = cols / UNIT_COLS;
+    float val[4] = {0.f, 0.f, 0.f, 0.f};
+    const U4 sx4 = *reinterpret_cast<const U4*>(xp.sx);
+    const float sxf[4] = {bits_to_float(sx4.x), bits_to_float(sx4.y), bits_to_float(sx4.z), bits_to_float(sx4.w)};
+    uint32_t dw[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t* dp = reinterpret_cast<const uint32_t*>(row[r] + (size_t)cols + (size_t)u * 8);
+        dw[r][0] = dp[0];
+        dw[r][1] = dp[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {            // 32-column block j of the unit = chunks 2j, 2j+1
+        int ah[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int i = 2 * j + v;
+            const U4 xh = xchunk(xp.hi, i, xp.sw);
+            U4 xl = {0, 0, 0, 0};
+            if (ABITS == 16) xl = xchunk(xp.lo, i, xp.sw);
+            const uint32_t x_h[4] = {xh.x, xh.y, xh.z, xh.w}, x_l[4] = {xl.x, xl.y, xl.z, xl.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const U4 qq = *reinterpret_cast<const U4*>(row[r] + ((size_t)i * nu + u) * 16);
+                const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ah[r] = dp4a_s(w[k], x_h[k], ah[r]);
+                    if (ABITS == 16) al[r] = dp4a_s(w[k], x_l[k], al[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float dj = half_bits_to_float((uint16_t)(dw[r][j >> 1] >> (16 * (j & 1))));
+            val[r] += dj * ((float)combine<ABITS>(ah[r], al[r]) * sxf[j]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = val[r];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -80,6 +80,65 @@ static int run(int type, const uint8_t* w, int rows, int cols, const float* x, f
     return 0;
 }
 
+// rows taken four at a time through the quad functions, x read from swizzled planes exactly as the GPU prologue lays them out
+template <int AB>
+static int run_quads(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
+    std::vector<XUnit> xs;
+    build_xunits<AB>(x, cols, xs);
+    const int nu = cols / UNIT_COLS;
+    // planes: hi [cols], lo [cols] (16-B chunk j of unit u at physical chunk j ^ (u & 7)), sx / sm [cols/32], s16 [cols/16]
+    std::vector<uint8_t> raw(2 * (size_t)cols + 64);
+    uint8_t* hi = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+    uint8_t* lo = hi + cols;
+    std::vector<float> sx(cols / 32 + 4), sm(cols / 32 + 4);
+    std::vector<int> s16(cols / 16 + 4);
+    float* sxp = sx.data() + ((16 - ((uintptr_t)sx.data() & 15)) & 15) / 4;
+    float* smp = sm.data() + ((16 - ((uintptr_t)sm.data() & 15)) & 15) / 4;
+    int* s16p = s16.data() + ((16 - ((uintptr_t)s16.data() & 15)) & 15) / 4;
+    for (int u = 0; u < nu; ++u) {
+        for (int j = 0; j < 8; ++j) {
+            memcpy(hi + (size_t)u * 128 + ((j ^ (u & 7)) << 4), &xs[u].hi[4 * j], 16);
+            memcpy(lo + (size_t)u * 128 + ((j ^ (u & 7)) << 4), &xs[u].lo[4 * j], 16);
+        }
+        for (int b = 0; b < 4; ++b) { sxp[4 * u + b] = xs[u].sx[b]; smp[4 * u + b] = xs[u].sm[b]; }
+        for (int g = 0; g < 8; ++g) s16p[8 * u + g] = xs[u].s16[g];
+    }
+    size_t rb = row_bytes(type, cols), rs = align16(rb);
+    std::vector<uint8_t> buf(4 * rs + 16);
+    uint8_t* base = buf.data() + ((16 - ((uintptr_t)buf.data() & 15)) & 15);
+    for (int i = 0; i < rows; i += 4) {
+        const uint8_t* rp[4];
+        for (int r = 0; r < 4; ++r) {
+            const int ri = i + r < rows ? i + r : rows - 1;       // clamp like the GPU consumer does for ragged quads
+            uint8_t* dst = base + (size_t)r * rs;
+            if (type == T_Q4_K) memcpy(dst, w + (size_t)ri * rb, rb);
+            else if (type == T_Q6_K) repack_row_q6k(w + (size_t)ri * rb, dst, cols / 256);
+            else repack_row_q80(w + (size_t)ri * rb, dst, cols);
+            rp[r] = dst;
+        }
+        float acc[4] = {0, 0, 0, 0};
+        for (int u = 0; u < nu; ++u) {
+            XPlanes xp{hi + (size_t)u * 128, lo + (size_t)u * 128, sxp + 4 * u, smp + 4 * u, s16p + 8 * u, u & 7};
+            float o[4];
+            if (type == T_Q4_K) {
+                const uint8_t* bp[4];
+                for (int r = 0; r < 4; ++r) bp[r] = rp[r] + (size_t)(u >> 1) * 144;
+                quad_dot_q4k<AB>(bp, u & 1, xp, o);
+            } else if (type == T_Q6_K) quad_dot_q6k<AB>(rp, cols / 256, u, xp, o);
+            else quad_dot_q80<AB>(rp, cols, u, xp, o);
+            for (int r = 0; r < 4; ++r) acc[r] += o[r];
+        }
+        for (int r = 0; r < 4 && i + r < rows; ++r) y[i + r] = acc[r];
+    }
+    return 0;
+}
+
+extern "C" int hc_gemv_quads(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
+    if (cols % 128) return -2;
+    if ((type == T_Q4_K || type == T_Q6_K) && cols % 256) return -2;
+    return abits == 16 ? run_quads<16>(type, w, rows, cols, x, y) : run_quads<8>(type, w, rows, cols, x, y);
+}
+
 extern "C" int hc_gemv_pairs(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
     if (cols % 256 || (rows & 1)) return -2;
     return abits == 16 ? run_pairs<16>(type, w, rows, cols, x, y) : run_pairs<8>(type, w, rows, cols, x, y);

@@ -63,3 +63,22 @@ def test_paired_row_functions_equal_single_row(hostcheck_lib, tname):
             rc = hostcheck_lib.hc_gemv_pairs(t, blocks.ctypes.data_as(ctypes.c_void_p), 10, cols, x.ctypes.data_as(ctypes.c_void_p),
                                              y2.ctypes.data_as(ctypes.c_void_p), ab)
             assert rc == 0 and np.array_equal(y1, y2)
+
+
+@pytest.mark.parametrize("tname", ["Q4_K", "Q6_K", "Q8_0"])
+def test_quad_row_functions_equal_single_row(hostcheck_lib, tname):
+    """quad_dot_* (four rows per lane iteration, activations read from the swizzled shared-memory planes -- the
+    production consumer loop) == unit_dot_* bit for bit, including ragged row counts"""
+    from oracle import gguf_synth as S
+    t = {"Q4_K": S.Q4_K, "Q6_K": S.Q6_K, "Q8_0": S.Q8_0}[tname]
+    rng = np.random.Generator(np.random.PCG64(41))
+    for cols in (256, 768, 4096, 14336):
+        for rows in (8, 11):
+            blocks = S.random_blocks(rng, t, rows, cols)
+            x = rng.standard_normal(cols).astype(np.float32)
+            for ab in (16, 8):
+                y1 = _run(hostcheck_lib, t, blocks, rows, cols, x, ab)
+                y2 = np.zeros(rows, np.float32)
+                rc = hostcheck_lib.hc_gemv_quads(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, x.ctypes.data_as(ctypes.c_void_p),
+                                                 y2.ctypes.data_as(ctypes.c_void_p), ab)
+                assert rc == 0 and np.array_equal(y1, y2), (tname, cols, rows, ab)

@@ -27,14 +27,14 @@ def main():
     for t, r, c in shapes:
         mats[(t, r, c)] = S.random_blocks(rng, t, r, c)
     configs = [
-        {"GL_STAGE_KB": "36", "GL_SMEM_KB": "200"},
-        {"GL_STAGE_KB": "36", "GL_SMEM_KB": "200", "GL_WARPS": "8"},
-        {"GL_STAGE_KB": "36", "GL_SMEM_KB": "200", "GL_ACT_BITS": "8"},
-        {"GL_STAGE_KB": "54", "GL_SMEM_KB": "220"},
-        {"GL_STAGE_KB": "54", "GL_SMEM_KB": "220", "GL_ACT_BITS": "8"},
+        {},
+        {"GL_ACT_BITS": "8"},
+        {"GL_CTAS_PER_SM": "1"},
+        {"GL_CTAS_PER_SM": "1", "GL_STAGE_KB": "36"},
+        {"GL_STAGE_KB": "27"},
     ]
     for cfg in configs:
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_STAGE_KB", "GL_SMEM_KB", "GL_WARPS"):
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_STAGE_KB", "GL_SMEM_KB", "GL_WARPS", "GL_CTAS_PER_SM"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         e = N.Engine(tiny)
