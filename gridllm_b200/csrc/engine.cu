@@ -153,7 +153,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     nw_ = env_int("GL_WARPS", 8);          // measured: 8 consumer warps beat 12 / 16 (per-stage costs per warp dominate)
     if (!gemv_variant_ok(abits_, nw_)) nw_ = 8;
     // measured (profiles/r01_run11): 72 KB stages / 224 KB of shared memory: a CTA's whole slice of a small matrix lands as one bulk copy
-    ctas_per_sm_ = std::max(1, std::min(2, env_int("GL_CTAS_PER_SM", 2)));
+    ctas_per_sm_ = std::max(1, std::min(2, env_int("GL_CTAS_PER_SM", 1)));
     stage_kb_ = env_int("GL_STAGE_KB", ctas_per_sm_ == 2 ? 36 : 72);
     smem_kb_ = env_int("GL_SMEM_KB", ctas_per_sm_ == 2 ? 112 : 224);
     attn_splits_ = std::max(1, std::min(64, env_int("GL_ATTN_SPLITS", 16)));
@@ -386,7 +386,7 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch) {
     int ns = (int)(((size_t)smem_kb_ * 1024 - fixed) / p.stage_bytes);
     p.n_stages = std::max(2, std::min(GEMV_MAX_STAGES, ns));
     if (gemv_smem_bytes(p.cols, p.n_stages, p.stage_bytes) > 227 * 1024) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
-    CU(gemv_launch(p, abits_, nw_, sm_count_ * ctas_per_sm_, use_pdl_, s));
+    CU(gemv_launch(p, abits_, nw_, sm_count_ * ctas_per_sm_, ctas_per_sm_, use_pdl_, s));
     ++*n_launch;
     return {};
 }

@@ -23,8 +23,8 @@ namespace gl {
 
 namespace {
 
-template <int ABITS, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 2) gemv_kernel(const __grid_constant__ GemvParams p) {
+template <int ABITS, int NW, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB) gemv_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
@@ -96,12 +96,15 @@ bool gemv_plan(GemvParams& p, int consumer_warps) {
 bool gemv_variant_ok(int abits, int nw) { return (abits == 16 || abits == 8) && nw == 8; }
 
 cudaError_t gemv_configure() {
-    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     return e;
 }
 
-cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
+// ctas_per_sm selects the register budget the kernel was compiled for (1: unconstrained, 2: <= 112 registers)
+cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, int ctas_per_sm, bool pdl, cudaStream_t s) {
     if (!gemv_variant_ok(abits, nw)) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);
@@ -113,7 +116,9 @@ cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    return abits == 16 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8>, p);
+    if (ctas_per_sm >= 2)
+        return abits == 16 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8, 2>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8, 2>, p);
+    return abits == 16 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8, 1>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8, 1>, p);
 }
 
 // ------------------------------------------------------------------------------------------------

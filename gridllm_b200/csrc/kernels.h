@@ -60,7 +60,7 @@ size_t gemv_smem_bytes(int cols, int n_stages, int stage_bytes);
 // fills seg[i].rows_per_stage; returns false if the shape is outside the kernel's envelope
 bool gemv_plan(GemvParams& p, int consumer_warps);
 cudaError_t gemv_configure();   // opt-in to large dynamic shared memory (once per process)
-cudaError_t gemv_launch(const GemvParams& p, int abits, int consumer_warps, int n_ctas, bool pdl, cudaStream_t s);
+cudaError_t gemv_launch(const GemvParams& p, int abits, int consumer_warps, int n_ctas, int ctas_per_sm, bool pdl, cudaStream_t s);
 // (abits, consumer_warps) combinations that are compiled: (16,8) (16,12) (8,8) (8,16)
 bool gemv_variant_ok(int abits, int consumer_warps);
 

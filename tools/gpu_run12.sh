@@ -1,10 +1,10 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_gemv.py tests/test_gpu_decode.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
-timeout 600 python tools/microbench.py > gpurun_out/microbench.log 2>&1
+
 timeout 900 python tools/bench_quick.py > gpurun_out/bench_quick.log 2>&1
 python - <<'PY'
 import json
