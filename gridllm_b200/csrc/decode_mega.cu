@@ -13,6 +13,7 @@
 // Reference call site replaced: the decode loop inside Ollama behind OllamaService.generate*Response
 // (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237).
 #include "decode_mega.h"
+#include "attn_core.cuh"
 #include "gemv_core.cuh"
 
 namespace gl {
@@ -154,46 +155,6 @@ __device__ __forceinline__ void attn_prefetch(uint8_t* abuf, const MegaParams& m
     }
 }
 
-template <int DPL>
-__device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv, int npos, const float* q, float* o, float& m_run, float& l_run) {
-    float sc[KV_PAGE_TOKENS];
-#pragma unroll
-    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].x));
-        float a = q[0] * k0.x + q[1] * k0.y;
-        if (DPL == 4) {
-            const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].y));
-            a += q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
-        }
-        sc[j] = a;
-    }
-    float m_t = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-        sc[j] = warp_sum(sc[j]);
-        if (j < npos) m_t = fmaxf(m_t, sc[j]);
-    }
-    const float m_new = fmaxf(m_run, m_t);
-    const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-    l_run *= corr;
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) o[d] *= corr;
-#pragma unroll
-    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-        if (j < npos) {
-            const float w = expf(sc[j] - m_new);
-            l_run += w;
-            const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
-            o[0] += w * v0.x; o[1] += w * v0.y;
-            if (DPL == 4) {
-                const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
-                o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
-            }
-        }
-    }
-    m_run = m_new;
-}
-
 template <int DPL, int NT>
 __device__ __forceinline__ void attn_item(uint8_t* abuf, bool prefetched, uint32_t aparity, const MegaParams& mp, const __half* kc,
                                           const __half* vc, int item, int warp, int lane, int tid, int pos, int* smem_flag) {
@@ -269,42 +230,7 @@ __device__ __forceinline__ void attn_item(uint8_t* abuf, bool prefetched, uint32
     }
     named_bar_sync(1, NT);
     if (*smem_flag && active) {
-        // one round trip: (m, l) of split `lane` and the partial outputs of the first 8 splits travel together
-        float ms = -INFINITY, ls = 0.f;
-        if (lane < n_splits) {
-            ms = __ldcg(mp.part_ml + ((size_t)head * n_splits + lane) * 2);
-            ls = __ldcg(mp.part_ml + ((size_t)head * n_splits + lane) * 2 + 1);
-        }
-        const float* pbase = mp.part_o + (size_t)head * n_splits * HD + lane * DPL;
-        float acc[DPL];
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
-        float M = 0.f, wl = 0.f, den = 0.f;
-        for (int s0 = 0; s0 < n_splits; s0 += 8) {
-            float po[8][DPL];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                for (int d = 0; d < DPL; ++d) po[i][d] = (s0 + i < n_splits) ? __ldcg(pbase + (size_t)(s0 + i) * HD + d) : 0.f;
-            }
-            if (s0 == 0) {
-                M = warp_max(ms);
-                wl = (ms == -INFINITY) ? 0.f : expf(ms - M);
-                den = warp_sum(wl * ls);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float w = __shfl_sync(0xffffffffu, wl, (s0 + i) & 31);
-                if (s0 + i < n_splits) {
-#pragma unroll
-                    for (int d = 0; d < DPL; ++d) acc[d] += w * po[i][d];
-                }
-            }
-        }
-        const float inv = 1.0f / den;
-        float* out = mp.attn_out + (size_t)head * HD + lane * DPL;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) out[d] = acc[d] * inv;
+        attn_merge_head<DPL>(mp.part_o, mp.part_ml, mp.attn_out, head, n_splits, lane);
     }
 }
 

@@ -156,7 +156,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     ctas_per_sm_ = std::max(1, std::min(2, env_int("GL_CTAS_PER_SM", 1)));
     stage_kb_ = env_int("GL_STAGE_KB", ctas_per_sm_ == 2 ? 36 : 72);
     smem_kb_ = env_int("GL_SMEM_KB", ctas_per_sm_ == 2 ? 112 : 224);
-    attn_splits_ = std::max(1, std::min(64, env_int("GL_ATTN_SPLITS", 16)));
+    attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
 
