@@ -6,7 +6,9 @@
 // of KV per layer), so everything is arranged to shorten the dependent chain: one launch; all pages of a split
 // (<= 4) staged at once with 1-D TMA bulk copies (a 16-token page of one KV head is one contiguous block); 16
 // independent dot/shuffle chains per page; partials merged by the last CTA of each KV head (atomic ticket) with
-// batched loads -- no second kernel.
+// batched loads -- no second kernel.  The grid is fixed (it lives in a CUDA graph) but the number of splits that take
+// part is chosen from the context length at run time -- one page per split at least: surplus CTAs leave at once,
+// and a context of one page is written straight to the output without partials, ticket or merge.
 #include "attn_core.cuh"
 
 namespace gl {
@@ -40,8 +42,9 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
 
     const int L = __ldcg(&p.st->pos) + 1;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
-    const int pps = (n_pages + p.n_splits - 1) / p.n_splits;
-    const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
+    const int active = min(n_pages, p.n_splits);
+    if (split >= active) return;
+    const int pg0 = (split * n_pages) / active, pg1 = ((split + 1) * n_pages) / active;
 
     float q[DPL], o[DPL];
     {
@@ -84,6 +87,13 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
         if (t0 + TILE_PAGES < pg1) __syncthreads();   // tile buffers are re-filled by the next TMA
     }
 
+    if (active == 1) {
+        const float inv = 1.0f / l_run;
+        float* out = p.out + (size_t)head * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) out[d] = o[d] * inv;
+        return;
+    }
     // partial result of (head, split)
     {
         float* po = p.part_o + ((size_t)head * p.n_splits + split) * HD + lane * DPL;
@@ -98,12 +108,12 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     if (threadIdx.x == 0) {
         unsigned ticket;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.counters + kvh) : "memory");
-        is_last = (ticket == (unsigned)p.n_splits - 1);
+        is_last = (ticket == (unsigned)active - 1);
         if (is_last) p.counters[kvh] = 0;      // ready for the next launch
     }
     __syncthreads();
     if (!is_last) return;
-    attn_merge_head<DPL>(p.part_o, p.part_ml, p.out, head, p.n_splits, lane);
+    attn_merge_head<DPL>(p.part_o, p.part_ml, p.out, head, p.n_splits, active, lane);
 }
 
 }  // namespace

@@ -50,15 +50,17 @@ __device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv,
 
 // Merge the split partials of one head (run by one warp; n_splits <= 32): out = sum_s w_s o_s / sum_s w_s l_s with
 // w_s = exp(m_s - max m).  (m, l) of split `lane` and the partial outputs of 8 splits travel in one round trip.
+// `stride` is the number of partial slots per head in the buffers, n_splits (<= stride) how many of them are in use.
 template <int DPL>
-__device__ __forceinline__ void attn_merge_head(const float* part_o, const float* part_ml, float* attn_out, int head, int n_splits, int lane) {
+__device__ __forceinline__ void attn_merge_head(const float* part_o, const float* part_ml, float* attn_out, int head, int stride, int n_splits,
+                                                int lane) {
     constexpr int HD = DPL * 32;
     float ms = -INFINITY, ls = 0.f;
     if (lane < n_splits) {
-        ms = __ldcg(part_ml + ((size_t)head * n_splits + lane) * 2);
-        ls = __ldcg(part_ml + ((size_t)head * n_splits + lane) * 2 + 1);
+        ms = __ldcg(part_ml + ((size_t)head * stride + lane) * 2);
+        ls = __ldcg(part_ml + ((size_t)head * stride + lane) * 2 + 1);
     }
-    const float* pbase = part_o + (size_t)head * n_splits * HD + lane * DPL;
+    const float* pbase = part_o + (size_t)head * stride * HD + lane * DPL;
     float acc[DPL];
 #pragma unroll
     for (int d = 0; d < DPL; ++d) acc[d] = 0.f;

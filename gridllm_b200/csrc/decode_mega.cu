@@ -230,7 +230,7 @@ __device__ __forceinline__ void attn_item(uint8_t* abuf, bool prefetched, uint32
     }
     named_bar_sync(1, NT);
     if (*smem_flag && active) {
-        attn_merge_head<DPL>(mp.part_o, mp.part_ml, mp.attn_out, head, n_splits, lane);
+        attn_merge_head<DPL>(mp.part_o, mp.part_ml, mp.attn_out, head, n_splits, n_splits, lane);
     }
 }
 

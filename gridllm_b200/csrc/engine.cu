@@ -249,6 +249,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(dalloc((void**)&part_o_, (size_t)n_head_ * std::max(attn_splits_, 32) * hd_ * 4));
     CU(dalloc((void**)&part_ml_, (size_t)n_head_ * std::max(attn_splits_, 32) * 2 * 4));
     CU(dalloc((void**)&counters_, (size_t)n_kv_ * 4));
+    CU(dalloc((void**)&sample_scratch_, (size_t)SAMPLE_SCRATCH_FLOATS * 4));
     n_pages_ = n_ctx_ / KV_PAGE_TOKENS;
     kv_layer_elems_ = (size_t)n_pages_ * n_kv_ * KV_PAGE_TOKENS * hd_;
     CU(dalloc((void**)&kcache_, kv_layer_elems_ * n_layer_ * sizeof(__half)));
@@ -485,7 +486,7 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
         CU(rmsnorm_launch(x_, output_norm_, n_embd_, eps_, xn_, s)); ++*n_launch;
         ST(plain_gemv(s, output_, xn_, logits_, n_launch));
     }
-    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_};
+    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_, sample_scratch_};
     CU(sample_greedy_launch(sp, pdl && fused_, s));
     ++*n_launch;
     return {};

@@ -95,7 +95,7 @@ __device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, in
 template <int ABITS, int NW>
 __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid) {
     constexpr int NT = NW * 32;
-    constexpr int MAX_IT = 4;              // K <= MAX_IT * NT/2 * 32 columns stay in registers (16384 at 8 warps)
+    constexpr int NB = 8;                  // float4 loads in flight per thread (one L2 round trip per batch)
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -105,62 +105,58 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
     float* sm_arr = sx_arr + K / 32;
     int* s16_arr = reinterpret_cast<int*>(sm_arr + K / 32);
 
-    // every read of data produced upstream uses ld.global.cg: this CTA may have been resident (and its
-    // SM's L1 populated) before the producer of x finished.
-    const int half = tid & 1;
-    const int nblk = K / 32;
+    // Thread t owns float4 #(t + i*NT): a warp instruction covers 512 contiguous bytes (= four 32-column blocks, one
+    // 128-column unit), eight lanes share a block.  Every read of data produced upstream uses ld.global.cg: this CTA
+    // may have been resident (and its SM's L1 populated) before the producer of x finished.
+    const int nf = K / 4;                  // K % 256 == 0, so liveness below is uniform over a warp
     const bool norm = p.norm_w != nullptr;
+    const float4* x4 = reinterpret_cast<const float4*>(p.x);
+    const float4* w4 = reinterpret_cast<const float4*>(p.norm_w);
     float ss = 0.f;
-    for (int it0 = 0; it0 * (NT / 2) < nblk; it0 += MAX_IT) {
-        float v[MAX_IT][16];
-        // all loads of the batch are issued before anything waits on them: one L2 round trip
+    for (int f0 = tid; f0 < nf; f0 += NB * NT) {
+        float4 v[NB], wv[NB];
 #pragma unroll
-        for (int it = 0; it < MAX_IT; ++it) {
-            const int blk = (tid >> 1) + (it0 + it) * (NT / 2);
-            if (blk < nblk) {
-                const float* xb = p.x + blk * 32 + half * 16;
+        for (int i = 0; i < NB; ++i) {
+            const int f = f0 + i * NT;
+            if (f < nf) v[i] = __ldcg(x4 + f);
+        }
+        if (norm) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 t = __ldcg(reinterpret_cast<const float4*>(xb + 4 * q));
-                    v[it][4 * q] = t.x; v[it][4 * q + 1] = t.y; v[it][4 * q + 2] = t.z; v[it][4 * q + 3] = t.w;
-                }
+            for (int i = 0; i < NB; ++i) {
+                const int f = f0 + i * NT;
+                if (f < nf) wv[i] = w4[f];
             }
         }
 #pragma unroll
-        for (int it = 0; it < MAX_IT; ++it) {
-            const int blk = (tid >> 1) + (it0 + it) * (NT / 2);
-            const bool live = blk < nblk;        // uniform over the lane pair that shares a block
-            float amax = 0.f;
-            if (live) {
+        for (int i = 0; i < NB; ++i) {
+            const int f = f0 + i * NT;
+            if (f < nf) {
+                float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
                 if (norm) {
-                    const float* wb = p.norm_w + blk * 32 + half * 16;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 wv = *reinterpret_cast<const float4*>(wb + 4 * q);
-                        ss += v[it][4 * q] * v[it][4 * q] + v[it][4 * q + 1] * v[it][4 * q + 1] + v[it][4 * q + 2] * v[it][4 * q + 2] +
-                              v[it][4 * q + 3] * v[it][4 * q + 3];
-                        v[it][4 * q] *= wv.x; v[it][4 * q + 1] *= wv.y; v[it][4 * q + 2] *= wv.z; v[it][4 * q + 3] *= wv.w;
-                    }
+                    ss += e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
+                    e[0] *= wv[i].x; e[1] *= wv[i].y; e[2] *= wv[i].z; e[3] *= wv[i].w;
                 }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(v[it][q]));
-            }
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            uint32_t h4[4], l4[4];
-            int vs = 0;
-            if (live) snap16<ABITS>(v[it], amax, h4, l4, &vs);
-            const int vs_other = __shfl_xor_sync(0xffffffffu, vs, 1);
-            if (live) {
+                float amax = fmaxf(fmaxf(fabsf(e[0]), fabsf(e[1])), fmaxf(fabsf(e[2]), fabsf(e[3])));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                uint32_t h, l;
+                int vs;
+                snap4<ABITS>(e, snap_inv<ABITS>(amax), &h, &l, &vs);
+                vs += __shfl_xor_sync(0xffffffffu, vs, 1);
+                vs += __shfl_xor_sync(0xffffffffu, vs, 2);           // sum(v) of this 16-column group
+                const int vs32 = vs + __shfl_xor_sync(0xffffffffu, vs, 4);
+                const int blk = f >> 3, half = (f >> 2) & 1;
                 const int u = blk >> 2;
-                const int j = 2 * (blk & 3) + half;
-                const int phys = j ^ (u & 7);
-                *reinterpret_cast<uint4*>(xhi + u * 128 + phys * 16) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + u * 128 + phys * 16) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-                s16_arr[2 * blk + half] = vs;
-                if (half == 0) {
+                const int phys = (2 * (blk & 3) + half) ^ (u & 7);
+                const int off = u * 128 + phys * 16 + (f & 3) * 4;
+                *reinterpret_cast<uint32_t*>(xhi + off) = h;
+                if (ABITS == 16) *reinterpret_cast<uint32_t*>(xlo + off) = l;
+                if ((f & 3) == 0) s16_arr[2 * blk + half] = vs;
+                if ((f & 7) == 0) {
                     const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
                     sx_arr[blk] = sx;
-                    sm_arr[blk] = sx * (float)(vs + vs_other);
+                    sm_arr[blk] = sx * (float)vs32;
                 }
             }
         }

@@ -103,7 +103,10 @@ struct SampleParams {
     float* out_logprobs;
     float* logits_keep;     // optional [max_steps][n_vocab] copy for parity tests
     int max_out;
+    float* scratch;         // SAMPLE_SCRATCH_FLOATS floats, zeroed once: per-CTA (max, argmax, sum exp) + ticket
 };
+constexpr int SAMPLE_CTAS = 64;
+constexpr int SAMPLE_SCRATCH_FLOATS = 3 * SAMPLE_CTAS + 1;
 // greedy: argmax + log-softmax of the winner; advances StepState (pos+1, token=argmax, out_idx+1).
 cudaError_t sample_greedy_launch(const SampleParams& p, bool pdl, cudaStream_t s);
 // sequential-prefill step without sampling: pos += 1

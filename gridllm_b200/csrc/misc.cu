@@ -57,64 +57,111 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
         const int np = __ldcg(&p.st->n_prompt);
         int tok = __ldcg(&p.st->token);
         if (pos < np) tok = __ldcg(p.prompt_ids + pos);
-        p.st->token = tok;
+        if (blockIdx.x == 0) p.st->token = tok;       // same value every CTA derives: no ordering needed
         tok_s = tok;
     }
     __syncthreads();
+    // one column per thread: the row's bytes arrive in a single round trip
     const uint8_t* row = p.w + (size_t)tok_s * p.row_bytes;
-    for (int c = threadIdx.x; c < p.cols; c += blockDim.x) p.x[c] = dequant_native(row, p.type, c);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < p.cols; c += gridDim.x * blockDim.x) p.x[c] = dequant_native(row, p.type, c);
 }
 
-__global__ void __launch_bounds__(1024) sample_greedy_kernel(const __grid_constant__ SampleParams p) {
+// Greedy sampling over SAMPLE_CTAS CTAs: each scans a slice of the logits once (online max / argmax / sum of exp, all
+// loads of a thread in flight together), the last CTA to finish (atomic ticket) merges the per-CTA triples and
+// advances the step state.  Ties go to the lowest index.
+constexpr int SAMPLE_THREADS = 256;
+constexpr int SAMPLE_ILP = 8;
+
+struct Cand { float m; int i; float s; };     // running max, its index, sum of exp(x - m)
+__device__ __forceinline__ Cand cand_merge(const Cand& a, const Cand& b) {
+    Cand r;
+    const bool ta = a.m > b.m || (a.m == b.m && a.i <= b.i);
+    r.m = ta ? a.m : b.m;
+    r.i = ta ? a.i : b.i;
+    const float ea = (a.m == -INFINITY) ? 0.f : expf(a.m - r.m), eb = (b.m == -INFINITY) ? 0.f : expf(b.m - r.m);
+    r.s = a.s * ea + b.s * eb;
+    return r;
+}
+__device__ __forceinline__ Cand cand_warp(Cand c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand t;
+        t.m = __shfl_xor_sync(0xffffffffu, c.m, o);
+        t.i = __shfl_xor_sync(0xffffffffu, c.i, o);
+        t.s = __shfl_xor_sync(0xffffffffu, c.s, o);
+        c = cand_merge(c, t);
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_greedy_kernel(const __grid_constant__ SampleParams p) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float smax[32];
-    __shared__ int sidx[32];
-    __shared__ float ssum[32];
+    __shared__ Cand sc[SAMPLE_THREADS / 32];
+    __shared__ int is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     StepState* st = p.st;
     const int done = __ldcg(&st->done);
     const int out_idx = __ldcg(&st->out_idx);
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int i = tid; i < p.n_vocab; i += 1024) {
-        const float v = __ldcg(p.logits + i);
-        if (v > best) { best = v; bi = i; }       // strided scan keeps the lowest index per thread on ties
-    }
+    const bool keep = p.logits_keep != nullptr && !done && out_idx < p.max_out;
+    float* dst = keep ? p.logits_keep + (size_t)out_idx * p.n_vocab : nullptr;
+    Cand c{-INFINITY, 0x7fffffff, 0.f};
+    const int stride = SAMPLE_CTAS * SAMPLE_THREADS;
+    for (int i0 = blockIdx.x * SAMPLE_THREADS + tid; i0 < p.n_vocab; i0 += stride * SAMPLE_ILP) {
+        float v[SAMPLE_ILP];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) { smax[warp] = best; sidx[warp] = bi; }
-    __syncthreads();
-    best = smax[0]; bi = sidx[0];
-    for (int w = 1; w < 32; ++w) {
-        if (smax[w] > best || (smax[w] == best && sidx[w] < bi)) { best = smax[w]; bi = sidx[w]; }
-    }
-    float s = 0.f;
-    for (int i = tid; i < p.n_vocab; i += 1024) s += expf(__ldcg(p.logits + i) - best);
-    s = warp_sum(s);
-    if (lane == 0) ssum[warp] = s;
-    __syncthreads();
-    if (p.logits_keep != nullptr && !done && out_idx < p.max_out) {
-        float* dst = p.logits_keep + (size_t)out_idx * p.n_vocab;
-        for (int i = tid; i < p.n_vocab; i += 1024) dst[i] = __ldcg(p.logits + i);
-    }
-    if (tid == 0 && !done) {
-        float tot = 0.f;
-        for (int w = 0; w < 32; ++w) tot += ssum[w];
-        if (out_idx < p.max_out) {
-            p.out_ids[out_idx] = bi;
-            p.out_logprobs[out_idx] = -logf(tot);
+        for (int k = 0; k < SAMPLE_ILP; ++k) {
+            const int i = i0 + k * stride;
+            v[k] = i < p.n_vocab ? __ldcg(p.logits + i) : -INFINITY;
         }
-        st->token = bi;
+        float m = c.m;
+#pragma unroll
+        for (int k = 0; k < SAMPLE_ILP; ++k)
+            if (v[k] > m) { m = v[k]; c.i = i0 + k * stride; }       // ascending indices: strict > keeps the lowest on ties
+        float sum = (c.m == -INFINITY) ? 0.f : c.s * expf(c.m - m);
+#pragma unroll
+        for (int k = 0; k < SAMPLE_ILP; ++k) {
+            if (v[k] != -INFINITY) sum += expf(v[k] - m);
+            if (keep && i0 + k * stride < p.n_vocab) dst[i0 + k * stride] = v[k];
+        }
+        c.m = m;
+        c.s = sum;
+    }
+    c = cand_warp(c);
+    if (lane == 0) sc[warp] = c;
+    __syncthreads();
+    float* pm = p.scratch;
+    int* pi = reinterpret_cast<int*>(p.scratch + SAMPLE_CTAS);
+    float* ps = p.scratch + 2 * SAMPLE_CTAS;
+    unsigned* ticket_ctr = reinterpret_cast<unsigned*>(p.scratch + 3 * SAMPLE_CTAS);
+    if (tid == 0) {
+        Cand t = sc[0];
+        for (int w = 1; w < SAMPLE_THREADS / 32; ++w) t = cand_merge(t, sc[w]);
+        pm[blockIdx.x] = t.m; pi[blockIdx.x] = t.i; ps[blockIdx.x] = t.s;
+        unsigned ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(ticket_ctr) : "memory");
+        is_last = (ticket == SAMPLE_CTAS - 1);
+        if (is_last) *ticket_ctr = 0;
+    }
+    __syncthreads();
+    if (!is_last || warp != 0) return;
+    Cand t{-INFINITY, 0x7fffffff, 0.f};
+    for (int k = lane; k < SAMPLE_CTAS; k += 32) {
+        Cand u{__ldcg(pm + k), __ldcg(pi + k), __ldcg(ps + k)};
+        t = cand_merge(t, u);
+    }
+    t = cand_warp(t);
+    if (lane == 0 && !done) {
+        if (out_idx < p.max_out) {
+            p.out_ids[out_idx] = t.i;
+            p.out_logprobs[out_idx] = -logf(t.s);
+        }
+        st->token = t.i;
         st->pos = st->pos + 1;
         st->out_idx = out_idx + 1;
         if (!st->ignore_eos) {
             for (int k = 0; k < st->n_stop; ++k)
-                if (st->stop_ids[k] == bi) st->done = 1;
+                if (st->stop_ids[k] == t.i) st->done = 1;
         }
     }
 }
@@ -195,10 +242,10 @@ cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, bool pdl, c
 }  // namespace
 
 cudaError_t embed_launch(const EmbedParams& p, bool pdl, cudaStream_t s) {
-    return launch_pdl(embed_kernel, dim3(1), dim3(256), pdl, s, p);
+    return launch_pdl(embed_kernel, dim3((unsigned)((p.cols + 255) / 256)), dim3(256), pdl, s, p);
 }
 cudaError_t sample_greedy_launch(const SampleParams& p, bool pdl, cudaStream_t s) {
-    return launch_pdl(sample_greedy_kernel, dim3(1), dim3(1024), pdl, s, p);
+    return launch_pdl(sample_greedy_kernel, dim3(SAMPLE_CTAS), dim3(SAMPLE_THREADS), pdl, s, p);
 }
 cudaError_t advance_launch(StepState* st, bool pdl, cudaStream_t s) {
     return launch_pdl(advance_kernel, dim3(1), dim3(32), pdl, s, st);

@@ -92,34 +92,47 @@ struct XUnit {
 
 template <int ABITS> GL_HD int combine(int acc_hi, int acc_lo) { return ABITS == 16 ? acc_hi * 128 + acc_lo : acc_hi; }
 
-// Snap 16 consecutive activations (half of a 32-column block) to the fixed point.  amax is the
-// max |x| over the WHOLE 32-column block.  Produces 4 hi words, 4 lo words and sum(v).
+// Snap 4 consecutive activations of a 32-column block to the fixed point: one hi word, one lo word, sum(v).
+// inv = RANGE / amax of the WHOLE block (0 for an all-zero block).
 // Spec (oracle/llama_oracle.py snap_i16 / snap_q8): sx = amax/RANGE, v = rint(x * (RANGE/amax)).
 template <int ABITS>
+GL_HD void snap4(const float* x, float inv, uint32_t* hi, uint32_t* lo, int* vsum) {
+    uint32_t h = 0, l = 0;
+    int s = 0;
+    for (int b = 0; b < 4; ++b) {
+#if defined(__CUDA_ARCH__)
+        int v = __float2int_rn(x[b] * inv);
+#else
+        int v = (int)__builtin_rintf(x[b] * inv);
+#endif
+        s += v;
+        if (ABITS == 16) {
+            int lw = ((v + 64) & 127) - 64;
+            int hh = (v - lw) >> 7;
+            h |= (uint32_t)(hh & 0xFF) << (8 * b);
+            l |= (uint32_t)(lw & 0xFF) << (8 * b);
+        } else {
+            h |= (uint32_t)(v & 0xFF) << (8 * b);
+        }
+    }
+    *hi = h;
+    *lo = l;
+    *vsum = s;
+}
+
+template <int ABITS> GL_HD float snap_inv(float amax) {
+    return amax > 0.f ? (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE) / amax : 0.f;
+}
+
+// 16 consecutive activations (half of a 32-column block): 4 hi words, 4 lo words and sum(v).
+template <int ABITS>
 GL_HD void snap16(const float* x, float amax, uint32_t* hi4, uint32_t* lo4, int* vsum) {
-    const float range = ABITS == 16 ? ACT16_RANGE : ACT8_RANGE;
-    const float inv = amax > 0.f ? range / amax : 0.f;
+    const float inv = snap_inv<ABITS>(amax);
     int s = 0;
     for (int w = 0; w < 4; ++w) {
-        uint32_t h = 0, l = 0;
-        for (int b = 0; b < 4; ++b) {
-#if defined(__CUDA_ARCH__)
-            int v = __float2int_rn(x[4 * w + b] * inv);
-#else
-            int v = (int)__builtin_rintf(x[4 * w + b] * inv);
-#endif
-            s += v;
-            if (ABITS == 16) {
-                int lo = ((v + 64) & 127) - 64;
-                int hh = (v - lo) >> 7;
-                h |= (uint32_t)(hh & 0xFF) << (8 * b);
-                l |= (uint32_t)(lo & 0xFF) << (8 * b);
-            } else {
-                h |= (uint32_t)(v & 0xFF) << (8 * b);
-            }
-        }
-        hi4[w] = h;
-        lo4[w] = l;
+        int vs;
+        snap4<ABITS>(x + 4 * w, inv, hi4 + w, lo4 + w, &vs);
+        s += vs;
     }
     *vsum = s;
 }

@@ -16,7 +16,7 @@ def main():
     os.environ.setdefault("GL_PREFILL", "1")      # no 16 GB fp16 copy needed to look at decode
     e = N.Engine(path, max_ctx=1024)
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-    ms, nl = e.time_decode(576, steps)
+    ms, nl = e.time_decode(int(sys.argv[2]) if len(sys.argv) > 2 else 576, steps)
     print("ms_per_token", ms, "launches", nl, flush=True)
     e.close()
 
