@@ -106,15 +106,19 @@ def load_cpu_oracle():
     portable prebuilt oracle/_ref/liboracle_cpu.so."""
     src = os.path.join(ROOT, "oracle", "c", "llama_cpu.c")
     so = os.path.join(ROOT, "oracle", "_ref", "liboracle_cpu.so")
-    native = os.path.join(MODEL_DIR, f"liboracle_cpu_native_{os.getuid()}.so")
+    # scratch build next to the portable one (oracle/_ref is git-ignored); /dev/shm is mounted noexec on the GPU boxes
+    native = os.path.join(ROOT, "oracle", "_ref", f"liboracle_cpu_native_{os.getuid()}.so")
+    lib = None
     try:
         cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
         subprocess.check_call([cc, "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", native, src, "-lm"],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
+        lib = C.CDLL(native)
         so = native
     except Exception:
-        pass
-    lib = C.CDLL(so)
+        lib = None
+    if lib is None:
+        lib = C.CDLL(so)
     lib.oc_load.restype = C.c_void_p
     lib.oc_load.argtypes = [C.c_char_p, C.c_int]
     lib.oc_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
