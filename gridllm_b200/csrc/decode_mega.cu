@@ -48,31 +48,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target,
     named_bar_sync(1, NT);
 }
 
-// producer: stream one GEMV phase described by a constant-bank descriptor
-__device__ __forceinline__ void produce_phase(const ProdDesc& d, Ring& ring, int cta, int n_ctas) {
-    const int nwork = d.pair ? 1 : d.nseg;
-    for (int s = 0; s < nwork; ++s) {
-        const ProdSeg sg = d.seg[s];
-        const int rps = d.rps[s];
-        const WorkRange wr = cta_range(sg.rows, d.gran, cta, n_ctas);
-        for (int r0 = wr.a; r0 < wr.b; r0 += rps) {
-            const int n = min(rps, wr.b - r0);
-            const uint32_t bytes = (uint32_t)n * (uint32_t)sg.row_stride;
-            mbar_wait(&ring.empty[ring.st], ring.ph ^ 1);
-            uint8_t* dst = ring.slot();
-            if (d.pair) {
-                mbar_expect_tx(&ring.full[ring.st], 2 * bytes);
-                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
-                tma_load_1d(dst + bytes, d.seg[1].w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
-            } else {
-                mbar_expect_tx(&ring.full[ring.st], bytes);
-                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
-            }
-            ring.advance();
-        }
-    }
-}
-
 __device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int type, int c) {
     switch (type) {
         case T_F32: return reinterpret_cast<const float*>(row)[c];
@@ -248,18 +223,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     uint64_t* abar = reinterpret_cast<uint64_t*>(abuf + ATTN_SMEM_BYTES - 64);
     uint32_t aparity = 0;
     Ring ring;
-    ring.full = reinterpret_cast<uint64_t*>(smem + SM_BARS);
-    ring.empty = ring.full + GEMV_MAX_STAGES;
-    ring.slots = smem + fixed + 1024 + ATTN_SMEM_BYTES;
-    ring.n_slots = mp.n_slots;
-    ring.slot_bytes = mp.slot_bytes;
-    ring.st = 0;
-    ring.ph = 0;
+    ring.init(smem, smem + fixed + 1024 + ATTN_SMEM_BYTES, mp.n_tracks, mp.depth, mp.slot_bytes);
     if (tid == 0) {
-        for (int i = 0; i < mp.n_slots; ++i) {
-            mbar_init(&ring.full[i], 1);
-            mbar_init(&ring.empty[i], NW);
-        }
+        ring.init_barriers();
         mbar_init(abar, 1);
         fence_mbar_init();
     }
@@ -267,10 +233,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
 
     if (warp == NW) {
         // ============ producer: every weight phase of every step, never blocked by grid barriers ============
-        if (lane == 0) {
-            for (int step = 0; step < mp.n_steps; ++step)
-                for (int i = 0; i < mp.n_prod; ++i) produce_phase(mp.prod[i], ring, cta, G);
-        }
+        Track tr{0u, 0u};
+        for (int step = 0; step < mp.n_steps; ++step)
+            for (int i = 0; i < mp.n_prod; ++i) gemv_produce(mp.prod[i], ring, tr, lane, cta, G);
         return;
     }
 
@@ -284,6 +249,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     StepState* st = mp.st;
     const unsigned bar_base = __ldcg(&st->bar_base);
     unsigned nbar = 0;
+    Track trk{0u, 0u};            // this warp's position in its ring track (mirrors its producer lane's)
     int dslot = 0;
     for (int step = 0; step < mp.n_steps; ++step) {
         // ---- token embedding (CTA 0) ----------------------------------------------------------------------
@@ -310,11 +276,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
             if (kind == PH_GEMV) {
                 const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid);
                 if (tr) tr[1] = gtime();
-                gemv_consume<ABITS, NW>(P.g, ring, smem, tid, scale, cta, G);
+                gemv_consume<ABITS>(P.g, ring, trk, smem, tid, scale, cta, G);
                 if (P.flags & PHF_HEAD) {
                     // per-CTA softmax statistics over the logits rows this CTA produced
                     named_bar_sync(1, NT);
-                    const WorkRange wr = cta_range(P.g.seg[0].rows, 1, cta, G);
+                    // the logits rows this CTA produced: its item range of the (single) lm_head matrix
+                    WorkRange wr = cta_range(P.g.pd.seg[0].n_items, cta, G);
+                    wr.a = min(wr.a * (int)P.g.pd.rpi[0], P.g.pd.seg[0].rows);
+                    wr.b = min(wr.b * (int)P.g.pd.rpi[0], P.g.pd.seg[0].rows);
                     float best = -INFINITY;
                     int bi = 0x7fffffff;
                     for (int i = wr.a + tid; i < wr.b; i += NT) {
@@ -350,7 +319,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
                     if (mp.logits_keep != nullptr) {
                         const int oi = __ldcg(&st->out_idx);
                         if (!__ldcg(&st->done) && oi < mp.max_out) {
-                            float* dst = mp.logits_keep + (size_t)oi * P.g.seg[0].rows;
+                            float* dst = mp.logits_keep + (size_t)oi * P.g.pd.seg[0].rows;
                             for (int i = wr.a + tid; i < wr.b; i += NT) dst[i] = __ldcg(mp.logits + i);
                         }
                     }
@@ -455,9 +424,24 @@ size_t mega_smem_bytes(int max_cols, int n_slots, int slot_bytes) {
     return (size_t)gemv_fixed_smem(max_cols) + 1024 + ATTN_SMEM_BYTES + (size_t)n_slots * slot_bytes;
 }
 
+namespace {
+template <int ABITS, int NW>
+cudaError_t mega_configure_one() {
+    return cudaFuncSetAttribute(decode_mega_kernel<ABITS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+template <int ABITS, int NW>
+cudaError_t mega_launch_one(const cudaLaunchConfig_t& cfg, const MegaParams& mp) {
+    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<ABITS, NW>, mp);
+}
+}  // namespace
+
 cudaError_t mega_configure() {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = mega_configure_one<16, 8>();
+    if (e == cudaSuccess) e = mega_configure_one<16, 12>();
+    if (e == cudaSuccess) e = mega_configure_one<16, 16>();
+    if (e == cudaSuccess) e = mega_configure_one<8, 8>();
+    if (e == cudaSuccess) e = mega_configure_one<8, 12>();
+    if (e == cudaSuccess) e = mega_configure_one<8, 16>();
     return e;
 }
 
@@ -466,14 +450,21 @@ cudaError_t mega_launch(const MegaParams& mp, int abits, int nw, int n_ctas, cud
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);
     cfg.blockDim = dim3((unsigned)gemv_threads(nw));
-    cfg.dynamicSmemBytes = mega_smem_bytes(mp.max_cols, mp.n_slots, mp.slot_bytes);
+    cfg.dynamicSmemBytes = mega_smem_bytes(mp.max_cols, mp.n_tracks * mp.depth, mp.slot_bytes);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barrier depends on it
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return abits == 16 ? cudaLaunchKernelEx(&cfg, decode_mega_kernel<16, 8>, mp) : cudaLaunchKernelEx(&cfg, decode_mega_kernel<8, 8>, mp);
+    if (abits == 16) {
+        if (nw == 8) return mega_launch_one<16, 8>(cfg, mp);
+        if (nw == 12) return mega_launch_one<16, 12>(cfg, mp);
+        return mega_launch_one<16, 16>(cfg, mp);
+    }
+    if (nw == 8) return mega_launch_one<8, 8>(cfg, mp);
+    if (nw == 12) return mega_launch_one<8, 12>(cfg, mp);
+    return mega_launch_one<8, 16>(cfg, mp);
 }
 
 }  // namespace gl

@@ -14,14 +14,8 @@ struct alignas(16) MegaPhase {
     GemvParams g;          // PH_GEMV: the whole work description; PH_ATTN: k_cache / v_cache of the layer
 };
 
-// What the producer lane needs to stream one GEMV phase.  Lives in the kernel-parameter constant bank so the
-// producer never waits on a global-memory round trip when it crosses a phase boundary.
-struct ProdSeg { const uint8_t* w; int rows; int row_stride; };
-struct alignas(16) ProdDesc {
-    ProdSeg seg[3];
-    short nseg, pair, gran, pad;
-    short rps[4];              // rows per stage of each segment
-};
+// The producer lane walks one ProdDesc (kernels.h) per GEMV phase.  They live in the kernel-parameter constant bank
+// so that it never waits on a global-memory round trip when it crosses a phase boundary.
 constexpr int MEGA_MAX_GEMV_PHASES = 400;     // 80 layers x 4 + head; 400 x 64 B = 25.6 KB of the 32 KB parameter space
 
 struct MegaParams {
@@ -53,7 +47,7 @@ struct MegaParams {
     float* logits_keep;
     int max_out;
     // ring
-    int n_slots, slot_bytes, max_cols;
+    int n_tracks, depth, slot_bytes, max_cols;   // ring: n_tracks x depth slots (gemv_core.cuh)
     unsigned long long* trace; // optional [n_ctas][n_phases+1][4] globaltimer stamps of the LAST step (GL_MEGA_TRACE=1)
     int n_prod;                // GEMV phases per token (entries of prod[] in use)
     ProdDesc prod[MEGA_MAX_GEMV_PHASES];

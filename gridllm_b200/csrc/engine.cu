@@ -103,8 +103,8 @@ Status Engine::upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layo
     m.gguf_bytes = t.nbytes;
     const size_t rb = row_bytes(t.type, t.cols());
     const bool repack = !native_layout && (t.type == T_Q6_K || t.type == T_Q8_0);
-    if (!native_layout && m.quantized() && (m.cols % UNIT_COLS)) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': cols must be a multiple of 128 for the quantised GEMV");
-    m.row_stride = (int)(native_layout ? rb : align16(rb));
+    if (!native_layout && m.quantized() && !ksplit(m.cols).nks) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': cols must be a multiple of 256 (and cut into <= 8 K-segments) for the quantised GEMV");
+    m.row_stride = (int)(native_layout ? rb : (m.quantized() ? (size_t)engine_row_stride(m.type, m.cols) : align16(rb)));
     const size_t total = (size_t)m.row_stride * m.rows;
     CU(cudaMalloc((void**)&m.w, total + 256));
     allocs_.push_back(m.w);
@@ -123,8 +123,8 @@ Status Engine::upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layo
                     for (size_t r = ti; r < nr; r += nthreads) {
                         const uint8_t* src = t.data + (r0 + r) * rb;
                         uint8_t* dst = stage.data() + r * m.row_stride;
-                        if (t.type == T_Q6_K && repack) { repack_row_q6k(src, dst, m.cols / 256); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
-                        else if (t.type == T_Q8_0 && repack) { repack_row_q80(src, dst, m.cols); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
+                        if (t.type == T_Q6_K && repack) repack_row_q6k(src, dst, m.cols);
+                        else if (t.type == T_Q8_0 && repack) repack_row_q80(src, dst, m.cols);
                         else { memcpy(dst, src, rb); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
                     }
                 });
@@ -150,12 +150,10 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     use_pdl_ = !(opts && opts->use_pdl == 0) && env_int("GL_PDL", 1) != 0;
     fused_ = env_int("GL_FUSE", 1) != 0;
     abits_ = env_int("GL_ACT_BITS", abits_) == 8 ? 8 : 16;
-    nw_ = env_int("GL_WARPS", 8);          // measured: 8 consumer warps beat 12 / 16 (per-stage costs per warp dominate)
-    if (!gemv_variant_ok(abits_, nw_)) nw_ = 8;
-    // measured (profiles/r01_run11): 72 KB stages / 224 KB of shared memory: a CTA's whole slice of a small matrix lands as one bulk copy
-    ctas_per_sm_ = std::max(1, std::min(2, env_int("GL_CTAS_PER_SM", 1)));
-    stage_kb_ = env_int("GL_STAGE_KB", ctas_per_sm_ == 2 ? 36 : 72);
-    smem_kb_ = env_int("GL_SMEM_KB", ctas_per_sm_ == 2 ? 112 : 224);
+    nw_ = env_int("GL_WARPS", 12);
+    if (!gemv_variant_ok(abits_, nw_)) nw_ = 12;
+    ring_depth_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH", 2)));
+    smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -375,19 +373,23 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
 // -------------------------------------------------------------------------------------------------
 // decode step
 // -------------------------------------------------------------------------------------------------
-Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch) {
-    p.n_stages = 3;
-    p.stage_bytes = stage_kb_ * 1024;
-    if (!gemv_plan(p, nw_)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(p.cols) + ")");
-    // shrink the stage to what the plan needs, then spend the shared-memory budget on depth
-    int need = 0;
-    for (int i = 0; i < p.nseg; ++i) need = std::max(need, p.seg[i].rows_per_stage * p.seg[i].row_stride * (p.pair ? 2 : 1));
-    p.stage_bytes = (need + 127) & ~127;
-    const size_t fixed = gemv_smem_bytes(p.cols, 0, 0);
-    int ns = (int)(((size_t)smem_kb_ * 1024 - fixed) / p.stage_bytes);
-    p.n_stages = std::max(2, std::min(GEMV_MAX_STAGES, ns));
-    if (gemv_smem_bytes(p.cols, p.n_stages, p.stage_bytes) > 227 * 1024) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
-    CU(gemv_launch(p, abits_, nw_, sm_count_ * ctas_per_sm_, ctas_per_sm_, use_pdl_, s));
+Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int* n_launch) {
+    // slot size: what the widest item of this kernel needs (Q4_K: 4 row segments, Q6_K / Q8_0: 2), ring depth: whatever
+    // shared memory is left, capped so that the bytes in flight stay near what the HBM pipe needs
+    int need = GEMV_MIN_SLOT_BYTES;
+    {
+        const KSplit ks = ksplit(cols);
+        if (!ks.nks) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
+        for (int i = 0; i < nmat; ++i) need = std::max(need, (mats[i].type == T_Q4_K ? 4 : 2) * kseg_bytes(mats[i].type, ks.seg_nb));
+    }
+    p.slot_bytes = (need + 127) & ~127;
+    if (!gemv_plan(p, mats, nmat, pair, cols, p.slot_bytes)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
+    const size_t fixed = gemv_smem_bytes(cols, 0, 0);
+    const int ns = std::min(RING_MAX_SLOTS, (int)(((size_t)smem_kb_ * 1024 - fixed) / p.slot_bytes));
+    p.depth = ring_depth_;
+    p.n_tracks = std::min(nw_, ns / p.depth);
+    if (p.n_tracks < 1) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
+    CU(gemv_launch(p, abits_, nw_, sm_count_, use_pdl_, s));
     ++*n_launch;
     return {};
 }
@@ -395,9 +397,9 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch) {
 Status Engine::plain_gemv(cudaStream_t s, const DevMatrix& m, const float* x, float* y, int* n_launch) {
     if (m.quantized()) {
         GemvParams p{};
-        p.seg[0] = GemvSeg{m.w, m.type, m.rows, m.row_stride, 0};
-        p.nseg = 1; p.cols = m.cols; p.x = x; p.epi = EPI_STORE; p.out = y; p.st = st_;
-        return enqueue_gemv(s, p, n_launch);
+        p.x = x; p.epi = EPI_STORE; p.out = y; p.st = st_;
+        const GemvMat mm[1] = {{m.w, m.type, m.rows}};
+        return enqueue_gemv(s, p, mm, 1, false, m.cols, n_launch);
     }
     CU(gemv_fp_launch(m.w, m.type, m.rows, m.cols, x, y, s));
     ++*n_launch;
@@ -418,13 +420,11 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         if (fused_) {
             GemvParams p{};
-            p.seg[0] = GemvSeg{L.wq.w, L.wq.type, L.wq.rows, L.wq.row_stride, 0};
-            p.seg[1] = GemvSeg{L.wk.w, L.wk.type, L.wk.rows, L.wk.row_stride, 0};
-            p.seg[2] = GemvSeg{L.wv.w, L.wv.type, L.wv.rows, L.wv.row_stride, 0};
-            p.nseg = 3; p.cols = n_embd_; p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
+            const GemvMat qkv[3] = {{L.wq.w, L.wq.type, L.wq.rows}, {L.wk.w, L.wk.type, L.wk.rows}, {L.wv.w, L.wv.type, L.wv.rows}};
+            p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
             p.rope_cos = rope_cos_; p.rope_sin = rope_sin_; p.head_dim = hd_; p.n_kv_heads = n_kv_;
             p.k_cache = kc; p.v_cache = vc; p.page_table = page_table_; p.st = st_;
-            ST(enqueue_gemv(s, p, n_launch));
+            ST(enqueue_gemv(s, p, qkv, 3, false, n_embd_, n_launch));
         } else {
             CU(rmsnorm_launch(x_, L.attn_norm, n_embd_, eps_, xn_, s)); ++*n_launch;
             ST(plain_gemv(s, L.wq, xn_, q_, n_launch));
@@ -442,19 +442,18 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
         }
         if (fused_) {
             GemvParams p{};
-            p.seg[0] = GemvSeg{L.wo.w, L.wo.type, L.wo.rows, L.wo.row_stride, 0};
-            p.nseg = 1; p.cols = n_head_ * hd_; p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
-            ST(enqueue_gemv(s, p, n_launch));
+            const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows}};
+            p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
+            ST(enqueue_gemv(s, p, mo, 1, false, n_head_ * hd_, n_launch));
             GemvParams g{};
-            g.seg[0] = GemvSeg{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.row_stride, 0};
-            g.seg[1] = GemvSeg{L.wup.w, L.wup.type, L.wup.rows, L.wup.row_stride, 0};
-            g.nseg = 2; g.pair = 1; g.cols = n_embd_; g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
+            const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows}, {L.wup.w, L.wup.type, L.wup.rows}};
+            g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
             if (L.wgate.type != L.wup.type) return fail(GL_ERR_UNSUPPORTED, "ffn_gate / ffn_up with different types");
-            ST(enqueue_gemv(s, g, n_launch));
+            ST(enqueue_gemv(s, g, mgu, 2, true, n_embd_, n_launch));
             GemvParams d{};
-            d.seg[0] = GemvSeg{L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.row_stride, 0};
-            d.nseg = 1; d.cols = n_ff_; d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
-            ST(enqueue_gemv(s, d, n_launch));
+            const GemvMat md[1] = {{L.wdown.w, L.wdown.type, L.wdown.rows}};
+            d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
+            ST(enqueue_gemv(s, d, md, 1, false, n_ff_, n_launch));
         } else {
             ST(plain_gemv(s, L.wo, attn_, ytmp_, n_launch));
             CU(add_launch(x_, ytmp_, n_embd_, x_, s)); ++*n_launch;
@@ -479,9 +478,9 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
     const bool pdl = use_pdl_;
     if (fused_) {
         GemvParams p{};
-        p.seg[0] = GemvSeg{output_.w, output_.type, output_.rows, output_.row_stride, 0};
-        p.nseg = 1; p.cols = n_embd_; p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
-        ST(enqueue_gemv(s, p, n_launch));
+        const GemvMat mh[1] = {{output_.w, output_.type, output_.rows}};
+        p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
+        ST(enqueue_gemv(s, p, mh, 1, false, n_embd_, n_launch));
     } else {
         CU(rmsnorm_launch(x_, output_norm_, n_embd_, eps_, xn_, s)); ++*n_launch;
         ST(plain_gemv(s, output_, xn_, logits_, n_launch));
@@ -542,32 +541,27 @@ Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
 Status Engine::build_mega() {
     CU(mega_configure());
     mega_max_cols_ = std::max(n_embd_, std::max(n_ff_, n_head_ * hd_));
-    if (mega_max_cols_ % UNIT_COLS || mega_max_cols_ > 32768) return {};      // outside the kernel envelope: per-op path
-    const int slot_kb = env_int("GL_MEGA_SLOT_KB", 36);
-    mega_slot_bytes_ = slot_kb * 1024;
+    if (mega_max_cols_ % 256 || mega_max_cols_ > 32768) return {};      // outside the kernel envelope: per-op path
+    mega_slot_bytes_ = (env_int("GL_MEGA_SLOT_BYTES", GEMV_MIN_SLOT_BYTES) + 127) & ~127;
     const size_t fixed = mega_smem_bytes(mega_max_cols_, 0, 0);
-    const size_t budget = (size_t)env_int("GL_MEGA_SMEM_KB", 224) * 1024;
+    const size_t budget = (size_t)env_int("GL_MEGA_SMEM_KB", 227) * 1024;
     if (fixed + 2 * (size_t)mega_slot_bytes_ > budget) return {};
-    mega_slots_ = (int)std::min<size_t>(GEMV_MAX_STAGES, (budget - fixed) / mega_slot_bytes_);
-    mega_slots_ = std::min(mega_slots_, env_int("GL_MEGA_SLOTS", GEMV_MAX_STAGES));
-    if (mega_slots_ < 2) return {};
+    mega_depth_ = ring_depth_;
+    mega_tracks_ = std::min(nw_, (int)std::min<size_t>(RING_MAX_SLOTS, (budget - fixed) / mega_slot_bytes_) / mega_depth_);
+    mega_tracks_ = std::min(mega_tracks_, env_int("GL_MEGA_TRACKS", nw_));
+    if (mega_tracks_ < 1) return {};
     std::vector<MegaPhase> ph;
     mega_prod_.clear();
     mega_splits_ = std::max(1, std::min(32, sm_count_ / n_kv_));
-    auto add_gemv = [&](GemvParams g, int flags) -> bool {
-        g.n_stages = mega_slots_;
-        g.stage_bytes = mega_slot_bytes_;
-        if (!gemv_plan(g, nw_)) return false;
+    auto add_gemv = [&](GemvParams g, const GemvMat* mats, int nmat, bool pair, int cols, int flags) -> bool {
+        g.n_tracks = mega_tracks_;
+        g.depth = mega_depth_;
+        g.slot_bytes = mega_slot_bytes_;
+        if (!gemv_plan(g, mats, nmat, pair, cols, mega_slot_bytes_)) return false;
         MegaPhase m{};
         m.kind = PH_GEMV; m.flags = flags; m.g = g;
         ph.push_back(m);
-        ProdDesc d{};
-        for (int i = 0; i < g.nseg; ++i) {
-            d.seg[i] = ProdSeg{g.seg[i].w, g.seg[i].rows, g.seg[i].row_stride};
-            d.rps[i] = (short)g.seg[i].rows_per_stage;
-        }
-        d.nseg = (short)g.nseg; d.pair = (short)g.pair; d.gran = (short)(g.epi == EPI_QKV ? 2 : 1);
-        mega_prod_.push_back(d);
+        mega_prod_.push_back(g.pd);
         return true;
     };
     for (int il = 0; il < n_layer_; ++il) {
@@ -575,37 +569,34 @@ Status Engine::build_mega() {
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         GemvParams p{};
-        p.seg[0] = GemvSeg{L.wq.w, L.wq.type, L.wq.rows, L.wq.row_stride, 0};
-        p.seg[1] = GemvSeg{L.wk.w, L.wk.type, L.wk.rows, L.wk.row_stride, 0};
-        p.seg[2] = GemvSeg{L.wv.w, L.wv.type, L.wv.rows, L.wv.row_stride, 0};
-        p.nseg = 3; p.cols = n_embd_; p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
+        const GemvMat qkv[3] = {{L.wq.w, L.wq.type, L.wq.rows}, {L.wk.w, L.wk.type, L.wk.rows}, {L.wv.w, L.wv.type, L.wv.rows}};
+        p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
         p.rope_cos = rope_cos_; p.rope_sin = rope_sin_; p.head_dim = hd_; p.n_kv_heads = n_kv_;
         p.k_cache = kc; p.v_cache = vc; p.page_table = page_table_; p.st = st_;
-        if (!add_gemv(p, 0)) return {};
+        if (!add_gemv(p, qkv, 3, false, n_embd_, 0)) return {};
         MegaPhase a{};
         a.kind = PH_ATTN; a.g.k_cache = kc; a.g.v_cache = vc;
         ph.push_back(a);
         GemvParams o{};
-        o.seg[0] = GemvSeg{L.wo.w, L.wo.type, L.wo.rows, L.wo.row_stride, 0};
-        o.nseg = 1; o.cols = n_head_ * hd_; o.x = attn_; o.epi = EPI_ADD; o.out = x_; o.resid = x_; o.st = st_;
-        if (!add_gemv(o, 0)) return {};
+        const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows}};
+        o.x = attn_; o.epi = EPI_ADD; o.out = x_; o.resid = x_; o.st = st_;
+        if (!add_gemv(o, mo, 1, false, n_head_ * hd_, 0)) return {};
         if (L.wgate.type != L.wup.type) return {};
         GemvParams g{};
-        g.seg[0] = GemvSeg{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.row_stride, 0};
-        g.seg[1] = GemvSeg{L.wup.w, L.wup.type, L.wup.rows, L.wup.row_stride, 0};
-        g.nseg = 2; g.pair = 1; g.cols = n_embd_; g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
-        if (!add_gemv(g, 0)) return {};
+        const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows}, {L.wup.w, L.wup.type, L.wup.rows}};
+        g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
+        if (!add_gemv(g, mgu, 2, true, n_embd_, 0)) return {};
         GemvParams d{};
-        d.seg[0] = GemvSeg{L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.row_stride, 0};
-        d.nseg = 1; d.cols = n_ff_; d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
-        if (!add_gemv(d, 0)) return {};
+        const GemvMat md[1] = {{L.wdown.w, L.wdown.type, L.wdown.rows}};
+        d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
+        if (!add_gemv(d, md, 1, false, n_ff_, 0)) return {};
     }
     mega_n_nohead_ = (int)ph.size();
     {
         GemvParams p{};
-        p.seg[0] = GemvSeg{output_.w, output_.type, output_.rows, output_.row_stride, 0};
-        p.nseg = 1; p.cols = n_embd_; p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
-        if (!add_gemv(p, PHF_HEAD)) return {};
+        const GemvMat mh[1] = {{output_.w, output_.type, output_.rows}};
+        p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
+        if (!add_gemv(p, mh, 1, false, n_embd_, PHF_HEAD)) return {};
     }
     mega_n_head_ = (int)ph.size();
     if ((int)mega_prod_.size() > MEGA_MAX_GEMV_PHASES) return {};          // too many layers for the parameter bank: per-op path
@@ -647,7 +638,7 @@ Status Engine::launch_mega(int n_steps, bool with_head, bool keep_logits) {
     mp.logits = logits_; mp.head_part = head_part_; mp.out_ids = out_ids_; mp.out_logprobs = out_lp_;
     mp.logits_keep = keep_logits ? logits_keep_ : nullptr;
     mp.max_out = keep_logits ? keep_cap_ : max_out_;
-    mp.n_slots = mega_slots_; mp.slot_bytes = mega_slot_bytes_; mp.max_cols = mega_max_cols_;
+    mp.n_tracks = mega_tracks_; mp.depth = mega_depth_; mp.slot_bytes = mega_slot_bytes_; mp.max_cols = mega_max_cols_;
     mp.trace = with_head ? mega_trace_ : nullptr;
     // producer descriptors: all GEMV phases of the token; the head phase is the last entry
     mp.n_prod = with_head ? (int)mega_prod_.size() : (int)mega_prod_.size() - 1;

@@ -72,7 +72,7 @@ private:
     Status upload_f32(const GGUFTensor& t, float** out, int expect);
     Status ensure_pages(int n_tokens);
     Status enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, int* n_launch);
-    Status enqueue_gemv(cudaStream_t s, GemvParams& p, int* n_launch);
+    Status enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int* n_launch);
     Status plain_gemv(cudaStream_t s, const DevMatrix& m, const float* x, float* y, int* n_launch);
     Status build_graphs();
     Status set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so);
@@ -101,10 +101,10 @@ private:
     // options
     int device_ = 0, sm_count_ = 148;
     int abits_ = 16;
-    int nw_ = 8;               // consumer warps per CTA of the GEMV / persistent kernels
-    int ctas_per_sm_ = 2;      // stand-alone GEMV kernels: CTAs per SM (<=112 registers, <=113 KB shared memory each)
+    int nw_ = 12;              // consumer warps per CTA of the GEMV / persistent kernels
+    int ring_depth_ = 2;       // ring slots per consumer warp (track depth, gemv_core.cuh)
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
-    int stage_kb_ = 24, smem_kb_ = 110, attn_splits_ = 16;
+    int smem_kb_ = 224, attn_splits_ = 16;
     int prefill_mode_ = 0, prefill_min_ = 8;
     bool have_w16_ = false, prefill_bf16_ = false;
     // prefill scratch (grown on demand)
@@ -117,7 +117,7 @@ private:
     // persistent decode kernel
     bool use_mega_ = false;
     MegaPhase *mega_head_ = nullptr, *mega_nohead_ = nullptr;
-    int mega_n_head_ = 0, mega_n_nohead_ = 0, mega_slots_ = 0, mega_slot_bytes_ = 0, mega_max_cols_ = 0;
+    int mega_n_head_ = 0, mega_n_nohead_ = 0, mega_tracks_ = 0, mega_depth_ = 2, mega_slot_bytes_ = 0, mega_max_cols_ = 0;
     unsigned* bar_counter_ = nullptr;
     float* head_part_ = nullptr;
     int mega_launches_ = 0;

@@ -4,17 +4,17 @@
 // OllamaService.generateResponse / generateStreamResponse
 // (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237).
 //
-// Design.  HBM-bound: every weight byte is used once per token, so the
-// kernel is a byte-streaming pipeline, not a GEMM.
-//   * persistent grid, one CTA per SM; each CTA owns a contiguous slice of every weight segment's
-//     rows (balanced to within 2 rows), so there is no tail wave and no atomics;
-//   * one producer warp streams whole rows with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP)
-//     into an mbarrier-guarded ring of shared-memory stages (weights are static, so the ring is
-//     filled BEFORE griddepcontrol.wait: under programmatic dependent launch the next kernel's
-//     weights are already in flight while the previous kernel drains);
-//   * eight consumer warps decode blocks straight out of shared memory with dp4a against the
-//     activation vector held in registers as two int8 planes (15-bit fixed point per 32-column
-//     block; rowdot.h), fp32 accumulate, warp-shuffle reduction;
+// Design (building blocks in gemv_core.cuh).  HBM-bound: every weight byte is used
+// once per token, so the kernel is a byte-streaming pipeline, not a GEMM.
+//   * persistent grid, one CTA per SM; each CTA owns a contiguous, balanced range of the phase's ITEMS
+//     (4 rows x K; 2 rows where 4 do not fit a slot), so there is no tail wave and no atomics;
+//   * one producer warp (lane w feeds consumer warp w) streams row segments with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into an
+//     mbarrier-guarded FIFO ring of small shared-memory slots (weights are static, so the ring is filled
+//     BEFORE griddepcontrol.wait: under programmatic dependent launch the next kernel's weights are
+//     already in flight while the previous kernel drains);
+//   * NW consumer warps, each owning whole items: dp4a block decode straight out of shared memory against
+//     the activation vector held in shared memory as two int8 planes (15-bit fixed point per 32-column
+//     block; rowdot.h), fp32 accumulate, warp-shuffle reduction -- no barrier between warps, ever;
 //   * fused prologue: RMSNorm + activation snap; fused epilogues: residual add, RoPE + KV-page
 //     append, SiLU*mul.
 #include "gemv_core.cuh"
@@ -23,23 +23,14 @@ namespace gl {
 
 namespace {
 
-template <int ABITS, int NW, int MINB>
-__global__ void __launch_bounds__((NW + 1) * 32, MINB) gemv_kernel(const __grid_constant__ GemvParams p) {
+template <int ABITS, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
-    ring.full = reinterpret_cast<uint64_t*>(smem + SM_BARS);
-    ring.empty = ring.full + GEMV_MAX_STAGES;
-    ring.slots = smem + gemv_fixed_smem(p.cols);
-    ring.n_slots = p.n_stages;
-    ring.slot_bytes = p.stage_bytes;
-    ring.st = 0;
-    ring.ph = 0;
+    ring.init(smem, smem + gemv_fixed_smem(p.cols), p.n_tracks, p.depth, p.slot_bytes);
     if (tid == 0) {
-        for (int i = 0; i < p.n_stages; ++i) {
-            mbar_init(&ring.full[i], 1);
-            mbar_init(&ring.empty[i], NW);
-        }
+        ring.init_barriers();
         fence_mbar_init();
     }
     __syncthreads();
@@ -47,78 +38,98 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) gemv_kernel(const __grid_
 
     if (warp == NW) {
         // producer: weights are static, so streaming starts before the upstream kernel has finished
-        if (lane == 0) gemv_produce(p, ring, blockIdx.x, gridDim.x);
+        Track tr{0u, 0u};
+        gemv_produce(p.pd, ring, tr, lane, blockIdx.x, gridDim.x);
         return;
     }
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
     const float scale = gemv_prologue<ABITS, NW>(p, smem, tid);
-    gemv_consume<ABITS, NW>(p, ring, smem, tid, scale, blockIdx.x, gridDim.x);
+    Track tr{0u, 0u};
+    gemv_consume<ABITS>(p, ring, tr, smem, tid, scale, blockIdx.x, gridDim.x);
 }
 
 }  // namespace
 
-size_t gemv_smem_bytes(int cols, int n_stages, int stage_bytes) {
-    return (size_t)gemv_fixed_smem(cols) + (size_t)n_stages * stage_bytes;
+size_t gemv_smem_bytes(int cols, int n_slots, int slot_bytes) {
+    return (size_t)gemv_fixed_smem(cols) + (size_t)n_slots * slot_bytes;
 }
 
-bool gemv_plan(GemvParams& p, int consumer_warps) {
-    if (p.cols % UNIT_COLS || p.cols <= 0 || p.cols > 32768) return false;
-    if (p.n_stages < 2 || p.n_stages > GEMV_MAX_STAGES || (p.stage_bytes & 127)) return false;
-    const int wpr = warps_per_row(p.cols);
-    const int ngrp = consumer_warps / wpr;
-    if (ngrp < 1) return false;
-    for (int s = 0; s < p.nseg; ++s) {
-        GemvSeg& sg = p.seg[s];
-        if (sg.type != T_Q4_K && sg.type != T_Q6_K && sg.type != T_Q8_0) return false;
-        if ((sg.type == T_Q4_K || sg.type == T_Q6_K) && (p.cols % 256)) return false;
-        if (sg.row_stride % 16 || ((uintptr_t)sg.w & 15)) return false;
-        const int mult = p.pair ? 2 : 1;
-        const bool pair_adj = (p.epi == EPI_QKV && s < 2);
-        int r = p.stage_bytes / (sg.row_stride * mult);
-        if (r > 128) r = 128;
-        // whole quads per stage: 4 rows (2 gate + 2 up rows in pair mode), and where it fits one quad per row group
-        const int quad = p.pair ? 2 : 4;
-        if (r >= quad * ngrp) r = r / (quad * ngrp) * (quad * ngrp);
-        else if (r >= quad) r = r / quad * quad;
-        if (pair_adj || p.epi == EPI_QKV) r &= ~1;
-        if (r < ((p.epi == EPI_QKV) ? 2 : 1)) return false;
-        sg.rows_per_stage = r;
-        if (p.epi == EPI_QKV && (sg.rows & 1)) return false;
+bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int slot_bytes) {
+    if (nmat < 1 || nmat > 3 || cols <= 0 || cols > 32768 || (cols & 255)) return false;
+    if (slot_bytes < GEMV_MIN_SLOT_BYTES || (slot_bytes & 127)) return false;
+    const KSplit ks = ksplit(cols);
+    if (!ks.nks) return false;
+    ProdDesc d{};
+    d.nseg = (unsigned char)nmat;
+    d.pair = pair ? 1 : 0;
+    d.nks = (unsigned char)ks.nks;
+    d.seg_nb = (unsigned char)ks.seg_nb;
+    for (int s = 0; s < nmat; ++s) {
+        const GemvMat& m = mats[s];
+        if (m.type != T_Q4_K && m.type != T_Q6_K && m.type != T_Q8_0) return false;
+        if (m.rows <= 0 || ((uintptr_t)m.w & 15)) return false;
+        const int sb = kseg_bytes(m.type, ks.seg_nb);
+        // Q4_K items are always 4 rows (GEMV_MIN_SLOT_BYTES guarantees the fit); the wider formats take 2
+        const int rpi = (m.type == T_Q4_K) ? 4 : 2;
+        if (rpi * sb > slot_bytes) return false;
+        d.seg[s].w = m.w;
+        d.seg[s].rows = m.rows;
+        const int rows_per_item = pair ? rpi / 2 : rpi;
+        d.seg[s].n_items = (m.rows + rows_per_item - 1) / rows_per_item;
+        d.seg_bytes[s] = (unsigned short)sb;
+        d.rpi[s] = (unsigned char)rpi;
+        d.type[s] = (unsigned char)m.type;
     }
-    if (p.pair) {
-        if (p.nseg != 2 || p.seg[0].type != p.seg[1].type || p.seg[0].rows != p.seg[1].rows ||
-            p.seg[0].row_stride != p.seg[1].row_stride) return false;
-        p.seg[1].rows_per_stage = p.seg[0].rows_per_stage;
-    }
+    if (pair && (nmat != 2 || mats[0].type != mats[1].type || mats[0].rows != mats[1].rows)) return false;
+    p.pd = d;
+    p.cols = cols;
     return true;
 }
 
-bool gemv_variant_ok(int abits, int nw) { return (abits == 16 || abits == 8) && nw == 8; }
+bool gemv_variant_ok(int abits, int nw) { return (abits == 16 || abits == 8) && (nw == 8 || nw == 12 || nw == 16); }
+
+namespace {
+template <int ABITS, int NW>
+cudaError_t configure_one() {
+    return cudaFuncSetAttribute(gemv_kernel<ABITS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+template <int ABITS, int NW>
+cudaError_t launch_one(const cudaLaunchConfig_t& cfg, const GemvParams& p) {
+    return cudaLaunchKernelEx(&cfg, gemv_kernel<ABITS, NW>, p);
+}
+}  // namespace
 
 cudaError_t gemv_configure() {
-    cudaError_t e = cudaFuncSetAttribute(gemv_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_kernel<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    cudaError_t e = configure_one<16, 8>();
+    if (e == cudaSuccess) e = configure_one<16, 12>();
+    if (e == cudaSuccess) e = configure_one<16, 16>();
+    if (e == cudaSuccess) e = configure_one<8, 8>();
+    if (e == cudaSuccess) e = configure_one<8, 12>();
+    if (e == cudaSuccess) e = configure_one<8, 16>();
     return e;
 }
 
-// ctas_per_sm selects the register budget the kernel was compiled for (1: unconstrained, 2: <= 112 registers)
-cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, int ctas_per_sm, bool pdl, cudaStream_t s) {
-    if (!gemv_variant_ok(abits, nw)) return cudaErrorInvalidValue;
+cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
+    if (!gemv_variant_ok(abits, nw) || p.n_tracks < 1 || p.n_tracks > nw || p.depth < 2 || p.n_tracks * p.depth > RING_MAX_SLOTS) return cudaErrorInvalidValue;
+    if (p.epi == EPI_QKV && ((p.pd.seg[0].rows & 1) || (p.pd.nseg > 1 && (p.pd.seg[1].rows & 1)))) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);
     cfg.blockDim = dim3((unsigned)gemv_threads(nw));
-    cfg.dynamicSmemBytes = gemv_smem_bytes(p.cols, p.n_stages, p.stage_bytes);
+    cfg.dynamicSmemBytes = gemv_smem_bytes(p.cols, p.n_tracks * p.depth, p.slot_bytes);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (ctas_per_sm >= 2)
-        return abits == 16 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8, 2>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8, 2>, p);
-    return abits == 16 ? cudaLaunchKernelEx(&cfg, gemv_kernel<16, 8, 1>, p) : cudaLaunchKernelEx(&cfg, gemv_kernel<8, 8, 1>, p);
+    if (abits == 16) {
+        if (nw == 8) return launch_one<16, 8>(cfg, p);
+        if (nw == 12) return launch_one<16, 12>(cfg, p);
+        return launch_one<16, 16>(cfg, p);
+    }
+    if (nw == 8) return launch_one<8, 8>(cfg, p);
+    if (nw == 12) return launch_one<8, 12>(cfg, p);
+    return launch_one<8, 16>(cfg, p);
 }
 
 // ------------------------------------------------------------------------------------------------

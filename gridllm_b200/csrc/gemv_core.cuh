@@ -1,15 +1,30 @@
 // Device-side building blocks of the weight-streaming GEMV, shared by the stand-alone kernel
 // (gemv.cu) and the persistent decode-step kernel (decode_mega.cu).
 //
-//   producer lane : gemv_produce()  -- 1-D TMA bulk copies of whole rows into an mbarrier ring
-//   consumer warps: gemv_prologue() -- (RMSNorm) + snap x to int8 planes -> this lane's XUnit registers
-//                   gemv_consume()  -- dp4a block decode out of shared memory, warp-shuffle reduction,
-//                                      fused epilogue (store / residual add / RoPE+KV append / SiLU*mul)
+//   producer warp : gemv_produce()  -- 1-D TMA bulk copies of row segments into an mbarrier ring of small
+//                                      slots; lane w feeds the track of consumer warp w
+//   consumer warps: gemv_prologue() -- (RMSNorm) + snap x to int8 planes in shared memory
+//                   gemv_consume()  -- every warp owns whole ITEMS (4 rows, or 2 where 4 do not fit a slot):
+//                                      dp4a block decode of the item's slots, warp-shuffle reduction, fused
+//                                      epilogue (store / residual add / RoPE+KV append / SiLU*mul)
 //
-// For K <= 4096 (one warp spans a row) every consumer warp is autonomous: it waits for a stage, reduces its
-// own rows, runs their epilogue from lane 0 with operands prefetched before the dot product, and releases
-// the stage -- there is no CTA-wide barrier in the steady state.  For larger K (ffn_down) the 2/4/8 warps
-// that share a row meet at a named barrier of just those warps.
+// Work decomposition (rowdot.h vocabulary).  The rows of a phase are cut into items; a CTA owns a contiguous,
+// balanced range of the flat item list; inside the CTA items are dealt round-robin to the consumer warps, so
+// no two warps ever share a row and there is NO barrier of any kind between the prologue and the end of the phase.
+// One ring slot = the R row-segments of one (item, K-segment).
+//
+// Ring discipline: TRACKS.  The ring is n_tracks x depth slots; consumer warp w owns track w (slots w*depth ..
+// w*depth+depth-1) and walks it cyclically, and producer lane w feeds exactly that track.  Every mbarrier therefore
+// has ONE waiter on each side, each of which completed the previous phase itself before it waits for the next --
+// the only situation in which a parity wait cannot alias.  (A shared FIFO of arbitrary depth looks attractive -- 19
+// slots for 12 warps -- but a warp can then wait two uses ahead of a slot another warp has not finished, and
+// try_wait.parity answers for the wrong phase; found on the GPU in run 20b.)  Warps beyond n_tracks idle in GEMV
+// phases; rounds are n_tracks items wide.
+//
+// Why small slots: the bytes a SM keeps in flight are what the HBM pipe needs (~48-64 KB per SM at 6.5 TB/s x ~1 us),
+// and nothing more -- every extra prefetched byte sits in the SM's request FIFO in front of the latency-critical
+// loads of a phase change (barrier flag, x), which is what profiles/r01_run19_mega_trace_inflight.log measured
+// (prologue 3.2 us at 72 KB in flight, 4.5 us at 144-180 KB).
 #pragma once
 #include "common.cuh"
 #include "gguf_file.h"
@@ -18,75 +33,132 @@
 
 namespace gl {
 
-constexpr int GEMV_MAX_WARPS = 16;      // consumer warps per CTA are a template parameter (8, 12 or 16)
-
 // shared-memory carve-up (bytes from the start of dynamic smem)
-constexpr int SM_BARS = 0;                 // full[8], empty[8] mbarriers
-constexpr int SM_RED = 128;                // 32 floats: RMSNorm partials
-constexpr int SM_RES = 256;                // 2 x 256 floats: cross-warp partial sums (K > 4096)
-constexpr int SM_X = 256 + 2 * 256 * 4;    // x planes start (2304)
+constexpr int SM_BARS = 0;                 // full[24], empty[24] mbarriers (384 B)
+constexpr int SM_RED = 384;                // 32 floats: RMSNorm partials
+constexpr int SM_MISC = 512;               // 128 B scratch (flags)
+constexpr int SM_X = 640;                  // x planes start
 
 __host__ __device__ inline int gemv_x_bytes(int cols) { return 2 * cols + cols / 2; }   // hi, lo, sx, sm, s16
 __host__ __device__ inline int gemv_fixed_smem(int cols) { return (SM_X + gemv_x_bytes(cols) + 127) & ~127; }
-
-__host__ __device__ inline int warps_per_row(int cols) {
-    const int w = (cols / UNIT_COLS + 31) / 32;
-    int p = 1;
-    while (p < w) p <<= 1;
-    return p;       // 1,2,4,8
-}
 
 struct Ring {
     uint64_t* full;
     uint64_t* empty;
     uint8_t* slots;
-    int n_slots;
-    int slot_bytes;
-    int st;
-    uint32_t ph;
-    __device__ __forceinline__ void advance() { if (++st == n_slots) { st = 0; ph ^= 1; } }
-    __device__ __forceinline__ uint8_t* slot() const { return slots + (size_t)st * slot_bytes; }
+    unsigned n_tracks;      // consumer warps that take items (<= NW)
+    unsigned depth;         // slots per track (>= 2)
+    unsigned slot_bytes;
+    __device__ __forceinline__ void init(uint8_t* smem, uint8_t* slot_base, int tracks, int d, int bytes) {
+        full = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+        empty = full + RING_MAX_SLOTS;
+        slots = slot_base;
+        n_tracks = (unsigned)tracks;
+        depth = (unsigned)d;
+        slot_bytes = (unsigned)bytes;
+    }
+    __device__ __forceinline__ void init_barriers() const {
+        for (unsigned i = 0; i < n_tracks * depth; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+    }
+};
+
+// Where a warp (or the producer lane that feeds it) stands in its track.
+struct Track {
+    unsigned d;      // slot inside the track
+    unsigned par;    // phase bit of that slot's next use
+    __device__ __forceinline__ void advance(unsigned depth) {
+        if (++d == depth) { d = 0; par ^= 1u; }
+    }
 };
 
 struct WorkRange { int a, b; };
-__device__ __forceinline__ WorkRange cta_range(int rows, int gran, int cta, int n_ctas) {
-    const int units = rows / gran;
+__device__ __forceinline__ WorkRange cta_range(int n, int cta, int n_ctas) {
     WorkRange r;
-    r.a = (int)(((long long)cta * units) / n_ctas) * gran;
-    r.b = (int)(((long long)(cta + 1) * units) / n_ctas) * gran;
+    r.a = (int)(((long long)cta * n) / n_ctas);
+    r.b = (int)(((long long)(cta + 1) * n) / n_ctas);
     return r;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// producer (one lane): stream this CTA's rows of every segment
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, int cta, int n_ctas) {
-    const int gran = (p.epi == EPI_QKV) ? 2 : 1;
-    const int nwork = p.pair ? 1 : p.nseg;
-    for (int s = 0; s < nwork; ++s) {
-        const GemvSeg sg = p.seg[s];
-        const WorkRange wr = cta_range(sg.rows, gran, cta, n_ctas);
-        for (int r0 = wr.a; r0 < wr.b; r0 += sg.rows_per_stage) {
-            const int n = min(sg.rows_per_stage, wr.b - r0);
-            const uint32_t bytes = (uint32_t)n * (uint32_t)sg.row_stride;
-            mbar_wait(&ring.empty[ring.st], ring.ph ^ 1);
-            uint8_t* dst = ring.slot();
-            if (p.pair) {
-                mbar_expect_tx(&ring.full[ring.st], 2 * bytes);
-                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
-                tma_load_1d(dst + bytes, p.seg[1].w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
-            } else {
-                mbar_expect_tx(&ring.full[ring.st], bytes);
-                tma_load_1d(dst, sg.w + (size_t)r0 * sg.row_stride, bytes, &ring.full[ring.st]);
+__device__ __forceinline__ int total_items(const ProdDesc& d) {
+    int t = d.seg[0].n_items;
+    if (!d.pair) {
+        if (d.nseg > 1) t += d.seg[1].n_items;
+        if (d.nseg > 2) t += d.seg[2].n_items;
+    }
+    return t;
+}
+
+// flat item index -> (weight segment, item inside it)
+__device__ __forceinline__ void item_of(const ProdDesc& d, int flat, int& s, int& it) {
+    s = 0;
+    it = flat;
+    if (!d.pair) {
+        if (d.nseg > 1 && it >= d.seg[0].n_items) {
+            it -= d.seg[0].n_items;
+            s = 1;
+            if (d.nseg > 2 && it >= d.seg[1].n_items) {
+                it -= d.seg[1].n_items;
+                s = 2;
             }
-            ring.advance();
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// consumer prologue: x -> (RMSNorm) -> int8 planes in smem -> XUnit registers of this lane
-// All NCT consumer threads must call it (named barrier 1).
+// producer (one WARP): stream this CTA's slots of one phase.  Lane w feeds track w (= consumer warp w): its item of
+// every round, K-segment by K-segment, each slot as soon as that track's next slot is free.  tr is the lane's
+// position in its track (continues across the phases of the persistent kernel).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemv_produce(const ProdDesc& d, const Ring& ring, Track& tr, int lane, int cta, int n_ctas) {
+    const WorkRange wr = cta_range(total_items(d), cta, n_ctas);
+    const int nks = d.nks;
+    const int A = (int)ring.n_tracks;
+    if (lane >= A) return;
+    for (int i0 = wr.a + lane; i0 < wr.b; i0 += A) {
+        // this lane's item: source pointers and row counts are the same for every K-segment
+        int s, it;
+        item_of(d, i0, s, it);
+        const uint32_t sb = d.seg_bytes[s];
+        const uint32_t stride = sb * (uint32_t)nks;
+        const int rpi = d.rpi[s];
+        const int rows = d.seg[s].rows;
+        const uint8_t *w0, *w1 = nullptr;
+        int n0, n1 = 0, off1 = 0;
+        if (d.pair) {
+            const int h = rpi >> 1, g0 = it * h;
+            n0 = n1 = min(h, rows - g0);
+            w0 = d.seg[0].w + (size_t)g0 * stride;
+            w1 = d.seg[1].w + (size_t)g0 * stride;
+            off1 = h * (int)sb;
+        } else {
+            const int r0 = it * rpi;
+            n0 = min(rpi, rows - r0);
+            w0 = d.seg[s].w + (size_t)r0 * stride;
+        }
+        for (int ks = 0; ks < nks; ++ks) {
+            const unsigned pos = (unsigned)lane * ring.depth + tr.d;
+            mbar_wait(&ring.empty[pos], tr.par ^ 1u);
+            uint8_t* dst = ring.slots + (size_t)pos * ring.slot_bytes;
+            uint64_t* bar = &ring.full[pos];
+            mbar_expect_tx(bar, (uint32_t)(n0 + n1) * sb);
+            if (nks == 1) {          // rows are contiguous in HBM: one bulk copy per matrix
+                tma_load_1d(dst, w0, (uint32_t)n0 * sb, bar);
+                if (n1) tma_load_1d(dst + off1, w1, (uint32_t)n1 * sb, bar);
+            } else {
+                const size_t ko = (size_t)ks * sb;
+                for (int j = 0; j < n0; ++j) tma_load_1d(dst + j * sb, w0 + (size_t)j * stride + ko, sb, bar);
+                for (int j = 0; j < n1; ++j) tma_load_1d(dst + off1 + j * sb, w1 + (size_t)j * stride + ko, sb, bar);
+            }
+            tr.advance(ring.depth);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// consumer prologue: x -> (RMSNorm) -> int8 planes in smem.  All NW*32 consumer threads call it (named barrier 1).
 // ---------------------------------------------------------------------------------------------------
 // Returns the scalar every row sum of this phase must be multiplied by: 1, or the RMSNorm factor
 // rstd = 1/sqrt(mean(x^2)+eps).  The fixed-point integers v = rint(x*w / amax_blk(x*w) * RANGE) do not depend on
@@ -95,7 +167,7 @@ __device__ __forceinline__ void gemv_produce(const GemvParams& p, Ring& ring, in
 template <int ABITS, int NW>
 __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid) {
     constexpr int NT = NW * 32;
-    constexpr int NB = 8;                  // float4 loads in flight per thread (one L2 round trip per batch)
+    constexpr int NB = 4;                  // float4 loads in flight per thread (one L2 round trip per batch)
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -124,7 +196,7 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
                 const int f = f0 + i * NT;
-                if (f < nf) wv[i] = w4[f];
+                if (f < nf) wv[i] = __ldg(w4 + f);
             }
         }
 #pragma unroll
@@ -173,7 +245,6 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
         for (int w = 0; w < NW; ++w) tot += red[w];
         scale = 1.0f / sqrtf(tot / (float)K + p.eps);
     }
-
     // NOTE: the planes (and red[]) are rewritten only by the NEXT prologue, which every caller separates from this
     // point by a CTA-wide barrier (end of kernel, or the grid barrier of the persistent kernel).
     return scale;
@@ -195,158 +266,131 @@ __device__ __forceinline__ float warp_sum4(const float* o, int lane) {
     k += __shfl_xor_sync(0xffffffffu, k, 1);
     return k;
 }
+// two partials, 5 shuffles: lanes 0-15 -> row 0, 16-31 -> row 1
+__device__ __forceinline__ float warp_sum2(const float* o, int lane) {
+    const bool b4 = lane & 16;
+    float k = b4 ? o[1] : o[0];
+    const float snd = b4 ? o[0] : o[1];
+    k += __shfl_xor_sync(0xffffffffu, snd, 16);
+    k += __shfl_xor_sync(0xffffffffu, k, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
 
-struct EpiCtx {      // per-kernel constants of the QKV epilogue, loaded once
+struct EpiCtx {      // per-phase constants of the QKV epilogue, loaded once
     int pos;
     int page;
 };
 
-// lane-0 epilogue of one item (1 or 2 rows)
-__device__ __forceinline__ void gemv_epilogue_item(const GemvParams& p, int seg, int r, float v0, float v1, float pre0, float pre1,
-                                                   const EpiCtx& ec) {
+// ---------------------------------------------------------------------------------------------------
+// one item of TYPE with R rows: all its K-segments, reduction, epilogue.  Warp-private.
+// ---------------------------------------------------------------------------------------------------
+template <int ABITS, int TYPE, int R>
+__device__ __forceinline__ void consume_item(const GemvParams& p, const Ring& ring, Track& tr, int warp, int s, int it, uint8_t* smem,
+                                             int lane, float scale, const EpiCtx& ec) {
+    const ProdDesc& d = p.pd;
+    const int K = p.cols;
+    const int nks = d.nks, n = 2 * d.seg_nb;
+    const int sb = d.seg_bytes[s];
+    const int rows = d.seg[s].rows;
+    const bool pair = d.pair != 0;
+    const bool rope = (p.epi == EPI_QKV && s < 2);
+    constexpr int LPR = 32 / R;                 // lanes per row after the reduction (8 or 16)
+    const int j = lane / LPR;                   // local row this lane reports
+    // rows of the item and the epilogue's operands (requested before the dot products)
+    const int h = R / 2;
+    const int base_row = pair ? it * h : it * R;
+    const int my_row = base_row + (pair ? (j % h) : j);
+    bool my_ok = (lane % LPR) == 0 && my_row < rows;
+    if (pair) my_ok = my_ok && j < h;
+    else if (rope) my_ok = my_ok && (j & 1) == 0;
+    float pre0 = 0.f, pre1 = 0.f;
+    if (my_ok) {
+        if (p.epi == EPI_ADD) pre0 = __ldcg(p.resid + my_row);
+        else if (rope) {
+            const int d2 = (my_row % p.head_dim) >> 1;
+            pre0 = __ldg(p.rope_cos + (size_t)ec.pos * (p.head_dim / 2) + d2);
+            pre1 = __ldg(p.rope_sin + (size_t)ec.pos * (p.head_dim / 2) + d2);
+        }
+    }
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    const uint8_t* xhi = smem + SM_X;
+    const float* sx_arr = reinterpret_cast<const float*>(xhi + 2 * K);
+    const bool valid = lane < n;
+    for (int ks = 0; ks < nks; ++ks) {
+        const unsigned pos = (unsigned)warp * ring.depth + tr.d, par = tr.par;
+        tr.advance(ring.depth);
+        const uint8_t* slot = ring.slots + (size_t)pos * ring.slot_bytes;
+        XPlanes xp;
+        {
+            const int ug = ks * n + (valid ? lane : 0);
+            xp.hi = xhi + ug * 128;
+            xp.lo = xhi + K + ug * 128;
+            xp.sx = sx_arr + 4 * ug;
+            xp.sm = sx_arr + K / 32 + 4 * ug;
+            xp.s16 = reinterpret_cast<const int*>(sx_arr + 2 * (K / 32)) + 8 * ug;
+            xp.sw = ug & 7;
+        }
+        mbar_wait(&ring.full[pos], par);
+        if (valid) {
+            if (TYPE == T_Q4_K) item_dot_q4k<ABITS, R>(slot, sb, lane, xp, acc);
+            else if (TYPE == T_Q6_K) item_dot_q6k<ABITS, R>(slot, sb, n, lane, xp, acc);
+            else item_dot_q80<ABITS, R>(slot, sb, n, lane, xp, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[pos]);      // this warp was the slot's only reader
+    }
+    const float tot = (R == 4) ? warp_sum4(acc, lane) : warp_sum2(acc, lane);
+    // partner row of a pair: adjacent row (RoPE) or the up row (gate/up, h local rows further)
+    const float other = __shfl_xor_sync(0xffffffffu, tot, pair ? h * LPR : LPR);
+    if (!my_ok) return;
+    const float v0 = tot * scale, v1 = other * scale;      // RMSNorm factor of the fused prologue (1 if none)
     if (p.epi == EPI_STORE) {
-        p.out[r] = v0;
+        p.out[my_row] = v0;
     } else if (p.epi == EPI_ADD) {
-        p.out[r] = pre0 + v0;
+        p.out[my_row] = pre0 + v0;
     } else if (p.epi == EPI_SILU) {
-        p.out[r] = (v0 / (1.0f + expf(-v0))) * v1;
+        p.out[my_row] = (v0 / (1.0f + expf(-v0))) * v1;
     } else {   // EPI_QKV
-        if (seg < 2) {
-            const int d = r % p.head_dim;
+        const int kvh = my_row / p.head_dim, dd = my_row % p.head_dim;
+        const size_t off = (((size_t)ec.page * p.n_kv_heads + kvh) * KV_PAGE_TOKENS + (ec.pos % KV_PAGE_TOKENS)) * p.head_dim + dd;
+        if (s < 2) {
             const float o0 = v0 * pre0 - v1 * pre1, o1 = v0 * pre1 + v1 * pre0;      // pre0 = cos, pre1 = sin
-            if (seg == 0) {
-                *reinterpret_cast<float2*>(p.out + r) = make_float2(o0, o1);
-            } else {
-                const int kvh = r / p.head_dim;
-                const size_t off = (((size_t)ec.page * p.n_kv_heads + kvh) * KV_PAGE_TOKENS + (ec.pos % KV_PAGE_TOKENS)) * p.head_dim + d;
-                *reinterpret_cast<__half2*>(p.k_cache + off) = __floats2half2_rn(o0, o1);
-            }
+            if (s == 0) *reinterpret_cast<float2*>(p.out + my_row) = make_float2(o0, o1);
+            else *reinterpret_cast<__half2*>(p.k_cache + off) = __floats2half2_rn(o0, o1);
         } else {
-            const int kvh = r / p.head_dim, d = r % p.head_dim;
-            const size_t off = (((size_t)ec.page * p.n_kv_heads + kvh) * KV_PAGE_TOKENS + (ec.pos % KV_PAGE_TOKENS)) * p.head_dim + d;
             p.v_cache[off] = __float2half_rn(v0);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// consumer main loop over this CTA's stages.  All consumer warps call it.
-//
-// A warp works on a QUAD of rows per iteration (quad_dot_* in rowdot.h): activations come from the shared-memory
-// planes, each x word is reused for four weight rows, 16 independent dp4a chains per lane.  After the 6-shuffle
-// reduction lane 8*r holds row r of the quad and runs that row's epilogue (operands prefetched before the dots).
-// Quad composition per epilogue kind:
-//   STORE / ADD / V rows : rows 4q .. 4q+3 of the stage
-//   RoPE pairs (q, k)    : same (pairs (0,1) and (2,3) are adjacent rows)
-//   gate/up (SiLU*mul)   : gate rows 2q, 2q+1 and the matching up rows (stage holds n gate rows, then n up rows)
+// consumer main loop over this CTA's items.  All consumer warps call it; tr is the warp's position in its track.
 // ---------------------------------------------------------------------------------------------------
-template <int ABITS, int NW>
-__device__ __forceinline__ void gemv_consume(const GemvParams& p, Ring& ring, uint8_t* smem, int tid, float scale, int cta, int n_ctas) {
-    const int K = p.cols;
+template <int ABITS>
+__device__ __forceinline__ void gemv_consume(const GemvParams& p, const Ring& ring, Track& tr, uint8_t* smem, int tid, float scale, int cta,
+                                             int n_ctas) {
+    const ProdDesc& d = p.pd;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nu = K / UNIT_COLS;
-    const int wpr = warps_per_row(K);
-    const int ngrp = NW / wpr;               // row groups working in parallel (warps beyond ngrp*wpr only hand stages back)
-    const int grp = warp / wpr, wsub = warp % wpr;
-    const int u = wsub * 32 + lane;
-    const bool valid = u < nu;
-    const bool in_grp = grp < ngrp;
-    float* res = reinterpret_cast<float*>(smem + SM_RES);
-    const int gran = (p.epi == EPI_QKV) ? 2 : 1;
-    const int nwork = p.pair ? 1 : p.nseg;
-
-    XPlanes xp;
-    {
-        uint8_t* xhi = smem + SM_X;
-        const int uu = valid ? u : 0;
-        xp.hi = xhi + uu * 128;
-        xp.lo = xhi + K + uu * 128;
-        const float* sx_arr = reinterpret_cast<const float*>(xhi + 2 * K);
-        xp.sx = sx_arr + 4 * uu;
-        xp.sm = sx_arr + K / 32 + 4 * uu;
-        xp.s16 = reinterpret_cast<const int*>(sx_arr + 2 * (K / 32)) + 8 * uu;
-        xp.sw = uu & 7;
-    }
+    const WorkRange wr = cta_range(total_items(d), cta, n_ctas);
+    const int A = (int)ring.n_tracks;
+    if (warp >= A) return;
     EpiCtx ec{0, 0};
     if (p.epi == EPI_QKV) {
         ec.pos = __ldcg(&p.st->pos);
         ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
     }
-    const int myrow = lane >> 3;             // row of the quad this lane reports after the reduction
-    const bool epi_lane = (lane & 7) == 0 && wsub == 0;
-    int buf = 0;
-    for (int s = 0; s < nwork; ++s) {
-        const GemvSeg sg = p.seg[s];
-        const WorkRange wr = cta_range(sg.rows, gran, cta, n_ctas);
-        const bool pair_adj = (p.epi == EPI_QKV && s < 2);
-        const bool pair_gu = p.pair != 0;
-        for (int r0 = wr.a; r0 < wr.b; r0 += sg.rows_per_stage) {
-            const int n = min(sg.rows_per_stage, wr.b - r0);
-            const int nq = pair_gu ? (n + 1) / 2 : (n + 3) / 4;
-            const uint8_t* base = ring.slot();
-            mbar_wait(&ring.full[ring.st], ring.ph);
-            for (int qi = in_grp ? grp : nq; qi < nq; qi += ngrp) {
-                // stage-local rows of the quad (clamped: a ragged quad repeats its last row and ignores the result)
-                int lr[4];
-                if (pair_gu) {
-                    const int g0 = 2 * qi, g1 = min(2 * qi + 1, n - 1);
-                    lr[0] = g0; lr[1] = g1; lr[2] = n + g0; lr[3] = n + g1;
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) lr[r] = min(4 * qi + r, n - 1);
-                }
-                // this lane's row for the epilogue
-                const int my_local = pair_gu ? (2 * qi + (myrow & 1)) : (4 * qi + myrow);
-                const bool my_ok = epi_lane && my_local < n && (pair_gu ? myrow < 2 : (pair_adj ? (myrow & 1) == 0 : true));
-                const int grow = r0 + my_local;                 // global row (gate row for gate/up)
-                float pre0 = 0.f, pre1 = 0.f;
-                if (my_ok) {
-                    if (p.epi == EPI_ADD) pre0 = __ldcg(p.resid + grow);
-                    else if (pair_adj) {
-                        const int d2 = (grow % p.head_dim) >> 1;
-                        pre0 = p.rope_cos[(size_t)ec.pos * (p.head_dim / 2) + d2];
-                        pre1 = p.rope_sin[(size_t)ec.pos * (p.head_dim / 2) + d2];
-                    }
-                }
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-                if (valid) {
-                    const uint8_t* rp[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) rp[r] = base + (size_t)lr[r] * sg.row_stride;
-                    if (sg.type == T_Q4_K) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) rp[r] += (size_t)(u >> 1) * 144;
-                        quad_dot_q4k<ABITS>(rp, u & 1, xp, o);
-                    } else if (sg.type == T_Q6_K) {
-                        quad_dot_q6k<ABITS>(rp, K >> 8, u, xp, o);
-                    } else {
-                        quad_dot_q80<ABITS>(rp, K, u, xp, o);
-                    }
-                }
-                float tot = warp_sum4(o, lane);
-                if (wpr > 1) {
-                    // K > 4096: wpr warps share the rows; their partials meet in shared memory
-                    float* rbuf = res + buf * 256 + grp * 4 * wpr;
-                    if ((lane & 7) == 0) rbuf[myrow * wpr + wsub] = tot;
-                    named_bar_sync(2 + grp, 32 * wpr);
-                    if (wsub == 0) {
-                        float t = 0.f;
-                        for (int j = 0; j < wpr; ++j) t += rbuf[myrow * wpr + j];
-                        tot = t;
-                    }
-                    buf ^= 1;     // double buffer: the next quad's partials never race the readers of this one
-                }
-                // partner row of a pair: adjacent row (RoPE) or the up row (gate/up)
-                const float other = __shfl_xor_sync(0xffffffffu, tot, pair_gu ? 16 : 8);
-                if (my_ok) {
-                    const float v0 = tot * scale, v1 = other * scale;      // RMSNorm factor of the fused prologue (1 if none)
-                    gemv_epilogue_item(p, s, grow, v0, v1, pre0, pre1, ec);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.empty[ring.st]);      // this warp is done with the stage's bytes
-            ring.advance();
-        }
+    for (int i0 = wr.a + warp; i0 < wr.b; i0 += A) {
+        int s, it;
+        item_of(d, i0, s, it);
+        const int type = d.type[s];      // rows per item follow from the type (gemv_plan): Q4_K 4, Q6_K / Q8_0 2
+        if (type == T_Q4_K) consume_item<ABITS, T_Q4_K, 4>(p, ring, tr, warp, s, it, smem, lane, scale, ec);
+        else if (type == T_Q6_K) consume_item<ABITS, T_Q6_K, 2>(p, ring, tr, warp, s, it, smem, lane, scale, ec);
+        else consume_item<ABITS, T_Q8_0, 2>(p, ring, tr, warp, s, it, smem, lane, scale, ec);
     }
 }
 

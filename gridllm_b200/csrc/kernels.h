@@ -12,7 +12,8 @@ struct StepState;
 
 // consumer warps per CTA: a launch-time choice among the compiled variants {8, 12, 16}
 inline int gemv_threads(int consumer_warps) { return (consumer_warps + 1) * 32; }
-constexpr int GEMV_MAX_STAGES = 8;
+constexpr int RING_MAX_SLOTS = 24;
+constexpr int GEMV_MIN_SLOT_BYTES = 9216;   // four Q4_K row segments of 16 blocks
 constexpr int KV_PAGE_TOKENS = 16;
 
 enum GemvEpilogue : int {
@@ -22,19 +23,28 @@ enum GemvEpilogue : int {
     EPI_SILU = 3,    // pair mode: out[r] = silu(gate[r]) * up[r]
 };
 
-struct GemvSeg {
-    const uint8_t* w;      // engine row layout (rowdot.h), row stride = row_stride bytes
-    int type;              // ggml type id
+// Geometry of one GEMV phase: what the producer lane needs to stream it and the consumers need to walk it
+// (gemv_core.cuh).  64 bytes, so that the persistent kernel can keep one per phase in its parameter constant bank.
+struct ProdSeg {
+    const uint8_t* w;      // engine row layout (rowdot.h); row stride = nks * seg_bytes
     int rows;
-    int row_stride;
-    int rows_per_stage;    // host-chosen: multiple of rows-per-pass where possible
+    int n_items;           // ceil(rows / rows-per-item)   (pair mode: gate rows / (rpi/2))
 };
+struct alignas(16) ProdDesc {
+    ProdSeg seg[3];
+    unsigned short seg_bytes[3];   // bytes of one K-segment of one row
+    unsigned char rpi[3];          // rows per item (4 or 2); pair mode: rpi/2 gate rows + rpi/2 up rows
+    unsigned char type[3];         // ggml type id
+    unsigned char nseg;
+    unsigned char pair;            // 1: seg[0] / seg[1] are gate / up, staged together, EPI_SILU
+    unsigned char nks;             // K-segments per row
+    unsigned char seg_nb;          // 256-column blocks per K-segment (<= 16)
+};
+static_assert(sizeof(ProdDesc) == 64, "ProdDesc must stay 64 bytes");
 
 struct GemvParams {
-    GemvSeg seg[3];
-    int nseg;
-    int pair;              // 1: seg[0] / seg[1] are gate / up, staged together, EPI_SILU
-    int cols;              // K, multiple of 128, <= 32768
+    ProdDesc pd;           // filled by gemv_plan()
+    int cols;              // K, multiple of 256, <= 32768
     const float* x;        // [cols] fp32 activations (produced by the previous kernel)
     const float* norm_w;   // fused RMSNorm prologue when non-null
     float eps;
@@ -50,18 +60,23 @@ struct GemvParams {
     __half* v_cache;
     const int* page_table; // logical page -> physical page
     const StepState* st;   // position (EPI_QKV) / done flag
-    // staging
-    int n_stages;
-    int stage_bytes;
+    // ring (stand-alone kernel; the persistent kernel has one ring for all phases)
+    int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
+    int depth;
+    int slot_bytes;
 };
 
+// a weight matrix as the planner sees it
+struct GemvMat { const uint8_t* w; int type; int rows; };
+
 // host helpers
-size_t gemv_smem_bytes(int cols, int n_stages, int stage_bytes);
-// fills seg[i].rows_per_stage; returns false if the shape is outside the kernel's envelope
-bool gemv_plan(GemvParams& p, int consumer_warps);
+size_t gemv_smem_bytes(int cols, int n_slots, int slot_bytes);
+// Fills p.pd (K-segmentation, rows per item, item counts) for nmat matrices sharing cols; slot_bytes is the ring's
+// slot size the items must fit.  Returns false if the shape is outside the kernel's envelope.
+bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int slot_bytes);
 cudaError_t gemv_configure();   // opt-in to large dynamic shared memory (once per process)
-cudaError_t gemv_launch(const GemvParams& p, int abits, int consumer_warps, int n_ctas, int ctas_per_sm, bool pdl, cudaStream_t s);
-// (abits, consumer_warps) combinations that are compiled: (16,8) (16,12) (8,8) (8,16)
+cudaError_t gemv_launch(const GemvParams& p, int abits, int consumer_warps, int n_ctas, bool pdl, cudaStream_t s);
+// (abits, consumer_warps) combinations that are compiled: abits in {16, 8} x warps in {8, 12, 16}
 bool gemv_variant_ok(int abits, int consumer_warps);
 
 // plain fp weights (F32/F16/BF16): y = W x, fp32 accumulate, no fusion

@@ -32,34 +32,9 @@ __device__ __forceinline__ float dequant_engine(const uint8_t* row, int type, in
         case T_F32: return reinterpret_cast<const float*>(row)[c];
         case T_F16: return __half2float(reinterpret_cast<const __half*>(row)[c]);
         case T_BF16: return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(row)[c] << 16);
-        case T_Q4_K: {
-            const uint8_t* b = row + (size_t)(c >> 8) * 144;
-            const int e = c & 255, sub = e >> 5, l = e & 31;
-            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b));
-            const float dmin = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 2));
-            const uint8_t* sc = b + 4;
-            int s, m;
-            if (sub < 4) { s = sc[sub] & 63; m = sc[4 + sub] & 63; }
-            else { s = (sc[4 + sub] & 0xF) | ((sc[sub - 4] >> 6) << 4); m = (sc[4 + sub] >> 4) | ((sc[sub] >> 6) << 4); }
-            const uint8_t qb = b[16 + (sub >> 1) * 32 + l];
-            const int q = (sub & 1) ? (qb >> 4) : (qb & 0xF);
-            return d * (float)s * (float)q - dmin * (float)m;
-        }
-        case T_Q6_K: {   // Q6_K-T
-            const int nb = cols >> 8, nu = 2 * nb;
-            const int b = c >> 8, e = c & 255, h = e >> 7, r = e & 127, u = 2 * b + h;
-            const int i = r & 63, s = r >> 6, j = r & 31, t = r >> 5;
-            const int qlv = (row[((size_t)(i >> 4) * nu + u) * 16 + (i & 15)] >> (4 * s)) & 0xF;
-            const int qhv = (row[(size_t)nb * 128 + ((size_t)(j >> 4) * nu + u) * 16 + (j & 15)] >> (2 * t)) & 3;
-            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(row + (size_t)nb * 208 + 2 * b));
-            const float sc = (float)(int8_t)row[(size_t)nb * 192 + (size_t)u * 8 + (r >> 4)];
-            return d * sc * (float)((qlv | (qhv << 4)) - 32);
-        }
-        case T_Q8_0: {   // Q8_0-T
-            const int nu = cols >> 7, u = c >> 7, w = c & 127;
-            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(row + (size_t)cols + (size_t)u * 8 + 2 * (w >> 5)));
-            return d * (float)(int8_t)row[((size_t)(w >> 4) * nu + u) * 16 + (w & 15)];
-        }
+        case T_Q4_K:
+        case T_Q6_K:
+        case T_Q8_0: return dequant_engine_quant(row, type, cols, c);
         default: return 0.f;
     }
 }

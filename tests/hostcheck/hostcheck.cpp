@@ -9,145 +9,121 @@
 
 using namespace gl;
 
+// activation planes exactly as the GPU prologue lays them out: hi [cols], lo [cols] (16-B chunk j of unit u at
+// physical chunk j ^ (u & 7)), sx / sm [cols/32], s16 [cols/16]
 template <int AB>
-static void build_xunits(const float* x, int cols, std::vector<XUnit>& xs) {
-    int nu = cols / UNIT_COLS;
-    xs.resize(nu);
-    for (int u = 0; u < nu; ++u) {
-        XUnit& xu = xs[u];
-        for (int b = 0; b < 4; ++b) {
-            const float* xb = x + u * 128 + b * 32;
-            float amax = 0.f;
-            for (int i = 0; i < 32; ++i) amax = std::fmax(amax, std::fabs(xb[i]));
-            int s0, s1;
-            snap16<AB>(xb, amax, &xu.hi[8 * b], &xu.lo[8 * b], &s0);
-            snap16<AB>(xb + 16, amax, &xu.hi[8 * b + 4], &xu.lo[8 * b + 4], &s1);
-            xu.sx[b] = amax / (AB == 16 ? ACT16_RANGE : ACT8_RANGE);
-            xu.sm[b] = xu.sx[b] * (float)(s0 + s1);
-            xu.s16[2 * b] = s0;
-            xu.s16[2 * b + 1] = s1;
+struct Planes {
+    std::vector<uint8_t> raw;
+    std::vector<float> sxv, smv;
+    std::vector<int> s16v;
+    uint8_t *hi, *lo;
+    float *sx, *sm;
+    int* s16;
+    Planes(const float* x, int cols) : raw(2 * (size_t)cols + 64), sxv(cols / 32 + 8), smv(cols / 32 + 8), s16v(cols / 16 + 8) {
+        hi = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+        lo = hi + cols;
+        sx = sxv.data() + ((16 - ((uintptr_t)sxv.data() & 15)) & 15) / 4;
+        sm = smv.data() + ((16 - ((uintptr_t)smv.data() & 15)) & 15) / 4;
+        s16 = s16v.data() + ((16 - ((uintptr_t)s16v.data() & 15)) & 15) / 4;
+        for (int u = 0; u < cols / UNIT_COLS; ++u) {
+            for (int b = 0; b < 4; ++b) {
+                const float* xb = x + u * 128 + b * 32;
+                float amax = 0.f;
+                for (int i = 0; i < 32; ++i) amax = std::fmax(amax, std::fabs(xb[i]));
+                uint32_t h[8], l[8];
+                int s0, s1;
+                snap16<AB>(xb, amax, h, l, &s0);
+                snap16<AB>(xb + 16, amax, h + 4, l + 4, &s1);
+                for (int v = 0; v < 2; ++v) {
+                    const int j = 2 * b + v;
+                    memcpy(hi + (size_t)u * 128 + ((j ^ (u & 7)) << 4), h + 4 * v, 16);
+                    memcpy(lo + (size_t)u * 128 + ((j ^ (u & 7)) << 4), l + 4 * v, 16);
+                }
+                sx[4 * u + b] = amax / (AB == 16 ? ACT16_RANGE : ACT8_RANGE);
+                sm[4 * u + b] = sx[4 * u + b] * (float)(s0 + s1);
+                s16[8 * u + 2 * b] = s0;
+                s16[8 * u + 2 * b + 1] = s1;
+            }
         }
     }
+};
+
+static void to_engine_row(int type, const uint8_t* src, uint8_t* dst, int cols) {
+    if (type == T_Q4_K) memcpy(dst, src, row_bytes(type, cols));
+    else if (type == T_Q6_K) repack_row_q6k(src, dst, cols);
+    else repack_row_q80(src, dst, cols);
 }
 
-// rows taken two at a time through the lock-step functions the GPU consumer uses for row pairs
-template <int AB>
-static int run_pairs(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
-    std::vector<XUnit> xs;
-    build_xunits<AB>(x, cols, xs);
-    int nu = cols / UNIT_COLS;
-    size_t rb = row_bytes(type, cols), rs = align16(rb);
-    std::vector<uint8_t> buf(2 * rs + 16);
-    uint8_t* r0 = buf.data() + ((16 - ((uintptr_t)buf.data() & 15)) & 15);
-    uint8_t* r1 = r0 + rs;
-    for (int i = 0; i + 1 < rows; i += 2) {
-        float acc0 = 0.f, acc1 = 0.f;
-        if (type == T_Q4_K) {
-            memcpy(r0, w + (size_t)i * rb, rb); memcpy(r1, w + (size_t)(i + 1) * rb, rb);
-            for (int u = 0; u < nu; ++u) { float a, b; unit_dot2_q4k<AB>(r0 + (size_t)(u >> 1) * 144, r1 + (size_t)(u >> 1) * 144, u & 1, xs[u], a, b); acc0 += a; acc1 += b; }
-        } else if (type == T_Q6_K) {
-            repack_row_q6k(w + (size_t)i * rb, r0, cols / 256); repack_row_q6k(w + (size_t)(i + 1) * rb, r1, cols / 256);
-            for (int u = 0; u < nu; ++u) { float a, b; unit_dot2_q6k<AB>(r0, r1, cols / 256, u, xs[u], a, b); acc0 += a; acc1 += b; }
-        } else return -1;
-        y[i] = acc0; y[i + 1] = acc1;
+// The consumer loop of gemv_core.cuh on the host: items of R rows, K-segment by K-segment, a "slot" holding the R
+// row segments back to back, lane l = unit l of the segment.
+template <int AB, int R>
+static int run_items(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
+    const KSplit ks = ksplit(cols);
+    if (!ks.nks) return -2;
+    Planes<AB> pl(x, cols);
+    const int n = 2 * ks.seg_nb, sb = kseg_bytes(type, ks.seg_nb);
+    const size_t rb = row_bytes(type, cols), rs = (size_t)engine_row_stride(type, cols);
+    std::vector<uint8_t> rowbuf(rs + 16), slotbuf((size_t)R * sb + 16);
+    uint8_t* er = rowbuf.data() + ((16 - ((uintptr_t)rowbuf.data() & 15)) & 15);
+    uint8_t* slot = slotbuf.data() + ((16 - ((uintptr_t)slotbuf.data() & 15)) & 15);
+    std::vector<uint8_t> erows((size_t)R * rs);
+    for (int i = 0; i < rows; i += R) {
+        const int nv = rows - i < R ? rows - i : R;
+        for (int r = 0; r < nv; ++r) { to_engine_row(type, w + (size_t)(i + r) * rb, er, cols); memcpy(erows.data() + (size_t)r * rs, er, rs); }
+        float acc[R];
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        for (int k = 0; k < ks.nks; ++k) {
+            memset(slot, 0xA5, (size_t)R * sb);                           // rows beyond the ragged end hold garbage on the GPU too
+            for (int r = 0; r < nv; ++r) memcpy(slot + (size_t)r * sb, erows.data() + (size_t)r * rs + (size_t)k * sb, sb);
+            for (int l = 0; l < n; ++l) {
+                const int ug = k * n + l;
+                XPlanes xp{pl.hi + (size_t)ug * 128, pl.lo + (size_t)ug * 128, pl.sx + 4 * ug, pl.sm + 4 * ug, pl.s16 + 8 * ug, ug & 7};
+                float part[R];
+                for (int r = 0; r < R; ++r) part[r] = 0.f;
+                if (type == T_Q4_K) item_dot_q4k<AB, R>(slot, sb, l, xp, part);
+                else if (type == T_Q6_K) item_dot_q6k<AB, R>(slot, sb, n, l, xp, part);
+                else item_dot_q80<AB, R>(slot, sb, n, l, xp, part);
+                for (int r = 0; r < R; ++r) acc[r] += part[r];
+            }
+        }
+        for (int r = 0; r < nv; ++r) y[i + r] = acc[r];
     }
     return 0;
 }
 
-template <int AB>
-static int run(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
-    std::vector<XUnit> xs;
-    build_xunits<AB>(x, cols, xs);
-    int nu = cols / UNIT_COLS;
-    size_t rb = row_bytes(type, cols), rs = align16(rb);
-    std::vector<uint8_t> row(rs + 16);
-    uint8_t* r = row.data() + ((16 - ((uintptr_t)row.data() & 15)) & 15);
-    for (int i = 0; i < rows; ++i) {
-        const uint8_t* src = w + (size_t)i * rb;
-        float acc = 0.f;
-        if (type == T_Q4_K) {
-            memcpy(r, src, rb);
-            for (int u = 0; u < nu; ++u) acc += unit_dot_q4k<AB>(r + (size_t)(u >> 1) * 144, u & 1, xs[u]);
-        } else if (type == T_Q6_K) {
-            repack_row_q6k(src, r, cols / 256);
-            for (int u = 0; u < nu; ++u) acc += unit_dot_q6k<AB>(r, cols / 256, u, xs[u]);
-        } else if (type == T_Q8_0) {
-            repack_row_q80(src, r, cols);
-            for (int u = 0; u < nu; ++u) acc += unit_dot_q80<AB>(r, cols, u, xs[u]);
-        } else return -1;
-        y[i] = acc;
+// rows per item: 0 = what gemv_plan picks for the type (Q4_K 4, Q6_K / Q8_0 2); else 1, 2 or 4
+extern "C" int hc_gemv_r(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits, int rpi) {
+    if (type != T_Q4_K && type != T_Q6_K && type != T_Q8_0) return -1;
+    if (!rpi) rpi = type == T_Q4_K ? 4 : 2;
+    if (abits == 16) {
+        if (rpi == 4) return run_items<16, 4>(type, w, rows, cols, x, y);
+        if (rpi == 2) return run_items<16, 2>(type, w, rows, cols, x, y);
+        return run_items<16, 1>(type, w, rows, cols, x, y);
     }
-    return 0;
+    if (rpi == 4) return run_items<8, 4>(type, w, rows, cols, x, y);
+    if (rpi == 2) return run_items<8, 2>(type, w, rows, cols, x, y);
+    return run_items<8, 1>(type, w, rows, cols, x, y);
 }
-
-// rows taken four at a time through the quad functions, x read from swizzled planes exactly as the GPU prologue lays them out
-template <int AB>
-static int run_quads(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
-    std::vector<XUnit> xs;
-    build_xunits<AB>(x, cols, xs);
-    const int nu = cols / UNIT_COLS;
-    // planes: hi [cols], lo [cols] (16-B chunk j of unit u at physical chunk j ^ (u & 7)), sx / sm [cols/32], s16 [cols/16]
-    std::vector<uint8_t> raw(2 * (size_t)cols + 64);
-    uint8_t* hi = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
-    uint8_t* lo = hi + cols;
-    std::vector<float> sx(cols / 32 + 4), sm(cols / 32 + 4);
-    std::vector<int> s16(cols / 16 + 4);
-    float* sxp = sx.data() + ((16 - ((uintptr_t)sx.data() & 15)) & 15) / 4;
-    float* smp = sm.data() + ((16 - ((uintptr_t)sm.data() & 15)) & 15) / 4;
-    int* s16p = s16.data() + ((16 - ((uintptr_t)s16.data() & 15)) & 15) / 4;
-    for (int u = 0; u < nu; ++u) {
-        for (int j = 0; j < 8; ++j) {
-            memcpy(hi + (size_t)u * 128 + ((j ^ (u & 7)) << 4), &xs[u].hi[4 * j], 16);
-            memcpy(lo + (size_t)u * 128 + ((j ^ (u & 7)) << 4), &xs[u].lo[4 * j], 16);
-        }
-        for (int b = 0; b < 4; ++b) { sxp[4 * u + b] = xs[u].sx[b]; smp[4 * u + b] = xs[u].sm[b]; }
-        for (int g = 0; g < 8; ++g) s16p[8 * u + g] = xs[u].s16[g];
-    }
-    size_t rb = row_bytes(type, cols), rs = align16(rb);
-    std::vector<uint8_t> buf(4 * rs + 16);
-    uint8_t* base = buf.data() + ((16 - ((uintptr_t)buf.data() & 15)) & 15);
-    for (int i = 0; i < rows; i += 4) {
-        const uint8_t* rp[4];
-        for (int r = 0; r < 4; ++r) {
-            const int ri = i + r < rows ? i + r : rows - 1;       // clamp like the GPU consumer does for ragged quads
-            uint8_t* dst = base + (size_t)r * rs;
-            if (type == T_Q4_K) memcpy(dst, w + (size_t)ri * rb, rb);
-            else if (type == T_Q6_K) repack_row_q6k(w + (size_t)ri * rb, dst, cols / 256);
-            else repack_row_q80(w + (size_t)ri * rb, dst, cols);
-            rp[r] = dst;
-        }
-        float acc[4] = {0, 0, 0, 0};
-        for (int u = 0; u < nu; ++u) {
-            XPlanes xp{hi + (size_t)u * 128, lo + (size_t)u * 128, sxp + 4 * u, smp + 4 * u, s16p + 8 * u, u & 7};
-            float o[4];
-            if (type == T_Q4_K) {
-                const uint8_t* bp[4];
-                for (int r = 0; r < 4; ++r) bp[r] = rp[r] + (size_t)(u >> 1) * 144;
-                quad_dot_q4k<AB>(bp, u & 1, xp, o);
-            } else if (type == T_Q6_K) quad_dot_q6k<AB>(rp, cols / 256, u, xp, o);
-            else quad_dot_q80<AB>(rp, cols, u, xp, o);
-            for (int r = 0; r < 4; ++r) acc[r] += o[r];
-        }
-        for (int r = 0; r < 4 && i + r < rows; ++r) y[i + r] = acc[r];
-    }
-    return 0;
-}
-
-extern "C" int hc_gemv_quads(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
-    if (cols % 128) return -2;
-    if ((type == T_Q4_K || type == T_Q6_K) && cols % 256) return -2;
-    return abits == 16 ? run_quads<16>(type, w, rows, cols, x, y) : run_quads<8>(type, w, rows, cols, x, y);
-}
-
-extern "C" int hc_gemv_pairs(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
-    if (cols % 256 || (rows & 1)) return -2;
-    return abits == 16 ? run_pairs<16>(type, w, rows, cols, x, y) : run_pairs<8>(type, w, rows, cols, x, y);
-}
-
 extern "C" int hc_gemv(int type, const uint8_t* w, int rows, int cols, const float* x, float* y, int abits) {
-    if (cols % 128) return -2;
-    if (type == T_Q4_K || type == T_Q6_K) { if (cols % 256) return -2; }
-    return abits == 16 ? run<16>(type, w, rows, cols, x, y) : run<8>(type, w, rows, cols, x, y);
+    return hc_gemv_r(type, w, rows, cols, x, y, abits, 0);
+}
+
+// engine row layout round trip: GGUF rows -> engine rows -> element-wise dequantisation (what the batched prefill's
+// 16-bit copy is built from)
+extern "C" int hc_dequant_engine(int type, const uint8_t* w, int rows, int cols, float* out) {
+    if (!ksplit(cols).nks) return -2;
+    const size_t rb = row_bytes(type, cols), rs = (size_t)engine_row_stride(type, cols);
+    std::vector<uint8_t> er(rs);
+    for (int i = 0; i < rows; ++i) {
+        to_engine_row(type, w + (size_t)i * rb, er.data(), cols);
+        for (int c = 0; c < cols; ++c) out[(size_t)i * cols + c] = dequant_engine_quant(er.data(), type, cols, c);
+    }
+    return 0;
+}
+extern "C" int hc_ksplit(int cols, int* nks, int* seg_nb) {
+    const KSplit k = ksplit(cols);
+    *nks = k.nks; *seg_nb = k.seg_nb;
+    return k.nks ? 0 : -1;
 }
 
 // GGUF reader check: returns number of tensors or -1; fills a few fields

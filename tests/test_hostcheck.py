@@ -48,27 +48,18 @@ def test_edge_activations(hostcheck_lib):
         assert np.allclose(y, ref, rtol=1e-5, atol=1e-30 + 1e-6 * np.abs(ref).max())
 
 
-@pytest.mark.parametrize("tname", ["Q4_K", "Q6_K"])
-def test_paired_row_functions_equal_single_row(hostcheck_lib, tname):
-    """unit_dot2_* (two rows in lock-step, what the GPU consumer runs for row pairs) == unit_dot_* bit for bit"""
-    from oracle import gguf_synth as S
-    t = {"Q4_K": S.Q4_K, "Q6_K": S.Q6_K}[tname]
-    rng = np.random.Generator(np.random.PCG64(31))
-    for cols in (256, 4096, 14336):
-        blocks = S.random_blocks(rng, t, 10, cols)
-        x = rng.standard_normal(cols).astype(np.float32)
-        for ab in (16, 8):
-            y1 = _run(hostcheck_lib, t, blocks, 10, cols, x, ab)
-            y2 = np.zeros(10, np.float32)
-            rc = hostcheck_lib.hc_gemv_pairs(t, blocks.ctypes.data_as(ctypes.c_void_p), 10, cols, x.ctypes.data_as(ctypes.c_void_p),
-                                             y2.ctypes.data_as(ctypes.c_void_p), ab)
-            assert rc == 0 and np.array_equal(y1, y2)
+def _run_r(lib, t, blocks, rows, cols, x, abits, rpi):
+    y = np.zeros(rows, np.float32)
+    rc = lib.hc_gemv_r(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, x.ctypes.data_as(ctypes.c_void_p),
+                       y.ctypes.data_as(ctypes.c_void_p), abits, rpi)
+    assert rc == 0
+    return y
 
 
 @pytest.mark.parametrize("tname", ["Q4_K", "Q6_K", "Q8_0"])
-def test_quad_row_functions_equal_single_row(hostcheck_lib, tname):
-    """quad_dot_* (four rows per lane iteration, activations read from the swizzled shared-memory planes -- the
-    production consumer loop) == unit_dot_* bit for bit, including ragged row counts"""
+def test_rows_per_item_variants_are_bit_identical(hostcheck_lib, tname):
+    """item_dot_* with 4, 2 or 1 rows per item (the GPU consumer picks 4 or 2 by type) give the same bits, including
+    ragged last items whose unused slot rows hold garbage"""
     from oracle import gguf_synth as S
     t = {"Q4_K": S.Q4_K, "Q6_K": S.Q6_K, "Q8_0": S.Q8_0}[tname]
     rng = np.random.Generator(np.random.PCG64(41))
@@ -77,8 +68,30 @@ def test_quad_row_functions_equal_single_row(hostcheck_lib, tname):
             blocks = S.random_blocks(rng, t, rows, cols)
             x = rng.standard_normal(cols).astype(np.float32)
             for ab in (16, 8):
-                y1 = _run(hostcheck_lib, t, blocks, rows, cols, x, ab)
-                y2 = np.zeros(rows, np.float32)
-                rc = hostcheck_lib.hc_gemv_quads(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, x.ctypes.data_as(ctypes.c_void_p),
-                                                 y2.ctypes.data_as(ctypes.c_void_p), ab)
-                assert rc == 0 and np.array_equal(y1, y2), (tname, cols, rows, ab)
+                y1 = _run_r(hostcheck_lib, t, blocks, rows, cols, x, ab, 1)
+                for rpi in (2, 4):
+                    y2 = _run_r(hostcheck_lib, t, blocks, rows, cols, x, ab, rpi)
+                    assert np.array_equal(y1, y2), (tname, cols, rows, ab, rpi)
+
+
+@pytest.mark.parametrize("cols,expect", [(256, (1, 1)), (768, (1, 3)), (4096, (1, 16)), (14336, (4, 14)), (8192, (2, 16)),
+                                          (28672, (7, 16)), (5632, (2, 11)), (4352, (0, 0)), (32768, (8, 16)), (300, (0, 0))])
+def test_ksplit_table(hostcheck_lib, cols, expect):
+    nks, nb = ctypes.c_int(), ctypes.c_int()
+    rc = hostcheck_lib.hc_ksplit(cols, ctypes.byref(nks), ctypes.byref(nb))
+    assert (nks.value, nb.value) == expect and (rc == 0) == (expect[0] > 0)
+
+
+@pytest.mark.parametrize("tname", ["Q4_K", "Q6_K", "Q8_0"])
+@pytest.mark.parametrize("cols", [256, 4096, 14336])
+def test_engine_layout_round_trip(hostcheck_lib, tname, cols):
+    """GGUF row -> engine row (K-segment-major transposed layouts) -> element access == gguf dequantisation, bit for bit"""
+    from oracle import gguf_synth as S, llama_oracle as O
+    t = {"Q4_K": S.Q4_K, "Q6_K": S.Q6_K, "Q8_0": S.Q8_0}[tname]
+    rng = np.random.Generator(np.random.PCG64(cols + 5))
+    rows = 3
+    blocks = S.random_blocks(rng, t, rows, cols)
+    out = np.zeros((rows, cols), np.float32)
+    rc = hostcheck_lib.hc_dequant_engine(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    assert np.array_equal(out, O.dequantize(blocks, t, (rows, cols)).astype(np.float32))

@@ -28,13 +28,13 @@ def main():
         mats[(t, r, c)] = S.random_blocks(rng, t, r, c)
     configs = [
         {},
+        {"GL_WARPS": "8"},
+        {"GL_WARPS": "8", "GL_RING_DEPTH": "3"},
+        {"GL_WARPS": "16"},
         {"GL_ACT_BITS": "8"},
-        {"GL_CTAS_PER_SM": "1"},
-        {"GL_CTAS_PER_SM": "1", "GL_STAGE_KB": "36"},
-        {"GL_STAGE_KB": "27"},
     ]
     for cfg in configs:
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_STAGE_KB", "GL_SMEM_KB", "GL_WARPS", "GL_CTAS_PER_SM"):
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_RING_DEPTH", "GL_SMEM_KB", "GL_WARPS"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         e = N.Engine(tiny)
