@@ -57,19 +57,7 @@ __device__ __forceinline__ float dequant_native_elem(const uint8_t* row, int typ
             const uint8_t* b = row + (size_t)(c >> 5) * 34;
             return half_bits_to_float(*reinterpret_cast<const uint16_t*>(b)) * (float)(int8_t)b[2 + (c & 31)];
         }
-        case T_Q4_K: {
-            const uint8_t* b = row + (size_t)(c >> 8) * 144;
-            const int e = c & 255, sub = e >> 5, l = e & 31;
-            const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b));
-            const float dmin = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 2));
-            const uint8_t* sc = b + 4;
-            int s, m;
-            if (sub < 4) { s = sc[sub] & 63; m = sc[4 + sub] & 63; }
-            else { s = (sc[4 + sub] & 0xF) | ((sc[sub - 4] >> 6) << 4); m = (sc[4 + sub] >> 4) | ((sc[sub] >> 6) << 4); }
-            const uint8_t qb = b[16 + (sub >> 1) * 32 + l];
-            const int q = (sub & 1) ? (qb >> 4) : (qb & 0xF);
-            return d * (float)s * (float)q - dmin * (float)m;
-        }
+        case T_Q4_K: return dequant_native_q4k(row, c);
         case T_Q6_K: {
             const uint8_t* b = row + (size_t)(c >> 8) * 210;
             const int e = c & 255, h = e >> 7, r = e & 127;

@@ -94,7 +94,7 @@ Status Engine::upload_f32(const GGUFTensor& t, float** out, int expect) {
     return {};
 }
 
-Status Engine::upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layout) {
+Status Engine::upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layout, bool paired) {
     BlockGeom g = block_geom(t.type);
     if (!g.weights) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': ggml type " + std::to_string(t.type) + " is outside the hot path (F32/F16/BF16/Q8_0/Q4_K/Q6_K)");
     m.type = (int)t.type;
@@ -102,36 +102,47 @@ Status Engine::upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layo
     m.cols = (int)t.cols();
     m.gguf_bytes = t.nbytes;
     const size_t rb = row_bytes(t.type, t.cols());
-    const bool repack = !native_layout && (t.type == T_Q6_K || t.type == T_Q8_0);
-    if (!native_layout && m.quantized() && !ksplit(m.cols).nks) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': cols must be a multiple of 256 (and cut into <= 8 K-segments) for the quantised GEMV");
-    m.row_stride = (int)(native_layout ? rb : (m.quantized() ? (size_t)engine_row_stride(m.type, m.cols) : align16(rb)));
-    const size_t total = (size_t)m.row_stride * m.rows;
+    const bool engine_layout = !native_layout && m.quantized();
+    if (engine_layout && !ksplit(m.cols).nks) return fail(GL_ERR_UNSUPPORTED, "tensor '" + t.name + "': cols must be a multiple of 256 (and cut into <= 8 K-segments) for the quantised GEMV");
+    size_t total;
+    if (engine_layout) {
+        // tile = the rows of one GEMV item of this matrix (half an item for the gate / up pair); rowdot.h
+        m.tile_rows = paired ? item_rows(m.type) / 2 : item_rows(m.type);
+        total = engine_matrix_bytes(m.type, m.rows, m.cols, m.tile_rows);
+        m.row_stride = 0;
+    } else {
+        m.tile_rows = 1;
+        m.row_stride = (int)(native_layout ? rb : align16(rb));
+        total = (size_t)m.row_stride * m.rows;
+    }
     CU(cudaMalloc((void**)&m.w, total + 256));
     allocs_.push_back(m.w);
-    if (!repack && (size_t)m.row_stride == rb) {
+    if (!engine_layout && (size_t)m.row_stride == rb) {
         CU(cudaMemcpy(m.w, t.data, total, cudaMemcpyHostToDevice));
-    } else {
-        // repack rows on the host (parallel over rows), in slabs through one staging buffer
-        const size_t slab_rows = std::max<size_t>(1, (size_t)(64u << 20) / m.row_stride);
-        std::vector<uint8_t> stage(slab_rows * m.row_stride);
-        for (size_t r0 = 0; r0 < (size_t)m.rows; r0 += slab_rows) {
-            const size_t nr = std::min(slab_rows, (size_t)m.rows - r0);
-            const int nthreads = (int)std::min<size_t>(8, std::max<size_t>(1, nr / 64));
-            std::vector<std::thread> th;
-            for (int ti = 0; ti < nthreads; ++ti) {
-                th.emplace_back([&, ti]() {
-                    for (size_t r = ti; r < nr; r += nthreads) {
-                        const uint8_t* src = t.data + (r0 + r) * rb;
-                        uint8_t* dst = stage.data() + r * m.row_stride;
-                        if (t.type == T_Q6_K && repack) repack_row_q6k(src, dst, m.cols);
-                        else if (t.type == T_Q8_0 && repack) repack_row_q80(src, dst, m.cols);
-                        else { memcpy(dst, src, rb); if ((size_t)m.row_stride > rb) memset(dst + rb, 0, m.row_stride - rb); }
-                    }
-                });
-            }
-            for (auto& x : th) x.join();
-            CU(cudaMemcpy(m.w + r0 * m.row_stride, stage.data(), nr * m.row_stride, cudaMemcpyHostToDevice));
+        return {};
+    }
+    // repack on the host (parallel over rows), in slabs of whole tiles through one staging buffer
+    const size_t slab_row_bytes = engine_layout ? total / ((m.rows + m.tile_rows - 1) / m.tile_rows * (size_t)m.tile_rows) : (size_t)m.row_stride;
+    size_t slab_rows = std::max<size_t>(1, (size_t)(64u << 20) / slab_row_bytes);
+    slab_rows = std::max<size_t>(m.tile_rows, slab_rows / m.tile_rows * m.tile_rows);
+    std::vector<uint8_t> stage;
+    for (size_t r0 = 0; r0 < (size_t)m.rows; r0 += slab_rows) {
+        const size_t nr = std::min(slab_rows, (size_t)m.rows - r0);
+        const size_t nr_pad = (nr + m.tile_rows - 1) / m.tile_rows * m.tile_rows;
+        stage.assign(nr_pad * slab_row_bytes, 0);
+        const int nthreads = (int)std::min<size_t>(8, std::max<size_t>(1, nr / 64));
+        std::vector<std::thread> th;
+        for (int ti = 0; ti < nthreads; ++ti) {
+            th.emplace_back([&, ti]() {
+                for (size_t r = ti; r < nr; r += nthreads) {
+                    const uint8_t* src = t.data + (r0 + r) * rb;
+                    if (engine_layout) repack_row(m.type, src, stage.data(), m.cols, m.tile_rows, (int)r);     // r0 is a tile boundary
+                    else memcpy(stage.data() + r * m.row_stride, src, rb);
+                }
+            });
         }
+        for (auto& x : th) x.join();
+        CU(cudaMemcpy(m.w + r0 * slab_row_bytes, stage.data(), stage.size(), cudaMemcpyHostToDevice));
     }
     return {};
 }
@@ -201,16 +212,16 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     for (int il = 0; il < n_layer_; ++il) {
         LayerWeights& L = layers_[il];
         const std::string p = "blk." + std::to_string(il) + ".";
-        struct Item { const char* n; DevMatrix* m; int rows, cols; };
-        Item items[] = {{"attn_q.weight", &L.wq, n_head_ * hd_, n_embd_},  {"attn_k.weight", &L.wk, n_kv_ * hd_, n_embd_},
-                        {"attn_v.weight", &L.wv, n_kv_ * hd_, n_embd_},    {"attn_output.weight", &L.wo, n_embd_, n_head_ * hd_},
-                        {"ffn_gate.weight", &L.wgate, n_ff_, n_embd_},     {"ffn_up.weight", &L.wup, n_ff_, n_embd_},
-                        {"ffn_down.weight", &L.wdown, n_embd_, n_ff_}};
+        struct Item { const char* n; DevMatrix* m; int rows, cols; bool paired; };
+        Item items[] = {{"attn_q.weight", &L.wq, n_head_ * hd_, n_embd_, false},  {"attn_k.weight", &L.wk, n_kv_ * hd_, n_embd_, false},
+                        {"attn_v.weight", &L.wv, n_kv_ * hd_, n_embd_, false},    {"attn_output.weight", &L.wo, n_embd_, n_head_ * hd_, false},
+                        {"ffn_gate.weight", &L.wgate, n_ff_, n_embd_, true},      {"ffn_up.weight", &L.wup, n_ff_, n_embd_, true},
+                        {"ffn_down.weight", &L.wdown, n_embd_, n_ff_, false}};
         for (auto& it : items) {
             const GGUFTensor* t = gguf_.tensor(p + it.n);
             if (!t) return fail(GL_ERR_FORMAT, "missing tensor " + p + it.n);
             if (t->rows() != it.rows || t->cols() != it.cols) return fail(GL_ERR_FORMAT, "tensor " + p + it.n + " has unexpected shape");
-            ST(upload_matrix(*t, *it.m, false));
+            ST(upload_matrix(*t, *it.m, false, it.paired));
             layer_bytes += t->nbytes;
             n_params_ += (uint64_t)t->rows() * t->cols();
             if (!it.m->quantized()) all_quant_ = false;
@@ -398,7 +409,7 @@ Status Engine::plain_gemv(cudaStream_t s, const DevMatrix& m, const float* x, fl
     if (m.quantized()) {
         GemvParams p{};
         p.x = x; p.epi = EPI_STORE; p.out = y; p.st = st_;
-        const GemvMat mm[1] = {{m.w, m.type, m.rows}};
+        const GemvMat mm[1] = {{m.w, m.type, m.rows, m.tile_rows}};
         return enqueue_gemv(s, p, mm, 1, false, m.cols, n_launch);
     }
     CU(gemv_fp_launch(m.w, m.type, m.rows, m.cols, x, y, s));
@@ -420,7 +431,7 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         if (fused_) {
             GemvParams p{};
-            const GemvMat qkv[3] = {{L.wq.w, L.wq.type, L.wq.rows}, {L.wk.w, L.wk.type, L.wk.rows}, {L.wv.w, L.wv.type, L.wv.rows}};
+            const GemvMat qkv[3] = {{L.wq.w, L.wq.type, L.wq.rows, L.wq.tile_rows}, {L.wk.w, L.wk.type, L.wk.rows, L.wk.tile_rows}, {L.wv.w, L.wv.type, L.wv.rows, L.wv.tile_rows}};
             p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
             p.rope_cos = rope_cos_; p.rope_sin = rope_sin_; p.head_dim = hd_; p.n_kv_heads = n_kv_;
             p.k_cache = kc; p.v_cache = vc; p.page_table = page_table_; p.st = st_;
@@ -442,16 +453,16 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
         }
         if (fused_) {
             GemvParams p{};
-            const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows}};
+            const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows, L.wo.tile_rows}};
             p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
             ST(enqueue_gemv(s, p, mo, 1, false, n_head_ * hd_, n_launch));
             GemvParams g{};
-            const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows}, {L.wup.w, L.wup.type, L.wup.rows}};
+            const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.tile_rows}, {L.wup.w, L.wup.type, L.wup.rows, L.wup.tile_rows}};
             g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
             if (L.wgate.type != L.wup.type) return fail(GL_ERR_UNSUPPORTED, "ffn_gate / ffn_up with different types");
             ST(enqueue_gemv(s, g, mgu, 2, true, n_embd_, n_launch));
             GemvParams d{};
-            const GemvMat md[1] = {{L.wdown.w, L.wdown.type, L.wdown.rows}};
+            const GemvMat md[1] = {{L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.tile_rows}};
             d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
             ST(enqueue_gemv(s, d, md, 1, false, n_ff_, n_launch));
         } else {
@@ -478,7 +489,7 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
     const bool pdl = use_pdl_;
     if (fused_) {
         GemvParams p{};
-        const GemvMat mh[1] = {{output_.w, output_.type, output_.rows}};
+        const GemvMat mh[1] = {{output_.w, output_.type, output_.rows, output_.tile_rows}};
         p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
         ST(enqueue_gemv(s, p, mh, 1, false, n_embd_, n_launch));
     } else {
@@ -569,7 +580,7 @@ Status Engine::build_mega() {
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         GemvParams p{};
-        const GemvMat qkv[3] = {{L.wq.w, L.wq.type, L.wq.rows}, {L.wk.w, L.wk.type, L.wk.rows}, {L.wv.w, L.wv.type, L.wv.rows}};
+        const GemvMat qkv[3] = {{L.wq.w, L.wq.type, L.wq.rows, L.wq.tile_rows}, {L.wk.w, L.wk.type, L.wk.rows, L.wk.tile_rows}, {L.wv.w, L.wv.type, L.wv.rows, L.wv.tile_rows}};
         p.x = x_; p.norm_w = L.attn_norm; p.eps = eps_; p.epi = EPI_QKV; p.out = q_;
         p.rope_cos = rope_cos_; p.rope_sin = rope_sin_; p.head_dim = hd_; p.n_kv_heads = n_kv_;
         p.k_cache = kc; p.v_cache = vc; p.page_table = page_table_; p.st = st_;
@@ -578,23 +589,23 @@ Status Engine::build_mega() {
         a.kind = PH_ATTN; a.g.k_cache = kc; a.g.v_cache = vc;
         ph.push_back(a);
         GemvParams o{};
-        const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows}};
+        const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows, L.wo.tile_rows}};
         o.x = attn_; o.epi = EPI_ADD; o.out = x_; o.resid = x_; o.st = st_;
         if (!add_gemv(o, mo, 1, false, n_head_ * hd_, 0)) return {};
         if (L.wgate.type != L.wup.type) return {};
         GemvParams g{};
-        const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows}, {L.wup.w, L.wup.type, L.wup.rows}};
+        const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.tile_rows}, {L.wup.w, L.wup.type, L.wup.rows, L.wup.tile_rows}};
         g.x = x_; g.norm_w = L.ffn_norm; g.eps = eps_; g.epi = EPI_SILU; g.out = h_; g.st = st_;
         if (!add_gemv(g, mgu, 2, true, n_embd_, 0)) return {};
         GemvParams d{};
-        const GemvMat md[1] = {{L.wdown.w, L.wdown.type, L.wdown.rows}};
+        const GemvMat md[1] = {{L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.tile_rows}};
         d.x = h_; d.epi = EPI_ADD; d.out = x_; d.resid = x_; d.st = st_;
         if (!add_gemv(d, md, 1, false, n_ff_, 0)) return {};
     }
     mega_n_nohead_ = (int)ph.size();
     {
         GemvParams p{};
-        const GemvMat mh[1] = {{output_.w, output_.type, output_.rows}};
+        const GemvMat mh[1] = {{output_.w, output_.type, output_.rows, output_.tile_rows}};
         p.x = x_; p.norm_w = output_norm_; p.eps = eps_; p.epi = EPI_STORE; p.out = logits_; p.st = st_;
         if (!add_gemv(p, mh, 1, false, n_embd_, PHF_HEAD)) return {};
     }

@@ -22,7 +22,8 @@ struct DevMatrix {
     uint8_t* w = nullptr;      // device
     int type = 0;
     int rows = 0, cols = 0;
-    int row_stride = 0;        // engine layout stride (bytes)
+    int row_stride = 0;        // row stride (bytes) of native / fp layouts; 0 for the tiled engine layout
+    int tile_rows = 1;         // engine layout: rows per tile (rowdot.h)
     size_t gguf_bytes = 0;     // algorithmic bytes (GGUF payload)
     bool quantized() const { return type == T_Q4_K || type == T_Q6_K || type == T_Q8_0; }
 };
@@ -68,7 +69,7 @@ public:
 private:
     Engine() = default;
     Status load(const std::string& path, int device, const gl_engine_opts* opts);
-    Status upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layout);
+    Status upload_matrix(const GGUFTensor& t, DevMatrix& m, bool native_layout, bool paired = false);
     Status upload_f32(const GGUFTensor& t, float** out, int expect);
     Status ensure_pages(int n_tokens);
     Status enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, int* n_launch);

@@ -46,13 +46,13 @@ Status Engine::build_prefill_weights() {
         CU(alloc(&L.wgu16, (size_t)2 * n_ff_ * n_embd_));
         CU(alloc(&L.wd16, (size_t)n_embd_ * n_ff_));
         if (n_ff_ % 8) return failp(GL_ERR_UNSUPPORTED, "n_ff must be a multiple of 8 for the batched prefill");
-        CU(dequant_rows_launch(L.wq.w, L.wq.type, L.wq.rows, L.wq.cols, L.wq.row_stride, L.wqkv16, n_embd_, 0, 0, prefill_bf16_, stream_));
-        CU(dequant_rows_launch(L.wk.w, L.wk.type, L.wk.rows, L.wk.cols, L.wk.row_stride, L.wqkv16, n_embd_, qd, 0, prefill_bf16_, stream_));
-        CU(dequant_rows_launch(L.wv.w, L.wv.type, L.wv.rows, L.wv.cols, L.wv.row_stride, L.wqkv16, n_embd_, qd + kvd, 0, prefill_bf16_, stream_));
-        CU(dequant_rows_launch(L.wo.w, L.wo.type, L.wo.rows, L.wo.cols, L.wo.row_stride, L.wo16, qd, 0, 0, prefill_bf16_, stream_));
-        CU(dequant_rows_launch(L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.cols, L.wgate.row_stride, L.wgu16, n_embd_, 0, 1, prefill_bf16_, stream_));
-        CU(dequant_rows_launch(L.wup.w, L.wup.type, L.wup.rows, L.wup.cols, L.wup.row_stride, L.wgu16, n_embd_, 0, 2, prefill_bf16_, stream_));
-        CU(dequant_rows_launch(L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.cols, L.wdown.row_stride, L.wd16, n_ff_, 0, 0, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wq.w, L.wq.type, L.wq.rows, L.wq.cols, L.wq.row_stride, L.wq.tile_rows, L.wqkv16, n_embd_, 0, 0, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wk.w, L.wk.type, L.wk.rows, L.wk.cols, L.wk.row_stride, L.wk.tile_rows, L.wqkv16, n_embd_, qd, 0, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wv.w, L.wv.type, L.wv.rows, L.wv.cols, L.wv.row_stride, L.wv.tile_rows, L.wqkv16, n_embd_, qd + kvd, 0, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wo.w, L.wo.type, L.wo.rows, L.wo.cols, L.wo.row_stride, L.wo.tile_rows, L.wo16, qd, 0, 0, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.cols, L.wgate.row_stride, L.wgate.tile_rows, L.wgu16, n_embd_, 0, 1, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wup.w, L.wup.type, L.wup.rows, L.wup.cols, L.wup.row_stride, L.wup.tile_rows, L.wgu16, n_embd_, 0, 2, prefill_bf16_, stream_));
+        CU(dequant_rows_launch(L.wdown.w, L.wdown.type, L.wdown.rows, L.wdown.cols, L.wdown.row_stride, L.wdown.tile_rows, L.wd16, n_ff_, 0, 0, prefill_bf16_, stream_));
     }
     CU(cudaStreamSynchronize(stream_));
     have_w16_ = true;

@@ -72,6 +72,8 @@ bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols
         // Q4_K items are always 4 rows (GEMV_MIN_SLOT_BYTES guarantees the fit); the wider formats take 2
         const int rpi = (m.type == T_Q4_K) ? 4 : 2;
         if (rpi * sb > slot_bytes) return false;
+        // with more than one K-segment the matrix must have been stored with this item's rows as its tile
+        if (ks.nks > 1 && m.tile_rows != (pair ? rpi / 2 : rpi)) return false;
         d.seg[s].w = m.w;
         d.seg[s].rows = m.rows;
         const int rows_per_item = pair ? rpi / 2 : rpi;

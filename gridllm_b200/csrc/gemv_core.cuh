@@ -118,39 +118,31 @@ __device__ __forceinline__ void gemv_produce(const ProdDesc& d, const Ring& ring
     const int A = (int)ring.n_tracks;
     if (lane >= A) return;
     for (int i0 = wr.a + lane; i0 < wr.b; i0 += A) {
-        // this lane's item: source pointers and row counts are the same for every K-segment
+        // this lane's item.  A matrix is stored [tile][K-segment][row in tile][segment] (rowdot.h) with the item's rows as
+        // the tile, so the rows of one (item, K-segment) are ONE contiguous range: one bulk copy per matrix per slot.
         int s, it;
         item_of(d, i0, s, it);
         const uint32_t sb = d.seg_bytes[s];
-        const uint32_t stride = sb * (uint32_t)nks;
         const int rpi = d.rpi[s];
-        const int rows = d.seg[s].rows;
-        const uint8_t *w0, *w1 = nullptr;
-        int n0, n1 = 0, off1 = 0;
-        if (d.pair) {
-            const int h = rpi >> 1, g0 = it * h;
-            n0 = n1 = min(h, rows - g0);
-            w0 = d.seg[0].w + (size_t)g0 * stride;
-            w1 = d.seg[1].w + (size_t)g0 * stride;
-            off1 = h * (int)sb;
-        } else {
-            const int r0 = it * rpi;
-            n0 = min(rpi, rows - r0);
-            w0 = d.seg[s].w + (size_t)r0 * stride;
-        }
+        const int tile = d.pair ? (rpi >> 1) : rpi;               // rows of this matrix per item
+        const int n = min(tile, d.seg[s].rows - it * tile);        // ragged last item
+        const size_t tile_bytes = (size_t)tile * nks * sb;
+        const uint8_t* w0 = d.seg[s].w + (size_t)it * tile_bytes;
+        const uint8_t* w1 = d.pair ? d.seg[1].w + (size_t)it * tile_bytes : nullptr;
+        const uint32_t bytes = (uint32_t)n * sb;
         for (int ks = 0; ks < nks; ++ks) {
             const unsigned pos = (unsigned)lane * ring.depth + tr.d;
             mbar_wait(&ring.empty[pos], tr.par ^ 1u);
             uint8_t* dst = ring.slots + (size_t)pos * ring.slot_bytes;
             uint64_t* bar = &ring.full[pos];
-            mbar_expect_tx(bar, (uint32_t)(n0 + n1) * sb);
-            if (nks == 1) {          // rows are contiguous in HBM: one bulk copy per matrix
-                tma_load_1d(dst, w0, (uint32_t)n0 * sb, bar);
-                if (n1) tma_load_1d(dst + off1, w1, (uint32_t)n1 * sb, bar);
+            const size_t ko = (size_t)ks * tile * sb;
+            if (d.pair) {
+                mbar_expect_tx(bar, 2u * bytes);
+                tma_load_1d(dst, w0 + ko, bytes, bar);
+                tma_load_1d(dst + tile * sb, w1 + ko, bytes, bar);
             } else {
-                const size_t ko = (size_t)ks * sb;
-                for (int j = 0; j < n0; ++j) tma_load_1d(dst + j * sb, w0 + (size_t)j * stride + ko, sb, bar);
-                for (int j = 0; j < n1; ++j) tma_load_1d(dst + off1 + j * sb, w1 + (size_t)j * stride + ko, sb, bar);
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(dst, w0 + ko, bytes, bar);
             }
             tr.advance(ring.depth);
         }
@@ -167,7 +159,7 @@ __device__ __forceinline__ void gemv_produce(const ProdDesc& d, const Ring& ring
 template <int ABITS, int NW>
 __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid) {
     constexpr int NT = NW * 32;
-    constexpr int NB = 4;                  // float4 loads in flight per thread (one L2 round trip per batch)
+    constexpr int NB = 5;                  // float4 loads in flight per thread (one L2 round trip per batch)
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -218,17 +210,16 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
                 vs += __shfl_xor_sync(0xffffffffu, vs, 1);
                 vs += __shfl_xor_sync(0xffffffffu, vs, 2);           // sum(v) of this 16-column group
                 const int vs32 = vs + __shfl_xor_sync(0xffffffffu, vs, 4);
-                const int blk = f >> 3, half = (f >> 2) & 1;
-                const int u = blk >> 2;
-                const int phys = (2 * (blk & 3) + half) ^ (u & 7);
-                const int off = u * 128 + phys * 16 + (f & 3) * 4;
+                // float4 f covers columns 4f..4f+3: unit f>>5, 16-B chunk (f>>2)&7 of the unit, word f&3 of the chunk
+                const int u = f >> 5;
+                const int off = (u << 7) + (((((f >> 2) & 7) ^ (u & 7))) << 4) + ((f & 3) << 2);
                 *reinterpret_cast<uint32_t*>(xhi + off) = h;
                 if (ABITS == 16) *reinterpret_cast<uint32_t*>(xlo + off) = l;
-                if ((f & 3) == 0) s16_arr[2 * blk + half] = vs;
+                if ((f & 3) == 0) s16_arr[f >> 2] = vs;
                 if ((f & 7) == 0) {
                     const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
-                    sx_arr[blk] = sx;
-                    sm_arr[blk] = sx * (float)vs32;
+                    sx_arr[f >> 3] = sx;
+                    sm_arr[f >> 3] = sx * (float)vs32;
                 }
             }
         }

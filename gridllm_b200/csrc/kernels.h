@@ -26,7 +26,7 @@ enum GemvEpilogue : int {
 // Geometry of one GEMV phase: what the producer lane needs to stream it and the consumers need to walk it
 // (gemv_core.cuh).  64 bytes, so that the persistent kernel can keep one per phase in its parameter constant bank.
 struct ProdSeg {
-    const uint8_t* w;      // engine row layout (rowdot.h); row stride = nks * seg_bytes
+    const uint8_t* w;      // engine layout (rowdot.h): [tile][K-segment][row in tile][seg_bytes]
     int rows;
     int n_items;           // ceil(rows / rows-per-item)   (pair mode: gate rows / (rpi/2))
 };
@@ -67,7 +67,7 @@ struct GemvParams {
 };
 
 // a weight matrix as the planner sees it
-struct GemvMat { const uint8_t* w; int type; int rows; };
+struct GemvMat { const uint8_t* w; int type; int rows; int tile_rows; };   // tile_rows: what the matrix was stored with (rowdot.h)
 
 // host helpers
 size_t gemv_smem_bytes(int cols, int n_slots, int slot_bytes);

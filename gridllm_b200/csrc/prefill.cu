@@ -27,14 +27,15 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // element access into ENGINE row layouts (rowdot.h) -- used once at load to build the 16-bit copy
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float dequant_engine(const uint8_t* row, int type, int cols, int c) {
+__device__ __forceinline__ float dequant_engine(const uint8_t* mat, int type, int cols, int row_stride, int tile_rows, int r, int c) {
+    const uint8_t* row = mat + (size_t)r * row_stride;      // fp types: plain row-major
     switch (type) {
         case T_F32: return reinterpret_cast<const float*>(row)[c];
         case T_F16: return __half2float(reinterpret_cast<const __half*>(row)[c]);
         case T_BF16: return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(row)[c] << 16);
         case T_Q4_K:
         case T_Q6_K:
-        case T_Q8_0: return dequant_engine_quant(row, type, cols, c);
+        case T_Q8_0: return dequant_engine_quant(mat, type, cols, tile_rows, r, c);
         default: return 0.f;
     }
 }
@@ -44,15 +45,14 @@ template <> __device__ __forceinline__ __half from_float<__half>(float v) { retu
 template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 template <typename T>
-__global__ void __launch_bounds__(256) dequant_rows_kernel(const uint8_t* __restrict__ src, int type, int rows, int cols, int row_stride,
+__global__ void __launch_bounds__(256) dequant_rows_kernel(const uint8_t* __restrict__ src, int type, int rows, int cols, int row_stride, int tile_rows,
                                                            T* __restrict__ dst, int dst_ld, int dst_row0, int interleave) {
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-        const uint8_t* row = src + (size_t)r * row_stride;
         int dr = r;
         if (interleave == 1) dr = (r >> 3) * 16 + (r & 7);            // gate rows
         else if (interleave == 2) dr = (r >> 3) * 16 + 8 + (r & 7);   // up rows
         T* out = dst + (size_t)(dst_row0 + dr) * dst_ld;
-        for (int c = threadIdx.x; c < cols; c += blockDim.x) out[c] = from_float<T>(dequant_engine(row, type, cols, c));
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) out[c] = from_float<T>(dequant_engine(src, type, cols, row_stride, tile_rows, r, c));
     }
 }
 
@@ -326,7 +326,8 @@ __device__ __forceinline__ float dequant_native_row(const uint8_t* row, int type
         const uint8_t* b = row + (size_t)(c >> 5) * 34;
         return half_bits_to_float(*reinterpret_cast<const uint16_t*>(b)) * (float)(int8_t)b[2 + (c & 31)];
     }
-    return dequant_engine(row, type, 0, c);     // F32 / F16 / BF16 / Q4_K are identical in both layouts
+    if (type == T_Q4_K) return dequant_native_q4k(row, c);
+    return dequant_engine(row, type, 0, 0, 1, 0, c);     // F32 / F16 / BF16: plain rows
 }
 
 __global__ void __launch_bounds__(256) embed_rows_kernel(const uint8_t* __restrict__ w, int type, int cols, int row_bytes, const int* __restrict__ ids,
@@ -377,11 +378,11 @@ cudaError_t gemm_tn_launch(const GemmParams& p, bool bf16, cudaStream_t s) {
     return bf16 ? gemm_launch_d<__nv_bfloat16>(p, s) : gemm_launch_d<__half>(p, s);
 }
 
-cudaError_t dequant_rows_launch(const uint8_t* src, int type, int rows, int cols, int row_stride, void* dst, int dst_ld, int dst_row0,
+cudaError_t dequant_rows_launch(const uint8_t* src, int type, int rows, int cols, int row_stride, int tile_rows, void* dst, int dst_ld, int dst_row0,
                                 int interleave, bool bf16, cudaStream_t s) {
     const int blocks = rows < 148 * 8 ? rows : 148 * 8;
-    if (bf16) dequant_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(src, type, rows, cols, row_stride, (__nv_bfloat16*)dst, dst_ld, dst_row0, interleave);
-    else dequant_rows_kernel<__half><<<blocks, 256, 0, s>>>(src, type, rows, cols, row_stride, (__half*)dst, dst_ld, dst_row0, interleave);
+    if (bf16) dequant_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(src, type, rows, cols, row_stride, tile_rows, (__nv_bfloat16*)dst, dst_ld, dst_row0, interleave);
+    else dequant_rows_kernel<__half><<<blocks, 256, 0, s>>>(src, type, rows, cols, row_stride, tile_rows, (__half*)dst, dst_ld, dst_row0, interleave);
     return cudaGetLastError();
 }
 

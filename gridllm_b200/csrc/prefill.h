@@ -32,7 +32,7 @@ struct GemmParams {
 
 cudaError_t prefill_configure();   // per device: opt in to the GEMM's dynamic shared memory
 cudaError_t gemm_tn_launch(const GemmParams& p, bool bf16, cudaStream_t s);
-cudaError_t dequant_rows_launch(const uint8_t* src, int type, int rows, int cols, int row_stride, void* dst, int dst_ld, int dst_row0,
+cudaError_t dequant_rows_launch(const uint8_t* src, int type, int rows, int cols, int row_stride, int tile_rows, void* dst, int dst_ld, int dst_row0,
                                 int interleave, bool bf16, cudaStream_t s);
 cudaError_t rmsnorm_rows_launch(const float* x, const float* w, int rows, int rows_pad, int n, float eps, void* y, bool bf16, cudaStream_t s);
 cudaError_t rope_split_launch(const float* qkv, int t_rows, int t_pad, int pos0, int n_head, int n_kv, int hd, const float* cos_t,

@@ -12,8 +12,9 @@
 //   item    : R rows (R = 4, or 2 when four do not fit a ring slot) x all K-segments; the unit of work of
 //             one consumer warp.  One ring slot holds the R row-segments of one (item, K-segment).
 //
-// Engine row layouts in HBM (per-row permutations of the GGUF row).  With
-// n = units per K-segment, a row is nks segments back to back, each padded to 16 B (TMA granularity):
+// Engine layouts in HBM (per-row permutations of the GGUF rows).  A matrix is stored as
+// [tile of R rows][K-segment][row in tile][segment], so the R row-segments of one ring slot are one contiguous
+// bulk copy.  With n = units per K-segment, a segment (padded to 16 B, the TMA granularity) is:
 //   Q4_K   : native GGUF (144-B super-blocks), a segment is n/2 consecutive super-blocks.  Conflict-free
 //            as is because 144 = 128 + 16 rotates consecutive blocks across the 16-B shared-memory slots.
 //   Q6_K-T : [ql : 4 x n x 16 B, chunk(i4,u) at (i4*n+u)*16 ]    bytes h*64+16*i4.. of block u>>1, h = u&1
@@ -98,32 +99,41 @@ struct XUnit {
 
 template <int ABITS> GL_HD int combine(int acc_hi, int acc_lo) { return ABITS == 16 ? acc_hi * 128 + acc_lo : acc_hi; }
 
+// four int8 lanes -> one word (two's complement bytes, lane 0 in the low byte)
+GL_HD uint32_t pack4_s8(int a0, int a1, int a2, int a3) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t p01 = __byte_perm((uint32_t)a0, (uint32_t)a1, 0x0040);
+    const uint32_t p23 = __byte_perm((uint32_t)a2, (uint32_t)a3, 0x0040);
+    return __byte_perm(p01, p23, 0x5410);
+#else
+    return ((uint32_t)a0 & 0xFF) | (((uint32_t)a1 & 0xFF) << 8) | (((uint32_t)a2 & 0xFF) << 16) | (((uint32_t)a3 & 0xFF) << 24);
+#endif
+}
+
 // Snap 4 consecutive activations of a 32-column block to the fixed point: one hi word, one lo word, sum(v).
 // inv = RANGE / amax of the WHOLE block (0 for an all-zero block).
-// Spec (oracle/llama_oracle.py snap_i16 / snap_q8): sx = amax/RANGE, v = rint(x * (RANGE/amax)).
+// Spec (oracle/llama_oracle.py snap_i16 / snap_q8): sx = amax/RANGE, v = rint(x * (RANGE/amax)); the 15-bit value is
+// split as v = 128*hi + lo with lo in [-64, 63]  (hi = floor((v + 64) / 128)).
 template <int ABITS>
 GL_HD void snap4(const float* x, float inv, uint32_t* hi, uint32_t* lo, int* vsum) {
-    uint32_t h = 0, l = 0;
-    int s = 0;
+    int v[4], h[4], l[4];
     for (int b = 0; b < 4; ++b) {
 #if defined(__CUDA_ARCH__)
-        int v = __float2int_rn(x[b] * inv);
+        v[b] = __float2int_rn(x[b] * inv);
 #else
-        int v = (int)__builtin_rintf(x[b] * inv);
+        v[b] = (int)__builtin_rintf(x[b] * inv);
 #endif
-        s += v;
         if (ABITS == 16) {
-            int lw = ((v + 64) & 127) - 64;
-            int hh = (v - lw) >> 7;
-            h |= (uint32_t)(hh & 0xFF) << (8 * b);
-            l |= (uint32_t)(lw & 0xFF) << (8 * b);
+            h[b] = (v[b] + 64) >> 7;
+            l[b] = v[b] - (h[b] << 7);
         } else {
-            h |= (uint32_t)(v & 0xFF) << (8 * b);
+            h[b] = v[b];
+            l[b] = 0;
         }
     }
-    *hi = h;
-    *lo = l;
-    *vsum = s;
+    *hi = pack4_s8(h[0], h[1], h[2], h[3]);
+    *lo = ABITS == 16 ? pack4_s8(l[0], l[1], l[2], l[3]) : 0u;
+    *vsum = (v[0] + v[1]) + (v[2] + v[3]);
 }
 
 template <int ABITS> GL_HD float snap_inv(float amax) {
@@ -168,10 +178,20 @@ GL_HD KSplit ksplit(int cols) {
 // ggml type ids (gguf_file.h): Q8_0 = 8, Q4_K = 12, Q6_K = 14.  Bytes of 256 columns.
 GL_HD int quant_block_bytes(int type) { return type == 12 ? 144 : type == 14 ? 210 : type == 8 ? 272 : 0; }
 GL_HD int kseg_bytes(int type, int seg_nb) { return (seg_nb * quant_block_bytes(type) + 15) & ~15; }
-GL_HD int engine_row_stride(int type, int cols) {
-    const KSplit k = ksplit(cols);
-    return k.nks * kseg_bytes(type, k.seg_nb);
+// Matrix layout: rows are grouped into TILES of tile_rows rows (the rows of one GEMV item); inside a tile the
+// K-segments are the outer index, so the tile_rows segments a ring slot holds are ONE contiguous byte range:
+//      [tile][K-segment][row in tile][segment bytes]
+// With one K-segment (K <= 4096) this is plain row-major whatever tile_rows is.
+GL_HD size_t engine_seg_offset(int seg_bytes, int nks, int tile_rows, int r, int ks) {
+    return (size_t)(r / tile_rows) * ((size_t)tile_rows * nks * seg_bytes) + (size_t)ks * tile_rows * seg_bytes +
+           (size_t)(r % tile_rows) * seg_bytes;
 }
+GL_HD size_t engine_matrix_bytes(int type, int rows, int cols, int tile_rows) {
+    const KSplit k = ksplit(cols);
+    return (size_t)((rows + tile_rows - 1) / tile_rows) * tile_rows * k.nks * kseg_bytes(type, k.seg_nb);
+}
+// rows of one non-paired item of a type (gemv_plan): the tile size a matrix is stored with unless it is a gate/up pair
+GL_HD int item_rows(int type) { return type == 12 ? 4 : 2; }
 
 // ---------------------------------------------------------------------------------------------
 // Activation planes in shared memory (written by the GEMV prologue)
@@ -375,63 +395,81 @@ GL_HD void item_dot_q80(const uint8_t* seg, int seg_bytes, int n, int l, const X
 }
 
 // ---------------------------------------------------------------------------------------------
-// host-side row repackers (loader) -- GGUF row -> engine row.  dst has engine_row_stride() bytes.
+// host-side repackers (loader) -- GGUF rows -> engine matrix
 // ---------------------------------------------------------------------------------------------
 inline size_t align16(size_t n) { return (n + 15) & ~(size_t)15; }
 
-inline void repack_row_q6k(const uint8_t* src, uint8_t* dst, int cols) {
-    const KSplit ks = ksplit(cols);
-    const int n = 2 * ks.seg_nb, sb = kseg_bytes(14, ks.seg_nb);
-    memset(dst, 0, (size_t)ks.nks * sb);
-    for (int b = 0; b < cols / 256; ++b) {
-        const uint8_t* blk = src + (size_t)b * 210;
-        uint8_t* seg = dst + (size_t)(b / ks.seg_nb) * sb;
-        const int bl = b % ks.seg_nb;
+// K-segment ks of one GGUF row -> engine segment (kseg_bytes() bytes at dst)
+inline void repack_seg_q4k(const uint8_t* src_row, uint8_t* dst, int cols, int ks) {
+    const KSplit k = ksplit(cols);
+    memcpy(dst, src_row + (size_t)ks * k.seg_nb * 144, (size_t)k.seg_nb * 144);
+}
+
+inline void repack_seg_q6k(const uint8_t* src_row, uint8_t* dst, int cols, int ks) {
+    const KSplit k = ksplit(cols);
+    const int n = 2 * k.seg_nb, sb = kseg_bytes(14, k.seg_nb);
+    memset(dst, 0, (size_t)sb);
+    for (int bl = 0; bl < k.seg_nb; ++bl) {
+        const uint8_t* blk = src_row + (size_t)(ks * k.seg_nb + bl) * 210;
         for (int h = 0; h < 2; ++h) {
             const int u = 2 * bl + h;
-            for (int i4 = 0; i4 < 4; ++i4) memcpy(seg + ((size_t)i4 * n + u) * 16, blk + h * 64 + 16 * i4, 16);
-            for (int i2 = 0; i2 < 2; ++i2) memcpy(seg + (size_t)n * 64 + ((size_t)i2 * n + u) * 16, blk + 128 + h * 32 + 16 * i2, 16);
-            memcpy(seg + (size_t)n * 96 + (size_t)u * 8, blk + 192 + 8 * h, 8);
+            for (int i4 = 0; i4 < 4; ++i4) memcpy(dst + ((size_t)i4 * n + u) * 16, blk + h * 64 + 16 * i4, 16);
+            for (int i2 = 0; i2 < 2; ++i2) memcpy(dst + (size_t)n * 64 + ((size_t)i2 * n + u) * 16, blk + 128 + h * 32 + 16 * i2, 16);
+            memcpy(dst + (size_t)n * 96 + (size_t)u * 8, blk + 192 + 8 * h, 8);
         }
-        memcpy(seg + (size_t)n * 104 + (size_t)bl * 2, blk + 208, 2);
+        memcpy(dst + (size_t)n * 104 + (size_t)bl * 2, blk + 208, 2);
     }
 }
 
-inline void repack_row_q80(const uint8_t* src, uint8_t* dst, int cols) {
-    const KSplit ks = ksplit(cols);
-    const int n = 2 * ks.seg_nb, sb = kseg_bytes(8, ks.seg_nb);
-    for (int ug = 0; ug < cols / UNIT_COLS; ++ug) {
-        uint8_t* seg = dst + (size_t)(ug / n) * sb;
-        const int u = ug % n;
+inline void repack_seg_q80(const uint8_t* src_row, uint8_t* dst, int cols, int ks) {
+    const KSplit k = ksplit(cols);
+    const int n = 2 * k.seg_nb;
+    for (int u = 0; u < n; ++u) {
+        const int ug = ks * n + u;
         for (int j = 0; j < 4; ++j) {
-            const uint8_t* blk = src + (size_t)(4 * ug + j) * 34;
-            memcpy(seg + ((size_t)(2 * j) * n + u) * 16, blk + 2, 16);
-            memcpy(seg + ((size_t)(2 * j + 1) * n + u) * 16, blk + 18, 16);
-            memcpy(seg + (size_t)n * 128 + (size_t)u * 8 + 2 * j, blk, 2);
+            const uint8_t* blk = src_row + (size_t)(4 * ug + j) * 34;
+            memcpy(dst + ((size_t)(2 * j) * n + u) * 16, blk + 2, 16);
+            memcpy(dst + ((size_t)(2 * j + 1) * n + u) * 16, blk + 18, 16);
+            memcpy(dst + (size_t)n * 128 + (size_t)u * 8 + 2 * j, blk, 2);
         }
     }
 }
 
-// element c of an ENGINE-layout quantised row (load-time 16-bit copy for the batched prefill; host checks)
-GL_HD float dequant_engine_quant(const uint8_t* row, int type, int cols, int c) {
-    if (type == 12) {
-        const uint8_t* b = row + (size_t)(c >> 8) * 144;
-        const int e = c & 255, sub = e >> 5, l = e & 31;
-        const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b));
-        const float dmin = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 2));
-        const uint8_t* sc = b + 4;
-        int s, m;
-        if (sub < 4) { s = sc[sub] & 63; m = sc[4 + sub] & 63; }
-        else { s = (sc[4 + sub] & 0xF) | ((sc[sub - 4] >> 6) << 4); m = (sc[4 + sub] >> 4) | ((sc[sub] >> 6) << 4); }
-        const uint8_t qb = b[16 + (sub >> 1) * 32 + l];
-        const int q = (sub & 1) ? (qb >> 4) : (qb & 0xF);
-        return d * (float)s * (float)q - dmin * (float)m;
+// one GGUF row -> its segments inside the engine matrix `mat` (engine_matrix_bytes() bytes, zero-initialised)
+inline void repack_row(int type, const uint8_t* src_row, uint8_t* mat, int cols, int tile_rows, int r) {
+    const KSplit k = ksplit(cols);
+    const int sb = kseg_bytes(type, k.seg_nb);
+    for (int ks = 0; ks < k.nks; ++ks) {
+        uint8_t* dst = mat + engine_seg_offset(sb, k.nks, tile_rows, r, ks);
+        if (type == 12) repack_seg_q4k(src_row, dst, cols, ks);
+        else if (type == 14) repack_seg_q6k(src_row, dst, cols, ks);
+        else repack_seg_q80(src_row, dst, cols, ks);
     }
+}
+
+// element c of a NATIVE GGUF Q4_K row
+GL_HD float dequant_native_q4k(const uint8_t* row, int c) {
+    const uint8_t* b = row + (size_t)(c >> 8) * 144;
+    const int e = c & 255, sub = e >> 5, l = e & 31;
+    const float d = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b));
+    const float dmin = half_bits_to_float(*reinterpret_cast<const uint16_t*>(b + 2));
+    const uint8_t* sc = b + 4;
+    int s, m;
+    if (sub < 4) { s = sc[sub] & 63; m = sc[4 + sub] & 63; }
+    else { s = (sc[4 + sub] & 0xF) | ((sc[sub - 4] >> 6) << 4); m = (sc[4 + sub] >> 4) | ((sc[sub] >> 6) << 4); }
+    const uint8_t qb = b[16 + (sub >> 1) * 32 + l];
+    const int q = (sub & 1) ? (qb >> 4) : (qb & 0xF);
+    return d * (float)s * (float)q - dmin * (float)m;
+}
+
+// element (r, c) of an ENGINE-layout quantised matrix (load-time 16-bit copy for the batched prefill; host checks)
+GL_HD float dequant_engine_quant(const uint8_t* mat, int type, int cols, int tile_rows, int r, int c) {
     const KSplit ks = ksplit(cols);
     const int n = 2 * ks.seg_nb;
     const int ug = c >> 7, w = c & 127;
-    const uint8_t* seg = row + (size_t)(ug / n) * kseg_bytes(type, ks.seg_nb);
+    const uint8_t* seg = mat + engine_seg_offset(kseg_bytes(type, ks.seg_nb), ks.nks, tile_rows, r, ug / n);
     const int u = ug % n;
+    if (type == 12) return dequant_native_q4k(seg, (u << 7) + w);      // a Q4_K segment is a run of native super-blocks
     if (type == 14) {
         const int i = w & 63, s = w >> 6, j = w & 31, t = w >> 5;
         const int qlv = (seg[((size_t)(i >> 4) * n + u) * 16 + (i & 15)] >> (4 * s)) & 0xF;

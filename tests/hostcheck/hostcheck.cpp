@@ -48,33 +48,27 @@ struct Planes {
     }
 };
 
-static void to_engine_row(int type, const uint8_t* src, uint8_t* dst, int cols) {
-    if (type == T_Q4_K) memcpy(dst, src, row_bytes(type, cols));
-    else if (type == T_Q6_K) repack_row_q6k(src, dst, cols);
-    else repack_row_q80(src, dst, cols);
-}
-
-// The consumer loop of gemv_core.cuh on the host: items of R rows, K-segment by K-segment, a "slot" holding the R
-// row segments back to back, lane l = unit l of the segment.
+// The consumer loop of gemv_core.cuh on the host: the matrix is stored in the engine layout with R-row tiles, a "slot"
+// is filled the way the producer lane does it (one contiguous range per (item, K-segment)), lane l = unit l of the segment.
 template <int AB, int R>
 static int run_items(int type, const uint8_t* w, int rows, int cols, const float* x, float* y) {
     const KSplit ks = ksplit(cols);
     if (!ks.nks) return -2;
     Planes<AB> pl(x, cols);
     const int n = 2 * ks.seg_nb, sb = kseg_bytes(type, ks.seg_nb);
-    const size_t rb = row_bytes(type, cols), rs = (size_t)engine_row_stride(type, cols);
-    std::vector<uint8_t> rowbuf(rs + 16), slotbuf((size_t)R * sb + 16);
-    uint8_t* er = rowbuf.data() + ((16 - ((uintptr_t)rowbuf.data() & 15)) & 15);
+    const size_t rb = row_bytes(type, cols);
+    std::vector<uint8_t> matbuf(engine_matrix_bytes(type, rows, cols, R) + 16, 0), slotbuf((size_t)R * sb + 16);
+    uint8_t* mat = matbuf.data() + ((16 - ((uintptr_t)matbuf.data() & 15)) & 15);
     uint8_t* slot = slotbuf.data() + ((16 - ((uintptr_t)slotbuf.data() & 15)) & 15);
-    std::vector<uint8_t> erows((size_t)R * rs);
-    for (int i = 0; i < rows; i += R) {
+    for (int r = 0; r < rows; ++r) repack_row(type, w + (size_t)r * rb, mat, cols, R, r);
+    const size_t tile_bytes = (size_t)R * ks.nks * sb;
+    for (int i = 0, it = 0; i < rows; i += R, ++it) {
         const int nv = rows - i < R ? rows - i : R;
-        for (int r = 0; r < nv; ++r) { to_engine_row(type, w + (size_t)(i + r) * rb, er, cols); memcpy(erows.data() + (size_t)r * rs, er, rs); }
         float acc[R];
         for (int r = 0; r < R; ++r) acc[r] = 0.f;
         for (int k = 0; k < ks.nks; ++k) {
             memset(slot, 0xA5, (size_t)R * sb);                           // rows beyond the ragged end hold garbage on the GPU too
-            for (int r = 0; r < nv; ++r) memcpy(slot + (size_t)r * sb, erows.data() + (size_t)r * rs + (size_t)k * sb, sb);
+            memcpy(slot, mat + (size_t)it * tile_bytes + (size_t)k * R * sb, (size_t)nv * sb);      // = the producer's one bulk copy
             for (int l = 0; l < n; ++l) {
                 const int ug = k * n + l;
                 XPlanes xp{pl.hi + (size_t)ug * 128, pl.lo + (size_t)ug * 128, pl.sx + 4 * ug, pl.sm + 4 * ug, pl.s16 + 8 * ug, ug & 7};
@@ -110,14 +104,13 @@ extern "C" int hc_gemv(int type, const uint8_t* w, int rows, int cols, const flo
 
 // engine row layout round trip: GGUF rows -> engine rows -> element-wise dequantisation (what the batched prefill's
 // 16-bit copy is built from)
-extern "C" int hc_dequant_engine(int type, const uint8_t* w, int rows, int cols, float* out) {
+extern "C" int hc_dequant_engine(int type, const uint8_t* w, int rows, int cols, int tile_rows, float* out) {
     if (!ksplit(cols).nks) return -2;
-    const size_t rb = row_bytes(type, cols), rs = (size_t)engine_row_stride(type, cols);
-    std::vector<uint8_t> er(rs);
-    for (int i = 0; i < rows; ++i) {
-        to_engine_row(type, w + (size_t)i * rb, er.data(), cols);
-        for (int c = 0; c < cols; ++c) out[(size_t)i * cols + c] = dequant_engine_quant(er.data(), type, cols, c);
-    }
+    const size_t rb = row_bytes(type, cols);
+    std::vector<uint8_t> mat(engine_matrix_bytes(type, rows, cols, tile_rows), 0);
+    for (int i = 0; i < rows; ++i) repack_row(type, w + (size_t)i * rb, mat.data(), cols, tile_rows, i);
+    for (int i = 0; i < rows; ++i)
+        for (int c = 0; c < cols; ++c) out[(size_t)i * cols + c] = dequant_engine_quant(mat.data(), type, cols, tile_rows, i, c);
     return 0;
 }
 extern "C" int hc_ksplit(int cols, int* nks, int* seg_nb) {

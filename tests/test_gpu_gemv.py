@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [  # (rows, cols)
     (64, 256), (130, 512), (48, 768), (256, 1024), (40, 2048), (1024, 4096), (300, 5632), (296, 14336), (2, 4096), (1, 256),
+    (9001, 4096), (5003, 14336),      # several rounds of items per CTA; ragged last items; 4 K-segments
 ]
 
 

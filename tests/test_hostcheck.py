@@ -85,13 +85,16 @@ def test_ksplit_table(hostcheck_lib, cols, expect):
 @pytest.mark.parametrize("tname", ["Q4_K", "Q6_K", "Q8_0"])
 @pytest.mark.parametrize("cols", [256, 4096, 14336])
 def test_engine_layout_round_trip(hostcheck_lib, tname, cols):
-    """GGUF row -> engine row (K-segment-major transposed layouts) -> element access == gguf dequantisation, bit for bit"""
+    """GGUF rows -> engine matrix ([tile][K-segment][row][segment], transposed Q6_K / Q8_0 segments) -> element access ==
+    gguf dequantisation, bit for bit, for every tile size"""
     from oracle import gguf_synth as S, llama_oracle as O
     t = {"Q4_K": S.Q4_K, "Q6_K": S.Q6_K, "Q8_0": S.Q8_0}[tname]
     rng = np.random.Generator(np.random.PCG64(cols + 5))
-    rows = 3
+    rows = 7
     blocks = S.random_blocks(rng, t, rows, cols)
-    out = np.zeros((rows, cols), np.float32)
-    rc = hostcheck_lib.hc_dequant_engine(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, out.ctypes.data_as(ctypes.c_void_p))
-    assert rc == 0
-    assert np.array_equal(out, O.dequantize(blocks, t, (rows, cols)).astype(np.float32))
+    ref = O.dequantize(blocks, t, (rows, cols)).astype(np.float32)
+    for tile_rows in (1, 2, 4):
+        out = np.zeros((rows, cols), np.float32)
+        rc = hostcheck_lib.hc_dequant_engine(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, tile_rows, out.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        assert np.array_equal(out, ref), tile_rows

@@ -2,7 +2,7 @@
 # v3 GEMV core (warp-owned items, FIFO ring of small slots): parity, microbench, decode probe
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q -k "gemv or decode" > gpurun_out/pytest_gpu.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
 timeout 600 python tools/microbench.py > gpurun_out/microbench.log 2>&1
