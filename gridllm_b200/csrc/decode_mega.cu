@@ -212,11 +212,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     uint32_t aparity = 0;
     Ring ring;
     ring.init(smem, smem + fixed + 1024 + ATTN_SMEM_BYTES, mp.n_tracks, mp.depth, mp.slot_bytes);
-    if (tid == 0) {
-        ring.init_barriers();
-        mbar_init(abar, 1);
-        fence_mbar_init();
-    }
+    ring.init_barriers(tid);
+    if (tid == 0) mbar_init(abar, 1);
+    if (tid < RING_MAX_SLOTS) fence_mbar_init();
     __syncthreads();
 
     if (warp == NW) {
@@ -255,6 +253,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
         ++nbar;
         grid_barrier<NT>(mp.bar_counter, bar_base + nbar * G, tid);
         const int step_pos = __ldcg(&st->pos);        // fixed for the whole step
+        const EpiCtx step_ec{step_pos, __ldcg(mp.page_table + step_pos / KV_PAGE_TOKENS)};
 
         for (int ph = 0; ph < mp.n_phases; ++ph) {
             const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<const uint8_t*>(sdesc) + dslot * 256);
@@ -262,9 +261,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
             unsigned long long* tr = (mp.trace != nullptr && tid == 0) ? mp.trace + ((size_t)cta * (mp.n_phases + 1) + ph) * 4 : nullptr;
             if (tr) tr[0] = gtime();
             if (kind == PH_GEMV) {
-                const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid);
+                PrologueStatic ps;
+                gemv_prologue_static<NW>(P.g, tid, ps);
+                const float scale = gemv_prologue<ABITS, NW>(P.g, smem, tid, ps);
                 if (tr) tr[1] = gtime();
-                gemv_consume<ABITS>(P.g, ring, trk, smem, tid, scale, cta, G);
+                gemv_consume<ABITS>(P.g, ring, trk, smem, tid, scale, step_ec, cta, G);
                 if (P.flags & PHF_HEAD) {
                     // per-CTA softmax statistics over the logits rows this CTA produced
                     named_bar_sync(1, NT);

@@ -29,10 +29,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
     ring.init(smem, smem + gemv_fixed_smem(p.cols), p.n_tracks, p.depth, p.slot_bytes);
-    if (tid == 0) {
-        ring.init_barriers();
-        fence_mbar_init();
-    }
+    ring.init_barriers(tid);
+    if (tid < RING_MAX_SLOTS) fence_mbar_init();
     __syncthreads();
     pdl_launch_dependents();
 
@@ -42,10 +40,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
         gemv_produce(p.pd, ring, tr, lane, blockIdx.x, gridDim.x);
         return;
     }
+    PrologueStatic ps;
+    gemv_prologue_static<NW>(p, tid, ps);     // RMSNorm weights: static, requested while the upstream kernel drains
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
-    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid);
+    const EpiCtx ec = load_epi_ctx(p);
+    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps);
     Track tr{0u, 0u};
-    gemv_consume<ABITS>(p, ring, tr, smem, tid, scale, blockIdx.x, gridDim.x);
+    gemv_consume<ABITS>(p, ring, tr, smem, tid, scale, ec, blockIdx.x, gridDim.x);
 }
 
 }  // namespace

@@ -57,10 +57,11 @@ struct Ring {
         depth = (unsigned)d;
         slot_bytes = (unsigned)bytes;
     }
-    __device__ __forceinline__ void init_barriers() const {
-        for (unsigned i = 0; i < n_tracks * depth; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+    // threads 0 .. n_slots-1 of the CTA, one slot each (followed by fence_mbar_init + a CTA barrier in the caller)
+    __device__ __forceinline__ void init_barriers(int tid) const {
+        if ((unsigned)tid < n_tracks * depth) {
+            mbar_init(&full[tid], 1);
+            mbar_init(&empty[tid], 1);
         }
     }
 };
@@ -156,10 +157,28 @@ __device__ __forceinline__ void gemv_produce(const ProdDesc& d, const Ring& ring
 // rstd = 1/sqrt(mean(x^2)+eps).  The fixed-point integers v = rint(x*w / amax_blk(x*w) * RANGE) do not depend on
 // rstd (it cancels), so the planes are built from x*w while the sum of squares is still being reduced, and rstd is
 // applied once per output row.  One named barrier in total.
-template <int ABITS, int NW>
-__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid) {
+constexpr int PROLOGUE_NB = 5;            // float4 loads in flight per thread (one L2 round trip per batch)
+
+// The static half of the prologue: the RMSNorm weights of this thread's first batch.  They do not depend on the
+// upstream kernel / phase, so the caller requests them BEFORE it waits for it (griddepcontrol.wait, grid barrier).
+struct PrologueStatic { float4 wv[PROLOGUE_NB]; };
+template <int NW>
+__device__ __forceinline__ void gemv_prologue_static(const GemvParams& p, int tid, PrologueStatic& ps) {
     constexpr int NT = NW * 32;
-    constexpr int NB = 5;                  // float4 loads in flight per thread (one L2 round trip per batch)
+    if (p.norm_w == nullptr) return;
+    const int nf = p.cols / 4;
+    const float4* w4 = reinterpret_cast<const float4*>(p.norm_w);
+#pragma unroll
+    for (int i = 0; i < PROLOGUE_NB; ++i) {
+        const int f = tid + i * NT;
+        if (f < nf) ps.wv[i] = __ldg(w4 + f);
+    }
+}
+
+template <int ABITS, int NW>
+__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps) {
+    constexpr int NT = NW * 32;
+    constexpr int NB = PROLOGUE_NB;
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -188,7 +207,8 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
                 const int f = f0 + i * NT;
-                if (f < nf) wv[i] = __ldg(w4 + f);
+                if (f0 == tid) wv[i] = ps.wv[i];          // first batch: requested before the upstream wait
+                else if (f < nf) wv[i] = __ldg(w4 + f);
             }
         }
 #pragma unroll
@@ -270,10 +290,19 @@ __device__ __forceinline__ float warp_sum2(const float* o, int lane) {
     return k;
 }
 
-struct EpiCtx {      // per-phase constants of the QKV epilogue, loaded once
+struct EpiCtx {      // per-step constants of the QKV epilogue (position, physical KV page of that position)
     int pos;
     int page;
 };
+// two dependent loads: the caller issues them right after the upstream wait so that they travel with the prologue's x
+__device__ __forceinline__ EpiCtx load_epi_ctx(const GemvParams& p) {
+    EpiCtx ec{0, 0};
+    if (p.epi == EPI_QKV) {
+        ec.pos = __ldcg(&p.st->pos);
+        ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
+    }
+    return ec;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // one item of TYPE with R rows: all its K-segments, reduction, epilogue.  Warp-private.
@@ -363,18 +392,13 @@ __device__ __forceinline__ void consume_item(const GemvParams& p, const Ring& ri
 // consumer main loop over this CTA's items.  All consumer warps call it; tr is the warp's position in its track.
 // ---------------------------------------------------------------------------------------------------
 template <int ABITS>
-__device__ __forceinline__ void gemv_consume(const GemvParams& p, const Ring& ring, Track& tr, uint8_t* smem, int tid, float scale, int cta,
-                                             int n_ctas) {
+__device__ __forceinline__ void gemv_consume(const GemvParams& p, const Ring& ring, Track& tr, uint8_t* smem, int tid, float scale,
+                                             const EpiCtx& ec, int cta, int n_ctas) {
     const ProdDesc& d = p.pd;
     const int warp = tid >> 5, lane = tid & 31;
     const WorkRange wr = cta_range(total_items(d), cta, n_ctas);
     const int A = (int)ring.n_tracks;
     if (warp >= A) return;
-    EpiCtx ec{0, 0};
-    if (p.epi == EPI_QKV) {
-        ec.pos = __ldcg(&p.st->pos);
-        ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
-    }
     for (int i0 = wr.a + warp; i0 < wr.b; i0 += A) {
         int s, it;
         item_of(d, i0, s, it);
