@@ -163,11 +163,13 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     abits_ = env_int("GL_ACT_BITS", abits_) == 8 ? 8 : 16;
     nw_ = env_int("GL_WARPS", 12);
     if (!gemv_variant_ok(abits_, nw_)) nw_ = 12;
-    ring_depth_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH", 2)));
+    ring_depth_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH", 2)));          // persistent kernel
+    ring_depth_max_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH_MAX", 3)));   // stand-alone kernels: up to this many slots per warp
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
+    prefill_tc5_ = env_int("GL_PREFILL_TC5", 1) != 0;
 
     std::string err = gguf_.open(path);
     if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);
@@ -198,6 +200,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     for (auto& ev : ev_) CU(cudaEventCreate(&ev));
     CU(gemv_configure());
     CU(prefill_configure());
+    CU(gemm_tc5_configure());
 
     // ---- weights -> HBM -------------------------------------------------------------------------
     ST(upload_matrix(*te, tok_embd_, /*native=*/true));
@@ -387,18 +390,19 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
 Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int* n_launch) {
     // slot size: what the widest item of this kernel needs (Q4_K: 4 row segments, Q6_K / Q8_0: 2), ring depth: whatever
     // shared memory is left, capped so that the bytes in flight stay near what the HBM pipe needs
-    int need = GEMV_MIN_SLOT_BYTES;
+    int need = 0;
     {
         const KSplit ks = ksplit(cols);
         if (!ks.nks) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
-        for (int i = 0; i < nmat; ++i) need = std::max(need, (mats[i].type == T_Q4_K ? 4 : 2) * kseg_bytes(mats[i].type, ks.seg_nb));
+        for (int i = 0; i < nmat; ++i) need = std::max(need, item_rows(mats[i].type) * kseg_bytes(mats[i].type, ks.seg_nb));
     }
     p.slot_bytes = (need + 127) & ~127;
     if (!gemv_plan(p, mats, nmat, pair, cols, p.slot_bytes)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
     const size_t fixed = gemv_smem_bytes(cols, 0, 0);
     const int ns = std::min(RING_MAX_SLOTS, (int)(((size_t)smem_kb_ * 1024 - fixed) / p.slot_bytes));
-    p.depth = ring_depth_;
-    p.n_tracks = std::min(nw_, ns / p.depth);
+    // as many consumer warps as there are, each with >= 2 slots; spare slots deepen the tracks (small slots: more bytes in flight)
+    p.n_tracks = std::min(nw_, ns / 2);
+    p.depth = p.n_tracks > 0 ? std::min(ring_depth_max_, ns / p.n_tracks) : 0;
     if (p.n_tracks < 1) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
     CU(gemv_launch(p, abits_, nw_, sm_count_, use_pdl_, s));
     ++*n_launch;

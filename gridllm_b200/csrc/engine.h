@@ -104,10 +104,11 @@ private:
     int abits_ = 16;
     int nw_ = 12;              // consumer warps per CTA of the GEMV / persistent kernels
     int ring_depth_ = 2;       // ring slots per consumer warp (track depth, gemv_core.cuh)
+    int ring_depth_max_ = 3;
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
     int smem_kb_ = 224, attn_splits_ = 16;
     int prefill_mode_ = 0, prefill_min_ = 8;
-    bool have_w16_ = false, prefill_bf16_ = false;
+    bool have_w16_ = false, prefill_bf16_ = false, prefill_tc5_ = true;
     // prefill scratch (grown on demand)
     int pf_cap_ = 0;
     float *pf_x_ = nullptr, *pf_qkv_ = nullptr, *pf_s_ = nullptr;

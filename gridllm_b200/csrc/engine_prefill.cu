@@ -94,6 +94,11 @@ Status Engine::prefill_batched(int n, int* n_launch) {
     cudaStream_t s = stream_;
     const bool bf = prefill_bf16_;
     int nl = 0;
+    // linear layers: tcgen05 / TMEM / TMA GEMM (prefill_tc5.cu); GL_PREFILL_TC5=0 keeps the mma.sync kernel for A/B runs
+    auto linear = [&](const GemmParams& g) -> cudaError_t {
+        if (prefill_tc5_ && gemm_tc5_supported(g)) return gemm_tc5_launch(g, tp, bf, s);
+        return gemm_tn_launch(g, bf, s);
+    };
     CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, prompt_ids_, T, pf_x_, s)); ++nl;
     const float scale = 1.0f / std::sqrt((float)hd_);
     for (int il = 0; il < n_layer_; ++il) {
@@ -105,7 +110,7 @@ Status Engine::prefill_batched(int n, int* n_launch) {
             GemmParams g{};
             g.a = pf_xn_; g.b = L.wqkv16; g.c = pf_qkv_; g.m = T; g.n = ldq; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = ldq;
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
-            CU(gemm_tn_launch(g, bf, s)); ++nl;
+            CU(linear(g)); ++nl;
         }
         CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, s)); ++nl;
         {   // S[h] = Q_h K_kvh^T
@@ -127,20 +132,20 @@ Status Engine::prefill_batched(int n, int* n_launch) {
             GemmParams g{};
             g.a = pf_attn_; g.b = L.wo16; g.c = pf_x_; g.m = T; g.n = n_embd_; g.k = qd; g.lda = qd; g.ldb = qd; g.ldc = n_embd_;
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_ADD_F32;
-            CU(gemm_tn_launch(g, bf, s)); ++nl;
+            CU(linear(g)); ++nl;
         }
         CU(rmsnorm_rows_launch(pf_x_, L.ffn_norm, T, TP, n_embd_, eps_, pf_xn_, bf, s)); ++nl;
         {
             GemmParams g{};
             g.a = pf_xn_; g.b = L.wgu16; g.c = pf_h_; g.m = T; g.n = 2 * n_ff_; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = n_ff_;
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_SILU;
-            CU(gemm_tn_launch(g, bf, s)); ++nl;
+            CU(linear(g)); ++nl;
         }
         {
             GemmParams g{};
             g.a = pf_h_; g.b = L.wd16; g.c = pf_x_; g.m = T; g.n = n_embd_; g.k = n_ff_; g.lda = n_ff_; g.ldb = n_ff_; g.ldc = n_embd_;
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_ADD_F32;
-            CU(gemm_tn_launch(g, bf, s)); ++nl;
+            CU(linear(g)); ++nl;
         }
     }
     // hidden state of the last prompt token -> the decode path's x buffer (lm_head / sampler follow)

@@ -57,7 +57,7 @@ size_t gemv_smem_bytes(int cols, int n_slots, int slot_bytes) {
 
 bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int slot_bytes) {
     if (nmat < 1 || nmat > 3 || cols <= 0 || cols > 32768 || (cols & 255)) return false;
-    if (slot_bytes < GEMV_MIN_SLOT_BYTES || (slot_bytes & 127)) return false;
+    if (slot_bytes <= 0 || (slot_bytes & 127)) return false;
     const KSplit ks = ksplit(cols);
     if (!ks.nks) return false;
     ProdDesc d{};
@@ -70,8 +70,8 @@ bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols
         if (m.type != T_Q4_K && m.type != T_Q6_K && m.type != T_Q8_0) return false;
         if (m.rows <= 0 || ((uintptr_t)m.w & 15)) return false;
         const int sb = kseg_bytes(m.type, ks.seg_nb);
-        // Q4_K items are always 4 rows (GEMV_MIN_SLOT_BYTES guarantees the fit); the wider formats take 2
-        const int rpi = (m.type == T_Q4_K) ? 4 : 2;
+        // Q4_K items are 4 rows; the wider formats take 2 (item_rows(), rowdot.h)
+        const int rpi = item_rows(m.type);
         if (rpi * sb > slot_bytes) return false;
         // with more than one K-segment the matrix must have been stored with this item's rows as its tile
         if (ks.nks > 1 && m.tile_rows != (pair ? rpi / 2 : rpi)) return false;

@@ -34,10 +34,10 @@
 namespace gl {
 
 // shared-memory carve-up (bytes from the start of dynamic smem)
-constexpr int SM_BARS = 0;                 // full[24], empty[24] mbarriers (384 B)
-constexpr int SM_RED = 384;                // 32 floats: RMSNorm partials
-constexpr int SM_MISC = 512;               // 128 B scratch (flags)
-constexpr int SM_X = 640;                  // x planes start
+constexpr int SM_BARS = 0;                 // full[36], empty[36] mbarriers (576 B)
+constexpr int SM_RED = 576;                // 32 floats: RMSNorm partials
+constexpr int SM_MISC = 704;               // 64 B scratch (flags)
+constexpr int SM_X = 768;                  // x planes start
 
 __host__ __device__ inline int gemv_x_bytes(int cols) { return 2 * cols + cols / 2; }   // hi, lo, sx, sm, s16
 __host__ __device__ inline int gemv_fixed_smem(int cols) { return (SM_X + gemv_x_bytes(cols) + 127) & ~127; }

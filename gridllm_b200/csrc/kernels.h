@@ -12,7 +12,7 @@ struct StepState;
 
 // consumer warps per CTA: a launch-time choice among the compiled variants {8, 12, 16}
 inline int gemv_threads(int consumer_warps) { return (consumer_warps + 1) * 32; }
-constexpr int RING_MAX_SLOTS = 24;
+constexpr int RING_MAX_SLOTS = 36;
 constexpr int GEMV_MIN_SLOT_BYTES = 9216;   // four Q4_K row segments of 16 blocks
 constexpr int KV_PAGE_TOKENS = 16;
 

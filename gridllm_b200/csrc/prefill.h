@@ -31,7 +31,11 @@ struct GemmParams {
 };
 
 cudaError_t prefill_configure();   // per device: opt in to the GEMM's dynamic shared memory
-cudaError_t gemm_tn_launch(const GemmParams& p, bool bf16, cudaStream_t s);
+cudaError_t gemm_tn_launch(const GemmParams& p, bool bf16, cudaStream_t s);      // mma.sync path (batched attention GEMMs)
+// tcgen05 / TMEM / TMA path (prefill_tc5.cu) for the plain linear layers; a_rows_alloc = rows of A that exist in memory
+cudaError_t gemm_tc5_configure();
+bool gemm_tc5_supported(const GemmParams& p);
+cudaError_t gemm_tc5_launch(const GemmParams& p, int a_rows_alloc, bool bf16, cudaStream_t s);
 cudaError_t dequant_rows_launch(const uint8_t* src, int type, int rows, int cols, int row_stride, int tile_rows, void* dst, int dst_ld, int dst_row0,
                                 int interleave, bool bf16, cudaStream_t s);
 cudaError_t rmsnorm_rows_launch(const float* x, const float* w, int rows, int rows_pad, int n, float eps, void* y, bool bf16, cudaStream_t s);

@@ -1,0 +1,285 @@
+// Batched-prefill linear layers on the 5th-generation tensor cores: C[M x N] = A[M x K] * B[N x K]^T, 16-bit inputs,
+// fp32 accumulation in TENSOR MEMORY.  This is the one place on the hot path where the work is a true dense
+// contraction (north_star): the prompt's [T x n_embd] activations against each resident 16-bit weight matrix.
+// Reference call site: the prompt-evaluation phase inside Ollama behind OllamaService.generate*Response /
+// generateEmbedding (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237, 633-636).
+//
+// Shape of the kernel (one 128 x 128 output tile per CTA, 6 warps, everything asynchronous, hand-written PTX):
+//   warp 0 / one lane : TMA producer -- cp.async.bulk.tensor.2d of a 128 x 64 A box and a 128 x 64 B box per K-step
+//                       into a 6-stage mbarrier ring (128-byte swizzle, 32 KB per stage);
+//   warp 1 / one lane : MMA issuer   -- per stage four tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16), operands
+//                       addressed by shared-memory matrix descriptors, accumulator = 128 TMEM columns;
+//                       tcgen05.commit hands the stage back to the producer and, after the last K-step, wakes the epilogue;
+//   warps 2..5        : epilogue     -- tcgen05.ld 32 lanes x 32 columns at a time (warp w may touch TMEM lanes
+//                       32*(w%4)..), fused epilogue (fp32 store, residual add, 16-bit store, SiLU*mul), global stores.
+// SASS to look for: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "prefill.h"
+
+namespace gl {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
+constexpr int UMMA_K = 16;
+constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2, STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+constexpr int TC5_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+constexpr size_t TC5_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+struct Tc5Params {
+    CUtensorMap ta;      // A: dims {K, M_alloc}, box {64, 128}, 128-B swizzle
+    CUtensorMap tb;      // B: dims {K, N},       box {64, 128}, 128-B swizzle
+    void* c;
+    int m, n, k, ldc;
+    int epi;
+    int bf16;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc5_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void tc5_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle, rows of 64 16-bit elements (one swizzle atom = 8 rows x 128 B = 1024 B):
+// start address, stride between 8-row groups = 1024 B, descriptor version 1 (sm_100), layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp receives row (lane base + t), 32 consecutive columns
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <typename T> __device__ __forceinline__ T cvt16(float v);
+template <> __device__ __forceinline__ __half cvt16<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 32 consecutive accumulator columns of one output row -> global memory
+template <typename T>
+__device__ __forceinline__ void epilogue_row(const Tc5Params& p, int row, int col0, const uint32_t* v) {
+    if (p.epi == GEMM_EPI_SILU) {
+        // B rows are interleaved [8 gate | 8 up] at load time: columns 16g..16g+7 gate, 16g+8..16g+15 up -> hidden column 8g+j
+        T* out = reinterpret_cast<T*>(p.c) + (size_t)row * p.ldc + (col0 >> 4) * 8;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (col0 + 16 * g >= p.n) break;
+            T o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gt = __uint_as_float(v[16 * g + j]), up = __uint_as_float(v[16 * g + 8 + j]);
+                o[j] = cvt16<T>((gt / (1.0f + expf(-gt))) * up);
+            }
+            *reinterpret_cast<uint4*>(out + 8 * g) = *reinterpret_cast<const uint4*>(o);
+        }
+        return;
+    }
+    const bool full = col0 + 32 <= p.n;
+    if (p.epi == GEMM_EPI_T16) {
+        T* out = reinterpret_cast<T*>(p.c) + (size_t)row * p.ldc + col0;
+        if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                T o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = cvt16<T>(__uint_as_float(v[8 * q + j]));
+                *reinterpret_cast<uint4*>(out + 8 * q) = *reinterpret_cast<const uint4*>(o);
+            }
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.n; ++j) out[j] = cvt16<T>(__uint_as_float(v[j]));
+        }
+        return;
+    }
+    float* out = reinterpret_cast<float*>(p.c) + (size_t)row * p.ldc + col0;
+    if (full && (p.ldc & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            float4* dst = reinterpret_cast<float4*>(out) + q;
+            if (p.epi == GEMM_EPI_ADD_F32) {
+                const float4 r = *dst;
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            *dst = o;
+        }
+    } else {
+        for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
+            const float a = __uint_as_float(v[j]);
+            out[j] = p.epi == GEMM_EPI_ADD_F32 ? out[j] + a : a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ Tc5Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128-byte-swizzled tiles must sit on 1024-byte boundaries
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nk = (p.k + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.ta) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {   // one warp allocates the accumulator's TMEM columns and publishes the base address
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int st = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&empty[st], ph ^ 1u);
+                uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
+                mbar_expect_tx(&full[st], STAGE_BYTES);
+                tma_load_2d(sa, &p.ta, kb * BK, m0, &full[st]);
+                tma_load_2d(sa + TILE_A_BYTES, &p.tb, kb * BK, n0, &full[st]);
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            // instruction descriptor: D = F32, A / B = F16 or BF16, both K-major, N = 128, M = 128
+            const uint32_t fmt = p.bf16 ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&full[st], ph);
+                tc5_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advancing K inside the swizzle atom: +32 bytes = +2 in the descriptor's 16-byte address units
+                    tc5_mma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                }
+                tc5_commit(&empty[st]);                 // the stage is free once these MMAs have read it
+                if (kb == nk - 1) tc5_commit(acc_full); // ... and the accumulator is complete
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(acc_full, 0);
+        tc5_fence_after();
+        const int q = warp & 3;                      // the TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            const int col0 = n0 + c * 32;
+            if (row < p.m && col0 < p.n) {
+                if (p.bf16) epilogue_row<__nv_bfloat16>(p, row, col0, v);
+                else epilogue_row<__half>(p, row, col0, v);
+            }
+        }
+    }
+    tc5_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// rows x k 16-bit elements, row stride ld elements; box = 128 rows x 64 elements, 128-byte swizzle
+bool make_map(CUtensorMap* map, const void* base, int rows, int k, int ld, bool bf16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+cudaError_t gemm_tc5_configure() {
+    return cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC5_SMEM);
+}
+
+bool gemm_tc5_supported(const GemmParams& p) {
+    // plain (un-batched, non-causal) TN GEMMs whose rows TMA can address: 16-byte aligned bases and row strides
+    return p.batch == 1 && !p.causal_skip && !p.causal_k && (p.lda % 8) == 0 && (p.ldb % 8) == 0 && (p.k % 8) == 0 &&
+           ((uintptr_t)p.a % 16) == 0 && ((uintptr_t)p.b % 16) == 0 && (p.epi != GEMM_EPI_SILU || (p.n % 16) == 0);
+}
+
+// a_rows_alloc: rows of A that exist in memory (>= m; the scratch is padded to whole tiles and zero-filled)
+cudaError_t gemm_tc5_launch(const GemmParams& p, int a_rows_alloc, bool bf16, cudaStream_t s) {
+    if (!gemm_tc5_supported(p)) return cudaErrorInvalidValue;
+    Tc5Params tp{};
+    if (!make_map(&tp.ta, p.a, a_rows_alloc, p.k, p.lda, bf16) || !make_map(&tp.tb, p.b, p.n, p.k, p.ldb, bf16)) return cudaErrorInvalidValue;
+    tp.c = p.c; tp.m = p.m; tp.n = p.n; tp.k = p.k; tp.ldc = p.ldc; tp.epi = p.epi; tp.bf16 = bf16 ? 1 : 0;
+    const dim3 grid((unsigned)((p.n + BN - 1) / BN), (unsigned)((p.m + BM - 1) / BM));
+    gemm_tc5_kernel<<<grid, TC5_THREADS, TC5_SMEM, s>>>(tp);
+    return cudaGetLastError();
+}
+
+}  // namespace gl

@@ -236,6 +236,15 @@ int oc_threads(void) {
 #endif
 }
 
+/* bench.py picks the thread count that is fastest on the box it runs on (all logical CPUs is rarely it) */
+void oc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---- block decoders (public ggml formats) ------------------------------------------------------ */
 static void q4k_scale_min(const uint8_t* s, int j, int* sc, int* mn) {
     if (j < 4) { *sc = s[j] & 63; *mn = s[j + 4] & 63; }
