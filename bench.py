@@ -271,6 +271,10 @@ def main():
     except Exception:
         pass
 
+    def multirank_seed(r, i):
+        from gridllm_b200 import multirank
+        return multirank.request_seeds(r, i, 1)[0]
+
     def prompt_for(i):
         return np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 128000, size=N_PROMPT).astype(np.int32)
 
@@ -286,7 +290,7 @@ def main():
     prefill_ns = 0
     last = None
     for i in range(args.steps):
-        p = prompt_for(rank * 1000 + i)
+        p = prompt_for(multirank_seed(rank, i))
         t0 = time.perf_counter()
         g = eng.generate(p, num_predict=N_GEN, ignore_eos=True)
         wall_s += time.perf_counter() - t0
@@ -303,14 +307,12 @@ def main():
     # decode-step roofline (same engine, CUDA events inside the library on its own stream)
     ms_tok, nl_tok = eng.time_decode(N_PROMPT + N_GEN // 2, 32)
 
-    t = np.array([dev_ns * 1e-9, wall_s], dtype=np.float64)
-    if dist is not None:
-        tt = torch.tensor(t, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t = tt.cpu().numpy()
-    total_tokens = gen_tokens * world
-    value = total_tokens / t[0]
-    e2e_v = total_tokens / t[1]
+    from gridllm_b200 import multirank
+    agg = multirank.aggregate_throughput(float(gen_tokens), dev_ns * 1e-9, wall_s, dist)      # sum of tokens / max of times
+    t = [agg["device_s"], agg["wall_s"]]
+    total_tokens = agg["tokens"]
+    value = agg["value"]
+    e2e_v = agg["e2e"]
 
     if rank == 0:
         bpt = int(info.decode_bytes_per_token)
