@@ -3,11 +3,12 @@
 // Stands in for the attention inside Ollama's decode step, reached in the reference only through
 // OllamaService.generate*Response (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237).
 // Bound: HBM (KV pages) in principle, latency in practice at the 512+128-token workloads of BASELINE.json (2.6 MB
-// of KV per layer), so everything is arranged to shorten the dependent chain: one launch; all pages of a split
-// (<= 4) staged at once with 1-D TMA bulk copies (a 16-token page of one KV head is one contiguous block); 16
-// independent dot/shuffle chains per page; partials merged by the last CTA of each KV head (atomic ticket) with
-// batched loads -- no second kernel.  The grid is fixed (it lives in a CUDA graph) but the number of splits that take
-// part is chosen from the context length at run time -- one page per split at least: surplus CTAs leave at once,
+// of KV per layer), so everything is arranged to shorten the dependent chain: one launch; split s owns pages s, s+S,
+// ... (independent of the context length), so the pages that are already final are staged with 1-D TMA bulk copies
+// BEFORE griddepcontrol.wait, while the QKV GEMV that appends the newest row is still running (a 16-token page of one
+// KV head is one contiguous 4 KB block); after the wait only the page holding the newest rows is fetched; per page a
+// transposing 16-shuffle score reduction; partials merged by the last CTA of each KV head (atomic ticket) with
+// batched loads -- no second kernel.  The grid is fixed (it lives in a CUDA graph); surplus splits leave at once,
 // and a context of one page is written straight to the output without partials, ticket or merge.
 #include "attn_core.cuh"
 
@@ -22,6 +23,7 @@ template <int DPL>   // dims per lane = head_dim / 32
 __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_constant__ AttnParams p) {
     constexpr int HD = DPL * 32;
     constexpr int PAGE_ELEMS = KV_PAGE_TOKENS * HD;
+    constexpr uint32_t PAGE_BYTES = PAGE_ELEMS * sizeof(__half);
     __shared__ __align__(128) __half ks[TILE_PAGES * PAGE_ELEMS];
     __shared__ __align__(128) __half vs[TILE_PAGES * PAGE_ELEMS];
     __shared__ __align__(8) uint64_t bar;
@@ -31,6 +33,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = p.n_head / p.n_kv_heads;
     const int head = kvh * grp + warp;
+    const int S = p.n_splits;
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -38,13 +41,33 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     }
     __syncthreads();
     pdl_launch_dependents();
+
+    // Split s owns pages s, s + S, s + 2S, ... -- a mapping that does not depend on the context length, so the pages
+    // that are already FINAL can be requested before the upstream kernel (this layer's QKV GEMV, which appends the
+    // newest row) has finished: the position counter only grows inside a sequence, so any value read here is a lower
+    // bound, and a page whose 16 rows all lie below it was completed by earlier steps.
+    const int pos_lb = __ldcg(&p.st->pos);
+    const int final_pages = pos_lb / KV_PAGE_TOKENS;
+    int npre = 0;
+    if (split < final_pages) npre = min(TILE_PAGES, (final_pages - split + S - 1) / S);
+    auto stage = [&](int slot, int pg) {          // one lane: page table entry -> two bulk copies
+        const int page = __ldcg(p.page_table + pg);
+        const size_t off = ((size_t)page * p.n_kv_heads + kvh) * PAGE_ELEMS;
+        tma_load_1d(ks + slot * PAGE_ELEMS, p.k_cache + off, PAGE_BYTES, &bar);
+        tma_load_1d(vs + slot * PAGE_ELEMS, p.v_cache + off, PAGE_BYTES, &bar);
+    };
+    if (warp == 0 && npre > 0) {
+        if (lane == 0) mbar_expect_tx(&bar, 2u * npre * PAGE_BYTES);
+        __syncwarp();
+        if (lane < npre) stage(lane, split + lane * S);
+    }
     pdl_wait();
 
     const int L = __ldcg(&p.st->pos) + 1;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
-    const int active = min(n_pages, p.n_splits);
-    if (split >= active) return;
-    const int pg0 = (split * n_pages) / active, pg1 = ((split + 1) * n_pages) / active;
+    const int active = min(n_pages, S);
+    if (split >= active) return;                    // (then nothing was staged either: final_pages <= n_pages)
+    const int my_pages = (n_pages - split + S - 1) / S;
 
     float q[DPL], o[DPL];
     {
@@ -54,20 +77,22 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     }
     float m_run = -INFINITY, l_run = 0.f;
     uint32_t ph = 0;
-    for (int t0 = pg0; t0 < pg1; t0 += TILE_PAGES) {
-        const int np = min(TILE_PAGES, pg1 - t0);
-        if (threadIdx.x == 0) {
-            const uint32_t page_bytes = PAGE_ELEMS * sizeof(__half);
-            mbar_expect_tx(&bar, 2u * np * page_bytes);
-            for (int i = 0; i < np; ++i) {
-                const int page = __ldcg(p.page_table + t0 + i);
-                const size_t off = ((size_t)page * p.n_kv_heads + kvh) * PAGE_ELEMS;
-                tma_load_1d(ks + i * PAGE_ELEMS, p.k_cache + off, page_bytes, &bar);
-                tma_load_1d(vs + i * PAGE_ELEMS, p.v_cache + off, page_bytes, &bar);
+    for (int t0 = 0; t0 < my_pages; t0 += TILE_PAGES) {
+        const int np = min(TILE_PAGES, my_pages - t0);
+        const int have = t0 == 0 ? npre : 0;        // pages of this tile already requested before the wait
+        if (have > 0) { mbar_wait(&bar, ph); ph ^= 1; }
+        if (np > have) {                            // the rest: the page holding the newest rows (and long contexts)
+            // every thread must have seen the previous phase complete before the barrier is armed again: a straggler
+            // that still waits for parity p when phase p+1 completes would wait for ever (parity aliasing)
+            if (have > 0) __syncthreads();
+            if (warp == 0) {
+                if (lane == 0) mbar_expect_tx(&bar, 2u * (np - have) * PAGE_BYTES);
+                __syncwarp();
+                if (lane >= have && lane < np) stage(lane, split + (t0 + lane) * S);
             }
+            mbar_wait(&bar, ph);
+            ph ^= 1;
         }
-        mbar_wait(&bar, ph);
-        ph ^= 1;
         for (int i = 0; i < np; ++i) {
             uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
             const __half* kb = ks + i * PAGE_ELEMS + lane * DPL;
@@ -82,9 +107,10 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
                     vv[j] = make_uint2(*reinterpret_cast<const unsigned*>(vb + j * HD), 0u);
                 }
             }
-            attn_page_math<DPL>(kk, vv, min(KV_PAGE_TOKENS, L - (t0 + i) * KV_PAGE_TOKENS), q, o, m_run, l_run);
+            const int pg = split + (t0 + i) * S;
+            attn_page_math<DPL>(kk, vv, min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
         }
-        if (t0 + TILE_PAGES < pg1) __syncthreads();   // tile buffers are re-filled by the next TMA
+        if (t0 + TILE_PAGES < my_pages) __syncthreads();   // tile buffers are re-filled by the next TMA
     }
 
     if (active == 1) {

@@ -6,42 +6,75 @@
 namespace gl {
 
 // One 16-token page against one query head.  kk / vv hold this lane's DPL dims of the 16 K / V rows (8 B each for
-// head_dim 128); the 16 positions are 16 independent dot + shuffle-reduce chains, then one online-softmax update.
+// head_dim 128).  The 16 per-lane partial dots are reduced with a TRANSPOSING butterfly (8 + 4 + 2 + 1 + 1 = 16 shuffles
+// instead of 16 x 5): afterwards lanes 2p and 2p+1 hold the score of position p, so the exponential is evaluated once
+// per lane; max and sum take 4 shuffles each and the 16 weights are broadcast for the P V update (16 shuffles).
 template <int DPL>
 __device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv, int npos, const float* q, float* o, float& m_run, float& l_run) {
-    float sc[KV_PAGE_TOKENS];
+    static_assert(KV_PAGE_TOKENS == 16, "the butterfly below is written for 16 positions per page");
+    const int lane = threadIdx.x & 31;
+    float a[KV_PAGE_TOKENS];
 #pragma unroll
     for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
         const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].x));
-        float a = q[0] * k0.x + q[1] * k0.y;
+        float t = q[0] * k0.x + q[1] * k0.y;
         if (DPL == 4) {
             const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk[j].y));
-            a += q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
+            t += q[DPL - 2] * k1.x + q[DPL - 1] * k1.y;
         }
-        sc[j] = a;
+        a[j] = t;
     }
-    float m_t = -INFINITY;
+    // after step with xor w, a lane keeps the half of its values selected by its bit w and adds the partner's
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float b[8], c[4], d[2];
 #pragma unroll
-    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-        sc[j] = warp_sum(sc[j]);
-        if (j < npos) m_t = fmaxf(m_t, sc[j]);
+    for (int i = 0; i < 8; ++i) {
+        const float send = b4 ? a[i] : a[i + 8], keep = b4 ? a[i + 8] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
-    const float m_new = fmaxf(m_run, m_t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b3 ? b[i] : b[i + 4], keep = b3 ? b[i + 4] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b2 ? c[i] : c[i + 2], keep = b2 ? c[i + 2] : c[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float s;
+    {
+        const float send = b1 ? d[0] : d[1], keep = b1 ? d[1] : d[0];
+        s = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);          // score of position (lane >> 1), held by both lanes of the pair
+    const int pj = lane >> 1;
+    if (pj >= npos) s = -INFINITY;
+    float m_t = s;
+    m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, 2));
+    m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, 4));
+    m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, 8));
+    m_t = fmaxf(m_t, __shfl_xor_sync(0xffffffffu, m_t, 16));
+    const float m_new = fmaxf(m_run, m_t);             // npos >= 1, so m_new is finite
     const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-    l_run *= corr;
+    const float w = (pj < npos) ? expf(s - m_new) : 0.f;
+    float ws = w;
+    ws += __shfl_xor_sync(0xffffffffu, ws, 2);
+    ws += __shfl_xor_sync(0xffffffffu, ws, 4);
+    ws += __shfl_xor_sync(0xffffffffu, ws, 8);
+    ws += __shfl_xor_sync(0xffffffffu, ws, 16);        // every position once (the xor-1 partner holds the duplicate)
+    l_run = l_run * corr + ws;
 #pragma unroll
-    for (int d = 0; d < DPL; ++d) o[d] *= corr;
+    for (int dd = 0; dd < DPL; ++dd) o[dd] *= corr;
 #pragma unroll
     for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-        if (j < npos) {
-            const float w = expf(sc[j] - m_new);
-            l_run += w;
-            const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
-            o[0] += w * v0.x; o[1] += w * v0.y;
-            if (DPL == 4) {
-                const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
-                o[DPL - 2] += w * v1.x; o[DPL - 1] += w * v1.y;
-            }
+        if (j >= npos) break;                                      // warp-uniform; rows beyond npos may hold anything
+        const float wj = __shfl_sync(0xffffffffu, w, 2 * j);
+        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
+        o[0] += wj * v0.x; o[1] += wj * v0.y;
+        if (DPL == 4) {
+            const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
+            o[DPL - 2] += wj * v1.x; o[DPL - 1] += wj * v1.y;
         }
     }
     m_run = m_new;
@@ -65,10 +98,11 @@ __device__ __forceinline__ void attn_merge_head(const float* part_o, const float
 #pragma unroll
     for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
     float M = 0.f, wl = 0.f, den = 0.f;
-    for (int s0 = 0; s0 < n_splits; s0 += 8) {
-        float po[8][DPL];
+    constexpr int MB = 16;      // partials per batch: one L2 round trip each
+    for (int s0 = 0; s0 < n_splits; s0 += MB) {
+        float po[MB][DPL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < MB; ++i) {
 #pragma unroll
             for (int d = 0; d < DPL; ++d) po[i][d] = (s0 + i < n_splits) ? __ldcg(pbase + (size_t)(s0 + i) * HD + d) : 0.f;
         }
@@ -78,7 +112,7 @@ __device__ __forceinline__ void attn_merge_head(const float* part_o, const float
             den = warp_sum(wl * ls);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < MB; ++i) {
             const float w = __shfl_sync(0xffffffffu, wl, (s0 + i) & 31);
             if (s0 + i < n_splits) {
 #pragma unroll

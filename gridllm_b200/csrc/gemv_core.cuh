@@ -175,10 +175,9 @@ __device__ __forceinline__ void gemv_prologue_static(const GemvParams& p, int ti
     }
 }
 
-template <int ABITS, int NW>
-__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps) {
+template <int ABITS, int NW, int NB>
+__device__ __forceinline__ float gemv_prologue_nb(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps) {
     constexpr int NT = NW * 32;
-    constexpr int NB = PROLOGUE_NB;
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -207,7 +206,7 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
                 const int f = f0 + i * NT;
-                if (f0 == tid) wv[i] = ps.wv[i];          // first batch: requested before the upstream wait
+                if (f0 == tid && i < PROLOGUE_NB) wv[i] = ps.wv[i < PROLOGUE_NB ? i : 0];      // first batch: requested before the upstream wait
                 else if (f < nf) wv[i] = __ldg(w4 + f);
             }
         }
@@ -259,6 +258,13 @@ __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* sme
     // NOTE: the planes (and red[]) are rewritten only by the NEXT prologue, which every caller separates from this
     // point by a CTA-wide barrier (end of kernel, or the grid barrier of the persistent kernel).
     return scale;
+}
+
+// Wide rows without RMSNorm (ffn_down: K = 14336, 9-14 float4 per thread) take all their loads in ONE round trip.
+template <int ABITS, int NW>
+__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps) {
+    if (p.norm_w == nullptr && p.cols > 8192) return gemv_prologue_nb<ABITS, NW, 2 * PROLOGUE_NB>(p, smem, tid, ps);
+    return gemv_prologue_nb<ABITS, NW, PROLOGUE_NB>(p, smem, tid, ps);
 }
 
 // reduce four per-lane partials over the warp with 6 shuffles.  On return, lane L holds the warp total of row

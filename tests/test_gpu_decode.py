@@ -197,6 +197,27 @@ def test_generate_with_batched_prefill(tiny128_gguf):
     e.close()
 
 
+def test_long_context_decode(tiny128_gguf):
+    """contexts beyond 512 tokens: more KV pages than attention splits, so a split owns a final page AND the page that
+    holds the newest rows (two staging batches), splits own several pages, and the merge covers all 32 partials"""
+    from oracle import llama_oracle as O
+    m = O.load_gguf(tiny128_gguf)
+    e = _engine(tiny128_gguf, max_ctx=1024)
+    orc = O.LlamaOracle(m, act="exact", kv_f16=True)
+    prompt = np.random.Generator(np.random.PCG64(77)).integers(0, m.n_vocab - 3, size=530)
+    ref = orc.generate(prompt, 40)
+    g = e.generate(prompt, num_predict=40, ignore_eos=True, want_logits=True)
+    assert g.stats.eval_count == 40 and g.stats.prompt_eval_count == 530
+    for i in range(40):
+        lg = e.last_logits(i)
+        assert np.isfinite(lg).all()
+        assert np.abs(lg - ref["logits"][i]).max() <= 1e-2 * np.abs(ref["logits"][i]).max(), i
+        if g.ids[i] != ref["ids"][i]:
+            assert ref["margins"][i] <= 5e-2
+            break
+    e.close()
+
+
 @pytest.mark.parametrize("abits,warps,mega", [(16, 8, 1), (8, 8, 1), (16, 8, 0), (8, 8, 0), (16, 1, 0)])
 def test_kernel_variants_match_oracle(tiny128_gguf, tiny_q8_gguf, abits, warps, mega, monkeypatch):
     if warps == 1:          # one CTA per SM with large stages instead of two with small ones
