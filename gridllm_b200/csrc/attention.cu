@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
+    unsigned long long* tr = nullptr;
+    if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tr = p.trace + (blockIdx.x == 0 ? 0 : 4);
+    if (tr) tr[0] = globaltimer_ns();
     __syncthreads();
     pdl_launch_dependents();
 
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
         if (lane < npre) stage(lane, split + lane * S);
     }
     pdl_wait();
+    if (tr) tr[1] = globaltimer_ns();
 
     const int L = __ldcg(&p.st->pos) + 1;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
         if (t0 + TILE_PAGES < my_pages) __syncthreads();   // tile buffers are re-filled by the next TMA
     }
 
+    if (tr) tr[2] = globaltimer_ns();
     if (active == 1) {
         const float inv = 1.0f / l_run;
         float* out = p.out + (size_t)head * HD + lane * DPL;
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     __syncthreads();
     if (!is_last) return;
     attn_merge_head<DPL>(p.part_o, p.part_ml, p.out, head, p.n_splits, active, lane);
+    if (tr) tr[3] = globaltimer_ns();
 }
 
 }  // namespace

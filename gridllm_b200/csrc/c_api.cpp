@@ -157,4 +157,10 @@ int gl_debug_mega_trace(gl_engine* e, unsigned long long* out, int32_t cap, int3
     return ret(e->impl->mega_trace(out, cap, n_ctas, n_phases));
 }
 
+// profiling aid: %globaltimer stamps of every GEMV / attention launch of the last decode step (GL_TRACE=1)
+int gl_debug_perop_trace(gl_engine* e, unsigned long long* out, int32_t cap, int32_t* n_launches) {
+    if (!e || !out || !n_launches) return bad("gl_debug_perop_trace: null argument");
+    return ret(e->impl->perop_trace(out, cap, n_launches));
+}
+
 }  // extern "C"

@@ -63,6 +63,7 @@ public:
     Status prefill(const int32_t* ids, int n, float* last_logits);
     Status time_decode(int ctx_len, int iters, float* ms, int* launches);
     Status mega_trace(unsigned long long* out, int cap, int* n_ctas, int* n_phases);
+    Status perop_trace(unsigned long long* out, int cap, int* n_launches);
     int position() const { return host_pos_; }
     const Tokenizer& tokenizer() const { return tok_; }
 
@@ -125,6 +126,8 @@ private:
     int mega_launches_ = 0;
     int mega_splits_ = 16;
     unsigned long long* mega_trace_ = nullptr;
+    static constexpr int PEROP_TRACE_LAUNCHES = 512;
+    unsigned long long* perop_trace_ = nullptr;    // GL_TRACE=1: [launch of the step][first / last CTA][4] %globaltimer stamps
     std::vector<ProdDesc> mega_prod_;
 
     // device state

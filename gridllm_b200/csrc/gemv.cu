@@ -34,19 +34,27 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     __syncthreads();
     pdl_launch_dependents();
 
+    // optional device-side timeline (GL_TRACE=1): entry / upstream wait over / planes ready / this warp's items done,
+    // for the first and the last CTA of the grid
+    unsigned long long* tr = nullptr;
+    if (p.trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tr = p.trace + (blockIdx.x == 0 ? 0 : 4);
+    if (tr) tr[0] = globaltimer_ns();
     if (warp == NW) {
         // producer: weights are static, so streaming starts before the upstream kernel has finished
-        Track tr{0u, 0u};
-        gemv_produce(p.pd, ring, tr, lane, blockIdx.x, gridDim.x);
+        Track trk{0u, 0u};
+        gemv_produce(p.pd, ring, trk, lane, blockIdx.x, gridDim.x);
         return;
     }
     PrologueStatic ps;
     gemv_prologue_static<NW>(p, tid, ps);     // RMSNorm weights: static, requested while the upstream kernel drains
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
+    if (tr) tr[1] = globaltimer_ns();
     const EpiCtx ec = load_epi_ctx(p);
     const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps);
-    Track tr{0u, 0u};
-    gemv_consume<ABITS>(p, ring, tr, smem, tid, scale, ec, blockIdx.x, gridDim.x);
+    if (tr) tr[2] = globaltimer_ns();
+    Track trk{0u, 0u};
+    gemv_consume<ABITS>(p, ring, trk, smem, tid, scale, ec, blockIdx.x, gridDim.x);
+    if (tr) tr[3] = globaltimer_ns();
 }
 
 }  // namespace
