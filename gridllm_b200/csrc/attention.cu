@@ -20,7 +20,7 @@ constexpr int TILE_PAGES = 4;
 constexpr int MAX_GRP = 8;
 
 template <int DPL>   // dims per lane = head_dim / 32
-__global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __maxnreg__(96) attn_decode_kernel(const __grid_constant__ AttnParams p) {
     constexpr int HD = DPL * 32;
     constexpr int PAGE_ELEMS = KV_PAGE_TOKENS * HD;
     constexpr uint32_t PAGE_BYTES = PAGE_ELEMS * sizeof(__half);
@@ -98,21 +98,9 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
             ph ^= 1;
         }
         for (int i = 0; i < np; ++i) {
-            uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
-            const __half* kb = ks + i * PAGE_ELEMS + lane * DPL;
-            const __half* vb = vs + i * PAGE_ELEMS + lane * DPL;
-#pragma unroll
-            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
-                if (DPL == 4) {
-                    kk[j] = *reinterpret_cast<const uint2*>(kb + j * HD);
-                    vv[j] = *reinterpret_cast<const uint2*>(vb + j * HD);
-                } else {
-                    kk[j] = make_uint2(*reinterpret_cast<const unsigned*>(kb + j * HD), 0u);
-                    vv[j] = make_uint2(*reinterpret_cast<const unsigned*>(vb + j * HD), 0u);
-                }
-            }
             const int pg = split + (t0 + i) * S;
-            attn_page_math<DPL>(kk, vv, min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
+            attn_page_math_smem<DPL>(ks + i * PAGE_ELEMS + lane * DPL, vs + i * PAGE_ELEMS + lane * DPL,
+                                     min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
         }
         if (t0 + TILE_PAGES < my_pages) __syncthreads();   // tile buffers are re-filled by the next TMA
     }

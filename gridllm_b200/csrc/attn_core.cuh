@@ -5,12 +5,10 @@
 
 namespace gl {
 
-// One 16-token page against one query head.  kk / vv hold this lane's DPL dims of the 16 K / V rows (8 B each for
-// head_dim 128).  The 16 per-lane partial dots are reduced with a TRANSPOSING butterfly (8 + 4 + 2 + 1 + 1 = 16 shuffles
-// instead of 16 x 5): afterwards lanes 2p and 2p+1 hold the score of position p, so the exponential is evaluated once
-// per lane; max and sum take 4 shuffles each and the 16 weights are broadcast for the P V update (16 shuffles).
+// scores of one page: returns this lane's softmax weight w (for position lane >> 1) after updating (m_run, l_run) and
+// rescaling o; kk = this lane's DPL dims of the 16 K rows
 template <int DPL>
-__device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv, int npos, const float* q, float* o, float& m_run, float& l_run) {
+__device__ __forceinline__ float attn_page_scores(const uint2* kk, int npos, const float* q, float* o, float& m_run, float& l_run) {
     static_assert(KV_PAGE_TOKENS == 16, "the butterfly below is written for 16 positions per page");
     const int lane = threadIdx.x & 31;
     float a[KV_PAGE_TOKENS];
@@ -24,7 +22,7 @@ __device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv,
         }
         a[j] = t;
     }
-    // after step with xor w, a lane keeps the half of its values selected by its bit w and adds the partner's
+    // after the step with xor w, a lane keeps the half of its values selected by its bit w and adds the partner's
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     float b[8], c[4], d[2];
 #pragma unroll
@@ -66,18 +64,57 @@ __device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv,
     l_run = l_run * corr + ws;
 #pragma unroll
     for (int dd = 0; dd < DPL; ++dd) o[dd] *= corr;
+    m_run = m_new;
+    return w;
+}
+
+// o += w_j * V_j for one row: the weight of position j is broadcast from the lane pair that holds it
+template <int DPL>
+__device__ __forceinline__ void attn_pv_row(float w, int j, uint2 vrow, float* o) {
+    const float wj = __shfl_sync(0xffffffffu, w, 2 * j);
+    const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vrow.x));
+    o[0] += wj * v0.x; o[1] += wj * v0.y;
+    if (DPL == 4) {
+        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vrow.y));
+        o[DPL - 2] += wj * v1.x; o[DPL - 1] += wj * v1.y;
+    }
+}
+
+// One 16-token page against one query head.  kk / vv hold this lane's DPL dims of the 16 K / V rows (8 B each for
+// head_dim 128).  The 16 per-lane partial dots are reduced with a TRANSPOSING butterfly (8 + 4 + 2 + 1 + 1 = 16 shuffles
+// instead of 16 x 5): afterwards lanes 2p and 2p+1 hold the score of position p, so the exponential is evaluated once
+// per lane; max and sum take 4 shuffles each and the 16 weights are broadcast for the P V update (16 shuffles).
+template <int DPL>
+__device__ __forceinline__ void attn_page_math(const uint2* kk, const uint2* vv, int npos, const float* q, float* o, float& m_run, float& l_run) {
+    const float w = attn_page_scores<DPL>(kk, npos, q, o, m_run, l_run);
 #pragma unroll
     for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
         if (j >= npos) break;                                      // warp-uniform; rows beyond npos may hold anything
-        const float wj = __shfl_sync(0xffffffffu, w, 2 * j);
-        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].x));
-        o[0] += wj * v0.x; o[1] += wj * v0.y;
-        if (DPL == 4) {
-            const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[j].y));
-            o[DPL - 2] += wj * v1.x; o[DPL - 1] += wj * v1.y;
-        }
+        attn_pv_row<DPL>(w, j, vv[j], o);
     }
-    m_run = m_new;
+}
+
+// the same with the page staged in shared memory: K rows are read for the scores, V rows only afterwards (fewer live
+// registers, which is what lets an attention CTA share an SM with the GEMV kernels around it)
+template <int DPL>
+__device__ __forceinline__ void attn_page_math_smem(const __half* kb, const __half* vb, int npos, const float* q, float* o, float& m_run,
+                                                    float& l_run) {
+    constexpr int HD = DPL * 32;
+    uint2 kk[KV_PAGE_TOKENS];
+#pragma unroll
+    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+        if (DPL == 4) kk[j] = *reinterpret_cast<const uint2*>(kb + j * HD);
+        else kk[j] = make_uint2(*reinterpret_cast<const unsigned*>(kb + j * HD), 0u);
+    }
+    const float w = attn_page_scores<DPL>(kk, npos, q, o, m_run, l_run);
+#pragma unroll
+    for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+        if (j >= npos) break;
+        uint2 v;
+        if (DPL == 4) v = *reinterpret_cast<const uint2*>(vb + j * HD);
+        else v = make_uint2(*reinterpret_cast<const unsigned*>(vb + j * HD), 0u);
+        attn_pv_row<DPL>(w, j, v, o);
+    }
 }
 
 

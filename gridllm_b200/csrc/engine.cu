@@ -166,6 +166,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     ring_depth_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH", 2)));          // persistent kernel
     ring_depth_max_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH_MAX", 3)));   // stand-alone kernels: up to this many slots per warp
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
+    lean_rings_ = env_int("GL_LEAN_RINGS", 1) != 0;
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -407,6 +408,14 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
     // as many consumer warps as there are, each with >= 2 slots; spare slots deepen the tracks (small slots: more bytes in flight)
     p.n_tracks = std::min(nw_, ns / 2);
     p.depth = p.n_tracks > 0 ? std::min(ring_depth_max_, ns / p.n_tracks) : 0;
+    // a phase in which no warp gets a second slot (one round of items, one K-segment) needs one slot per warp: the smaller
+    // footprint (121 KB instead of 232 KB) lets the next kernel's CTAs become resident -- and start their own prefetch --
+    // while this one is still running (programmatic dependent launch)
+    if (lean_rings_ && p.n_tracks > 0 && p.pd.nks == 1) {
+        int items = 0;
+        for (int i = 0; i < (pair ? 1 : nmat); ++i) items += p.pd.seg[i].n_items;
+        if ((items + sm_count_ - 1) / sm_count_ <= p.n_tracks) p.depth = 1;
+    }
     if (p.n_tracks < 1) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
     p.trace = perop_trace_ ? perop_trace_ + 8 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;
     CU(gemv_launch(p, abits_, nw_, sm_count_, use_pdl_, s));
@@ -824,52 +833,61 @@ Status Engine::embed(const int32_t* ids, const int32_t* offs, int n_seq, float* 
     CU(cudaSetDevice(device_));
     const int64_t t0 = now_ns();
     int total = 0, launches = 0;
-    std::vector<float> hid(n_embd_), nw(n_embd_);
-    CU(cudaMemcpy(nw.data(), output_norm_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost));
+    // pooling runs on the device (misc.cu): hidden rows -> output_norm -> mean over positions -> L2 normalise
+    int max_n = 0;
+    for (int sidx = 0; sidx < n_seq; ++sidx) max_n = std::max(max_n, offs[sidx + 1] - offs[sidx]);
+    if (max_n <= 0) return fail(GL_ERR_INVALID, "empty sequence in gl_embed");
+    float *d_rows = nullptr, *d_rstd = nullptr, *d_pooled = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_rstd); cudaFree(d_pooled); cudaFree(d_out); };
+    cudaError_t ae = cudaMalloc((void**)&d_rstd, (size_t)max_n * 4);
+    if (ae == cudaSuccess) ae = cudaMalloc((void**)&d_pooled, (size_t)n_embd_ * 4);
+    if (ae == cudaSuccess) ae = cudaMalloc((void**)&d_out, (size_t)n_seq * n_embd_ * 4);
+    if (ae != cudaSuccess) { cleanup(); CU(ae); }
     CU(cudaEventRecord(ev_[0], stream_));
     for (int sidx = 0; sidx < n_seq; ++sidx) {
         const int n = offs[sidx + 1] - offs[sidx];
-        if (n <= 0) return fail(GL_ERR_INVALID, "empty sequence in gl_embed");
+        if (n <= 0) { cleanup(); return fail(GL_ERR_INVALID, "empty sequence in gl_embed"); }
         const int32_t* sid = ids + offs[sidx];
         for (int i = 0; i < n; ++i)
-            if (sid[i] < 0 || sid[i] >= n_vocab_) return fail(GL_ERR_INVALID, "token id out of range");
-        ST(kv_reset());
-        ST(ensure_pages(n));
-        CU(cudaMemcpyAsync(prompt_ids_, sid, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+            if (sid[i] < 0 || sid[i] >= n_vocab_) { cleanup(); return fail(GL_ERR_INVALID, "token id out of range"); }
+        Status st = kv_reset();
+        if (st.ok()) st = ensure_pages(n);
+        if (!st.ok()) { cleanup(); return st; }
+        cudaMemcpyAsync(prompt_ids_, sid, (size_t)n * 4, cudaMemcpyHostToDevice, stream_);
         gl_sample_opts so{};
         so.ignore_eos = 1;
-        ST(set_state(0, sid[0], n, 0, &so));
-        // mean pooling of output_norm(hidden) over positions, accumulated on the host in double
-        std::vector<double> acc(n_embd_, 0.0);
-        auto pool_row = [&](const float* hrow) {
-            double ss = 0;
-            for (int d = 0; d < n_embd_; ++d) ss += (double)hrow[d] * hrow[d];
-            const double rstd = 1.0 / std::sqrt(ss / n_embd_ + (double)eps_);
-            for (int d = 0; d < n_embd_; ++d) acc[d] += hrow[d] * rstd * nw[d];
-        };
+        st = set_state(0, sid[0], n, 0, &so);
+        if (!st.ok()) { cleanup(); return st; }
+        const float* rows = nullptr;
         if (can_batch_prefill(n)) {
             int nl = 0;
-            ST(prefill_batched(n, &nl));
+            st = prefill_batched(n, &nl);
+            if (!st.ok()) { cleanup(); return st; }
             launches += nl;
-            std::vector<float> all((size_t)n * n_embd_);
-            CU(cudaMemcpyAsync(all.data(), pf_x_, all.size() * 4, cudaMemcpyDeviceToHost, stream_));
-            CU(cudaStreamSynchronize(stream_));
-            for (int i = 0; i < n; ++i) pool_row(all.data() + (size_t)i * n_embd_);
+            rows = pf_x_;                              // [n x n_embd] hidden states of the whole prompt
         } else {
+            // sequential prefill through the decode kernels: keep every position's hidden state
+            if (!d_rows) {
+                ae = cudaMalloc((void**)&d_rows, (size_t)max_n * n_embd_ * 4);
+                if (ae != cudaSuccess) { cleanup(); CU(ae); }
+            }
             for (int i = 0; i < n; ++i) {
-                ST(run_steps(1, 0, false));
-                CU(cudaMemcpyAsync(hid.data(), x_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToHost, stream_));
-                CU(cudaStreamSynchronize(stream_));
-                pool_row(hid.data());
+                st = run_steps(1, 0, false);
+                if (!st.ok()) { cleanup(); return st; }
+                cudaMemcpyAsync(d_rows + (size_t)i * n_embd_, x_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToDevice, stream_);
             }
             launches += n * launches_nohead_;
+            rows = d_rows;
         }
-        double nrm = 0;
-        for (int d = 0; d < n_embd_; ++d) { acc[d] /= n; nrm += acc[d] * acc[d]; }
-        nrm = std::max(std::sqrt(nrm), 1e-12);
-        for (int d = 0; d < n_embd_; ++d) out[(size_t)sidx * n_embd_ + d] = (float)(acc[d] / nrm);
+        ae = pool_embedding_launch(rows, n, n_embd_, output_norm_, eps_, d_rstd, d_pooled, d_out + (size_t)sidx * n_embd_, stream_);
+        if (ae != cudaSuccess) { cleanup(); CU(ae); }
+        launches += 3;
         total += n;
     }
+    ae = cudaMemcpyAsync(out, d_out, (size_t)n_seq * n_embd_ * 4, cudaMemcpyDeviceToHost, stream_);
+    if (ae == cudaSuccess) ae = cudaStreamSynchronize(stream_);
+    cleanup();
+    CU(ae);
     CU(cudaEventRecord(ev_[1], stream_));
     CU(cudaEventSynchronize(ev_[1]));
     if (stats) {

@@ -121,7 +121,7 @@ cudaError_t gemv_configure() {
 }
 
 cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
-    if (!gemv_variant_ok(abits, nw) || p.n_tracks < 1 || p.n_tracks > nw || p.depth < 2 || p.n_tracks * p.depth > RING_MAX_SLOTS) return cudaErrorInvalidValue;
+    if (!gemv_variant_ok(abits, nw) || p.n_tracks < 1 || p.n_tracks > nw || p.depth < 1 || p.n_tracks * p.depth > RING_MAX_SLOTS) return cudaErrorInvalidValue;
     if (p.epi == EPI_QKV && ((p.pd.seg[0].rows & 1) || (p.pd.nseg > 1 && (p.pd.seg[1].rows & 1)))) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);

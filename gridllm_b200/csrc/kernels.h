@@ -136,6 +136,9 @@ cudaError_t rope_kv_launch(float* q, const float* k, const float* v, int n_head,
                            __half* v_cache, const int* page_table, cudaStream_t s);
 cudaError_t silu_mul_launch(const float* g, const float* u, int n, float* out, cudaStream_t s);
 cudaError_t add_launch(const float* a, const float* b, int n, float* out, cudaStream_t s);
+// generateEmbedding: out[n] = L2-normalised mean over rows of RMSNorm(h_t) * norm_w;  scratch: rstd [rows], pooled [n]
+cudaError_t pool_embedding_launch(const float* h, int rows, int n, const float* norm_w, float eps, float* rstd_scratch, float* pooled_scratch,
+                                  float* out, cudaStream_t s);
 cudaError_t l2_flush_launch(float* buf, size_t n, cudaStream_t s);
 
 }  // namespace gl

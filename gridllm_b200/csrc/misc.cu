@@ -224,6 +224,45 @@ __global__ void l2_flush_kernel(float* buf, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = buf[i] * 0.5f + 1.0f;
 }
 
+// ---- embedding pooling (generateEmbedding: prefill -> output_norm -> mean over positions -> L2 normalise) -----------
+// h [rows x n] fp32 hidden states of one sequence.  Three tiny launches, fixed summation orders (deterministic):
+//   rstd[t] = 1/sqrt(mean(h_t^2) + eps);  pooled[d] = w[d]/rows * sum_t h[t][d] * rstd[t];  out = pooled / |pooled|
+__global__ void __launch_bounds__(256) pool_rstd_kernel(const float* __restrict__ h, int rows, int n, float eps, float* __restrict__ rstd) {
+    const int t = blockIdx.x;
+    __shared__ float red[8];
+    const float* hr = h + (size_t)t * n;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) { const float v = hr[i]; ss += v * v; }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int k = 0; k < 8; ++k) tot += red[k];
+        rstd[t] = 1.0f / sqrtf(tot / (float)n + eps);
+    }
+}
+__global__ void __launch_bounds__(256) pool_cols_kernel(const float* __restrict__ h, const float* __restrict__ rstd, const float* __restrict__ w,
+                                                        int rows, int n, float* __restrict__ pooled) {
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= n) return;
+    float acc = 0.f;
+    for (int t = 0; t < rows; ++t) acc += h[(size_t)t * n + d] * rstd[t];
+    pooled[d] = acc * w[d] / (float)rows;
+}
+__global__ void __launch_bounds__(1024) pool_normalize_kernel(const float* __restrict__ pooled, int n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) ss += pooled[i] * pooled[i];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < 32; ++k) tot += red[k];
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    for (int i = threadIdx.x; i < n; i += 1024) out[i] = pooled[i] * inv;
+}
+
 template <typename... Args>
 cudaError_t launch_pdl(void (*kern)(Args...), dim3 grid, dim3 block, bool pdl, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -269,6 +308,14 @@ cudaError_t add_launch(const float* a, const float* b, int n, float* out, cudaSt
     add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, out);
     return cudaGetLastError();
 }
+cudaError_t pool_embedding_launch(const float* h, int rows, int n, const float* norm_w, float eps, float* rstd_scratch, float* pooled_scratch,
+                                  float* out, cudaStream_t s) {
+    pool_rstd_kernel<<<rows, 256, 0, s>>>(h, rows, n, eps, rstd_scratch);
+    pool_cols_kernel<<<(n + 255) / 256, 256, 0, s>>>(h, rstd_scratch, norm_w, rows, n, pooled_scratch);
+    pool_normalize_kernel<<<1, 1024, 0, s>>>(pooled_scratch, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t l2_flush_launch(float* buf, size_t n, cudaStream_t s) {
     l2_flush_kernel<<<148 * 4, 256, 0, s>>>(buf, n);
     return cudaGetLastError();

@@ -18,9 +18,9 @@ def main():
     t0 = time.time()
     info = S.build_model(path, S.LLAMA3_8B, "q4_k_m", seed=1234, mode="random", with_vocab=False)
     print("build_s", round(time.time() - t0, 1), info, flush=True)
-    cfgs = ({}, {"GL_ACT_BITS": "8"}, {"GL_MEGA": "1", "GL_WARPS": "8"})
+    cfgs = ({}, {"GL_LEAN_RINGS": "0"}, {"GL_ACT_BITS": "8"})
     for cfg in cfgs:
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_BYTES", "GL_MEGA_SLOTS", "GL_MEGA_INFLIGHT", "GL_ATTN_SPLITS", "GL_WARPS", "GL_RING_DEPTH", "GL_MEGA_TRACKS", "GL_SMEM_KB"):
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_BYTES", "GL_MEGA_SLOTS", "GL_MEGA_INFLIGHT", "GL_ATTN_SPLITS", "GL_WARPS", "GL_RING_DEPTH", "GL_MEGA_TRACKS", "GL_LEAN_RINGS", "GL_SMEM_KB"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         t0 = time.time()
@@ -29,7 +29,7 @@ def main():
         e = N.Engine(path, max_ctx=2048)
         load_s = time.time() - t0
         bpt = e.info.decode_bytes_per_token
-        for ctx in (1, 576, 2048 - 40):
+        for ctx in (1, 576):
             ms, nl = e.time_decode(ctx, 32)
             print(json.dumps({"cfg": cfg, "ctx": ctx, "ms_per_token": round(ms, 4), "tok_s": round(1000 / ms, 1), "launches": nl,
                               "weights_GBps": round(bpt / ms / 1e6, 1), "load_s": round(load_s, 1)}), flush=True)

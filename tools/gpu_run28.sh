@@ -8,3 +8,9 @@ S.build_model('/dev/shm/prof_llama3_8b.gguf', S.LLAMA3_8B, 'q4_k_m', seed=1234, 
 PY
 timeout 300 python tools/perop_trace.py 576 > gpurun_out/perop_trace.log 2>&1
 cat gpurun_out/perop_trace.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "embed or service or decode" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -n 3 gpurun_out/pytest_gpu.log
+timeout 400 python tools/bench_quick.py > gpurun_out/bench_quick.log 2>&1
+echo "bench_quick rc=$?" >> gpurun_out/bench_quick.log
+grep -h '^{' gpurun_out/bench_quick.log | sort -u | cut -c1-200; tail -n 2 gpurun_out/bench_quick.log
