@@ -20,7 +20,7 @@ constexpr int TILE_PAGES = 4;
 constexpr int MAX_GRP = 8;
 
 template <int DPL>   // dims per lane = head_dim / 32
-__global__ void __maxnreg__(96) attn_decode_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_constant__ AttnParams p) {
     constexpr int HD = DPL * 32;
     constexpr int PAGE_ELEMS = KV_PAGE_TOKENS * HD;
     constexpr uint32_t PAGE_BYTES = PAGE_ELEMS * sizeof(__half);
@@ -67,18 +67,21 @@ __global__ void __maxnreg__(96) attn_decode_kernel(const __grid_constant__ AttnP
     pdl_wait();
     if (tr) tr[1] = globaltimer_ns();
 
+    // q and the position travel together (a warp issues in order: nothing below may consume the position before q is requested)
+    float q[DPL], o[DPL];
+    {
+        const float* qp = p.q + (size_t)head * HD + lane * DPL;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) { q[d] = __ldcg(qp + d); o[d] = 0.f; }
+    }
     const int L = __ldcg(&p.st->pos) + 1;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) q[d] *= p.scale;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
     const int active = min(n_pages, S);
     if (split >= active) return;                    // (then nothing was staged either: final_pages <= n_pages)
     const int my_pages = (n_pages - split + S - 1) / S;
 
-    float q[DPL], o[DPL];
-    {
-        const float* qp = p.q + (size_t)head * HD + lane * DPL;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) { q[d] = __ldcg(qp + d) * p.scale; o[d] = 0.f; }
-    }
     float m_run = -INFINITY, l_run = 0.f;
     uint32_t ph = 0;
     for (int t0 = 0; t0 < my_pages; t0 += TILE_PAGES) {
@@ -98,9 +101,21 @@ __global__ void __maxnreg__(96) attn_decode_kernel(const __grid_constant__ AttnP
             ph ^= 1;
         }
         for (int i = 0; i < np; ++i) {
+            uint2 kk[KV_PAGE_TOKENS], vv[KV_PAGE_TOKENS];
+            const __half* kb = ks + i * PAGE_ELEMS + lane * DPL;
+            const __half* vb = vs + i * PAGE_ELEMS + lane * DPL;
+#pragma unroll
+            for (int j = 0; j < KV_PAGE_TOKENS; ++j) {
+                if (DPL == 4) {
+                    kk[j] = *reinterpret_cast<const uint2*>(kb + j * HD);
+                    vv[j] = *reinterpret_cast<const uint2*>(vb + j * HD);
+                } else {
+                    kk[j] = make_uint2(*reinterpret_cast<const unsigned*>(kb + j * HD), 0u);
+                    vv[j] = make_uint2(*reinterpret_cast<const unsigned*>(vb + j * HD), 0u);
+                }
+            }
             const int pg = split + (t0 + i) * S;
-            attn_page_math_smem<DPL>(ks + i * PAGE_ELEMS + lane * DPL, vs + i * PAGE_ELEMS + lane * DPL,
-                                     min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
+            attn_page_math<DPL>(kk, vv, min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS), q, o, m_run, l_run);
         }
         if (t0 + TILE_PAGES < my_pages) __syncthreads();   // tile buffers are re-filled by the next TMA
     }

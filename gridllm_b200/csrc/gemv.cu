@@ -49,8 +49,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     gemv_prologue_static<NW>(p, tid, ps);     // RMSNorm weights: static, requested while the upstream kernel drains
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
     if (tr) tr[1] = globaltimer_ns();
-    const EpiCtx ec = load_epi_ctx(p);
+    // the QKV epilogue needs (position, physical KV page): two DEPENDENT loads.  A warp issues in order, so the first is
+    // requested here, ahead of the prologue's x loads, and the second only after the prologue, when the first has long
+    // arrived -- neither ever stalls the instruction stream (doing both here cost the QKV prologue 1.2 us, run 28)
+    EpiCtx ec{0, 0};
+    if (p.epi == EPI_QKV) ec.pos = __ldcg(&p.st->pos);
     const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps);
+    if (p.epi == EPI_QKV) ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
     if (tr) tr[2] = globaltimer_ns();
     Track trk{0u, 0u};
     gemv_consume<ABITS>(p, ring, trk, smem, tid, scale, ec, blockIdx.x, gridDim.x);
