@@ -261,8 +261,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(dalloc((void**)&logits_, (size_t)n_vocab_ * 4));
     CU(dalloc((void**)&part_o_, (size_t)n_head_ * std::max(attn_splits_, 32) * hd_ * 4));
     if (env_int("GL_TRACE", 0)) {
-        CU(dalloc((void**)&perop_trace_, (size_t)PEROP_TRACE_LAUNCHES * 8 * 8));
-        CU(cudaMemset(perop_trace_, 0, (size_t)PEROP_TRACE_LAUNCHES * 8 * 8));
+        CU(dalloc((void**)&perop_trace_, (size_t)PEROP_TRACE_LAUNCHES * 16 * 8));
+        CU(cudaMemset(perop_trace_, 0, (size_t)PEROP_TRACE_LAUNCHES * 16 * 8));
     }
     CU(dalloc((void**)&part_ml_, (size_t)n_head_ * std::max(attn_splits_, 32) * 2 * 4));
     CU(dalloc((void**)&counters_, (size_t)n_kv_ * 4));
@@ -417,7 +417,7 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
         if ((items + sm_count_ - 1) / sm_count_ <= p.n_tracks) p.depth = 1;
     }
     if (p.n_tracks < 1) return fail(GL_ERR_UNSUPPORTED, "GEMV staging does not fit shared memory");
-    p.trace = perop_trace_ ? perop_trace_ + 8 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;
+    p.trace = perop_trace_ ? perop_trace_ + 16 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;
     CU(gemv_launch(p, abits_, nw_, sm_count_, use_pdl_, s));
     ++*n_launch;
     return {};
@@ -466,7 +466,7 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
             a.q = q_; a.k_cache = kc; a.v_cache = vc; a.page_table = page_table_; a.st = st_; a.out = attn_;
             a.part_o = part_o_; a.part_ml = part_ml_; a.counters = counters_;
             a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = attn_splits_; a.scale = scale;
-            a.trace = perop_trace_ ? perop_trace_ + 8 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;
+            a.trace = perop_trace_ ? perop_trace_ + 16 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;
             CU(attn_decode_launch(a, pdl && fused_, s));
             ++*n_launch;
         }
@@ -1007,8 +1007,8 @@ Status Engine::gemv_tensor(const std::string& name, const float* x, float* y, in
 
 Status Engine::perop_trace(unsigned long long* out, int cap, int* n_launches) {
     if (!perop_trace_) return fail(GL_ERR_UNSUPPORTED, "trace not enabled (GL_TRACE=1)");
-    if (cap < PEROP_TRACE_LAUNCHES * 8) return fail(GL_ERR_INVALID, "trace buffer too small");
-    CU(cudaMemcpy(out, perop_trace_, (size_t)PEROP_TRACE_LAUNCHES * 8 * 8, cudaMemcpyDeviceToHost));
+    if (cap < PEROP_TRACE_LAUNCHES * 16) return fail(GL_ERR_INVALID, "trace buffer too small");
+    CU(cudaMemcpy(out, perop_trace_, (size_t)PEROP_TRACE_LAUNCHES * 16 * 8, cudaMemcpyDeviceToHost));
     *n_launches = launches_head_;
     return {};
 }

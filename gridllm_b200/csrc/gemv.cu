@@ -37,7 +37,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     // optional device-side timeline (GL_TRACE=1): entry / upstream wait over / planes ready / this warp's items done,
     // for the first and the last CTA of the grid
     unsigned long long* tr = nullptr;
-    if (p.trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tr = p.trace + (blockIdx.x == 0 ? 0 : 4);
+    if (p.trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tr = p.trace + (blockIdx.x == 0 ? 0 : 8);
     if (tr) tr[0] = globaltimer_ns();
     if (warp == NW) {
         // producer: weights are static, so streaming starts before the upstream kernel has finished
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     // arrived -- neither ever stalls the instruction stream (doing both here cost the QKV prologue 1.2 us, run 28)
     EpiCtx ec{0, 0};
     if (p.epi == EPI_QKV) ec.pos = __ldcg(&p.st->pos);
-    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps);
+    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps, tr);
     if (p.epi == EPI_QKV) ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
     if (tr) tr[2] = globaltimer_ns();
     Track trk{0u, 0u};

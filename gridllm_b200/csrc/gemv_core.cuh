@@ -176,7 +176,7 @@ __device__ __forceinline__ void gemv_prologue_static(const GemvParams& p, int ti
 }
 
 template <int ABITS, int NW, int NB>
-__device__ __forceinline__ float gemv_prologue_nb(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps) {
+__device__ __forceinline__ float gemv_prologue_nb(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps, unsigned long long* tr) {
     constexpr int NT = NW * 32;
     const int K = p.cols;
     const int warp = tid >> 5, lane = tid & 31;
@@ -210,39 +210,94 @@ __device__ __forceinline__ float gemv_prologue_nb(const GemvParams& p, uint8_t* 
                 else if (f < nf) wv[i] = __ldg(w4 + f);
             }
         }
+        if (tr && f0 == tid) {      // (profiling) the first batch's x has arrived when its first value can be consumed
+            if (__float_as_uint(v[0].x) != 0x7fc12345u) tr[4] = globaltimer_ns();
+        }
+        if constexpr (NB > PROLOGUE_NB) {
+            // WIDE rows (every iteration of the batch is live): the batch is processed phase by phase across its NB float4s, not float4 by float4: the two shuffle butterflies
+            // (block amax, block sums) are 3 dependent shuffles each, and interleaving NB independent chains is what hides their
+            // latency (the float4-at-a-time loop spent 1.0 us on K = 4096 and 3.0 us on K = 14336, run 34).  Validity of an
+            // iteration is uniform over the warp (nf is a multiple of 32), so the shuffles of invalid iterations are harmless.
+            float e[NB][4], amax[NB];
+            uint32_t hw[NB], lw[NB];
+            int vs[NB], vs32[NB];
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const int f = f0 + i * NT;
-            if (f < nf) {
-                float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                if (norm) {
-                    ss += e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
-                    e[0] *= wv[i].x; e[1] *= wv[i].y; e[2] *= wv[i].z; e[3] *= wv[i].w;
+            for (int i = 0; i < NB; ++i) {
+                const bool ok = f0 + i * NT < nf;
+                e[i][0] = ok ? v[i].x : 0.f; e[i][1] = ok ? v[i].y : 0.f; e[i][2] = ok ? v[i].z : 0.f; e[i][3] = ok ? v[i].w : 0.f;
+                if (norm && ok) {
+                    ss += e[i][0] * e[i][0] + e[i][1] * e[i][1] + e[i][2] * e[i][2] + e[i][3] * e[i][3];
+                    e[i][0] *= wv[i].x; e[i][1] *= wv[i].y; e[i][2] *= wv[i].z; e[i][3] *= wv[i].w;
                 }
-                float amax = fmaxf(fmaxf(fabsf(e[0]), fabsf(e[1])), fmaxf(fabsf(e[2]), fabsf(e[3])));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-                uint32_t h, l;
-                int vs;
-                snap4<ABITS>(e, snap_inv<ABITS>(amax), &h, &l, &vs);
-                vs += __shfl_xor_sync(0xffffffffu, vs, 1);
-                vs += __shfl_xor_sync(0xffffffffu, vs, 2);           // sum(v) of this 16-column group
-                const int vs32 = vs + __shfl_xor_sync(0xffffffffu, vs, 4);
-                // float4 f covers columns 4f..4f+3: unit f>>5, 16-B chunk (f>>2)&7 of the unit, word f&3 of the chunk
-                const int u = f >> 5;
-                const int off = (u << 7) + (((((f >> 2) & 7) ^ (u & 7))) << 4) + ((f & 3) << 2);
-                *reinterpret_cast<uint32_t*>(xhi + off) = h;
-                if (ABITS == 16) *reinterpret_cast<uint32_t*>(xlo + off) = l;
-                if ((f & 3) == 0) s16_arr[f >> 2] = vs;
-                if ((f & 7) == 0) {
-                    const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
-                    sx_arr[f >> 3] = sx;
-                    sm_arr[f >> 3] = sx * (float)vs32;
+                amax[i] = fmaxf(fmaxf(fabsf(e[i][0]), fabsf(e[i][1])), fmaxf(fabsf(e[i][2]), fabsf(e[i][3])));
+            }
+#pragma unroll
+            for (int w = 1; w <= 4; w <<= 1) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) amax[i] = fmaxf(amax[i], __shfl_xor_sync(0xffffffffu, amax[i], w));
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) snap4<ABITS>(e[i], snap_inv<ABITS>(amax[i]), &hw[i], &lw[i], &vs[i]);
+#pragma unroll
+            for (int w = 1; w <= 2; w <<= 1) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) vs[i] += __shfl_xor_sync(0xffffffffu, vs[i], w);           // sum(v) of the 16-column group
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) vs32[i] = vs[i] + __shfl_xor_sync(0xffffffffu, vs[i], 4);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int f = f0 + i * NT;
+                if (f < nf) {
+                    // float4 f covers columns 4f..4f+3: unit f>>5, 16-B chunk (f>>2)&7 of the unit, word f&3 of the chunk
+                    const int u = f >> 5;
+                    const int off = (u << 7) + (((((f >> 2) & 7) ^ (u & 7))) << 4) + ((f & 3) << 2);
+                    *reinterpret_cast<uint32_t*>(xhi + off) = hw[i];
+                    if (ABITS == 16) *reinterpret_cast<uint32_t*>(xlo + off) = lw[i];
+                    if ((f & 3) == 0) s16_arr[f >> 2] = vs[i];
+                    if ((f & 7) == 0) {
+                        const float sx = amax[i] / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                        sx_arr[f >> 3] = sx;
+                        sm_arr[f >> 3] = sx * (float)vs32[i];
+                    }
+                }
+            }
+            } else {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int f = f0 + i * NT;
+                if (f < nf) {
+                    float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                    if (norm) {
+                        ss += e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3];
+                        e[0] *= wv[i].x; e[1] *= wv[i].y; e[2] *= wv[i].z; e[3] *= wv[i].w;
+                    }
+                    float amax = fmaxf(fmaxf(fabsf(e[0]), fabsf(e[1])), fmaxf(fabsf(e[2]), fabsf(e[3])));
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                    uint32_t h, l;
+                    int vs;
+                    snap4<ABITS>(e, snap_inv<ABITS>(amax), &h, &l, &vs);
+                    vs += __shfl_xor_sync(0xffffffffu, vs, 1);
+                    vs += __shfl_xor_sync(0xffffffffu, vs, 2);           // sum(v) of this 16-column group
+                    const int vs32 = vs + __shfl_xor_sync(0xffffffffu, vs, 4);
+                    // float4 f covers columns 4f..4f+3: unit f>>5, 16-B chunk (f>>2)&7 of the unit, word f&3 of the chunk
+                    const int u = f >> 5;
+                    const int off = (u << 7) + (((((f >> 2) & 7) ^ (u & 7))) << 4) + ((f & 3) << 2);
+                    *reinterpret_cast<uint32_t*>(xhi + off) = h;
+                    if (ABITS == 16) *reinterpret_cast<uint32_t*>(xlo + off) = l;
+                    if ((f & 3) == 0) s16_arr[f >> 2] = vs;
+                    if ((f & 7) == 0) {
+                        const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                        sx_arr[f >> 3] = sx;
+                        sm_arr[f >> 3] = sx * (float)vs32;
+                    }
                 }
             }
         }
     }
+    if (tr) tr[5] = globaltimer_ns();
     if (norm) {
         ss = warp_sum(ss);
         if (lane == 0) red[warp] = ss;
@@ -262,9 +317,9 @@ __device__ __forceinline__ float gemv_prologue_nb(const GemvParams& p, uint8_t* 
 
 // Wide rows without RMSNorm (ffn_down: K = 14336, 9-14 float4 per thread) take all their loads in ONE round trip.
 template <int ABITS, int NW>
-__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps) {
-    if (p.norm_w == nullptr && p.cols > 8192) return gemv_prologue_nb<ABITS, NW, 2 * PROLOGUE_NB>(p, smem, tid, ps);
-    return gemv_prologue_nb<ABITS, NW, PROLOGUE_NB>(p, smem, tid, ps);
+__device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps, unsigned long long* tr = nullptr) {
+    if (p.norm_w == nullptr && p.cols > 8192) return gemv_prologue_nb<ABITS, NW, 2 * PROLOGUE_NB>(p, smem, tid, ps, tr);
+    return gemv_prologue_nb<ABITS, NW, PROLOGUE_NB>(p, smem, tid, ps, tr);
 }
 
 // reduce four per-lane partials over the warp with 6 shuffles.  On return, lane L holds the warp total of row

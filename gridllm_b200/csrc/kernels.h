@@ -61,7 +61,7 @@ struct GemvParams {
     const int* page_table; // logical page -> physical page
     const StepState* st;   // position (EPI_QKV) / done flag
     // ring (stand-alone kernel; the persistent kernel has one ring for all phases)
-    unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][4] %globaltimer stamps of this launch (first / last CTA)
+    unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps of this launch (first / last CTA)
     int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
     int depth;
     int slot_bytes;
@@ -108,7 +108,7 @@ struct AttnParams {
     unsigned* counters;     // [n_kv_heads], zero between launches
     int n_head, n_kv_heads, head_dim, n_splits;
     float scale;
-    unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][4] %globaltimer stamps
+    unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps
 };
 cudaError_t attn_decode_launch(const AttnParams& p, bool pdl, cudaStream_t s);
 

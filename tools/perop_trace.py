@@ -22,13 +22,14 @@ def main():
     ctx = int(sys.argv[1]) if len(sys.argv) > 1 else 576
     ms, nl = e.time_decode(ctx, 8)
     lib = N.load_library()
-    cap = 512 * 8
+    cap = 512 * 16
     buf = np.zeros(cap, dtype=np.uint64)
     n = C.c_int32()
     lib.gl_debug_perop_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
     rc = lib.gl_debug_perop_trace(e._h, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n))
     assert rc == 0, lib.gl_last_error()
-    t = buf.reshape(512, 2, 4).astype(np.int64)
+    t8 = buf.reshape(512, 2, 8).astype(np.int64)
+    t = t8[:, :, :4]
     # launch order of a step: embed, 32 x (QKV, attn, O, gate/up, down), lm_head, sampler; only GEMV / attention launches stamp
     names = ["QKV", "ATTN", "O", "GATEUP", "DOWN"]
     rows = []
@@ -57,6 +58,13 @@ def main():
         m = d.mean(axis=0)
         print(f"{name:8s} {m[0]:7.0f} {m[1]:7.0f} {m[2]:7.0f} {m[3]:7.0f} {m[4]:7.0f} | {m[5]:7.0f} {m[6]:7.0f} {m[7]:7.0f}   x{len(d)}")
     print(f"span first QKV entry -> lm_head end: {(prev_end - t_first) / 1e3:.1f} us")
+    # prologue split (GEMV launches): wait-done -> x arrived -> snap done -> planes ready (named barrier)
+    print('prologue split, first CTA, mean ns: x arrives | snap | barrier')
+    for k, name in enumerate(names):
+        if name == 'ATTN':
+            continue
+        r = np.array([t8[1 + 5 * il + k][0] for il in range(32)], dtype=np.float64)
+        print(f'{name:8s} {np.mean(r[:, 4] - r[:, 1]):7.0f} {np.mean(r[:, 5] - r[:, 4]):7.0f} {np.mean(r[:, 2] - r[:, 5]):7.0f}')
     # one layer in detail
     il = 16
     base = None
