@@ -31,6 +31,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     ring.init(smem, smem + gemv_fixed_smem(p.cols), p.n_tracks, p.depth, p.slot_bytes);
     ring.init_barriers(tid);
     if (tid < RING_MAX_SLOTS) fence_mbar_init();
+    if (tid == 0) reinterpret_cast<volatile int*>(smem + SM_MISC)[2] = 0;
     __syncthreads();
     pdl_launch_dependents();
 
@@ -43,19 +44,31 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
         // producer: weights are static, so streaming starts before the upstream kernel has finished
         Track trk{0u, 0u};
         gemv_produce(p.pd, ring, trk, lane, blockIdx.x, gridDim.x);
+        if (p.epi == EPI_QKV && lane == 31) {
+            pdl_wait();                                  // the position belongs to the upstream chain (sampler of the previous step)
+            volatile int* box = reinterpret_cast<volatile int*>(smem + SM_MISC);
+            const int pos = __ldcg(&p.st->pos);
+            box[0] = pos;
+            box[1] = __ldcg(p.page_table + pos / KV_PAGE_TOKENS);
+            __threadfence_block();
+            box[2] = 1;
+        }
         return;
     }
     PrologueStatic ps;
     gemv_prologue_static<NW>(p, tid, ps);     // RMSNorm weights: static, requested while the upstream kernel drains
     pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
     if (tr) tr[1] = globaltimer_ns();
-    // the QKV epilogue needs (position, physical KV page): two DEPENDENT loads.  A warp issues in order, so the first is
-    // requested here, ahead of the prologue's x loads, and the second only after the prologue, when the first has long
-    // arrived -- neither ever stalls the instruction stream (doing both here cost the QKV prologue 1.2 us, run 28)
-    EpiCtx ec{0, 0};
-    if (p.epi == EPI_QKV) ec.pos = __ldcg(&p.st->pos);
     const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps, tr);
-    if (p.epi == EPI_QKV) ec.page = __ldcg(p.page_table + ec.pos / KV_PAGE_TOKENS);
+    // the QKV epilogue needs (position, physical KV page): two dependent loads, fetched by an idle lane of the producer
+    // warp and handed over through shared memory, so that no consumer warp ever stalls on them
+    EpiCtx ec{0, 0};
+    if (p.epi == EPI_QKV) {
+        volatile int* box = reinterpret_cast<volatile int*>(smem + SM_MISC);
+        while (box[2] == 0) { }
+        ec.pos = box[0];
+        ec.page = box[1];
+    }
     if (tr) tr[2] = globaltimer_ns();
     Track trk{0u, 0u};
     gemv_consume<ABITS>(p, ring, trk, smem, tid, scale, ec, blockIdx.x, gridDim.x);
