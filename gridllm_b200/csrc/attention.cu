@@ -53,8 +53,10 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     const int final_pages = pos_lb / KV_PAGE_TOKENS;
     int npre = 0;
     if (split < final_pages) npre = min(TILE_PAGES, (final_pages - split + S - 1) / S);
-    auto stage = [&](int slot, int pg) {          // one lane: page table entry -> two bulk copies
-        const int page = __ldcg(p.page_table + pg);
+    // lane i's page-table entry of this split's i-th page: static, requested before the wait (clamped to the table)
+    int my_entry = 0;
+    if (warp == 0 && lane < TILE_PAGES) my_entry = __ldcg(p.page_table + min(split + lane * S, p.n_table - 1));
+    auto stage = [&](int slot, int page) {        // one lane: two bulk copies of a physical page
         const size_t off = ((size_t)page * p.n_kv_heads + kvh) * PAGE_ELEMS;
         tma_load_1d(ks + slot * PAGE_ELEMS, p.k_cache + off, PAGE_BYTES, &bar);
         tma_load_1d(vs + slot * PAGE_ELEMS, p.v_cache + off, PAGE_BYTES, &bar);
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     if (warp == 0 && npre > 0) {
         if (lane == 0) mbar_expect_tx(&bar, 2u * npre * PAGE_BYTES);
         __syncwarp();
-        if (lane < npre) stage(lane, split + lane * S);
+        if (lane < npre) stage(lane, my_entry);
     }
     pdl_wait();
     if (tr) tr[1] = globaltimer_ns();
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
             if (warp == 0) {
                 if (lane == 0) mbar_expect_tx(&bar, 2u * (np - have) * PAGE_BYTES);
                 __syncwarp();
-                if (lane >= have && lane < np) stage(lane, split + (t0 + lane) * S);
+                if (lane >= have && lane < np) stage(lane, t0 == 0 ? my_entry : __ldcg(p.page_table + split + (t0 + lane) * S));
             }
             mbar_wait(&bar, ph);
             ph ^= 1;

@@ -463,7 +463,7 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
         }
         {
             AttnParams a{};
-            a.q = q_; a.k_cache = kc; a.v_cache = vc; a.page_table = page_table_; a.st = st_; a.out = attn_;
+            a.q = q_; a.k_cache = kc; a.v_cache = vc; a.page_table = page_table_; a.n_table = n_pages_; a.st = st_; a.out = attn_;
             a.part_o = part_o_; a.part_ml = part_ml_; a.counters = counters_;
             a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = attn_splits_; a.scale = scale;
             a.trace = perop_trace_ ? perop_trace_ + 16 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;

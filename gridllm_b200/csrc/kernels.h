@@ -101,6 +101,7 @@ struct AttnParams {
     const __half* k_cache;  // layer base
     const __half* v_cache;
     const int* page_table;
+    int n_table;            // entries in page_table
     const StepState* st;    // attends to positions 0..st->pos
     float* out;             // [n_head][head_dim]
     float* part_o;          // [n_head][n_splits][head_dim]
