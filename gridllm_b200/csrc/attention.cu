@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     }
     __syncthreads();
     if (!is_last) return;
-    attn_merge_head<DPL>(p.part_o, p.part_ml, p.out, head, p.n_splits, active, lane);
+    attn_merge_head<DPL, 32>(p.part_o, p.part_ml, p.out, head, p.n_splits, active, lane);      // all 32 partials in one round trip
     if (tr) tr[3] = globaltimer_ns();
 }
 

@@ -121,7 +121,7 @@ __device__ __forceinline__ void attn_page_math_smem(const __half* kb, const __ha
 // Merge the split partials of one head (run by one warp; n_splits <= 32): out = sum_s w_s o_s / sum_s w_s l_s with
 // w_s = exp(m_s - max m).  (m, l) of split `lane` and the partial outputs of 8 splits travel in one round trip.
 // `stride` is the number of partial slots per head in the buffers, n_splits (<= stride) how many of them are in use.
-template <int DPL>
+template <int DPL, int MB = 16>      // MB partials per round trip
 __device__ __forceinline__ void attn_merge_head(const float* part_o, const float* part_ml, float* attn_out, int head, int stride, int n_splits,
                                                 int lane) {
     constexpr int HD = DPL * 32;
@@ -135,7 +135,6 @@ __device__ __forceinline__ void attn_merge_head(const float* part_o, const float
 #pragma unroll
     for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
     float M = 0.f, wl = 0.f, den = 0.f;
-    constexpr int MB = 16;      // partials per batch: one L2 round trip each
     for (int s0 = 0; s0 < n_splits; s0 += MB) {
         float po[MB][DPL];
 #pragma unroll

@@ -406,8 +406,14 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
     const size_t fixed = gemv_smem_bytes(cols, 0, 0);
     const int ns = std::min(RING_MAX_SLOTS, (int)(((size_t)smem_kb_ * 1024 - fixed) / p.slot_bytes));
     // as many consumer warps as there are, each with >= 2 slots; spare slots deepen the tracks (small slots: more bytes in flight)
+    // tracks x depth: as many bytes in flight as the ring can hold, giving up at most two consumer warps for depth
+    // (small slots -- Q6_K pairs -- would otherwise leave a third of the shared memory unused: lm_head 0.94 -> 0.86 of peak)
     p.n_tracks = std::min(nw_, ns / 2);
     p.depth = p.n_tracks > 0 ? std::min(ring_depth_max_, ns / p.n_tracks) : 0;
+    for (int t = std::max(1, nw_ - 2); t < std::min(nw_, ns / 2); ++t) {
+        const int dd = std::min(ring_depth_max_, ns / t);
+        if (dd >= 2 && t * dd > p.n_tracks * p.depth) { p.n_tracks = t; p.depth = dd; }
+    }
     // a phase in which no warp gets a second slot (one round of items, one K-segment) needs one slot per warp: the smaller
     // footprint (121 KB instead of 232 KB) lets the next kernel's CTAs become resident -- and start their own prefetch --
     // while this one is still running (programmatic dependent launch)
