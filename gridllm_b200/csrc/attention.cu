@@ -73,8 +73,15 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     float q[DPL], o[DPL];
     {
         const float* qp = p.q + (size_t)head * HD + lane * DPL;
+        if (DPL == 4) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(qp));
+            q[0] = t.x; q[1] = t.y; q[DPL - 2] = t.z; q[DPL - 1] = t.w;
+        } else {
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(qp));
+            q[0] = t.x; q[1] = t.y;
+        }
 #pragma unroll
-        for (int d = 0; d < DPL; ++d) { q[d] = __ldcg(qp + d); o[d] = 0.f; }
+        for (int d = 0; d < DPL; ++d) o[d] = 0.f;
     }
     const int L = __ldcg(&p.st->pos) + 1;
 #pragma unroll
@@ -133,24 +140,26 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     // partial result of (head, split)
     {
         float* po = p.part_o + ((size_t)head * p.n_splits + split) * HD + lane * DPL;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) po[d] = o[d];
+        if (DPL == 4) *reinterpret_cast<float4*>(po) = make_float4(o[0], o[1], o[DPL - 2], o[DPL - 1]);
+        else *reinterpret_cast<float2*>(po) = make_float2(o[0], o[1]);
         if (lane == 0) {
             p.part_ml[((size_t)head * p.n_splits + split) * 2] = m_run;
             p.part_ml[((size_t)head * p.n_splits + split) * 2 + 1] = l_run;
         }
     }
     __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + 5, globaltimer_ns());      // (profiling) last partial written
     if (threadIdx.x == 0) {
         unsigned ticket;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.counters + kvh) : "memory");
+        if (p.trace != nullptr) atomicMax(p.trace + 6, globaltimer_ns());                           // (profiling) last ticket drawn
         is_last = (ticket == (unsigned)active - 1);
         if (is_last) p.counters[kvh] = 0;      // ready for the next launch
     }
     __syncthreads();
     if (!is_last) return;
     attn_merge_head<DPL, 32>(p.part_o, p.part_ml, p.out, head, p.n_splits, active, lane);      // all 32 partials in one round trip
-    if (tr) tr[3] = globaltimer_ns();
+    if (p.trace != nullptr && lane == 0) atomicMax(p.trace + 7, globaltimer_ns());                  // (profiling) last merge done
 }
 
 }  // namespace

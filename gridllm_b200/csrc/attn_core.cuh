@@ -137,10 +137,21 @@ __device__ __forceinline__ void attn_merge_head(const float* part_o, const float
     float M = 0.f, wl = 0.f, den = 0.f;
     for (int s0 = 0; s0 < n_splits; s0 += MB) {
         float po[MB][DPL];
+        // one vector load per partial (lane * DPL floats are 16- / 8-byte aligned: HD is a multiple of 32 * DPL)
 #pragma unroll
         for (int i = 0; i < MB; ++i) {
+            if (s0 + i < n_splits) {
+                if (DPL == 4) {
+                    const float4 t = __ldcg(reinterpret_cast<const float4*>(pbase + (size_t)(s0 + i) * HD));
+                    po[i][0] = t.x; po[i][1] = t.y; po[i][DPL - 2] = t.z; po[i][DPL - 1] = t.w;
+                } else {
+                    const float2 t = __ldcg(reinterpret_cast<const float2*>(pbase + (size_t)(s0 + i) * HD));
+                    po[i][0] = t.x; po[i][1] = t.y;
+                }
+            } else {
 #pragma unroll
-            for (int d = 0; d < DPL; ++d) po[i][d] = (s0 + i < n_splits) ? __ldcg(pbase + (size_t)(s0 + i) * HD + d) : 0.f;
+                for (int d = 0; d < DPL; ++d) po[i][d] = 0.f;
+            }
         }
         if (s0 == 0) {
             M = warp_max(ms);
@@ -158,8 +169,8 @@ __device__ __forceinline__ void attn_merge_head(const float* part_o, const float
     }
     const float inv = 1.0f / den;
     float* out = attn_out + (size_t)head * HD + lane * DPL;
-#pragma unroll
-    for (int d = 0; d < DPL; ++d) out[d] = acc[d] * inv;
+    if (DPL == 4) *reinterpret_cast<float4*>(out) = make_float4(acc[0] * inv, acc[1] * inv, acc[DPL - 2] * inv, acc[DPL - 1] * inv);
+    else *reinterpret_cast<float2*>(out) = make_float2(acc[0] * inv, acc[1] * inv);
 }
 
 }  // namespace gl

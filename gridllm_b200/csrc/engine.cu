@@ -167,6 +167,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     ring_depth_max_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH_MAX", 3)));   // stand-alone kernels: up to this many slots per warp
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     lean_rings_ = env_int("GL_LEAN_RINGS", 1) != 0;
+    polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -480,6 +481,7 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
             GemvParams p{};
             const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows, L.wo.tile_rows}};
             p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
+            p.polite_tracks = polite_tracks_;      // resident beside the attention CTAs: prefetch politely (gemv.cu)
             ST(enqueue_gemv(s, p, mo, 1, false, n_head_ * hd_, n_launch));
             GemvParams g{};
             const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.tile_rows}, {L.wup.w, L.wup.type, L.wup.rows, L.wup.tile_rows}};
@@ -1016,6 +1018,7 @@ Status Engine::perop_trace(unsigned long long* out, int cap, int* n_launches) {
     if (cap < PEROP_TRACE_LAUNCHES * 16) return fail(GL_ERR_INVALID, "trace buffer too small");
     CU(cudaMemcpy(out, perop_trace_, (size_t)PEROP_TRACE_LAUNCHES * 16 * 8, cudaMemcpyDeviceToHost));
     *n_launches = launches_head_;
+    CU(cudaMemset(perop_trace_, 0, (size_t)PEROP_TRACE_LAUNCHES * 16 * 8));      // the atomicMax slots start from zero again
     return {};
 }
 

@@ -42,6 +42,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     if (tr) tr[0] = globaltimer_ns();
     if (warp == NW) {
         // producer: weights are static, so streaming starts before the upstream kernel has finished
+        // A kernel whose CTAs become resident beside the upstream kernel's (attn_output beside the attention CTAs) must not
+        // flood the SM's request queue while those are still on their latency-critical tail: the attention merge took
+        // 4.4 us instead of ~1.5 behind 110 KB of early weight prefetch (run 43).  Such a launch lets only a few lanes
+        // prefetch early; the others start when the upstream kernel is done.
+        if (p.polite_tracks > 0 && lane >= p.polite_tracks) pdl_wait();
         Track trk{0u, 0u};
         gemv_produce(p.pd, ring, trk, lane, blockIdx.x, gridDim.x);
         if (p.epi == EPI_QKV && lane == 31) {

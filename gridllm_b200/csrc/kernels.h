@@ -62,6 +62,7 @@ struct GemvParams {
     const StepState* st;   // position (EPI_QKV) / done flag
     // ring (stand-alone kernel; the persistent kernel has one ring for all phases)
     unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps of this launch (first / last CTA)
+    int polite_tracks;     // > 0: only the first polite_tracks producer lanes prefetch before griddepcontrol.wait (see gemv.cu)
     int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
     int depth;
     int slot_bytes;
