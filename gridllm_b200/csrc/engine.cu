@@ -167,6 +167,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     ring_depth_max_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH_MAX", 3)));   // stand-alone kernels: up to this many slots per warp
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     lean_rings_ = env_int("GL_LEAN_RINGS", 1) != 0;
+    xraw_ = env_int("GL_XRAW", 1) != 0;
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
@@ -404,7 +405,9 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
     }
     p.slot_bytes = (need + 127) & ~127;
     if (!gemv_plan(p, mats, nmat, pair, cols, p.slot_bytes)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
-    const size_t fixed = gemv_smem_bytes(cols, 0, 0);
+    // narrow rows: x staged raw by one bulk copy for the half-block prologue (gemv_core.cuh); costs 16 KB of ring
+    p.xraw_bytes = (xraw_ && cols <= GEMV_XRAW_MAX_COLS && cols / 16 <= nw_ * 32) ? cols * 4 : 0;
+    const size_t fixed = gemv_smem_bytes(cols, 0, 0) + (size_t)p.xraw_bytes;
     const int ns = std::min(RING_MAX_SLOTS, (int)(((size_t)smem_kb_ * 1024 - fixed) / p.slot_bytes));
     // as many consumer warps as there are, each with >= 2 slots; spare slots deepen the tracks (small slots: more bytes in flight)
     // tracks x depth: as many bytes in flight as the ring can hold, giving up at most two consumer warps for depth

@@ -28,10 +28,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
-    ring.init(smem, smem + gemv_fixed_smem(p.cols), p.n_tracks, p.depth, p.slot_bytes);
+    const float* xraw = reinterpret_cast<const float*>(smem + gemv_fixed_smem(p.cols));       // raw x staging (xraw_bytes, may be 0)
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + SM_MISC + 16);
+    ring.init(smem, smem + gemv_fixed_smem(p.cols) + p.xraw_bytes, p.n_tracks, p.depth, p.slot_bytes);
     ring.init_barriers(tid);
+    if (tid == 0) {
+        reinterpret_cast<volatile int*>(smem + SM_MISC)[2] = 0;
+        mbar_init(xbar, 1);
+    }
     if (tid < RING_MAX_SLOTS) fence_mbar_init();
-    if (tid == 0) reinterpret_cast<volatile int*>(smem + SM_MISC)[2] = 0;
     __syncthreads();
     pdl_launch_dependents();
 
@@ -60,11 +65,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
         }
         return;
     }
-    PrologueStatic ps;
-    gemv_prologue_static<NW>(p, tid, ps);     // RMSNorm weights: static, requested while the upstream kernel drains
-    pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
-    if (tr) tr[1] = globaltimer_ns();
-    const float scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps, tr);
+    float scale;
+    if (p.xraw_bytes > 0) {
+        PrologueStaticHB ps;
+        gemv_prologue_static_hb(p, tid, ps);      // RMSNorm weights: static, requested while the upstream kernel drains
+        pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
+        if (tr) tr[1] = globaltimer_ns();
+        scale = gemv_prologue_tma<ABITS, NW>(p, smem, xraw, xbar, tid, ps, tr);
+    } else {
+        PrologueStatic ps;
+        gemv_prologue_static<NW>(p, tid, ps);
+        pdl_wait();
+        if (tr) tr[1] = globaltimer_ns();
+        scale = gemv_prologue<ABITS, NW>(p, smem, tid, ps, tr);
+    }
     // the QKV epilogue needs (position, physical KV page): two dependent loads, fetched by an idle lane of the producer
     // warp and handed over through shared memory, so that no consumer warp ever stalls on them
     EpiCtx ec{0, 0};
@@ -145,11 +159,12 @@ cudaError_t gemv_configure() {
 
 cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
     if (!gemv_variant_ok(abits, nw) || p.n_tracks < 1 || p.n_tracks > nw || p.depth < 1 || p.n_tracks * p.depth > RING_MAX_SLOTS) return cudaErrorInvalidValue;
+    if (p.xraw_bytes != 0 && (p.xraw_bytes != p.cols * 4 || p.cols > GEMV_XRAW_MAX_COLS || p.cols / 16 > nw * 32 || ((uintptr_t)p.x & 15))) return cudaErrorInvalidValue;
     if (p.epi == EPI_QKV && ((p.pd.seg[0].rows & 1) || (p.pd.nseg > 1 && (p.pd.seg[1].rows & 1)))) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);
     cfg.blockDim = dim3((unsigned)gemv_threads(nw));
-    cfg.dynamicSmemBytes = gemv_smem_bytes(p.cols, p.n_tracks * p.depth, p.slot_bytes);
+    cfg.dynamicSmemBytes = gemv_smem_bytes(p.cols, p.n_tracks * p.depth, p.slot_bytes) + (size_t)p.xraw_bytes;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -315,6 +315,107 @@ __device__ __forceinline__ float gemv_prologue_nb(const GemvParams& p, uint8_t* 
     return scale;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Prologue for K <= GEMV_XRAW_MAX_COLS in the stand-alone kernel: x is brought in by ONE bulk copy (TMA) into a raw fp32
+// staging buffer, then one thread per HALF BLOCK (16 columns) snaps it out of shared memory; lanes 2k / 2k+1 share a
+// 32-column block, so one shuffle gives the block amax and one the block sum.
+//   * the float4-per-lane version above needs six shuffles per float4 and recomputes the reciprocal, the addresses and
+//     the stores every 4 columns: 21 instructions per column, 1.0 us of arithmetic per K = 4096 prologue (run 45);
+//   * reading x with 64-B-per-lane global loads instead (no staging) cut the arithmetic to 0.33 us but multiplied the
+//     load requests by eight, and those queue behind the ring's bulk prefetch in the SM's request FIFO: x arrived after
+//     3.2 us instead of 0.6 (run 46).  One bulk copy is one request.
+// ps carries this thread's RMSNorm weights (its half block), requested before the upstream wait.
+// ---------------------------------------------------------------------------------------------------
+struct PrologueStaticHB { float4 wv[4]; };
+__device__ __forceinline__ void gemv_prologue_static_hb(const GemvParams& p, int tid, PrologueStaticHB& ps) {
+    if (p.norm_w == nullptr || tid >= p.cols / 16) return;
+    const float4* w4 = reinterpret_cast<const float4*>(p.norm_w) + 4 * tid;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ps.wv[i] = __ldg(w4 + i);
+}
+
+template <int ABITS, int NW>
+__device__ __forceinline__ float gemv_prologue_tma(const GemvParams& p, uint8_t* smem, const float* xraw, uint64_t* xbar, int tid,
+                                                   const PrologueStaticHB& ps, unsigned long long* tr) {
+    constexpr int NT = NW * 32;
+    const int K = p.cols;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* red = reinterpret_cast<float*>(smem + SM_RED);
+    uint8_t* xhi = smem + SM_X;
+    uint8_t* xlo = xhi + K;
+    float* sx_arr = reinterpret_cast<float*>(xlo + K);
+    float* sm_arr = sx_arr + K / 32;
+    int* s16_arr = reinterpret_cast<int*>(sm_arr + K / 32);
+    const int nhb = K / 16;                 // <= NT (the host only selects this variant then); a multiple of 16
+    const bool norm = p.norm_w != nullptr;
+    if (tid == 0) {
+        mbar_expect_tx(xbar, (uint32_t)K * 4u);
+        tma_load_1d(const_cast<float*>(xraw), p.x, (uint32_t)K * 4u, xbar);
+    }
+    float ss = 0.f;
+    // a warp whose lower half is live runs the body with all its lanes (the two shuffles need them)
+    if ((tid & ~31) < nhb) {
+        const bool ok = tid < nhb;
+        mbar_wait(xbar, 0);
+        if (tr) tr[4] = globaltimer_ns();
+        float e[16];
+        const float4* xr = reinterpret_cast<const float4*>(xraw) + 4 * (ok ? tid : 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 t = xr[i];
+            e[4 * i] = ok ? t.x : 0.f; e[4 * i + 1] = ok ? t.y : 0.f; e[4 * i + 2] = ok ? t.z : 0.f; e[4 * i + 3] = ok ? t.w : 0.f;
+        }
+        if (norm && ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ss += e[4 * i] * e[4 * i] + e[4 * i + 1] * e[4 * i + 1] + e[4 * i + 2] * e[4 * i + 2] + e[4 * i + 3] * e[4 * i + 3];
+                e[4 * i] *= ps.wv[i].x; e[4 * i + 1] *= ps.wv[i].y; e[4 * i + 2] *= ps.wv[i].z; e[4 * i + 3] *= ps.wv[i].w;
+            }
+        }
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(e[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));            // the other half of the 32-column block
+        const float inv = snap_inv<ABITS>(amax);
+        uint32_t hw[4], lw[4];
+        int s16 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int vs;
+            snap4<ABITS>(e + 4 * i, inv, &hw[i], &lw[i], &vs);
+            s16 += vs;                                                        // sum(v) of this 16-column group
+        }
+        const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
+        if (ok) {
+            // half block tid = columns 16 tid ..: unit tid >> 3, 16-B chunk tid & 7 of the unit
+            const int u = tid >> 3;
+            const int off = (u << 7) + (((tid & 7) ^ (u & 7)) << 4);
+            *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            s16_arr[tid] = s16;
+            if ((tid & 1) == 0) {
+                const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                sx_arr[tid >> 1] = sx;
+                sm_arr[tid >> 1] = sx * (float)s32;
+            }
+        }
+    }
+    if (tr) tr[5] = globaltimer_ns();
+    if (norm) {
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+    }
+    named_bar_sync(1, NT);
+    float scale = 1.f;
+    if (norm) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += red[w];
+        scale = 1.0f / sqrtf(tot / (float)K + p.eps);
+    }
+    return scale;
+}
+
 // Wide rows without RMSNorm (ffn_down: K = 14336, 9-14 float4 per thread) take all their loads in ONE round trip.
 template <int ABITS, int NW>
 __device__ __forceinline__ float gemv_prologue(const GemvParams& p, uint8_t* smem, int tid, const PrologueStatic& ps, unsigned long long* tr = nullptr) {

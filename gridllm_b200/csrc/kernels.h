@@ -62,11 +62,14 @@ struct GemvParams {
     const StepState* st;   // position (EPI_QKV) / done flag
     // ring (stand-alone kernel; the persistent kernel has one ring for all phases)
     unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps of this launch (first / last CTA)
+    int xraw_bytes;        // > 0: stand-alone kernel stages x with one bulk copy into a raw buffer of this size after the planes
     int polite_tracks;     // > 0: only the first polite_tracks producer lanes prefetch before griddepcontrol.wait (see gemv.cu)
     int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
     int depth;
     int slot_bytes;
 };
+
+constexpr int GEMV_XRAW_MAX_COLS = 4096;    // x rows up to this width are staged raw (16 KB) for the half-block prologue
 
 // a weight matrix as the planner sees it
 struct GemvMat { const uint8_t* w; int type; int rows; int tile_rows; };   // tile_rows: what the matrix was stored with (rowdot.h)

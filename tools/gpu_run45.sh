@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "decode or service or long" > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -k "decode or service or long or gemv" > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -n 3 gpurun_out/pytest_gpu.log
 python - <<'PY' > gpurun_out/build_model.log 2>&1
