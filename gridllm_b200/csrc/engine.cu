@@ -168,6 +168,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     lean_rings_ = env_int("GL_LEAN_RINGS", 1) != 0;
     xraw_ = env_int("GL_XRAW", 1) != 0;
+    xraw_wide_ = env_int("GL_XRAW_WIDE", 1) != 0;
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
@@ -406,7 +407,17 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
     p.slot_bytes = (need + 127) & ~127;
     if (!gemv_plan(p, mats, nmat, pair, cols, p.slot_bytes)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
     // narrow rows: x staged raw by one bulk copy for the half-block prologue (gemv_core.cuh); costs 16 KB of ring
-    p.xraw_bytes = (xraw_ && cols <= GEMV_XRAW_MAX_COLS && cols / 16 <= nw_ * 32) ? cols * 4 : 0;
+    p.xraw_bytes = 0;
+    p.xraw_nseg = 1;
+    if (xraw_) {
+        const KSplit ks = ksplit(cols);
+        if (cols <= GEMV_XRAW_MAX_COLS && cols / 16 <= nw_ * 32) {
+            p.xraw_bytes = cols * 4;
+        } else if (xraw_wide_ && ks.nks > 1 && cols / ks.nks / 16 <= nw_ * 32) {     // wide rows: K-segment pieces, two buffers
+            p.xraw_nseg = ks.nks;
+            p.xraw_bytes = 2 * (cols / ks.nks) * 4;
+        }
+    }
     const size_t fixed = gemv_smem_bytes(cols, 0, 0) + (size_t)p.xraw_bytes;
     const int ns = std::min(RING_MAX_SLOTS, (int)(((size_t)smem_kb_ * 1024 - fixed) / p.slot_bytes));
     // as many consumer warps as there are, each with >= 2 slots; spare slots deepen the tracks (small slots: more bytes in flight)
@@ -414,7 +425,7 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
     // (small slots -- Q6_K pairs -- would otherwise leave a third of the shared memory unused: lm_head 0.94 -> 0.86 of peak)
     p.n_tracks = std::min(nw_, ns / 2);
     p.depth = p.n_tracks > 0 ? std::min(ring_depth_max_, ns / p.n_tracks) : 0;
-    for (int t = std::max(1, nw_ - 2); t < std::min(nw_, ns / 2); ++t) {
+    for (int t = std::max(1, nw_ - 2); p.pd.nks > 1 && t < std::min(nw_, ns / 2); ++t) {      // (narrow rows keep every warp: lm_head is issue-bound at 10)
         const int dd = std::min(ring_depth_max_, ns / t);
         if (dd >= 2 && t * dd > p.n_tracks * p.depth) { p.n_tracks = t; p.depth = dd; }
     }

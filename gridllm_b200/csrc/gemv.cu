@@ -29,12 +29,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Ring ring;
     const float* xraw = reinterpret_cast<const float*>(smem + gemv_fixed_smem(p.cols));       // raw x staging (xraw_bytes, may be 0)
-    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + SM_MISC + 16);
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + SM_MISC + 16);                          // two mbarriers
     ring.init(smem, smem + gemv_fixed_smem(p.cols) + p.xraw_bytes, p.n_tracks, p.depth, p.slot_bytes);
     ring.init_barriers(tid);
     if (tid == 0) {
         reinterpret_cast<volatile int*>(smem + SM_MISC)[2] = 0;
-        mbar_init(xbar, 1);
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
     }
     if (tid < RING_MAX_SLOTS) fence_mbar_init();
     __syncthreads();
@@ -159,7 +160,12 @@ cudaError_t gemv_configure() {
 
 cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
     if (!gemv_variant_ok(abits, nw) || p.n_tracks < 1 || p.n_tracks > nw || p.depth < 1 || p.n_tracks * p.depth > RING_MAX_SLOTS) return cudaErrorInvalidValue;
-    if (p.xraw_bytes != 0 && (p.xraw_bytes != p.cols * 4 || p.cols > GEMV_XRAW_MAX_COLS || p.cols / 16 > nw * 32 || ((uintptr_t)p.x & 15))) return cudaErrorInvalidValue;
+    if (p.xraw_bytes != 0) {
+        const int ns = p.xraw_nseg;
+        if (ns < 1 || p.cols % (ns * 16) || p.cols / ns / 16 > nw * 32 || ((uintptr_t)p.x & 15) || ((p.cols / ns * 4) & 15) ||
+            p.xraw_bytes != (ns == 1 ? 1 : 2) * (p.cols / ns) * 4)
+            return cudaErrorInvalidValue;
+    }
     if (p.epi == EPI_QKV && ((p.pd.seg[0].rows & 1) || (p.pd.nseg > 1 && (p.pd.seg[1].rows & 1)))) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_ctas);

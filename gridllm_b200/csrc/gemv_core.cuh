@@ -334,6 +334,8 @@ __device__ __forceinline__ void gemv_prologue_static_hb(const GemvParams& p, int
     for (int i = 0; i < 4; ++i) ps.wv[i] = __ldg(w4 + i);
 }
 
+// x is staged in nseg pieces of seg_cols columns (narrow rows: one piece = the whole row; wide rows: one K-segment at
+// a time through TWO buffers, the bulk copy of piece s+2 issued as soon as piece s has been snapped).
 template <int ABITS, int NW>
 __device__ __forceinline__ float gemv_prologue_tma(const GemvParams& p, uint8_t* smem, const float* xraw, uint64_t* xbar, int tid,
                                                    const PrologueStaticHB& ps, unsigned long long* tr) {
@@ -346,57 +348,75 @@ __device__ __forceinline__ float gemv_prologue_tma(const GemvParams& p, uint8_t*
     float* sx_arr = reinterpret_cast<float*>(xlo + K);
     float* sm_arr = sx_arr + K / 32;
     int* s16_arr = reinterpret_cast<int*>(sm_arr + K / 32);
-    const int nhb = K / 16;                 // <= NT (the host only selects this variant then); a multiple of 16
+    const int nseg = p.xraw_nseg;
+    const int seg_cols = K / nseg;
+    const int nhb = seg_cols / 16;          // <= NT (the host only selects this variant then); a multiple of 16
+    const uint32_t seg_bytes = (uint32_t)seg_cols * 4u;
     const bool norm = p.norm_w != nullptr;
     if (tid == 0) {
-        mbar_expect_tx(xbar, (uint32_t)K * 4u);
-        tma_load_1d(const_cast<float*>(xraw), p.x, (uint32_t)K * 4u, xbar);
+        for (int s = 0; s < min(nseg, 2); ++s) {
+            mbar_expect_tx(&xbar[s], seg_bytes);
+            tma_load_1d(const_cast<float*>(xraw) + (size_t)s * seg_cols, p.x + (size_t)s * seg_cols, seg_bytes, &xbar[s]);
+        }
     }
     float ss = 0.f;
-    // a warp whose lower half is live runs the body with all its lanes (the two shuffles need them)
-    if ((tid & ~31) < nhb) {
-        const bool ok = tid < nhb;
-        mbar_wait(xbar, 0);
-        if (tr) tr[4] = globaltimer_ns();
-        float e[16];
-        const float4* xr = reinterpret_cast<const float4*>(xraw) + 4 * (ok ? tid : 0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 t = xr[i];
-            e[4 * i] = ok ? t.x : 0.f; e[4 * i + 1] = ok ? t.y : 0.f; e[4 * i + 2] = ok ? t.z : 0.f; e[4 * i + 3] = ok ? t.w : 0.f;
-        }
-        if (norm && ok) {
+    for (int s = 0; s < nseg; ++s) {
+        const int b = s & 1;
+        // a warp whose lower half is live runs the body with all its lanes (the two shuffles need them)
+        if ((tid & ~31) < nhb) {
+            const bool ok = tid < nhb;
+            mbar_wait(&xbar[b], (uint32_t)(s >> 1) & 1u);
+            if (tr && s == 0) tr[4] = globaltimer_ns();
+            const int hb = s * nhb + (ok ? tid : 0);          // half block of the whole row
+            float e[16];
+            const float4* xr = reinterpret_cast<const float4*>(xraw + (size_t)b * seg_cols) + 4 * (ok ? tid : 0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                ss += e[4 * i] * e[4 * i] + e[4 * i + 1] * e[4 * i + 1] + e[4 * i + 2] * e[4 * i + 2] + e[4 * i + 3] * e[4 * i + 3];
-                e[4 * i] *= ps.wv[i].x; e[4 * i + 1] *= ps.wv[i].y; e[4 * i + 2] *= ps.wv[i].z; e[4 * i + 3] *= ps.wv[i].w;
+                const float4 t = xr[i];
+                e[4 * i] = ok ? t.x : 0.f; e[4 * i + 1] = ok ? t.y : 0.f; e[4 * i + 2] = ok ? t.z : 0.f; e[4 * i + 3] = ok ? t.w : 0.f;
+            }
+            if (norm && ok) {
+                const float4* w4 = reinterpret_cast<const float4*>(p.norm_w) + 4 * hb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 wv = (s == 0) ? ps.wv[i] : __ldg(w4 + i);
+                    ss += e[4 * i] * e[4 * i] + e[4 * i + 1] * e[4 * i + 1] + e[4 * i + 2] * e[4 * i + 2] + e[4 * i + 3] * e[4 * i + 3];
+                    e[4 * i] *= wv.x; e[4 * i + 1] *= wv.y; e[4 * i + 2] *= wv.z; e[4 * i + 3] *= wv.w;
+                }
+            }
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(e[i]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));            // the other half of the 32-column block
+            const float inv = snap_inv<ABITS>(amax);
+            uint32_t hw[4], lw[4];
+            int s16 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int vs;
+                snap4<ABITS>(e + 4 * i, inv, &hw[i], &lw[i], &vs);
+                s16 += vs;                                                        // sum(v) of this 16-column group
+            }
+            const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
+            if (ok) {
+                // half block hb = columns 16 hb ..: unit hb >> 3, 16-B chunk hb & 7 of the unit
+                const int u = hb >> 3;
+                const int off = (u << 7) + (((hb & 7) ^ (u & 7)) << 4);
+                *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                s16_arr[hb] = s16;
+                if ((hb & 1) == 0) {
+                    const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                    sx_arr[hb >> 1] = sx;
+                    sm_arr[hb >> 1] = sx * (float)s32;
+                }
             }
         }
-        float amax = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(e[i]));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));            // the other half of the 32-column block
-        const float inv = snap_inv<ABITS>(amax);
-        uint32_t hw[4], lw[4];
-        int s16 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int vs;
-            snap4<ABITS>(e + 4 * i, inv, &hw[i], &lw[i], &vs);
-            s16 += vs;                                                        // sum(v) of this 16-column group
-        }
-        const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
-        if (ok) {
-            // half block tid = columns 16 tid ..: unit tid >> 3, 16-B chunk tid & 7 of the unit
-            const int u = tid >> 3;
-            const int off = (u << 7) + (((tid & 7) ^ (u & 7)) << 4);
-            *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            s16_arr[tid] = s16;
-            if ((tid & 1) == 0) {
-                const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
-                sx_arr[tid >> 1] = sx;
-                sm_arr[tid >> 1] = sx * (float)s32;
+        if (s + 1 < nseg) {
+            named_bar_sync(1, NT);                              // buffer b has been read by everyone
+            if (tid == 0 && s + 2 < nseg) {
+                mbar_expect_tx(&xbar[b], seg_bytes);
+                tma_load_1d(const_cast<float*>(xraw) + (size_t)b * seg_cols, p.x + (size_t)(s + 2) * seg_cols, seg_bytes, &xbar[b]);
             }
         }
     }

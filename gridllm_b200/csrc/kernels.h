@@ -62,7 +62,8 @@ struct GemvParams {
     const StepState* st;   // position (EPI_QKV) / done flag
     // ring (stand-alone kernel; the persistent kernel has one ring for all phases)
     unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps of this launch (first / last CTA)
-    int xraw_bytes;        // > 0: stand-alone kernel stages x with one bulk copy into a raw buffer of this size after the planes
+    int xraw_bytes;        // > 0: stand-alone kernel stages x raw (bulk copies) in a buffer of this size after the planes
+    int xraw_nseg;         // pieces x is staged in: 1 (narrow rows) or the K-segments, two buffers deep (wide rows)
     int polite_tracks;     // > 0: only the first polite_tracks producer lanes prefetch before griddepcontrol.wait (see gemv.cu)
     int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
     int depth;
