@@ -168,7 +168,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     lean_rings_ = env_int("GL_LEAN_RINGS", 1) != 0;
     xraw_ = env_int("GL_XRAW", 1) != 0;
-    xraw_wide_ = env_int("GL_XRAW_WIDE", 1) != 0;
+    xraw_wide_ = env_int("GL_XRAW_WIDE", 0) != 0;        // measured (run 49): no gain -- each 14 KB piece waits ~1 us for its bulk copy
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);

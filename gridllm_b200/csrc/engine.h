@@ -107,7 +107,7 @@ private:
     int ring_depth_ = 2;       // ring slots per consumer warp (track depth, gemv_core.cuh)
     int ring_depth_max_ = 3;
     int polite_tracks_ = 3;    // attn_output: producer lanes that may prefetch before the attention kernel is done (0: all)
-    bool xraw_wide_ = true;    // wide rows: the same through two K-segment buffers
+    bool xraw_wide_ = false;   // wide rows: the same through two K-segment buffers (opt-in: GL_XRAW_WIDE=1)
     bool xraw_ = true;         // narrow rows: raw x staging + half-block prologue in the stand-alone GEMV kernels
     bool lean_rings_ = true;   // one ring slot per warp for single-round kernels (room for the next kernel's CTAs)
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
