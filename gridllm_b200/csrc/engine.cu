@@ -167,7 +167,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     ring_depth_max_ = std::max(2, std::min(4, env_int("GL_RING_DEPTH_MAX", 3)));   // stand-alone kernels: up to this many slots per warp
     smem_kb_ = std::min(227, env_int("GL_SMEM_KB", 227));
     lean_rings_ = env_int("GL_LEAN_RINGS", 1) != 0;
-    xraw_ = env_int("GL_XRAW", 1) != 0;
+    xraw_ = env_int("GL_XRAW", 0) != 0;       // opt-in: a second prologue variant = a second kernel in the step (see hb256_)
+    hb256_ = env_int("GL_HB256", 1) != 0;
     xraw_wide_ = env_int("GL_XRAW_WIDE", 0) != 0;        // measured (run 49): no gain -- each 14 KB piece waits ~1 us for its bulk copy
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
@@ -406,10 +407,13 @@ Status Engine::enqueue_gemv(cudaStream_t s, GemvParams& p, const GemvMat* mats, 
     }
     p.slot_bytes = (need + 127) & ~127;
     if (!gemv_plan(p, mats, nmat, pair, cols, p.slot_bytes)) return fail(GL_ERR_UNSUPPORTED, "GEMV shape outside the kernel envelope (cols=" + std::to_string(cols) + ")");
-    // narrow rows: x staged raw by one bulk copy for the half-block prologue (gemv_core.cuh); costs 16 KB of ring
+    // prologue variant (= which kernel, gemv.cu): by default the 256-bit-load half-block prologue for every width, so that all
+    // GEMV launches of a step are one kernel; GL_XRAW=1 stages narrow rows raw by one bulk copy instead (16 KB of ring)
     p.xraw_bytes = 0;
     p.xraw_nseg = 1;
-    if (xraw_) {
+    const bool variants = gemv_prologue_variants(nw_);
+    p.hb256 = (variants && hb256_ && (cols > GEMV_XRAW_MAX_COLS || !xraw_) && cols <= 16 * nw_ * 32 * (nw_ >= 12 ? 3 : 4)) ? 1 : 0;
+    if (variants && xraw_ && !p.hb256) {
         const KSplit ks = ksplit(cols);
         if (cols <= GEMV_XRAW_MAX_COLS && cols / 16 <= nw_ * 32) {
             p.xraw_bytes = cols * 4;

@@ -108,7 +108,10 @@ private:
     int ring_depth_max_ = 3;
     int polite_tracks_ = 3;    // attn_output: producer lanes that may prefetch before the attention kernel is done (0: all)
     bool xraw_wide_ = false;   // wide rows: the same through two K-segment buffers (opt-in: GL_XRAW_WIDE=1)
-    bool xraw_ = true;         // narrow rows: raw x staging + half-block prologue in the stand-alone GEMV kernels
+    // GEMV prologue variant.  Every GEMV launch of a step should be the SAME kernel: two variants alternating (61 + 68 KB of
+    // code, plus 30 KB of attention) overflow the SM's instruction cache and cost 0.5 us per launch (runs 52 / 53).
+    bool hb256_ = true;        // half-block prologue with 256-bit global loads, all widths (default)
+    bool xraw_ = false;        // narrow rows: raw x staging by bulk copy + half-block prologue (opt-in, GL_XRAW=1)
     bool lean_rings_ = true;   // one ring slot per warp for single-round kernels (room for the next kernel's CTAs)
     bool use_graph_ = true, use_pdl_ = true, fused_ = true;
     int smem_kb_ = 224, attn_splits_ = 16;

@@ -23,7 +23,10 @@ namespace gl {
 
 namespace {
 
-template <int ABITS, int NW>
+// PRO selects the ONE prologue variant a kernel carries (gemv_core.cuh): 0 coalesced float4 loads (any shape), 1 raw staging by
+// bulk copy + half-block snap (narrow rows), 2 half-block snap with 256-bit loads (wide rows).  One variant per kernel keeps the
+// code small: with all three inlined the latency-bound single-item phases slowed by 20 % (instruction cache, run 51).
+template <int ABITS, int NW, int PRO>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -67,10 +70,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
         return;
     }
     float scale;
-    if (p.xraw_bytes > 0) {
+    if constexpr (PRO == 2) {
         PrologueStaticHB ps;
         gemv_prologue_static_hb(p, tid, ps);      // RMSNorm weights: static, requested while the upstream kernel drains
         pdl_wait();   // x (and the residual / KV pages we write) belong to the upstream kernel
+        if (tr) tr[1] = globaltimer_ns();
+        scale = gemv_prologue_hb256<ABITS, NW>(p, smem, tid, ps, tr);
+    } else if constexpr (PRO == 1) {
+        PrologueStaticHB ps;
+        gemv_prologue_static_hb(p, tid, ps);
+        pdl_wait();
         if (tr) tr[1] = globaltimer_ns();
         scale = gemv_prologue_tma<ABITS, NW>(p, smem, xraw, xbar, tid, ps, tr);
     } else {
@@ -138,28 +147,45 @@ bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols
 bool gemv_variant_ok(int abits, int nw) { return (abits == 16 || abits == 8) && (nw == 8 || nw == 12 || nw == 16); }
 
 namespace {
-template <int ABITS, int NW>
+template <int ABITS, int NW, int PRO>
 cudaError_t configure_one() {
-    return cudaFuncSetAttribute(gemv_kernel<ABITS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(gemv_kernel<ABITS, NW, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
-template <int ABITS, int NW>
+template <int ABITS, int NW, int PRO>
 cudaError_t launch_one(const cudaLaunchConfig_t& cfg, const GemvParams& p) {
-    return cudaLaunchKernelEx(&cfg, gemv_kernel<ABITS, NW>, p);
+    return cudaLaunchKernelEx(&cfg, gemv_kernel<ABITS, NW, PRO>, p);
+}
+template <int ABITS>
+cudaError_t configure_abits() {
+    cudaError_t e = configure_one<ABITS, 8, 0>();
+    if (e == cudaSuccess) e = configure_one<ABITS, 16, 0>();
+    if (e == cudaSuccess) e = configure_one<ABITS, 12, 0>();
+    if (e == cudaSuccess) e = configure_one<ABITS, 12, 1>();
+    if (e == cudaSuccess) e = configure_one<ABITS, 12, 2>();
+    return e;
+}
+template <int ABITS>
+cudaError_t launch_abits(const cudaLaunchConfig_t& cfg, const GemvParams& p, int nw, int pro) {
+    if (nw == 8) return launch_one<ABITS, 8, 0>(cfg, p);
+    if (nw == 16) return launch_one<ABITS, 16, 0>(cfg, p);
+    if (pro == 2) return launch_one<ABITS, 12, 2>(cfg, p);
+    if (pro == 1) return launch_one<ABITS, 12, 1>(cfg, p);
+    return launch_one<ABITS, 12, 0>(cfg, p);
 }
 }  // namespace
 
+// the specialised prologues are compiled for 12 consumer warps only
+bool gemv_prologue_variants(int consumer_warps) { return consumer_warps == 12; }
+
 cudaError_t gemv_configure() {
-    cudaError_t e = configure_one<16, 8>();
-    if (e == cudaSuccess) e = configure_one<16, 12>();
-    if (e == cudaSuccess) e = configure_one<16, 16>();
-    if (e == cudaSuccess) e = configure_one<8, 8>();
-    if (e == cudaSuccess) e = configure_one<8, 12>();
-    if (e == cudaSuccess) e = configure_one<8, 16>();
+    cudaError_t e = configure_abits<16>();
+    if (e == cudaSuccess) e = configure_abits<8>();
     return e;
 }
 
 cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool pdl, cudaStream_t s) {
     if (!gemv_variant_ok(abits, nw) || p.n_tracks < 1 || p.n_tracks > nw || p.depth < 1 || p.n_tracks * p.depth > RING_MAX_SLOTS) return cudaErrorInvalidValue;
+    if (p.hb256 && (p.xraw_bytes != 0 || p.cols > 16 * nw * 32 * (nw >= 12 ? 3 : 4) || ((uintptr_t)p.x & 31))) return cudaErrorInvalidValue;
     if (p.xraw_bytes != 0) {
         const int ns = p.xraw_nseg;
         if (ns < 1 || p.cols % (ns * 16) || p.cols / ns / 16 > nw * 32 || ((uintptr_t)p.x & 15) || ((p.cols / ns * 4) & 15) ||
@@ -177,14 +203,9 @@ cudaError_t gemv_launch(const GemvParams& p, int abits, int nw, int n_ctas, bool
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (abits == 16) {
-        if (nw == 8) return launch_one<16, 8>(cfg, p);
-        if (nw == 12) return launch_one<16, 12>(cfg, p);
-        return launch_one<16, 16>(cfg, p);
-    }
-    if (nw == 8) return launch_one<8, 8>(cfg, p);
-    if (nw == 12) return launch_one<8, 12>(cfg, p);
-    return launch_one<8, 16>(cfg, p);
+    const int pro = p.hb256 ? 2 : (p.xraw_bytes > 0 ? 1 : 0);
+    if (pro != 0 && !gemv_prologue_variants(nw)) return cudaErrorInvalidValue;
+    return abits == 16 ? launch_abits<16>(cfg, p, nw, pro) : launch_abits<8>(cfg, p, nw, pro);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -334,6 +334,107 @@ __device__ __forceinline__ void gemv_prologue_static_hb(const GemvParams& p, int
     for (int i = 0; i < 4; ++i) ps.wv[i] = __ldg(w4 + i);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Prologue, half block per thread straight from global memory with 256-BIT LOADS (ld.global.v8.f32, SASS LDG.E.256,
+// new on sm_100): a lane's 16 columns are two whole 32-byte sectors, so the load requests are as few as in the coalesced
+// float4 version (the LDG.128 attempt doubled them and x arrived after 3.2 us, run 46) while the arithmetic keeps the
+// half-block form: one shuffle for the block maximum, one for the block sum, reciprocal / addresses / stores once per 16
+// columns.  Serves every width: K = 14336 is 896 half blocks = 2.3 per thread, all of them requested at once.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldcg256(const float* p, float* v) {
+    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+
+template <int ABITS, int NW>
+__device__ __forceinline__ float gemv_prologue_hb256(const GemvParams& p, uint8_t* smem, int tid, const PrologueStaticHB& ps, unsigned long long* tr) {
+    constexpr int NT = NW * 32;
+    constexpr int MAXR = NW >= 12 ? 3 : 4;          // rounds of half blocks per thread: K <= 16 * NT * MAXR (checked by the host)
+    const int K = p.cols;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* red = reinterpret_cast<float*>(smem + SM_RED);
+    uint8_t* xhi = smem + SM_X;
+    uint8_t* xlo = xhi + K;
+    float* sx_arr = reinterpret_cast<float*>(xlo + K);
+    float* sm_arr = sx_arr + K / 32;
+    int* s16_arr = reinterpret_cast<int*>(sm_arr + K / 32);
+    const int nhb = K / 16;                 // a multiple of 16: a warp whose lower half is live runs with all its lanes
+    const bool norm = p.norm_w != nullptr;
+    float e[MAXR][16];
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int hb = tid + r * NT;
+        if (hb < nhb) {
+            ldcg256(p.x + 16 * (size_t)hb, e[r]);
+            ldcg256(p.x + 16 * (size_t)hb + 8, e[r] + 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e[r][i] = 0.f;
+        }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int hb = tid + r * NT;
+        if ((hb & ~31) < nhb) {             // uniform over the warp
+            const bool ok = hb < nhb;
+            if (tr && r == 0) { if (__float_as_uint(e[0][0]) != 0x7fc12345u) tr[4] = globaltimer_ns(); }
+            if (norm && ok) {
+                const float4* w4 = reinterpret_cast<const float4*>(p.norm_w) + 4 * hb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 wv = (r == 0) ? ps.wv[i] : __ldg(w4 + i);
+                    ss += e[r][4 * i] * e[r][4 * i] + e[r][4 * i + 1] * e[r][4 * i + 1] + e[r][4 * i + 2] * e[r][4 * i + 2] + e[r][4 * i + 3] * e[r][4 * i + 3];
+                    e[r][4 * i] *= wv.x; e[r][4 * i + 1] *= wv.y; e[r][4 * i + 2] *= wv.z; e[r][4 * i + 3] *= wv.w;
+                }
+            }
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(e[r][i]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));            // the other half of the 32-column block
+            const float inv = snap_inv<ABITS>(amax);
+            uint32_t hw[4], lw[4];
+            int s16 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int vs;
+                snap4<ABITS>(e[r] + 4 * i, inv, &hw[i], &lw[i], &vs);
+                s16 += vs;                                                        // sum(v) of this 16-column group
+            }
+            const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
+            if (ok) {
+                // half block hb = columns 16 hb ..: unit hb >> 3, 16-B chunk hb & 7 of the unit
+                const int u = hb >> 3;
+                const int off = (u << 7) + (((hb & 7) ^ (u & 7)) << 4);
+                *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (ABITS == 16) *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                s16_arr[hb] = s16;
+                if ((hb & 1) == 0) {
+                    const float sx = amax / (ABITS == 16 ? ACT16_RANGE : ACT8_RANGE);
+                    sx_arr[hb >> 1] = sx;
+                    sm_arr[hb >> 1] = sx * (float)s32;
+                }
+            }
+        }
+    }
+    if (tr) tr[5] = globaltimer_ns();
+    if (norm) {
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+    }
+    named_bar_sync(1, NT);
+    float scale = 1.f;
+    if (norm) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += red[w];
+        scale = 1.0f / sqrtf(tot / (float)K + p.eps);
+    }
+    return scale;
+}
+
 // x is staged in nseg pieces of seg_cols columns (narrow rows: one piece = the whole row; wide rows: one K-segment at
 // a time through TWO buffers, the bulk copy of piece s+2 issued as soon as piece s has been snapped).
 template <int ABITS, int NW>

@@ -62,6 +62,7 @@ struct GemvParams {
     const StepState* st;   // position (EPI_QKV) / done flag
     // ring (stand-alone kernel; the persistent kernel has one ring for all phases)
     unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps of this launch (first / last CTA)
+    int hb256;             // stand-alone kernel: half-block prologue with 256-bit loads straight from global memory (gemv_core.cuh)
     int xraw_bytes;        // > 0: stand-alone kernel stages x raw (bulk copies) in a buffer of this size after the planes
     int xraw_nseg;         // pieces x is staged in: 1 (narrow rows) or the K-segments, two buffers deep (wide rows)
     int polite_tracks;     // > 0: only the first polite_tracks producer lanes prefetch before griddepcontrol.wait (see gemv.cu)
@@ -81,6 +82,7 @@ size_t gemv_smem_bytes(int cols, int n_slots, int slot_bytes);
 // slot size the items must fit.  Returns false if the shape is outside the kernel's envelope.
 bool gemv_plan(GemvParams& p, const GemvMat* mats, int nmat, bool pair, int cols, int slot_bytes);
 cudaError_t gemv_configure();   // opt-in to large dynamic shared memory (once per process)
+bool gemv_prologue_variants(int consumer_warps);   // are the specialised prologues (raw staging, 256-bit loads) compiled for this width?
 cudaError_t gemv_launch(const GemvParams& p, int abits, int consumer_warps, int n_ctas, bool pdl, cudaStream_t s);
 // (abits, consumer_warps) combinations that are compiled: abits in {16, 8} x warps in {8, 12, 16}
 bool gemv_variant_ok(int abits, int consumer_warps);
