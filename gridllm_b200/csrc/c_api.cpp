@@ -108,6 +108,15 @@ int gl_last_logits(gl_engine* e, int32_t step, float* out, int32_t n_vocab) {
     return ret(e->impl->last_logits(step, out, n_vocab));
 }
 
+int gl_sample_logits(gl_engine* e, const float* logits, int32_t n_vocab, const gl_sample_opts* opts, int32_t out_index, int32_t* id,
+                     float* logprob) {
+    if (!e || !logits || !opts) return bad("gl_sample_logits: null argument");
+    int tid = 0;
+    const int rc = ret(e->impl->sample_logits(logits, n_vocab, *opts, out_index, &tid, logprob));
+    if (rc == GL_OK && id) *id = tid;
+    return rc;
+}
+
 int gl_gemv(gl_engine* e, int ggml_type, const void* w_host, int32_t rows, int32_t cols, const float* x, float* y, int32_t iters,
             float* kernel_ms) {
     if (!e) return bad("gl_gemv: null engine");

@@ -19,6 +19,11 @@ struct StepState {
     int n_stop;
     int stop_ids[8];
     unsigned bar_base;  // epoch of the persistent kernel's grid barrier (decode_mega.cu)
+    // sampling (sampler.cu); temperature 0 = greedy
+    float temperature;
+    int top_k;          // <= 0 or > SAMPLE_MAX_K: the SAMPLE_MAX_K best logits
+    float top_p;        // 1 = off
+    unsigned seed_lo, seed_hi;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -80,6 +80,8 @@ Engine::~Engine() {
     if (g_nohead_) cudaGraphExecDestroy(g_nohead_);
     if (g_head_) cudaGraphExecDestroy(g_head_);
     if (g_head_keep_) cudaGraphExecDestroy(g_head_keep_);
+    if (g_head_s_) cudaGraphExecDestroy(g_head_s_);
+    if (g_head_s_keep_) cudaGraphExecDestroy(g_head_s_keep_);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     for (void* p : allocs_) cudaFree(p);
     for (void* p : pf_allocs_) cudaFree(p);
@@ -171,6 +173,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     hb256_ = env_int("GL_HB256", 1) != 0;
     xraw_wide_ = env_int("GL_XRAW_WIDE", 0) != 0;        // measured (run 49): no gain -- each 14 KB piece waits ~1 us for its bulk copy
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
+    l2pf_kb_ = std::max(0, env_int("GL_L2PF_KB", 0));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -387,6 +390,12 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
         for (int i = 0; i < so->n_stop_ids && h.n_stop < 8; ++i) h.stop_ids[h.n_stop++] = so->stop_ids[i];
     }
     h.bar_base = 0;
+    sampled_ = so && so->temperature > 0.f;
+    h.temperature = so ? so->temperature : 0.f;
+    h.top_k = so ? so->top_k : 0;
+    h.top_p = (so && so->top_p > 0.f) ? so->top_p : 1.f;
+    h.seed_lo = so ? (unsigned)(so->seed & 0xffffffffull) : 0u;
+    h.seed_hi = so ? (unsigned)(so->seed >> 32) : 0u;
     if (bar_counter_) CU(cudaMemsetAsync(bar_counter_, 0, 4, stream_));
     CU(cudaMemcpyAsync(st_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
     CU(cudaStreamSynchronize(stream_));     // h is on the stack
@@ -500,6 +509,14 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
             const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows, L.wo.tile_rows}};
             p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
             p.polite_tracks = polite_tracks_;      // resident beside the attention CTAs: prefetch politely (gemv.cu)
+            if (l2pf_kb_ > 0 && L.wgate.quantized() && L.wgate.type == L.wup.type) {
+                // while attn_output waits for the attention (7 us of idle HBM), pull the head of gate / up into L2
+                const int rpi = item_rows(L.wgate.type) / 2;
+                p.pf_w[0] = L.wgate.w; p.pf_w[1] = L.wup.w;
+                p.pf_item_bytes = rpi * (n_embd_ / 256) * quant_block_bytes(L.wgate.type);
+                p.pf_items = (n_ff_ + rpi - 1) / rpi;
+                p.pf_max = l2pf_kb_ * 1024;
+            }
             ST(enqueue_gemv(s, p, mo, 1, false, n_head_ * hd_, n_launch));
             GemvParams g{};
             const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.tile_rows}, {L.wup.w, L.wup.type, L.wup.rows, L.wup.tile_rows}};
@@ -542,7 +559,8 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
         ST(plain_gemv(s, output_, xn_, logits_, n_launch));
     }
     SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_, sample_scratch_};
-    CU(sample_greedy_launch(sp, pdl && fused_, s));
+    if (sampled_) CU(sample_topk_launch(sp, pdl && fused_, s));      // temperature > 0: seeded top-k / top-p draw (sampler.cu)
+    else CU(sample_greedy_launch(sp, pdl && fused_, s));
     ++*n_launch;
     return {};
 }
@@ -572,14 +590,16 @@ Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
         if (n_head > 0) ST(launch_mega(n_head, true, keep_logits));
         return {};
     }
-    if (keep_logits && use_graph_ && !g_head_keep_) {
+    // the step with a head exists in four captured variants (greedy / sampled x plain / logits kept); all but the first lazily
+    cudaGraphExec_t* head = sampled_ ? (keep_logits ? &g_head_s_keep_ : &g_head_s_) : (keep_logits ? &g_head_keep_ : &g_head_);
+    if (use_graph_ && n_head > 0 && !*head) {
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-        Status s = enqueue_step(stream_, true, true, &dummy);
+        Status s = enqueue_step(stream_, true, keep_logits, &dummy);
         cudaError_t e = cudaStreamEndCapture(stream_, &g);
         if (!s.ok()) { if (g) cudaGraphDestroy(g); return s; }
         if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&g_head_keep_, g, 0);
+        e = cudaGraphInstantiate(head, g, 0);
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
     }
@@ -588,7 +608,7 @@ Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
         else ST(enqueue_step(stream_, false, false, &dummy));
     }
     for (int i = 0; i < n_head; ++i) {
-        if (use_graph_) CU(cudaGraphLaunch(keep_logits ? g_head_keep_ : g_head_, stream_));
+        if (use_graph_) CU(cudaGraphLaunch(*head, stream_));
         else ST(enqueue_step(stream_, true, keep_logits, &dummy));
     }
     return {};
@@ -713,7 +733,8 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
     const int64_t t0 = now_ns();
     if (n_prompt <= 0 || !prompt) return fail(GL_ERR_INVALID, "empty prompt");
     const int n_pred = so.num_predict > 0 ? so.num_predict : 128;     // OllamaService.ts:105
-    if (so.temperature > 0.f) return fail(GL_ERR_UNSUPPORTED, "only greedy decoding (temperature 0) is on the hot path");
+    if (!(so.temperature >= 0.f) || !std::isfinite(so.temperature)) return fail(GL_ERR_INVALID, "temperature must be a finite number >= 0");
+    if (so.temperature > 0.f && use_mega_) return fail(GL_ERR_UNSUPPORTED, "the persistent decode kernel (GL_MEGA=1) samples greedily only");
     for (int i = 0; i < n_prompt; ++i)
         if (prompt[i] < 0 || prompt[i] >= n_vocab_) return fail(GL_ERR_INVALID, "prompt token id out of range");
     ST(kv_reset());
@@ -726,6 +747,7 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
             logits_keep_ = p;
             keep_cap_ = n_pred;
             if (g_head_keep_) { cudaGraphExecDestroy(g_head_keep_); g_head_keep_ = nullptr; }
+            if (g_head_s_keep_) { cudaGraphExecDestroy(g_head_s_keep_); g_head_s_keep_ = nullptr; }
         }
     }
     CU(cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_));
@@ -806,6 +828,31 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
 Status Engine::last_logits(int step, float* out, int n_vocab) {
     if (!logits_keep_ || step < 0 || step >= keep_cap_ || n_vocab != n_vocab_) return fail(GL_ERR_INVALID, "no kept logits for that step");
     CU(cudaMemcpy(out, logits_keep_ + (size_t)step * n_vocab_, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost));
+    return {};
+}
+
+// The sampler alone on caller-supplied logits (parity tests of the draw against oracle/sampler.py).  Rewinds the sequence.
+Status Engine::sample_logits(const float* logits, int n_vocab, const gl_sample_opts& so, int out_index, int* id, float* logprob) {
+    CU(cudaSetDevice(device_));
+    if (!logits || n_vocab != n_vocab_) return fail(GL_ERR_INVALID, "logits must hold n_vocab values");
+    if (out_index < 0 || out_index >= max_out_) return fail(GL_ERR_INVALID, "output index out of range");
+    if (!(so.temperature >= 0.f) || !std::isfinite(so.temperature)) return fail(GL_ERR_INVALID, "temperature must be a finite number >= 0");
+    ST(kv_reset());
+    gl_sample_opts o = so;
+    o.ignore_eos = 1;
+    ST(set_state(0, 0, 0, out_index, &o));
+    CU(cudaMemcpyAsync(logits_, logits, (size_t)n_vocab_ * 4, cudaMemcpyHostToDevice, stream_));
+    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, nullptr, max_out_, sample_scratch_};
+    if (sampled_) CU(sample_topk_launch(sp, false, stream_));
+    else CU(sample_greedy_launch(sp, false, stream_));
+    int tid = 0;
+    float lp = 0.f;
+    CU(cudaMemcpyAsync(&tid, out_ids_ + out_index, 4, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaMemcpyAsync(&lp, out_lp_ + out_index, 4, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaStreamSynchronize(stream_));
+    ST(kv_reset());
+    if (id) *id = tid;
+    if (logprob) *logprob = lp;
     return {};
 }
 

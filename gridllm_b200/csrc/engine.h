@@ -55,6 +55,7 @@ public:
                     int32_t* out_ids, float* out_lp, gl_gen_stats* stats);
     Status embed(const int32_t* ids, const int32_t* offs, int n_seq, float* out, gl_gen_stats* stats);
     Status last_logits(int step, float* out, int n_vocab);
+    Status sample_logits(const float* logits, int n_vocab, const gl_sample_opts& so, int out_index, int* id, float* logprob);
     Status gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms);
     Status gemv_tensor(const std::string& name, const float* x, float* y, int iters, int flush, float* ms, uint64_t* wbytes);
     Status rmsnorm(const float* x, const float* w, int n, float eps, float* y);
@@ -107,6 +108,9 @@ private:
     int ring_depth_ = 2;       // ring slots per consumer warp (track depth, gemv_core.cuh)
     int ring_depth_max_ = 3;
     int polite_tracks_ = 3;    // attn_output: producer lanes that may prefetch before the attention kernel is done (0: all)
+    // attn_output: KB of gate and of up (each, per CTA) prefetched into L2 behind the attention (GL_L2PF_KB; 0: off).  Measured
+    // (run 55): 64 KB -1 %, 128 KB 0, 224 KB +5 % per token -- the prefetch delays the attention's own tail by what it saves.
+    int l2pf_kb_ = 0;
     bool xraw_wide_ = false;   // wide rows: the same through two K-segment buffers (opt-in: GL_XRAW_WIDE=1)
     // GEMV prologue variant.  Every GEMV launch of a step should be the SAME kernel: two variants alternating (61 + 68 KB of
     // code, plus 30 KB of attention) overflow the SM's instruction cache and cost 0.5 us per launch (runs 52 / 53).
@@ -163,7 +167,8 @@ private:
     int max_out_ = 0;
     int host_pos_ = 0;
 
-    cudaGraphExec_t g_nohead_ = nullptr, g_head_ = nullptr, g_head_keep_ = nullptr;
+    cudaGraphExec_t g_nohead_ = nullptr, g_head_ = nullptr, g_head_keep_ = nullptr, g_head_s_ = nullptr, g_head_s_keep_ = nullptr;
+    bool sampled_ = false;     // the running request draws from the distribution (temperature > 0) instead of taking the argmax
     int launches_nohead_ = 0, launches_head_ = 0;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t load_ns_ = 0;

@@ -66,6 +66,12 @@ struct GemvParams {
     int xraw_bytes;        // > 0: stand-alone kernel stages x raw (bulk copies) in a buffer of this size after the planes
     int xraw_nseg;         // pieces x is staged in: 1 (narrow rows) or the K-segments, two buffers deep (wide rows)
     int polite_tracks;     // > 0: only the first polite_tracks producer lanes prefetch before griddepcontrol.wait (see gemv.cu)
+    // optional L2 prefetch of the NEXT kernel's weights by an idle producer lane (a kernel that waits long for its upstream:
+    // attn_output behind the attention).  CTA c requests the first pf_max bytes of the range the next kernel's CTA c will read.
+    const uint8_t* pf_w[2];
+    int pf_item_bytes;     // bytes of one item in each matrix
+    int pf_items;          // items of the next kernel (dealt to CTAs by cta_range)
+    int pf_max;            // bytes per matrix and CTA; 0: off
     int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
     int depth;
     int slot_bytes;
@@ -134,6 +140,10 @@ constexpr int SAMPLE_CTAS = 64;
 constexpr int SAMPLE_SCRATCH_FLOATS = 3 * SAMPLE_CTAS + 1;
 // greedy: argmax + log-softmax of the winner; advances StepState (pos+1, token=argmax, out_idx+1).
 cudaError_t sample_greedy_launch(const SampleParams& p, bool pdl, cudaStream_t s);
+// temperature / top-k / top-p draw with a counter-based generator (sampler.cu); same state update as the greedy sampler.
+// Candidates are the top_k best logits, at most SAMPLE_MAX_K (top_k <= 0 "off" means SAMPLE_MAX_K, not the whole vocabulary).
+constexpr int SAMPLE_MAX_K = 1024;
+cudaError_t sample_topk_launch(const SampleParams& p, bool pdl, cudaStream_t s);
 // sequential-prefill step without sampling: pos += 1
 cudaError_t advance_launch(StepState* st, bool pdl, cudaStream_t s);
 

@@ -26,7 +26,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 # every symbol include/gridllm_native.h declares (tests/test_abi.py checks the library exports all)
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
-    "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_generate", "gl_embed", "gl_last_logits",
+    "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
     lib.gl_generate.argtypes = [vp, i32p, i32, C.POINTER(SampleOpts), TOKEN_CB, vp, i32p, f32p, C.POINTER(GenStats)]
     lib.gl_embed.argtypes = [vp, i32p, i32p, i32, f32p, C.POINTER(GenStats)]
     lib.gl_last_logits.argtypes = [vp, i32, f32p, i32]
+    lib.gl_sample_logits.argtypes = [vp, f32p, i32, C.POINTER(SampleOpts), i32, i32p, f32p]
     lib.gl_gemv.argtypes = [vp, C.c_int, vp, i32, i32, f32p, f32p, i32, f32p]
     lib.gl_gemv_model_tensor.argtypes = [vp, C.c_char_p, f32p, f32p, i32, i32, f32p, C.POINTER(C.c_uint64)]
     lib.gl_rmsnorm.argtypes = [vp, f32p, f32p, i32, C.c_float, f32p]
@@ -178,10 +179,12 @@ class Engine:
     # ---- hot path ---------------------------------------------------------------------------
     def generate(self, prompt: Sequence[int], num_predict: int = 128, ignore_eos: bool = False,
                  on_token: Optional[Callable[[int, float, bytes], bool]] = None, want_logits: bool = False,
-                 stop_ids: Sequence[int] = ()) -> Generation:
+                 stop_ids: Sequence[int] = (), temperature: float = 0.0, top_k: int = 0, top_p: float = 1.0,
+                 seed: int = 0) -> Generation:
         p = np.ascontiguousarray(prompt, dtype=np.int32)
         so = SampleOpts()
-        so.num_predict, so.temperature, so.top_p, so.ignore_eos, so.want_logits = num_predict, 0.0, 1.0, int(ignore_eos), int(want_logits)
+        so.num_predict, so.ignore_eos, so.want_logits = num_predict, int(ignore_eos), int(want_logits)
+        so.temperature, so.top_k, so.top_p, so.seed = float(temperature), int(top_k), float(top_p), int(seed) & (2**64 - 1)
         stops = np.ascontiguousarray(stop_ids, dtype=np.int32)
         so.n_stop_ids = len(stops)
         so.stop_ids = _i32p(stops) if len(stops) else None
@@ -198,6 +201,17 @@ class Engine:
         if rc != GL_OK and rc != GL_ERR_CANCELLED:
             _check(rc)
         return Generation(ids[: st.eval_count].copy(), lps[: st.eval_count].copy(), st)
+
+    def sample_logits(self, logits: np.ndarray, temperature: float, top_k: int = 0, top_p: float = 1.0, seed: int = 0,
+                      out_index: int = 0):
+        """The sampler alone (gl_sample_logits): (token id, logprob) for output number out_index of such a request."""
+        a = np.ascontiguousarray(logits, dtype=np.float32)
+        so = SampleOpts()
+        so.num_predict, so.ignore_eos = 1, 1
+        so.temperature, so.top_k, so.top_p, so.seed = float(temperature), int(top_k), float(top_p), int(seed) & (2**64 - 1)
+        tid, lp = C.c_int32(0), C.c_float(0.0)
+        _check(self._lib.gl_sample_logits(self._h, _f32p(a), len(a), C.byref(so), out_index, C.byref(tid), C.byref(lp)))
+        return int(tid.value), float(lp.value)
 
     def last_logits(self, step: int) -> np.ndarray:
         out = np.empty(self.info.n_vocab, dtype=np.float32)

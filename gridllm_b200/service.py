@@ -17,6 +17,7 @@ import asyncio
 import hashlib
 import os
 import queue
+import secrets
 import threading
 import time
 from datetime import datetime, timezone
@@ -38,8 +39,15 @@ def _now_iso() -> str:
 class NativeInferenceService:
     """One engine = one GPU = one loaded model (one service per worker id)."""
 
-    def __init__(self, models: Dict[str, str], device: int = 0, max_ctx: int = 0, **engine_kw):
-        """models: Ollama-style model name -> GGUF path."""
+    # what Ollama applies when a request leaves the sampling options out [external: Ollama's documented parameter defaults]
+    OLLAMA_SAMPLING_DEFAULTS = {"temperature": 0.8, "top_k": 40, "top_p": 0.9}
+
+    def __init__(self, models: Dict[str, str], device: int = 0, max_ctx: int = 0,
+                 sampling_defaults: Optional[Dict[str, Any]] = None, **engine_kw):
+        """models: Ollama-style model name -> GGUF path.
+        sampling_defaults: options a request inherits when it does not carry them.  None = greedy (temperature 0, the
+        BASELINE.json configuration); pass OLLAMA_SAMPLING_DEFAULTS to behave like an Ollama worker for such requests."""
+        self._sampling_defaults = dict(sampling_defaults or {})
         self._paths = dict(models)
         self._device = device
         self._max_ctx = max_ctx
@@ -120,12 +128,29 @@ class NativeInferenceService:
 
     def _run(self, model: str, ids: np.ndarray, num_predict: int, options: Dict[str, Any], on_token=None):
         eng = self._engine(model)
-        temperature = options.get("temperature")
-        if temperature not in (None, 0, 0.0):
-            raise RuntimeError("only greedy decoding (temperature 0) is implemented on the native path")
+        kw = self._sampling(options)
         ignore_eos = bool(options.get("ignore_eos", False))
         with self._lock:
-            return eng, eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token)
+            return eng, eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token, **kw)
+
+    def _sampling(self, options: Dict[str, Any]) -> Dict[str, Any]:
+        """InferenceRequest.options.{temperature, top_k, top_p, seed} (client/src/types/index.ts:1-27; gateway ranges
+        server/src/routes/ollama.ts:26-48) -> gl_sample_opts.  temperature 0 (or absent, with the default configuration) is
+        greedy; a sampled request without a seed draws one, as Ollama does for seed 0 / absent."""
+        def opt(name):
+            v = options.get(name)
+            return self._sampling_defaults.get(name) if v is None else v
+        temperature = float(opt("temperature") or 0.0)
+        if not (temperature >= 0.0) or temperature == float("inf"):
+            raise RuntimeError("temperature must be a finite number >= 0")
+        if temperature == 0.0:
+            return {}
+        top_k = int(opt("top_k") or 0)
+        top_p = float(opt("top_p") if opt("top_p") is not None else 1.0)
+        seed = opt("seed")
+        if seed is None:
+            seed = secrets.randbits(63)
+        return {"temperature": temperature, "top_k": top_k, "top_p": top_p, "seed": int(seed)}
 
     def _response(self, request: InferenceRequest, eng: N.Engine, gen: N.Generation, text: str) -> InferenceResponse:
         st = gen.stats

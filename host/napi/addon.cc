@@ -167,6 +167,13 @@ napi_value Generate(napi_env env, napi_callback_info info) {
     if (napi_get_named_property(env, argv[2], "numPredict", &v) == napi_ok) napi_get_value_int32(env, v, &j->so.num_predict);
     bool b = false;
     if (napi_get_named_property(env, argv[2], "ignoreEos", &v) == napi_ok && napi_get_value_bool(env, v, &b) == napi_ok) j->so.ignore_eos = b;
+    // sampling options (InferenceRequest.options: client/src/types/index.ts:1-27); absent = greedy
+    double d = 0.0;
+    if (napi_get_named_property(env, argv[2], "temperature", &v) == napi_ok && napi_get_value_double(env, v, &d) == napi_ok) j->so.temperature = (float)d;
+    if (napi_get_named_property(env, argv[2], "topK", &v) == napi_ok) napi_get_value_int32(env, v, &j->so.top_k);
+    if (napi_get_named_property(env, argv[2], "topP", &v) == napi_ok && napi_get_value_double(env, v, &d) == napi_ok) j->so.top_p = (float)d;
+    bool lossless = false;
+    if (napi_get_named_property(env, argv[2], "seed", &v) == napi_ok) napi_get_value_bigint_uint64(env, v, &j->so.seed, &lossless);
     napi_valuetype vt;
     if (argc > 3 && napi_typeof(env, argv[3], &vt) == napi_ok && vt == napi_function) {
         napi_value name;

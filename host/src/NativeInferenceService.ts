@@ -63,11 +63,18 @@ export class NativeInferenceService {
 			eval_duration: st.evalDurationNs, context: Array.from(ids), system_fingerprint: "fp_gridllm_b200_native" };
 	}
 
+	// InferenceRequest.options -> gl_sample_opts; temperature absent / 0 = greedy, a sampled request without seed draws one
+	private sampleOpts(request: InferenceRequest) {
+		const o = request.options ?? {};
+		const temperature = o.temperature ?? 0;
+		return { numPredict: o.num_predict || 128, ignoreEos: !!o.ignore_eos, temperature, topK: o.top_k ?? 0, topP: o.top_p ?? 1,
+			seed: BigInt(o.seed ?? (temperature > 0 ? Math.floor(Math.random() * 2 ** 53) : 0)) };
+	}
+
 	async generateResponse(request: InferenceRequest): Promise<InferenceResponse> {   // :97-184
 		try {
 			const e = this.engine(request.model);
-			const out = await native.generate(e, this.ids(e, request), { numPredict: request.options?.num_predict || 128,
-				ignoreEos: !!request.options?.ignore_eos }, null);
+			const out = await native.generate(e, this.ids(e, request), this.sampleOpts(request), null);
 			return this.toResponse(request, native.detokenize(e, out.ids), out.ids, out.stats);
 		} catch (error) {
 			throw new Error(`Inference failed: ${error instanceof Error ? error.message : "Unknown error"}`);
@@ -79,8 +86,7 @@ export class NativeInferenceService {
 			const e = this.engine(request.model);
 			const queue: StreamResponse[] = [];
 			let wake: (() => void) | null = null;
-			const done = native.generate(e, this.ids(e, request), { numPredict: request.options?.num_predict || 128,
-				ignoreEos: !!request.options?.ignore_eos },
+			const done = native.generate(e, this.ids(e, request), this.sampleOpts(request),
 				(_id: number, _lp: number, piece: string) => { queue.push({ id: request.id, response: piece, done: false }); wake?.(); });
 			let finished = false;
 			done.then(() => { finished = true; wake?.(); }, () => { finished = true; wake?.(); });

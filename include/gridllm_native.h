@@ -74,10 +74,10 @@ typedef struct gl_model_info {
 
 typedef struct gl_sample_opts {
     int32_t  num_predict;     /* OllamaService.ts:105  max_tokens = options.num_predict || 128 */
-    float    temperature;     /* 0 = greedy (the parity configuration) */
-    int32_t  top_k;           /* 0 = off */
-    float    top_p;           /* 1 = off */
-    uint64_t seed;
+    float    temperature;     /* 0 = greedy (the parity configuration); > 0: draw from softmax(logits / temperature) */
+    int32_t  top_k;           /* candidates = the top_k best logits; <= 0 or > 1024: the 1024 best (not the whole vocabulary) */
+    float    top_p;           /* shortest prefix of the candidates whose mass reaches top_p; <= 0 or >= 1: off */
+    uint64_t seed;            /* the draw for output i depends on (seed, i) only: a request is reproducible */
     int32_t  ignore_eos;      /* 1: fixed-length generation (bench workloads) */
     int32_t  n_stop_ids;
     const int32_t* stop_ids;  /* extra stop token ids (host resolves stop strings) */
@@ -128,6 +128,12 @@ int  gl_embed(gl_engine* e, const int32_t* ids, const int32_t* seq_offsets, int3
               float* out, gl_gen_stats* stats);
 /* logits of generation step i of the last gl_generate that ran with want_logits=1 */
 int  gl_last_logits(gl_engine* e, int32_t step, float* out, int32_t n_vocab);
+
+/* the sampler alone on caller-supplied logits [n_vocab]: the token gl_generate would emit as output number out_index
+ * of a request with these options (temperature 0: argmax; else the seeded top-k / top-p draw), and its log-softmax.
+ * Parity tests of the draw against oracle/sampler.py.  Rewinds the sequence like gl_kv_reset(). */
+int  gl_sample_logits(gl_engine* e, const float* logits, int32_t n_vocab, const gl_sample_opts* opts, int32_t out_index,
+                      int32_t* id, float* logprob);
 
 /* ---- kernel-level entry points (parity tests and roofline measurement) ------------------ */
 /* y[rows] = W[rows x cols] (GGUF-layout blocks of ggml_type, host memory) * x[cols].

@@ -116,3 +116,26 @@ def test_workers_shard_requests_like_the_scheduler(tiny_gguf):
     ref.close()
     for s in svcs:
         s.close()
+
+
+def test_sampled_requests(svc):
+    """options.temperature / top_k / top_p / seed reach the native sampler: same seed -> same text, streamed or not;
+    another seed -> another draw; a sampled request without a seed still answers."""
+    opts = {"num_predict": 16, "ignore_eos": True, "temperature": 0.9, "top_k": 40, "top_p": 0.95, "seed": 7}
+    req = {"id": "t1", "model": "tiny:latest", "prompt": "once upon a time", "options": opts, "priority": "medium"}
+    a = _run(svc.generateResponse(req))
+    b = _run(svc.generateResponse(dict(req, id="t2")))
+    c = _run(svc.generateResponse(dict(req, id="t3", options=dict(opts, seed=8))))
+    assert a["context"] == b["context"] and a["response"] == b["response"] and a["eval_count"] == 16
+    assert a["context"] != c["context"]
+    greedy = _run(svc.generateResponse(dict(req, id="t4", options=dict(opts, temperature=0))))
+    assert greedy["context"] != a["context"]
+
+    async def collect():
+        return [ch async for ch in svc.generateStreamResponse(dict(req, id="t5", stream=True))]
+    chunks = _run(collect())
+    assert "".join(ch["response"] for ch in chunks) == a["response"]
+    d = _run(svc.generateResponse(dict(req, id="t6", options={k: v for k, v in opts.items() if k != "seed"})))
+    assert d["eval_count"] == 16
+    with pytest.raises(RuntimeError, match="Inference failed"):
+        _run(svc.generateResponse(dict(req, id="t7", options=dict(opts, temperature=-1))))
