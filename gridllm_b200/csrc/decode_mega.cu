@@ -204,9 +204,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, G = gridDim.x;
     const int fixed = gemv_fixed_smem(mp.max_cols);
-    MegaPhase* sdesc = reinterpret_cast<MegaPhase*>(smem + fixed);              // 2 x 256 B: phase descriptors, double-buffered
-    int* sflag = reinterpret_cast<int*>(smem + fixed + 512);
-    float* sstat = reinterpret_cast<float*>(smem + fixed + 512 + 16);            // 3 x NW floats
+    constexpr int DESC_SLOT = 384;                                                // bytes per descriptor buffer
+    MegaPhase* sdesc = reinterpret_cast<MegaPhase*>(smem + fixed);              // 2 x 384 B: phase descriptors, double-buffered
+    int* sflag = reinterpret_cast<int*>(smem + fixed + 2 * DESC_SLOT);
+    float* sstat = reinterpret_cast<float*>(smem + fixed + 2 * DESC_SLOT + 16);  // 3 x NW floats (< 1024 in all)
     uint8_t* abuf = smem + fixed + 1024;                                          // attention staging: K/V tiles + mbarrier
     uint64_t* abar = reinterpret_cast<uint64_t*>(abuf + ATTN_SMEM_BYTES - 64);
     uint32_t aparity = 0;
@@ -226,11 +227,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
     }
 
     // ============ consumers ==================================================================================
-    static_assert(sizeof(MegaPhase) <= 256 && sizeof(MegaPhase) % 4 == 0, "descriptor slot");
+    static_assert(sizeof(MegaPhase) <= DESC_SLOT && sizeof(MegaPhase) % 4 == 0, "descriptor slot");
     constexpr int DESC_WORDS = sizeof(MegaPhase) / 4;
     auto prefetch_desc = [&](int ph, int slot) {      // static data: plain loads; visible after the next barrier
         if (tid < DESC_WORDS)
-            reinterpret_cast<uint32_t*>(sdesc)[slot * 64 + tid] = reinterpret_cast<const uint32_t*>(mp.phases + ph)[tid];
+            reinterpret_cast<uint32_t*>(sdesc)[slot * (DESC_SLOT / 4) + tid] = reinterpret_cast<const uint32_t*>(mp.phases + ph)[tid];
     };
     StepState* st = mp.st;
     const unsigned bar_base = __ldcg(&st->bar_base);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) decode_mega_kernel(const __g
         const EpiCtx step_ec{step_pos, __ldcg(mp.page_table + step_pos / KV_PAGE_TOKENS)};
 
         for (int ph = 0; ph < mp.n_phases; ++ph) {
-            const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<const uint8_t*>(sdesc) + dslot * 256);
+            const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<const uint8_t*>(sdesc) + dslot * DESC_SLOT);
             const int kind = P.kind;
             unsigned long long* tr = (mp.trace != nullptr && tid == 0) ? mp.trace + ((size_t)cta * (mp.n_phases + 1) + ph) * 4 : nullptr;
             if (tr) tr[0] = gtime();

@@ -173,7 +173,6 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     hb256_ = env_int("GL_HB256", 1) != 0;
     xraw_wide_ = env_int("GL_XRAW_WIDE", 0) != 0;        // measured (run 49): no gain -- each 14 KB piece waits ~1 us for its bulk copy
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
-    l2pf_kb_ = std::max(0, env_int("GL_L2PF_KB", 0));
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -509,14 +508,6 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
             const GemvMat mo[1] = {{L.wo.w, L.wo.type, L.wo.rows, L.wo.tile_rows}};
             p.x = attn_; p.epi = EPI_ADD; p.out = x_; p.resid = x_; p.st = st_;
             p.polite_tracks = polite_tracks_;      // resident beside the attention CTAs: prefetch politely (gemv.cu)
-            if (l2pf_kb_ > 0 && L.wgate.quantized() && L.wgate.type == L.wup.type) {
-                // while attn_output waits for the attention (7 us of idle HBM), pull the head of gate / up into L2
-                const int rpi = item_rows(L.wgate.type) / 2;
-                p.pf_w[0] = L.wgate.w; p.pf_w[1] = L.wup.w;
-                p.pf_item_bytes = rpi * (n_embd_ / 256) * quant_block_bytes(L.wgate.type);
-                p.pf_items = (n_ff_ + rpi - 1) / rpi;
-                p.pf_max = l2pf_kb_ * 1024;
-            }
             ST(enqueue_gemv(s, p, mo, 1, false, n_head_ * hd_, n_launch));
             GemvParams g{};
             const GemvMat mgu[2] = {{L.wgate.w, L.wgate.type, L.wgate.rows, L.wgate.tile_rows}, {L.wup.w, L.wup.type, L.wup.rows, L.wup.tile_rows}};

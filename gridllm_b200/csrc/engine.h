@@ -108,9 +108,6 @@ private:
     int ring_depth_ = 2;       // ring slots per consumer warp (track depth, gemv_core.cuh)
     int ring_depth_max_ = 3;
     int polite_tracks_ = 3;    // attn_output: producer lanes that may prefetch before the attention kernel is done (0: all)
-    // attn_output: KB of gate and of up (each, per CTA) prefetched into L2 behind the attention (GL_L2PF_KB; 0: off).  Measured
-    // (run 55): 64 KB -1 %, 128 KB 0, 224 KB +5 % per token -- the prefetch delays the attention's own tail by what it saves.
-    int l2pf_kb_ = 0;
     bool xraw_wide_ = false;   // wide rows: the same through two K-segment buffers (opt-in: GL_XRAW_WIDE=1)
     // GEMV prologue variant.  Every GEMV launch of a step should be the SAME kernel: two variants alternating (61 + 68 KB of
     // code, plus 30 KB of attention) overflow the SM's instruction cache and cost 0.5 us per launch (runs 52 / 53).

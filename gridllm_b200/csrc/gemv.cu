@@ -55,19 +55,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) gemv_kernel(const __grid_con
         // flood the SM's request queue while those are still on their latency-critical tail: the attention merge took
         // 4.4 us instead of ~1.5 behind 110 KB of early weight prefetch (run 43).  Such a launch lets only a few lanes
         // prefetch early; the others start when the upstream kernel is done.
-        if (p.pf_max > 0 && lane == 30) {
-            // HBM idles while this kernel waits for its upstream: pull the head of the next kernel's weight stream into L2
-            const WorkRange wr = cta_range(p.pf_items, blockIdx.x, gridDim.x);
-            const long long len = min((long long)(wr.b - wr.a) * p.pf_item_bytes, (long long)p.pf_max) & ~15ll;
-            for (int m = 0; m < 2; ++m) {
-                if (p.pf_w[m] == nullptr) continue;
-                const uint8_t* src = p.pf_w[m] + (size_t)wr.a * p.pf_item_bytes;
-                for (long long o = 0; o < len; o += 16384) {
-                    const unsigned n = (unsigned)min(16384ll, len - o);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + o), "r"(n) : "memory");
-                }
-            }
-        }
         if (p.polite_tracks > 0 && lane >= p.polite_tracks) pdl_wait();
         Track trk{0u, 0u};
         gemv_produce(p.pd, ring, trk, lane, blockIdx.x, gridDim.x);

@@ -66,12 +66,6 @@ struct GemvParams {
     int xraw_bytes;        // > 0: stand-alone kernel stages x raw (bulk copies) in a buffer of this size after the planes
     int xraw_nseg;         // pieces x is staged in: 1 (narrow rows) or the K-segments, two buffers deep (wide rows)
     int polite_tracks;     // > 0: only the first polite_tracks producer lanes prefetch before griddepcontrol.wait (see gemv.cu)
-    // optional L2 prefetch of the NEXT kernel's weights by an idle producer lane (a kernel that waits long for its upstream:
-    // attn_output behind the attention).  CTA c requests the first pf_max bytes of the range the next kernel's CTA c will read.
-    const uint8_t* pf_w[2];
-    int pf_item_bytes;     // bytes of one item in each matrix
-    int pf_items;          // items of the next kernel (dealt to CTAs by cta_range)
-    int pf_max;            // bytes per matrix and CTA; 0: off
     int n_tracks;          // consumer warps that take items; each owns `depth` ring slots (gemv_core.cuh)
     int depth;
     int slot_bytes;
