@@ -18,6 +18,8 @@ from oracle import gguf_synth as S
 S.build_model('/dev/shm/prof_llama3_8b.gguf', S.LLAMA3_8B, 'q4_k_m', seed=1234, mode='random', with_vocab=False)
 PY
 timeout 300 python tools/perop_trace.py 576 > gpurun_out/perop_trace_576.log 2>&1
+timeout 300 python tools/sample_probe.py > gpurun_out/sample_probe.log 2>&1
+grep -h '^{' gpurun_out/sample_probe.log
 timeout 900 ncu --set full --clock-control none --import-source on -s 342 -c 5 -o gpurun_out/layer_full -f python tools/profile_decode.py 3 576 > gpurun_out/prof_layer.log 2>&1
 echo "ncu layer rc=$?" >> gpurun_out/prof_layer.log
 timeout 900 ncu --set full --clock-control none -k regex:"gemv_kernel" -s 515 -c 1 -o gpurun_out/head_full -f python tools/profile_decode.py 3 576 > gpurun_out/prof_head.log 2>&1
