@@ -4,16 +4,22 @@
 // Reference call site: the prompt-evaluation phase inside Ollama behind OllamaService.generate*Response /
 // generateEmbedding (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237, 633-636).
 //
-// Shape of the kernel (one 128 x 128 output tile per CTA, 6 warps, everything asynchronous, hand-written PTX):
+// Shape of the kernel (persistent: one CTA per SM walks 128 x 128 output tiles, 6 warps, everything asynchronous,
+// hand-written PTX; the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1
+// and the TMA ring never drains between tiles):
 //   warp 0 / one lane : TMA producer -- cp.async.bulk.tensor.2d of a 128 x 64 A box and a 128 x 64 B box per K-step
 //                       into a 6-stage mbarrier ring (128-byte swizzle, 32 KB per stage);
 //   warp 1 / one lane : MMA issuer   -- per stage four tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16), operands
-//                       addressed by shared-memory matrix descriptors, accumulator = 128 TMEM columns;
-//                       tcgen05.commit hands the stage back to the producer and, after the last K-step, wakes the epilogue;
+//                       addressed by shared-memory matrix descriptors, accumulator = 128 of the CTA's 256 TMEM columns
+//                       (tiles alternate between the two halves); tcgen05.commit hands the stage back to the producer and,
+//                       after the last K-step of a tile, wakes the epilogue;
 //   warps 2..5        : epilogue     -- tcgen05.ld 32 lanes x 32 columns at a time (warp w may touch TMEM lanes
-//                       32*(w%4)..), fused epilogue (fp32 store, residual add, 16-bit store, SiLU*mul), global stores.
+//                       32*(w%4)..), fused epilogue (fp32 store, residual add, 16-bit store, SiLU*mul), global stores;
+//                       then hands the accumulator half back to the MMA issuer (acc_empty).
 // SASS to look for: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit).
 #include <cuda.h>
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -28,7 +34,8 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
 constexpr int UMMA_K = 16;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2, STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
 constexpr int TC5_THREADS = 192;
-constexpr int TMEM_COLS = 128;
+constexpr int ACC_BUFS = 2;
+constexpr int TMEM_COLS = ACC_BUFS * BN;       // 256 of the SM's 512 columns
 constexpr size_t TC5_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
 struct Tc5Params {
@@ -144,13 +151,14 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* acc_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* acc_full = empty + STAGES;          // [ACC_BUFS] MMA issuer -> epilogue
+    uint64_t* acc_empty = acc_full + ACC_BUFS;    // [ACC_BUFS] epilogue (4 warps) -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_BUFS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // M tiles are the fast grid dimension: the (few) CTAs that share a weight tile run back to back and find it in L2
     // (N-major order re-read every weight byte from DRAM once per M tile: 943 MB for the 235 MB gate/up matrix, run 39)
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int tiles_m = (p.m + BM - 1) / BM, tiles_n = (p.n + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
     const int nk = (p.k + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -162,7 +170,10 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < ACC_BUFS; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
         fence_mbar_init();
     }
     if (warp == 2) {   // one warp allocates the accumulator's TMEM columns and publishes the base address
@@ -176,16 +187,19 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== TMA producer =====
+            // ===== TMA producer: the ring runs on across tile boundaries =====
             int st = 0;
             uint32_t ph = 0;
-            for (int kb = 0; kb < nk; ++kb) {
-                mbar_wait(&empty[st], ph ^ 1u);
-                uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
-                mbar_expect_tx(&full[st], STAGE_BYTES);
-                tma_load_2d(sa, &p.ta, kb * BK, m0, &full[st]);
-                tma_load_2d(sa + TILE_A_BYTES, &p.tb, kb * BK, n0, &full[st]);
-                if (++st == STAGES) { st = 0; ph ^= 1u; }
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&empty[st], ph ^ 1u);
+                    uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
+                    mbar_expect_tx(&full[st], STAGE_BYTES);
+                    tma_load_2d(sa, &p.ta, kb * BK, m0, &full[st]);
+                    tma_load_2d(sa + TILE_A_BYTES, &p.tb, kb * BK, n0, &full[st]);
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -196,36 +210,52 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int st = 0;
             uint32_t ph = 0;
-            for (int kb = 0; kb < nk; ++kb) {
-                mbar_wait(&full[st], ph);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&acc_empty[buf], aph ^ 1u);      // the epilogue has drained this half (free on its first use)
                 tc5_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&full[st], ph);
+                    tc5_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advancing K inside the swizzle atom: +32 bytes = +2 in the descriptor's 16-byte address units
-                    tc5_mma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advancing K inside the swizzle atom: +32 bytes = +2 in the descriptor's 16-byte address units
+                        tc5_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    tc5_commit(&empty[st]);                       // the stage is free once these MMAs have read it
+                    if (kb == nk - 1) tc5_commit(&acc_full[buf]); // ... and the accumulator is complete
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
-                tc5_commit(&empty[st]);                 // the stage is free once these MMAs have read it
-                if (kb == nk - 1) tc5_commit(acc_full); // ... and the accumulator is complete
-                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(acc_full, 0);
-        tc5_fence_after();
         const int q = warp & 3;                      // the TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+            tc5_fence_after();
+            const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            const int col0 = n0 + c * 32;
-            if (row < p.m && col0 < p.n) {
-                if (p.bf16) epilogue_row<__nv_bfloat16>(p, row, col0, v);
-                else epilogue_row<__half>(p, row, col0, v);
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+                const int col0 = n0 + c * 32;
+                if (row < p.m && col0 < p.n) {
+                    if (p.bf16) epilogue_row<__nv_bfloat16>(p, row, col0, v);
+                    else epilogue_row<__half>(p, row, col0, v);
+                }
             }
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp's quarter of the accumulator half is in registers / memory
         }
     }
     tc5_fence_before();
@@ -279,7 +309,11 @@ cudaError_t gemm_tc5_launch(const GemmParams& p, int a_rows_alloc, bool bf16, cu
     Tc5Params tp{};
     if (!make_map(&tp.ta, p.a, a_rows_alloc, p.k, p.lda, bf16) || !make_map(&tp.tb, p.b, p.n, p.k, p.ldb, bf16)) return cudaErrorInvalidValue;
     tp.c = p.c; tp.m = p.m; tp.n = p.n; tp.k = p.k; tp.ldc = p.ldc; tp.epi = p.epi; tp.bf16 = bf16 ? 1 : 0;
-    const dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)((p.n + BN - 1) / BN));
+    // persistent grid: one CTA per SM walks the tiles, M tiles fastest (the CTAs that share a weight tile run together)
+    static const int n_sm = []() { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
+    static const bool persist = []() { const char* e = getenv("GL_TC5_PERSIST"); return !(e && e[0] == '0'); }();
+    const int n_tiles = ((p.m + BM - 1) / BM) * ((p.n + BN - 1) / BN);
+    const dim3 grid((unsigned)(persist ? std::min(n_tiles, n_sm) : n_tiles));
     gemm_tc5_kernel<<<grid, TC5_THREADS, TC5_SMEM, s>>>(tp);
     return cudaGetLastError();
 }

@@ -177,6 +177,42 @@ def test_batched_prefill_matches_oracle(fixture, n_tok, request):
     es.close()
 
 
+@pytest.fixture(scope="module")
+def wide_ffn_gguf(tmp_models):
+    """One layer, d = 256, n_ff = 6400: with a 300-token prompt the gate/up GEMM has 3 x 100 output tiles -- more than two
+    per SM, so the persistent tcgen05 kernel reuses both halves of its double-buffered TMEM accumulator and its TMA ring
+    runs on across tile boundaries."""
+    from oracle import gguf_synth as S
+    shape = S.LlamaShape("wide-ffn-synth", 1, 256, 4, 2, 6400, 512, 10000.0, 1e-5, 512)
+    p = str(tmp_models / "wide_ffn.gguf")
+    S.build_model(p, shape, "q4_k_m", seed=7)
+    return p
+
+
+@pytest.mark.parametrize("n_tok", [129, 300])
+def test_batched_prefill_many_tiles_per_sm(wide_ffn_gguf, n_tok, monkeypatch):
+    from oracle import llama_oracle as O
+    m = O.load_gguf(wide_ffn_gguf)
+    toks = np.random.Generator(np.random.PCG64(3000 + n_tok)).integers(0, m.n_vocab - 3, size=n_tok)
+    orc = O.LlamaOracle(m, act="exact", kv_f16=True)
+    for t in toks:
+        ref = orc.step(int(t))
+    scale = np.abs(ref).max()
+    e = _engine(wide_ffn_gguf, prefill_mode=0)
+    for _ in range(2):                                   # twice: barriers / TMEM are set up per launch
+        e.kv_reset()
+        lb = e.prefill(toks)
+        assert np.isfinite(lb).all()
+        assert np.abs(lb - ref).max() <= 1e-2 * scale, (n_tok, np.abs(lb - ref).max(), scale)
+    e.close()
+    # one tile per CTA (the non-persistent grid) must give the same numbers: same tiles, same K order
+    monkeypatch.setenv("GL_PREFILL_TC5", "0")
+    e2 = _engine(wide_ffn_gguf, prefill_mode=0)
+    l2 = e2.prefill(toks)
+    e2.close()
+    assert np.abs(lb - l2).max() <= 1e-2 * scale
+
+
 def test_generate_with_batched_prefill(tiny128_gguf):
     from oracle import llama_oracle as O
     m = O.load_gguf(tiny128_gguf)
