@@ -273,6 +273,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(dalloc((void**)&part_ml_, (size_t)n_head_ * std::max(attn_splits_, 32) * 2 * 4));
     CU(dalloc((void**)&counters_, (size_t)n_kv_ * 4));
     CU(dalloc((void**)&sample_scratch_, (size_t)SAMPLE_SCRATCH_FLOATS * 4));
+    CU(dalloc((void**)&topk_scratch_, TOPK_SCRATCH_BYTES));
     n_pages_ = n_ctx_ / KV_PAGE_TOKENS;
     kv_layer_elems_ = (size_t)n_pages_ * n_kv_ * KV_PAGE_TOKENS * hd_;
     CU(dalloc((void**)&kcache_, kv_layer_elems_ * n_layer_ * sizeof(__half)));
@@ -549,10 +550,14 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
         CU(rmsnorm_launch(x_, output_norm_, n_embd_, eps_, xn_, s)); ++*n_launch;
         ST(plain_gemv(s, output_, xn_, logits_, n_launch));
     }
-    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_, sample_scratch_};
-    if (sampled_) CU(sample_topk_launch(sp, pdl && fused_, s));      // temperature > 0: seeded top-k / top-p draw (sampler.cu)
-    else CU(sample_greedy_launch(sp, pdl && fused_, s));
-    ++*n_launch;
+    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_, sample_scratch_, topk_scratch_};
+    if (sampled_) {      // temperature > 0: seeded top-k / top-p draw (sampler.cu)
+        CU(sample_topk_launch(sp, pdl && fused_, s));
+        *n_launch += sample_topk_launches(n_vocab_);
+    } else {
+        CU(sample_greedy_launch(sp, pdl && fused_, s));
+        ++*n_launch;
+    }
     return {};
 }
 
@@ -811,7 +816,7 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
         stats->load_duration_ns = load_ns_;
         stats->done_reason = done_reason;
         stats->kernel_launches = use_mega_ ? prefill_launches + (mega_launches_ - mega0) + (batched ? 2 : 0)
-                                           : prefill_launches + std::max(produced, 1) * launches_head_;
+                                           : prefill_launches + std::max(produced, 1) * (launches_head_ + (sampled_ ? sample_topk_launches(n_vocab_) - 1 : 0));
     }
     return cancelled ? fail(GL_ERR_CANCELLED, "cancelled by token callback") : Status{};
 }
@@ -833,7 +838,7 @@ Status Engine::sample_logits(const float* logits, int n_vocab, const gl_sample_o
     o.ignore_eos = 1;
     ST(set_state(0, 0, 0, out_index, &o));
     CU(cudaMemcpyAsync(logits_, logits, (size_t)n_vocab_ * 4, cudaMemcpyHostToDevice, stream_));
-    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, nullptr, max_out_, sample_scratch_};
+    SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, nullptr, max_out_, sample_scratch_, topk_scratch_};
     if (sampled_) CU(sample_topk_launch(sp, false, stream_));
     else CU(sample_greedy_launch(sp, false, stream_));
     int tid = 0;

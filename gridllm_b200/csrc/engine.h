@@ -147,6 +147,7 @@ private:
     float *part_o_ = nullptr, *part_ml_ = nullptr;
     unsigned* counters_ = nullptr;
     float* sample_scratch_ = nullptr;
+    unsigned long long* topk_scratch_ = nullptr;
     __half *kcache_ = nullptr, *vcache_ = nullptr;    // [layer][page][kv][16][hd]
     size_t kv_layer_elems_ = 0;
     int n_pages_ = 0;

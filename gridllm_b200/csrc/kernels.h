@@ -129,6 +129,7 @@ struct SampleParams {
     float* logits_keep;     // optional [max_steps][n_vocab] copy for parity tests
     int max_out;
     float* scratch;         // SAMPLE_SCRATCH_FLOATS floats, zeroed once: per-CTA (max, argmax, sum exp) + ticket
+    unsigned long long* topk_scratch;   // TOPK_SCRATCH_BYTES, zeroed once: two-stage top-k sampler (sampler.cu); may be null
 };
 constexpr int SAMPLE_CTAS = 64;
 constexpr int SAMPLE_SCRATCH_FLOATS = 3 * SAMPLE_CTAS + 1;
@@ -137,6 +138,10 @@ cudaError_t sample_greedy_launch(const SampleParams& p, bool pdl, cudaStream_t s
 // temperature / top-k / top-p draw with a counter-based generator (sampler.cu); same state update as the greedy sampler.
 // Candidates are the top_k best logits, at most SAMPLE_MAX_K (top_k <= 0 "off" means SAMPLE_MAX_K, not the whole vocabulary).
 constexpr int SAMPLE_MAX_K = 1024;
+constexpr int TOPK_FAST_K = 64;              // top_k up to this takes the two-stage path ...
+constexpr int TOPK_FAST_MAX_CTAS = 64;       // ... for vocabularies up to 64 x 2048 entries
+constexpr size_t TOPK_SCRATCH_BYTES = (size_t)TOPK_FAST_MAX_CTAS * TOPK_FAST_K * 8 + TOPK_FAST_MAX_CTAS * 8 + 16;
+int sample_topk_launches(int n_vocab);       // kernels sample_topk_launch enqueues (1 or 2)
 cudaError_t sample_topk_launch(const SampleParams& p, bool pdl, cudaStream_t s);
 // sequential-prefill step without sampling: pos += 1
 cudaError_t advance_launch(StepState* st, bool pdl, cudaStream_t s);

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "sampler or sampled or many_tiles or batched_prefill" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -n 15 gpurun_out/pytest_gpu.log
+timeout 400 python tools/sample_probe.py > gpurun_out/sample_probe.log 2>&1
+grep -h '^{' gpurun_out/sample_probe.log
