@@ -78,10 +78,9 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     if (g_nohead_) cudaGraphExecDestroy(g_nohead_);
-    if (g_head_) cudaGraphExecDestroy(g_head_);
-    if (g_head_keep_) cudaGraphExecDestroy(g_head_keep_);
-    if (g_head_s_) cudaGraphExecDestroy(g_head_s_);
-    if (g_head_s_keep_) cudaGraphExecDestroy(g_head_s_keep_);
+    for (auto& v : g_head_var_)
+        for (auto& g : v)
+            if (g) cudaGraphExecDestroy(g);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     for (void* p : allocs_) cudaFree(p);
     for (void* p : pf_allocs_) cudaFree(p);
@@ -390,7 +389,8 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
         for (int i = 0; i < so->n_stop_ids && h.n_stop < 8; ++i) h.stop_ids[h.n_stop++] = so->stop_ids[i];
     }
     h.bar_base = 0;
-    sampled_ = so && so->temperature > 0.f;
+    // 0 greedy; 1 two-stage top-k sampler (top_k <= 64); 2 single-CTA radix select (sampler.cu)
+    sampler_ = !(so && so->temperature > 0.f) ? 0 : (sample_topk_fast_applies(so->top_k, n_vocab_) ? 1 : 2);
     h.temperature = so ? so->temperature : 0.f;
     h.top_k = so ? so->top_k : 0;
     h.top_p = (so && so->top_p > 0.f) ? so->top_p : 1.f;
@@ -551,13 +551,9 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
         ST(plain_gemv(s, output_, xn_, logits_, n_launch));
     }
     SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_, sample_scratch_, topk_scratch_};
-    if (sampled_) {      // temperature > 0: seeded top-k / top-p draw (sampler.cu)
-        CU(sample_topk_launch(sp, pdl && fused_, s));
-        *n_launch += sample_topk_launches(n_vocab_);
-    } else {
-        CU(sample_greedy_launch(sp, pdl && fused_, s));
-        ++*n_launch;
-    }
+    if (sampler_ != 0) CU(sample_topk_launch(sp, sampler_ == 1, pdl && fused_, s));      // temperature > 0: seeded top-k / top-p draw (sampler.cu)
+    else CU(sample_greedy_launch(sp, pdl && fused_, s));
+    ++*n_launch;
     return {};
 }
 
@@ -574,7 +570,7 @@ Status Engine::build_graphs() {
         e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return fail(GL_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-        if (which == 0) { g_nohead_ = ge; launches_nohead_ = n; } else { g_head_ = ge; launches_head_ = n; }
+        if (which == 0) { g_nohead_ = ge; launches_nohead_ = n; } else { g_head_var_[0][0] = ge; launches_head_ = n; }
     }
     return {};
 }
@@ -586,8 +582,8 @@ Status Engine::run_steps(int n_nohead, int n_head, bool keep_logits) {
         if (n_head > 0) ST(launch_mega(n_head, true, keep_logits));
         return {};
     }
-    // the step with a head exists in four captured variants (greedy / sampled x plain / logits kept); all but the first lazily
-    cudaGraphExec_t* head = sampled_ ? (keep_logits ? &g_head_s_keep_ : &g_head_s_) : (keep_logits ? &g_head_keep_ : &g_head_);
+    // the step with a head exists in six captured variants (sampler x plain / logits kept); all but the first lazily
+    cudaGraphExec_t* head = &g_head_var_[sampler_][keep_logits ? 1 : 0];
     if (use_graph_ && n_head > 0 && !*head) {
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
@@ -742,8 +738,8 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
             allocs_.push_back(p);
             logits_keep_ = p;
             keep_cap_ = n_pred;
-            if (g_head_keep_) { cudaGraphExecDestroy(g_head_keep_); g_head_keep_ = nullptr; }
-            if (g_head_s_keep_) { cudaGraphExecDestroy(g_head_s_keep_); g_head_s_keep_ = nullptr; }
+            for (auto& v : g_head_var_)
+                if (v[1]) { cudaGraphExecDestroy(v[1]); v[1] = nullptr; }      // captured with the old logits buffer
         }
     }
     CU(cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_));
@@ -816,7 +812,7 @@ Status Engine::generate(const int32_t* prompt, int n_prompt, const gl_sample_opt
         stats->load_duration_ns = load_ns_;
         stats->done_reason = done_reason;
         stats->kernel_launches = use_mega_ ? prefill_launches + (mega_launches_ - mega0) + (batched ? 2 : 0)
-                                           : prefill_launches + std::max(produced, 1) * (launches_head_ + (sampled_ ? sample_topk_launches(n_vocab_) - 1 : 0));
+                                           : prefill_launches + std::max(produced, 1) * launches_head_;
     }
     return cancelled ? fail(GL_ERR_CANCELLED, "cancelled by token callback") : Status{};
 }
@@ -839,7 +835,7 @@ Status Engine::sample_logits(const float* logits, int n_vocab, const gl_sample_o
     ST(set_state(0, 0, 0, out_index, &o));
     CU(cudaMemcpyAsync(logits_, logits, (size_t)n_vocab_ * 4, cudaMemcpyHostToDevice, stream_));
     SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, nullptr, max_out_, sample_scratch_, topk_scratch_};
-    if (sampled_) CU(sample_topk_launch(sp, false, stream_));
+    if (sampler_ != 0) CU(sample_topk_launch(sp, sampler_ == 1, false, stream_));
     else CU(sample_greedy_launch(sp, false, stream_));
     int tid = 0;
     float lp = 0.f;

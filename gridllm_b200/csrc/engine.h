@@ -165,8 +165,9 @@ private:
     int max_out_ = 0;
     int host_pos_ = 0;
 
-    cudaGraphExec_t g_nohead_ = nullptr, g_head_ = nullptr, g_head_keep_ = nullptr, g_head_s_ = nullptr, g_head_s_keep_ = nullptr;
-    bool sampled_ = false;     // the running request draws from the distribution (temperature > 0) instead of taking the argmax
+    cudaGraphExec_t g_nohead_ = nullptr;
+    cudaGraphExec_t g_head_var_[3][2] = {};   // [sampler of the running request][logits kept]
+    int sampler_ = 0;                          // 0 greedy (argmax), 1 / 2: the two kernels of sampler.cu (temperature > 0)
     int launches_nohead_ = 0, launches_head_ = 0;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t load_ns_ = 0;

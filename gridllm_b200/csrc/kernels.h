@@ -141,8 +141,8 @@ constexpr int SAMPLE_MAX_K = 1024;
 constexpr int TOPK_FAST_K = 64;              // top_k up to this takes the two-stage path ...
 constexpr int TOPK_FAST_MAX_CTAS = 64;       // ... for vocabularies up to 64 x 2048 entries
 constexpr size_t TOPK_SCRATCH_BYTES = (size_t)TOPK_FAST_MAX_CTAS * TOPK_FAST_K * 8 + TOPK_FAST_MAX_CTAS * 8 + 16;
-int sample_topk_launches(int n_vocab);       // kernels sample_topk_launch enqueues (1 or 2)
-cudaError_t sample_topk_launch(const SampleParams& p, bool pdl, cudaStream_t s);
+bool sample_topk_fast_applies(int top_k, int n_vocab);
+cudaError_t sample_topk_launch(const SampleParams& p, bool fast, bool pdl, cudaStream_t s);
 // sequential-prefill step without sampling: pos += 1
 cudaError_t advance_launch(StepState* st, bool pdl, cudaStream_t s);
 

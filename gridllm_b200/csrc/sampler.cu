@@ -15,8 +15,7 @@
 // Bound: latency.  Measured in a request (run 59): 0.17 ms per token -- one load in flight per thread and pass -- so requests
 // with top_k <= 64 (Ollama's default is 40) take a two-stage path instead, sample_topk_fast_kernel below: <= 64 CTAs each sort
 // a 2048-logit slice in shared memory and publish their 64 best keys, the last CTA (atomic ticket) merges the sorted lists and
-// draws.  Both kernels are in the captured graph of a sampled step; the one that does not apply returns at once.  Greedy
-// requests launch neither.
+// draws.  The host picks the kernel by the request's top_k (a captured graph per sampler).  Greedy requests launch neither.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(TF_THREADS) sample_topk_fast_kernel(const __gr
     if (__ldcg(&st->done)) return;
     const int n = p.n_vocab;
     const int top_k = __ldcg(&st->top_k);
-    if (!topk_fast_applies(top_k, n)) return;                    // sample_topk_kernel draws this token
+    if (!topk_fast_applies(top_k, n)) __trap();                  // the host picks the kernel by the request's top_k (sample_topk_fast_applies)
     const int out_idx = __ldcg(&st->out_idx);
     const int n_ctas = gridDim.x;                                // = ceil(n / TF_SLICE)
     const bool keep = p.logits_keep != nullptr && out_idx < p.max_out;
@@ -237,7 +236,6 @@ __global__ void __launch_bounds__(TS_THREADS) sample_topk_kernel(const __grid_co
     if (done) return;
     const int out_idx = __ldcg(&st->out_idx);
     const int n = p.n_vocab;
-    if (p.topk_scratch != nullptr && topk_fast_applies(__ldcg(&st->top_k), n)) return;       // sample_topk_fast_kernel has drawn this token
     const bool keep = p.logits_keep != nullptr && out_idx < p.max_out;
     float* dst = keep ? p.logits_keep + (size_t)out_idx * n : nullptr;
 
@@ -367,31 +365,28 @@ __global__ void __launch_bounds__(TS_THREADS) sample_topk_kernel(const __grid_co
 
 }  // namespace
 
-cudaError_t sample_topk_launch(const SampleParams& p, bool pdl, cudaStream_t s) {
+bool sample_topk_fast_applies(int top_k, int n_vocab) {
+    return top_k >= 1 && top_k <= TOPK_FAST_K && n_vocab <= TOPK_FAST_MAX_CTAS * TF_SLICE;
+}
+
+// fast: the two-stage kernel (the caller has checked sample_topk_fast_applies for the request's top_k), else the single-CTA one
+cudaError_t sample_topk_launch(const SampleParams& p, bool fast, bool pdl, cudaStream_t s) {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    // two launches; the one that does not apply to the request's top_k (device-resident) returns at once
-    const int n_fast = (p.n_vocab + TF_SLICE - 1) / TF_SLICE;
-    if (p.topk_scratch != nullptr && n_fast <= TOPK_FAST_MAX_CTAS) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)n_fast);
-        cfg.blockDim = dim3(TF_THREADS);
-        cfg.stream = s;
-        cfg.attrs = at;
-        cfg.numAttrs = pdl ? 1 : 0;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, sample_topk_fast_kernel, p);
-        if (e != cudaSuccess) return e;
-    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(1);
-    cfg.blockDim = dim3(TS_THREADS);
     cfg.stream = s;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
+    if (fast) {
+        if (p.topk_scratch == nullptr || p.n_vocab > TOPK_FAST_MAX_CTAS * TF_SLICE) return cudaErrorInvalidValue;
+        cfg.gridDim = dim3((unsigned)((p.n_vocab + TF_SLICE - 1) / TF_SLICE));
+        cfg.blockDim = dim3(TF_THREADS);
+        return cudaLaunchKernelEx(&cfg, sample_topk_fast_kernel, p);
+    }
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(TS_THREADS);
     return cudaLaunchKernelEx(&cfg, sample_topk_kernel, p);
 }
-
-int sample_topk_launches(int n_vocab) { return (n_vocab + TF_SLICE - 1) / TF_SLICE <= TOPK_FAST_MAX_CTAS ? 2 : 1; }
 
 }  // namespace gl
