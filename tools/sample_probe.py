@@ -16,6 +16,7 @@ def main():
     if not os.path.exists(path):
         from oracle import gguf_synth as S
         S.build_model(path, S.LLAMA3_8B, "q4_k_m", seed=1234, mode="random", with_vocab=False)
+    pdl = os.environ.get("GL_PDL", "1")
     e = N.Engine(path, max_ctx=2048)
     prompt = np.random.Generator(np.random.PCG64(1000)).integers(0, 128000, size=512)
     for name, kw in (("greedy", {}), ("t0.8_k40_p0.9", dict(temperature=0.8, top_k=40, top_p=0.9, seed=1)),
@@ -25,7 +26,7 @@ def main():
             g = e.generate(prompt, num_predict=128, ignore_eos=True, **kw)
             ms = g.stats.eval_duration_ns / 1e6 / g.stats.eval_count
             best = ms if best is None else min(best, ms)
-        print(json.dumps({"sampler": name, "decode_ms_per_token": round(best, 4), "distinct_tokens": int(len(set(g.ids.tolist())))}), flush=True)
+        print(json.dumps({"pdl": pdl, "sampler": name, "decode_ms_per_token": round(best, 4), "distinct_tokens": int(len(set(g.ids.tolist())))}), flush=True)
     e.close()
 
 
