@@ -173,6 +173,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     xraw_wide_ = env_int("GL_XRAW_WIDE", 0) != 0;        // measured (run 49): no gain -- each 14 KB piece waits ~1 us for its bulk copy
     polite_tracks_ = std::max(0, env_int("GL_POLITE_TRACKS", 3));
     sampler_pdl_ = env_int("GL_SAMPLER_PDL", 0) != 0;
+    greedy_pdl_ = env_int("GL_GREEDY_PDL", 0) != 0;
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
@@ -553,7 +554,7 @@ Status Engine::enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch) {
     }
     SampleParams sp{logits_, n_vocab_, st_, out_ids_, out_lp_, keep_logits ? logits_keep_ : nullptr, keep_logits ? keep_cap_ : max_out_, sample_scratch_, topk_scratch_};
     if (sampler_ != 0) CU(sample_topk_launch(sp, sampler_ == 1, pdl && fused_ && sampler_pdl_, s));      // temperature > 0: seeded top-k / top-p draw (sampler.cu)
-    else CU(sample_greedy_launch(sp, pdl && fused_, s));
+    else CU(sample_greedy_launch(sp, pdl && fused_ && greedy_pdl_, s));
     ++*n_launch;
     return {};
 }

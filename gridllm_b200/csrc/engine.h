@@ -170,6 +170,7 @@ private:
     // The top-k samplers are launched WITHOUT programmatic dependent launch: their CTAs (33 KB of shared memory each) resident
     // beside the lm_head CTAs cost the step 60 us (run 67: 1.537 -> 1.478 ms/token at top_k 40); the greedy sampler keeps it.
     bool sampler_pdl_ = false;
+    bool greedy_pdl_ = false;                 // the greedy sampler likewise (64 small CTAs: 3 us per token, run 68)
     int sampler_ = 0;                          // 0 greedy (argmax), 1 / 2: the two kernels of sampler.cu (temperature > 0)
     int launches_nohead_ = 0, launches_head_ = 0;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};

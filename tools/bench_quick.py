@@ -18,9 +18,9 @@ def main():
     t0 = time.time()
     info = S.build_model(path, S.LLAMA3_8B, "q4_k_m", seed=1234, mode="random", with_vocab=False)
     print("build_s", round(time.time() - t0, 1), info, flush=True)
-    cfgs = ({}, {"GL_POLITE_TRACKS": "2"}, {"GL_POLITE_TRACKS": "5"}, {"GL_RING_DEPTH_MAX": "4"}, {"GL_ATTN_SPLITS": "16"})
+    cfgs = ({}, {"GL_ACT_BITS": "8"})
     for cfg in cfgs:
-        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_BYTES", "GL_MEGA_SLOTS", "GL_MEGA_INFLIGHT", "GL_ATTN_SPLITS", "GL_WARPS", "GL_RING_DEPTH", "GL_MEGA_TRACKS", "GL_LEAN_RINGS", "GL_POLITE_TRACKS", "GL_XRAW", "GL_HB256", "GL_XRAW_WIDE", "GL_SMEM_KB"):
+        for k in ("GL_ACT_BITS", "GL_PDL", "GL_GRAPH", "GL_MEGA", "GL_MEGA_SLOT_BYTES", "GL_MEGA_SLOTS", "GL_MEGA_INFLIGHT", "GL_ATTN_SPLITS", "GL_WARPS", "GL_RING_DEPTH", "GL_MEGA_TRACKS", "GL_LEAN_RINGS", "GL_POLITE_TRACKS", "GL_GREEDY_PDL", "GL_XRAW", "GL_HB256", "GL_XRAW_WIDE", "GL_SMEM_KB"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         t0 = time.time()
