@@ -5,6 +5,9 @@ these are produced by the pinned oracle + the independent gguf-py dequantisers:
   gemv_<type>.npz      : blocks + x -> W_deq @ x in float64 (exact) and with x snapped to the engine's fixed point
   tiny_model_logits.npz: the 2-layer d=256 synthetic q4_K_M model (oracle/gguf_synth.py TINY, seed 1234):
                          logits of 16 prompt positions + 8 greedy steps, ids, logprobs, margins (exact mode, fp16 KV)
+  sampler_draws.npz    : two 512-entry logit vectors (smooth / heavily tied) x 24 settings of (temperature, top_k, top_p,
+                         seed, output index) -> token id, logprob, distance of the draw from the nearest CDF boundary
+                         (oracle/sampler.py; the uniform generator is pinned to splitmix64's published outputs)
 
 Run from the repo root:  python tests/golden/make_golden.py
 """
@@ -15,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import gguf_synth as S, llama_oracle as O  # noqa: E402
+from oracle import gguf_synth as S, llama_oracle as O, sampler as SM  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -46,6 +49,25 @@ def main():
                         prompt_logits=np.stack(prompt_logits), gen_ids=g["ids"], gen_logprobs=g["logprobs"],
                         gen_margins=g["margins"], gen_logits=g["logits"], file_sha_hint=np.array([os.path.getsize(path)]))
     os.remove(path)
+    # sampler draws
+    srng = np.random.Generator(np.random.PCG64(77))
+    logits = np.stack([(srng.standard_normal(512) * 3.0).astype(np.float32), srng.integers(-3, 4, size=512).astype(np.float32)])
+    settings, results = [], []
+    for v in range(2):
+        for _ in range(24):
+            t = float(srng.choice([0.2, 0.8, 1.0, 1.5]))
+            k = int(srng.choice([1, 5, 40, 64, 100, 0]))
+            p = float(srng.choice([1.0, 0.9, 0.5]))
+            seed, idx = int(srng.integers(0, 2 ** 62)), int(srng.integers(0, 32))
+            tok, lp, margin = SM.sample(logits[v], t, k, p, seed, idx)
+            settings.append((v, t, k, p, seed, idx))
+            results.append((tok, lp, margin))
+    np.savez_compressed(os.path.join(OUT, "sampler_draws.npz"), logits=logits,
+                        vector=np.array([s[0] for s in settings], np.int32), temperature=np.array([s[1] for s in settings], np.float32),
+                        top_k=np.array([s[2] for s in settings], np.int32), top_p=np.array([s[3] for s in settings], np.float32),
+                        seed=np.array([s[4] for s in settings], np.int64), out_index=np.array([s[5] for s in settings], np.int32),
+                        token=np.array([r[0] for r in results], np.int32), logprob=np.array([r[1] for r in results], np.float64),
+                        margin=np.array([r[2] for r in results], np.float64))
     print("golden vectors written to", OUT)
 
 
