@@ -36,6 +36,52 @@ def _now_iso() -> str:
     return datetime.now(timezone.utc).isoformat(timespec="milliseconds").replace("+00:00", "Z")
 
 
+class StopFilter:
+    """options.stop (forwarded by the reference: OllamaService.ts:101-134): generation ends at the first occurrence of a stop
+    string in the GENERATED TEXT; the stop string is not part of the response.  A stop string can span tokens, so text that
+    could still turn into one is held back (what Ollama's runner does for streamed responses [external])."""
+
+    def __init__(self, stops: List[str]):
+        self.stops = [s for s in stops if s]
+        self.text = ""        # released text (the response so far)
+        self.held = ""        # decoded but not yet released: a prefix of some stop string
+        self._bytes = b""     # bytes of an incomplete UTF-8 character
+        self.hit = False
+
+    def feed(self, piece: bytes) -> str:
+        """-> the text this token releases ('' while a possible stop string is pending); sets .hit when a stop string completed"""
+        if self.hit:
+            return ""
+        self._bytes += piece or b""
+        try:
+            new = self._bytes.decode("utf-8")
+            self._bytes = b""
+        except UnicodeDecodeError:
+            return ""
+        buf = self.held + new
+        cut = min((i for i in (buf.find(s) for s in self.stops) if i >= 0), default=-1)
+        if cut >= 0:
+            self.hit = True
+            out, self.held = buf[:cut], ""
+        else:
+            keep = 0          # longest suffix of buf that is a proper prefix of a stop string
+            for s in self.stops:
+                for n in range(min(len(s) - 1, len(buf)), 0, -1):
+                    if buf.endswith(s[:n]):
+                        keep = max(keep, n)
+                        break
+            out, self.held = buf[:len(buf) - keep], buf[len(buf) - keep:]
+        self.text += out
+        return out
+
+    def flush(self) -> str:
+        """generation ended without a stop string: release what was held back"""
+        out = "" if self.hit else self.held + self._bytes.decode("utf-8", "replace")
+        self.held, self._bytes = "", b""
+        self.text += out
+        return out
+
+
 class NativeInferenceService:
     """One engine = one GPU = one loaded model (one service per worker id)."""
 
@@ -130,8 +176,27 @@ class NativeInferenceService:
         eng = self._engine(model)
         kw = self._sampling(options)
         ignore_eos = bool(options.get("ignore_eos", False))
+        stops = options.get("stop")
+        stops = [stops] if isinstance(stops, str) else list(stops or [])
+        if not stops or not eng.info.has_tokenizer:
+            with self._lock:
+                return eng, eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token, **kw)
+        # stop strings: the token callback sees only released text, and cancels the native call when one completes
+        filt = StopFilter(stops)
+
+        def cb(tid: int, lp: float, piece: bytes) -> bool:
+            out = filt.feed(piece)
+            stop_user = bool(on_token(tid, lp, out.encode("utf-8"))) if on_token is not None else False
+            return stop_user or filt.hit
+
         with self._lock:
-            return eng, eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token, **kw)
+            gen = eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=cb, **kw)
+        tail = filt.flush()
+        if tail and on_token is not None:
+            on_token(-1, 0.0, tail.encode("utf-8"))          # held-back text of a generation that ended by length / EOS
+        gen.stop_text = filt.text
+        gen.stopped = filt.hit
+        return eng, gen
 
     def _sampling(self, options: Dict[str, Any]) -> Dict[str, Any]:
         """InferenceRequest.options.{temperature, top_k, top_p, seed} (client/src/types/index.ts:1-27; gateway ranges
@@ -154,13 +219,15 @@ class NativeInferenceService:
 
     def _response(self, request: InferenceRequest, eng: N.Engine, gen: N.Generation, text: str) -> InferenceResponse:
         st = gen.stats
+        if getattr(gen, "stop_text", None) is not None:      # options.stop was active: the filtered text is the response
+            text = gen.stop_text
         return {
             "id": request["id"],
             "model": request["model"],
             "created_at": _now_iso(),
             "response": text,
             "done": True,
-            "done_reason": "stop" if st.done_reason == 0 else "length",
+            "done_reason": "stop" if (st.done_reason == 0 or getattr(gen, "stopped", False)) else "length",
             "total_duration": int(st.total_duration_ns),           # real numbers (the reference reports 0, :156-161)
             "load_duration": int(st.load_duration_ns),
             "prompt_eval_count": int(st.prompt_eval_count),
@@ -249,9 +316,8 @@ class NativeInferenceService:
                     raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
                 ids = eng.tokenize(prompt, add_bos=True, parse_special=True)
             eng, gen = await asyncio.to_thread(self._run, request["model"], ids, num_predict, options)
-            res = self._response(request, eng, gen, "")
-            res.pop("response")
-            res["message"] = {"role": "assistant", "content": self._text(eng, gen.ids)}
+            res = self._response(request, eng, gen, self._text(eng, gen.ids))
+            res["message"] = {"role": "assistant", "content": res.pop("response")}
             return res
         except Exception as error:
             raise RuntimeError(f"Chat inference failed: {error}")

@@ -42,3 +42,95 @@ def test_ollama_defaults_apply_only_to_missing_options():
 def test_invalid_temperature_is_rejected(bad):
     with pytest.raises(RuntimeError):
         _svc()._sampling({"temperature": bad})
+
+
+# ---- options.stop: stop strings end the generation, are not part of the response, may span tokens -----------------------
+from gridllm_b200.service import StopFilter  # noqa: E402
+
+
+def test_stop_filter_spanning_tokens_and_holdback():
+    f = StopFilter(["###", "END"])
+    out = [f.feed(p) for p in (b"Hello", b" wor", b"ld #", b"#", b" not yet", b" ##", b"#", b" after")]
+    assert out == ["Hello", " wor", "ld ", "", "## not yet", " ", "", ""]       # '#' / '##' are held back until they resolve
+    assert f.hit and f.text == "Hello world ## not yet "
+    assert f.flush() == "" and f.text == "Hello world ## not yet "
+
+
+def test_stop_filter_multibyte_and_flush():
+    f = StopFilter(["\n\n"])
+    euro = "€".encode("utf-8")
+    assert f.feed(euro[:1]) == "" and f.feed(euro[1:]) == "€"
+    assert f.feed(b"x\n") == "x" and not f.hit                   # a lone newline could start the stop string
+    assert f.flush() == "\n" and f.text == "€x\n"                # generation ended by length: the held text is released
+    g = StopFilter(["ab"])
+    assert g.feed(b"a") == "" and g.feed(b"c") == "ac" and g.feed(b"ab") == "" and g.hit and g.text == "ac"
+
+
+class _FakeInfo:
+    has_tokenizer = True
+    n_vocab = 100
+
+
+class _FakeStats:
+    prompt_eval_count, eval_count, prompt_eval_duration_ns, eval_duration_ns, total_duration_ns, load_duration_ns = 3, 0, 1, 1, 1, 1
+    done_reason, kernel_launches = 1, 1
+
+
+class _FakeGen:
+    def __init__(self, ids):
+        self.ids, self.logprobs, self.stats = ids, [0.0] * len(ids), _FakeStats()
+        self.stats.eval_count = len(ids)
+
+
+class _FakeEngine:
+    """Emits fixed pieces; honours the cancel return of the token callback like gl_generate does."""
+    info = _FakeInfo()
+    PIECES = [b"one", b" two", b" th", b"ree", b" four", b" five"]
+
+    def tokenize(self, text, add_bos=True, parse_special=False):
+        return [1, 2, 3]
+
+    def detokenize(self, ids):
+        return b"".join(self.PIECES[i] for i in ids).decode()
+
+    def generate(self, ids, num_predict=128, ignore_eos=False, on_token=None, **kw):
+        self.kw = kw
+        out = []
+        for i, p in enumerate(self.PIECES[:num_predict]):
+            out.append(i)
+            if on_token is not None and on_token(i, -0.5, p):
+                break
+        return _FakeGen(out)
+
+
+def _service_with_fake():
+    import threading
+    s = _svc()
+    s._paths = {"m": "unused"}
+    s._engines = {"m": _FakeEngine()}
+    s._lock = threading.Lock()
+    return s
+
+
+def test_stop_string_through_the_service():
+    import asyncio
+    s = _service_with_fake()
+    req = {"id": "r", "model": "m", "prompt": "p", "options": {"num_predict": 6, "stop": ["three"]}}
+    res = asyncio.run(s.generateResponse(req))
+    assert res["response"] == "one two " and res["done_reason"] == "stop" and res["eval_count"] == 4
+    # without stop strings nothing changes
+    res = asyncio.run(s.generateResponse({"id": "r", "model": "m", "prompt": "p", "options": {"num_predict": 6}}))
+    assert res["response"] == "one two three four five" and res["done_reason"] == "length"
+    # a stop string that never appears: full text, held-back pieces released at the end
+    res = asyncio.run(s.generateResponse(dict(req, options={"num_predict": 6, "stop": "fivex"})))
+    assert res["response"] == "one two three four five" and res["done_reason"] == "length"
+
+    async def collect(r):
+        return [c async for c in s.generateStreamResponse(r)]
+    chunks = asyncio.run(collect(dict(req, stream=True)))
+    assert "".join(c["response"] for c in chunks) == "one two " and chunks[-1]["done"] is True
+    chunks = asyncio.run(collect(dict(req, stream=True, options={"num_predict": 6, "stop": ["fivex"]})))
+    assert "".join(c["response"] for c in chunks) == "one two three four five"
+    chat = asyncio.run(s.generateChatResponse({"id": "c", "model": "m", "options": {"num_predict": 6, "stop": [" four"]},
+                                               "metadata": {"messages": [{"role": "user", "content": "hi"}]}}))
+    assert chat["message"] == {"role": "assistant", "content": "one two three"} and chat["done_reason"] == "stop"
