@@ -157,6 +157,10 @@ class NativeInferenceService:
             return np.asarray(md["prompt_token_ids"], dtype=np.int32)
         if not eng.info.has_tokenizer:
             raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
+        ctx = md.get("context")                          # token ids of the conversation so far (OllamaService.ts:224-226)
+        if ctx:
+            new = eng.tokenize(text or "", add_bos=False, parse_special=False)
+            return np.concatenate([np.asarray(ctx, dtype=np.int32), np.asarray(new, dtype=np.int32)])
         return eng.tokenize(text or "", add_bos=True, parse_special=False)
 
     def _chat_prompt(self, eng: N.Engine, messages: List[Dict[str, Any]]) -> str:

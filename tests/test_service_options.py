@@ -134,3 +134,25 @@ def test_stop_string_through_the_service():
     chat = asyncio.run(s.generateChatResponse({"id": "c", "model": "m", "options": {"num_predict": 6, "stop": [" four"]},
                                                "metadata": {"messages": [{"role": "user", "content": "hi"}]}}))
     assert chat["message"] == {"role": "assistant", "content": "one two three"} and chat["done_reason"] == "stop"
+
+
+def test_context_ids_continue_a_conversation():
+    """metadata.context (OllamaService.ts:224-226): the prior token ids come first, the new prompt follows without a BOS"""
+    import asyncio
+    s = _service_with_fake()
+    eng = s._engines["m"]
+    seen = {}
+    orig_tok, orig_gen = eng.tokenize, eng.generate
+
+    def tok(text, add_bos=True, parse_special=False):
+        seen["add_bos"] = add_bos
+        return [7, 8] if not add_bos else [0, 7, 8]
+
+    def gen(ids, **kw):
+        seen["ids"] = [int(i) for i in ids]
+        return orig_gen(ids, **kw)
+    eng.tokenize, eng.generate = tok, gen
+    asyncio.run(s.generateResponse({"id": "r", "model": "m", "prompt": "p", "options": {"num_predict": 2}, "metadata": {"context": [11, 12, 13]}}))
+    assert seen["ids"] == [11, 12, 13, 7, 8] and seen["add_bos"] is False
+    asyncio.run(s.generateResponse({"id": "r", "model": "m", "prompt": "p", "options": {"num_predict": 2}}))
+    assert seen["ids"] == [0, 7, 8] and seen["add_bos"] is True
