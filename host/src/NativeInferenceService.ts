@@ -53,7 +53,27 @@ export class NativeInferenceService {
 
 	private ids(e: unknown, request: InferenceRequest): Int32Array {
 		const pre = request.metadata?.prompt_token_ids;
-		return pre ? Int32Array.from(pre) : native.tokenize(e, request.prompt || "", true, false);
+		if (pre) return Int32Array.from(pre);
+		const ctx: number[] | undefined = request.metadata?.context;          // conversation so far (OllamaService.ts:224-226)
+		if (ctx?.length) return Int32Array.from([...ctx, ...native.tokenize(e, request.prompt || "", false, false)]);
+		return native.tokenize(e, request.prompt || "", true, false);
+	}
+
+	// options.stop: same rule as gridllm_b200/service.py::StopFilter -- end at the first stop string in the generated text,
+	// hold back text that could still become one.  feed() returns the text a token releases; hit ends the native call.
+	private stopFilter(stops: string[]) {
+		const st = { text: "", held: "", hit: false,
+			feed(piece: string): string {
+				if (st.hit) return "";
+				const buf = st.held + piece;
+				const cuts = stops.map((s) => buf.indexOf(s)).filter((i) => i >= 0);
+				if (cuts.length) { st.hit = true; st.held = ""; const out = buf.slice(0, Math.min(...cuts)); st.text += out; return out; }
+				let keep = 0;
+				for (const s of stops) for (let n = Math.min(s.length - 1, buf.length); n > 0; --n) if (buf.endsWith(s.slice(0, n))) { keep = Math.max(keep, n); break; }
+				const out = buf.slice(0, buf.length - keep); st.held = buf.slice(buf.length - keep); st.text += out; return out;
+			},
+			flush(): string { const out = st.hit ? "" : st.held; st.held = ""; st.text += out; return out; } };
+		return st;
 	}
 
 	private toResponse(request: InferenceRequest, text: string, ids: Int32Array, st: NativeStats): InferenceResponse {
@@ -74,8 +94,19 @@ export class NativeInferenceService {
 	async generateResponse(request: InferenceRequest): Promise<InferenceResponse> {   // :97-184
 		try {
 			const e = this.engine(request.model);
-			const out = await native.generate(e, this.ids(e, request), this.sampleOpts(request), null);
-			return this.toResponse(request, native.detokenize(e, out.ids), out.ids, out.stats);
+			const stop = request.options?.stop;
+			const stops: string[] = (typeof stop === "string" ? [stop] : stop || []).filter(Boolean);
+			if (!stops.length) {
+				const out = await native.generate(e, this.ids(e, request), this.sampleOpts(request), null);
+				return this.toResponse(request, native.detokenize(e, out.ids), out.ids, out.stats);
+			}
+			const f = this.stopFilter(stops);         // a non-zero return of the token callback cancels gl_generate
+			const out = await native.generate(e, this.ids(e, request), this.sampleOpts(request),
+				(_id: number, _lp: number, piece: string) => { f.feed(piece); return f.hit; });
+			f.flush();
+			const res = this.toResponse(request, f.text, out.ids, out.stats);
+			if (f.hit) res.done_reason = "stop";
+			return res;
 		} catch (error) {
 			throw new Error(`Inference failed: ${error instanceof Error ? error.message : "Unknown error"}`);
 		}
