@@ -16,6 +16,7 @@
 
 #include <cstring>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -87,17 +88,18 @@ struct GenJob {
     napi_threadsafe_function tsfn = nullptr;
     napi_deferred deferred = nullptr;
     napi_async_work work = nullptr;
-    std::atomic<int> cancel{0};      // set on the JS thread when the token callback returns a truthy value
+    // set on the JS thread when the token callback returns a truthy value; shared with the queued tokens, which can outlive the job
+    std::shared_ptr<std::atomic<int>> cancel = std::make_shared<std::atomic<int>>(0);
 };
-struct Tok { int32_t id; float lp; std::string piece; GenJob* job; };
+struct Tok { int32_t id; float lp; std::string piece; std::shared_ptr<std::atomic<int>> cancel; };
 
 int on_token(void* user, int32_t id, float lp, const char* piece, int32_t n) {
     GenJob* j = static_cast<GenJob*>(user);
     if (!j->tsfn) return 0;
     // tokens reach JS asynchronously, so a cancel request (job_cancellation, a completed stop string) arrives a few tokens
     // late: the wrapper trims the text, gl_generate stops at the next callback
-    if (j->cancel.load(std::memory_order_relaxed)) return 1;
-    Tok* t = new Tok{id, lp, piece ? std::string(piece, n) : std::string(), j};
+    if (j->cancel->load(std::memory_order_relaxed)) return 1;
+    Tok* t = new Tok{id, lp, piece ? std::string(piece, n) : std::string(), j->cancel};
     return napi_call_threadsafe_function(j->tsfn, t, napi_tsfn_nonblocking) == napi_ok ? 0 : 1;
 }
 
@@ -113,7 +115,7 @@ void call_js(napi_env env, napi_value cb, void*, void* data) {
         bool stop = false;
         if (napi_call_function(env, undef, cb, 3, argv, &ret) == napi_ok && napi_coerce_to_bool(env, ret, &ret) == napi_ok &&
             napi_get_value_bool(env, ret, &stop) == napi_ok && stop)
-            t->job->cancel.store(1, std::memory_order_relaxed);
+            t->cancel->store(1, std::memory_order_relaxed);
     }
     delete t;
 }
