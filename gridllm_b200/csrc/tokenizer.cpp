@@ -1,5 +1,6 @@
 // Byte-level BPE (GPT-2 style) from GGUF metadata.  See tokenizer.h.
 #include "tokenizer.h"
+#include "unicode_ranges.h"
 
 #include <algorithm>
 #include <climits>
@@ -38,37 +39,74 @@ uint32_t utf8_decode1(const std::string& ch) {
     return ((c & 0x07) << 18) | ((ch[1] & 0x3F) << 12) | ((ch[2] & 0x3F) << 6) | (ch[3] & 0x3F);
 }
 
-inline bool is_letter(unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80; }
-inline bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
-inline bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
-inline bool is_nl(unsigned char c) { return c == '\n' || c == '\r'; }
+struct Cp { uint32_t cp; uint32_t off; };      // code point and its byte offset in the text
 
-// llama-bpe pre-tokeniser restated over bytes:
-//  (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n L N]? L+ | N{1,3} | ' '? [^\s L N]+ [\r\n]* | \s*[\r\n]+ | \s+(?!\S) | \s+
-std::vector<std::string> pretokenize(const std::string& t) {
-    std::vector<std::string> out;
-    const size_t n = t.size();
-    size_t i = 0;
-    auto lower = [](unsigned char c) { return (c >= 'A' && c <= 'Z') ? (unsigned char)(c + 32) : c; };
-    while (i < n) {
+bool in_ranges(const uint32_t (*r)[2], int n, uint32_t cp) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (cp < r[mid][0]) hi = mid - 1;
+        else if (cp > r[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+inline bool is_letter(uint32_t c) { return c < 0x80 ? ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') : in_ranges(UNI_LETTER, UNI_LETTER_N, c); }
+inline bool is_digit(uint32_t c) { return c < 0x80 ? (c >= '0' && c <= '9') : in_ranges(UNI_NUMBER, UNI_NUMBER_N, c); }
+// \s of the pre-tokeniser's regular expression: the Unicode White_Space property
+inline bool is_space(uint32_t c) {
+    return (c >= 0x9 && c <= 0xD) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) || c == 0x2028 ||
+           c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+inline bool is_nl(uint32_t c) { return c == '\n' || c == '\r'; }
+
+}  // namespace
+
+// llama-bpe pre-tokeniser (the "llama3" split of llama.cpp / the Llama-3 tokenizer.json [external]) restated over code points:
+//  (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n\p{L}\p{N}]?\p{L}+ | \p{N}{1,3} | ' '?[^\s\p{L}\p{N}]+[\r\n]* | \s*[\r\n]+ | \s+(?!\S) | \s+
+// Alternatives are tried in this order at every position, each greedy with the backtracking the expression implies.  Pinned
+// against the Hugging Face `tokenizers` regex engine in tests/test_tokenizer.py (ASCII, accents, CJK, other-script digits,
+// Unicode spaces, emoji).  The contraction alternative is case-insensitive for ASCII only.
+std::vector<std::string> llama3_pretokenize(const std::string& t) {
+    std::vector<Cp> u;
+    u.reserve(t.size());
+    for (size_t i = 0; i < t.size();) {
         const unsigned char c = (unsigned char)t[i];
+        size_t n = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+        if (i + n > t.size()) n = 1;
+        uint32_t cp = c;
+        if (n == 2) cp = ((c & 0x1F) << 6) | (t[i + 1] & 0x3F);
+        else if (n == 3) cp = ((c & 0x0F) << 12) | ((t[i + 1] & 0x3F) << 6) | (t[i + 2] & 0x3F);
+        else if (n == 4) cp = ((c & 0x07) << 18) | ((t[i + 1] & 0x3F) << 12) | ((t[i + 2] & 0x3F) << 6) | (t[i + 3] & 0x3F);
+        else if (c >= 0x80) cp = 0xFFFD;            // stray byte: neither letter, number nor space
+        u.push_back(Cp{cp, (uint32_t)i});
+        i += n;
+    }
+    const size_t n = u.size();
+    u.push_back(Cp{0, (uint32_t)t.size()});          // sentinel: byte offset of the end
+    std::vector<std::string> out;
+    auto emit = [&](size_t a, size_t b) { out.push_back(t.substr(u[a].off, u[b].off - u[a].off)); };
+    auto lower = [](uint32_t c) { return (c >= 'A' && c <= 'Z') ? c + 32 : c; };
+    size_t i = 0;
+    while (i < n) {
+        const uint32_t c = u[i].cp;
         // contractions
         if (c == '\'' && i + 1 < n) {
-            const unsigned char a = lower((unsigned char)t[i + 1]);
-            const unsigned char b = i + 2 < n ? lower((unsigned char)t[i + 2]) : 0;
+            const uint32_t a = lower(u[i + 1].cp);
+            const uint32_t b = i + 2 < n ? lower(u[i + 2].cp) : 0;
             size_t len = 0;
             if (a == 's' || a == 't' || a == 'm' || a == 'd') len = 2;
             if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e') || (a == 'l' && b == 'l')) len = 3;
-            if (len) { out.push_back(t.substr(i, len)); i += len; continue; }
+            if (len) { emit(i, i + len); i += len; continue; }
         }
         // [^\r\n L N]? L+
         {
             size_t j = i;
-            if (!is_nl(c) && !is_letter(c) && !is_digit(c) && j + 1 < n && is_letter((unsigned char)t[j + 1])) ++j;
-            if (j < n && is_letter((unsigned char)t[j])) {
+            if (!is_nl(c) && !is_letter(c) && !is_digit(c) && j + 1 < n && is_letter(u[j + 1].cp)) ++j;
+            if (is_letter(u[j].cp) && j < n) {
                 size_t k = j;
-                while (k < n && is_letter((unsigned char)t[k])) ++k;
-                out.push_back(t.substr(i, k - i));
+                while (k < n && is_letter(u[k].cp)) ++k;
+                emit(i, k);
                 i = k;
                 continue;
             }
@@ -76,8 +114,8 @@ std::vector<std::string> pretokenize(const std::string& t) {
         // N{1,3}
         if (is_digit(c)) {
             size_t k = i;
-            while (k < n && k - i < 3 && is_digit((unsigned char)t[k])) ++k;
-            out.push_back(t.substr(i, k - i));
+            while (k < n && k - i < 3 && is_digit(u[k].cp)) ++k;
+            emit(i, k);
             i = k;
             continue;
         }
@@ -85,12 +123,12 @@ std::vector<std::string> pretokenize(const std::string& t) {
         {
             size_t j = i;
             if (c == ' ' && j + 1 < n) ++j;
-            auto punct = [&](size_t p) { unsigned char d = (unsigned char)t[p]; return !is_space(d) && !is_letter(d) && !is_digit(d); };
+            auto punct = [&](size_t p) { const uint32_t d = u[p].cp; return !is_space(d) && !is_letter(d) && !is_digit(d); };
             if (j < n && punct(j)) {
                 size_t k = j;
                 while (k < n && punct(k)) ++k;
-                while (k < n && is_nl((unsigned char)t[k])) ++k;
-                out.push_back(t.substr(i, k - i));
+                while (k < n && is_nl(u[k].cp)) ++k;
+                emit(i, k);
                 i = k;
                 continue;
             }
@@ -98,28 +136,23 @@ std::vector<std::string> pretokenize(const std::string& t) {
         // whitespace runs
         if (is_space(c)) {
             size_t k = i;
-            while (k < n && is_space((unsigned char)t[k])) ++k;
-            // \s*[\r\n]+ : take through the last newline in the run
+            while (k < n && is_space(u[k].cp)) ++k;
+            // \s*[\r\n]+ : through the last newline of the run
             size_t last_nl = std::string::npos;
-            for (size_t p = i; p < k; ++p) if (is_nl((unsigned char)t[p])) last_nl = p;
-            if (last_nl != std::string::npos) { out.push_back(t.substr(i, last_nl + 1 - i)); i = last_nl + 1; continue; }
-            // \s+(?!\S): leave the last space for the next word if something follows
-            if (k < n && k - i > 1) { out.push_back(t.substr(i, k - 1 - i)); i = k - 1; continue; }
-            if (k < n && k - i == 1) {
-                // single space followed by non-space that is not letter/punct-start (e.g. digit): emit alone
-                out.push_back(t.substr(i, 1)); i = k; continue;
-            }
-            out.push_back(t.substr(i, k - i));
+            for (size_t p = i; p < k; ++p) if (is_nl(u[p].cp)) last_nl = p;
+            if (last_nl != std::string::npos) { emit(i, last_nl + 1); i = last_nl + 1; continue; }
+            // \s+(?!\S): leave the last space character to the next piece if something follows
+            if (k < n && k - i > 1) { emit(i, k - 1); i = k - 1; continue; }
+            // \s+ : a single space character before something that did not take it, or the run at the end of the text
+            emit(i, k);
             i = k;
             continue;
         }
-        out.push_back(t.substr(i, 1));
+        emit(i, i + 1);
         ++i;
     }
     return out;
 }
-
-}  // namespace
 
 bool Tokenizer::load(const GGUFFile& f) {
     ok_ = false;
@@ -212,7 +245,7 @@ std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos, bo
     }
     for (auto& pr : parts) {
         if (pr.second >= 0) { out.push_back(pr.second); continue; }
-        for (auto& w : pretokenize(pr.first)) {
+        for (auto& w : llama3_pretokenize(pr.first)) {
             std::string wu;
             for (unsigned char c : w) wu += byte2u_[c];
             bpe_word(wu, out);

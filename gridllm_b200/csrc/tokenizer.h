@@ -2,8 +2,7 @@
 // In the reference the tokenizer lives inside Ollama; OllamaService only ever ships prompt TEXT
 // (/root/reference/client/src/services/OllamaService.ts:101-104, 190-195), so a native worker needs
 // its own.  Supports tokenizer.ggml.model == "gpt2" (Llama-3 family).  The pre-tokeniser is the
-// llama-bpe split restated for ASCII classes with every non-ASCII UTF-8 sequence treated as a
-// letter (documented limitation).
+// llama-bpe split over Unicode code points (general categories L* / N* from generated tables, White_Space).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -13,6 +12,9 @@
 #include "gguf_file.h"
 
 namespace gl {
+
+// the pre-tokeniser alone (pieces in text order; their concatenation is the text)
+std::vector<std::string> llama3_pretokenize(const std::string& text);
 
 class Tokenizer {
 public:

@@ -60,7 +60,7 @@ def hostcheck_lib():
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
     deps = [src, os.path.join(ROOT, "gridllm_b200", "csrc", "rowdot.h"), os.path.join(ROOT, "gridllm_b200", "csrc", "gguf_file.cpp"),
-            os.path.join(ROOT, "gridllm_b200", "csrc", "tokenizer.cpp")]
+            os.path.join(ROOT, "gridllm_b200", "csrc", "tokenizer.cpp"), os.path.join(ROOT, "gridllm_b200", "csrc", "unicode_ranges.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src,
                                os.path.join(ROOT, "gridllm_b200", "csrc", "gguf_file.cpp"),

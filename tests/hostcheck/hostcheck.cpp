@@ -144,6 +144,14 @@ extern "C" int hc_tokenize(const char* gguf_path, const char* text, int add_bos,
     for (size_t i = 0; i < v.size(); ++i) ids[i] = v[i];
     return (int)v.size();
 }
+// the pre-tokeniser alone: byte offsets of the piece ENDS
+extern "C" int hc_pretokenize(const char* text, int n_bytes, int32_t* ends, int cap) {
+    std::vector<std::string> v = llama3_pretokenize(std::string(text, (size_t)n_bytes));
+    if ((int)v.size() > cap) return -3;
+    int off = 0;
+    for (size_t i = 0; i < v.size(); ++i) { off += (int)v[i].size(); ends[i] = off; }
+    return (int)v.size();
+}
 extern "C" int hc_detokenize(const char* gguf_path, const int32_t* ids, int n, char* buf, int cap) {
     GGUFFile f;
     if (!f.open(gguf_path).empty()) return -1;

@@ -48,3 +48,49 @@ def test_special_tokens(hostcheck_lib, tiny_gguf):
     assert ids[n - 1] == S.TINY.n_vocab - 1
     n2 = hostcheck_lib.hc_tokenize(tiny_gguf.encode(), b"hi<|eot_id|>", 0, 0, ids.ctypes.data_as(ctypes.c_void_p), 64)
     assert n2 > n                                                    # not parsed: spelled out byte by byte
+
+
+# ---- the pre-tokeniser against an independent regex engine -----------------------------------------------------------
+LLAMA3_SPLIT = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+")
+
+PRETOK_TEXTS = [
+    "Hello  world's café 中文。12345 x=42\n\nend  ", "it's We'LL they'Re I'M he'D 'tis o'clock", "a\tb\t\tc \t d", "tabs\t\tand\r\nCRLF\r\n\r\nlines \n x",
+    "naïve façade Ünïcödé straße ǅ", "日本語のテキスト、句読点。「引用」", "Привет, мир! Ελληνικά; עברית ، العربية", "१२३४५ ٣٤٥ Ⅻ ½ ²³ 1234567890",
+    "no break em　ideographic  spaces line", "emoji 😀😃 mixed👍🏽text 🇩🇪", "x=y+z*(a/b)-[c]{d}<e>|f&g^h%i$j#k@l!m~n`o", "   leading and trailing   ",
+    "...!!!???\n\n\n", "CamelCaseWordsAndsnake_case_words and kebab-case", "price: $1,234.56 (≈€1.100,00) 50% off!!", "\n", " ", "", "a", "'", "''s", "１２３ｆｕｌｌｗｉｄｔｈ",
+    "mixed١٢٣abc४५६def", "end with space ", "end with spaces  \t", "\t\tword", " \n \n x", "a  \n  b", "def f(x):\n    return x**2  # comment\n",
+]
+
+
+def _hc_pretokenize(lib, text):
+    import ctypes
+    raw = text.encode("utf-8")
+    ends = np.zeros(len(raw) + 8, np.int32)
+    n = lib.hc_pretokenize(raw, len(raw), ends.ctypes.data_as(ctypes.c_void_p), len(ends))
+    assert n >= 0
+    out, a = [], 0
+    for e in ends[:n]:
+        out.append(raw[a:int(e)].decode("utf-8"))
+        a = int(e)
+    assert a == len(raw)                      # the pieces tile the text
+    return out
+
+
+def test_pretokeniser_matches_the_tokenizers_regex_engine(hostcheck_lib):
+    tokenizers = pytest.importorskip("tokenizers")
+    split = tokenizers.pre_tokenizers.Split(tokenizers.Regex(LLAMA3_SPLIT), behavior="isolated", invert=False)
+    for text in PRETOK_TEXTS:
+        ref = [p for p, _ in split.pre_tokenize_str(text)]
+        assert _hc_pretokenize(hostcheck_lib, text) == ref, text
+
+
+def test_pretokeniser_random_strings(hostcheck_lib):
+    """random strings over an alphabet that mixes every character class the expression distinguishes"""
+    tokenizers = pytest.importorskip("tokenizers")
+    split = tokenizers.pre_tokenizers.Split(tokenizers.Regex(LLAMA3_SPLIT), behavior="isolated", invert=False)
+    alphabet = list("ab Z9 0'\n\r\t.,!-_世界éß٣½ 　😀") + ["'s", "'ll", "  ", "\n\n"]
+    rng = np.random.Generator(np.random.PCG64(11))
+    for _ in range(400):
+        text = "".join(rng.choice(alphabet, size=int(rng.integers(1, 24))))
+        ref = [p for p, _ in split.pre_tokenize_str(text)]
+        assert _hc_pretokenize(hostcheck_lib, text) == ref, repr(text)
