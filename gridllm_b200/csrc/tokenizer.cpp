@@ -173,6 +173,9 @@ bool Tokenizer::load(const GGUFFile& f) {
     eos = (int)f.get_u("tokenizer.ggml.eos_token_id", (uint64_t)-1);
     eot = (int)f.get_u("tokenizer.ggml.eot_token_id", (uint64_t)-1);
     add_bos_default = f.get_u("tokenizer.ggml.add_bos_token", 1) != 0;
+    // Llama-3's tokenizer.json sets ignore_merges; llama.cpp derives it from the pre-tokeniser name [external]
+    const std::string pre = f.get_s("tokenizer.ggml.pre", "");
+    ignore_merges_ = pre == "llama-bpe" || pre == "llama3" || pre == "llama-v3";
     chat_template = f.get_s("tokenizer.chat_template", "");
     // GPT-2 byte <-> unicode table
     std::vector<int> bs;
@@ -195,6 +198,10 @@ bool Tokenizer::load(const GGUFFile& f) {
 }
 
 void Tokenizer::bpe_word(const std::string& word_u, std::vector<int32_t>& out) const {
+    if (ignore_merges_) {      // a pre-token that is itself in the vocabulary is emitted whole (llama-bpe; see load())
+        auto it = tok2id_.find(word_u);
+        if (it != tok2id_.end()) { out.push_back(it->second); return; }
+    }
     std::vector<std::string> sym = utf8_chars(word_u);
     while (sym.size() > 1) {
         int best = INT_MAX;

@@ -31,6 +31,7 @@ public:
 private:
     void bpe_word(const std::string& word_u, std::vector<int32_t>& out) const;
     bool ok_ = false;
+    bool ignore_merges_ = false;                      // pre-tokens found whole in the vocabulary skip the merge loop
     std::vector<std::string> tokens_;                 // in "unicode-escaped bytes" form (GPT-2)
     std::vector<int> types_;
     std::unordered_map<std::string, int32_t> tok2id_;
