@@ -3,7 +3,6 @@ Matrices are sized > 126 MB so back-to-back launches cannot be served from L2.""
 import json
 import os
 import sys
-import time
 
 import numpy as np
 

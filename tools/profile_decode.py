@@ -1,7 +1,6 @@
 """Profiling driver (run under ncu on the GPU box): a few decode steps of the Llama-3-8B-shaped model."""
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
