@@ -1,0 +1,80 @@
+"""TEST INFRASTRUCTURE: an engine double with the surface of gridllm_b200.native.Engine, backed by the numpy oracle and the
+product tokenizer compiled for the host (tests/hostcheck).  It lets the CPU suite drive the UNMODIFIED host layer
+(gridllm_b200/service.py, worker.py) end to end; the real engine takes its place in tests/test_gpu_service.py."""
+import ctypes
+import time
+from types import SimpleNamespace
+
+import numpy as np
+
+from oracle import llama_oracle as O, sampler as SM
+
+_LIB = None
+
+
+def use_hostcheck(lib):
+    global _LIB
+    _LIB = lib
+
+
+class OracleEngine:
+    def __init__(self, gguf_path, device=0, max_ctx=0, **kw):
+        assert _LIB is not None, "call oracle_engine.use_hostcheck(hostcheck_lib) first"
+        self.path = gguf_path
+        self.m = O.load_gguf(gguf_path)
+        self.info = SimpleNamespace(has_tokenizer=1, n_vocab=self.m.n_vocab, n_embd=self.m.n_embd, n_params=int(1e6), quantization=b"Q4_K_M",
+                                    eos_id=self.m.n_vocab - 2, eot_id=self.m.n_vocab - 1, bos_id=self.m.n_vocab - 3)
+        self.calls = []
+
+    # ---- tokenizer: the product's C++ code --------------------------------------------------------------------------
+    def tokenize(self, text, add_bos=True, parse_special=False):
+        ids = np.zeros(8192, np.int32)
+        n = _LIB.hc_tokenize(self.path.encode(), text.encode("utf-8"), int(add_bos), int(parse_special), ids.ctypes.data_as(ctypes.c_void_p), 8192)
+        assert n >= 0
+        return ids[:n].copy()
+
+    def _bytes(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        buf = ctypes.create_string_buffer(16 * max(1, len(a)) + 16)
+        n = _LIB.hc_detokenize(self.path.encode(), a.ctypes.data_as(ctypes.c_void_p), len(a), buf, len(buf))
+        assert n >= 0
+        return buf.raw[:n]
+
+    def detokenize(self, ids):
+        return self._bytes(ids).decode("utf-8", "replace")
+
+    # ---- generation: the oracle's forward, greedy or the oracle's seeded draw -----------------------------------------
+    def generate(self, prompt, num_predict=128, ignore_eos=False, on_token=None, want_logits=False, stop_ids=(), temperature=0.0, top_k=0,
+                 top_p=1.0, seed=0):
+        self.calls.append(dict(n_prompt=len(prompt), num_predict=num_predict, temperature=temperature, top_k=top_k, top_p=top_p, seed=seed))
+        t0 = time.perf_counter_ns()
+        orc = O.LlamaOracle(self.m, act="i16", kv_f16=True)
+        logits = None
+        for t in prompt:
+            logits = orc.step(int(t))
+        t1 = time.perf_counter_ns()
+        stops = set(int(s) for s in stop_ids) | ({self.info.eos_id, self.info.eot_id} if not ignore_eos else set())
+        ids, lps, reason = [], [], 1
+        for i in range(num_predict):
+            tok, lp, _ = SM.sample(logits, temperature, top_k, top_p, seed, i)
+            if tok in stops:
+                reason = 0
+                break
+            ids.append(tok)
+            lps.append(lp)
+            if on_token is not None and on_token(tok, lp, self._bytes([tok])):
+                reason = 2
+                break
+            logits = orc.step(tok)
+        t2 = time.perf_counter_ns()
+        stats = SimpleNamespace(prompt_eval_count=len(prompt), eval_count=len(ids), prompt_eval_duration_ns=t1 - t0, eval_duration_ns=max(1, t2 - t1),
+                                total_duration_ns=t2 - t0, load_duration_ns=1, done_reason=reason, kernel_launches=0)
+        return SimpleNamespace(ids=np.array(ids, dtype=np.int32), logprobs=np.array(lps, dtype=np.float32), stats=stats)
+
+    def embed(self, seqs):
+        orc = O.LlamaOracle(self.m, act="i16")
+        out = np.stack([orc.embed(s) for s in seqs]).astype(np.float32)
+        return out, SimpleNamespace(prompt_eval_count=int(sum(len(s) for s in seqs)), load_duration_ns=1)
+
+    def close(self):
+        pass

@@ -1,0 +1,133 @@
+"""CPU: the reference-facing host layer end to end -- NativeInferenceService (drop-in for OllamaService) and NativeWorker
+(WorkerClientService job dispatch) exactly as shipped, over an engine double backed by the numpy oracle and the product
+tokenizer (tests/oracle_engine.py).  The same scenarios run against the real engine in tests/test_gpu_service.py."""
+import asyncio
+import json
+
+import numpy as np
+import pytest
+
+
+def _run(coro):
+    return asyncio.new_event_loop().run_until_complete(coro)
+
+
+@pytest.fixture()
+def svc(tiny_gguf, hostcheck_lib, monkeypatch):
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 1)
+    s = SV.NativeInferenceService({"tiny:latest": tiny_gguf}, device=0)
+    yield s
+    s.close()
+
+
+def test_health_models_validate(svc):
+    assert _run(svc.checkHealth()) is True
+    models = _run(svc.getAvailableModels())
+    assert models[0]["name"] == "tiny:latest" and models[0]["details"]["format"] == "gguf" and models[0]["size"] > 0
+    assert _run(svc.validateModel("tiny:latest")) and not _run(svc.validateModel("other"))
+
+
+def test_generate_matches_the_oracle_and_streams_the_same_text(svc):
+    from oracle import llama_oracle as O
+    req = {"id": "r1", "model": "tiny:latest", "prompt": "hello world, the rain in spain", "options": {"num_predict": 6, "temperature": 0, "ignore_eos": True},
+           "priority": "medium"}
+    res = _run(svc.generateResponse(req))
+    assert res["id"] == "r1" and res["done"] is True and res["done_reason"] == "length" and res["eval_count"] == 6
+    eng = svc._engine("tiny:latest")
+    ids = eng.tokenize(req["prompt"])
+    assert res["prompt_eval_count"] == len(ids) and eng.detokenize(ids[1:]) == req["prompt"]
+    ref = O.LlamaOracle(eng.m, act="i16", kv_f16=True).generate(ids, 6)
+    assert res["context"] == [int(t) for t in ref["ids"]]                  # the service hands the oracle's greedy ids through
+    assert res["response"] == eng.detokenize(ref["ids"])
+
+    async def collect():
+        return [c async for c in svc.generateStreamResponse(dict(req, id="s1", stream=True))]
+    chunks = _run(collect())
+    assert [c["done"] for c in chunks] == [False] * 6 + [True] and all(set(c) == {"id", "response", "done"} for c in chunks)
+    assert "".join(c["response"] for c in chunks) == res["response"]
+    # default generation length when num_predict is absent: OllamaService.ts:105 -> 128
+    res2 = _run(svc.generateResponse({"id": "r2", "model": "tiny:latest", "prompt": "hi", "options": {"ignore_eos": True}, "priority": "low"}))
+    assert res2["eval_count"] == 128
+
+
+def test_sampled_and_stop_options_reach_the_engine(svc):
+    opts = {"num_predict": 12, "ignore_eos": True, "temperature": 0.9, "top_k": 40, "top_p": 0.95, "seed": 7}
+    req = {"id": "t1", "model": "tiny:latest", "prompt": "once upon a time", "options": opts, "priority": "medium"}
+    a = _run(svc.generateResponse(req))
+    b = _run(svc.generateResponse(dict(req, id="t2")))
+    c = _run(svc.generateResponse(dict(req, id="t3", options=dict(opts, seed=8))))
+    assert a["context"] == b["context"] and a["context"] != c["context"]
+    call = svc._engine("tiny:latest").calls[-1]
+    assert (call["temperature"], call["top_k"], call["top_p"], call["seed"]) == (0.9, 40, 0.95, 8)
+    # a stop string taken from the middle of the sampled text ends the response there, streamed or not
+    text = a["response"]
+    assert len(text) >= 4
+    stop = text[len(text) // 2: len(text) // 2 + 2]
+    cut = text.index(stop)
+    d = _run(svc.generateResponse(dict(req, id="t4", options=dict(opts, stop=[stop]))))
+    assert d["response"] == text[:cut] and d["done_reason"] == "stop" and d["eval_count"] <= a["eval_count"]
+
+    async def collect():
+        return [ch async for ch in svc.generateStreamResponse(dict(req, id="t5", stream=True, options=dict(opts, stop=[stop])))]
+    assert "".join(ch["response"] for ch in _run(collect())) == text[:cut]
+
+
+def test_chat_embedding_and_errors(svc):
+    chat = {"id": "c1", "model": "tiny:latest", "options": {"num_predict": 4, "ignore_eos": True}, "priority": "high",
+            "metadata": {"requestType": "chat", "messages": [{"role": "user", "content": "hello"}]}}
+    res = _run(svc.generateChatResponse(chat))
+    assert res["message"]["role"] == "assistant" and res["eval_count"] == 4 and "response" not in res
+
+    async def collect():
+        return [c async for c in svc.generateChatStreamResponse(dict(chat, id="c3", stream=True))]
+    assert "".join(c["response"] for c in _run(collect())) == res["message"]["content"]
+    emb = _run(svc.generateEmbedding({"id": "e1", "model": "tiny:latest", "input": ["the rain", "hello world"], "priority": "low",
+                                      "metadata": {"requestType": "embedding"}}))
+    e = np.asarray(emb["embeddings"])
+    assert e.shape == (2, 256) and np.allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+    with pytest.raises(RuntimeError, match="Embedding failed: Input is required"):
+        _run(svc.generateEmbedding({"id": "e2", "model": "tiny:latest", "priority": "low"}))
+    with pytest.raises(RuntimeError, match="Chat inference failed: Chat request must include messages"):
+        _run(svc.generateChatResponse({"id": "c2", "model": "tiny:latest", "priority": "low"}))
+    with pytest.raises(RuntimeError, match="Inference failed"):
+        _run(svc.generateResponse({"id": "x", "model": "missing", "prompt": "a", "priority": "low"}))
+
+
+def test_workers_shard_requests_like_the_scheduler(tiny_gguf, hostcheck_lib, monkeypatch):
+    """two workers behind the scheduler stand-in: least-loaded selection, priority order, results equal to the oracle's"""
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    from oracle import llama_oracle as O
+    from sched_standin import SchedulerStandIn
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 2)
+    bus = LocalBus()
+    sched = SchedulerStandIn(bus)
+    svcs = [SV.NativeInferenceService({"tiny:latest": tiny_gguf}, device=i) for i in range(2)]
+    workers = [NativeWorker(f"b200-{i}", s, bus) for i, s in enumerate(svcs)]
+
+    async def go():
+        await sched.start()
+        for w in workers:
+            await w.start()
+        for i in range(6):
+            ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=12).tolist()
+            sched.add_job({"id": f"job-{i}", "model": "tiny:latest", "prompt": "", "stream": False, "priority": "high" if i == 5 else "medium",
+                           "options": {"num_predict": 4, "ignore_eos": True}, "timeout": 300000, "metadata": {"prompt_token_ids": ids}})
+        await sched.run_until_empty()
+    _run(go())
+    assert len(sched.results) == 6 and all("result" in r for r in sched.results.values())
+    assert set(sched.assigned.values()) == {"b200-0", "b200-1"}
+    first = [c for c, m in bus.log if c.startswith("worker:b200-") and c.endswith(":job")][0]
+    assert json.loads([m for c, m in bus.log if c == first][0])["job"]["jobId"] == "job-5"          # priority sort (JobScheduler.ts:145-151)
+    m = O.load_gguf(tiny_gguf)
+    for i in range(6):
+        ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=12)
+        ref = O.LlamaOracle(m, act="i16", kv_f16=True).generate(ids, 4)
+        assert sched.results[f"job-{i}"]["result"]["context"] == [int(t) for t in ref["ids"]]
