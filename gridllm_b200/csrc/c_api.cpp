@@ -89,6 +89,16 @@ int gl_detokenize(const gl_engine* e, const int32_t* ids, int32_t n, char* buf, 
     return GL_OK;
 }
 
+int gl_chat_template(const gl_engine* e, char* buf, int32_t cap, int32_t* len_out) {
+    if (!e || !len_out) return bad("gl_chat_template: null argument");
+    const std::string& s = e->impl->tokenizer().chat_template;      // "" when the file carries none
+    *len_out = (int32_t)s.size();
+    if (!buf) return GL_OK;                                          // size query
+    if ((int32_t)s.size() > cap) { gl::set_last_error("gl_chat_template: output buffer too small"); return GL_ERR_INVALID; }
+    std::memcpy(buf, s.data(), s.size());
+    return GL_OK;
+}
+
 int gl_generate(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_sample_opts* opts, gl_token_cb cb, void* user,
                 int32_t* out_ids, float* out_logprobs, gl_gen_stats* stats) {
     if (!e || !prompt) return bad("gl_generate: null argument");

@@ -26,7 +26,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 # every symbol include/gridllm_native.h declares (tests/test_abi.py checks the library exports all)
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
-    "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
+    "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_chat_template", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
     lib.gl_engine_info.argtypes = [vp, C.POINTER(ModelInfo)]
     lib.gl_tokenize.argtypes = [vp, C.c_char_p, i32, C.c_int, C.c_int, i32p, i32, i32p]
     lib.gl_detokenize.argtypes = [vp, i32p, i32, C.c_char_p, i32, i32p]
+    lib.gl_chat_template.argtypes = [vp, C.c_char_p, i32, i32p]
     lib.gl_generate.argtypes = [vp, i32p, i32, C.POINTER(SampleOpts), TOKEN_CB, vp, i32p, f32p, C.POINTER(GenStats)]
     lib.gl_embed.argtypes = [vp, i32p, i32p, i32, f32p, C.POINTER(GenStats)]
     lib.gl_last_logits.argtypes = [vp, i32, f32p, i32]
@@ -174,6 +175,17 @@ class Engine:
         buf = C.create_string_buffer(cap)
         n = C.c_int32(0)
         _check(self._lib.gl_detokenize(self._h, _i32p(a), len(a), buf, cap, C.byref(n)))
+        return buf.raw[: n.value].decode("utf-8", "replace")
+
+    @property
+    def chat_template(self) -> str:
+        """tokenizer.chat_template of the GGUF ('' when absent)"""
+        n = C.c_int32(0)
+        _check(self._lib.gl_chat_template(self._h, None, 0, C.byref(n)))
+        if n.value <= 0:
+            return ""
+        buf = C.create_string_buffer(n.value)
+        _check(self._lib.gl_chat_template(self._h, buf, n.value, C.byref(n)))
         return buf.raw[: n.value].decode("utf-8", "replace")
 
     # ---- hot path ---------------------------------------------------------------------------

@@ -164,12 +164,32 @@ class NativeInferenceService:
         return eng.tokenize(text or "", add_bos=True, parse_special=False)
 
     def _chat_prompt(self, eng: N.Engine, messages: List[Dict[str, Any]]) -> str:
-        # Llama-3 style header framing when the GGUF has no usable template engine on this side;
-        # the gateway's own /api/chat flattening ("role: content\n...assistant:", ollama.ts:367-370)
-        # reaches generate*, not this method.
-        parts = []
-        for m in messages:
-            parts.append(f"<|start_header_id|>{m.get('role', 'user')}<|end_header_id|>\n\n{m.get('content', '')}<|eot_id|>")
+        """messages -> prompt text.  The GGUF's chat template is not interpreted (it is Jinja); its FAMILY is recognised from
+        the markers it contains -- what llama.cpp's template detection does [external] -- and the family's framing applied:
+        Llama-3 headers (also the default without a template), ChatML, Llama-2 / Mistral [INST].  The gateway's own /api/chat
+        flattening ("role: content\n...assistant:", ollama.ts:367-370) reaches generate*, not this method."""
+        try:
+            tmpl = eng.chat_template or ""
+        except Exception:
+            tmpl = ""
+        msgs = [(m.get("role", "user"), m.get("content", "")) for m in messages]
+        if "<|im_start|>" in tmpl:                       # ChatML
+            return "".join(f"<|im_start|>{r}\n{c}<|im_end|>\n" for r, c in msgs) + "<|im_start|>assistant\n"
+        if "[INST]" in tmpl:                             # Llama-2 / Mistral
+            system = "\n\n".join(c for r, c in msgs if r == "system")
+            out, first = "", True
+            for r, c in msgs:
+                if r == "system":
+                    continue
+                if r == "assistant":
+                    out += f" {c}</s>"
+                    continue
+                if first and system:
+                    c = f"<<SYS>>\n{system}\n<</SYS>>\n\n{c}" if "<<SYS>>" in tmpl else f"{system}\n\n{c}"
+                first = False
+                out += f"[INST] {c} [/INST]"
+            return out
+        parts = [f"<|start_header_id|>{r}<|end_header_id|>\n\n{c}<|eot_id|>" for r, c in msgs]      # Llama-3 (and default)
         parts.append("<|start_header_id|>assistant<|end_header_id|>\n\n")
         return "".join(parts)
 

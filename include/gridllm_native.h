@@ -114,6 +114,9 @@ int  gl_engine_info(const gl_engine* e, gl_model_info* out); /* getAvailableMode
 int  gl_tokenize(const gl_engine* e, const char* utf8, int32_t n_bytes, int add_bos, int parse_special,
                  int32_t* ids, int32_t cap, int32_t* n_out);
 int  gl_detokenize(const gl_engine* e, const int32_t* ids, int32_t n, char* buf, int32_t cap, int32_t* len_out);
+/* tokenizer.chat_template of the GGUF (UTF-8, not NUL-terminated; *len_out = its length, 0 when absent; buf may be NULL to
+ * query the size).  The host picks the message framing from it (generateChat*Response, OllamaService.ts:353-599). */
+int  gl_chat_template(const gl_engine* e, char* buf, int32_t cap, int32_t* len_out);
 
 /* ---- the hot path ---------------------------------------------------------------------
  * gl_generate: generateResponse / generateStreamResponse / generateChat*Response

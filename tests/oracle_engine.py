@@ -25,6 +25,7 @@ class OracleEngine:
         self.info = SimpleNamespace(has_tokenizer=1, n_vocab=self.m.n_vocab, n_embd=self.m.n_embd, n_params=int(1e6), quantization=b"Q4_K_M",
                                     eos_id=self.m.n_vocab - 2, eot_id=self.m.n_vocab - 1, bos_id=self.m.n_vocab - 3)
         self.calls = []
+        self.chat_template = ""
 
     # ---- tokenizer: the product's C++ code --------------------------------------------------------------------------
     def tokenize(self, text, add_bos=True, parse_special=False):

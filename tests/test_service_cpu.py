@@ -131,3 +131,27 @@ def test_workers_shard_requests_like_the_scheduler(tiny_gguf, hostcheck_lib, mon
         ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=12)
         ref = O.LlamaOracle(m, act="i16", kv_f16=True).generate(ids, 4)
         assert sched.results[f"job-{i}"]["result"]["context"] == [int(t) for t in ref["ids"]]
+
+
+def test_chat_framing_follows_the_template_family(svc):
+    eng = svc._engine("tiny:latest")
+    msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "hi"}, {"role": "assistant", "content": "hello"},
+            {"role": "user", "content": "bye"}]
+    eng.chat_template = ""                                   # no template in the file: Llama-3 framing
+    p = svc._chat_prompt(eng, msgs)
+    assert p.startswith("<|start_header_id|>system<|end_header_id|>\n\nbe brief<|eot_id|>") and p.endswith("<|start_header_id|>assistant<|end_header_id|>\n\n")
+    ids = eng.tokenize(p, add_bos=True, parse_special=True)
+    assert int(ids[0]) == eng.info.bos_id and (ids == eng.info.eot_id).sum() == 4      # control tokens parsed, not spelled out
+    eng.chat_template = "{% for m in messages %}<|im_start|>{{ m.role }}\n{{ m.content }}<|im_end|>\n{% endfor %}"
+    assert svc._chat_prompt(eng, msgs) == ("<|im_start|>system\nbe brief<|im_end|>\n<|im_start|>user\nhi<|im_end|>\n<|im_start|>assistant\nhello<|im_end|>\n"
+                                           "<|im_start|>user\nbye<|im_end|>\n<|im_start|>assistant\n")
+    eng.chat_template = "{{ bos_token }}{% for m in messages %}[INST] {{ m.content }} [/INST]{% endfor %}"
+    assert svc._chat_prompt(eng, msgs) == "[INST] be brief\n\nhi [/INST] hello</s>[INST] bye [/INST]"
+    eng.chat_template = "[INST] <<SYS>>\n{{ system }}\n<</SYS>>\n\n{{ user }} [/INST]"
+    assert svc._chat_prompt(eng, msgs[:2]) == "[INST] <<SYS>>\nbe brief\n<</SYS>>\n\nhi [/INST]"
+
+    class Broken:                                            # an engine whose accessor fails still gets the default framing
+        @property
+        def chat_template(self):
+            raise RuntimeError("boom")
+    assert svc._chat_prompt(Broken(), msgs[1:2]).startswith("<|start_header_id|>user<|end_header_id|>\n\nhi<|eot_id|>")
