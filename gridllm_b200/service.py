@@ -89,11 +89,16 @@ class NativeInferenceService:
     OLLAMA_SAMPLING_DEFAULTS = {"temperature": 0.8, "top_k": 40, "top_p": 0.9}
 
     def __init__(self, models: Dict[str, str], device: int = 0, max_ctx: int = 0,
-                 sampling_defaults: Optional[Dict[str, Any]] = None, **engine_kw):
+                 sampling_defaults: Optional[Dict[str, Any]] = None, apply_template: bool = False, **engine_kw):
         """models: Ollama-style model name -> GGUF path.
         sampling_defaults: options a request inherits when it does not carry them.  None = greedy (temperature 0, the
-        BASELINE.json configuration); pass OLLAMA_SAMPLING_DEFAULTS to behave like an Ollama worker for such requests."""
+        BASELINE.json configuration); pass OLLAMA_SAMPLING_DEFAULTS to behave like an Ollama worker for such requests.
+        apply_template: frame generate / completion prompts as one user turn of the model's chat template (with
+        metadata.system as the system turn) unless metadata.raw, as Ollama does; default False = raw prompts."""
         self._sampling_defaults = dict(sampling_defaults or {})
+        # Ollama wraps the prompt of /api/generate and /v1/completions in the model's template (system + prompt as one user
+        # turn) unless the request says raw [external]; off by default: the prompt text is tokenised as it is
+        self._apply_template = bool(apply_template)
         self._paths = dict(models)
         self._device = device
         self._max_ctx = max_ctx
@@ -158,6 +163,9 @@ class NativeInferenceService:
         if not eng.info.has_tokenizer:
             raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
         ctx = md.get("context")                          # token ids of the conversation so far (OllamaService.ts:224-226)
+        if self._apply_template and not md.get("raw") and not ctx:      # metadata.system / raw: OllamaService.ts:212-220
+            msgs = ([{"role": "system", "content": md["system"]}] if md.get("system") else []) + [{"role": "user", "content": text or ""}]
+            return eng.tokenize(self._chat_prompt(eng, msgs), add_bos=True, parse_special=True)
         if ctx:
             new = eng.tokenize(text or "", add_bos=False, parse_special=False)
             return np.concatenate([np.asarray(ctx, dtype=np.int32), np.asarray(new, dtype=np.int32)])

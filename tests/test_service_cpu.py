@@ -155,3 +155,23 @@ def test_chat_framing_follows_the_template_family(svc):
         def chat_template(self):
             raise RuntimeError("boom")
     assert svc._chat_prompt(Broken(), msgs[1:2]).startswith("<|start_header_id|>user<|end_header_id|>\n\nhi<|eot_id|>")
+
+
+def test_generate_prompts_can_be_framed_like_ollama(tiny_gguf, hostcheck_lib, monkeypatch):
+    """apply_template=True: /api/generate-style prompts become one user turn of the model's template (metadata.system as the
+    system turn) unless metadata.raw; the default service tokenises the prompt text as it is"""
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    s = SV.NativeInferenceService({"tiny:latest": tiny_gguf}, apply_template=True)
+    eng = s._engine("tiny:latest")
+    req = {"id": "g", "model": "tiny:latest", "prompt": "hi there", "metadata": {"system": "be brief"}}
+    framed = eng.detokenize(s._prompt_ids(eng, req, req["prompt"])[1:])
+    assert "be brief" in framed and "hi there" in framed and framed.index("be brief") < framed.index("hi there")
+    ids = s._prompt_ids(eng, req, req["prompt"])
+    assert (ids == eng.info.eot_id).sum() == 2
+    raw = s._prompt_ids(eng, dict(req, metadata={"raw": True}), req["prompt"])
+    assert list(raw) == list(eng.tokenize("hi there"))
+    plain = SV.NativeInferenceService({"tiny:latest": tiny_gguf})
+    assert list(plain._prompt_ids(plain._engine("tiny:latest"), req, req["prompt"])) == list(eng.tokenize("hi there"))
