@@ -8,6 +8,7 @@ from gridllm_b200.service import NativeInferenceService
 def _svc(defaults=None):
     s = NativeInferenceService.__new__(NativeInferenceService)       # no engines: only the option logic is exercised
     s._sampling_defaults = dict(defaults or {})
+    s._apply_template = False
     return s
 
 
