@@ -387,6 +387,11 @@ class NativeInferenceService:
                     raise RuntimeError("model carries no tokenizer; supply metadata.input_token_ids")
                 texts = inp if isinstance(inp, list) else [inp]
                 seqs = [eng.tokenize(t, add_bos=True, parse_special=False) for t in texts]
+            # metadata.truncate (OllamaService.ts:626-628): inputs longer than the context are cut to it unless truncate is false,
+            # in which case the engine's context error surfaces (what /api/embed does [external])
+            n_ctx = int(getattr(eng.info, "n_ctx", 0) or 0)
+            if n_ctx > 0 and md.get("truncate", True) is not False:
+                seqs = [s[:n_ctx] for s in seqs]
 
             def work():
                 with self._lock:

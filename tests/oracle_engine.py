@@ -22,7 +22,7 @@ class OracleEngine:
         assert _LIB is not None, "call oracle_engine.use_hostcheck(hostcheck_lib) first"
         self.path = gguf_path
         self.m = O.load_gguf(gguf_path)
-        self.info = SimpleNamespace(has_tokenizer=1, n_vocab=self.m.n_vocab, n_embd=self.m.n_embd, n_params=int(1e6), quantization=b"Q4_K_M",
+        self.info = SimpleNamespace(has_tokenizer=1, n_vocab=self.m.n_vocab, n_embd=self.m.n_embd, n_params=int(1e6), quantization=b"Q4_K_M", n_ctx=int(max_ctx) if max_ctx else 512,
                                     eos_id=self.m.n_vocab - 2, eot_id=self.m.n_vocab - 1, bos_id=self.m.n_vocab - 3)
         self.calls = []
         self.chat_template = ""
@@ -73,6 +73,8 @@ class OracleEngine:
         return SimpleNamespace(ids=np.array(ids, dtype=np.int32), logprobs=np.array(lps, dtype=np.float32), stats=stats)
 
     def embed(self, seqs):
+        if any(len(s) > self.info.n_ctx for s in seqs):
+            raise RuntimeError("GL_ERR_CONTEXT: sequence exceeds the engine context")
         orc = O.LlamaOracle(self.m, act="i16")
         out = np.stack([orc.embed(s) for s in seqs]).astype(np.float32)
         return out, SimpleNamespace(prompt_eval_count=int(sum(len(s) for s in seqs)), load_duration_ns=1)

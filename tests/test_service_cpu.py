@@ -175,3 +175,19 @@ def test_generate_prompts_can_be_framed_like_ollama(tiny_gguf, hostcheck_lib, mo
     assert list(raw) == list(eng.tokenize("hi there"))
     plain = SV.NativeInferenceService({"tiny:latest": tiny_gguf})
     assert list(plain._prompt_ids(plain._engine("tiny:latest"), req, req["prompt"])) == list(eng.tokenize("hi there"))
+
+
+def test_embedding_inputs_are_truncated_to_the_context(tiny_gguf, hostcheck_lib, monkeypatch):
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    s = SV.NativeInferenceService({"tiny:latest": tiny_gguf}, max_ctx=16)
+    long_ids = list(range(1, 41))
+    req = {"id": "e", "model": "tiny:latest", "metadata": {"requestType": "embedding", "input_token_ids": [long_ids, long_ids[:5]]}}
+    res = _run(s.generateEmbedding(req))
+    assert res["prompt_eval_count"] == 16 + 5 and len(res["embeddings"]) == 2
+    ref = _run(s.generateEmbedding(dict(req, metadata=dict(req["metadata"], input_token_ids=[long_ids[:16], long_ids[:5]]))))
+    assert np.allclose(res["embeddings"], ref["embeddings"])
+    with pytest.raises(RuntimeError, match="Embedding failed"):
+        _run(s.generateEmbedding(dict(req, metadata=dict(req["metadata"], truncate=False))))
