@@ -208,6 +208,11 @@ class NativeInferenceService:
         eng = self._engine(model)
         kw = self._sampling(options)
         ignore_eos = bool(options.get("ignore_eos", False))
+        # a generation that would run past the engine's context ends at it (done_reason "length") instead of failing; a prompt
+        # that does not fit at all still fails (GL_ERR_CONTEXT)
+        n_ctx = int(getattr(eng.info, "n_ctx", 0) or 0)
+        if n_ctx > 0 and len(ids) < n_ctx:
+            num_predict = min(num_predict, n_ctx - len(ids))
         stops = options.get("stop")
         stops = [stops] if isinstance(stops, str) else list(stops or [])
         if not stops or not eng.info.has_tokenizer:

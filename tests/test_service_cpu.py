@@ -191,3 +191,16 @@ def test_embedding_inputs_are_truncated_to_the_context(tiny_gguf, hostcheck_lib,
     assert np.allclose(res["embeddings"], ref["embeddings"])
     with pytest.raises(RuntimeError, match="Embedding failed"):
         _run(s.generateEmbedding(dict(req, metadata=dict(req["metadata"], truncate=False))))
+
+
+def test_generation_ends_at_the_context(tiny_gguf, hostcheck_lib, monkeypatch):
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    s = SV.NativeInferenceService({"tiny:latest": tiny_gguf}, max_ctx=16)
+    req = {"id": "g", "model": "tiny:latest", "prompt": "", "options": {"num_predict": 50, "ignore_eos": True},
+           "metadata": {"prompt_token_ids": list(range(1, 11))}}
+    res = _run(s.generateResponse(req))
+    assert res["prompt_eval_count"] == 10 and res["eval_count"] == 6 and res["done_reason"] == "length"
+    assert s._engine("tiny:latest").calls[-1]["num_predict"] == 6
