@@ -66,6 +66,7 @@ class NativeWorker:
         self.currentJobs = 0
         self.capabilities: Optional[Dict[str, Any]] = None
         self._cancelled: set = set()
+        self._hb_task: Optional[asyncio.Task] = None
 
     # ---- boot (WorkerClientService.initialize/start, :35-89) ----------------------------------------
     async def start(self) -> None:
@@ -84,6 +85,25 @@ class NativeWorker:
               "currentJobs": self.currentJobs, "connectionHealth": "healthy"}
         await self.bus.set_with_expiry(f"heartbeat:{self.worker_id}", json.dumps(hb), self.heartbeat_interval_ms * 2 / 1000)
         await self.bus.publish("worker:heartbeat", json.dumps(hb))
+
+    # the reference fires heartbeats from a timer (WorkerClientService.ts:316-323); they must keep firing while a job runs,
+    # which is why every engine call of the service runs off the event loop (asyncio.to_thread / a worker thread)
+    def start_heartbeats(self) -> None:
+        async def loop():
+            while True:
+                await self.sendHeartbeat()
+                await asyncio.sleep(self.heartbeat_interval_ms / 1000)
+        if self._hb_task is None:
+            self._hb_task = asyncio.get_running_loop().create_task(loop())
+
+    async def stop(self) -> None:
+        if self._hb_task is not None:
+            self._hb_task.cancel()
+            try:
+                await self._hb_task
+            except asyncio.CancelledError:
+                pass
+            self._hb_task = None
 
     async def publishStatusUpdate(self) -> None:
         await self.bus.publish("worker:status_update", json.dumps(

@@ -204,3 +204,31 @@ def test_generation_ends_at_the_context(tiny_gguf, hostcheck_lib, monkeypatch):
     res = _run(s.generateResponse(req))
     assert res["prompt_eval_count"] == 10 and res["eval_count"] == 6 and res["done_reason"] == "length"
     assert s._engine("tiny:latest").calls[-1]["num_predict"] == 6
+
+
+def test_heartbeats_keep_firing_while_a_job_runs(tiny_gguf, hostcheck_lib, monkeypatch):
+    """the native call must not block the worker's event loop (heartbeats, WorkerClientService.ts:316-323)"""
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 1)
+    bus = LocalBus()
+    w = NativeWorker("b200-0", SV.NativeInferenceService({"tiny:latest": tiny_gguf}), bus, heartbeat_interval_ms=10)
+    job = {"type": "job_assignment", "job": {"jobId": "j1", "request": {
+        "id": "j1", "model": "tiny:latest", "prompt": "", "stream": False, "priority": "medium", "options": {"num_predict": 60, "ignore_eos": True},
+        "metadata": {"prompt_token_ids": list(range(1, 40))}}}}
+
+    async def go():
+        await w.start()
+        w.start_heartbeats()
+        await bus.publish("worker:b200-0:job", json.dumps(job))
+        await asyncio.sleep(0.03)
+        await w.stop()
+    _run(go())
+    beats = [json.loads(m) for c, m in bus.log if c == "worker:heartbeat"]
+    busy = [b for b in beats if b["status"] == "busy"]
+    assert len(busy) >= 3 and all(b["currentJobs"] == 1 for b in busy)      # fired DURING the job
+    assert beats[-1]["status"] == "online"                                   # and after it
+    assert any(c == "job:completed" for c, _ in bus.log)
