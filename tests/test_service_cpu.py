@@ -232,3 +232,37 @@ def test_heartbeats_keep_firing_while_a_job_runs(tiny_gguf, hostcheck_lib, monke
     assert len(busy) >= 3 and all(b["currentJobs"] == 1 for b in busy)      # fired DURING the job
     assert beats[-1]["status"] == "online"                                   # and after it
     assert any(c == "job:completed" for c, _ in bus.log)
+
+
+def test_job_cancellation_stops_a_streaming_job(tiny_gguf, hostcheck_lib, monkeypatch):
+    """job_cancellation (JobScheduler.ts:530-536; ignored by the reference worker, honoured here): the stream ends early, the
+    engine call is cancelled through the token callback, the result carries what was generated so far"""
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 1)
+    bus = LocalBus()
+    svc = SV.NativeInferenceService({"tiny:latest": tiny_gguf})
+    w = NativeWorker("b200-0", svc, bus)
+    job = {"type": "job_assignment", "job": {"jobId": "j1", "request": {
+        "id": "j1", "model": "tiny:latest", "prompt": "", "stream": True, "priority": "medium", "options": {"num_predict": 120, "ignore_eos": True},
+        "metadata": {"prompt_token_ids": list(range(1, 10))}}}}
+
+    async def go():
+        await w.start()
+        task = asyncio.get_running_loop().create_task(bus.publish("worker:b200-0:job", json.dumps(job)))
+        while not any(c == "job:stream:j1" for c, _ in bus.log):        # wait for the first streamed chunk
+            await asyncio.sleep(0.005)
+        await w.handleJobMessage(json.dumps({"type": "job_cancellation", "jobId": "j1"}))
+        await task
+    _run(go())
+    chunks = [json.loads(m) for c, m in bus.log if c == "job:stream:j1"]
+    assert 1 <= len(chunks) < 120
+    done = [json.loads(m) for c, m in bus.log if c == "job:completed"]
+    assert len(done) == 1 and done[0]["result"]["done"] is True
+    # the engine stopped too: far fewer than the 120 requested steps were taken
+    import time
+    time.sleep(0.05)
+    assert w.isProcessingJob is False and w.currentJobs == 0
