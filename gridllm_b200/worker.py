@@ -57,11 +57,17 @@ class LocalBus:
 class NativeWorker:
     """One worker id <-> one GPU engine."""
 
-    def __init__(self, worker_id: str, service: NativeInferenceService, bus: LocalBus, heartbeat_interval_ms: int = 5000):
+    def __init__(self, worker_id: str, service: NativeInferenceService, bus: LocalBus, heartbeat_interval_ms: int = 5000,
+                 max_concurrent: int = 1):
         self.worker_id = worker_id
         self.service = service
         self.bus = bus
         self.heartbeat_interval_ms = heartbeat_interval_ms
+        # jobs this worker holds at once (MAX_CONCURRENT_JOBS_PER_WORKER on the server side, server/src/config/index.ts:31).
+        # 1 = the reference's busy-drop (:500-505).  More than one keeps the next job waiting at the engine while the current one
+        # runs, so the worker does not idle until the scheduler's next tick (the engine itself still runs one request at a time)
+        self.max_concurrent = max(1, int(max_concurrent))
+        self._tasks: set = set()
         self.isProcessingJob = False
         self.currentJobs = 0
         self.capabilities: Optional[Dict[str, Any]] = None
@@ -73,7 +79,7 @@ class NativeWorker:
         if not await self.service.checkHealth():
             raise RuntimeError("Ollama service is not available")      # same message the reference throws (:43-47)
         models = await self.service.getAvailableModels()
-        self.capabilities = {"workerId": self.worker_id, "availableModels": models, "maxConcurrentTasks": 1,
+        self.capabilities = {"workerId": self.worker_id, "availableModels": models, "maxConcurrentTasks": self.max_concurrent,
                              "supportedFormats": ["json", "text"], "lastUpdated": _iso()}
         reg = {"workerId": self.worker_id, "capabilities": self.capabilities, "status": "online", "registeredAt": _iso()}
         await self.bus.hset("workers", self.worker_id, json.dumps(reg))
@@ -96,7 +102,13 @@ class NativeWorker:
         if self._hb_task is None:
             self._hb_task = asyncio.get_running_loop().create_task(loop())
 
+    async def drain(self) -> None:
+        """wait for the jobs this worker holds (max_concurrent > 1 runs them as tasks)"""
+        while self._tasks:
+            await asyncio.gather(*list(self._tasks), return_exceptions=True)
+
     async def stop(self) -> None:
+        await self.drain()
         if self._hb_task is not None:
             self._hb_task.cancel()
             try:
@@ -113,17 +125,22 @@ class NativeWorker:
     async def handleJobMessage(self, message: str) -> None:
         data = json.loads(message)
         if data.get("type") == "job_assignment":
-            await self.processJobAssignment(data["job"])
+            if self.max_concurrent == 1:
+                await self.processJobAssignment(data["job"])
+            else:                                    # run beside the jobs already held; the message handler returns at once
+                t = asyncio.get_running_loop().create_task(self.processJobAssignment(data["job"]))
+                self._tasks.add(t)
+                t.add_done_callback(self._tasks.discard)
         elif data.get("type") == "job_cancellation":
             self._cancelled.add(data.get("jobId"))
 
     # ---- processJobAssignment (:497-712) ---------------------------------------------------------------
     async def processJobAssignment(self, assignment: Dict[str, Any]) -> None:
         request = assignment["request"]
-        if self.isProcessingJob:
+        if self.currentJobs >= self.max_concurrent or (self.max_concurrent == 1 and self.isProcessingJob):
             return                                   # dropped; the server notices via timeout / orphan scan
+        self.currentJobs += 1
         self.isProcessingJob = True
-        self.currentJobs = 1
         await self.publishStatusUpdate()
         jid = request["id"]
         try:
@@ -170,7 +187,7 @@ class NativeWorker:
             await self.bus.publish("job:failed", payload)
             await self.bus.publish(f"job:result:{jid}", payload)
         finally:
-            self.isProcessingJob = False
-            self.currentJobs = 0
+            self.currentJobs -= 1
+            self.isProcessingJob = self.currentJobs > 0
             self._cancelled.discard(jid)
             await self.publishStatusUpdate()

@@ -266,3 +266,42 @@ def test_job_cancellation_stops_a_streaming_job(tiny_gguf, hostcheck_lib, monkey
     import time
     time.sleep(0.05)
     assert w.isProcessingJob is False and w.currentJobs == 0
+
+
+def test_worker_can_hold_more_than_one_job(tiny_gguf, hostcheck_lib, monkeypatch):
+    """max_concurrent = 2 (MAX_CONCURRENT_JOBS_PER_WORKER > 1 on the server side): a second assignment is accepted while the
+    first runs and waits at the engine; a third is dropped like the reference drops a second; results are unaffected"""
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    from oracle import llama_oracle as O
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 1)
+    bus = LocalBus()
+    w = NativeWorker("b200-0", SV.NativeInferenceService({"tiny:latest": tiny_gguf}), bus, heartbeat_interval_ms=5, max_concurrent=2)
+    prompts = {f"j{i}": np.random.Generator(np.random.PCG64(50 + i)).integers(0, 500, size=10).tolist() for i in range(3)}
+
+    def job(jid):
+        return json.dumps({"type": "job_assignment", "job": {"jobId": jid, "request": {
+            "id": jid, "model": "tiny:latest", "prompt": "", "stream": False, "priority": "medium", "options": {"num_predict": 20, "ignore_eos": True},
+            "metadata": {"prompt_token_ids": prompts[jid]}}}})
+
+    async def go():
+        await w.start()
+        assert w.capabilities["maxConcurrentTasks"] == 2
+        w.start_heartbeats()
+        for jid in ("j0", "j1", "j2"):
+            await bus.publish("worker:b200-0:job", job(jid))         # returns at once: the jobs run as tasks
+        await asyncio.sleep(0.01)                                    # let the tasks start
+        assert w.currentJobs == 2                                    # j2 was dropped
+        await w.stop()
+    _run(go())
+    done = {json.loads(m)["jobId"]: json.loads(m) for c, m in bus.log if c == "job:completed"}
+    assert set(done) == {"j0", "j1"} and not any(c == "job:failed" for c, _ in bus.log)
+    m = O.load_gguf(tiny_gguf)
+    for jid in ("j0", "j1"):
+        ref = O.LlamaOracle(m, act="i16", kv_f16=True).generate(prompts[jid], 20)
+        assert done[jid]["result"]["context"] == [int(t) for t in ref["ids"]]
+    assert max(json.loads(m)["currentJobs"] for c, m in bus.log if c == "worker:heartbeat") == 2
+    assert w.currentJobs == 0 and w.isProcessingJob is False
