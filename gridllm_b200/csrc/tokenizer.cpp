@@ -66,7 +66,7 @@ inline bool is_nl(uint32_t c) { return c == '\n' || c == '\r'; }
 //  (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n\p{L}\p{N}]?\p{L}+ | \p{N}{1,3} | ' '?[^\s\p{L}\p{N}]+[\r\n]* | \s*[\r\n]+ | \s+(?!\S) | \s+
 // Alternatives are tried in this order at every position, each greedy with the backtracking the expression implies.  Pinned
 // against the Hugging Face `tokenizers` regex engine in tests/test_tokenizer.py (ASCII, accents, CJK, other-script digits,
-// Unicode spaces, emoji).  The contraction alternative is case-insensitive for ASCII only.
+// Unicode spaces, emoji).  The contraction alternative folds case for ASCII and U+017F.
 std::vector<std::string> llama3_pretokenize(const std::string& t) {
     std::vector<Cp> u;
     u.reserve(t.size());
@@ -86,7 +86,8 @@ std::vector<std::string> llama3_pretokenize(const std::string& t) {
     u.push_back(Cp{0, (uint32_t)t.size()});          // sentinel: byte offset of the end
     std::vector<std::string> out;
     auto emit = [&](size_t a, size_t b) { out.push_back(t.substr(u[a].off, u[b].off - u[a].off)); };
-    auto lower = [](uint32_t c) { return (c >= 'A' && c <= 'Z') ? c + 32 : c; };
+    // case folding of the contraction alternative: ASCII, plus U+017F (long s), which folds to 's' in Unicode-aware engines
+    auto lower = [](uint32_t c) { return (c >= 'A' && c <= 'Z') ? c + 32 : (c == 0x17F ? (uint32_t)'s' : c); };
     size_t i = 0;
     while (i < n) {
         const uint32_t c = u[i].cp;

@@ -60,7 +60,7 @@ PRETOK_TEXTS = [
     "naïve façade Ünïcödé straße ǅ", "日本語のテキスト、句読点。「引用」", "Привет, мир! Ελληνικά; עברית ، العربية", "१२३४५ ٣٤٥ Ⅻ ½ ²³ 1234567890",
     "no break em　ideographic  spaces line", "emoji 😀😃 mixed👍🏽text 🇩🇪", "x=y+z*(a/b)-[c]{d}<e>|f&g^h%i$j#k@l!m~n`o", "   leading and trailing   ",
     "...!!!???\n\n\n", "CamelCaseWordsAndsnake_case_words and kebab-case", "price: $1,234.56 (≈€1.100,00) 50% off!!", "\n", " ", "", "a", "'", "''s", "１２３ｆｕｌｌｗｉｄｔｈ",
-    "mixed١٢٣abc४५६def", "end with space ", "end with spaces  \t", "\t\tword", " \n \n x", "a  \n  b", "def f(x):\n    return x**2  # comment\n",
+    "mixed١٢٣abc४५६def", "it'ſ ok x'ſt we'LL I'D", "end with space ", "end with spaces  \t", "\t\tword", " \n \n x", "a  \n  b", "def f(x):\n    return x**2  # comment\n",
 ]
 
 
