@@ -2,7 +2,8 @@
 // In the reference the tokenizer lives inside Ollama; OllamaService only ever ships prompt TEXT
 // (/root/reference/client/src/services/OllamaService.ts:101-104, 190-195), so a native worker needs
 // its own.  Supports tokenizer.ggml.model == "gpt2" (Llama-3 family).  The pre-tokeniser is the
-// llama-bpe split over Unicode code points (general categories L* / N* from generated tables, White_Space).
+// llama-bpe split over Unicode code points (general categories L* / N* from generated tables -- tools/gen_unicode_ranges.py --
+// and White_Space).
 #pragma once
 #include <cstdint>
 #include <string>

@@ -117,3 +117,22 @@ def test_full_tokenizer_matches_the_tokenizers_library(hostcheck_lib, tiny_gguf)
         ids = np.zeros(2048, np.int32)
         n = hostcheck_lib.hc_tokenize(tiny_gguf.encode(), text.encode(), 0, 0, ids.ctypes.data_as(ctypes.c_void_p), 2048)
         assert list(ids[:n]) == tk.encode(text).ids, repr(text)
+
+
+def test_pretokeniser_unicode_fuzz(hostcheck_lib):
+    """random strings over thousands of code points from every plane in use, exotic spaces, case-folding specials: the tables
+    in unicode_ranges.h are derived from the same engine, so any difference is a difference in the split logic"""
+    tokenizers = pytest.importorskip("tokenizers")
+    split = tokenizers.pre_tokenizers.Split(tokenizers.Regex(LLAMA3_SPLIT), behavior="isolated", invert=False)
+    rng = np.random.Generator(np.random.PCG64(321))
+    cands = [chr(cp) for cp in list(range(0x20, 0x7F)) + [9, 10, 11, 12, 13, 0x1C, 0x1F, 0x85, 0xA0, 0x1680, 0x180E, 0x2003, 0x200A, 0x2028, 0x2029, 0x202F,
+                                                            0x205F, 0x3000, 0x200B, 0x200D, 0xFEFF, 0xAD, 0x301, 0x20E3, 0x1F600, 0x1F1E9, 0x1F3FD, 0x2764,
+                                                            0xFE0F, 0x17F, 0x212A, 0x130]]
+    while len(cands) < 4000:
+        cp = int(rng.integers(0x80, 0x3FFFF))
+        if not 0xD800 <= cp <= 0xDFFF:
+            cands.append(chr(cp))
+    for _ in range(4000):
+        text = "".join(rng.choice(cands, size=int(rng.integers(1, 12))))
+        ref = [p for p, _ in split.pre_tokenize_str(text)]
+        assert _hc_pretokenize(hostcheck_lib, text) == ref, repr(text)
