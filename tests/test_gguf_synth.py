@@ -82,3 +82,28 @@ def test_engine_gguf_reader_agrees(tiny_gguf, hostcheck_lib):
     # corrupt / missing files are rejected with a message, not a crash
     assert hostcheck_lib.hc_gguf_probe(b"/nonexistent.gguf", arch, 256, ctypes.byref(nkv), ctypes.byref(tb)) == -1
     assert b"cannot open" in arch.value
+
+
+def test_engine_gguf_reader_rejects_truncated_files_and_survives_corruption(tiny_gguf, hostcheck_lib, tmp_path):
+    """the product's GGUF reader (gguf_file.cpp) on damaged files: every truncation is an error with a message, random byte
+    damage in the metadata / tensor-info region is either parsed or rejected -- never a crash or an out-of-bounds read"""
+    data = open(tiny_gguf, "rb").read()
+    arch = ctypes.create_string_buffer(256)
+    nkv, tb = ctypes.c_uint64(), ctypes.c_uint64()
+    cut = str(tmp_path / "damaged.gguf").encode()
+
+    def probe(b):
+        open(cut, "wb").write(b)
+        return hostcheck_lib.hc_gguf_probe(cut, arch, 256, ctypes.byref(nkv), ctypes.byref(tb))
+    assert probe(data) > 0
+    rng = np.random.Generator(np.random.PCG64(1))
+    cuts = sorted(set([0, 1, 3, 4, 8, 12, 16, 20, 24, 31, 32, 64, 100, 1000, 5000, 20000, len(data) // 2, len(data) - 1] + [int(x) for x in rng.integers(0, 60000, 30)]))
+    for c in cuts:
+        assert probe(data[:c]) == -1 and arch.value, c
+    outcomes = {True: 0, False: 0}
+    for _ in range(150):
+        b = bytearray(data)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, 40000))] = int(rng.integers(0, 256))
+        outcomes[probe(bytes(b)) >= 0] += 1
+    assert outcomes[True] + outcomes[False] == 150 and outcomes[False] > 0
