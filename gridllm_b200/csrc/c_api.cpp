@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 
 #include "../../include/gridllm_native.h"
@@ -47,11 +49,21 @@ int gl_device_count(int* n) {
 int gl_engine_create(const char* gguf_path, int device, const gl_engine_opts* opts, gl_engine** out) {
     if (!gguf_path || !out) return bad("gl_engine_create: null argument");
     *out = nullptr;
-    Engine* e = nullptr;
-    Status s = Engine::create(gguf_path, device, opts, &e);
-    if (!s.ok()) return ret(s);
-    *out = new gl_engine{e};
-    return GL_OK;
+    // nothing may unwind through the extern "C" boundary: a damaged file that makes the loader run out of memory or throw
+    // is an error code, not std::terminate
+    try {
+        Engine* e = nullptr;
+        Status s = Engine::create(gguf_path, device, opts, &e);
+        if (!s.ok()) return ret(s);
+        *out = new gl_engine{e};
+        return GL_OK;
+    } catch (const std::bad_alloc&) {
+        gl::set_last_error("gl_engine_create: out of host memory while loading (damaged or oversized GGUF?)");
+        return GL_ERR_NOMEM;
+    } catch (const std::exception& ex) {
+        gl::set_last_error(std::string("gl_engine_create: ") + ex.what());
+        return GL_ERR_FORMAT;
+    }
 }
 
 void gl_engine_destroy(gl_engine* e) {

@@ -195,7 +195,25 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     if (!n_layer_ || !n_embd_ || !n_head_ || !n_ff_) return fail(GL_ERR_FORMAT, "missing llama hyper-parameters in GGUF metadata");
     hd_ = (int)gguf_.get_u(key("rope.dimension_count"), n_embd_ / n_head_);
     if (hd_ * n_head_ != n_embd_ || (hd_ != 64 && hd_ != 128)) return fail(GL_ERR_UNSUPPORTED, "head_dim must be 64 or 128 and n_head*head_dim == n_embd");
-    if (n_head_ % n_kv_ || n_head_ / n_kv_ > 8) return fail(GL_ERR_UNSUPPORTED, "GQA group must divide n_head and be <= 8");
+    if (n_kv_ <= 0 || n_head_ % n_kv_ || n_head_ / n_kv_ > 8) return fail(GL_ERR_UNSUPPORTED, "GQA group must divide n_head and be <= 8");
+    // RoPE variants that are also general.architecture == llama: Llama-3.1 / 3.2 carry per-frequency factors in
+    // rope_freqs.weight, some long-context fine-tunes a linear position scale; YaRN / longrope change the attention scale and
+    // the interpolation ramp as well and are outside the path -- refused loudly rather than decoded with the wrong angles
+    const std::string rs_type = gguf_.get_s(key("rope.scaling.type"), "");
+    float rope_lin = 1.f;
+    if (rs_type == "linear") {
+        rope_lin = (float)gguf_.get_f(key("rope.scaling.factor"), 1.0);
+        if (!(rope_lin > 0.f) || !std::isfinite(rope_lin)) return fail(GL_ERR_FORMAT, "rope.scaling.factor must be a positive number");
+    } else if (!rs_type.empty() && rs_type != "none") {
+        return fail(GL_ERR_UNSUPPORTED, "rope.scaling.type '" + rs_type + "' is outside the hot path (none / linear only)");
+    }
+    std::vector<float> rope_ff;                       // frequency factors (Llama-3.1+), one per rotated pair
+    if (const GGUFTensor* tf = gguf_.tensor("rope_freqs.weight")) {
+        if (tf->type != T_F32 || tf->cols() * tf->rows() != hd_ / 2) return fail(GL_ERR_FORMAT, "rope_freqs.weight: expected F32[head_dim/2]");
+        rope_ff.assign(reinterpret_cast<const float*>(tf->data), reinterpret_cast<const float*>(tf->data) + hd_ / 2);
+        for (float f : rope_ff)
+            if (!(f > 0.f) || !std::isfinite(f)) return fail(GL_ERR_FORMAT, "rope_freqs.weight holds a non-positive factor");
+    }
     n_ctx_ = (opts && opts->max_ctx > 0) ? opts->max_ctx : std::min(n_ctx_train, 8192);
     n_ctx_ = (n_ctx_ + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS * KV_PAGE_TOKENS;
 
@@ -294,10 +312,13 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     {
         std::vector<float> c((size_t)n_ctx_ * hd_ / 2), s((size_t)n_ctx_ * hd_ / 2);
         std::vector<float> inv(hd_ / 2);
-        for (int i = 0; i < hd_ / 2; ++i) inv[i] = (float)std::pow((double)rope_base_, -2.0 * i / hd_);
+        for (int i = 0; i < hd_ / 2; ++i) {
+            inv[i] = (float)std::pow((double)rope_base_, -2.0 * i / hd_);
+            if (!rope_ff.empty()) inv[i] = inv[i] / rope_ff[i];       // fp32 division, like the oracle
+        }
         for (int pos = 0; pos < n_ctx_; ++pos)
             for (int i = 0; i < hd_ / 2; ++i) {
-                const float ang = (float)pos * inv[i];
+                const float ang = ((float)pos / rope_lin) * inv[i];
                 c[(size_t)pos * hd_ / 2 + i] = (float)std::cos((double)ang);
                 s[(size_t)pos * hd_ / 2 + i] = (float)std::sin((double)ang);
             }

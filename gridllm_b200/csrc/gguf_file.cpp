@@ -113,7 +113,10 @@ std::string GGUFFile::open(const std::string& path) {
         } else if (v.type == V_ARR) {
             v.arr_type = c.rd<uint32_t>();
             uint64_t n = c.rd<uint64_t>();
-            if (!c.ok || n > (1ull << 28)) return "corrupt GGUF array '" + key + "'";
+            // every element takes at least one byte of the file: an element count beyond what is left is damage, and is
+            // refused BEFORE any reserve() (2^28 strings would ask for 8 GB ahead of the first validated element)
+            const uint64_t left = (uint64_t)(c.end - c.p);
+            if (!c.ok || n > (1ull << 28) || n > left) return "corrupt GGUF array '" + key + "'";
             if (v.arr_type == V_STR) {
                 v.arr_s.reserve((size_t)n);
                 for (uint64_t j = 0; j < n && c.ok; ++j) v.arr_s.push_back(c.str());
@@ -137,7 +140,15 @@ std::string GGUFFile::open(const std::string& path) {
         uint32_t nd = c.rd<uint32_t>();
         if (!c.ok || nd > 4) return "corrupt GGUF tensor info";
         t.ne.resize(nd);
-        for (uint32_t d = 0; d < nd; ++d) t.ne[d] = (int64_t)c.rd<uint64_t>();
+        for (uint32_t d = 0; d < nd; ++d) {
+            t.ne[d] = (int64_t)c.rd<uint64_t>();
+            if (t.ne[d] < 0 || t.ne[d] > (int64_t)1 << 40) return "corrupt GGUF tensor info (dimension out of range)";
+        }
+        {   // element count must not overflow (4 dims of up to 2^40 each could)
+            unsigned __int128 prod = 1;
+            for (uint32_t d = 0; d < nd; ++d) prod *= (unsigned __int128)(uint64_t)t.ne[d];
+            if (prod > ((unsigned __int128)1 << 48)) return "corrupt GGUF tensor info (too many elements)";
+        }
         t.type = c.rd<uint32_t>();
         t.offset = c.rd<uint64_t>();
         if (!c.ok) return "truncated GGUF tensor info";
@@ -146,13 +157,18 @@ std::string GGUFFile::open(const std::string& path) {
     if (align == 0 || (align & (align - 1))) return "bad general.alignment";
     size_t data_off = (size_t)(c.p - (const uint8_t*)map_);
     data_off = (data_off + align - 1) / align * align;
+    if (data_off > map_len_) return "truncated GGUF (no tensor data section)";
+    const size_t data_len = map_len_ - data_off;
     for (size_t i = 0; i < tensors.size(); ++i) {
         auto& t = tensors[i];
         BlockGeom g = block_geom(t.type);
         if (g.weights) {
             if (t.cols() % g.weights) return "tensor '" + t.name + "': cols not a multiple of the block size";
             t.nbytes = row_bytes(t.type, t.cols()) * (size_t)t.rows();
-            if (data_off + t.offset + t.nbytes > map_len_) return "tensor '" + t.name + "' runs past end of file";
+            // overflow-free: offset and size are compared against what is left, never added to anything first
+            if (t.offset > data_len || t.nbytes > data_len - t.offset) return "tensor '" + t.name + "' runs past end of file";
+        } else if (t.offset > data_len) {
+            return "tensor '" + t.name + "' starts past end of file";
         }
         t.data = (const uint8_t*)map_ + data_off + t.offset;
         index_[t.name] = i;

@@ -160,6 +160,13 @@ bool Tokenizer::load(const GGUFFile& f) {
     const GGUFValue* toks = f.find("tokenizer.ggml.tokens");
     if (!toks || toks->arr_s.empty()) return false;
     if (f.get_s("tokenizer.ggml.model", "") != "gpt2") return false;
+    // Only the llama-bpe ("llama3") pre-tokeniser split is restated here.  Other byte-level BPE files that are also
+    // general.architecture == llama (tekken, smollm, deepseek-llm, ... -- each has its own split regex in llama.cpp [external])
+    // would tokenise silently wrong, so they load WITHOUT a tokenizer: text requests fail with a message, token-id requests work.
+    {
+        const std::string pre0 = f.get_s("tokenizer.ggml.pre", "");
+        if (pre0 != "llama-bpe" && pre0 != "llama3" && pre0 != "llama-v3") return false;
+    }
     tokens_ = toks->arr_s;
     const GGUFValue* ty = f.find("tokenizer.ggml.token_type");
     types_.assign(tokens_.size(), 1);

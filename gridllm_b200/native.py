@@ -200,8 +200,12 @@ class Engine:
         stops = np.ascontiguousarray(stop_ids, dtype=np.int32)
         so.n_stop_ids = len(stops)
         so.stop_ids = _i32p(stops) if len(stops) else None
-        ids = np.zeros(num_predict, dtype=np.int32)
-        lps = np.zeros(num_predict, dtype=np.float32)
+        # the library maps num_predict <= 0 to 128 (OllamaService.ts:105): size the output buffers from the same rule, never
+        # from the raw argument (a 0-length buffer would be written past its end)
+        n_out = num_predict if num_predict > 0 else 128
+        so.num_predict = n_out
+        ids = np.zeros(n_out, dtype=np.int32)
+        lps = np.zeros(n_out, dtype=np.float32)
         st = GenStats()
 
         def _cb(_user, tid, lp, piece, plen):

@@ -105,6 +105,7 @@ class NativeInferenceService:
         self._engine_kw = engine_kw
         self._engines: Dict[str, N.Engine] = {}
         self._lock = threading.Lock()          # one engine call at a time (one CUDA stream per engine)
+        self._load_lock = threading.Lock()     # model load: once, and never on the event-loop thread (see _engine_async)
         self.isConnected = False
         self.lastHealthCheck = datetime.now(timezone.utc)
 
@@ -112,9 +113,32 @@ class NativeInferenceService:
     def _engine(self, name: str) -> N.Engine:
         if name not in self._paths:
             raise RuntimeError(f"model '{name}' not found")
-        if name not in self._engines:
-            self._engines[name] = N.Engine(self._paths[name], device=self._device, max_ctx=self._max_ctx, **self._engine_kw)
-        return self._engines[name]
+        with self._load_lock:
+            if name not in self._engines:
+                self._engines[name] = N.Engine(self._paths[name], device=self._device, max_ctx=self._max_ctx, **self._engine_kw)
+            return self._engines[name]
+
+    async def _engine_async(self, name: str) -> N.Engine:
+        """The first request for a model loads it (mmap, host repack, H2D of several GB, graph capture): seconds during which
+        the event loop must keep firing heartbeats (the server drops a worker after WORKER_HEARTBEAT_TIMEOUT = 15 s,
+        server/src/config/index.ts:24) -- so the load runs on a worker thread, like every other engine call."""
+        if name in self._engines:
+            return self._engines[name]
+        return await asyncio.to_thread(self._engine, name)
+
+    def preload(self) -> None:
+        """load every configured model now (NativeWorker.start() calls this before registering)"""
+        for name in self._paths:
+            self._engine(name)
+
+    @staticmethod
+    def _num_predict(options: Dict[str, Any]) -> int:
+        """options.num_predict (OllamaService.ts:105: `options.num_predict || 128`).  The gateway also lets -1 / -2 through
+        (ollama.ts:47, Ollama's "until EOS / fill the context"): those become "as many as the context holds" in _run."""
+        v = options.get("num_predict")
+        if v is None or v == 0:
+            return 128
+        return int(v)
 
     def close(self):
         for e in self._engines.values():
@@ -211,13 +235,17 @@ class NativeInferenceService:
         # a generation that would run past the engine's context ends at it (done_reason "length") instead of failing; a prompt
         # that does not fit at all still fails (GL_ERR_CONTEXT)
         n_ctx = int(getattr(eng.info, "n_ctx", 0) or 0)
+        if num_predict <= 0:                             # -1 / -2: until EOS, bounded by the context
+            num_predict = max(1, n_ctx - len(ids)) if n_ctx > 0 else 128
         if n_ctx > 0 and len(ids) < n_ctx:
             num_predict = min(num_predict, n_ctx - len(ids))
         stops = options.get("stop")
         stops = [stops] if isinstance(stops, str) else list(stops or [])
         if not stops or not eng.info.has_tokenizer:
             with self._lock:
-                return eng, eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token, **kw)
+                gen = eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token, **kw)
+            gen.prompt_ids = ids
+            return eng, gen
         # stop strings: the token callback sees only released text, and cancels the native call when one completes
         filt = StopFilter(stops)
 
@@ -233,6 +261,7 @@ class NativeInferenceService:
             on_token(-1, 0.0, tail.encode("utf-8"))          # held-back text of a generation that ended by length / EOS
         gen.stop_text = filt.text
         gen.stopped = filt.hit
+        gen.prompt_ids = ids
         return eng, gen
 
     def _sampling(self, options: Dict[str, Any]) -> Dict[str, Any]:
@@ -272,7 +301,10 @@ class NativeInferenceService:
             "eval_count": int(st.eval_count),
             "eval_duration": int(st.eval_duration_ns),
             "system_fingerprint": "fp_gridllm_b200_native",
-            "context": [int(t) for t in gen.ids],                   # token ids: SURVEY.md section 8f.4 (optional field)
+            # Ollama's `context` is the WHOLE conversation so far -- prompt ids then reply ids -- and the gateway round-trips it
+            # (ollama.ts:143 returns it, :234 forwards it as metadata.context): a client that feeds it back continues from here
+            "context": [int(t) for t in getattr(gen, "prompt_ids", [])] + [int(t) for t in gen.ids],
+            "token_ids": [int(t) for t in gen.ids],                 # generated ids alone: SURVEY.md section 8f.4 (optional field)
             "logprobs": [float(x) for x in gen.logprobs],
         }
 
@@ -283,8 +315,8 @@ class NativeInferenceService:
     async def generateResponse(self, request: InferenceRequest) -> InferenceResponse:
         try:
             options = request.get("options") or {}
-            num_predict = options.get("num_predict") or 128              # OllamaService.ts:105
-            eng = self._engine(request["model"])
+            num_predict = self._num_predict(options)
+            eng = await self._engine_async(request["model"])
             ids = self._prompt_ids(eng, request, request.get("prompt"))
             eng, gen = await asyncio.to_thread(self._run, request["model"], ids, num_predict, options)
             return self._response(request, eng, gen, self._text(eng, gen.ids))
@@ -295,8 +327,8 @@ class NativeInferenceService:
     async def generateStreamResponse(self, request: InferenceRequest) -> AsyncGenerator[StreamResponse, None]:
         try:
             options = request.get("options") or {}
-            num_predict = options.get("num_predict") or 128
-            eng = self._engine(request["model"])
+            num_predict = self._num_predict(options)
+            eng = await self._engine_async(request["model"])
             ids = self._prompt_ids(eng, request, request.get("prompt"))
             q: "queue.Queue" = queue.Queue()
             cancel = threading.Event()
@@ -343,8 +375,8 @@ class NativeInferenceService:
             if not md.get("messages"):
                 raise RuntimeError("Chat request must include messages in metadata")
             options = request.get("options") or {}
-            num_predict = options.get("num_predict") or 128
-            eng = self._engine(request["model"])
+            num_predict = self._num_predict(options)
+            eng = await self._engine_async(request["model"])
             prompt = self._chat_prompt(eng, md["messages"])
             if md.get("prompt_token_ids") is not None:
                 ids = np.asarray(md["prompt_token_ids"], dtype=np.int32)
@@ -365,7 +397,7 @@ class NativeInferenceService:
             md = request.get("metadata") or {}
             if not md.get("messages"):
                 raise RuntimeError("Chat request must include messages in metadata")
-            eng = self._engine(request["model"])
+            eng = await self._engine_async(request["model"])
             sub = dict(request)
             if md.get("prompt_token_ids") is None:
                 if not eng.info.has_tokenizer:
@@ -384,7 +416,7 @@ class NativeInferenceService:
             md = request.get("metadata") or {}
             if not inp and md.get("input_token_ids") is None:
                 raise RuntimeError("Input is required for embedding requests")
-            eng = self._engine(request["model"])
+            eng = await self._engine_async(request["model"])
             if md.get("input_token_ids") is not None:
                 seqs = [np.asarray(s, dtype=np.int32) for s in md["input_token_ids"]]
             else:

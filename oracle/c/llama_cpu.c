@@ -130,10 +130,17 @@ void* oc_load(const char* path, int n_ctx) {
     uint64_t align = 32;
     m->eps = 1e-5f; m->rope_base = 10000.f;
     int n_ctx_train = 2048, rope_dim = 0;
+    char rope_scaling[32] = "";          /* rope.scaling.type: "", none, linear are restated; anything else refuses to load */
+    float rope_lin = 1.f;
     for (uint64_t i = 0; i < nkv && c.ok; ++i) {
         char key[256]; rd_str(&c, key, sizeof key);
         uint32_t t = (uint32_t)rd(&c, 4);
-        if (t == 8) { rd_str(&c, NULL, 0); continue; }
+        if (t == 8) {
+            const char* ks = strchr(key, '.'); ks = ks ? ks + 1 : key;
+            if (!strcmp(ks, "rope.scaling.type")) rd_str(&c, rope_scaling, sizeof rope_scaling);
+            else rd_str(&c, NULL, 0);
+            continue;
+        }
         if (t == 9) {
             uint32_t et = (uint32_t)rd(&c, 4); uint64_t n = rd(&c, 8);
             if (et == 8) { for (uint64_t j = 0; j < n && c.ok; ++j) rd_str(&c, NULL, 0); }
@@ -152,6 +159,7 @@ void* oc_load(const char* path, int n_ctx) {
         else if (!strcmp(k, "attention.layer_norm_rms_epsilon")) m->eps = (float)v;
         else if (!strcmp(k, "rope.freq_base")) m->rope_base = (float)v;
         else if (!strcmp(k, "rope.dimension_count")) rope_dim = (int)v;
+        else if (!strcmp(k, "rope.scaling.factor")) rope_lin = (float)v;
         else if (!strcmp(k, "context_length")) n_ctx_train = (int)v;
     }
     tinfo_t* ti = calloc(nt, sizeof(tinfo_t));
@@ -163,6 +171,8 @@ void* oc_load(const char* path, int n_ctx) {
         ti[i].off = rd(&c, 8);
     }
     if (!c.ok || !m->n_layer || !m->n_embd || !m->n_head) { free(ti); oc_free(m); return NULL; }
+    if (rope_scaling[0] && strcmp(rope_scaling, "none") && strcmp(rope_scaling, "linear")) { free(ti); oc_free(m); return NULL; }
+    if (strcmp(rope_scaling, "linear") || !(rope_lin > 0.f)) rope_lin = 1.f;
     if (!m->n_kv) m->n_kv = m->n_head;
     m->hd = rope_dim ? rope_dim : m->n_embd / m->n_head;
     m->n_ctx = n_ctx > 0 ? n_ctx : n_ctx_train;
@@ -176,6 +186,8 @@ void* oc_load(const char* path, int n_ctx) {
     const tinfo_t* on = find_t(ti, nt, "output_norm.weight");
     if (!on) bad = 1; else m->output_norm = (const float*)(base + on->off);
     m->n_vocab = m->tok_embd.rows;
+    const tinfo_t* rf = find_t(ti, nt, "rope_freqs.weight");      /* Llama-3.1+: per-pair frequency factors, F32[hd/2] */
+    const float* rope_ff = (rf && rf->type == T_F32) ? (const float*)(base + rf->off) : NULL;
     m->layers = calloc(m->n_layer, sizeof(layer_t));
     for (int il = 0; il < m->n_layer && !bad; ++il) {
         char nm[160];
@@ -199,7 +211,8 @@ void* oc_load(const char* path, int n_ctx) {
     for (int p = 0; p < m->n_ctx; ++p)
         for (int i = 0; i < m->hd / 2; ++i) {
             float inv = (float)pow((double)m->rope_base, -2.0 * i / m->hd);
-            float ang = (float)p * inv;
+            if (rope_ff) inv = inv / rope_ff[i];
+            float ang = ((float)p / rope_lin) * inv;
             m->cos_t[(size_t)p * m->hd / 2 + i] = (float)cos((double)ang);
             m->sin_t[(size_t)p * m->hd / 2 + i] = (float)sin((double)ang);
         }

@@ -277,6 +277,26 @@ LLAMA3_8B = LlamaShape("llama3-8b-synth", 32, 4096, 32, 8, 14336, 128256, 500000
 MISTRAL_7B = LlamaShape("mistral-7b-synth", 32, 4096, 32, 8, 14336, 32000, 10000.0, 1e-5, 8192)
 
 
+def llama3_rope_factors(head_dim: int, base: float, factor: float = 8.0, low_freq_factor: float = 1.0,
+                         high_freq_factor: float = 4.0, original_ctx: int = 8192) -> np.ndarray:
+    """rope_freqs.weight as the Llama-3.1 GGUF converter computes it from the checkpoint's rope_scaling block
+    ([external] convert_hf_to_gguf.py, rope_type "llama3"): 1 for short wavelengths, `factor` for long ones, a smooth
+    ramp between.  inv_freq_i / factor_i is what the model then rotates by."""
+    freqs = 1.0 / (base ** (np.arange(0, head_dim, 2, dtype=np.float64) / head_dim))
+    low_wl, high_wl = original_ctx / low_freq_factor, original_ctx / high_freq_factor
+    out = []
+    for f in freqs:
+        wl = 2 * np.pi / f
+        if wl < high_wl:
+            out.append(1.0)
+        elif wl > low_wl:
+            out.append(factor)
+        else:
+            smooth = (original_ctx / wl - low_freq_factor) / (high_freq_factor - low_freq_factor)
+            out.append(1.0 / ((1 - smooth) / factor + smooth))
+    return np.asarray(out, dtype=np.float32)
+
+
 def q4_k_m_uses_q6(i_layer: int, n_layer: int) -> bool:
     """llama.cpp q4_K_M 'use_more_bits' rule for attn_v / ffn_down ([external])."""
     return (i_layer < n_layer // 8 or i_layer >= 7 * n_layer // 8
@@ -361,13 +381,16 @@ def gpt2_byte_to_unicode() -> Dict[int, str]:
 
 def build_model(path: str, shape: LlamaShape, recipe: str = "q4_k_m", seed: int = 1234,
                 mode: str = "quantize", gain: float = 1.0, with_vocab: bool = True,
-                arch: str = "llama") -> Dict[str, object]:
+                arch: str = "llama", rope_freqs: Optional[np.ndarray] = None,
+                rope_scaling: Optional[Tuple[str, float]] = None, pre: str = "llama-bpe") -> Dict[str, object]:
     """Write a synthetic Llama-architecture GGUF.
 
     mode="quantize": fp32 master weights N(0, gain^2/fan_in) (embedding N(0,1), norm weights
                      1 + 0.1 N(0,1)) quantised with the valid-block quantisers above.  Use for
                      small models whose logits must be non-degenerate.
     mode="random":   raw random well-formed blocks (fast; for Llama-3-8B shaped benches).
+    rope_freqs:   per-pair frequency factors written as rope_freqs.weight F32[head_dim/2] (what the Llama-3.1 converter emits).
+    rope_scaling: (type, factor) -> {arch}.rope.scaling.type / .factor.   pre: tokenizer.ggml.pre.
     Returns {"bytes": file size, "n_params": ..., "weights_bytes": matrix payload}.
     """
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -388,10 +411,13 @@ def build_model(path: str, shape: LlamaShape, recipe: str = "q4_k_m", seed: int 
     g.add_f32(f"{arch}.rope.freq_base", shape.rope_base)
     g.add_u32(f"{arch}.rope.dimension_count", shape.head_dim)
     g.add_u32(f"{arch}.vocab_size", shape.n_vocab)
+    if rope_scaling is not None:
+        g.add_str(f"{arch}.rope.scaling.type", rope_scaling[0])
+        g.add_f32(f"{arch}.rope.scaling.factor", rope_scaling[1])
     if with_vocab:
         toks, merges, types = synth_vocab(shape.n_vocab)
         g.add_str("tokenizer.ggml.model", "gpt2")
-        g.add_str("tokenizer.ggml.pre", "llama-bpe")
+        g.add_str("tokenizer.ggml.pre", pre)
         g.add_arr("tokenizer.ggml.tokens", _STR, toks)
         g.add_arr("tokenizer.ggml.token_type", _I32, types)
         g.add_arr("tokenizer.ggml.merges", _STR, merges)
@@ -403,6 +429,10 @@ def build_model(path: str, shape: LlamaShape, recipe: str = "q4_k_m", seed: int 
                   "{% for m in messages %}<|{{ m.role }}|>\n{{ m.content }}<|eot_id|>{% endfor %}<|assistant|>\n")
     n_params = 0
     wbytes = 0
+    if rope_freqs is not None:
+        ff = np.ascontiguousarray(rope_freqs, dtype=np.float32).reshape(-1)
+        assert ff.size == shape.head_dim // 2
+        g.add_tensor("rope_freqs.weight", F32, (ff.size,), ff)
     for name, t, (rows, cols) in tensor_plan(shape, recipe):
         n_params += rows * cols
         if name.endswith("_norm.weight"):

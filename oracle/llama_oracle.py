@@ -115,6 +115,10 @@ def load_gguf(path: str) -> OracleModel:
         n_ctx=int(field(f"{arch}.context_length", 2048)),
         raw=raw, meta=meta, _cache={},
     )
+    st = field(f"{arch}.rope.scaling.type", "") or ""
+    if st not in ("", "none", "linear"):
+        raise ValueError(f"rope.scaling.type {st!r} is not restated (none / linear only)")
+    m.rope_linear = float(field(f"{arch}.rope.scaling.factor", 1.0)) if st == "linear" else 1.0
     m.meta["reader"] = r
     return m
 
@@ -185,13 +189,17 @@ def rmsnorm(x: np.ndarray, w: np.ndarray, eps: float) -> np.ndarray:
     return x / np.sqrt(np.mean(x * x, axis=-1, keepdims=True) + eps) * w.astype(np.float64)
 
 
-def rope_table(n_pos: int, n_rot: int, base: float) -> Tuple[np.ndarray, np.ndarray]:
+def rope_table(n_pos: int, n_rot: int, base: float, freq_factors: Optional[np.ndarray] = None,
+               linear_factor: float = 1.0) -> Tuple[np.ndarray, np.ndarray]:
     """cos/sin [n_pos, n_rot/2] as fp32.  inv_freq_i = base^(-2i/n_rot) rounded to fp32, the
     angle pos*inv_freq_i is formed in fp32, cos/sin evaluated in float64 and rounded to fp32.
     (ggml 'NORM' rope, adjacent pairs (x[2i], x[2i+1]); [external] llama.cpp ggml_rope.)"""
     i = np.arange(n_rot // 2, dtype=np.float64)
     inv = (base ** (-2.0 * i / n_rot)).astype(np.float32)
-    ang = (np.arange(n_pos, dtype=np.float32)[:, None] * inv[None, :]).astype(np.float32)
+    if freq_factors is not None:          # Llama-3.1+ rope_freqs.weight: theta_i / factor_i ([external] llama.cpp rope with freq_factors)
+        inv = (inv / np.asarray(freq_factors, dtype=np.float32)).astype(np.float32)
+    p = (np.arange(n_pos, dtype=np.float32) / np.float32(linear_factor)).astype(np.float32)      # rope.scaling.type == linear
+    ang = (p[:, None] * inv[None, :]).astype(np.float32)
     return np.cos(ang.astype(np.float64)).astype(np.float32), np.sin(ang.astype(np.float64)).astype(np.float32)
 
 
@@ -217,7 +225,8 @@ class LlamaOracle:
         self.m = model
         self.act = act
         self.kv_f16 = kv_f16
-        self.cos, self.sin = rope_table(model.n_ctx, model.head_dim, model.rope_base)
+        ff = model.w("rope_freqs.weight").reshape(-1) if model.has("rope_freqs.weight") else None
+        self.cos, self.sin = rope_table(model.n_ctx, model.head_dim, model.rope_base, ff, getattr(model, "rope_linear", 1.0))
         self.reset()
 
     def reset(self):

@@ -39,7 +39,7 @@ def test_generate_text_prompt_roundtrip(svc):
     ids = eng.tokenize(req["prompt"])
     assert eng.detokenize(ids[1:]) == req["prompt"]                 # byte-level BPE round trip (id 0 is BOS)
     g = eng.generate(ids, num_predict=6, ignore_eos=True)
-    assert res["context"] == [int(t) for t in g.ids]                # service == direct C-ABI call
+    assert res["token_ids"] == [int(t) for t in g.ids]                # service == direct C-ABI call
     assert res["response"] == eng.detokenize(g.ids)
     # default generation length when num_predict is absent: OllamaService.ts:105 -> 128
     res2 = _run(svc.generateResponse({"id": "r2", "model": "tiny:latest", "prompt": "hi", "options": {"ignore_eos": True}, "priority": "low"}))
@@ -112,7 +112,7 @@ def test_workers_shard_requests_like_the_scheduler(tiny_gguf):
     for i in range(6):
         ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=20)
         g = ref.generate(ids, num_predict=5, ignore_eos=True)
-        assert sched.results[f"job-{i}"]["result"]["context"] == [int(t) for t in g.ids]
+        assert sched.results[f"job-{i}"]["result"]["token_ids"] == [int(t) for t in g.ids]
     ref.close()
     for s in svcs:
         s.close()

@@ -22,20 +22,37 @@ def _unpermute(w, n_head):
     return w.reshape(n_head, hd // 2, 2, cols).swapaxes(1, 2).reshape(rows, cols)
 
 
-@pytest.mark.parametrize("shape_name", ["TINY", "TINY128"])
-def test_forward_matches_transformers(tmp_models, shape_name):
+@pytest.mark.parametrize("shape_name,rope", [("TINY", None), ("TINY128", None), ("TINY128", "llama3"), ("TINY", "linear")])
+def test_forward_matches_transformers(tmp_models, shape_name, rope):
+    """rope None: plain RoPE.  "llama3": rope_freqs.weight (Llama-3.1 / 3.2 frequency factors) against transformers'
+    rope_type llama3 built from the same parameters.  "linear": {arch}.rope.scaling.type linear against rope_type linear."""
     torch = pytest.importorskip("torch")
     tr = pytest.importorskip("transformers")
     from oracle import gguf_synth as S, llama_oracle as O
     shape = getattr(S, shape_name)
-    path = str(tmp_models / f"pin_{shape_name}_f32.gguf")
-    S.build_model(path, shape, "f32", seed=2024)
+    path = str(tmp_models / f"pin_{shape_name}_{rope}_f32.gguf")
+    kw, rope_cfg = {}, None
+    if rope == "llama3":
+        # original context 64 so that the 19 test positions see all three regimes of the factor ramp
+        kw["rope_freqs"] = S.llama3_rope_factors(shape.head_dim, shape.rope_base, 8.0, 1.0, 4.0, 64)
+        assert len(set(kw["rope_freqs"].tolist())) > 2
+        rope_cfg = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                    "original_max_position_embeddings": 64, "rope_theta": shape.rope_base}
+    elif rope == "linear":
+        kw["rope_scaling"] = ("linear", 4.0)
+        rope_cfg = {"rope_type": "linear", "factor": 4.0, "rope_theta": shape.rope_base}
+    S.build_model(path, shape, "f32", seed=2024, **kw)
     m = O.load_gguf(path)
     cfg = tr.LlamaConfig(vocab_size=shape.n_vocab, hidden_size=shape.n_embd, intermediate_size=shape.n_ff,
                          num_hidden_layers=shape.n_layer, num_attention_heads=shape.n_head,
                          num_key_value_heads=shape.n_head_kv, head_dim=shape.head_dim, rms_norm_eps=shape.rms_eps,
                          rope_theta=shape.rope_base, max_position_embeddings=shape.n_ctx, tie_word_embeddings=False,
                          attention_bias=False, mlp_bias=False, hidden_act="silu")
+    if rope_cfg is not None:
+        try:
+            cfg = tr.LlamaConfig(**{**cfg.to_dict(), "rope_scaling": rope_cfg, "rope_parameters": rope_cfg})
+        except Exception:
+            cfg.rope_scaling = rope_cfg
     try:
         cfg._attn_implementation = "eager"
     except Exception:

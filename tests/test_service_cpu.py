@@ -41,7 +41,7 @@ def test_generate_matches_the_oracle_and_streams_the_same_text(svc):
     ids = eng.tokenize(req["prompt"])
     assert res["prompt_eval_count"] == len(ids) and eng.detokenize(ids[1:]) == req["prompt"]
     ref = O.LlamaOracle(eng.m, act="i16", kv_f16=True).generate(ids, 6)
-    assert res["context"] == [int(t) for t in ref["ids"]]                  # the service hands the oracle's greedy ids through
+    assert res["token_ids"] == [int(t) for t in ref["ids"]]                  # the service hands the oracle's greedy ids through
     assert res["response"] == eng.detokenize(ref["ids"])
 
     async def collect():
@@ -130,7 +130,7 @@ def test_workers_shard_requests_like_the_scheduler(tiny_gguf, hostcheck_lib, mon
     for i in range(6):
         ids = np.random.Generator(np.random.PCG64(1000 + i)).integers(0, 500, size=12)
         ref = O.LlamaOracle(m, act="i16", kv_f16=True).generate(ids, 4)
-        assert sched.results[f"job-{i}"]["result"]["context"] == [int(t) for t in ref["ids"]]
+        assert sched.results[f"job-{i}"]["result"]["token_ids"] == [int(t) for t in ref["ids"]]
 
 
 def test_chat_framing_follows_the_template_family(svc):
@@ -302,6 +302,31 @@ def test_worker_can_hold_more_than_one_job(tiny_gguf, hostcheck_lib, monkeypatch
     m = O.load_gguf(tiny_gguf)
     for jid in ("j0", "j1"):
         ref = O.LlamaOracle(m, act="i16", kv_f16=True).generate(prompts[jid], 20)
-        assert done[jid]["result"]["context"] == [int(t) for t in ref["ids"]]
+        assert done[jid]["result"]["token_ids"] == [int(t) for t in ref["ids"]]
     assert max(json.loads(m)["currentJobs"] for c, m in bus.log if c == "worker:heartbeat") == 2
     assert w.currentJobs == 0 and w.isProcessingJob is False
+
+
+def test_context_round_trip_continues_the_whole_conversation(svc):
+    """Ollama's `context` is the conversation so far; the gateway returns it (ollama.ts:143) and forwards it back
+    (ollama.ts:234 -> metadata.context): the second turn must run on prompt1 + reply1 + prompt2, BOS included once."""
+    eng = svc._engine("tiny:latest")
+    r1 = _run(svc.generateResponse({"id": "c1", "model": "tiny:latest", "prompt": "hello world", "options": {"num_predict": 4, "ignore_eos": True},
+                                    "priority": "medium"}))
+    p1 = [int(t) for t in eng.tokenize("hello world")]
+    assert r1["context"] == p1 + r1["token_ids"] and len(r1["token_ids"]) == 4
+    n_calls = len(eng.calls)
+    r2 = _run(svc.generateResponse({"id": "c2", "model": "tiny:latest", "prompt": " the rain", "options": {"num_predict": 3, "ignore_eos": True},
+                                    "priority": "medium", "metadata": {"context": r1["context"]}}))
+    p2 = [int(t) for t in eng.tokenize(" the rain", add_bos=False, parse_special=False)]
+    assert eng.calls[n_calls]["n_prompt"] == len(p1) + 4 + len(p2)
+    assert r2["context"] == r1["context"] + p2 + r2["token_ids"] and r2["prompt_eval_count"] == len(r1["context"]) + len(p2)
+
+
+def test_num_predict_minus_one_runs_until_the_context_is_full(svc):
+    """the gateway lets num_predict -1 through (ollama.ts:47, Ollama's 'until EOS'): it must not fail, and ends at the context"""
+    eng = svc._engine("tiny:latest")
+    ids = eng.tokenize("hi")
+    res = _run(svc.generateResponse({"id": "n1", "model": "tiny:latest", "prompt": "hi", "options": {"num_predict": -1, "ignore_eos": True},
+                                     "priority": "low"}))
+    assert res["eval_count"] == eng.info.n_ctx - len(ids) and res["done_reason"] == "length"

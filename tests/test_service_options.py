@@ -110,6 +110,7 @@ def _service_with_fake():
     s._paths = {"m": "unused"}
     s._engines = {"m": _FakeEngine()}
     s._lock = threading.Lock()
+    s._load_lock = threading.Lock()
     return s
 
 
