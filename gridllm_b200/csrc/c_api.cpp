@@ -125,6 +125,42 @@ int gl_embed(gl_engine* e, const int32_t* ids, const int32_t* seq_offsets, int32
     return ret(e->impl->embed(ids, seq_offsets, n_seq, out, stats));
 }
 
+// ---- continuous batching -------------------------------------------------------------------------
+int gl_seq_open(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_sample_opts* opts, int32_t* slot) {
+    if (!e || !prompt || !slot) return bad("gl_seq_open: null argument");
+    gl_sample_opts so{};
+    if (opts) so = *opts;
+    else { so.num_predict = 128; so.top_p = 1.f; }
+    int s = -1;
+    const int rc = ret(e->impl->seq_open(prompt, n_prompt, so, &s));
+    if (rc == GL_OK) *slot = s;
+    return rc;
+}
+
+int gl_batch_step(gl_engine* e, int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int32_t cap, int32_t* n) {
+    if (!e || !n) return bad("gl_batch_step: null argument");
+    int k = 0;
+    const int rc = ret(e->impl->batch_step(slots, ids, logprobs, done, cap, &k));
+    *n = k;
+    return rc;
+}
+
+int gl_seq_close(gl_engine* e, int32_t slot) {
+    if (!e) return bad("gl_seq_close: null engine");
+    return ret(e->impl->seq_close(slot));
+}
+
+int gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab) {
+    if (!e || !out) return bad("gl_seq_logits: null argument");
+    return ret(e->impl->seq_logits(slot, out, n_vocab));
+}
+
+int gl_time_batch_step(gl_engine* e, int32_t batch, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step,
+                       uint64_t* weight_bytes) {
+    if (!e) return bad("gl_time_batch_step: null engine");
+    return ret(e->impl->time_batch_step(batch, ctx_len, iters, ms_per_step, launches_per_step, weight_bytes));
+}
+
 int gl_last_logits(gl_engine* e, int32_t step, float* out, int32_t n_vocab) {
     if (!e || !out) return bad("gl_last_logits: null argument");
     return ret(e->impl->last_logits(step, out, n_vocab));

@@ -81,6 +81,8 @@ Engine::~Engine() {
     for (auto& v : g_head_var_)
         for (auto& g : v)
             if (g) cudaGraphExecDestroy(g);
+    for (auto& g : g_batch_)
+        if (g) cudaGraphExecDestroy(g);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     for (void* p : allocs_) cudaFree(p);
     for (void* p : pf_allocs_) cudaFree(p);
@@ -294,7 +296,22 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(dalloc((void**)&sample_scratch_, (size_t)SAMPLE_SCRATCH_FLOATS * 4));
     CU(dalloc((void**)&topk_scratch_, TOPK_SCRATCH_BYTES));
     n_pages_ = n_ctx_ / KV_PAGE_TOKENS;
-    kv_layer_elems_ = (size_t)n_pages_ * n_kv_ * KV_PAGE_TOKENS * hd_;
+    // the page pool is shared by every open sequence (gl_generate's one sequence and the gl_seq_open slots)
+    max_batch_ = std::max(0, std::min(MAX_BATCH, env_int("GL_MAX_BATCH", opts ? opts->max_batch : 0)));
+    if (max_batch_ == 1) max_batch_ = 0;
+    batch_weights_ = env_int("GL_BATCH_WEIGHTS", opts ? opts->batch_weights : 0);
+    {
+        long long pool_tokens = (opts && opts->kv_pool_tokens > 0) ? opts->kv_pool_tokens : (long long)n_ctx_ * std::max(1, max_batch_);
+        pool_tokens = std::max<long long>(pool_tokens, n_ctx_);
+        // never more than 60 % of what is free right now (the 16-bit prefill copy and the scratch come after this)
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_token = (size_t)2 * n_layer_ * n_kv_ * hd_ * sizeof(__half);
+        const long long cap_tokens = (long long)(free_b * 6 / 10 / per_token);
+        if (pool_tokens > cap_tokens) pool_tokens = std::max<long long>(cap_tokens, n_ctx_);
+        pool_pages_ = (int)((pool_tokens + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS);
+    }
+    kv_layer_elems_ = (size_t)pool_pages_ * n_kv_ * KV_PAGE_TOKENS * hd_;
     CU(dalloc((void**)&kcache_, kv_layer_elems_ * n_layer_ * sizeof(__half)));
     CU(dalloc((void**)&vcache_, kv_layer_elems_ * n_layer_ * sizeof(__half)));
     CU(dalloc((void**)&page_table_, (size_t)n_pages_ * 4));
@@ -304,8 +321,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(dalloc((void**)&out_ids_, (size_t)max_out_ * 4));
     CU(dalloc((void**)&out_lp_, (size_t)max_out_ * 4));
     // physical pages are handed out in reverse order so that the page table is a real indirection
-    free_pages_.resize(n_pages_);
-    for (int i = 0; i < n_pages_; ++i) free_pages_[i] = i;
+    free_pages_.resize(pool_pages_);
+    for (int i = 0; i < pool_pages_; ++i) free_pages_[i] = i;
 
     // RoPE tables (oracle/llama_oracle.py rope_table): inv_freq rounded to fp32, angle formed in fp32,
     // cos/sin evaluated in double, rounded to fp32.

@@ -13,6 +13,7 @@
 #include "gguf_file.h"
 #include "kernels.h"
 #include "prefill.h"
+#include "batch.h"
 #include "decode_mega.h"
 #include "tokenizer.h"
 
@@ -55,6 +56,12 @@ public:
                     int32_t* out_ids, float* out_lp, gl_gen_stats* stats);
     Status embed(const int32_t* ids, const int32_t* offs, int n_seq, float* out, gl_gen_stats* stats);
     Status last_logits(int step, float* out, int n_vocab);
+    // continuous batching (engine_batch.cu): B open sequences share one decode step
+    Status seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, int* slot);
+    Status batch_step(int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int cap, int* n);
+    Status seq_close(int slot);
+    Status seq_logits(int slot, float* out, int n_vocab);
+    Status time_batch_step(int batch, int ctx_len, int iters, float* ms, int* launches, uint64_t* wbytes);
     Status sample_logits(const float* logits, int n_vocab, const gl_sample_opts& so, int out_index, int* id, float* logprob);
     Status gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms);
     Status gemv_tensor(const std::string& name, const float* x, float* y, int iters, int flush, float* ms, uint64_t* wbytes);
@@ -150,7 +157,8 @@ private:
     unsigned long long* topk_scratch_ = nullptr;
     __half *kcache_ = nullptr, *vcache_ = nullptr;    // [layer][page][kv][16][hd]
     size_t kv_layer_elems_ = 0;
-    int n_pages_ = 0;
+    int n_pages_ = 0;                                // entries of ONE sequence's page table (n_ctx / 16)
+    int pool_pages_ = 0;                             // physical pages of the pool all sequences share
     int* page_table_ = nullptr;                      // device
     std::vector<int> free_pages_;
     std::vector<int> seq_pages_;
@@ -164,6 +172,38 @@ private:
     size_t flush_elems_ = 0;
     int max_out_ = 0;
     int host_pos_ = 0;
+
+    // ---- continuous batching (engine_batch.cu) ----
+    struct SeqSlot {
+        bool open = false, done = false, first_pending = false;
+        std::vector<int> pages;
+        int n_prompt = 0, n_pred = 0, produced = 0, sampler = 0;
+        int32_t last_token = 0;
+        float first_lp = 0.f;
+        int last_row = -1;                            // row of the last batched step this sequence took part in
+    };
+    static constexpr int N_BUCKETS = 5;               // batch-size buckets of the captured step: 8, 16, 32, 64, 128 rows
+    int max_batch_ = 0;                               // gl_engine_opts.max_batch (0: batching off)
+    int batch_weights_ = 0;                           // 1: resident 16-bit copy, 2: quantised weights (engine_batch.cu picks for 0)
+    std::vector<SeqSlot> slots_;
+    std::vector<int> last_rows_;                      // composition the device-resident BatchCtl currently describes
+    int last_bucket_ = 0;
+    BatchCtl* bctl_ = nullptr;
+    StepState* bst_ = nullptr;                        // [MAX_BATCH]
+    int* btables_ = nullptr;                          // [MAX_BATCH][n_pages_]
+    int *bids_ = nullptr, *bout_ids_ = nullptr;
+    float *bx_ = nullptr, *bqkv_ = nullptr, *bq_ = nullptr, *blogits_ = nullptr, *bout_lp_ = nullptr, *bpart_o_ = nullptr, *bpart_ml_ = nullptr;
+    __half *bxn16_ = nullptr, *battn16_ = nullptr, *bh16_ = nullptr;
+    unsigned* bcounters_ = nullptr;
+    BatchOut* bout_ = nullptr;
+    void* head16_ = nullptr;                          // [n_vocab x n_embd] fp16 copy of the lm_head (16-bit batched path)
+    cudaGraphExec_t g_batch_[N_BUCKETS] = {};
+    int batch_launches_ = 0;                          // kernels of one batched step
+    Status ensure_batch_state();
+    Status enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch);
+    Status run_batch_graph(int bucket);
+    static int bucket_of(int rows) { int b = 8; while (b < rows) b <<= 1; return b; }
+    static int bucket_index(int bucket) { int i = 0; while ((8 << i) < bucket) ++i; return i; }
 
     cudaGraphExec_t g_nohead_ = nullptr;
     cudaGraphExec_t g_head_var_[3][2] = {};   // [sampler of the running request][logits kept]

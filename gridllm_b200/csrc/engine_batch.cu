@@ -1,0 +1,367 @@
+// Engine: continuous batching (include/gridllm_native.h gl_seq_open / gl_batch_step / gl_seq_close).
+//
+// The reference worker holds one job at a time (/root/reference/client/src/services/WorkerClientService.ts:500-505;
+// MAX_CONCURRENT_JOBS_PER_WORKER, server/src/config/index.ts:31).  With that limit raised, every job the worker holds is an
+// open SEQUENCE here: its own KV pages out of the shared pool, its own device-resident StepState (position, last token,
+// sampling options), its own page-table row.  One batched decode step then serves all of them:
+//     gather tokens -> embedding rows -> per layer { RMSNorm rows -> QKV GEMM -> RoPE + KV append per row -> paged attention per
+//     row -> O GEMM (+residual) -> RMSNorm rows -> gate/up GEMM (SiLU*mul) -> down GEMM (+residual) } -> final norm -> lm_head
+//     GEMM -> sampler per row -> collect
+// The GEMMs are tensor-core GEMMs with M = rows of the step: the weights are read ONCE per step for all sequences.  The step
+// is captured as a CUDA graph per batch-size bucket (8 / 16 / 32 / 64 / 128 rows); which sequences form the rows is device
+// state (BatchCtl), so joining and leaving costs one small copy, not a re-capture.
+// A sequence's arithmetic never looks at another row: its tokens do not depend on who shares the batch.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace gl {
+
+namespace {
+Status failb(int code, const std::string& m) { return Status{code, m}; }
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) return failb(GL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+#define ST(expr)                 \
+    do {                         \
+        Status _s = (expr);      \
+        if (!_s.ok()) return _s; \
+    } while (0)
+
+int attn_splits_for(int bucket, int n_kv) {
+    // enough CTAs to fill the machine a few times over; every split costs a partial + a merge, so no more than that
+    int s = 1;
+    while (s < 16 && n_kv * bucket * s < 512) s <<= 1;
+    return s;
+}
+}  // namespace
+
+Status Engine::ensure_batch_state() {
+    if (bst_) return {};
+    if (max_batch_ < 2) return failb(GL_ERR_UNSUPPORTED, "continuous batching is off: create the engine with gl_engine_opts.max_batch >= 2");
+    if (!have_w16_) return failb(GL_ERR_UNSUPPORTED, "continuous batching needs the resident 16-bit weights (not enough HBM at load, or prefill_mode 1)");
+    if (n_ff_ % 8) return failb(GL_ERR_UNSUPPORTED, "continuous batching: n_ff must be a multiple of 8");
+    const int qd = n_head_ * hd_, kvd = n_kv_ * hd_, ldq = qd + 2 * kvd;
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) { allocs_.push_back(*p); e = cudaMemsetAsync(*p, 0, bytes, stream_); }
+        return e;
+    };
+    const size_t R = MAX_BATCH;
+    CU(dalloc((void**)&bctl_, sizeof(BatchCtl)));
+    CU(dalloc((void**)&btables_, R * n_pages_ * 4));
+    CU(dalloc((void**)&bids_, R * 4));
+    CU(dalloc((void**)&bout_ids_, R * max_out_ * 4));
+    CU(dalloc((void**)&bout_lp_, R * max_out_ * 4));
+    CU(dalloc((void**)&bout_, R * sizeof(BatchOut)));
+    CU(dalloc((void**)&bx_, R * n_embd_ * 4));
+    CU(dalloc((void**)&bxn16_, R * n_embd_ * 2));
+    CU(dalloc((void**)&bqkv_, R * ldq * 4));
+    CU(dalloc((void**)&bq_, R * qd * 4));
+    CU(dalloc((void**)&battn16_, R * qd * 2));
+    CU(dalloc((void**)&bh16_, R * n_ff_ * 2));
+    CU(dalloc((void**)&blogits_, R * n_vocab_ * 4));
+    CU(dalloc((void**)&bpart_o_, R * n_head_ * 16 * hd_ * 4));
+    CU(dalloc((void**)&bpart_ml_, R * n_head_ * 16 * 2 * 4));
+    CU(dalloc((void**)&bcounters_, R * n_kv_ * 4));
+    // the lm_head as a 16-bit matrix (the layer matrices already have their copy: build_prefill_weights)
+    CU(dalloc(&head16_, (size_t)n_vocab_ * n_embd_ * 2));
+    CU(dequant_rows_launch(output_.w, output_.type, output_.rows, output_.cols, output_.row_stride, output_.tile_rows, head16_, n_embd_, 0, 0, false,
+                           stream_));
+    CU(dalloc((void**)&bst_, sizeof(StepState) * R));        // last: bst_ != null means "state is complete"
+    CU(cudaStreamSynchronize(stream_));
+    slots_.assign(MAX_BATCH, SeqSlot{});
+    last_rows_.clear();
+    last_bucket_ = 0;
+    return {};
+}
+
+// Prefill a prompt into a free slot's own pages and draw its first token.  The single-sequence code runs unchanged on the
+// slot's state: the members it reads (page table, step state, output buffers) point at the slot's rows for the duration.
+Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, int* slot_out) {
+    CU(cudaSetDevice(device_));
+    if (!prompt || n_prompt <= 0 || !slot_out) return failb(GL_ERR_INVALID, "seq_open: empty prompt");
+    for (int i = 0; i < n_prompt; ++i)
+        if (prompt[i] < 0 || prompt[i] >= n_vocab_) return failb(GL_ERR_INVALID, "prompt token id out of range");
+    if (!(so.temperature >= 0.f) || !std::isfinite(so.temperature)) return failb(GL_ERR_INVALID, "temperature must be a finite number >= 0");
+    ST(ensure_batch_state());
+    const int n_pred = so.num_predict > 0 ? so.num_predict : 128;
+    if (n_prompt + n_pred > n_ctx_) return failb(GL_ERR_CONTEXT, "prompt + num_predict exceeds the engine context");
+    int slot = -1;
+    for (int i = 0; i < max_batch_; ++i)
+        if (!slots_[i].open) { slot = i; break; }
+    if (slot < 0) return failb(GL_ERR_NOMEM, "no free sequence slot (max_batch " + std::to_string(max_batch_) + ")");
+    const int need = (n_prompt + n_pred + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;      // reserved up front: a step can never run out
+    if ((int)free_pages_.size() < need) return failb(GL_ERR_NOMEM, "KV page pool exhausted");
+    SeqSlot& S = slots_[slot];
+    S = SeqSlot{};
+    for (int i = 0; i < need; ++i) { S.pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
+    int* table = btables_ + (size_t)slot * n_pages_;
+    CU(cudaMemcpyAsync(table, S.pages.data(), S.pages.size() * 4, cudaMemcpyHostToDevice, stream_));
+
+    struct Saved { int* pt; StepState* st; int* oi; float* ol; int hp; } sv{page_table_, st_, out_ids_, out_lp_, host_pos_};
+    page_table_ = table; st_ = bst_ + slot; out_ids_ = bout_ids_ + (size_t)slot * max_out_; out_lp_ = bout_lp_ + (size_t)slot * max_out_; host_pos_ = 0;
+    Status rs;
+    do {
+        int dummy = 0;
+        cudaError_t ce = cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_);
+        if (ce != cudaSuccess) { rs = failb(GL_ERR_CUDA, cudaGetErrorString(ce)); break; }
+        if (can_batch_prefill(n_prompt)) {
+            rs = set_state(n_prompt - 1, prompt[n_prompt - 1], n_prompt, 0, &so);
+            if (rs.ok()) rs = prefill_batched(n_prompt, &dummy);
+            if (rs.ok()) rs = enqueue_head(stream_, false, &dummy);
+        } else {      // short prompts: plain launches of the decode step (the captured graphs hold the engine's own pointers)
+            rs = set_state(0, prompt[0], n_prompt, 0, &so);
+            for (int i = 0; rs.ok() && i < n_prompt; ++i) rs = enqueue_step(stream_, i == n_prompt - 1, false, &dummy);
+        }
+        if (!rs.ok()) break;
+        StepState hs{};
+        float lp = 0.f;
+        ce = cudaMemcpyAsync(&hs, st_, sizeof(hs), cudaMemcpyDeviceToHost, stream_);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(&lp, out_lp_, 4, cudaMemcpyDeviceToHost, stream_);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream_);
+        if (ce != cudaSuccess) { rs = failb(GL_ERR_CUDA, cudaGetErrorString(ce)); break; }
+        S.last_token = hs.token;
+        S.first_lp = lp;
+        S.done = hs.done != 0;
+    } while (false);
+    const int sampler = sampler_;
+    page_table_ = sv.pt; st_ = sv.st; out_ids_ = sv.oi; out_lp_ = sv.ol; host_pos_ = sv.hp;
+    if (!rs.ok()) {
+        for (int p : S.pages) free_pages_.push_back(p);
+        S = SeqSlot{};
+        return rs;
+    }
+    S.open = true;
+    S.n_prompt = n_prompt; S.n_pred = n_pred; S.produced = 0; S.sampler = sampler; S.first_pending = true;
+    *slot_out = slot;
+    return {};
+}
+
+Status Engine::seq_close(int slot) {
+    if (slot < 0 || slot >= (int)slots_.size() || !slots_[slot].open) return failb(GL_ERR_INVALID, "seq_close: no such open sequence");
+    for (int p : slots_[slot].pages) free_pages_.push_back(p);
+    slots_[slot] = SeqSlot{};
+    return {};
+}
+
+Status Engine::seq_logits(int slot, float* out, int n_vocab) {
+    CU(cudaSetDevice(device_));
+    if (slot < 0 || slot >= (int)slots_.size() || !slots_[slot].open || n_vocab != n_vocab_ || !out) return failb(GL_ERR_INVALID, "seq_logits: bad argument");
+    const SeqSlot& S = slots_[slot];
+    // the first token is drawn from the single-sequence logits buffer at gl_seq_open; later ones from the step's row
+    const float* src = S.last_row < 0 ? logits_ : blogits_ + (size_t)S.last_row * n_vocab_;
+    CU(cudaMemcpy(out, src, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost));
+    return {};
+}
+
+// every launch of one batched step, for `bucket` rows; all pointers are fixed, the composition is read from bctl_ / bst_
+Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
+    const int qd = n_head_ * hd_, kvd = n_kv_ * hd_, ldq = qd + 2 * kvd;
+    const float scale = 1.0f / std::sqrt((float)hd_);
+    int nl = 0;
+    auto linear = [&](const void* a, const void* w, void* c, int n, int k, int ldc, int epi) -> cudaError_t {
+        GemmParams g{};
+        g.a = a; g.b = w; g.c = c; g.m = bucket; g.n = n; g.k = k; g.lda = k; g.ldb = k; g.ldc = ldc;
+        g.batch = 1; g.b_batch_div = 1; g.epi = epi;
+        ++nl;
+        return gemm_tc5_supported(g) ? gemm_tc5_launch(g, MAX_BATCH, false, s) : gemm_tn_launch(g, false, s);
+    };
+    CU(batch_gather_tokens_launch(bctl_, bst_, bids_, bucket, s)); ++nl;
+    CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, bids_, bucket, bx_, s)); ++nl;
+    const int splits = attn_splits_for(bucket, n_kv_);
+    for (int il = 0; il < n_layer_; ++il) {
+        const LayerWeights& L = layers_[il];
+        __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
+        __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
+        CU(batch_rmsnorm_launch(bx_, L.attn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
+        CU(linear(bxn16_, L.wqkv16, bqkv_, ldq, n_embd_, ldq, GEMM_EPI_F32));
+        CU(batch_rope_kv_launch(bqkv_, bucket, bctl_, bst_, btables_, n_pages_, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, bq_, kc, vc, s)); ++nl;
+        BatchAttnParams a{};
+        a.q = bq_; a.k_cache = kc; a.v_cache = vc; a.tables = btables_; a.table_stride = n_pages_; a.st = bst_; a.ctl = bctl_;
+        a.out16 = battn16_; a.part_o = bpart_o_; a.part_ml = bpart_ml_; a.counters = bcounters_;
+        a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = splits; a.scale = scale;
+        CU(batch_attn_launch(a, bucket, s)); ++nl;
+        CU(linear(battn16_, L.wo16, bx_, n_embd_, qd, n_embd_, GEMM_EPI_ADD_F32));
+        CU(batch_rmsnorm_launch(bx_, L.ffn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
+        CU(linear(bxn16_, L.wgu16, bh16_, 2 * n_ff_, n_embd_, n_ff_, GEMM_EPI_SILU));
+        CU(linear(bh16_, L.wd16, bx_, n_embd_, n_ff_, n_embd_, GEMM_EPI_ADD_F32));
+    }
+    CU(batch_rmsnorm_launch(bx_, output_norm_, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
+    CU(linear(bxn16_, head16_, blogits_, n_vocab_, n_embd_, n_vocab_, GEMM_EPI_F32));
+    CU(batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, s)); ++nl;
+    if (n_launch) *n_launch = nl;
+    return {};
+}
+
+Status Engine::run_batch_graph(int bucket) {
+    const int bi = bucket_index(bucket);
+    if (!use_graph_) {
+        int nl = 0;
+        ST(enqueue_batch_step(stream_, bucket, &nl));
+        batch_launches_ = nl;
+        return {};
+    }
+    if (!g_batch_[bi]) {
+        cudaGraph_t g = nullptr;
+        int nl = 0;
+        CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        Status st = enqueue_batch_step(stream_, bucket, &nl);
+        cudaError_t e = cudaStreamEndCapture(stream_, &g);
+        if (!st.ok()) { if (g) cudaGraphDestroy(g); return st; }
+        if (e != cudaSuccess) return failb(GL_ERR_CUDA, std::string("batched step: graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&g_batch_[bi], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return failb(GL_ERR_CUDA, std::string("batched step: graph instantiate: ") + cudaGetErrorString(e));
+        batch_launches_ = nl;
+    }
+    CU(cudaGraphLaunch(g_batch_[bi], stream_));
+    return {};
+}
+
+// One token for every open, unfinished sequence.  Entries: (slot, id, logprob, done) -- see include/gridllm_native.h.
+Status Engine::batch_step(int32_t* out_slots, int32_t* out_ids, float* out_lps, int32_t* out_done, int cap, int* n_out) {
+    CU(cudaSetDevice(device_));
+    if (!n_out) return failb(GL_ERR_INVALID, "batch_step: null argument");
+    *n_out = 0;
+    if (slots_.empty()) return {};
+    int n = 0;
+    auto emit = [&](int slot, int32_t id, float lp, int done) {
+        if (out_slots) out_slots[n] = slot;
+        if (out_ids) out_ids[n] = id;
+        if (out_lps) out_lps[n] = lp;
+        if (out_done) out_done[n] = done;
+        ++n;
+    };
+    int n_first = 0, n_rows = 0;
+    for (int s = 0; s < max_batch_; ++s) {
+        const SeqSlot& S = slots_[s];
+        if (!S.open) continue;
+        if (S.first_pending) ++n_first;
+        else if (!S.done) ++n_rows;
+    }
+    if (n_first + n_rows > cap) return failb(GL_ERR_INVALID, "batch_step: output capacity too small");
+    std::vector<int> rows;
+    for (int s = 0; s < max_batch_; ++s) {
+        SeqSlot& S = slots_[s];
+        if (!S.open || (S.done && !S.first_pending)) continue;
+        if (S.first_pending) {                       // the token drawn at gl_seq_open
+            S.first_pending = false;
+            if (S.done) { emit(s, -1, 0.f, 1); continue; }
+            S.produced = 1;
+            if (S.produced >= S.n_pred) S.done = true;
+            emit(s, S.last_token, S.first_lp, S.done ? 1 : 0);
+            continue;
+        }
+        rows.push_back(s);
+    }
+    const int B = (int)rows.size();
+    if (B == 0) { *n_out = n; return {}; }
+    const int bucket = bucket_of(B);
+    if (rows != last_rows_) {                        // composition changed: one small copy, the captured step is unchanged
+        BatchCtl h{};
+        h.n_rows = B;
+        for (int r = 0; r < B; ++r) h.row_slot[r] = rows[r];
+        CU(cudaMemcpyAsync(bctl_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));      // pageable source: staged before the call returns
+        last_rows_ = rows;
+    }
+    last_bucket_ = bucket;
+    ST(run_batch_graph(bucket));
+    for (int r = 0; r < B; ++r) {                    // sampled rows: the seeded top-k / top-p sampler of the single-sequence path
+        const int slot = rows[r];
+        if (slots_[slot].sampler == 0) continue;
+        SampleParams sp{blogits_ + (size_t)r * n_vocab_, n_vocab_, bst_ + slot, bout_ids_ + (size_t)slot * max_out_, bout_lp_ + (size_t)slot * max_out_,
+                        nullptr, max_out_, sample_scratch_, topk_scratch_};
+        CU(sample_topk_launch(sp, slots_[slot].sampler == 1, false, stream_));
+    }
+    CU(batch_collect_launch(bctl_, bst_, bout_lp_, max_out_, bout_, bucket, stream_));
+    std::vector<BatchOut> ho(B);
+    CU(cudaMemcpyAsync(ho.data(), bout_, sizeof(BatchOut) * B, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaStreamSynchronize(stream_));
+    for (int r = 0; r < B; ++r) {
+        SeqSlot& S = slots_[rows[r]];
+        S.last_row = r;
+        if (ho[r].done) {                            // the token just drawn is a stop token: not part of the output
+            S.done = true;
+            emit(rows[r], -1, 0.f, 1);
+            continue;
+        }
+        S.last_token = ho[r].token;
+        ++S.produced;
+        if (S.produced >= S.n_pred) S.done = true;
+        emit(rows[r], ho[r].token, ho[r].logprob, S.done ? 1 : 0);
+    }
+    *n_out = n;
+    return {};
+}
+
+// Device time of one batched step with `batch` synthetic sequences at context ctx_len (bench roofline line).  The sequences are
+// real slots whose KV pages hold whatever is resident (timing does not depend on the values); they are closed afterwards.
+Status Engine::time_batch_step(int batch, int ctx_len, int iters, float* ms, int* launches, uint64_t* wbytes) {
+    CU(cudaSetDevice(device_));
+    ST(ensure_batch_state());
+    if (batch < 1 || batch > max_batch_ || ctx_len < 1 || iters < 1) return failb(GL_ERR_INVALID, "time_batch_step: bad arguments");
+    for (const SeqSlot& S : slots_)
+        if (S.open) return failb(GL_ERR_INVALID, "time_batch_step: close the open sequences first");
+    const int need_tokens = ctx_len + iters + 8;
+    if (need_tokens > n_ctx_) return failb(GL_ERR_CONTEXT, "time_batch_step: context too long for this engine");
+    const int need = (need_tokens + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+    if ((size_t)need * batch > free_pages_.size()) return failb(GL_ERR_NOMEM, "time_batch_step: KV page pool too small for this batch");
+    std::vector<StepState> hst(batch);
+    std::vector<int> rows(batch);
+    for (int b = 0; b < batch; ++b) {
+        SeqSlot& S = slots_[b];
+        S = SeqSlot{};
+        S.open = true;
+        for (int i = 0; i < need; ++i) { S.pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
+        CU(cudaMemcpyAsync(btables_ + (size_t)b * n_pages_, S.pages.data(), S.pages.size() * 4, cudaMemcpyHostToDevice, stream_));
+        StepState h{};
+        h.pos = ctx_len - 1; h.token = (7 + 13 * b) % n_vocab_; h.ignore_eos = 1; h.top_p = 1.f;
+        hst[b] = h;
+        rows[b] = b;
+    }
+    const int bucket = bucket_of(batch);
+    BatchCtl hc{};
+    hc.n_rows = batch;
+    for (int b = 0; b < batch; ++b) hc.row_slot[b] = b;
+    CU(cudaMemcpyAsync(bctl_, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
+    last_rows_ = rows;
+    auto reset = [&]() -> cudaError_t { return cudaMemcpyAsync(bst_, hst.data(), sizeof(StepState) * batch, cudaMemcpyHostToDevice, stream_); };
+    CU(reset());
+    Status rs;
+    for (int i = 0; i < 3 && rs.ok(); ++i) rs = run_batch_graph(bucket);         // warm-up (captures the bucket's graph)
+    if (rs.ok()) {
+        cudaError_t e = reset();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);                 // hst must outlive the copy
+        if (e == cudaSuccess) e = cudaEventRecord(ev_[0], stream_);
+        for (int i = 0; i < iters && rs.ok() && e == cudaSuccess; ++i) rs = run_batch_graph(bucket);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_[1], stream_);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev_[1]);
+        if (rs.ok() && e != cudaSuccess) rs = failb(GL_ERR_CUDA, std::string("time_batch_step: ") + cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(stream_);
+    for (int b = 0; b < batch; ++b) {
+        for (int p : slots_[b].pages) free_pages_.push_back(p);
+        slots_[b] = SeqSlot{};
+    }
+    last_rows_.clear();
+    ST(rs);
+    float t_ms = 0.f;
+    cudaEventElapsedTime(&t_ms, ev_[0], ev_[1]);
+    if (ms) *ms = t_ms / iters;
+    if (launches) *launches = batch_launches_;
+    if (wbytes) {
+        // bytes of weights one batched step reads: the resident 16-bit matrices of every layer + the 16-bit lm_head + norms
+        const uint64_t per_layer = ((uint64_t)(n_head_ * hd_ + 2 * n_kv_ * hd_) * n_embd_ + (uint64_t)n_embd_ * n_head_ * hd_ +
+                                    (uint64_t)2 * n_ff_ * n_embd_ + (uint64_t)n_embd_ * n_ff_) * 2;
+        *wbytes = per_layer * n_layer_ + (uint64_t)n_vocab_ * n_embd_ * 2 + (uint64_t)(2 * n_layer_ + 1) * n_embd_ * 4;
+    }
+    return {};
+}
+
+}  // namespace gl

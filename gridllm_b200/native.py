@@ -27,6 +27,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
     "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_chat_template", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
+    "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_time_batch_step",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -41,7 +42,8 @@ class NativeError(RuntimeError):
 
 class EngineOpts(C.Structure):
     _fields_ = [("max_ctx", C.c_int32), ("act_bits", C.c_int32), ("use_graph", C.c_int32), ("use_pdl", C.c_int32),
-                ("prefill_mode", C.c_int32), ("reserved", C.c_int32 * 11)]
+                ("prefill_mode", C.c_int32), ("max_batch", C.c_int32), ("kv_pool_tokens", C.c_int32), ("batch_weights", C.c_int32),
+                ("reserved", C.c_int32 * 8)]
 
 
 class ModelInfo(C.Structure):
@@ -96,6 +98,11 @@ def load_library() -> C.CDLL:
     lib.gl_embed.argtypes = [vp, i32p, i32p, i32, f32p, C.POINTER(GenStats)]
     lib.gl_last_logits.argtypes = [vp, i32, f32p, i32]
     lib.gl_sample_logits.argtypes = [vp, f32p, i32, C.POINTER(SampleOpts), i32, i32p, f32p]
+    lib.gl_seq_open.argtypes = [vp, i32p, i32, C.POINTER(SampleOpts), i32p]
+    lib.gl_batch_step.argtypes = [vp, i32p, i32p, f32p, i32p, i32, i32p]
+    lib.gl_seq_close.argtypes = [vp, i32]
+    lib.gl_seq_logits.argtypes = [vp, i32, f32p, i32]
+    lib.gl_time_batch_step.argtypes = [vp, i32, i32, i32, f32p, i32p, C.POINTER(C.c_uint64)]
     lib.gl_gemv.argtypes = [vp, C.c_int, vp, i32, i32, f32p, f32p, i32, f32p]
     lib.gl_gemv_model_tensor.argtypes = [vp, C.c_char_p, f32p, f32p, i32, i32, f32p, C.POINTER(C.c_uint64)]
     lib.gl_rmsnorm.argtypes = [vp, f32p, f32p, i32, C.c_float, f32p]
@@ -138,12 +145,14 @@ class Engine:
     """One GGUF model resident on one GPU (gl_engine)."""
 
     def __init__(self, gguf_path: str, device: int = 0, max_ctx: int = 0, act_bits: int = 16, use_graph: bool = True,
-                 use_pdl: bool = True, prefill_mode: int = 0):
+                 use_pdl: bool = True, prefill_mode: int = 0, max_batch: int = 0, kv_pool_tokens: int = 0, batch_weights: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         o = EngineOpts()
         o.max_ctx, o.act_bits, o.use_graph, o.use_pdl = max_ctx, act_bits, int(use_graph), int(use_pdl)
         o.prefill_mode = prefill_mode   # 0 auto (batched tensor-core prefill), 1 sequential decode steps
+        # continuous batching: sequences open at once (gl_seq_open), the KV pool they share, and which weights the batched step reads
+        o.max_batch, o.kv_pool_tokens, o.batch_weights = int(max_batch), int(kv_pool_tokens), int(batch_weights)
         _check(self._lib.gl_engine_create(gguf_path.encode(), device, C.byref(o), C.byref(self._h)))
         self.info = ModelInfo()
         _check(self._lib.gl_engine_info(self._h, C.byref(self.info)))
@@ -217,6 +226,42 @@ class Engine:
         if rc != GL_OK and rc != GL_ERR_CANCELLED:
             _check(rc)
         return Generation(ids[: st.eval_count].copy(), lps[: st.eval_count].copy(), st)
+
+    # ---- continuous batching (gl_seq_open / gl_batch_step / gl_seq_close) ---------------------------------
+    def seq_open(self, prompt: Sequence[int], num_predict: int = 128, ignore_eos: bool = False, temperature: float = 0.0, top_k: int = 0,
+                 top_p: float = 1.0, seed: int = 0, stop_ids: Sequence[int] = ()) -> int:
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        so = SampleOpts()
+        so.num_predict, so.ignore_eos = (num_predict if num_predict > 0 else 128), int(ignore_eos)
+        so.temperature, so.top_k, so.top_p, so.seed = float(temperature), int(top_k), float(top_p), int(seed) & (2**64 - 1)
+        stops = np.ascontiguousarray(stop_ids, dtype=np.int32)
+        so.n_stop_ids = len(stops)
+        so.stop_ids = _i32p(stops) if len(stops) else None
+        slot = C.c_int32(-1)
+        _check(self._lib.gl_seq_open(self._h, _i32p(p), len(p), C.byref(so), C.byref(slot)))
+        return int(slot.value)
+
+    def batch_step(self, cap: int = 128):
+        """-> [(slot, token id, logprob, done)]: one entry per open, unfinished sequence.  id -1 with done: a stop token was drawn."""
+        slots, ids, done = (np.zeros(cap, np.int32) for _ in range(3))
+        lps = np.zeros(cap, np.float32)
+        n = C.c_int32(0)
+        _check(self._lib.gl_batch_step(self._h, _i32p(slots), _i32p(ids), _f32p(lps), _i32p(done), cap, C.byref(n)))
+        return [(int(slots[i]), int(ids[i]), float(lps[i]), bool(done[i])) for i in range(n.value)]
+
+    def seq_close(self, slot: int) -> None:
+        _check(self._lib.gl_seq_close(self._h, int(slot)))
+
+    def seq_logits(self, slot: int) -> np.ndarray:
+        out = np.empty(self.info.n_vocab, dtype=np.float32)
+        _check(self._lib.gl_seq_logits(self._h, int(slot), _f32p(out), self.info.n_vocab))
+        return out
+
+    def time_batch_step(self, batch: int, ctx_len: int, iters: int = 16):
+        """-> (ms per batched step, kernel launches per step, weight bytes one step reads)"""
+        ms, nl, wb = C.c_float(0), C.c_int32(0), C.c_uint64(0)
+        _check(self._lib.gl_time_batch_step(self._h, batch, ctx_len, iters, C.byref(ms), C.byref(nl), C.byref(wb)))
+        return ms.value, nl.value, wb.value
 
     def sample_logits(self, logits: np.ndarray, temperature: float, top_k: int = 0, top_p: float = 1.0, seed: int = 0,
                       out_index: int = 0):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GL_ABI_VERSION 1
+#define GL_ABI_VERSION 2
 
 typedef enum gl_status {
     GL_OK = 0,
@@ -54,7 +54,12 @@ typedef struct gl_engine_opts {
     int32_t use_graph;        /* 1 (default): decode step replayed as a CUDA graph; 0: plain launches */
     int32_t use_pdl;          /* 1 (default): programmatic dependent launch between step kernels */
     int32_t prefill_mode;     /* 0 auto, 1 sequential decode steps, 2 batched tensor-core prefill */
-    int32_t reserved[11];
+    int32_t max_batch;        /* continuous batching: sequences that may be open at once (gl_seq_open); 0 / 1 = none, <= 128.
+                                 The KV pool is provisioned for max_batch sequences of max_ctx tokens unless kv_pool_tokens says otherwise */
+    int32_t kv_pool_tokens;   /* tokens of KV cache shared by all open sequences; 0 = max_ctx * max(1, max_batch) */
+    int32_t batch_weights;    /* batched step reads: 0 auto (the quantised weights, dequantised tile by tile inside the GEMM, when the
+                                 model's types allow it; else the resident 16-bit copy), 1 the 16-bit copy, 2 the quantised weights */
+    int32_t reserved[8];
 } gl_engine_opts;
 
 typedef struct gl_model_info {
@@ -129,6 +134,29 @@ int  gl_generate(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl
  *   L2-normalise. seq_offsets has n_seq+1 entries into ids. out is [n_seq][n_embd]. */
 int  gl_embed(gl_engine* e, const int32_t* ids, const int32_t* seq_offsets, int32_t n_seq,
               float* out, gl_gen_stats* stats);
+/* ---- continuous batching inside one engine ----------------------------------------------------
+ * The reference worker holds one job at a time (WorkerClientService.ts:500-505; MAX_CONCURRENT_JOBS_PER_WORKER,
+ * server/src/config/index.ts:31).  With that limit raised the worker opens one sequence per job and steps them TOGETHER:
+ * one batched decode step reads the weights once for every open sequence.
+ *   gl_seq_open   prefill `prompt` into a free slot's own KV pages and draw its first token (reported by the next
+ *                 gl_batch_step); pages for n_prompt + num_predict tokens are reserved up front, so a step cannot run out.
+ *                 GL_ERR_NOMEM when no slot / not enough pages are free -- the caller may retry after a gl_seq_close.
+ *   gl_batch_step one token for every open, unfinished sequence.  Entry i: slots[i], ids[i], logprobs[i], done[i].
+ *                 done = 1 with id >= 0: that token was the sequence's last (num_predict reached);  done = 1 with id = -1:
+ *                 the token drawn was a stop token (not part of the output).  Finished sequences stay open, holding
+ *                 their pages, until gl_seq_close.  *n = entries written (<= cap).
+ *   gl_seq_close  return the slot and its pages.
+ *   gl_seq_logits logits [n_vocab] the sequence's LAST token was drawn from (parity tests; valid until the next step).
+ * Sequences join and leave between steps; a sequence's tokens do not depend on who shares its batch. */
+int  gl_seq_open(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_sample_opts* opts, int32_t* slot);
+int  gl_batch_step(gl_engine* e, int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int32_t cap, int32_t* n);
+int  gl_seq_close(gl_engine* e, int32_t slot);
+int  gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab);
+/* mean device time (ms) of one batched decode step with `batch` synthetic sequences at context length ctx_len (roofline line
+ * of the batched workload); weight_bytes = bytes of weights one such step reads */
+int  gl_time_batch_step(gl_engine* e, int32_t batch, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step,
+                        uint64_t* weight_bytes);
+
 /* logits of generation step i of the last gl_generate that ran with want_logits=1 */
 int  gl_last_logits(gl_engine* e, int32_t step, float* out, int32_t n_vocab);
 

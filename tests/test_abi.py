@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), f"libgridllm_native.so does not export {s}"
     assert sorted(N.ABI_SYMBOLS) == declared
-    assert lib.gl_abi_version() == 1
+    assert lib.gl_abi_version() == 2
 
 
 def test_header_cites_reference_interfaces():
