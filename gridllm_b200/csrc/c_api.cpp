@@ -155,6 +155,23 @@ int gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab) {
     return ret(e->impl->seq_logits(slot, out, n_vocab));
 }
 
+int gl_seq_stats(gl_engine* e, int32_t slot, gl_gen_stats* stats) {
+    if (!e || !stats) return bad("gl_seq_stats: null argument");
+    return ret(e->impl->seq_stats(slot, stats));
+}
+
+int gl_token_piece(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32_t* len_out) {
+    if (!e || !len_out) return bad("gl_token_piece: null argument");
+    const gl::Tokenizer& t = e->impl->tokenizer();
+    if (!t.ok()) { *len_out = 0; return GL_OK; }                    // no tokenizer: no piece, like the gl_generate callback
+    const std::string pc = t.piece(id);
+    *len_out = (int32_t)pc.size();
+    if (!buf) return GL_OK;
+    if ((int32_t)pc.size() > cap) { gl::set_last_error("gl_token_piece: output buffer too small"); return GL_ERR_INVALID; }
+    std::memcpy(buf, pc.data(), pc.size());
+    return GL_OK;
+}
+
 int gl_time_batch_step(gl_engine* e, int32_t batch, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step,
                        uint64_t* weight_bytes) {
     if (!e) return bad("gl_time_batch_step: null engine");

@@ -61,6 +61,7 @@ public:
     Status batch_step(int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int cap, int* n);
     Status seq_close(int slot);
     Status seq_logits(int slot, float* out, int n_vocab);
+    Status seq_stats(int slot, gl_gen_stats* out) const;
     Status time_batch_step(int batch, int ctx_len, int iters, float* ms, int* launches, uint64_t* wbytes);
     Status sample_logits(const float* logits, int n_vocab, const gl_sample_opts& so, int out_index, int* id, float* logprob);
     Status gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms);
@@ -181,6 +182,9 @@ private:
         int32_t last_token = 0;
         float first_lp = 0.f;
         int last_row = -1;                            // row of the last batched step this sequence took part in
+        int64_t prefill_ns = 0, eval_ns = 0, t_open_ns = 0;      // device time of its prefill / of the steps it took part in; host clock at open
+        int launches = 0;
+        bool stopped = false;                         // ended on a stop token
     };
     static constexpr int N_BUCKETS = 5;               // batch-size buckets of the captured step: 8, 16, 32, 64, 128 rows
     int max_batch_ = 0;                               // gl_engine_opts.max_batch (0: batching off)

@@ -12,6 +12,7 @@
 // state (BatchCtl), so joining and leaving costs one small copy, not a re-capture.
 // A sequence's arithmetic never looks at another row: its tokens do not depend on who shares the batch.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -107,9 +108,12 @@ Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opt
     struct Saved { int* pt; StepState* st; int* oi; float* ol; int hp; } sv{page_table_, st_, out_ids_, out_lp_, host_pos_};
     page_table_ = table; st_ = bst_ + slot; out_ids_ = bout_ids_ + (size_t)slot * max_out_; out_lp_ = bout_lp_ + (size_t)slot * max_out_; host_pos_ = 0;
     Status rs;
+    int prefill_launches = 0;
+    const int64_t t_open = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
     do {
-        int dummy = 0;
+        int& dummy = prefill_launches;
         cudaError_t ce = cudaMemcpyAsync(prompt_ids_, prompt, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, stream_);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev_[2], stream_);
         if (ce != cudaSuccess) { rs = failb(GL_ERR_CUDA, cudaGetErrorString(ce)); break; }
         if (can_batch_prefill(n_prompt)) {
             rs = set_state(n_prompt - 1, prompt[n_prompt - 1], n_prompt, 0, &so);
@@ -122,10 +126,14 @@ Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opt
         if (!rs.ok()) break;
         StepState hs{};
         float lp = 0.f;
-        ce = cudaMemcpyAsync(&hs, st_, sizeof(hs), cudaMemcpyDeviceToHost, stream_);
+        ce = cudaEventRecord(ev_[3], stream_);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(&hs, st_, sizeof(hs), cudaMemcpyDeviceToHost, stream_);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(&lp, out_lp_, 4, cudaMemcpyDeviceToHost, stream_);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream_);
         if (ce != cudaSuccess) { rs = failb(GL_ERR_CUDA, cudaGetErrorString(ce)); break; }
+        float pms = 0.f;
+        cudaEventElapsedTime(&pms, ev_[2], ev_[3]);
+        S.prefill_ns = (int64_t)(pms * 1e6);
         S.last_token = hs.token;
         S.first_lp = lp;
         S.done = hs.done != 0;
@@ -139,6 +147,7 @@ Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opt
     }
     S.open = true;
     S.n_prompt = n_prompt; S.n_pred = n_pred; S.produced = 0; S.sampler = sampler; S.first_pending = true;
+    S.t_open_ns = t_open; S.launches = prefill_launches; S.stopped = S.done;
     *slot_out = slot;
     return {};
 }
@@ -147,6 +156,21 @@ Status Engine::seq_close(int slot) {
     if (slot < 0 || slot >= (int)slots_.size() || !slots_[slot].open) return failb(GL_ERR_INVALID, "seq_close: no such open sequence");
     for (int p : slots_[slot].pages) free_pages_.push_back(p);
     slots_[slot] = SeqSlot{};
+    return {};
+}
+
+Status Engine::seq_stats(int slot, gl_gen_stats* out) const {
+    if (slot < 0 || slot >= (int)slots_.size() || !slots_[slot].open || !out) return failb(GL_ERR_INVALID, "seq_stats: no such open sequence");
+    const SeqSlot& S = slots_[slot];
+    std::memset(out, 0, sizeof(*out));
+    out->prompt_eval_count = S.n_prompt;
+    out->eval_count = S.produced;
+    out->prompt_eval_duration_ns = S.prefill_ns;
+    out->eval_duration_ns = S.eval_ns;
+    out->total_duration_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - S.t_open_ns;
+    out->load_duration_ns = load_ns_;
+    out->done_reason = S.stopped ? 0 : 1;
+    out->kernel_launches = S.launches;
     return {};
 }
 
@@ -271,6 +295,7 @@ Status Engine::batch_step(int32_t* out_slots, int32_t* out_ids, float* out_lps, 
         last_rows_ = rows;
     }
     last_bucket_ = bucket;
+    CU(cudaEventRecord(ev_[2], stream_));
     ST(run_batch_graph(bucket));
     for (int r = 0; r < B; ++r) {                    // sampled rows: the seeded top-k / top-p sampler of the single-sequence path
         const int slot = rows[r];
@@ -280,14 +305,20 @@ Status Engine::batch_step(int32_t* out_slots, int32_t* out_ids, float* out_lps, 
         CU(sample_topk_launch(sp, slots_[slot].sampler == 1, false, stream_));
     }
     CU(batch_collect_launch(bctl_, bst_, bout_lp_, max_out_, bout_, bucket, stream_));
+    CU(cudaEventRecord(ev_[3], stream_));
     std::vector<BatchOut> ho(B);
     CU(cudaMemcpyAsync(ho.data(), bout_, sizeof(BatchOut) * B, cudaMemcpyDeviceToHost, stream_));
     CU(cudaStreamSynchronize(stream_));
+    float step_ms = 0.f;
+    cudaEventElapsedTime(&step_ms, ev_[2], ev_[3]);
     for (int r = 0; r < B; ++r) {
         SeqSlot& S = slots_[rows[r]];
         S.last_row = r;
+        S.eval_ns += (int64_t)(step_ms * 1e6);
+        S.launches += batch_launches_ + 1;
         if (ho[r].done) {                            // the token just drawn is a stop token: not part of the output
             S.done = true;
+            S.stopped = true;
             emit(rows[r], -1, 0.f, 1);
             continue;
         }

@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
     "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_chat_template", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
-    "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_time_batch_step",
+    "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_time_batch_step",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -102,6 +102,8 @@ def load_library() -> C.CDLL:
     lib.gl_batch_step.argtypes = [vp, i32p, i32p, f32p, i32p, i32, i32p]
     lib.gl_seq_close.argtypes = [vp, i32]
     lib.gl_seq_logits.argtypes = [vp, i32, f32p, i32]
+    lib.gl_seq_stats.argtypes = [vp, i32, C.POINTER(GenStats)]
+    lib.gl_token_piece.argtypes = [vp, i32, C.c_char_p, i32, i32p]
     lib.gl_time_batch_step.argtypes = [vp, i32, i32, i32, f32p, i32p, C.POINTER(C.c_uint64)]
     lib.gl_gemv.argtypes = [vp, C.c_int, vp, i32, i32, f32p, f32p, i32, f32p]
     lib.gl_gemv_model_tensor.argtypes = [vp, C.c_char_p, f32p, f32p, i32, i32, f32p, C.POINTER(C.c_uint64)]
@@ -256,6 +258,18 @@ class Engine:
         out = np.empty(self.info.n_vocab, dtype=np.float32)
         _check(self._lib.gl_seq_logits(self._h, int(slot), _f32p(out), self.info.n_vocab))
         return out
+
+    def seq_stats(self, slot: int) -> GenStats:
+        st = GenStats()
+        _check(self._lib.gl_seq_stats(self._h, int(slot), C.byref(st)))
+        return st
+
+    def token_piece(self, tid: int) -> bytes:
+        """the bytes of one token, as gl_generate's callback hands them over (b'' when the model has no tokenizer)"""
+        buf = C.create_string_buffer(256)
+        n = C.c_int32(0)
+        _check(self._lib.gl_token_piece(self._h, int(tid), buf, 256, C.byref(n)))
+        return buf.raw[: n.value]
 
     def time_batch_step(self, batch: int, ctx_len: int, iters: int = 16):
         """-> (ms per batched step, kernel launches per step, weight bytes one step reads)"""

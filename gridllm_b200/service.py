@@ -16,7 +16,6 @@ from __future__ import annotations
 import asyncio
 import hashlib
 import os
-import queue
 import secrets
 import threading
 import time
@@ -89,12 +88,14 @@ class NativeInferenceService:
     OLLAMA_SAMPLING_DEFAULTS = {"temperature": 0.8, "top_k": 40, "top_p": 0.9}
 
     def __init__(self, models: Dict[str, str], device: int = 0, max_ctx: int = 0,
-                 sampling_defaults: Optional[Dict[str, Any]] = None, apply_template: bool = False, **engine_kw):
+                 sampling_defaults: Optional[Dict[str, Any]] = None, apply_template: bool = False, max_batch: int = 0, **engine_kw):
         """models: Ollama-style model name -> GGUF path.
         sampling_defaults: options a request inherits when it does not carry them.  None = greedy (temperature 0, the
         BASELINE.json configuration); pass OLLAMA_SAMPLING_DEFAULTS to behave like an Ollama worker for such requests.
         apply_template: frame generate / completion prompts as one user turn of the model's chat template (with
-        metadata.system as the system turn) unless metadata.raw, as Ollama does; default False = raw prompts."""
+        metadata.system as the system turn) unless metadata.raw, as Ollama does; default False = raw prompts.
+        max_batch: > 1 turns on continuous batching: concurrent generate* calls become sequences of
+        one engine and are decoded together, one batched step per token (gridllm_b200/batching.py); 0 / 1 = one request at a time."""
         self._sampling_defaults = dict(sampling_defaults or {})
         # Ollama wraps the prompt of /api/generate and /v1/completions in the model's template (system + prompt as one user
         # turn) unless the request says raw [external]; off by default: the prompt text is tokenised as it is
@@ -103,6 +104,10 @@ class NativeInferenceService:
         self._device = device
         self._max_ctx = max_ctx
         self._engine_kw = engine_kw
+        self._max_batch = int(max_batch) if int(max_batch) > 1 else 0
+        if self._max_batch:
+            self._engine_kw = dict(engine_kw, max_batch=self._max_batch)
+        self._runners: Dict[str, Any] = {}
         self._engines: Dict[str, N.Engine] = {}
         self._lock = threading.Lock()          # one engine call at a time (one CUDA stream per engine)
         self._load_lock = threading.Lock()     # model load: once, and never on the event-loop thread (see _engine_async)
@@ -141,9 +146,25 @@ class NativeInferenceService:
         return int(v)
 
     def close(self):
+        for r in self._runners.values():
+            r.close()
+        self._runners.clear()
         for e in self._engines.values():
             e.close()
         self._engines.clear()
+
+    def _runner(self, name: str):
+        """the batch runner of a model's engine (continuous batching; one thread per engine)"""
+        with self._load_lock:
+            r = self._runners.get(name)
+        if r is None:
+            eng = self._engine(name)
+            from .batching import BatchRunner
+            with self._load_lock:
+                r = self._runners.get(name)
+                if r is None:
+                    r = self._runners[name] = BatchRunner(eng, self._lock, self._max_batch, N.Generation)
+        return r
 
     # ---- OllamaService.checkHealth (OllamaService.ts:65-83) ------------------------------------
     async def checkHealth(self) -> bool:
@@ -228,8 +249,8 @@ class NativeInferenceService:
     def _stop_ids(self, eng: N.Engine, request: InferenceRequest) -> List[int]:
         return []
 
-    def _run(self, model: str, ids: np.ndarray, num_predict: int, options: Dict[str, Any], on_token=None):
-        eng = self._engine(model)
+    def _plan(self, eng: N.Engine, ids: np.ndarray, num_predict: int, options: Dict[str, Any], on_token):
+        """-> (num_predict, ignore_eos, sampling kw, token callback, finish(gen)): what one generation needs, however it is run"""
         kw = self._sampling(options)
         ignore_eos = bool(options.get("ignore_eos", False))
         # a generation that would run past the engine's context ends at it (done_reason "length") instead of failing; a prompt
@@ -242,10 +263,10 @@ class NativeInferenceService:
         stops = options.get("stop")
         stops = [stops] if isinstance(stops, str) else list(stops or [])
         if not stops or not eng.info.has_tokenizer:
-            with self._lock:
-                gen = eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=on_token, **kw)
-            gen.prompt_ids = ids
-            return eng, gen
+            def finish(gen):
+                gen.prompt_ids = ids
+                return gen
+            return num_predict, ignore_eos, kw, on_token, finish
         # stop strings: the token callback sees only released text, and cancels the native call when one completes
         filt = StopFilter(stops)
 
@@ -254,15 +275,35 @@ class NativeInferenceService:
             stop_user = bool(on_token(tid, lp, out.encode("utf-8"))) if on_token is not None else False
             return stop_user or filt.hit
 
+        def finish(gen):
+            tail = filt.flush()
+            if tail and on_token is not None:
+                on_token(-1, 0.0, tail.encode("utf-8"))      # held-back text of a generation that ended by length / EOS
+            gen.stop_text = filt.text
+            gen.stopped = filt.hit
+            gen.prompt_ids = ids
+            return gen
+        return num_predict, ignore_eos, kw, cb, finish
+
+    def _run(self, model: str, ids: np.ndarray, num_predict: int, options: Dict[str, Any], on_token=None):
+        """one request at a time: the blocking gl_generate call (runs on a worker thread)"""
+        eng = self._engine(model)
+        num_predict, ignore_eos, kw, cb, finish = self._plan(eng, ids, num_predict, options, on_token)
         with self._lock:
             gen = eng.generate(ids, num_predict=num_predict, ignore_eos=ignore_eos, on_token=cb, **kw)
-        tail = filt.flush()
-        if tail and on_token is not None:
-            on_token(-1, 0.0, tail.encode("utf-8"))          # held-back text of a generation that ended by length / EOS
-        gen.stop_text = filt.text
-        gen.stopped = filt.hit
-        gen.prompt_ids = ids
-        return eng, gen
+        return eng, finish(gen)
+
+    async def _generate(self, model: str, ids: np.ndarray, num_predict: int, options: Dict[str, Any], on_token=None):
+        """-> (engine, Generation).  With continuous batching the request becomes a sequence of the engine's batch runner and
+        this coroutine just awaits its future (no thread is parked per request: 256 concurrent jobs are 256 futures); otherwise
+        the blocking call runs on a worker thread.  Either way the event loop stays free for heartbeats."""
+        if not self._max_batch:
+            return await asyncio.to_thread(self._run, model, ids, num_predict, options, on_token)
+        eng = await self._engine_async(model)
+        num_predict, ignore_eos, kw, cb, finish = self._plan(eng, ids, num_predict, options, on_token)
+        runner = await asyncio.to_thread(self._runner, model)
+        gen = await asyncio.wrap_future(runner.submit(ids, num_predict, ignore_eos, kw, cb))
+        return eng, finish(gen)
 
     def _sampling(self, options: Dict[str, Any]) -> Dict[str, Any]:
         """InferenceRequest.options.{temperature, top_k, top_p, seed} (client/src/types/index.ts:1-27; gateway ranges
@@ -318,7 +359,7 @@ class NativeInferenceService:
             num_predict = self._num_predict(options)
             eng = await self._engine_async(request["model"])
             ids = self._prompt_ids(eng, request, request.get("prompt"))
-            eng, gen = await asyncio.to_thread(self._run, request["model"], ids, num_predict, options)
+            eng, gen = await self._generate(request["model"], ids, num_predict, options)
             return self._response(request, eng, gen, self._text(eng, gen.ids))
         except Exception as error:
             raise RuntimeError(f"Inference failed: {error}")
@@ -330,26 +371,26 @@ class NativeInferenceService:
             num_predict = self._num_predict(options)
             eng = await self._engine_async(request["model"])
             ids = self._prompt_ids(eng, request, request.get("prompt"))
-            q: "queue.Queue" = queue.Queue()
+            loop = asyncio.get_running_loop()
+            q: "asyncio.Queue" = asyncio.Queue()
             cancel = threading.Event()
 
-            def on_token(tid: int, lp: float, piece: bytes) -> bool:
-                q.put(("tok", tid, piece))
+            def on_token(tid: int, lp: float, piece: bytes) -> bool:      # called on an engine thread
+                loop.call_soon_threadsafe(q.put_nowait, ("tok", tid, piece))
                 return cancel.is_set()          # non-zero return cancels (job_cancellation, JobScheduler.ts:530-536)
 
-            def work():
+            async def work():
                 try:
-                    _, gen = self._run(request["model"], ids, num_predict, options, on_token)
-                    q.put(("done", gen, None))
+                    _, gen = await self._generate(request["model"], ids, num_predict, options, on_token)
+                    q.put_nowait(("done", gen, None))     # after every token this generation queued (same loop, FIFO)
                 except Exception as ex:          # surfaced on the consumer side
-                    q.put(("err", ex, None))
+                    q.put_nowait(("err", ex, None))
 
-            th = threading.Thread(target=work, daemon=True)
-            th.start()
+            task = asyncio.ensure_future(work())
             pending = b""
             try:
                 while True:
-                    kind, a, b = await asyncio.to_thread(q.get)
+                    kind, a, b = await q.get()
                     if kind == "tok":
                         pending += b or b""
                         try:
@@ -365,6 +406,11 @@ class NativeInferenceService:
                         raise a
             finally:
                 cancel.set()
+                if not task.done():              # the consumer left early: the cancel flag ends the generation at its next token
+                    try:
+                        await task
+                    except Exception:
+                        pass
         except Exception as error:
             raise RuntimeError(f"Streaming inference failed: {error}")
 
@@ -384,7 +430,7 @@ class NativeInferenceService:
                 if not eng.info.has_tokenizer:
                     raise RuntimeError("model carries no tokenizer; supply metadata.prompt_token_ids")
                 ids = eng.tokenize(prompt, add_bos=True, parse_special=True)
-            eng, gen = await asyncio.to_thread(self._run, request["model"], ids, num_predict, options)
+            eng, gen = await self._generate(request["model"], ids, num_predict, options)
             res = self._response(request, eng, gen, self._text(eng, gen.ids))
             res["message"] = {"role": "assistant", "content": res.pop("response")}
             return res

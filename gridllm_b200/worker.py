@@ -64,8 +64,9 @@ class NativeWorker:
         self.bus = bus
         self.heartbeat_interval_ms = heartbeat_interval_ms
         # jobs this worker holds at once (MAX_CONCURRENT_JOBS_PER_WORKER on the server side, server/src/config/index.ts:31).
-        # 1 = the reference's busy-drop (:500-505).  More than one keeps the next job waiting at the engine while the current one
-        # runs, so the worker does not idle until the scheduler's next tick (the engine itself still runs one request at a time)
+        # 1 = the reference's busy-drop (:500-505).  More than one: the jobs run as concurrent tasks, and a service created with
+        # max_batch > 1 decodes them TOGETHER (continuous batching, gridllm_b200/batching.py) -- one batched step per token for
+        # every job the worker holds; with an un-batched service they wait at the engine one after the other
         self.max_concurrent = max(1, int(max_concurrent))
         self._tasks: set = set()
         self.isProcessingJob = False
@@ -86,8 +87,15 @@ class NativeWorker:
         await self.bus.publish("worker:registered", json.dumps(reg))
         await self.bus.subscribe(f"worker:{self.worker_id}:job", self.handleJobMessage)
 
+    def _status(self) -> str:
+        """The server takes `status` verbatim (WorkerRegistry.ts:266,331) and only assigns to workers that are "online"
+        (WorkerRegistry.ts:397-403).  Its own bookkeeping calls a worker "busy" once currentJobs reaches
+        MAX_CONCURRENT_JOBS_PER_WORKER (WorkerRegistry.ts:431-438) -- so a worker that can hold several jobs reports "busy" only
+        when it is full; with max_concurrent 1 this is the reference's busy-while-processing (WorkerClientService.ts:337,451)."""
+        return "busy" if self.currentJobs >= self.max_concurrent else "online"
+
     async def sendHeartbeat(self) -> None:
-        hb = {"workerId": self.worker_id, "status": "busy" if self.isProcessingJob else "online", "timestamp": _iso(),
+        hb = {"workerId": self.worker_id, "status": self._status(), "timestamp": _iso(),
               "currentJobs": self.currentJobs, "connectionHealth": "healthy"}
         await self.bus.set_with_expiry(f"heartbeat:{self.worker_id}", json.dumps(hb), self.heartbeat_interval_ms * 2 / 1000)
         await self.bus.publish("worker:heartbeat", json.dumps(hb))
@@ -119,7 +127,7 @@ class NativeWorker:
 
     async def publishStatusUpdate(self) -> None:
         await self.bus.publish("worker:status_update", json.dumps(
-            {"workerId": self.worker_id, "status": "busy" if self.isProcessingJob else "online", "currentJobs": self.currentJobs}))
+            {"workerId": self.worker_id, "status": self._status(), "currentJobs": self.currentJobs}))
 
     # ---- message handling (:478-495) -----------------------------------------------------------------
     async def handleJobMessage(self, message: str) -> None:
@@ -128,19 +136,26 @@ class NativeWorker:
             if self.max_concurrent == 1:
                 await self.processJobAssignment(data["job"])
             else:                                    # run beside the jobs already held; the message handler returns at once
-                t = asyncio.get_running_loop().create_task(self.processJobAssignment(data["job"]))
+                # the job is COUNTED here, synchronously with the message: the count the next status update / heartbeat reports
+                # (which the server takes over verbatim, WorkerRegistry.ts:269,332) never lags behind what was accepted
+                if self.currentJobs >= self.max_concurrent:
+                    return                           # full: dropped, like the reference's busy-drop (:500-505)
+                self.currentJobs += 1
+                self.isProcessingJob = True
+                t = asyncio.get_running_loop().create_task(self.processJobAssignment(data["job"], counted=True))
                 self._tasks.add(t)
                 t.add_done_callback(self._tasks.discard)
         elif data.get("type") == "job_cancellation":
             self._cancelled.add(data.get("jobId"))
 
     # ---- processJobAssignment (:497-712) ---------------------------------------------------------------
-    async def processJobAssignment(self, assignment: Dict[str, Any]) -> None:
+    async def processJobAssignment(self, assignment: Dict[str, Any], counted: bool = False) -> None:
         request = assignment["request"]
-        if self.currentJobs >= self.max_concurrent or (self.max_concurrent == 1 and self.isProcessingJob):
-            return                                   # dropped; the server notices via timeout / orphan scan
-        self.currentJobs += 1
-        self.isProcessingJob = True
+        if not counted:
+            if self.currentJobs >= self.max_concurrent or (self.max_concurrent == 1 and self.isProcessingJob):
+                return                               # dropped; the server notices via timeout / orphan scan
+            self.currentJobs += 1
+            self.isProcessingJob = True
         await self.publishStatusUpdate()
         jid = request["id"]
         try:
@@ -154,26 +169,34 @@ class NativeWorker:
             elif rtype == "chat":
                 if request.get("stream"):
                     full = ""
-                    async for chunk in self.service.generateChatStreamResponse(request):
-                        full += chunk["response"]
-                        await self.bus.publish(f"job:stream:{jid}", json.dumps(
-                            {"jobId": jid, "workerId": self.worker_id,
-                             "chunk": dict(chunk, message={"content": chunk["response"]}), "timestamp": _iso()}))
-                        if chunk["done"] or jid in self._cancelled:
-                            result = dict(chunk, id=jid, message={"content": full})
-                            break
+                    agen = self.service.generateChatStreamResponse(request)
+                    try:
+                        async for chunk in agen:
+                            full += chunk["response"]
+                            await self.bus.publish(f"job:stream:{jid}", json.dumps(
+                                {"jobId": jid, "workerId": self.worker_id,
+                                 "chunk": dict(chunk, message={"content": chunk["response"]}), "timestamp": _iso()}))
+                            if chunk["done"] or jid in self._cancelled:
+                                result = dict(chunk, id=jid, message={"content": full})
+                                break
+                    finally:
+                        await agen.aclose()          # a cancelled job: closing the generator stops the engine at its next token
                 else:
                     result = await self.service.generateChatResponse(request)
             elif request.get("stream"):
                 full = ""
-                async for chunk in self.service.generateStreamResponse(request):
-                    full += chunk["response"]
-                    await self.bus.publish(f"job:stream:{jid}", json.dumps(
-                        {"jobId": jid, "workerId": self.worker_id,
-                         "chunk": {"id": chunk["id"], "response": chunk["response"], "done": chunk["done"]}, "timestamp": _iso()}))
-                    if chunk["done"] or jid in self._cancelled:
-                        result = {"id": jid, "response": full, "done": True}
-                        break
+                agen = self.service.generateStreamResponse(request)
+                try:
+                    async for chunk in agen:
+                        full += chunk["response"]
+                        await self.bus.publish(f"job:stream:{jid}", json.dumps(
+                            {"jobId": jid, "workerId": self.worker_id,
+                             "chunk": {"id": chunk["id"], "response": chunk["response"], "done": chunk["done"]}, "timestamp": _iso()}))
+                        if chunk["done"] or jid in self._cancelled:
+                            result = {"id": jid, "response": full, "done": True}
+                            break
+                finally:
+                    await agen.aclose()
             else:
                 result = await self.service.generateResponse(request)
             if not result:

@@ -152,6 +152,12 @@ int  gl_seq_open(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl
 int  gl_batch_step(gl_engine* e, int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int32_t cap, int32_t* n);
 int  gl_seq_close(gl_engine* e, int32_t slot);
 int  gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab);
+/* counts and DEVICE durations of one open sequence (InferenceResponse fields, client/src/types/index.ts:39-68):
+ * prompt_eval_duration = the prefill of gl_seq_open, eval_duration = the sum of the batched steps it took part in (a step's
+ * device time is shared by everyone in it: B sequences each see the whole step), done_reason as for gl_generate. */
+int  gl_seq_stats(gl_engine* e, int32_t slot, gl_gen_stats* stats);
+/* the bytes of one token as gl_generate's callback would hand them over (may be an incomplete UTF-8 sequence) */
+int  gl_token_piece(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32_t* len_out);
 /* mean device time (ms) of one batched decode step with `batch` synthetic sequences at context length ctx_len (roofline line
  * of the batched workload); weight_bytes = bytes of weights one such step reads */
 int  gl_time_batch_step(gl_engine* e, int32_t batch, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step,

@@ -26,6 +26,7 @@ class OracleEngine:
                                     eos_id=self.m.n_vocab - 2, eot_id=self.m.n_vocab - 1, bos_id=self.m.n_vocab - 3)
         self.calls = []
         self.chat_template = ""
+        self.max_batch = int(kw.get("max_batch", 0) or 0)
 
     # ---- tokenizer: the product's C++ code --------------------------------------------------------------------------
     def tokenize(self, text, add_bos=True, parse_special=False):
@@ -71,6 +72,61 @@ class OracleEngine:
         stats = SimpleNamespace(prompt_eval_count=len(prompt), eval_count=len(ids), prompt_eval_duration_ns=t1 - t0, eval_duration_ns=max(1, t2 - t1),
                                 total_duration_ns=t2 - t0, load_duration_ns=1, done_reason=reason, kernel_launches=0)
         return SimpleNamespace(ids=np.array(ids, dtype=np.int32), logprobs=np.array(lps, dtype=np.float32), stats=stats)
+
+    # ---- continuous batching: the same oracle, one instance per open sequence, stepped together -------------------------
+    def seq_open(self, prompt, num_predict=128, ignore_eos=False, temperature=0.0, top_k=0, top_p=1.0, seed=0, stop_ids=()):
+        from gridllm_b200.native import NativeError
+        if not getattr(self, "max_batch", 0):
+            raise NativeError(-4, "continuous batching is off")
+        if not hasattr(self, "_seqs"):
+            self._seqs = {}
+        if len(prompt) + num_predict > self.info.n_ctx:
+            raise NativeError(-9, "prompt + num_predict exceeds the engine context")
+        free = [i for i in range(self.max_batch) if i not in self._seqs]
+        if not free:
+            raise NativeError(-6, "no free sequence slot")
+        self.calls.append(dict(n_prompt=len(prompt), num_predict=num_predict, temperature=temperature, top_k=top_k, top_p=top_p, seed=seed, batched=True))
+        orc = O.LlamaOracle(self.m, act="i16", kv_f16=True)
+        logits = None
+        for t in prompt:
+            logits = orc.step(int(t))
+        stops = set(int(s) for s in stop_ids) | ({self.info.eos_id, self.info.eot_id} if not ignore_eos else set())
+        self._seqs[free[0]] = SimpleNamespace(orc=orc, logits=logits, n=0, n_pred=num_predict, stops=stops, opts=(temperature, top_k, top_p, seed),
+                                              n_prompt=len(prompt), done=False, stopped=False, t0=time.perf_counter_ns())
+        return free[0]
+
+    def batch_step(self, cap=128):
+        out = []
+        self.batch_sizes = getattr(self, "batch_sizes", [])
+        live = [(slot, q) for slot, q in sorted(getattr(self, "_seqs", {}).items()) if not q.done]
+        self.batch_sizes.append(len(live))
+        for slot, q in live:
+            tok, lp, _ = SM.sample(q.logits, *q.opts, q.n)
+            if tok in q.stops:
+                q.done = q.stopped = True
+                out.append((slot, -1, 0.0, True))
+                continue
+            q.n += 1
+            q.done = q.n >= q.n_pred
+            out.append((slot, int(tok), float(lp), q.done))
+            if not q.done:
+                q.logits = q.orc.step(int(tok))
+        return out
+
+    def seq_stats(self, slot):
+        q = self._seqs[slot]
+        dt = time.perf_counter_ns() - q.t0
+        return SimpleNamespace(prompt_eval_count=q.n_prompt, eval_count=q.n, prompt_eval_duration_ns=1, eval_duration_ns=max(1, dt), total_duration_ns=dt,
+                               load_duration_ns=1, done_reason=0 if q.stopped else 1, kernel_launches=0)
+
+    def seq_close(self, slot):
+        from gridllm_b200.native import NativeError
+        if slot not in getattr(self, "_seqs", {}):
+            raise NativeError(-1, "seq_close: no such open sequence")
+        del self._seqs[slot]
+
+    def token_piece(self, tid):
+        return self._bytes([tid])
 
     def embed(self, seqs):
         if any(len(s) > self.info.n_ctx for s in seqs):

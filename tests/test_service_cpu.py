@@ -330,3 +330,122 @@ def test_num_predict_minus_one_runs_until_the_context_is_full(svc):
     res = _run(svc.generateResponse({"id": "n1", "model": "tiny:latest", "prompt": "hi", "options": {"num_predict": -1, "ignore_eos": True},
                                      "priority": "low"}))
     assert res["eval_count"] == eng.info.n_ctx - len(ids) and res["done_reason"] == "length"
+
+
+# ---- continuous batching on the host side (gridllm_b200/batching.py): concurrent requests share the engine's batched step ----
+@pytest.fixture()
+def bsvc(tiny_gguf, hostcheck_lib, monkeypatch):
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 1)
+    s = SV.NativeInferenceService({"tiny:latest": tiny_gguf}, device=0, max_batch=4)
+    yield s
+    s.close()
+
+
+def test_concurrent_requests_are_decoded_together_and_match_the_oracle(bsvc):
+    from oracle import llama_oracle as O
+    eng = bsvc._engine("tiny:latest")
+    prompts = [np.random.Generator(np.random.PCG64(500 + i)).integers(0, 500, size=6 + i).tolist() for i in range(6)]
+    reqs = [{"id": f"b{i}", "model": "tiny:latest", "prompt": "", "options": {"num_predict": 3 + i % 3, "ignore_eos": True}, "priority": "medium",
+             "metadata": {"prompt_token_ids": p}} for i, p in enumerate(prompts)]
+
+    async def go():
+        return await asyncio.gather(*[bsvc.generateResponse(r) for r in reqs])
+    res = _run(go())
+    for r, p, q in zip(res, prompts, reqs):
+        ref = O.LlamaOracle(eng.m, act="i16", kv_f16=True).generate(np.asarray(p), q["options"]["num_predict"])
+        assert r["token_ids"] == [int(t) for t in ref["ids"]] and r["eval_count"] == q["options"]["num_predict"]
+        assert r["context"] == p + r["token_ids"] and r["done_reason"] == "length" and r["prompt_eval_count"] == len(p)
+    assert max(eng.batch_sizes) == 4                     # six requests, four slots: the engine stepped four sequences at once,
+    assert all(c.get("batched") for c in eng.calls)      # ... every request went through gl_seq_open, none through gl_generate
+    runner = bsvc._runners["tiny:latest"]
+    assert runner.max_rows == 4 and runner.steps >= 3
+
+
+def test_batched_streams_stop_strings_and_cancellation(bsvc):
+    eng = bsvc._engine("tiny:latest")
+    base = {"model": "tiny:latest", "prompt": "hello world, the rain in spain", "options": {"num_predict": 8, "ignore_eos": True}, "priority": "medium"}
+    plain = _run(bsvc.generateResponse(dict(base, id="p0")))
+    text = plain["response"]
+    assert plain["eval_count"] == 8 and len(text) >= 4
+    stop = text[len(text) // 2: len(text) // 2 + 2]
+
+    async def collect(req, cancel_after=None):
+        out = []
+        agen = bsvc.generateStreamResponse(req)
+        async for c in agen:
+            out.append(c)
+            if cancel_after is not None and len(out) >= cancel_after:
+                await agen.aclose()
+                break
+        return out
+
+    async def go():
+        return await asyncio.gather(
+            collect(dict(base, id="s1", stream=True)),
+            collect(dict(base, id="s2", stream=True, options=dict(base["options"], stop=[stop]))),
+            collect(dict(base, id="s3", stream=True), cancel_after=2),
+            bsvc.generateResponse(dict(base, id="s4")))
+    full, stopped, cancelled, again = _run(go())
+    assert "".join(c["response"] for c in full) == text and [c["done"] for c in full] == [False] * 8 + [True]
+    assert "".join(c["response"] for c in stopped) == text[:text.index(stop)] and stopped[-1]["done"] is True
+    assert len(cancelled) == 2
+    assert again["response"] == text                     # a stop string or a cancellation in one sequence leaves the others alone
+    # every sequence was returned to the engine: nothing is left open
+    import time
+    for _ in range(200):
+        if not getattr(eng, "_seqs", {}):
+            break
+        time.sleep(0.01)
+    assert not eng._seqs
+
+
+def test_workers_with_concurrent_jobs_behind_the_scheduler(tiny_gguf, hostcheck_lib, monkeypatch):
+    """MAX_CONCURRENT_JOBS_PER_WORKER = 3 on the server side, max_concurrent = 3 / max_batch = 3 on the worker side: the
+    scheduler's least-loaded rule spreads nine jobs over two workers, each worker decodes the jobs it holds together"""
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    from oracle import llama_oracle as O
+    from sched_standin import SchedulerStandIn
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 2)
+    bus = LocalBus()
+    sched = SchedulerStandIn(bus, max_jobs_per_worker=3)
+    svcs = [SV.NativeInferenceService({"tiny:latest": tiny_gguf}, device=i, max_batch=3) for i in range(2)]
+    workers = [NativeWorker(f"b200-{i}", s, bus, max_concurrent=3) for i, s in enumerate(svcs)]
+
+    async def go():
+        await sched.start()
+        for w in workers:
+            await w.start()
+        for i in range(9):
+            ids = np.random.Generator(np.random.PCG64(2000 + i)).integers(0, 500, size=10).tolist()
+            sched.add_job({"id": f"job-{i}", "model": "tiny:latest", "prompt": "", "stream": i % 2 == 0, "priority": "medium",
+                           "options": {"num_predict": 4, "ignore_eos": True}, "timeout": 300000, "metadata": {"prompt_token_ids": ids}})
+            if i % 2 == 0:
+                await sched.watch_stream(f"job-{i}")
+        await sched.run_until_empty()
+        for w in workers:
+            await w.stop()
+    _run(go())
+    assert len(sched.results) == 9 and all("result" in r for r in sched.results.values())
+    per_worker = {w: sum(1 for v in sched.assigned.values() if v == w) for w in ("b200-0", "b200-1")}
+    assert min(per_worker.values()) >= 3                 # both workers were used, neither ever held more than three jobs
+    assert all(max(s._engine("tiny:latest").batch_sizes) <= 3 for s in svcs)
+    assert max(max(s._engine("tiny:latest").batch_sizes) for s in svcs) >= 2         # jobs really shared steps
+    m = O.load_gguf(tiny_gguf)
+    for i in range(9):
+        ids = np.random.Generator(np.random.PCG64(2000 + i)).integers(0, 500, size=10)
+        ref = O.LlamaOracle(m, act="i16", kv_f16=True).generate(ids, 4)
+        r = sched.results[f"job-{i}"]["result"]
+        if i % 2 == 0:
+            assert sched.stream_chunks[f"job-{i}"] == 5 and r["done"] is True       # 4 tokens + the done chunk on job:stream:<id>
+        else:
+            assert r["token_ids"] == [int(t) for t in ref["ids"]]
+    for s in svcs:
+        s.close()

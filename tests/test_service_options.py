@@ -111,6 +111,8 @@ def _service_with_fake():
     s._engines = {"m": _FakeEngine()}
     s._lock = threading.Lock()
     s._load_lock = threading.Lock()
+    s._max_batch = 0
+    s._runners = {}
     return s
 
 
