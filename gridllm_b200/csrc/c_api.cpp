@@ -172,6 +172,12 @@ int gl_token_piece(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32
     return GL_OK;
 }
 
+int gl_batch_counters(gl_engine* e, uint64_t out[8], int32_t reset) {
+    if (!e || !out) return bad("gl_batch_counters: null argument");
+    e->impl->batch_counters(out, reset != 0);
+    return GL_OK;
+}
+
 int gl_time_batch_step(gl_engine* e, int32_t batch, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step,
                        uint64_t* weight_bytes) {
     if (!e) return bad("gl_time_batch_step: null engine");

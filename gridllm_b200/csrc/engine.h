@@ -62,6 +62,7 @@ public:
     Status seq_close(int slot);
     Status seq_logits(int slot, float* out, int n_vocab);
     Status seq_stats(int slot, gl_gen_stats* out) const;
+    void batch_counters(uint64_t out[8], bool reset) { for (int i = 0; i < 8; ++i) { out[i] = bc_[i]; if (reset) bc_[i] = 0; } }
     Status time_batch_step(int batch, int ctx_len, int iters, float* ms, int* launches, uint64_t* wbytes);
     Status sample_logits(const float* logits, int n_vocab, const gl_sample_opts& so, int out_index, int* id, float* logprob);
     Status gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms);
@@ -188,6 +189,7 @@ private:
     };
     static constexpr int N_BUCKETS = 5;               // batch-size buckets of the captured step: 8, 16, 32, 64, 128 rows
     int max_batch_ = 0;                               // gl_engine_opts.max_batch (0: batching off)
+    bool batch_ready_ = false;
     int batch_weights_ = 0;                           // 1: resident 16-bit copy, 2: quantised weights (engine_batch.cu picks for 0)
     std::vector<SeqSlot> slots_;
     std::vector<int> last_rows_;                      // composition the device-resident BatchCtl currently describes
@@ -196,13 +198,14 @@ private:
     StepState* bst_ = nullptr;                        // [MAX_BATCH]
     int* btables_ = nullptr;                          // [MAX_BATCH][n_pages_]
     int *bids_ = nullptr, *bout_ids_ = nullptr;
-    float *bx_ = nullptr, *bqkv_ = nullptr, *bq_ = nullptr, *blogits_ = nullptr, *bout_lp_ = nullptr, *bpart_o_ = nullptr, *bpart_ml_ = nullptr;
+    float *bx_ = nullptr, *bqkv_ = nullptr, *bq_ = nullptr, *blogits_ = nullptr, *bfirst_logits_ = nullptr, *bout_lp_ = nullptr, *bpart_o_ = nullptr, *bpart_ml_ = nullptr;
     __half *bxn16_ = nullptr, *battn16_ = nullptr, *bh16_ = nullptr;
     unsigned* bcounters_ = nullptr;
     BatchOut* bout_ = nullptr;
     void* head16_ = nullptr;                          // [n_vocab x n_embd] fp16 copy of the lm_head (16-bit batched path)
     cudaGraphExec_t g_batch_[N_BUCKETS] = {};
     int batch_launches_ = 0;                          // kernels of one batched step
+    uint64_t bc_[8] = {};                             // gl_batch_counters
     Status ensure_batch_state();
     Status enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch);
     Status run_batch_graph(int bucket);

@@ -43,7 +43,8 @@ int attn_splits_for(int bucket, int n_kv) {
 }  // namespace
 
 Status Engine::ensure_batch_state() {
-    if (bst_) return {};
+    if (batch_ready_) return {};
+    if (bst_) return failb(GL_ERR_CUDA, "continuous batching: an earlier initialisation failed on this engine");
     if (max_batch_ < 2) return failb(GL_ERR_UNSUPPORTED, "continuous batching is off: create the engine with gl_engine_opts.max_batch >= 2");
     if (!have_w16_) return failb(GL_ERR_UNSUPPORTED, "continuous batching needs the resident 16-bit weights (not enough HBM at load, or prefill_mode 1)");
     if (n_ff_ % 8) return failb(GL_ERR_UNSUPPORTED, "continuous batching: n_ff must be a multiple of 8");
@@ -67,6 +68,7 @@ Status Engine::ensure_batch_state() {
     CU(dalloc((void**)&battn16_, R * qd * 2));
     CU(dalloc((void**)&bh16_, R * n_ff_ * 2));
     CU(dalloc((void**)&blogits_, R * n_vocab_ * 4));
+    CU(dalloc((void**)&bfirst_logits_, (size_t)max_batch_ * n_vocab_ * 4));      // logits each sequence's FIRST token was drawn from (gl_seq_logits)
     CU(dalloc((void**)&bpart_o_, R * n_head_ * 16 * hd_ * 4));
     CU(dalloc((void**)&bpart_ml_, R * n_head_ * 16 * 2 * 4));
     CU(dalloc((void**)&bcounters_, R * n_kv_ * 4));
@@ -74,11 +76,19 @@ Status Engine::ensure_batch_state() {
     CU(dalloc(&head16_, (size_t)n_vocab_ * n_embd_ * 2));
     CU(dequant_rows_launch(output_.w, output_.type, output_.rows, output_.cols, output_.row_stride, output_.tile_rows, head16_, n_embd_, 0, 0, false,
                            stream_));
-    CU(dalloc((void**)&bst_, sizeof(StepState) * R));        // last: bst_ != null means "state is complete"
+    CU(dalloc((void**)&bst_, sizeof(StepState) * R));
     CU(cudaStreamSynchronize(stream_));
     slots_.assign(MAX_BATCH, SeqSlot{});
     last_rows_.clear();
     last_bucket_ = 0;
+    // one un-captured pass with an empty batch (n_rows = 0: the per-row kernels leave at once, the GEMMs run on zero rows): every
+    // launch configuration is validated -- and every lazily initialised driver entry point touched -- OUTSIDE stream capture,
+    // where an error has a name
+    int nl = 0;
+    ST(enqueue_batch_step(stream_, 8, &nl));
+    CU(cudaStreamSynchronize(stream_));
+    batch_launches_ = nl;
+    batch_ready_ = true;
     return {};
 }
 
@@ -127,6 +137,7 @@ Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opt
         StepState hs{};
         float lp = 0.f;
         ce = cudaEventRecord(ev_[3], stream_);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(bfirst_logits_ + (size_t)slot * n_vocab_, logits_, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToDevice, stream_);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(&hs, st_, sizeof(hs), cudaMemcpyDeviceToHost, stream_);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(&lp, out_lp_, 4, cudaMemcpyDeviceToHost, stream_);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream_);
@@ -148,6 +159,7 @@ Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opt
     S.open = true;
     S.n_prompt = n_prompt; S.n_pred = n_pred; S.produced = 0; S.sampler = sampler; S.first_pending = true;
     S.t_open_ns = t_open; S.launches = prefill_launches; S.stopped = S.done;
+    bc_[3] += (uint64_t)S.prefill_ns; bc_[4] += (uint64_t)n_prompt; bc_[5] += 1; bc_[6] += (uint64_t)prefill_launches;
     *slot_out = slot;
     return {};
 }
@@ -178,8 +190,8 @@ Status Engine::seq_logits(int slot, float* out, int n_vocab) {
     CU(cudaSetDevice(device_));
     if (slot < 0 || slot >= (int)slots_.size() || !slots_[slot].open || n_vocab != n_vocab_ || !out) return failb(GL_ERR_INVALID, "seq_logits: bad argument");
     const SeqSlot& S = slots_[slot];
-    // the first token is drawn from the single-sequence logits buffer at gl_seq_open; later ones from the step's row
-    const float* src = S.last_row < 0 ? logits_ : blogits_ + (size_t)S.last_row * n_vocab_;
+    // the first token is drawn at gl_seq_open (its logits are kept per slot); later ones from the sequence's row of the last step
+    const float* src = S.last_row < 0 ? bfirst_logits_ + (size_t)slot * n_vocab_ : blogits_ + (size_t)S.last_row * n_vocab_;
     CU(cudaMemcpy(out, src, (size_t)n_vocab_ * 4, cudaMemcpyDeviceToHost));
     return {};
 }
@@ -311,6 +323,7 @@ Status Engine::batch_step(int32_t* out_slots, int32_t* out_ids, float* out_lps, 
     CU(cudaStreamSynchronize(stream_));
     float step_ms = 0.f;
     cudaEventElapsedTime(&step_ms, ev_[2], ev_[3]);
+    bc_[0] += 1; bc_[1] += (uint64_t)B; bc_[2] += (uint64_t)(step_ms * 1e6); bc_[6] += (uint64_t)batch_launches_ + 1;
     for (int r = 0; r < B; ++r) {
         SeqSlot& S = slots_[rows[r]];
         S.last_row = r;

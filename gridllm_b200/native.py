@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
     "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_chat_template", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
-    "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_time_batch_step",
+    "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_batch_counters", "gl_time_batch_step",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -104,6 +104,7 @@ def load_library() -> C.CDLL:
     lib.gl_seq_logits.argtypes = [vp, i32, f32p, i32]
     lib.gl_seq_stats.argtypes = [vp, i32, C.POINTER(GenStats)]
     lib.gl_token_piece.argtypes = [vp, i32, C.c_char_p, i32, i32p]
+    lib.gl_batch_counters.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     lib.gl_time_batch_step.argtypes = [vp, i32, i32, i32, f32p, i32p, C.POINTER(C.c_uint64)]
     lib.gl_gemv.argtypes = [vp, C.c_int, vp, i32, i32, f32p, f32p, i32, f32p]
     lib.gl_gemv_model_tensor.argtypes = [vp, C.c_char_p, f32p, f32p, i32, i32, f32p, C.POINTER(C.c_uint64)]
@@ -270,6 +271,12 @@ class Engine:
         n = C.c_int32(0)
         _check(self._lib.gl_token_piece(self._h, int(tid), buf, 256, C.byref(n)))
         return buf.raw[: n.value]
+
+    def batch_counters(self, reset: bool = False) -> dict:
+        out = (C.c_uint64 * 8)()
+        _check(self._lib.gl_batch_counters(self._h, out, int(reset)))
+        return {"steps": out[0], "rows": out[1], "step_ns": out[2], "prefill_ns": out[3], "prefill_tokens": out[4], "sequences": out[5],
+                "launches": out[6]}
 
     def time_batch_step(self, batch: int, ctx_len: int, iters: int = 16):
         """-> (ms per batched step, kernel launches per step, weight bytes one step reads)"""

@@ -158,6 +158,10 @@ int  gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab);
 int  gl_seq_stats(gl_engine* e, int32_t slot, gl_gen_stats* stats);
 /* the bytes of one token as gl_generate's callback would hand them over (may be an incomplete UTF-8 sequence) */
 int  gl_token_piece(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32_t* len_out);
+/* engine-wide batching counters since creation (or the last reset): out[0] batched steps, [1] sum over steps of sequences in
+ * the step, [2] device ns of those steps, [3] device ns of the prefills of gl_seq_open, [4] prompt tokens prefilled,
+ * [5] sequences opened, [6] kernel launches, [7] reserved.  reset != 0 zeroes them after reading. */
+int  gl_batch_counters(gl_engine* e, uint64_t out[8], int32_t reset);
 /* mean device time (ms) of one batched decode step with `batch` synthetic sequences at context length ctx_len (roofline line
  * of the batched workload); weight_bytes = bytes of weights one such step reads */
 int  gl_time_batch_step(gl_engine* e, int32_t batch, int32_t ctx_len, int32_t iters, float* ms_per_step, int32_t* launches_per_step,

@@ -505,6 +505,128 @@ int oc_step(void* vm, int token, int mode, float* logits, float* hidden) {
     return 0;
 }
 
+
+/* ---- batched prompt evaluation ("prefill"): T tokens per weight pass ----------------------------------------------------
+ * What llama.cpp's CPU backend does with a prompt [external]: every weight row is decoded once and used for all T tokens of
+ * the batch, so the prompt costs one pass over the weights (compute-bound) instead of T passes (bandwidth-bound).  The
+ * arithmetic per (row, token) is exactly oc_step's mode-1 arithmetic (int8 activations, integer dots), so oc_prefill and
+ * T calls of oc_step give the same numbers (tests/test_c_oracle.py).  bench.py times this for the reference arm's prompt
+ * phase -- charging the CPU a token-by-token prefill would flatter the GPU. */
+static void quant_act_into(const float* x, int n, int blk, int8_t* xq, float* xs, int* bs) {
+    for (int b = 0; b < n / blk; ++b) {
+        float amax = 0.f;
+        for (int i = 0; i < blk; ++i) { float a = fabsf(x[b * blk + i]); if (a > amax) amax = a; }
+        const float inv = amax > 0.f ? 127.0f / amax : 0.f;
+        xs[b] = amax / 127.0f;
+        for (int i = 0; i < blk; ++i) xq[b * blk + i] = (int8_t)lrintf(x[b * blk + i] * inv);
+    }
+    for (int g = 0; g < n / 16; ++g) { int s = 0; for (int i = 0; i < 16; ++i) s += xq[g * 16 + i]; bs[g] = s; }
+}
+
+/* Y[t][r] = W[r] . X[t]  for t < T (X: [T][cols], Y: [T][rows]) */
+static void matmat(const mat_t* w, const float* X, int T, float* Y, int8_t* xq, float* xs, int* bs) {
+    const int cols = w->cols, quant = (w->type == T_Q4_K || w->type == T_Q6_K || w->type == T_Q8_0);
+    const int blk = w->type == T_Q8_0 ? 32 : 256, nxs = cols / 32 + 1, nbs = cols / 16 + 1;
+    if (quant) {
+#pragma omp parallel for schedule(static)
+        for (int t = 0; t < T; ++t) quant_act_into(X + (size_t)t * cols, cols, blk, xq + (size_t)t * cols, xs + (size_t)t * nxs, bs + (size_t)t * nbs);
+    }
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < w->rows; ++r) {
+        const uint8_t* row = w->data + (size_t)r * w->row_bytes;
+        for (int t = 0; t < T; ++t)
+            Y[(size_t)t * w->rows + r] = row_dot_q8(row, w->type, cols, xq + (size_t)t * cols, xs + (size_t)t * nxs, bs + (size_t)t * nbs, X + (size_t)t * cols);
+    }
+}
+
+/* n prompt tokens from the model's current position; logits (may be NULL) of the LAST one.  mode must be 1. */
+int oc_prefill(void* vm, const int* ids, int n, int mode, float* logits) {
+    model_t* m = vm;
+    if (mode != 1 || n <= 0 || m->pos + n > m->n_ctx) return -1;
+    const int E = m->n_embd, H = m->n_head, KV = m->n_kv, hd = m->hd, kvd = KV * hd, qd = H * hd, grp = H / KV, FF = m->n_ff, pos0 = m->pos;
+    for (int t = 0; t < n; ++t) if (ids[t] < 0 || ids[t] >= m->n_vocab) return -1;
+    int big = FF > E ? FF : E; if (qd > big) big = qd;
+    float* X = malloc((size_t)n * E * 4); float* XN = malloc((size_t)n * big * 4); float* Q = malloc((size_t)n * qd * 4);
+    float* K = malloc((size_t)n * kvd * 4); float* V = malloc((size_t)n * kvd * 4); float* A = malloc((size_t)n * qd * 4);
+    float* G = malloc((size_t)n * FF * 4); float* U = malloc((size_t)n * FF * 4); float* Y = malloc((size_t)n * big * 4);
+    int8_t* xq = malloc((size_t)n * big + 64); float* xs = malloc((size_t)n * (big / 32 + 1) * 4); int* bs = malloc((size_t)n * (big / 16 + 1) * 4);
+    float* SC = malloc((size_t)H * m->n_ctx * 4);
+    for (int t = 0; t < n; ++t) dequant_row(m->tok_embd.data + (size_t)ids[t] * m->tok_embd.row_bytes, m->tok_embd.type, E, X + (size_t)t * E);
+    const float scale = 1.0f / sqrtf((float)hd);
+    for (int il = 0; il < m->n_layer; ++il) {
+        layer_t* L = &m->layers[il];
+        for (int t = 0; t < n; ++t) rmsnorm(X + (size_t)t * E, L->attn_norm, E, m->eps, XN + (size_t)t * E);
+        matmat(&L->wq, XN, n, Q, xq, xs, bs);
+        matmat(&L->wk, XN, n, K, xq, xs, bs);
+        matmat(&L->wv, XN, n, V, xq, xs, bs);
+        float* kc = m->kc + ((size_t)il * m->n_ctx) * kvd; float* vc = m->vc + ((size_t)il * m->n_ctx) * kvd;
+        for (int t = 0; t < n; ++t) {
+            const int pos = pos0 + t;
+            const float* c = m->cos_t + (size_t)pos * hd / 2; const float* s = m->sin_t + (size_t)pos * hd / 2;
+            rope(Q + (size_t)t * qd, H, hd, c, s);
+            rope(K + (size_t)t * kvd, KV, hd, c, s);
+            for (int i = 0; i < kvd; ++i) { kc[(size_t)pos * kvd + i] = f16_round(K[(size_t)t * kvd + i]); vc[(size_t)pos * kvd + i] = f16_round(V[(size_t)t * kvd + i]); }
+        }
+        for (int t = 0; t < n; ++t) {
+            const int pos = pos0 + t;
+#pragma omp parallel for schedule(static)
+            for (int h = 0; h < H; ++h) {
+                const int kvh = h / grp;
+                float* sc = SC + (size_t)h * m->n_ctx;
+                const float* q = Q + (size_t)t * qd + h * hd;
+                float mx = -INFINITY;
+                for (int p = 0; p <= pos; ++p) {
+                    const float* kr = kc + (size_t)p * kvd + kvh * hd; double a = 0;
+                    for (int d = 0; d < hd; ++d) a += (double)q[d] * kr[d];
+                    sc[p] = (float)a * scale; if (sc[p] > mx) mx = sc[p];
+                }
+                double den = 0; for (int p = 0; p <= pos; ++p) { sc[p] = expf(sc[p] - mx); den += sc[p]; }
+                for (int d = 0; d < hd; ++d) {
+                    double a = 0; for (int p = 0; p <= pos; ++p) a += (double)sc[p] * vc[(size_t)p * kvd + kvh * hd + d];
+                    A[(size_t)t * qd + h * hd + d] = (float)(a / den);
+                }
+            }
+        }
+        matmat(&L->wo, A, n, Y, xq, xs, bs);
+        for (size_t i = 0; i < (size_t)n * E; ++i) X[i] += Y[i];
+        for (int t = 0; t < n; ++t) rmsnorm(X + (size_t)t * E, L->ffn_norm, E, m->eps, XN + (size_t)t * E);
+        matmat(&L->wg, XN, n, G, xq, xs, bs);
+        matmat(&L->wu, XN, n, U, xq, xs, bs);
+        for (size_t i = 0; i < (size_t)n * FF; ++i) G[i] = (G[i] / (1.0f + expf(-G[i]))) * U[i];
+        matmat(&L->wd, G, n, Y, xq, xs, bs);
+        for (size_t i = 0; i < (size_t)n * E; ++i) X[i] += Y[i];
+    }
+    if (logits) {
+        rmsnorm(X + (size_t)(n - 1) * E, m->output_norm, E, m->eps, m->xn);
+        matvec(m, &m->output, m->xn, logits, 1);
+    }
+    m->pos += n;
+    free(X); free(XN); free(Q); free(K); free(V); free(A); free(G); free(U); free(Y); free(xq); free(xs); free(bs); free(SC);
+    return 0;
+}
+
+/* Synthetic KV prefix: positions [0, n_pos) of every layer get small pseudo-random fp16-rounded values and the model's
+ * position is set to n_pos.  bench.py uses it so that a bounded CPU sample decodes at the same context length as the tail
+ * of the real 512-in / 128-out request without paying for the prompt first (timing only: the values mean nothing). */
+int oc_fill_kv(void* vm, int n_pos, unsigned seed) {
+    model_t* m = vm;
+    if (n_pos < 0 || n_pos > m->n_ctx) return -1;
+    const size_t kvd = (size_t)m->n_kv * m->hd;
+    unsigned long long st = 0x9E3779B97F4A7C15ull ^ seed;
+    for (int il = 0; il < m->n_layer; ++il) {
+        float* kc = m->kc + ((size_t)il * m->n_ctx) * kvd; float* vc = m->vc + ((size_t)il * m->n_ctx) * kvd;
+        for (size_t i = 0; i < (size_t)n_pos * kvd; ++i) {
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            const float a = (float)((int)((st >> 33) & 0xFFFF) - 32768) * (1.0f / 32768.0f);
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            const float b = (float)((int)((st >> 33) & 0xFFFF) - 32768) * (1.0f / 32768.0f);
+            kc[i] = f16_round(a); vc[i] = f16_round(b);
+        }
+    }
+    m->pos = n_pos;
+    return 0;
+}
+
 /* greedy generate; returns number generated.  logits_buf must hold n_vocab floats. */
 int oc_generate(void* vm, const int* prompt, int n_prompt, int n_predict, int mode, int* out_ids, float* out_lp, float* logits_buf) {
     model_t* m = vm;

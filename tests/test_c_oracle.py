@@ -66,3 +66,28 @@ def test_c_generate_matches_oracle_ids(oc, tiny_gguf):
             break
         assert abs(lps[i] - ref["logprobs"][i]) < 1e-3
     oc.oc_free(h)
+
+
+def test_batched_prefill_equals_token_by_token(oc, tiny128_gguf):
+    """oc_prefill (what bench.py's reference arm times for the prompt phase: one pass over the weights for T tokens) computes
+    exactly what T calls of oc_step compute; oc_fill_kv moves the position without touching the arithmetic."""
+    from oracle import llama_oracle as O
+    om = O.load_gguf(tiny128_gguf)
+    oc.oc_prefill.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    oc.oc_fill_kv.argtypes = [C.c_void_p, C.c_int, C.c_uint]
+    h = oc.oc_load(tiny128_gguf.encode(), 128)
+    toks = np.random.Generator(np.random.PCG64(8)).integers(0, om.n_vocab - 3, size=37).astype(np.int32)
+    a = np.zeros(om.n_vocab, np.float32)
+    b = np.zeros(om.n_vocab, np.float32)
+    for t in toks[:5]:
+        oc.oc_step(h, int(t), 1, None, None)
+    assert oc.oc_prefill(h, toks[5:].ctypes.data_as(C.c_void_p), 32, 1, a.ctypes.data_as(C.c_void_p)) == 0
+    assert oc.oc_step(h, 3, 1, a.ctypes.data_as(C.c_void_p), None) == 0          # decode continues on the KV the prefill wrote
+    oc.oc_reset(h)
+    for t in toks:
+        oc.oc_step(h, int(t), 1, b.ctypes.data_as(C.c_void_p), None)
+    assert oc.oc_step(h, 3, 1, b.ctypes.data_as(C.c_void_p), None) == 0
+    assert np.array_equal(a, b)
+    assert oc.oc_fill_kv(h, 64, 1) == 0 and oc.oc_step(h, 3, 1, a.ctypes.data_as(C.c_void_p), None) == 0 and np.isfinite(a).all()
+    assert oc.oc_prefill(h, toks.ctypes.data_as(C.c_void_p), 37, 0, None) == -1     # exact mode is not batched
+    oc.oc_free(h)
