@@ -261,6 +261,11 @@ def main():
     ap.add_argument("--batch-weights", type=int, default=0, help="config3: 0 auto, 1 resident 16-bit weights, 2 quantised weights")
     args = ap.parse_args()
     wl = args.workload
+    # a stall must leave evidence: every thread's stack goes to stderr if the run makes no visible progress for a while
+    import faulthandler
+    faulthandler.enable()
+    if os.environ.get("GL_BENCH_WATCHDOG", "1") != "0":
+        faulthandler.dump_traceback_later(int(os.environ.get("GL_BENCH_WATCHDOG_S", "240")), repeat=True, file=sys.stderr)
     if args.steps is None:
         args.steps = {"config2": 4, "config3": 2, "config4": 2, "config5": 1}[wl]
 
@@ -513,6 +518,7 @@ def run_config3(args, N, path, rank, local_rank, world, dist, timed, peaks, extr
     for s in svcs:
         s.preload()
     engines = [s._engine(name) for s in svcs]
+    log(f"[bench] config3: {n_local} engine(s) loaded, batch {B}")
 
     def make_jobs(step_tag, n_req):
         jobs = []
@@ -551,7 +557,8 @@ def run_config3(args, N, path, rank, local_rank, world, dist, timed, peaks, extr
 
     loop = asyncio.new_event_loop()
     for w in range(min(args.warmup, 1) + 0):                          # one warm pass captures the graphs of every bucket it meets
-        loop.run_until_complete(run_step(1000 + w, 0.0))
+        r = loop.run_until_complete(run_step(1000 + w, 0.0))
+        log(f"[bench] config3 warm pass: {r['ok']}/{r['n']} requests in {r['wall']:.2f} s, counters {engines[0].batch_counters()}")
     for e in engines:
         e.batch_counters(reset=True)
 
@@ -559,6 +566,7 @@ def run_config3(args, N, path, rank, local_rank, world, dist, timed, peaks, extr
         res = []
         for i in range(args.steps):
             res.append(loop.run_until_complete(run_step(i, 0.0)))
+            log(f"[bench] config3 step {i}: {res[-1]['ok']}/{res[-1]['n']} requests in {res[-1]['wall']:.2f} s")
         return res
     res, clocks = timed(region)
     ctr = [e.batch_counters(reset=True) for e in engines]
@@ -571,6 +579,7 @@ def run_config3(args, N, path, rank, local_rank, world, dist, timed, peaks, extr
     agg = multirank.aggregate_throughput(gen_tokens, dev_s, wall_s, dist)
     # the same workload once more with the reference's 1 s dispatch tick (JobScheduler.ts:128-135), reported beside the headline
     tick1 = loop.run_until_complete(run_step(500, 1.0))
+    log(f"[bench] config3 1 s-tick pass: {tick1['wall']:.2f} s, {tick1['ticks']} ticks")
     for e in engines:
         e.batch_counters(reset=True)
     # roofline of the batched step: weights are read once per step for all B sequences

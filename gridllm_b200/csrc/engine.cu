@@ -934,67 +934,114 @@ Status Engine::prefill(const int32_t* ids, int n, float* last_logits) {
     return {};
 }
 
+// generateEmbedding (/root/reference/client/src/services/OllamaService.ts:601-665; the batched form is `input: string[]` of
+// /api/embed, server/src/routes/ollama.ts:574-643): prompt pass only -> output_norm -> mean over positions -> L2 normalise.
+// The sequences of a call are PACKED: up to EMB_PACK_TOKENS rows share one pass over the layers (engine_prefill.cu
+// prefill_packed), each sequence attending only to itself.  No allocation per call (buffers grow on demand and stay), the
+// device time in the stats is bracketed by events around device work only.
 Status Engine::embed(const int32_t* ids, const int32_t* offs, int n_seq, float* out, gl_gen_stats* stats) {
     CU(cudaSetDevice(device_));
     const int64_t t0 = now_ns();
-    int total = 0, launches = 0;
-    // pooling runs on the device (misc.cu): hidden rows -> output_norm -> mean over positions -> L2 normalise
-    int max_n = 0;
-    for (int sidx = 0; sidx < n_seq; ++sidx) max_n = std::max(max_n, offs[sidx + 1] - offs[sidx]);
-    if (max_n <= 0) return fail(GL_ERR_INVALID, "empty sequence in gl_embed");
-    float *d_rows = nullptr, *d_rstd = nullptr, *d_pooled = nullptr, *d_out = nullptr;
-    auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_rstd); cudaFree(d_pooled); cudaFree(d_out); };
-    cudaError_t ae = cudaMalloc((void**)&d_rstd, (size_t)max_n * 4);
-    if (ae == cudaSuccess) ae = cudaMalloc((void**)&d_pooled, (size_t)n_embd_ * 4);
-    if (ae == cudaSuccess) ae = cudaMalloc((void**)&d_out, (size_t)n_seq * n_embd_ * 4);
-    if (ae != cudaSuccess) { cleanup(); CU(ae); }
-    CU(cudaEventRecord(ev_[0], stream_));
+    int total = 0, launches = 0, max_n = 0;
     for (int sidx = 0; sidx < n_seq; ++sidx) {
         const int n = offs[sidx + 1] - offs[sidx];
-        if (n <= 0) { cleanup(); return fail(GL_ERR_INVALID, "empty sequence in gl_embed"); }
-        const int32_t* sid = ids + offs[sidx];
+        if (n <= 0) return fail(GL_ERR_INVALID, "empty sequence in gl_embed");
+        if (n > n_ctx_) return fail(GL_ERR_CONTEXT, "sequence of " + std::to_string(n) + " tokens exceeds the engine context " + std::to_string(n_ctx_));
         for (int i = 0; i < n; ++i)
-            if (sid[i] < 0 || sid[i] >= n_vocab_) { cleanup(); return fail(GL_ERR_INVALID, "token id out of range"); }
-        Status st = kv_reset();
-        if (st.ok()) st = ensure_pages(n);
-        if (!st.ok()) { cleanup(); return st; }
-        cudaMemcpyAsync(prompt_ids_, sid, (size_t)n * 4, cudaMemcpyHostToDevice, stream_);
-        gl_sample_opts so{};
-        so.ignore_eos = 1;
-        st = set_state(0, sid[0], n, 0, &so);
-        if (!st.ok()) { cleanup(); return st; }
-        const float* rows = nullptr;
-        if (can_batch_prefill(n)) {
-            int nl = 0;
-            st = prefill_batched(n, &nl);
-            if (!st.ok()) { cleanup(); return st; }
-            launches += nl;
-            rows = pf_x_;                              // [n x n_embd] hidden states of the whole prompt
-        } else {
-            // sequential prefill through the decode kernels: keep every position's hidden state
-            if (!d_rows) {
-                ae = cudaMalloc((void**)&d_rows, (size_t)max_n * n_embd_ * 4);
-                if (ae != cudaSuccess) { cleanup(); CU(ae); }
+            if (ids[offs[sidx] + i] < 0 || ids[offs[sidx] + i] >= n_vocab_) return fail(GL_ERR_INVALID, "token id out of range");
+        max_n = std::max(max_n, n);
+        total += n;
+    }
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) allocs_.push_back(*p);
+        return e;
+    };
+    if (!pk_ids_) {
+        CU(dalloc((void**)&pk_ids_, (size_t)EMB_PACK_TOKENS * 4));
+        CU(dalloc((void**)&emb_pooled_, (size_t)n_embd_ * 4));
+        CU(dalloc((void**)&emb_rstd_, (size_t)std::max(EMB_PACK_TOKENS, n_ctx_) * 4));
+    }
+    if (n_seq > emb_out_cap_) {                            // grows, never shrinks; the old buffer stays in allocs_ until the engine goes
+        CU(cudaStreamSynchronize(stream_));
+        CU(dalloc((void**)&emb_out_, (size_t)n_seq * n_embd_ * 4));
+        emb_out_cap_ = n_seq;
+    }
+    const bool packed = have_w16_ && prefill_mode_ != 1;
+    float* d_rows = nullptr;                               // sequential path only
+    CU(cudaEventRecord(ev_[0], stream_));
+    if (packed) {
+        // greedy packing in call order; every sequence starts on a 128-row boundary (pad rows hold token 0 and are never read back)
+        int sidx = 0;
+        std::vector<int32_t> h_ids(EMB_PACK_TOKENS);
+        while (sidx < n_seq) {
+            std::vector<int> starts, lens, which;
+            int rows = 0;
+            std::fill(h_ids.begin(), h_ids.end(), 0);
+            while (sidx < n_seq) {
+                const int n = offs[sidx + 1] - offs[sidx], lp = (n + 127) / 128 * 128;
+                if (n > EMB_PACK_TOKENS) break;            // longer than a pack: handled alone below
+                if (rows + lp > EMB_PACK_TOKENS) break;
+                starts.push_back(rows); lens.push_back(n); which.push_back(sidx);
+                std::memcpy(h_ids.data() + rows, ids + offs[sidx], (size_t)n * 4);
+                rows += lp;
+                ++sidx;
             }
-            for (int i = 0; i < n; ++i) {
+            if (starts.empty()) {                          // one sequence longer than a pack: the single-sequence batched pass
+                const int n = offs[sidx + 1] - offs[sidx];
+                ST(kv_reset());
+                ST(ensure_pages(n));
+                CU(cudaMemcpyAsync(prompt_ids_, ids + offs[sidx], (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+                gl_sample_opts so{};
+                so.ignore_eos = 1;
+                ST(set_state(0, ids[offs[sidx]], n, 0, &so));
+                if (!can_batch_prefill(n)) return fail(GL_ERR_CONTEXT, "sequence too long for the batched prompt pass");
+                ST(prefill_batched(n, &launches));
+                CU(pool_embedding_launch(pf_x_, n, n_embd_, output_norm_, eps_, emb_rstd_, emb_pooled_, emb_out_ + (size_t)sidx * n_embd_, stream_));
+                launches += 3;
+                ++sidx;
+                continue;
+            }
+            CU(cudaMemcpyAsync(pk_ids_, h_ids.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, stream_));      // pageable source: staged before return
+            ST(prefill_packed(starts, lens, rows, &launches));
+            for (size_t i = 0; i < starts.size(); ++i) {
+                CU(pool_embedding_launch(pf_x_ + (size_t)starts[i] * n_embd_, lens[i], n_embd_, output_norm_, eps_, emb_rstd_, emb_pooled_,
+                                         emb_out_ + (size_t)which[i] * n_embd_, stream_));
+                launches += 3;
+            }
+        }
+    } else {
+        // no 16-bit copy (prefill_mode 1 / not enough HBM): every sequence steps through the decode kernels, hidden state kept per position
+        CU(cudaMalloc((void**)&d_rows, (size_t)max_n * n_embd_ * 4));
+        Status st;
+        for (int sidx = 0; sidx < n_seq && st.ok(); ++sidx) {
+            const int n = offs[sidx + 1] - offs[sidx];
+            const int32_t* sid = ids + offs[sidx];
+            st = kv_reset();
+            if (st.ok()) st = ensure_pages(n);
+            if (!st.ok()) break;
+            cudaMemcpyAsync(prompt_ids_, sid, (size_t)n * 4, cudaMemcpyHostToDevice, stream_);
+            gl_sample_opts so{};
+            so.ignore_eos = 1;
+            st = set_state(0, sid[0], n, 0, &so);
+            for (int i = 0; i < n && st.ok(); ++i) {
                 st = run_steps(1, 0, false);
-                if (!st.ok()) { cleanup(); return st; }
                 cudaMemcpyAsync(d_rows + (size_t)i * n_embd_, x_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToDevice, stream_);
             }
             launches += n * launches_nohead_;
-            rows = d_rows;
+            if (st.ok()) {
+                cudaError_t ae = pool_embedding_launch(d_rows, n, n_embd_, output_norm_, eps_, emb_rstd_, emb_pooled_, emb_out_ + (size_t)sidx * n_embd_, stream_);
+                if (ae != cudaSuccess) st = fail(GL_ERR_CUDA, cudaGetErrorString(ae));
+                launches += 3;
+            }
         }
-        ae = pool_embedding_launch(rows, n, n_embd_, output_norm_, eps_, d_rstd, d_pooled, d_out + (size_t)sidx * n_embd_, stream_);
-        if (ae != cudaSuccess) { cleanup(); CU(ae); }
-        launches += 3;
-        total += n;
+        if (!st.ok()) { cudaStreamSynchronize(stream_); cudaFree(d_rows); return st; }
     }
-    ae = cudaMemcpyAsync(out, d_out, (size_t)n_seq * n_embd_ * 4, cudaMemcpyDeviceToHost, stream_);
-    if (ae == cudaSuccess) ae = cudaStreamSynchronize(stream_);
-    cleanup();
-    CU(ae);
     CU(cudaEventRecord(ev_[1], stream_));
-    CU(cudaEventSynchronize(ev_[1]));
+    cudaError_t ae = cudaMemcpyAsync(out, emb_out_, (size_t)n_seq * n_embd_ * 4, cudaMemcpyDeviceToHost, stream_);
+    if (ae == cudaSuccess) ae = cudaStreamSynchronize(stream_);
+    if (d_rows) cudaFree(d_rows);
+    CU(ae);
     if (stats) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev_[0], ev_[1]);

@@ -14,6 +14,7 @@
 #include "kernels.h"
 #include "prefill.h"
 #include "batch.h"
+#include "qgemm.h"
 #include "decode_mega.h"
 #include "tokenizer.h"
 
@@ -62,7 +63,10 @@ public:
     Status seq_close(int slot);
     Status seq_logits(int slot, float* out, int n_vocab);
     Status seq_stats(int slot, gl_gen_stats* out) const;
-    void batch_counters(uint64_t out[8], bool reset) { for (int i = 0; i < 8; ++i) { out[i] = bc_[i]; if (reset) bc_[i] = 0; } }
+    void batch_counters(uint64_t out[8], bool reset) {
+        for (int i = 0; i < 8; ++i) { out[i] = bc_[i]; if (reset) bc_[i] = 0; }
+        out[7] = have_qg_ ? 2 : 1;                    // which weights the batched step reads (2: quantised, 1: 16-bit copy)
+    }
     Status time_batch_step(int batch, int ctx_len, int iters, float* ms, int* launches, uint64_t* wbytes);
     Status sample_logits(const float* logits, int n_vocab, const gl_sample_opts& so, int out_index, int* id, float* logprob);
     Status gemv_host(int type, const void* w_host, int rows, int cols, const float* x, float* y, int iters, float* ms);
@@ -95,6 +99,12 @@ private:
     Status launch_mega(int n_steps, bool with_head, bool keep_logits);
     Status ensure_prefill_scratch(int t_pad);
     Status prefill_batched(int n, int* n_launch);     // tokens already in prompt_ids_[0..n)
+    // embeddings: several sequences in ONE prompt pass (block-diagonal causal attention); seq s = rows [starts[s], starts[s] + lens[s])
+    Status prefill_packed(const std::vector<int>& starts, const std::vector<int>& lens, int t_rows, int* n_launch);
+    static constexpr int EMB_PACK_TOKENS = 2048;      // rows of one packed pass (each sequence starts on a 128-row boundary)
+    int* pk_ids_ = nullptr;                           // [EMB_PACK_TOKENS] token ids of a pack (pad rows: token 0)
+    float *emb_out_ = nullptr, *emb_rstd_ = nullptr, *emb_pooled_ = nullptr;
+    int emb_out_cap_ = 0;
     bool can_batch_prefill(int n) const { return have_w16_ && prefill_mode_ != 1 && host_pos_ == 0 && n >= prefill_min_ && n <= 4096; }
     const DevMatrix* find_matrix(const std::string& name) const;
 
@@ -203,6 +213,15 @@ private:
     unsigned* bcounters_ = nullptr;
     BatchOut* bout_ = nullptr;
     void* head16_ = nullptr;                          // [n_vocab x n_embd] fp16 copy of the lm_head (16-bit batched path)
+    // batched step on the QUANTISED weights (qgemm.cu): a second copy of the matrices in the QG qtile layout, same bytes as the GGUF
+    struct QLayer { QGemmWeights qkv, o, gu, down; };
+    std::vector<QLayer> qlayers_;
+    QGemmWeights qhead_;
+    float* qpartial_ = nullptr;
+    bool have_qg_ = false;
+    std::string qg_why_not_;                          // why the quantised path is unavailable for this model (message for batch_weights = 2)
+    Status build_qgemm_weights();
+    Status pack_qgemm(const std::vector<const GGUFTensor*>& src, int mode, QGemmWeights& out, uint8_t*& tmp, size_t& tmp_cap);
     cudaGraphExec_t g_batch_[N_BUCKETS] = {};
     int batch_launches_ = 0;                          // kernels of one batched step
     uint64_t bc_[8] = {};                             // gl_batch_counters

@@ -42,6 +42,90 @@ int attn_splits_for(int bucket, int n_kv) {
 }
 }  // namespace
 
+// One GEMM's weights -> QG qtile stream: the sources' native GGUF bytes go to the device as they are (mmap -> staging buffer),
+// the packer kernel (qgemm.cu) regroups the bits of every super-block into the qtile planes.
+Status Engine::pack_qgemm(const std::vector<const GGUFTensor*>& src, int mode, QGemmWeights& out, uint8_t*& tmp, size_t& tmp_cap) {
+    size_t total = 0;
+    int rows = 0;
+    for (const GGUFTensor* t : src) { total += t->nbytes; rows += (int)t->rows(); }
+    if (total + 256 > tmp_cap) {
+        if (tmp) cudaFree(tmp);
+        tmp = nullptr;
+        CU(cudaMalloc((void**)&tmp, total + 256));
+        tmp_cap = total + 256;
+    }
+    QGemmSource qs[3];
+    size_t off = 0;
+    for (size_t i = 0; i < src.size(); ++i) {
+        CU(cudaMemcpyAsync(tmp + off, src[i]->data, src[i]->nbytes, cudaMemcpyHostToDevice, stream_));
+        qs[i] = QGemmSource{tmp + off, (int)src[i]->type, (int)src[i]->rows()};
+        off += (src[i]->nbytes + 255) & ~(size_t)255;
+        if (off > tmp_cap) return failb(GL_ERR_NOMEM, "qgemm staging overflow");
+    }
+    const int k = (int)src[0]->cols();
+    out.n = rows; out.k = k; out.nkb = k / 256; out.n_tiles = rows / 128; out.bytes = total;
+    CU(cudaMalloc((void**)&out.w, total + 256));
+    allocs_.push_back(out.w);
+    std::vector<uint64_t> toff(out.n_tiles);
+    std::vector<uint8_t> ttype(out.n_tiles);
+    CU(qgemm_pack_launch(qs, (int)src.size(), mode, k, out.w, toff.data(), ttype.data(), stream_));
+    CU(cudaMalloc((void**)&out.tile_off, (size_t)out.n_tiles * 8));
+    allocs_.push_back(out.tile_off);
+    CU(cudaMalloc((void**)&out.tile_type, (size_t)out.n_tiles + 16));
+    allocs_.push_back(out.tile_type);
+    CU(cudaMalloc((void**)&out.counters, (size_t)out.n_tiles * 4));
+    allocs_.push_back(out.counters);
+    CU(cudaMemcpy(out.tile_off, toff.data(), (size_t)out.n_tiles * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(out.tile_type, ttype.data(), (size_t)out.n_tiles, cudaMemcpyHostToDevice));
+    CU(cudaMemset(out.counters, 0, (size_t)out.n_tiles * 4));
+    return {};
+}
+
+// The second copy of the weights for the batched step on quantised weights: same bytes as the GGUF (4.6 GB for Llama-3-8B
+// q4_K_M), QG layout.  Only for models whose matrices are all Q4_K / Q6_K with 128-row / 256-column granularity; anything else
+// keeps the 16-bit path (have_qg_ stays false, qg_why_not_ says why).
+Status Engine::build_qgemm_weights() {
+    have_qg_ = false;
+    const int qd = n_head_ * hd_, kvd = n_kv_ * hd_;
+    auto ok_t = [](const GGUFTensor* t) { return t && (t->type == T_Q4_K || t->type == T_Q6_K); };
+    if (n_embd_ % 256 || n_ff_ % 256 || qd % 256) { qg_why_not_ = "widths must be multiples of 256"; return {}; }
+    if (qd % 128 || kvd % 128 || n_embd_ % 128 || n_ff_ % 64 || n_vocab_ % 128) { qg_why_not_ = "matrix heights must be multiples of 128"; return {}; }
+    const GGUFTensor* tout = gguf_.tensor("output.weight");
+    if (!tout) tout = gguf_.tensor("token_embd.weight");
+    if (!ok_t(tout)) { qg_why_not_ = "output.weight is not Q4_K / Q6_K"; return {}; }
+    std::vector<std::vector<const GGUFTensor*>> per_layer;
+    for (int il = 0; il < n_layer_; ++il) {
+        const std::string p = "blk." + std::to_string(il) + ".";
+        std::vector<const GGUFTensor*> t;
+        for (const char* n : {"attn_q.weight", "attn_k.weight", "attn_v.weight", "attn_output.weight", "ffn_gate.weight", "ffn_up.weight", "ffn_down.weight"}) {
+            const GGUFTensor* x = gguf_.tensor(p + n);
+            if (!ok_t(x)) { qg_why_not_ = "tensor " + p + n + " is not Q4_K / Q6_K"; return {}; }
+            t.push_back(x);
+        }
+        if (t[4]->type != t[5]->type) { qg_why_not_ = "ffn_gate / ffn_up of different types"; return {}; }
+        per_layer.push_back(t);
+    }
+    CU(qgemm_configure());
+    uint8_t* tmp = nullptr;
+    size_t tmp_cap = 0;
+    qlayers_.assign(n_layer_, QLayer{});
+    Status st;
+    for (int il = 0; il < n_layer_ && st.ok(); ++il) {
+        const auto& t = per_layer[il];
+        st = pack_qgemm({t[0], t[1], t[2]}, 0, qlayers_[il].qkv, tmp, tmp_cap);
+        if (st.ok()) st = pack_qgemm({t[3]}, 0, qlayers_[il].o, tmp, tmp_cap);
+        if (st.ok()) st = pack_qgemm({t[4], t[5]}, 1, qlayers_[il].gu, tmp, tmp_cap);
+        if (st.ok()) st = pack_qgemm({t[6]}, 0, qlayers_[il].down, tmp, tmp_cap);
+    }
+    if (st.ok()) st = pack_qgemm({tout}, 0, qhead_, tmp, tmp_cap);
+    if (tmp) cudaFree(tmp);
+    ST(st);
+    CU(cudaMalloc((void**)&qpartial_, qgemm_partial_floats(64) * 4));
+    allocs_.push_back(qpartial_);
+    have_qg_ = true;
+    return {};
+}
+
 Status Engine::ensure_batch_state() {
     if (batch_ready_) return {};
     if (bst_) return failb(GL_ERR_CUDA, "continuous batching: an earlier initialisation failed on this engine");
@@ -78,6 +162,11 @@ Status Engine::ensure_batch_state() {
                            stream_));
     CU(dalloc((void**)&bst_, sizeof(StepState) * R));
     CU(cudaStreamSynchronize(stream_));
+    if (batch_weights_ != 1) {
+        ST(build_qgemm_weights());
+        if (!have_qg_ && batch_weights_ == 2)
+            return failb(GL_ERR_UNSUPPORTED, "batch_weights = 2 (quantised weights) is not available for this model: " + qg_why_not_);
+    }
     slots_.assign(MAX_BATCH, SeqSlot{});
     last_rows_.clear();
     last_bucket_ = 0;
@@ -201,7 +290,15 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
     const int qd = n_head_ * hd_, kvd = n_kv_ * hd_, ldq = qd + 2 * kvd;
     const float scale = 1.0f / std::sqrt((float)hd_);
     int nl = 0;
-    auto linear = [&](const void* a, const void* w, void* c, int n, int k, int ldc, int epi) -> cudaError_t {
+    // the GEMMs read the QUANTISED weights (4.5 / 6.56 bits per weight, unpacked inside the kernel) for up to 64 rows; the
+    // resident 16-bit copy otherwise (models with other tensor types, or 65..128 rows, where the step is tensor-bound anyway)
+    const bool use_q = have_qg_ && bucket <= 64;
+    const int nb = std::max(16, bucket);
+    auto linear = [&](const void* a, const void* w, void* c, int n, int k, int ldc, int epi, const QGemmWeights* qw) -> cudaError_t {
+        if (use_q) {
+            ++nl;
+            return qgemm_launch(*qw, (const __half*)a, MAX_BATCH, nb, c, ldc, epi, qpartial_, sm_count_, s);
+        }
         GemmParams g{};
         g.a = a; g.b = w; g.c = c; g.m = bucket; g.n = n; g.k = k; g.lda = k; g.ldb = k; g.ldc = ldc;
         g.batch = 1; g.b_batch_div = 1; g.epi = epi;
@@ -216,20 +313,20 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         CU(batch_rmsnorm_launch(bx_, L.attn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
-        CU(linear(bxn16_, L.wqkv16, bqkv_, ldq, n_embd_, ldq, GEMM_EPI_F32));
+        CU(linear(bxn16_, L.wqkv16, bqkv_, ldq, n_embd_, ldq, GEMM_EPI_F32, use_q ? &qlayers_[il].qkv : nullptr));
         CU(batch_rope_kv_launch(bqkv_, bucket, bctl_, bst_, btables_, n_pages_, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, bq_, kc, vc, s)); ++nl;
         BatchAttnParams a{};
         a.q = bq_; a.k_cache = kc; a.v_cache = vc; a.tables = btables_; a.table_stride = n_pages_; a.st = bst_; a.ctl = bctl_;
         a.out16 = battn16_; a.part_o = bpart_o_; a.part_ml = bpart_ml_; a.counters = bcounters_;
         a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = splits; a.scale = scale;
         CU(batch_attn_launch(a, bucket, s)); ++nl;
-        CU(linear(battn16_, L.wo16, bx_, n_embd_, qd, n_embd_, GEMM_EPI_ADD_F32));
+        CU(linear(battn16_, L.wo16, bx_, n_embd_, qd, n_embd_, GEMM_EPI_ADD_F32, use_q ? &qlayers_[il].o : nullptr));
         CU(batch_rmsnorm_launch(bx_, L.ffn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
-        CU(linear(bxn16_, L.wgu16, bh16_, 2 * n_ff_, n_embd_, n_ff_, GEMM_EPI_SILU));
-        CU(linear(bh16_, L.wd16, bx_, n_embd_, n_ff_, n_embd_, GEMM_EPI_ADD_F32));
+        CU(linear(bxn16_, L.wgu16, bh16_, 2 * n_ff_, n_embd_, n_ff_, GEMM_EPI_SILU, use_q ? &qlayers_[il].gu : nullptr));
+        CU(linear(bh16_, L.wd16, bx_, n_embd_, n_ff_, n_embd_, GEMM_EPI_ADD_F32, use_q ? &qlayers_[il].down : nullptr));
     }
     CU(batch_rmsnorm_launch(bx_, output_norm_, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
-    CU(linear(bxn16_, head16_, blogits_, n_vocab_, n_embd_, n_vocab_, GEMM_EPI_F32));
+    CU(linear(bxn16_, head16_, blogits_, n_vocab_, n_embd_, n_vocab_, GEMM_EPI_F32, use_q ? &qhead_ : nullptr));
     CU(batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, s)); ++nl;
     if (n_launch) *n_launch = nl;
     return {};
@@ -400,10 +497,12 @@ Status Engine::time_batch_step(int batch, int ctx_len, int iters, float* ms, int
     if (ms) *ms = t_ms / iters;
     if (launches) *launches = batch_launches_;
     if (wbytes) {
-        // bytes of weights one batched step reads: the resident 16-bit matrices of every layer + the 16-bit lm_head + norms
+        // bytes of weights one batched step reads: the quantised matrices (= the GGUF bytes), or the resident 16-bit matrices of
+        // every layer + the 16-bit lm_head + norms
         const uint64_t per_layer = ((uint64_t)(n_head_ * hd_ + 2 * n_kv_ * hd_) * n_embd_ + (uint64_t)n_embd_ * n_head_ * hd_ +
                                     (uint64_t)2 * n_ff_ * n_embd_ + (uint64_t)n_embd_ * n_ff_) * 2;
-        *wbytes = per_layer * n_layer_ + (uint64_t)n_vocab_ * n_embd_ * 2 + (uint64_t)(2 * n_layer_ + 1) * n_embd_ * 4;
+        *wbytes = (have_qg_ && bucket <= 64) ? decode_bytes_
+                                             : per_layer * n_layer_ + (uint64_t)n_vocab_ * n_embd_ * 2 + (uint64_t)(2 * n_layer_ + 1) * n_embd_ * 4;
     }
     return {};
 }

@@ -112,7 +112,7 @@ Status Engine::prefill_batched(int n, int* n_launch) {
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
             CU(linear(g)); ++nl;
         }
-        CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, s)); ++nl;
+        CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, tp, s)); ++nl;
         {   // S[h] = Q_h K_kvh^T
             GemmParams g{};
             g.a = pf_q_; g.b = pf_k_; g.c = pf_s_; g.m = T; g.n = T; g.k = hd_; g.lda = qd; g.ldb = kvd; g.ldc = tp;
@@ -152,6 +152,79 @@ Status Engine::prefill_batched(int n, int* n_launch) {
     CU(cudaMemcpyAsync(x_, pf_x_ + (size_t)(T - 1) * n_embd_, (size_t)n_embd_ * 4, cudaMemcpyDeviceToDevice, s));
     if (n_launch) *n_launch += nl;
     last_prefill_launches_ = nl;
+    return {};
+}
+
+// Packed prompt pass for embeddings (generateEmbedding with `input: string[]`, /root/reference/server/src/routes/ollama.ts:574-643 ->
+// client/src/services/OllamaService.ts:619-636): the sequences of a call share the linear layers -- one [T x n_embd] activation
+// matrix, T = all their tokens, every weight matrix read once per PACK instead of once per sequence -- and attend only inside
+// themselves (block-diagonal causal attention: the three attention launches run per sequence on its own rows).  Nothing is
+// cached: an embedding has no decode phase.  Hidden states end up in pf_x_ for pooling.
+Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<int>& lens, int t_rows, int* n_launch) {
+    const int TP = (t_rows + 127) / 128 * 128;
+    const int qd = n_head_ * hd_, kvd = n_kv_ * hd_, ldq = qd + 2 * kvd, grp = n_head_ / n_kv_;
+    ST(ensure_prefill_scratch(std::max(TP, 128)));
+    const int tp = pf_cap_;
+    cudaStream_t s = stream_;
+    const bool bf = prefill_bf16_;
+    int nl = 0;
+    auto linear = [&](const GemmParams& g) -> cudaError_t {
+        if (prefill_tc5_ && gemm_tc5_supported(g)) return gemm_tc5_launch(g, tp, bf, s);
+        return gemm_tn_launch(g, bf, s);
+    };
+    CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, pk_ids_, TP, pf_x_, s)); ++nl;
+    const float scale = 1.0f / std::sqrt((float)hd_);
+    for (int il = 0; il < n_layer_; ++il) {
+        const LayerWeights& L = layers_[il];
+        CU(rmsnorm_rows_launch(pf_x_, L.attn_norm, TP, TP, n_embd_, eps_, pf_xn_, bf, s)); ++nl;
+        {
+            GemmParams g{};
+            g.a = pf_xn_; g.b = L.wqkv16; g.c = pf_qkv_; g.m = TP; g.n = ldq; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = ldq;
+            g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
+            CU(linear(g)); ++nl;
+        }
+        for (size_t i = 0; i < starts.size(); ++i) {
+            const int r0 = starts[i], len = lens[i], lp = (len + 127) / 128 * 128;
+            // RoPE at positions 0..len-1 of THIS sequence; V^T columns r0.. of the pack-wide [kvd][tp] matrix; no cache
+            CU(rope_split_launch(pf_qkv_ + (size_t)r0 * ldq, len, lp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_ + (size_t)r0 * qd,
+                                 pf_k_ + (size_t)r0 * kvd, pf_vt_ + r0, nullptr, nullptr, nullptr, tp, s)); ++nl;
+            {   // S[h] = Q_h K_kvh^T, compact [n_head][lp][lp]
+                GemmParams g{};
+                g.a = pf_q_ + (size_t)r0 * qd; g.b = pf_k_ + (size_t)r0 * kvd; g.c = pf_s_; g.m = len; g.n = len; g.k = hd_; g.lda = qd; g.ldb = kvd; g.ldc = lp;
+                g.batch = n_head_; g.a_batch_stride = hd_; g.b_batch_stride = hd_; g.b_batch_div = grp; g.c_batch_stride = (long long)lp * lp;
+                g.epi = GEMM_EPI_F32; g.causal_skip = 1;
+                CU(gemm_tn_launch(g, false, s)); ++nl;
+            }
+            CU(softmax_causal_launch(pf_s_, n_head_, len, lp, scale, pf_p_, s)); ++nl;
+            {   // O[:, h] = P[h] V_kvh
+                GemmParams g{};
+                g.a = pf_p_; g.b = pf_vt_ + r0; g.c = (__half*)pf_attn_ + (size_t)r0 * qd; g.m = len; g.n = hd_; g.k = lp; g.lda = lp; g.ldb = tp; g.ldc = qd;
+                g.batch = n_head_; g.a_batch_stride = (long long)lp * lp; g.b_batch_stride = (long long)hd_ * tp; g.b_batch_div = grp; g.c_batch_stride = hd_;
+                g.epi = GEMM_EPI_T16; g.causal_k = 1;
+                CU(gemm_tn_launch(g, false, s)); ++nl;
+            }
+        }
+        {
+            GemmParams g{};
+            g.a = pf_attn_; g.b = L.wo16; g.c = pf_x_; g.m = TP; g.n = n_embd_; g.k = qd; g.lda = qd; g.ldb = qd; g.ldc = n_embd_;
+            g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_ADD_F32;
+            CU(linear(g)); ++nl;
+        }
+        CU(rmsnorm_rows_launch(pf_x_, L.ffn_norm, TP, TP, n_embd_, eps_, pf_xn_, bf, s)); ++nl;
+        {
+            GemmParams g{};
+            g.a = pf_xn_; g.b = L.wgu16; g.c = pf_h_; g.m = TP; g.n = 2 * n_ff_; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = n_ff_;
+            g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_SILU;
+            CU(linear(g)); ++nl;
+        }
+        {
+            GemmParams g{};
+            g.a = pf_h_; g.b = L.wd16; g.c = pf_x_; g.m = TP; g.n = n_embd_; g.k = n_ff_; g.lda = n_ff_; g.ldb = n_ff_; g.ldc = n_embd_;
+            g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_ADD_F32;
+            CU(linear(g)); ++nl;
+        }
+    }
+    if (n_launch) *n_launch += nl;
     return {};
 }
 

@@ -243,17 +243,19 @@ template <typename T>
 __global__ void __launch_bounds__(256) rope_split_kernel(const float* __restrict__ qkv, int t_rows, int t_pad, int pos0, int n_head, int n_kv, int hd,
                                                          const float* __restrict__ cos_t, const float* __restrict__ sin_t, T* __restrict__ qo,
                                                          T* __restrict__ ko, T* __restrict__ vt, __half* __restrict__ k_cache,
-                                                         __half* __restrict__ v_cache, const int* __restrict__ page_table) {
+                                                         __half* __restrict__ v_cache, const int* __restrict__ page_table, int vt_ld) {
     const int t = blockIdx.x;
     const int qd = n_head * hd, kvd = n_kv * hd, ld = qd + 2 * kvd;
     if (t >= t_rows) {   // padding rows: zeros (finite inputs for the padded GEMM tiles)
         for (int i = threadIdx.x; i < qd; i += 256) qo[(size_t)t * qd + i] = from_float<T>(0.f);
-        for (int i = threadIdx.x; i < kvd; i += 256) { ko[(size_t)t * kvd + i] = from_float<T>(0.f); vt[(size_t)i * t_pad + t] = from_float<T>(0.f); }
+        for (int i = threadIdx.x; i < kvd; i += 256) { ko[(size_t)t * kvd + i] = from_float<T>(0.f); vt[(size_t)i * vt_ld + t] = from_float<T>(0.f); }
         return;
     }
     const int pos = pos0 + t;
     const float* row = qkv + (size_t)t * ld;
-    const int page = page_table[pos / KV_PAGE_TOKENS], tok = pos % KV_PAGE_TOKENS;
+    // k_cache == nullptr: embeddings -- the prompt pass is all there is, nothing is cached
+    const bool cache = k_cache != nullptr;
+    const int page = cache ? page_table[pos / KV_PAGE_TOKENS] : 0, tok = pos % KV_PAGE_TOKENS;
     for (int i = threadIdx.x; i < (qd + kvd) / 2; i += 256) {
         const int r = 2 * i;                       // even element index into [q | k]
         const int d = r % hd;
@@ -269,16 +271,18 @@ __global__ void __launch_bounds__(256) rope_split_kernel(const float* __restrict
             const __half h0 = __float2half_rn(o0), h1 = __float2half_rn(o1);
             ko[(size_t)t * kvd + rk] = from_float<T>(__half2float(h0));
             ko[(size_t)t * kvd + rk + 1] = from_float<T>(__half2float(h1));
-            const size_t off = (((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d;
-            k_cache[off] = h0;
-            k_cache[off + 1] = h1;
+            if (cache) {
+                const size_t off = (((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d;
+                k_cache[off] = h0;
+                k_cache[off + 1] = h1;
+            }
         }
     }
     for (int i = threadIdx.x; i < kvd; i += 256) {
         const __half hv = __float2half_rn(row[qd + kvd + i]);
-        vt[(size_t)i * t_pad + t] = from_float<T>(__half2float(hv));
+        vt[(size_t)i * vt_ld + t] = from_float<T>(__half2float(hv));
         const int kvh = i / hd, d = i % hd;
-        v_cache[(((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d] = hv;
+        if (cache) v_cache[(((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d] = hv;
     }
 }
 
@@ -394,8 +398,8 @@ cudaError_t rmsnorm_rows_launch(const float* x, const float* w, int rows, int ro
 
 cudaError_t rope_split_launch(const float* qkv, int t_rows, int t_pad, int pos0, int n_head, int n_kv, int hd, const float* cos_t,
                               const float* sin_t, __half* qo, __half* ko, __half* vt, __half* k_cache, __half* v_cache,
-                              const int* page_table, cudaStream_t s) {
-    rope_split_kernel<__half><<<t_pad, 256, 0, s>>>(qkv, t_rows, t_pad, pos0, n_head, n_kv, hd, cos_t, sin_t, qo, ko, vt, k_cache, v_cache, page_table);
+                              const int* page_table, int vt_ld, cudaStream_t s) {
+    rope_split_kernel<__half><<<t_pad, 256, 0, s>>>(qkv, t_rows, t_pad, pos0, n_head, n_kv, hd, cos_t, sin_t, qo, ko, vt, k_cache, v_cache, page_table, vt_ld);
     return cudaGetLastError();
 }
 

@@ -30,13 +30,21 @@ namespace gl {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
+constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2, STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+constexpr int TILE_A_BYTES = BM * BK * 2;
 constexpr int TC5_THREADS = 192;
 constexpr int ACC_BUFS = 2;
-constexpr int TMEM_COLS = ACC_BUFS * BN;       // 256 of the SM's 512 columns
-constexpr size_t TC5_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+// Output tile 128 x BN.  BN = 128: 6 stages of 32 KB, accumulators in 256 of the SM's 512 TMEM columns.  BN = 256: 4 stages of
+// 48 KB, accumulators in all 512 columns -- each K-step then stages 48 KB for 128 x 256 x 64 MACs (96 B per MMA cycle instead
+// of 128): the L2 -> shared-memory feed, not the tensor pipe, is what limits the 128 x 128 tile (tensor pipe active 46 %, run 59).
+template <int BN> struct Tc5Cfg {
+    static constexpr int STAGES = BN == 128 ? 6 : 4;
+    static constexpr int TILE_B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+    static constexpr int TMEM_COLS = ACC_BUFS * BN;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+};
 
 struct Tc5Params {
     CUtensorMap ta;      // A: dims {K, M_alloc}, box {64, 128}, 128-B swizzle
@@ -145,7 +153,11 @@ __device__ __forceinline__ void epilogue_row(const Tc5Params& p, int row, int co
     }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ Tc5Params p) {
+    constexpr int STAGES = Tc5Cfg<BN>::STAGES, TILE_B_BYTES = Tc5Cfg<BN>::TILE_B_BYTES, STAGE_BYTES = Tc5Cfg<BN>::STAGE_BYTES;
+    constexpr int TMEM_COLS = Tc5Cfg<BN>::TMEM_COLS;
+    (void)TILE_B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 128-byte-swizzled tiles must sit on 1024-byte boundaries
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -197,7 +209,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
                     uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
                     mbar_expect_tx(&full[st], STAGE_BYTES);
                     tma_load_2d(sa, &p.ta, kb * BK, m0, &full[st]);
-                    tma_load_2d(sa + TILE_A_BYTES, &p.tb, kb * BK, n0, &full[st]);
+#pragma unroll
+                    for (int h = 0; h < BN / 128; ++h)      // the tensor map's box is 128 rows: a 256-row B tile is two boxes, 16 KB apart
+                        tma_load_2d(sa + TILE_A_BYTES + h * (128 * BK * 2), &p.tb, kb * BK, n0 + h * 128, &full[st]);
                     if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
             }
@@ -294,7 +308,9 @@ bool make_map(CUtensorMap* map, const void* base, int rows, int k, int ld, bool 
 }  // namespace
 
 cudaError_t gemm_tc5_configure() {
-    return cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC5_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<128>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc5_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<256>::SMEM);
+    return e;
 }
 
 bool gemm_tc5_supported(const GemmParams& p) {
@@ -312,9 +328,22 @@ cudaError_t gemm_tc5_launch(const GemmParams& p, int a_rows_alloc, bool bf16, cu
     // persistent grid: one CTA per SM walks the tiles, M tiles fastest (the CTAs that share a weight tile run together)
     static const int n_sm = []() { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
     static const bool persist = []() { const char* e = getenv("GL_TC5_PERSIST"); return !(e && e[0] == '0'); }();
-    const int n_tiles = ((p.m + BM - 1) / BM) * ((p.n + BN - 1) / BN);
-    const dim3 grid((unsigned)(persist ? std::min(n_tiles, n_sm) : n_tiles));
-    gemm_tc5_kernel<<<grid, TC5_THREADS, TC5_SMEM, s>>>(tp);
+    // tile width: 128 x 256 tiles stage 25 % fewer bytes per MAC (the L2 -> shared-memory feed is the limit of this kernel);
+    // taken when they do not cost whole waves of the persistent grid (GL_TC5_BN = 128 / 256 forces one for A/B runs)
+    static const int force_bn = []() { const char* e = getenv("GL_TC5_BN"); return e ? atoi(e) : 0; }();
+    const int tiles_m = (p.m + BM - 1) / BM;
+    const int t128 = tiles_m * ((p.n + 127) / 128), t256 = tiles_m * ((p.n + 255) / 256);
+    auto waves = [&](int t) { return (t + n_sm - 1) / n_sm; };
+    bool wide = p.m > 128 && p.n >= 512 && 2 * waves(t256) <= waves(t128) + (waves(t128) > 6 ? 1 : 0);
+    if (force_bn == 128) wide = false;
+    if (force_bn == 256) wide = p.n >= 256;
+    if (wide) {
+        const dim3 grid((unsigned)(persist ? std::min(t256, n_sm) : t256));
+        gemm_tc5_kernel<256><<<grid, TC5_THREADS, Tc5Cfg<256>::SMEM, s>>>(tp);
+    } else {
+        const dim3 grid((unsigned)(persist ? std::min(t128, n_sm) : t128));
+        gemm_tc5_kernel<128><<<grid, TC5_THREADS, Tc5Cfg<128>::SMEM, s>>>(tp);
+    }
     return cudaGetLastError();
 }
 

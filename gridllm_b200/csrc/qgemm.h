@@ -1,0 +1,42 @@
+// Launcher interface of the batched decode GEMM on quantised weights (qgemm.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "prefill.h"
+
+namespace gl {
+
+// One weight matrix (or a row-wise concatenation / interleave of several) in the QG layout (qgemm_layout.h):
+// tiles of 128 output rows, each tile = nkb consecutive qtiles (one per 256-column block), tiles in order.
+struct QGemmWeights {
+    uint8_t* w = nullptr;             // qtile stream
+    uint64_t* tile_off = nullptr;     // device [n_tiles]: byte offset of a tile's first qtile
+    uint8_t* tile_type = nullptr;     // device [n_tiles]: ggml type of the tile's rows (12 Q4_K / 14 Q6_K)
+    unsigned* counters = nullptr;     // device [n_tiles]: split-tile tickets, zero between launches
+    int n = 0;                        // output features (rows of the matrix), multiple of 128
+    int k = 0;                        // input features, multiple of 256
+    int n_tiles = 0, nkb = 0;
+    uint64_t bytes = 0;               // bytes of the stream = the GGUF bytes of the matrix
+};
+
+// source of rows for the load-time packer: a matrix in NATIVE GGUF row layout on the device
+struct QGemmSource { const uint8_t* w; int type; int rows; };
+
+constexpr int QGEMM_MAX_GRID = 148;
+
+size_t qgemm_partial_floats(int nb);          // floats of split-tile scratch a launch with nb batch columns may use
+cudaError_t qgemm_configure();                // opt in to the kernel's dynamic shared memory (once per device)
+bool qgemm_batch_ok(int nb);                  // nb in {16, 32, 64}
+// Pack nsrc native matrices (all with k columns) into one QG stream.  mode 0: rows concatenated (Q | K | V);
+// mode 1: two sources interleaved in groups of 8 rows (8 gate | 8 up), the order the SiLU*mul epilogue expects.
+// dst must hold the sum of the sources' GGUF bytes; tile_off / tile_type get n_tiles entries (host arrays).
+cudaError_t qgemm_pack_launch(const QGemmSource* src, int nsrc, int mode, int k, uint8_t* dst, uint64_t* tile_off_host, uint8_t* tile_type_host,
+                              cudaStream_t s);
+// C[b][n] (+)= sum_k act[b][k] * W[n][k] for b < nb batch rows.  act: fp16 [>= 128 rows][k] (rows beyond the batch are
+// read but their results never stored); epi as GemmEpilogue (F32, ADD_F32, SILU with C fp16 [.. x n/2]).
+cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows_alloc, int nb, void* c, int ldc, int epi, float* partial,
+                         int n_sm, cudaStream_t s);
+
+}  // namespace gl

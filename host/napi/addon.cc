@@ -11,6 +11,10 @@
 //   tokenize(engine, text, addBos, parseSpecial) -> Int32Array ; detokenize(engine, Int32Array) -> string
 //   generate(engine, Int32Array prompt, {numPredict, ignoreEos, stopIds}, onToken|null) -> Promise<{ids, logprobs, stats}>
 //   embed(engine, Int32Array ids, Int32Array offsets) -> Promise<{embeddings: Float32Array, stats}>
+//   chatTemplate(engine) -> string   (tokenizer.chat_template of the GGUF; the TS host picks the message framing from it)
+//   seqOpen(engine, Int32Array prompt, {numPredict, ...}) -> Promise<number>      \  continuous batching:
+//   batchStep(engine) -> Promise<Array<{slot, id, logprob, done, piece}>>          |  every job the worker holds is a sequence;
+//   seqClose(engine, slot) ; seqStats(engine, slot) -> stats                      /  one batched step serves all of them
 //   destroyEngine(engine)
 #include <node_api.h>
 
@@ -66,6 +70,8 @@ napi_value CreateEngine(napi_env env, napi_callback_info info) {
         napi_value v;
         if (napi_get_named_property(env, argv[2], "maxCtx", &v) == napi_ok) napi_get_value_int32(env, v, &o.max_ctx);
         if (napi_get_named_property(env, argv[2], "actBits", &v) == napi_ok) napi_get_value_int32(env, v, &o.act_bits);
+        if (napi_get_named_property(env, argv[2], "maxBatch", &v) == napi_ok) napi_get_value_int32(env, v, &o.max_batch);
+        if (napi_get_named_property(env, argv[2], "kvPoolTokens", &v) == napi_ok) napi_get_value_int32(env, v, &o.kv_pool_tokens);
     }
     o.use_graph = 1;
     o.use_pdl = 1;
@@ -328,6 +334,183 @@ napi_value DestroyEngine(napi_env env, napi_callback_info) {
     return u;
 }
 
+// tokenizer.chat_template of the GGUF ("" when the file carries none)
+napi_value ChatTemplate(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    gl_engine* e = unwrap(env, argv[0]);
+    int32_t len = 0;
+    if (gl_chat_template(e, nullptr, 0, &len) != GL_OK) return throw_gl(env, "gl_chat_template");
+    std::string buf((size_t)len, '\0');
+    if (len > 0 && gl_chat_template(e, &buf[0], len, &len) != GL_OK) return throw_gl(env, "gl_chat_template");
+    napi_value out;
+    NAPI_OK(napi_create_string_utf8(env, buf.data(), (size_t)len, &out));
+    return out;
+}
+
+void read_sample_opts(napi_env env, napi_value o, gl_sample_opts& so, std::vector<int32_t>& stop_ids) {
+    napi_value v;
+    so.num_predict = 128;
+    so.top_p = 1.f;
+    double d = 0;
+    bool b = false;
+    if (napi_get_named_property(env, o, "numPredict", &v) == napi_ok && napi_get_value_int32(env, v, &so.num_predict) != napi_ok) so.num_predict = 128;
+    if (so.num_predict <= 0) so.num_predict = 128;
+    if (napi_get_named_property(env, o, "ignoreEos", &v) == napi_ok && napi_get_value_bool(env, v, &b) == napi_ok) so.ignore_eos = b ? 1 : 0;
+    if (napi_get_named_property(env, o, "temperature", &v) == napi_ok && napi_get_value_double(env, v, &d) == napi_ok) so.temperature = (float)d;
+    if (napi_get_named_property(env, o, "topK", &v) == napi_ok) napi_get_value_int32(env, v, &so.top_k);
+    if (napi_get_named_property(env, o, "topP", &v) == napi_ok && napi_get_value_double(env, v, &d) == napi_ok) so.top_p = (float)d;
+    if (napi_get_named_property(env, o, "seed", &v) == napi_ok && napi_get_value_double(env, v, &d) == napi_ok) so.seed = (uint64_t)d;
+    if (napi_get_named_property(env, o, "stopIds", &v) == napi_ok) {
+        void* data; size_t n; napi_typedarray_type ty; napi_value ab; size_t off;
+        if (napi_get_typedarray_info(env, v, &ty, &n, &data, &ab, &off) == napi_ok && ty == napi_int32_array)
+            stop_ids.assign(static_cast<int32_t*>(data), static_cast<int32_t*>(data) + n);
+    }
+}
+
+// ---- continuous batching: gl_seq_open (a prefill: async work) / gl_batch_step (one token for every open sequence: async work) ----
+struct SeqJob {
+    gl_engine* e;
+    std::vector<int32_t> prompt, stop_ids;
+    gl_sample_opts so{};
+    int32_t slot = -1;
+    // batch step
+    std::vector<int32_t> slots, ids, done;
+    std::vector<float> lps;
+    std::vector<std::string> pieces;
+    int32_t n = 0;
+    bool is_step = false;
+    int rc = 0;
+    std::string err;
+    napi_deferred deferred = nullptr;
+    napi_async_work work = nullptr;
+};
+void seq_execute(napi_env, void* data) {
+    SeqJob* j = static_cast<SeqJob*>(data);
+    if (!j->is_step) {
+        j->so.n_stop_ids = (int32_t)j->stop_ids.size();
+        j->so.stop_ids = j->stop_ids.data();
+        j->rc = gl_seq_open(j->e, j->prompt.data(), (int32_t)j->prompt.size(), &j->so, &j->slot);
+    } else {
+        j->slots.resize(128); j->ids.resize(128); j->done.resize(128); j->lps.resize(128);
+        j->rc = gl_batch_step(j->e, j->slots.data(), j->ids.data(), j->lps.data(), j->done.data(), 128, &j->n);
+        for (int i = 0; j->rc == GL_OK && i < j->n; ++i) {
+            char buf[256];
+            int32_t len = 0;
+            if (j->ids[i] >= 0 && gl_token_piece(j->e, j->ids[i], buf, (int32_t)sizeof buf, &len) == GL_OK) j->pieces.emplace_back(buf, (size_t)len);
+            else j->pieces.emplace_back();
+        }
+    }
+    if (j->rc != GL_OK) j->err = gl_last_error();
+}
+void seq_complete(napi_env env, napi_status, void* data) {
+    SeqJob* j = static_cast<SeqJob*>(data);
+    if (j->rc != GL_OK) {
+        napi_value msg, err;
+        napi_create_string_utf8(env, j->err.c_str(), NAPI_AUTO_LENGTH, &msg);
+        napi_create_error(env, nullptr, msg, &err);
+        napi_reject_deferred(env, j->deferred, err);
+    } else if (!j->is_step) {
+        napi_value v;
+        napi_create_int32(env, j->slot, &v);
+        napi_resolve_deferred(env, j->deferred, v);
+    } else {
+        // an object {n, slots, ids, logprobs, done, pieces: {0: ..., 1: ...}} -- typed arrays, one entry per open sequence
+        napi_value out, v, ab;
+        napi_create_object(env, &out);
+        napi_create_int32(env, j->n, &v);
+        napi_set_named_property(env, out, "n", v);
+        auto put_i32 = [&](const char* k, const std::vector<int32_t>& a) {
+            void* p;
+            napi_create_arraybuffer(env, (size_t)j->n * 4, &p, &ab);
+            memcpy(p, a.data(), (size_t)j->n * 4);
+            napi_create_typedarray(env, napi_int32_array, (size_t)j->n, ab, 0, &v);
+            napi_set_named_property(env, out, k, v);
+        };
+        put_i32("slots", j->slots); put_i32("ids", j->ids); put_i32("done", j->done);
+        void* p;
+        napi_create_arraybuffer(env, (size_t)j->n * 4, &p, &ab);
+        memcpy(p, j->lps.data(), (size_t)j->n * 4);
+        napi_create_typedarray(env, napi_float32_array, (size_t)j->n, ab, 0, &v);
+        napi_set_named_property(env, out, "logprobs", v);
+        napi_value pieces;
+        napi_create_object(env, &pieces);
+        for (int i = 0; i < j->n; ++i) {
+            napi_create_string_utf8(env, j->pieces[i].data(), j->pieces[i].size(), &v);
+            napi_set_named_property(env, pieces, std::to_string(i).c_str(), v);
+        }
+        napi_set_named_property(env, out, "pieces", pieces);
+        napi_resolve_deferred(env, j->deferred, out);
+    }
+    napi_delete_async_work(env, j->work);
+    delete j;
+}
+napi_value queue_seq(napi_env env, SeqJob* j, const char* name) {
+    napi_value promise, rname;
+    if (napi_create_promise(env, &j->deferred, &promise) != napi_ok) { delete j; return nullptr; }
+    napi_create_string_utf8(env, name, NAPI_AUTO_LENGTH, &rname);
+    if (napi_create_async_work(env, nullptr, rname, seq_execute, seq_complete, j, &j->work) != napi_ok || napi_queue_async_work(env, j->work) != napi_ok) {
+        delete j;
+        napi_throw_error(env, nullptr, "could not queue engine work");
+        return nullptr;
+    }
+    return promise;
+}
+napi_value SeqOpen(napi_env env, napi_callback_info info) {
+    size_t argc = 3;
+    napi_value argv[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    SeqJob* j = new SeqJob();
+    j->e = unwrap(env, argv[0]);
+    void* data; size_t n; napi_typedarray_type ty; napi_value ab; size_t off;
+    if (napi_get_typedarray_info(env, argv[1], &ty, &n, &data, &ab, &off) != napi_ok || ty != napi_int32_array) {
+        delete j;
+        napi_throw_error(env, nullptr, "seqOpen: prompt must be an Int32Array");
+        return nullptr;
+    }
+    j->prompt.assign(static_cast<int32_t*>(data), static_cast<int32_t*>(data) + n);
+    if (argc > 2) read_sample_opts(env, argv[2], j->so, j->stop_ids);
+    else { j->so.num_predict = 128; j->so.top_p = 1.f; }
+    return queue_seq(env, j, "gl_seq_open");
+}
+napi_value BatchStep(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    SeqJob* j = new SeqJob();
+    j->e = unwrap(env, argv[0]);
+    j->is_step = true;
+    return queue_seq(env, j, "gl_batch_step");
+}
+napi_value SeqClose(napi_env env, napi_callback_info info) {
+    size_t argc = 2;
+    napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    int32_t slot = -1;
+    NAPI_OK(napi_get_value_int32(env, argv[1], &slot));
+    if (gl_seq_close(unwrap(env, argv[0]), slot) != GL_OK) return throw_gl(env, "gl_seq_close");
+    napi_value u;
+    NAPI_OK(napi_get_undefined(env, &u));
+    return u;
+}
+napi_value SeqStats(napi_env env, napi_callback_info info) {
+    size_t argc = 2;
+    napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    int32_t slot = -1;
+    NAPI_OK(napi_get_value_int32(env, argv[1], &slot));
+    gl_gen_stats st{};
+    if (gl_seq_stats(unwrap(env, argv[0]), slot, &st) != GL_OK) return throw_gl(env, "gl_seq_stats");
+    napi_value out;
+    NAPI_OK(napi_create_object(env, &out));
+    auto seti = [&](const char* k, double d) { napi_value x; napi_create_double(env, d, &x); napi_set_named_property(env, out, k, x); };
+    seti("promptEvalCount", st.prompt_eval_count); seti("evalCount", st.eval_count);
+    seti("promptEvalDurationNs", (double)st.prompt_eval_duration_ns); seti("evalDurationNs", (double)st.eval_duration_ns);
+    seti("totalDurationNs", (double)st.total_duration_ns); seti("loadDurationNs", (double)st.load_duration_ns); seti("doneReason", st.done_reason);
+    return out;
+}
+
 napi_value Init(napi_env env, napi_value exports) {
     napi_property_descriptor d[] = {
         {"deviceCount", nullptr, DeviceCount, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -337,6 +520,11 @@ napi_value Init(napi_env env, napi_value exports) {
         {"tokenize", nullptr, Tokenize, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"detokenize", nullptr, Detokenize, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"embed", nullptr, Embed, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"chatTemplate", nullptr, ChatTemplate, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"seqOpen", nullptr, SeqOpen, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"batchStep", nullptr, BatchStep, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"seqClose", nullptr, SeqClose, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"seqStats", nullptr, SeqStats, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"destroyEngine", nullptr, DestroyEngine, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);

@@ -51,10 +51,46 @@ export class NativeInferenceService {
 		return !!this.models[modelName];
 	}
 
+	// GRIDLLM_SAMPLING=ollama: requests that leave temperature / top_k / top_p out inherit Ollama's documented defaults
+	// (0.8 / 40 / 0.9); default: greedy, the BASELINE configuration.  GRIDLLM_APPLY_TEMPLATE=1: frame generate prompts as one user
+	// turn of the model's chat template unless metadata.raw (what Ollama does).  Same switches as gridllm_b200/service.py.
+	private samplingDefaults: Record<string, number> = process.env.GRIDLLM_SAMPLING === "ollama" ? { temperature: 0.8, top_k: 40, top_p: 0.9 } : {};
+	private applyTemplate = process.env.GRIDLLM_APPLY_TEMPLATE === "1";
+
+	// messages -> prompt text.  The GGUF's chat template is Jinja and is not interpreted: its FAMILY is recognised from the
+	// markers it contains (gl_chat_template) -- Llama-3 headers (also the default), ChatML, Llama-2 / Mistral [INST] -- and
+	// that family's framing applied; identical to gridllm_b200/service.py::_chat_prompt.
+	private chatPrompt(e: unknown, messages: Array<{ role: string; content: string }>): string {
+		let tmpl = "";
+		try { tmpl = native.chatTemplate(e) || ""; } catch { tmpl = ""; }
+		const msgs = messages.map((m) => [m.role ?? "user", m.content ?? ""] as [string, string]);
+		if (tmpl.includes("<|im_start|>"))
+			return msgs.map(([r, c]) => `<|im_start|>${r}\n${c}<|im_end|>\n`).join("") + "<|im_start|>assistant\n";
+		if (tmpl.includes("[INST]")) {
+			const system = msgs.filter(([r]) => r === "system").map(([, c]) => c).join("\n\n");
+			let out = "", first = true;
+			for (const [r, c0] of msgs) {
+				if (r === "system") continue;
+				if (r === "assistant") { out += ` ${c0}</s>`; continue; }
+				let c = c0;
+				if (first && system) c = tmpl.includes("<<SYS>>") ? `<<SYS>>\n${system}\n<</SYS>>\n\n${c}` : `${system}\n\n${c}`;
+				first = false;
+				out += `[INST] ${c} [/INST]`;
+			}
+			return out;
+		}
+		return msgs.map(([r, c]) => `<|start_header_id|>${r}<|end_header_id|>\n\n${c}<|eot_id|>`).join("")
+			+ "<|start_header_id|>assistant<|end_header_id|>\n\n";
+	}
+
 	private ids(e: unknown, request: InferenceRequest): Int32Array {
-		const pre = request.metadata?.prompt_token_ids;
-		if (pre) return Int32Array.from(pre);
-		const ctx: number[] | undefined = request.metadata?.context;          // conversation so far (OllamaService.ts:224-226)
+		const md = request.metadata ?? {};
+		if (md.prompt_token_ids) return Int32Array.from(md.prompt_token_ids);
+		const ctx: number[] | undefined = md.context;                          // conversation so far (OllamaService.ts:224-226)
+		if (this.applyTemplate && !md.raw && !ctx?.length) {
+			const msgs = [...(md.system ? [{ role: "system", content: md.system }] : []), { role: "user", content: request.prompt || "" }];
+			return native.tokenize(e, this.chatPrompt(e, msgs), true, true);
+		}
 		if (ctx?.length) return Int32Array.from([...ctx, ...native.tokenize(e, request.prompt || "", false, false)]);
 		return native.tokenize(e, request.prompt || "", true, false);
 	}
@@ -76,18 +112,29 @@ export class NativeInferenceService {
 		return st;
 	}
 
-	private toResponse(request: InferenceRequest, text: string, ids: Int32Array, st: NativeStats): InferenceResponse {
+	// `context` is the WHOLE conversation so far -- prompt ids then reply ids: the gateway returns it (ollama.ts:143) and forwards
+	// it back as metadata.context (ollama.ts:234), and a client that feeds it back must continue from here
+	private toResponse(request: InferenceRequest, text: string, ids: Int32Array, st: NativeStats, promptIds?: Int32Array): InferenceResponse {
 		return { id: request.id, model: request.model, created_at: new Date().toISOString(), response: text, done: true,
 			done_reason: st.doneReason === 0 ? "stop" : "length", total_duration: st.totalDurationNs, load_duration: st.loadDurationNs,
 			prompt_eval_count: st.promptEvalCount, prompt_eval_duration: st.promptEvalDurationNs, eval_count: st.evalCount,
-			eval_duration: st.evalDurationNs, context: Array.from(ids), system_fingerprint: "fp_gridllm_b200_native" };
+			eval_duration: st.evalDurationNs, context: [...Array.from(promptIds ?? []), ...Array.from(ids)], token_ids: Array.from(ids),
+			system_fingerprint: "fp_gridllm_b200_native" };
 	}
 
 	// InferenceRequest.options -> gl_sample_opts; temperature absent / 0 = greedy, a sampled request without seed draws one
-	private sampleOpts(request: InferenceRequest) {
+	// num_predict: `options.num_predict || 128` (OllamaService.ts:105); the gateway also lets -1 / -2 through (ollama.ts:47,
+	// "until EOS"): those run until the engine's context is full, like service.py::_plan
+	private sampleOpts(request: InferenceRequest, e?: unknown, nPrompt = 0) {
 		const o = request.options ?? {};
-		const temperature = o.temperature ?? 0;
-		return { numPredict: o.num_predict || 128, ignoreEos: !!o.ignore_eos, temperature, topK: o.top_k ?? 0, topP: o.top_p ?? 1,
+		const d = this.samplingDefaults;
+		const temperature = o.temperature ?? d.temperature ?? 0;
+		if (!(temperature >= 0) || !Number.isFinite(temperature)) throw new Error("temperature must be a finite number >= 0");
+		let numPredict = o.num_predict || 128;
+		const nCtx = e ? (native.engineInfo(e).nCtx as number) : 0;
+		if (numPredict < 0) numPredict = nCtx > 0 ? Math.max(1, nCtx - nPrompt) : 128;
+		if (nCtx > 0 && nPrompt < nCtx) numPredict = Math.min(numPredict, nCtx - nPrompt);
+		return { numPredict, ignoreEos: !!o.ignore_eos, temperature, topK: o.top_k ?? d.top_k ?? 0, topP: o.top_p ?? d.top_p ?? 1,
 			seed: BigInt(o.seed ?? (temperature > 0 ? Math.floor(Math.random() * 2 ** 53) : 0)) };
 	}
 
@@ -96,15 +143,16 @@ export class NativeInferenceService {
 			const e = this.engine(request.model);
 			const stop = request.options?.stop;
 			const stops: string[] = (typeof stop === "string" ? [stop] : stop || []).filter(Boolean);
+			const promptIds = this.ids(e, request);
 			if (!stops.length) {
-				const out = await native.generate(e, this.ids(e, request), this.sampleOpts(request), null);
-				return this.toResponse(request, native.detokenize(e, out.ids), out.ids, out.stats);
+				const out = await native.generate(e, promptIds, this.sampleOpts(request, e, promptIds.length), null);
+				return this.toResponse(request, native.detokenize(e, out.ids), out.ids, out.stats, promptIds);
 			}
 			const f = this.stopFilter(stops);         // a non-zero return of the token callback cancels gl_generate
-			const out = await native.generate(e, this.ids(e, request), this.sampleOpts(request),
+			const out = await native.generate(e, promptIds, this.sampleOpts(request, e, promptIds.length),
 				(_id: number, _lp: number, piece: string) => { f.feed(piece); return f.hit; });
 			f.flush();
-			const res = this.toResponse(request, f.text, out.ids, out.stats);
+			const res = this.toResponse(request, f.text, out.ids, out.stats, promptIds);
 			if (f.hit) res.done_reason = "stop";
 			return res;
 		} catch (error) {
@@ -117,7 +165,8 @@ export class NativeInferenceService {
 			const e = this.engine(request.model);
 			const queue: StreamResponse[] = [];
 			let wake: (() => void) | null = null;
-			const done = native.generate(e, this.ids(e, request), this.sampleOpts(request),
+			const promptIds = this.ids(e, request);
+			const done = native.generate(e, promptIds, this.sampleOpts(request, e, promptIds.length),
 				(_id: number, _lp: number, piece: string) => { queue.push({ id: request.id, response: piece, done: false }); wake?.(); });
 			let finished = false;
 			done.then(() => { finished = true; wake?.(); }, () => { finished = true; wake?.(); });
@@ -134,18 +183,18 @@ export class NativeInferenceService {
 
 	async generateChatResponse(request: InferenceRequest): Promise<InferenceResponse> {   // :353-449
 		if (!request.metadata?.messages) throw new Error("Chat inference failed: Chat request must include messages in metadata");
-		const prompt = request.metadata.messages.map((m) => `<|start_header_id|>${m.role}<|end_header_id|>\n\n${m.content}<|eot_id|>`).join("")
-			+ "<|start_header_id|>assistant<|end_header_id|>\n\n";
-		const r = await this.generateResponse({ ...request, prompt });
+		const e = this.engine(request.model);
+		const ids = request.metadata.prompt_token_ids ?? Array.from(native.tokenize(e, this.chatPrompt(e, request.metadata.messages), true, true) as Int32Array);
+		const r = await this.generateResponse({ ...request, metadata: { ...request.metadata, prompt_token_ids: ids } });
 		const { response, ...rest } = r;
 		return { ...rest, message: { role: "assistant", content: response } };
 	}
 
 	async *generateChatStreamResponse(request: InferenceRequest): AsyncGenerator<StreamResponse> {   // :451-599
 		if (!request.metadata?.messages) throw new Error("Chat streaming inference failed: Chat request must include messages in metadata");
-		const prompt = request.metadata.messages.map((m) => `<|start_header_id|>${m.role}<|end_header_id|>\n\n${m.content}<|eot_id|>`).join("")
-			+ "<|start_header_id|>assistant<|end_header_id|>\n\n";
-		yield* this.generateStreamResponse({ ...request, prompt });
+		const e = this.engine(request.model);
+		const ids = request.metadata.prompt_token_ids ?? Array.from(native.tokenize(e, this.chatPrompt(e, request.metadata.messages), true, true) as Int32Array);
+		yield* this.generateStreamResponse({ ...request, metadata: { ...request.metadata, prompt_token_ids: ids } });
 	}
 
 	async generateEmbedding(request: InferenceRequest): Promise<InferenceResponse> {   // :601-665
@@ -153,7 +202,10 @@ export class NativeInferenceService {
 			if (!request.input) throw new Error("Input is required for embedding requests");
 			const e = this.engine(request.model);
 			const texts = Array.isArray(request.input) ? request.input : [request.input];
-			const seqs = texts.map((t) => native.tokenize(e, t, true, false) as Int32Array);
+			// metadata.truncate (OllamaService.ts:626-628): inputs longer than the context are cut to it unless truncate is false
+			const nCtx = native.engineInfo(e).nCtx as number;
+			const cut = request.metadata?.truncate !== false && nCtx > 0;
+			const seqs = texts.map((t) => { const a = native.tokenize(e, t, true, false) as Int32Array; return cut ? a.subarray(0, nCtx) : a; });
 			const offsets = new Int32Array(seqs.length + 1);
 			seqs.forEach((s, i) => (offsets[i + 1] = offsets[i] + s.length));
 			const flat = new Int32Array(offsets[seqs.length]);

@@ -144,6 +144,21 @@ def random_blocks(rng: np.random.Generator, ggml_type: int, rows: int, cols: int
     nb = rows * cols // BLOCK[ggml_type][0]
     bb = BLOCK[ggml_type][1]
     target = gain / np.sqrt(cols)
+    if ggml_type in (F16, BF16) and rows * cols >= (1 << 24):
+        # big 16-bit matrices (the bf16 Llama-3-8B of BASELINE config 4 is 16 GB): random BIT PATTERNS instead of 8 G normal
+        # draws -- random sign and mantissa, exponent one of two adjacent values around `target`, so |w| is spread over
+        # [target/2, 2*target) with zero mean: finite, well-scaled weights at a few GB/s of generation
+        n = rows * cols
+        man_bits = 7 if ggml_type == BF16 else 10
+        bias = 127 if ggml_type == BF16 else 15
+        e0 = int(np.floor(np.log2(target))) + bias
+        raw = rng.bit_generator.random_raw((n + 3) // 4).view(np.uint16)[:n]           # 16 random bits per weight, ~GB/s
+        ebit = raw & np.uint16(1 << man_bits)                                            # one random bit picks the exponent
+        raw &= np.uint16(0x8000 | ((1 << man_bits) - 1))                                 # keep sign and mantissa
+        raw += np.uint16(e0 << man_bits)
+        raw -= ebit
+        out16 = raw
+        return out16.view(np.uint8).reshape(rows, cols * 2)
     if ggml_type in (F32, F16, BF16):
         w = rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(target)
         return quantize(w, ggml_type)

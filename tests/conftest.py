@@ -2,12 +2,26 @@ import os
 import subprocess
 import sys
 
+# The checker (numpy oracle: thousands of small matmuls; C restatement: OpenMP) must not fan out over every logical CPU of a
+# 128-thread GPU box: BLAS / OpenMP thread pools that large spend their time synchronising, and the round-2 GPU suite took 21
+# minutes (331 CPU-minutes) instead of two.  Set BEFORE numpy loads its BLAS.  bench.py is not affected (it picks the CPU
+# baseline's thread count itself).
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, str(max(1, min(16, (os.cpu_count() or 8)))))
+
 import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+
+try:        # numpy may have been imported by a plugin before this file ran: cap the pools that already exist as well
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=int(os.environ["OPENBLAS_NUM_THREADS"]))
+except Exception:
+    pass
 
 
 def pytest_configure(config):

@@ -163,3 +163,33 @@ extern "C" int hc_detokenize(const char* gguf_path, const int32_t* ids, int n, c
     buf[s.size()] = 0;
     return (int)s.size();
 }
+
+// ---- batched decode GEMM on quantised weights (qgemm_layout.h): pack 128 GGUF super-blocks into a qtile, run the kernel's
+// per-thread dequantisation program for all 256 (row, half) threads into four swizzled operand tiles, un-swizzle with the
+// TMA / tcgen05 128-byte-swizzle rule and hand back the fp16 bit patterns [128 rows][256 columns] ------------------------------
+#include "../../gridllm_b200/csrc/qgemm_layout.h"
+extern "C" int hc_qg_dequant(int type, const uint8_t* blocks /*[128][block bytes]*/, uint16_t* out /*[128][256]*/, int* qtile_bytes) {
+    if (!qg_type_ok(type)) return -1;
+    const int bb = type == 12 ? 144 : 210;
+    std::vector<uint8_t> qt((size_t)qg_qtile_bytes(type) + 64, 0xAB);     // poison: every byte must be written by the packer
+    for (int r = 0; r < QG_ROWS; ++r) qg_pack_block(type, blocks + (size_t)r * bb, qt.data(), r);
+    *qtile_bytes = qg_qtile_bytes(type);
+    alignas(16) static uint8_t tiles[4 * QG_A_TILE_BYTES];
+    memset(tiles, 0xCD, sizeof tiles);
+    int order_ok = 1, last[2] = {-1, -1};
+    for (int h = 0; h < 2; ++h)
+        for (int r = 0; r < QG_ROWS; ++r)
+            qg_dequant_thread(type, qt.data(), r, h, [&](int kk) { return tiles + (size_t)kk * QG_A_TILE_BYTES; },
+                              [&](int kk) { if (kk / 2 != h) order_ok = 0; last[h] = kk; }, [&](int) {});
+    if (!order_ok) return -2;
+    for (int r = 0; r < QG_ROWS; ++r)
+        for (int col = 0; col < QG_COLS; ++col) {
+            const int kk = col / QG_KSTEP, c = (col % QG_KSTEP) / 8, i = col % 8;
+            // what the tensor core reads as element (row r, k = col % 64) of K-step kk: the chunk sits at chunk slot c ^ (r & 7)
+            const uint8_t* p = tiles + (size_t)kk * QG_A_TILE_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((c ^ (r & 7)) << 4) + 2 * i;
+            uint16_t v;
+            memcpy(&v, p, 2);
+            out[(size_t)r * QG_COLS + col] = v;
+        }
+    return 0;
+}

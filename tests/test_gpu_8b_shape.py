@@ -35,6 +35,8 @@ def oracle_8b(bench_model):
     lib.oc_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.oc_reset.argtypes = [C.c_void_p]
     lib.oc_free.argtypes = [C.c_void_p]
+    lib.oc_set_threads.argtypes = [C.c_int]
+    lib.oc_set_threads(min(32, os.cpu_count() or 8))                # not every logical CPU: exact mode is memory-bound
     h = lib.oc_load(bench_model.encode(), 64)
     assert h
     yield lib, h
@@ -76,7 +78,7 @@ def test_decode_step_at_the_benchmarked_shape(engine_8b, bench_model):
 
 
 def test_batched_prefill_at_the_benchmarked_shape(engine_8b, oracle_8b):
-    toks = np.random.Generator(np.random.PCG64(31337)).integers(0, 128000, size=24)
+    toks = np.random.Generator(np.random.PCG64(31337)).integers(0, 128000, size=16)
     ref = _oracle_run(oracle_8b, toks, 1)[-1]
     engine_8b.kv_reset()
     lg = engine_8b.prefill(toks)                                       # tcgen05 GEMMs on the resident 16-bit weights
@@ -96,7 +98,7 @@ def test_batched_prefill_at_the_benchmarked_shape(engine_8b, oracle_8b):
 
 def test_batched_decode_step_at_the_benchmarked_shape(engine_8b, oracle_8b):
     rng = np.random.Generator(np.random.PCG64(4242))
-    prompts = [rng.integers(0, 128000, size=n) for n in (9, 6)]
+    prompts = [rng.integers(0, 128000, size=n) for n in (9, 5)]
     slots = [engine_8b.seq_open(p, num_predict=3, ignore_eos=True) for p in prompts]
     got = {s: [] for s in slots}
     lgs = {s: [] for s in slots}

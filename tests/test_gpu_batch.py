@@ -15,7 +15,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-MODES = [1]             # gl_engine_opts.batch_weights: 1 = resident 16-bit copy, 2 = quantised weights dequantised inside the GEMM
+MODES = [1, 2]          # gl_engine_opts.batch_weights: 1 = resident 16-bit copy, 2 = quantised weights dequantised inside the GEMM
 
 
 def _engine(path, **kw):
@@ -102,6 +102,32 @@ def test_tokens_do_not_depend_on_who_shares_the_batch(tiny128_gguf, mode):
                 srt = np.sort(lgi)
                 assert srt[-1] - srt[-2] <= 2e-2 * float(np.abs(lgi).max()), (i, srt[-1] - srt[-2])
                 break
+    e.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("mode", MODES)
+def test_large_batch_long_contexts(tiny128_gguf, mode):
+    """28 sequences (the 32-row bucket: two attention splits per KV head) with 300..700-token contexts (20+ KV pages per split:
+    several TMA tiles per CTA, partial merge) -- the shape of BASELINE config 3 at test size.  Spot-checked against the oracle
+    on four of them; all of them must finish, with finite logprobs."""
+    from oracle import llama_oracle as O
+    m = O.load_gguf(tiny128_gguf)
+    e = _engine(tiny128_gguf, max_batch=32, max_ctx=1024, batch_weights=mode)
+    rng = np.random.Generator(np.random.PCG64(2024))
+    lens = [int(x) for x in rng.integers(300, 700, size=28)]
+    prompts = [rng.integers(0, m.n_vocab - 3, size=n) for n in lens]
+    slots = [e.seq_open(p, num_predict=6, ignore_eos=True) for p in prompts]
+    lg = {}
+    got = _drain(e, {s: 6 for s in slots}, lg)
+    assert all(len(got[s][0]) == 6 and np.isfinite(got[s][1]).all() for s in slots)
+    for k in (0, 9, 17, 27):
+        ref = O.LlamaOracle(m, act="exact", kv_f16=True).generate(prompts[k], 6)
+        assert _check_against_oracle(ref, got[slots[k]][0], got[slots[k]][1], lg[slots[k]], ("large", mode, lens[k])) >= 1
+    for s in slots:
+        e.seq_close(s)
+    ms, launches, wbytes = e.time_batch_step(32, 500, iters=4)
+    assert ms > 0 and launches > 0
     e.close()
 
 

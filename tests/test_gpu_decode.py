@@ -397,3 +397,32 @@ def test_unsupported_rope_scaling_and_pretokenizer_fail_loudly(tmp_models):
     with pytest.raises(N.NativeError):
         e.tokenize("hello")
     e.close()
+
+
+# ---- packed embeddings (/api/embed `input: string[]`, ollama.ts:574-643 -> OllamaService.ts:619-636) ----------
+@pytest.mark.parametrize("fixture", ["tiny128_gguf", "tiny_q8_gguf"])
+def test_packed_embeddings_ragged_batch_matches_oracle(fixture, request):
+    """26 sequences of ragged lengths in ONE gl_embed call: they are packed 128-row-aligned into passes of <= 2048 rows (several
+    packs here), share the linear layers and attend only inside themselves.  Every embedding equals the oracle's for that sequence
+    alone (same tolerance as the single-sequence batched prefill), whatever its neighbours in the pack; order is preserved."""
+    from oracle import llama_oracle as O
+    path = request.getfixturevalue(fixture)
+    m = O.load_gguf(path)
+    rng = np.random.Generator(np.random.PCG64(5150))
+    lens = [1, 9, 33, 2, 128, 129, 300, 7, 64, 255, 256, 257, 16, 3, 500, 31, 127, 200, 5, 90, 12, 384, 1, 77, 140, 20]
+    seqs = [rng.integers(0, m.n_vocab - 3, size=n) for n in lens]
+    e = _engine(path, max_ctx=512)
+    out, st = e.embed(seqs)
+    assert out.shape == (len(seqs), m.n_embd) and st.prompt_eval_count == sum(lens) and st.prompt_eval_duration_ns > 0
+    orc = O.LlamaOracle(m, act="exact")
+    worst = 0.0
+    for i, s in enumerate(seqs):
+        ref = orc.embed(s)
+        assert abs(np.linalg.norm(out[i]) - 1.0) < 1e-5
+        worst = max(worst, float(np.abs(out[i] - ref).max()))
+        assert np.abs(out[i] - ref).max() <= 5e-3, (fixture, i, lens[i])
+    # the same sequence alone, or first / last in another call: the same bits (its rows never see a neighbour)
+    alone, _ = e.embed([seqs[6]])
+    other, _ = e.embed([seqs[20], seqs[6], seqs[3]])
+    assert np.array_equal(alone[0], out[6]) and np.array_equal(other[1], out[6])
+    e.close()

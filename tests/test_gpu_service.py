@@ -139,3 +139,59 @@ def test_sampled_requests(svc):
     assert d["eval_count"] == 16
     with pytest.raises(RuntimeError, match="Inference failed"):
         _run(svc.generateResponse(dict(req, id="t7", options=dict(opts, temperature=-1))))
+
+
+# ---- the north_star's multi-GPU shape: N engines, one per GPU, in ONE process behind the scheduler rules ------
+def test_in_process_workers_one_engine_per_gpu(tiny128_gguf):
+    """One NativeWorker + NativeInferenceService + engine per visible GPU (up to 8), all in this process, each registered under its
+    own worker id; the restated scheduler rules (tests/sched_standin.py: JobScheduler.ts:137-217, 317-360) shard 6 jobs per GPU.
+    Every worker id is used, priority order is honoured, and every result equals the single-engine answer for that prompt.
+    Needs >= 2 GPUs (`gpurun --gpus N`, the driver's multi-GPU tier); on one GPU the same path runs in
+    test_workers_shard_requests_like_the_scheduler with both engines on device 0."""
+    from gridllm_b200 import native as N
+    from gridllm_b200.service import NativeInferenceService
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    from sched_standin import SchedulerStandIn
+    n_dev = min(8, N.device_count())
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    bus = LocalBus()
+    sched = SchedulerStandIn(bus, max_jobs_per_worker=2)
+    svcs = [NativeInferenceService({"tiny128:latest": tiny128_gguf}, device=d, max_batch=2) for d in range(n_dev)]
+    workers = [NativeWorker(f"b200-{d}", s, bus, max_concurrent=2) for d, s in enumerate(svcs)]
+    n_jobs = 6 * n_dev
+    prompts = [np.random.Generator(np.random.PCG64(7000 + i)).integers(0, 1000, size=20 + i % 7).tolist() for i in range(n_jobs)]
+
+    async def go():
+        await sched.start()
+        for w in workers:
+            await w.start()
+        for i, p in enumerate(prompts):
+            sched.add_job({"id": f"job-{i}", "model": "tiny128:latest", "prompt": "", "stream": i % 3 == 0, "timeout": 300000,
+                           "priority": "high" if i == n_jobs - 1 else "medium", "options": {"num_predict": 6, "ignore_eos": True},
+                           "metadata": {"prompt_token_ids": p}})
+            if i % 3 == 0:
+                await sched.watch_stream(f"job-{i}")
+        await sched.run_until_empty()
+        for w in workers:
+            await w.stop()
+    asyncio.new_event_loop().run_until_complete(go())
+    assert len(sched.results) == n_jobs and all("result" in r for r in sched.results.values())
+    assert set(sched.assigned.values()) == {f"b200-{d}" for d in range(n_dev)}                  # every GPU's worker took jobs
+    first_assignment = [json.loads(m) for c, m in bus.log if c.endswith(":job")][0]
+    assert first_assignment["job"]["jobId"] == f"job-{n_jobs - 1}"                              # the high-priority job went out first
+    ref_engine = N.Engine(tiny128_gguf, device=0, max_batch=2)                                  # the single-engine answers, same batched path
+    for i, p in enumerate(prompts):
+        slot = ref_engine.seq_open(p, num_predict=6, ignore_eos=True)
+        ids = []
+        while len(ids) < 6:
+            ids += [t for s, t, _lp, _d in ref_engine.batch_step() if s == slot]
+        ref_engine.seq_close(slot)
+        r = sched.results[f"job-{i}"]["result"]
+        if i % 3 == 0:
+            assert sched.stream_chunks[f"job-{i}"] == 7 and r["done"] is True
+        else:
+            assert r["token_ids"] == ids, i
+    ref_engine.close()
+    for s in svcs:
+        s.close()

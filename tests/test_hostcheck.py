@@ -98,3 +98,43 @@ def test_engine_layout_round_trip(hostcheck_lib, tname, cols):
         rc = hostcheck_lib.hc_dequant_engine(t, blocks.ctypes.data_as(ctypes.c_void_p), rows, cols, tile_rows, out.ctypes.data_as(ctypes.c_void_p))
         assert rc == 0
         assert np.array_equal(out, ref), tile_rows
+
+
+# ---- batched decode GEMM on quantised weights: qtile packing + the dequantisation program of the kernel (qgemm_layout.h) ----------
+@pytest.mark.parametrize("tname", ["Q4_K", "Q6_K"])
+def test_qgemm_tile_program_reproduces_the_gguf_values(hostcheck_lib, tname):
+    """128 GGUF super-blocks -> QG qtile (a lossless permutation of the same bytes) -> the kernel's per-thread fp16
+    dequantisation into four 128-byte-swizzled operand tiles -> un-swizzled: equals the GGUF dequantisation (gguf-py-pinned
+    oracle) to fp16 arithmetic: |got - exact| <= 2^-10 * (|d*sc*q| + |dmin*mn|) + one fp16 ulp of the result."""
+    import ctypes
+    from oracle import gguf_synth as S, llama_oracle as O
+    t = getattr(S, tname)
+    bb = S.BLOCK[t][1]
+    lib = hostcheck_lib
+    lib.hc_qg_dequant.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    for seed, mode in ((1, "random"), (2, "quantize")):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        if mode == "random":
+            blocks = S.random_blocks(rng, t, 128, 256)
+        else:
+            blocks = S.quantize(rng.standard_normal((128, 256), dtype=np.float32) * np.float32(0.02), t)
+        blocks = np.ascontiguousarray(blocks).view(np.uint8).reshape(128, bb)
+        out = np.zeros((128, 256), np.uint16)
+        nbytes = ctypes.c_int(0)
+        rc = lib.hc_qg_dequant(t, blocks.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nbytes))
+        assert rc == 0 and nbytes.value == 128 * bb                   # the qtile is exactly the GGUF bytes of its blocks
+        got = out.view(np.float16).astype(np.float64)
+        exact = O.dequantize(blocks, t, (128, 256)).astype(np.float64)
+        # magnitude of the terms that are rounded to fp16 before they are combined
+        if t == S.Q4_K:
+            d = blocks[:, 0:2].copy().view(np.float16).astype(np.float64)
+            dmin = blocks[:, 2:4].copy().view(np.float16).astype(np.float64)
+            mag = np.abs(d) * 63 * 15 + np.abs(dmin) * 63
+        else:
+            d = blocks[:, 208:210].copy().view(np.float16).astype(np.float64)
+            mag = np.abs(d) * 128 * 32
+        tol = 2.0 ** -10 * mag + np.abs(exact) * 2.0 ** -10 + 1e-12
+        assert np.all(np.abs(got - exact) <= tol), (tname, mode, float(np.abs(got - exact).max()))
+        # and it is not a loose match: the typical error is a fraction of an fp16 ulp of the weight
+        nz = np.abs(exact) > 0
+        assert np.median(np.abs(got - exact)[nz] / np.abs(exact)[nz]) < 2.0 ** -10
