@@ -105,19 +105,51 @@ class BatchRunner:
                 job.future.set_exception(ex)
 
     def _admit(self) -> None:
-        """prefill waiting requests into free slots (between steps: sequences join and leave at step boundaries)"""
-        while len(self._jobs) < self.max_batch:
-            with self._cv:
-                if not self._pending:
+        """prefill waiting requests into free slots (between steps: sequences join and leave at step boundaries).  Everything
+        that is waiting goes to the engine in ONE call: the prompts share packed prompt passes (gl_seq_open_many)."""
+        room = self.max_batch - len(self._jobs)
+        if room <= 0:
+            return
+        with self._cv:
+            batch = [self._pending.popleft() for _ in range(min(room, len(self._pending)))]
+        if not batch:
+            return
+        many = getattr(self.eng, "seq_open_many", None)
+        if many is not None and len(batch) > 1:
+            try:
+                with self.lock:
+                    slots = many([j.ids for j in batch], [dict(j.kw, num_predict=j.num_predict, ignore_eos=j.ignore_eos) for j in batch])
+            except Exception as ex:
+                if getattr(ex, "code", None) == GL_ERR_NOMEM and self._jobs:
+                    with self._cv:                   # nothing fits right now: wait for a sequence to leave
+                        self._pending.extendleft(reversed(batch))
                     return
-                job = self._pending.popleft()
+                # nothing was opened (the engine validates every prompt before it opens any): a bad request among them, or not
+                # even one fits -- the one-by-one path below finds out which, and fails only the requests that deserve it
+                slots = None
+            if slots is not None:
+                back = []
+                for j, slot in zip(batch, slots):
+                    if slot >= 0:
+                        self._jobs[slot] = j
+                    else:
+                        back.append(j)
+                if back:
+                    if self._jobs:
+                        with self._cv:
+                            self._pending.extendleft(reversed(back))
+                        return
+                    batch = back                     # nothing is running and these still do not fit: fail them one by one below
+                else:
+                    return
+        for k, job in enumerate(batch):
             try:
                 with self.lock:
                     slot = self.eng.seq_open(job.ids, num_predict=job.num_predict, ignore_eos=job.ignore_eos, **job.kw)
             except Exception as ex:
                 if getattr(ex, "code", None) == GL_ERR_NOMEM and self._jobs:
                     with self._cv:                   # no slot / pages right now: wait for a sequence to leave
-                        self._pending.appendleft(job)
+                        self._pending.extendleft(reversed(batch[k:]))
                     return
                 job.future.set_exception(ex)         # can never fit (or a real error): this request fails, the others go on
                 continue

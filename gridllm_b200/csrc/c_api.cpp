@@ -137,6 +137,15 @@ int gl_seq_open(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_
     return rc;
 }
 
+int gl_seq_open_many(gl_engine* e, const int32_t* ids, const int32_t* offsets, int32_t n_seq, const gl_sample_opts* opts, int32_t* slots,
+                     int32_t* n_opened) {
+    if (!e || !ids || !offsets || !opts || !slots || !n_opened) return bad("gl_seq_open_many: null argument");
+    int k = 0;
+    const int rc = ret(e->impl->seq_open_many(ids, offsets, n_seq, opts, slots, &k));
+    *n_opened = k;
+    return rc;
+}
+
 int gl_batch_step(gl_engine* e, int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int32_t cap, int32_t* n) {
     if (!e || !n) return bad("gl_batch_step: null argument");
     int k = 0;

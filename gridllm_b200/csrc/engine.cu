@@ -418,7 +418,7 @@ Status Engine::ensure_pages(int n_tokens) {
     return {};
 }
 
-Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so) {
+StepState Engine::make_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so, int* sampler) const {
     StepState h{};
     h.pos = pos; h.token = token; h.n_prompt = n_prompt; h.out_idx = out_idx; h.done = 0;
     h.ignore_eos = so ? so->ignore_eos : 1;
@@ -430,12 +430,17 @@ Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl
     }
     h.bar_base = 0;
     // 0 greedy; 1 two-stage top-k sampler (top_k <= 64); 2 single-CTA radix select (sampler.cu)
-    sampler_ = !(so && so->temperature > 0.f) ? 0 : (sample_topk_fast_applies(so->top_k, n_vocab_) ? 1 : 2);
+    if (sampler) *sampler = !(so && so->temperature > 0.f) ? 0 : (sample_topk_fast_applies(so->top_k, n_vocab_) ? 1 : 2);
     h.temperature = so ? so->temperature : 0.f;
     h.top_k = so ? so->top_k : 0;
     h.top_p = (so && so->top_p > 0.f) ? so->top_p : 1.f;
     h.seed_lo = so ? (unsigned)(so->seed & 0xffffffffull) : 0u;
     h.seed_hi = so ? (unsigned)(so->seed >> 32) : 0u;
+    return h;
+}
+
+Status Engine::set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so) {
+    const StepState h = make_state(pos, token, n_prompt, out_idx, so, &sampler_);
     if (bar_counter_) CU(cudaMemsetAsync(bar_counter_, 0, 4, stream_));
     CU(cudaMemcpyAsync(st_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
     CU(cudaStreamSynchronize(stream_));     // h is on the stack

@@ -59,6 +59,7 @@ public:
     Status last_logits(int step, float* out, int n_vocab);
     // continuous batching (engine_batch.cu): B open sequences share one decode step
     Status seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, int* slot);
+    Status seq_open_many(const int32_t* ids, const int32_t* offs, int n_seq, const gl_sample_opts* opts, int32_t* slots, int* n_opened);
     Status batch_step(int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int cap, int* n);
     Status seq_close(int slot);
     Status seq_logits(int slot, float* out, int n_vocab);
@@ -92,6 +93,7 @@ private:
     Status plain_gemv(cudaStream_t s, const DevMatrix& m, const float* x, float* y, int* n_launch);
     Status build_graphs();
     Status set_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so);
+    StepState make_state(int pos, int token, int n_prompt, int out_idx, const gl_sample_opts* so, int* sampler) const;
     Status run_steps(int n_nohead, int n_head, bool keep_logits);
     Status enqueue_head(cudaStream_t s, bool keep_logits, int* n_launch);
     Status build_prefill_weights();
@@ -100,7 +102,9 @@ private:
     Status ensure_prefill_scratch(int t_pad);
     Status prefill_batched(int n, int* n_launch);     // tokens already in prompt_ids_[0..n)
     // embeddings: several sequences in ONE prompt pass (block-diagonal causal attention); seq s = rows [starts[s], starts[s] + lens[s])
-    Status prefill_packed(const std::vector<int>& starts, const std::vector<int>& lens, int t_rows, int* n_launch);
+    // tables: per sequence, the device page table its K / V rows are cached through (null: nothing is cached -- embeddings)
+    Status prefill_packed(const std::vector<int>& starts, const std::vector<int>& lens, int t_rows, int* n_launch,
+                          const std::vector<const int*>* tables = nullptr);
     static constexpr int EMB_PACK_TOKENS = 2048;      // rows of one packed pass (each sequence starts on a 128-row boundary)
     int* pk_ids_ = nullptr;                           // [EMB_PACK_TOKENS] token ids of a pack (pad rows: token 0)
     float *emb_out_ = nullptr, *emb_rstd_ = nullptr, *emb_pooled_ = nullptr;

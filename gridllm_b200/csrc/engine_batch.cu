@@ -253,6 +253,177 @@ Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opt
     return {};
 }
 
+// Several prompts at once: they share ONE packed prompt pass per <= EMB_PACK_TOKENS rows (engine_prefill.cu prefill_packed: the
+// linear layers see all their tokens as one [T x n_embd] matrix, each sequence attends only to itself and caches its K / V rows
+// through its own page table), then one lm_head GEMM over the last hidden row of every sequence and one sampler pass draw all the
+// first tokens.  32 prompts of 512 tokens: 8 passes with M = 2048 instead of 32 passes with M = 512, and one 1 GB lm_head read
+// instead of 32.  Sequences are opened in order until slots or KV pages run out: slots[i] = -1 for those that did not fit.
+Status Engine::seq_open_many(const int32_t* ids, const int32_t* offs, int n_seq, const gl_sample_opts* opts, int32_t* slots_out, int* n_opened) {
+    CU(cudaSetDevice(device_));
+    if (!ids || !offs || !opts || !slots_out || !n_opened || n_seq <= 0) return failb(GL_ERR_INVALID, "seq_open_many: bad argument");
+    *n_opened = 0;
+    ST(ensure_batch_state());
+    for (int i = 0; i < n_seq; ++i) {
+        slots_out[i] = -1;
+        const int n = offs[i + 1] - offs[i];
+        if (n <= 0) return failb(GL_ERR_INVALID, "seq_open_many: empty prompt");
+        for (int k = 0; k < n; ++k)
+            if (ids[offs[i] + k] < 0 || ids[offs[i] + k] >= n_vocab_) return failb(GL_ERR_INVALID, "prompt token id out of range");
+        if (!(opts[i].temperature >= 0.f) || !std::isfinite(opts[i].temperature)) return failb(GL_ERR_INVALID, "temperature must be a finite number >= 0");
+        const int n_pred = opts[i].num_predict > 0 ? opts[i].num_predict : 128;
+        if (n + n_pred > n_ctx_) return failb(GL_ERR_CONTEXT, "prompt + num_predict exceeds the engine context");
+    }
+    if (!pk_ids_) {
+        auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(p, bytes);
+            if (e == cudaSuccess) allocs_.push_back(*p);
+            return e;
+        };
+        CU(dalloc((void**)&pk_ids_, (size_t)EMB_PACK_TOKENS * 4));
+        CU(dalloc((void**)&emb_pooled_, (size_t)n_embd_ * 4));
+        CU(dalloc((void**)&emb_rstd_, (size_t)std::max(EMB_PACK_TOKENS, n_ctx_) * 4));
+    }
+    const bool packable = have_w16_ && prefill_mode_ != 1;
+    const int64_t t_open = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    int next = 0;
+    std::vector<int32_t> h_ids(EMB_PACK_TOKENS);
+    while (next < n_seq) {
+        // ---- one pack: as many of the next prompts as fit EMB_PACK_TOKENS rows, free slots and free pages ----
+        std::vector<int> starts, lens, which, pslots;
+        std::vector<const int*> tables;
+        int rows = 0;
+        bool out_of_room = false;
+        std::fill(h_ids.begin(), h_ids.end(), 0);
+        while (next < n_seq && (int)which.size() < MAX_BATCH) {
+            const int n = offs[next + 1] - offs[next], lp = (n + 127) / 128 * 128;
+            if (!packable || n > EMB_PACK_TOKENS || n < prefill_min_) break;              // this one goes through gl_seq_open's own path
+            if (rows + lp > EMB_PACK_TOKENS) break;
+            const int n_pred = opts[next].num_predict > 0 ? opts[next].num_predict : 128;
+            const int need = (n + n_pred + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+            int slot = -1;
+            for (int k = 0; k < max_batch_; ++k)
+                if (!slots_[k].open && std::find(pslots.begin(), pslots.end(), k) == pslots.end()) { slot = k; break; }
+            if (slot < 0 || (int)free_pages_.size() < need) { out_of_room = true; break; }
+            SeqSlot& S = slots_[slot];
+            S = SeqSlot{};
+            for (int k = 0; k < need; ++k) { S.pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
+            CU(cudaMemcpyAsync(btables_ + (size_t)slot * n_pages_, S.pages.data(), S.pages.size() * 4, cudaMemcpyHostToDevice, stream_));
+            std::memcpy(h_ids.data() + rows, ids + offs[next], (size_t)n * 4);
+            starts.push_back(rows); lens.push_back(n); which.push_back(next); pslots.push_back(slot);
+            tables.push_back(btables_ + (size_t)slot * n_pages_);
+            rows += lp;
+            ++next;
+        }
+        if (which.empty()) {
+            if (out_of_room) break;
+            // a prompt the packed pass does not take (too short / too long / no 16-bit weights): the single-sequence open
+            int slot = -1;
+            Status st = seq_open(ids + offs[next], offs[next + 1] - offs[next], opts[next], &slot);
+            if (!st.ok()) {
+                if (st.code == GL_ERR_NOMEM || *n_opened > 0) break;      // what was opened so far stays open and is reported
+                return st;
+            }
+            slots_out[next] = slot;
+            ++*n_opened;
+            ++next;
+            continue;
+        }
+        const int P = (int)which.size();
+        Status rs;
+        int launches = 0;
+        float pack_ms = 0.f;
+        std::vector<BatchOut> ho(P);
+        do {
+            cudaError_t ce = cudaMemcpyAsync(pk_ids_, h_ids.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, stream_);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ev_[2], stream_);
+            if (ce != cudaSuccess) { rs = failb(GL_ERR_CUDA, cudaGetErrorString(ce)); break; }
+            rs = prefill_packed(starts, lens, rows, &launches, &tables);
+            if (!rs.ok()) break;
+            // first tokens: last hidden row of each sequence -> rows 0..P-1 of the batched-step buffers -> final norm -> lm_head GEMM
+            for (int i = 0; i < P && ce == cudaSuccess; ++i)
+                ce = cudaMemcpyAsync(bx_ + (size_t)i * n_embd_, pf_x_ + (size_t)(starts[i] + lens[i] - 1) * n_embd_, (size_t)n_embd_ * 4,
+                                     cudaMemcpyDeviceToDevice, stream_);
+            if (ce == cudaSuccess) ce = batch_rmsnorm_launch(bx_, output_norm_, P, n_embd_, eps_, bxn16_, stream_);
+            if (ce == cudaSuccess) {
+                GemmParams g{};
+                g.a = bxn16_; g.b = head16_; g.c = blogits_; g.m = P; g.n = n_vocab_; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = n_vocab_;
+                g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
+                ce = gemm_tc5_supported(g) ? gemm_tc5_launch(g, MAX_BATCH, false, stream_) : gemm_tn_launch(g, false, stream_);
+            }
+            launches += P + 2;
+            // the sequences' step states and a temporary row map (the next gl_batch_step uploads its own)
+            std::vector<StepState> hst(P);
+            BatchCtl hc{};
+            hc.n_rows = P;
+            for (int i = 0; i < P && ce == cudaSuccess; ++i) {
+                const int w = which[i], n = lens[i];
+                int sampler = 0;
+                hst[i] = make_state(n - 1, ids[offs[w] + n - 1], n, 0, &opts[w], &sampler);
+                slots_[pslots[i]].sampler = sampler;
+                hc.row_slot[i] = pslots[i];
+                ce = cudaMemcpyAsync(bst_ + pslots[i], &hst[i], sizeof(StepState), cudaMemcpyHostToDevice, stream_);
+            }
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(bctl_, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_);
+            last_rows_.clear();
+            const int bucket = bucket_of(P);
+            if (ce == cudaSuccess) ce = batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, stream_);
+            for (int i = 0; i < P && ce == cudaSuccess; ++i) {
+                const int slot = pslots[i];
+                if (slots_[slot].sampler != 0) {
+                    SampleParams sp{blogits_ + (size_t)i * n_vocab_, n_vocab_, bst_ + slot, bout_ids_ + (size_t)slot * max_out_,
+                                    bout_lp_ + (size_t)slot * max_out_, nullptr, max_out_, sample_scratch_, topk_scratch_};
+                    ce = sample_topk_launch(sp, slots_[slot].sampler == 1, false, stream_);
+                }
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyAsync(bfirst_logits_ + (size_t)slot * n_vocab_, blogits_ + (size_t)i * n_vocab_, (size_t)n_vocab_ * 4,
+                                         cudaMemcpyDeviceToDevice, stream_);
+            }
+            if (ce == cudaSuccess) ce = batch_collect_launch(bctl_, bst_, bout_lp_, max_out_, bout_, bucket, stream_);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ev_[3], stream_);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(ho.data(), bout_, sizeof(BatchOut) * P, cudaMemcpyDeviceToHost, stream_);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream_);
+            if (ce != cudaSuccess) { rs = failb(GL_ERR_CUDA, cudaGetErrorString(ce)); break; }
+            cudaEventElapsedTime(&pack_ms, ev_[2], ev_[3]);
+            launches += 3;
+        } while (false);
+        if (!rs.ok()) {
+            for (int i = 0; i < P; ++i) {
+                for (int p : slots_[pslots[i]].pages) free_pages_.push_back(p);
+                slots_[pslots[i]] = SeqSlot{};
+            }
+            if (*n_opened > 0) break;                // earlier packs are open and reported; the caller sees -1 for the rest
+            return rs;
+        }
+        int64_t pack_tokens = 0;
+        for (int i = 0; i < P; ++i) pack_tokens += lens[i];
+        for (int i = 0; i < P; ++i) {
+            SeqSlot& S = slots_[pslots[i]];
+            const int w = which[i];
+            S.open = true;
+            S.n_prompt = lens[i];
+            S.n_pred = opts[w].num_predict > 0 ? opts[w].num_predict : 128;
+            S.produced = 0;
+            S.first_pending = true;
+            S.last_token = ho[i].token;
+            S.first_lp = ho[i].logprob;
+            S.done = ho[i].done != 0;
+            S.stopped = S.done;
+            S.t_open_ns = t_open;
+            S.prefill_ns = (int64_t)(pack_ms * 1e6 * (double)lens[i] / (double)pack_tokens);      // its share of the pass
+            S.launches = launches / P;
+            slots_out[w] = pslots[i];
+            bc_[4] += (uint64_t)lens[i];
+            bc_[5] += 1;
+        }
+        bc_[3] += (uint64_t)(pack_ms * 1e6);
+        bc_[6] += (uint64_t)launches;
+        *n_opened += P;
+        if (out_of_room) break;
+    }
+    if (*n_opened == 0) return failb(GL_ERR_NOMEM, "no free sequence slot / KV pages for any of the prompts");
+    return {};
+}
+
 Status Engine::seq_close(int slot) {
     if (slot < 0 || slot >= (int)slots_.size() || !slots_[slot].open) return failb(GL_ERR_INVALID, "seq_close: no such open sequence");
     for (int p : slots_[slot].pages) free_pages_.push_back(p);

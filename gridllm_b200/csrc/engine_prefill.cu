@@ -160,7 +160,8 @@ Status Engine::prefill_batched(int n, int* n_launch) {
 // matrix, T = all their tokens, every weight matrix read once per PACK instead of once per sequence -- and attend only inside
 // themselves (block-diagonal causal attention: the three attention launches run per sequence on its own rows).  Nothing is
 // cached: an embedding has no decode phase.  Hidden states end up in pf_x_ for pooling.
-Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<int>& lens, int t_rows, int* n_launch) {
+Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<int>& lens, int t_rows, int* n_launch,
+                              const std::vector<const int*>* tables) {
     const int TP = (t_rows + 127) / 128 * 128;
     const int qd = n_head_ * hd_, kvd = n_kv_ * hd_, ldq = qd + 2 * kvd, grp = n_head_ / n_kv_;
     ST(ensure_prefill_scratch(std::max(TP, 128)));
@@ -176,6 +177,8 @@ Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<
     const float scale = 1.0f / std::sqrt((float)hd_);
     for (int il = 0; il < n_layer_; ++il) {
         const LayerWeights& L = layers_[il];
+        __half* kc = tables ? kcache_ + (size_t)il * kv_layer_elems_ : nullptr;      // gl_seq_open_many: each sequence's K / V rows go
+        __half* vc = tables ? vcache_ + (size_t)il * kv_layer_elems_ : nullptr;      // to its own pages; embeddings cache nothing
         CU(rmsnorm_rows_launch(pf_x_, L.attn_norm, TP, TP, n_embd_, eps_, pf_xn_, bf, s)); ++nl;
         {
             GemmParams g{};
@@ -187,7 +190,7 @@ Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<
             const int r0 = starts[i], len = lens[i], lp = (len + 127) / 128 * 128;
             // RoPE at positions 0..len-1 of THIS sequence; V^T columns r0.. of the pack-wide [kvd][tp] matrix; no cache
             CU(rope_split_launch(pf_qkv_ + (size_t)r0 * ldq, len, lp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_ + (size_t)r0 * qd,
-                                 pf_k_ + (size_t)r0 * kvd, pf_vt_ + r0, nullptr, nullptr, nullptr, tp, s)); ++nl;
+                                 pf_k_ + (size_t)r0 * kvd, pf_vt_ + r0, kc, vc, tables ? (*tables)[i] : nullptr, tp, s)); ++nl;
             {   // S[h] = Q_h K_kvh^T, compact [n_head][lp][lp]
                 GemmParams g{};
                 g.a = pf_q_ + (size_t)r0 * qd; g.b = pf_k_ + (size_t)r0 * kvd; g.c = pf_s_; g.m = len; g.n = len; g.k = hd_; g.lda = qd; g.ldb = kvd; g.ldc = lp;

@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
     "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_chat_template", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
-    "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_batch_counters", "gl_time_batch_step",
+    "gl_seq_open", "gl_seq_open_many", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_batch_counters", "gl_time_batch_step",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -99,6 +99,7 @@ def load_library() -> C.CDLL:
     lib.gl_last_logits.argtypes = [vp, i32, f32p, i32]
     lib.gl_sample_logits.argtypes = [vp, f32p, i32, C.POINTER(SampleOpts), i32, i32p, f32p]
     lib.gl_seq_open.argtypes = [vp, i32p, i32, C.POINTER(SampleOpts), i32p]
+    lib.gl_seq_open_many.argtypes = [vp, i32p, i32p, i32, C.POINTER(SampleOpts), i32p, i32p]
     lib.gl_batch_step.argtypes = [vp, i32p, i32p, f32p, i32p, i32, i32p]
     lib.gl_seq_close.argtypes = [vp, i32]
     lib.gl_seq_logits.argtypes = [vp, i32, f32p, i32]
@@ -243,6 +244,30 @@ class Engine:
         slot = C.c_int32(-1)
         _check(self._lib.gl_seq_open(self._h, _i32p(p), len(p), C.byref(so), C.byref(slot)))
         return int(slot.value)
+
+    def seq_open_many(self, prompts: Sequence[Sequence[int]], options: Sequence[dict]) -> List[int]:
+        """Open several sequences with ONE packed prompt pass (gl_seq_open_many).  options[i]: the keyword arguments of seq_open
+        for prompt i.  Returns one slot per prompt, -1 for those that did not fit (no free slot / KV pages) -- retry them later."""
+        n = len(prompts)
+        offs = np.zeros(n + 1, dtype=np.int32)
+        for i, p in enumerate(prompts):
+            offs[i + 1] = offs[i] + len(p)
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32) for p in prompts]), dtype=np.int32)
+        so = (SampleOpts * n)()
+        keep = []                                      # stop-id arrays must outlive the call
+        for i, o in enumerate(options):
+            np_ = int(o.get("num_predict", 128))
+            so[i].num_predict, so[i].ignore_eos = (np_ if np_ > 0 else 128), int(bool(o.get("ignore_eos", False)))
+            so[i].temperature, so[i].top_k, so[i].top_p = float(o.get("temperature", 0.0)), int(o.get("top_k", 0)), float(o.get("top_p", 1.0))
+            so[i].seed = int(o.get("seed", 0)) & (2**64 - 1)
+            stops = np.ascontiguousarray(o.get("stop_ids", ()), dtype=np.int32)
+            keep.append(stops)
+            so[i].n_stop_ids = len(stops)
+            so[i].stop_ids = _i32p(stops) if len(stops) else None
+        slots = np.full(n, -1, dtype=np.int32)
+        k = C.c_int32(0)
+        _check(self._lib.gl_seq_open_many(self._h, _i32p(ids), _i32p(offs), n, so, _i32p(slots), C.byref(k)))
+        return [int(x) for x in slots]
 
     def batch_step(self, cap: int = 128):
         """-> [(slot, token id, logprob, done)]: one entry per open, unfinished sequence.  id -1 with done: a stop token was drawn."""

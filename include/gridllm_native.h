@@ -149,6 +149,13 @@ int  gl_embed(gl_engine* e, const int32_t* ids, const int32_t* seq_offsets, int3
  *   gl_seq_logits logits [n_vocab] the sequence's LAST token was drawn from (parity tests; valid until the next step).
  * Sequences join and leave between steps; a sequence's tokens do not depend on who shares its batch. */
 int  gl_seq_open(gl_engine* e, const int32_t* prompt, int32_t n_prompt, const gl_sample_opts* opts, int32_t* slot);
+/* Several prompts in one call: they share one packed prompt pass (block-diagonal causal attention, every weight matrix read
+ * once per <= 2048 prompt tokens instead of once per prompt) and one lm_head pass for their first tokens.  ids / offsets as for
+ * gl_embed (offsets has n_seq + 1 entries), opts has n_seq entries.  Prompts are opened in order until slots or KV pages run
+ * out: slots[i] = -1 for those that did not fit (the caller retries them after a gl_seq_close); *n_opened = how many did.
+ * GL_ERR_NOMEM only when none could be opened. */
+int  gl_seq_open_many(gl_engine* e, const int32_t* ids, const int32_t* offsets, int32_t n_seq, const gl_sample_opts* opts, int32_t* slots,
+                      int32_t* n_opened);
 int  gl_batch_step(gl_engine* e, int32_t* slots, int32_t* ids, float* logprobs, int32_t* done, int32_t cap, int32_t* n);
 int  gl_seq_close(gl_engine* e, int32_t slot);
 int  gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab);

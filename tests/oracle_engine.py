@@ -95,6 +95,24 @@ class OracleEngine:
                                               n_prompt=len(prompt), done=False, stopped=False, t0=time.perf_counter_ns())
         return free[0]
 
+    def seq_open_many(self, prompts, options):
+        from gridllm_b200.native import NativeError
+        self.open_many_calls = getattr(self, "open_many_calls", []) + [len(prompts)]
+        for p, o in zip(prompts, options):          # the engine validates everything before it opens anything
+            if len(p) + o.get("num_predict", 128) > self.info.n_ctx:
+                raise NativeError(-9, "prompt + num_predict exceeds the engine context")
+        slots = []
+        for p, o in zip(prompts, options):
+            try:
+                slots.append(self.seq_open(p, **o))
+            except NativeError as ex:
+                if ex.code != -6:
+                    raise
+                slots.append(-1)
+        if all(s < 0 for s in slots):
+            raise NativeError(-6, "no free sequence slot")
+        return slots
+
     def batch_step(self, cap=128):
         out = []
         self.batch_sizes = getattr(self, "batch_sizes", [])

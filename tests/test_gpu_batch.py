@@ -131,6 +131,41 @@ def test_large_batch_long_contexts(tiny128_gguf, mode):
     e.close()
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_open_many_equals_open_one_by_one(tiny128_gguf, mode):
+    """gl_seq_open_many: the prompts share packed prompt passes (each attends only to itself, caches K / V through its own page
+    table) and one lm_head pass.  Every sequence must continue exactly as if it had been opened alone: same first token and
+    logits bits (its rows never see a neighbour), same later tokens; prompts that do not fit come back as -1 and can be retried."""
+    e = _engine(tiny128_gguf, max_batch=8, max_ctx=1024, batch_weights=mode)
+    rng = np.random.Generator(np.random.PCG64(99))
+    lens = (300, 9, 512, 130, 4, 77, 256, 600, 33, 20)              # one shorter than the packed pass takes, several packs, 10 > 8 slots
+    prompts = [rng.integers(0, e.info.n_vocab - 3, size=n) for n in lens]
+    opts = [dict(num_predict=6, ignore_eos=True) for _ in lens]
+    opts[3] = dict(num_predict=6, ignore_eos=True, temperature=0.8, top_k=40, top_p=0.9, seed=11)       # a sampled one among them
+    alone = []
+    for p, o in zip(prompts, opts):
+        s = e.seq_open(p, **o)
+        lg = {}
+        ids, lps = _drain(e, {s: 6}, lg)[s]
+        alone.append((ids, lps, lg[s]))
+        e.seq_close(s)
+    slots = e.seq_open_many(prompts, opts)
+    assert len(slots) == 10 and sum(1 for s in slots if s >= 0) == 8 and slots[8] == -1 and slots[9] == -1     # in order, until the slots run out
+    live = [s for s in slots if s >= 0]
+    assert len(set(live)) == 8
+    lg = {}
+    got = _drain(e, {s: 6 for s in live}, lg)
+    for i, s in enumerate(slots[:8]):
+        assert got[s][0] == alone[i][0], (i, lens[i])
+        assert np.array_equal(lg[s][0], alone[i][2][0]), (i, "first-token logits")
+        e.seq_close(s)
+    rest = e.seq_open_many(prompts[8:], opts[8:])                    # the two that did not fit
+    assert all(s >= 0 for s in rest)
+    got = _drain(e, {s: 6 for s in rest})
+    assert [got[s][0] for s in rest] == [alone[8][0], alone[9][0]]
+    e.close()
+
+
 def test_sequences_join_and_leave_between_steps(tiny128_gguf):
     e = _engine(tiny128_gguf)
     rng = np.random.Generator(np.random.PCG64(17))

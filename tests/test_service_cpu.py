@@ -363,6 +363,7 @@ def test_concurrent_requests_are_decoded_together_and_match_the_oracle(bsvc):
     assert all(c.get("batched") for c in eng.calls)      # ... every request went through gl_seq_open, none through gl_generate
     runner = bsvc._runners["tiny:latest"]
     assert runner.max_rows == 4 and runner.steps >= 3
+    assert max(eng.open_many_calls) >= 2                 # requests that were waiting together were admitted in one engine call
 
 
 def test_batched_streams_stop_strings_and_cancellation(bsvc):
