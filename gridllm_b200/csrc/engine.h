@@ -230,6 +230,7 @@ private:
     int batch_launches_ = 0;                          // kernels of one batched step
     uint64_t bc_[8] = {};                             // gl_batch_counters
     Status ensure_batch_state();
+    Status seq_open_single(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, int* slot);
     Status enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch);
     Status run_batch_graph(int bucket);
     static int bucket_of(int rows) { int b = 8; while (b < rows) b <<= 1; return b; }

@@ -183,7 +183,23 @@ Status Engine::ensure_batch_state() {
 
 // Prefill a prompt into a free slot's own pages and draw its first token.  The single-sequence code runs unchanged on the
 // slot's state: the members it reads (page table, step state, output buffers) point at the slot's rows for the duration.
+// One prompt.  It takes the SAME path as a prompt opened together with others (gl_seq_open_many with one entry: packed prompt
+// pass, lm_head GEMM on the 16-bit matrix), so a sequence's first token does not depend on how it was admitted; only prompts the
+// packed pass does not take (shorter than 8 tokens, longer than a pack, no 16-bit weights) go through seq_open_single.
 Status Engine::seq_open(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, int* slot_out) {
+    if (!prompt || n_prompt <= 0 || !slot_out) return failb(GL_ERR_INVALID, "seq_open: empty prompt");
+    if (have_w16_ && prefill_mode_ != 1 && n_prompt >= prefill_min_ && n_prompt <= EMB_PACK_TOKENS) {
+        const int32_t offs[2] = {0, n_prompt};
+        int32_t slot = -1;
+        int n = 0;
+        ST(seq_open_many(prompt, offs, 1, &so, &slot, &n));
+        *slot_out = slot;
+        return {};
+    }
+    return seq_open_single(prompt, n_prompt, so, slot_out);
+}
+
+Status Engine::seq_open_single(const int32_t* prompt, int n_prompt, const gl_sample_opts& so, int* slot_out) {
     CU(cudaSetDevice(device_));
     if (!prompt || n_prompt <= 0 || !slot_out) return failb(GL_ERR_INVALID, "seq_open: empty prompt");
     for (int i = 0; i < n_prompt; ++i)
@@ -318,7 +334,7 @@ Status Engine::seq_open_many(const int32_t* ids, const int32_t* offs, int n_seq,
             if (out_of_room) break;
             // a prompt the packed pass does not take (too short / too long / no 16-bit weights): the single-sequence open
             int slot = -1;
-            Status st = seq_open(ids + offs[next], offs[next + 1] - offs[next], opts[next], &slot);
+            Status st = seq_open_single(ids + offs[next], offs[next + 1] - offs[next], opts[next], &slot);
             if (!st.ok()) {
                 if (st.code == GL_ERR_NOMEM || *n_opened > 0) break;      // what was opened so far stays open and is reported
                 return st;
