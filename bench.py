@@ -375,17 +375,15 @@ def main():
                 "clocks": out["clocks"]}
         line.update(out.get("extra", {}))
         if not args.no_cpu:
+            # the CPU leg runs in its own process (the reference arm of this same file, two measured samples after a warm one): the
+            # engines are gone by now, and an OpenMP runtime started inside a process that has run CUDA, asyncio and a batch-runner
+            # thread has been seen to stall for minutes -- a separate process cannot
             try:
-                cpu = CpuRestatement(path, 640 if wl in ("config2", "config3") else 512)
-                n1, d1, desc = cpu_step(cpu, wl, 0)                    # warm
-                units, secs = 0, 0.0
-                for i in range(1, 3):
-                    n, dt, desc = cpu_step(cpu, wl, i)
-                    units += n
-                    secs += dt
-                line["cpu_baseline"] = {"value": units / secs, "unit": unit, "cores": cpu.threads, "kind": "port", "sample": desc + " (2 samples after a warm one)",
-                                        "lib": cpu.so}
-                cpu.close()
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", wl, "--steps", "2", "--warmup", "1"],
+                                   capture_output=True, text=True, timeout=420,
+                                   env={k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")})
+                ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                line["cpu_baseline"] = dict(ref["cpu_baseline"], sample=ref["cpu_baseline"]["sample"] + " (2 measured samples after a warm one)")
             except Exception as ex:  # the baseline is a report, never a gate
                 line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
         print(json.dumps(line), flush=True)

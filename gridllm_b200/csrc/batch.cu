@@ -4,6 +4,9 @@
 // (client/src/services/WorkerClientService.ts:500-505) decide whether a worker ever sees more than one request.
 #include "batch.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "attn_core.cuh"
 #include "common.cuh"
 
@@ -31,7 +34,9 @@ __global__ void __launch_bounds__(256) batch_rope_kv_kernel(const float* __restr
     const int page = tables[(size_t)slot * table_stride + pos / KV_PAGE_TOKENS], tok = pos % KV_PAGE_TOKENS;
     const int qd = n_head * hd, kvd = n_kv * hd, ld = qd + 2 * kvd;
     const float* row = qkv + (size_t)r * ld;
-    for (int i = threadIdx.x; i < (qd + kvd) / 2; i += 256) {
+    // blockIdx.y: the row's work is cut into gridDim.y slices (one CTA per row left 32 CTAs walking ten dependent loads each)
+    const int tid = blockIdx.y * 256 + threadIdx.x, nthr = gridDim.y * 256;
+    for (int i = tid; i < (qd + kvd) / 2; i += nthr) {
         const int e = 2 * i, d = e % hd;
         const float c = cos_t[(size_t)pos * (hd / 2) + d / 2], s = sin_t[(size_t)pos * (hd / 2) + d / 2];
         const float a = row[e], b = row[e + 1];
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(256) batch_rope_kv_kernel(const float* __restr
             *reinterpret_cast<__half2*>(k_cache + off) = __halves2half2(__float2half_rn(o0), __float2half_rn(o1));
         }
     }
-    for (int i = threadIdx.x; i < kvd / 2; i += 256) {
+    for (int i = tid; i < kvd / 2; i += nthr) {
         const int e = 2 * i, kvh = e / hd, d = e % hd;
         const size_t off = (((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d;
         *reinterpret_cast<__half2*>(v_cache + off) =
@@ -177,9 +182,220 @@ __global__ void __launch_bounds__(32 * B_MAX_GRP) batch_attn_kernel(const __grid
         *reinterpret_cast<__half2*>(out + d) = __halves2half2(__float2half_rn(acc[d] * inv), __float2half_rn(acc[d + 1] * inv));
 }
 
+
+// ---- the same attention on the tensor cores (mma.sync m16n8k16) --------------------------------------------------------------
+// The kernel above spends ~560 instructions per (page, query head): with B = 32 sequences at 576 tokens that is 20 M warp
+// instructions per layer, 39 us of a step in which the KV bytes themselves need 12 us (profiles/r02_runC).  Here ONE warp serves
+// all the query heads of a KV head at once: the GQA group is the M dimension of the MMA (rows = query heads, padded to 16),
+// S = Q K^T and O += P V are 32 tensor-core instructions per 16-token page instead of ~2 000 scalar ones.
+//   grid (KV head, split, row), 4 warps; the CTA's pages (split s: pages s, s + S, ...) are dealt round-robin to the warps;
+//   each warp streams its pages with cp.async (16-byte chunks, XOR-swizzled by the row so that ldmatrix is conflict-free)
+//   through its own double buffer -- no CTA barrier inside the loop; K fragments by ldmatrix, V fragments by ldmatrix.trans;
+//   online softmax per query head in the accumulator layout; the four warps' partial (m, l, O) are merged through shared
+//   memory, the splits through the same atomic ticket as above.  Bound: HBM (KV pages).
+template <int HD> struct BamCfg {
+    static constexpr int ROW_BYTES = HD * 2;
+    static constexpr int PAGE_BYTES = KV_PAGE_TOKENS * ROW_BYTES;
+    static constexpr int CHUNKS_PER_ROW = ROW_BYTES / 16;
+    static constexpr int WARP_BYTES = 2 /*buffers*/ * 2 /*K, V*/ * PAGE_BYTES;
+    static constexpr size_t SMEM = (size_t)4 * WARP_BYTES;       // 64 KB (head_dim 128): three CTAs per SM; the merge reuses the page buffers
+    static_assert(8 * (HD + 2) * 4 <= WARP_BYTES, "a warp's (m, l, O) of 8 heads must fit its own page buffers");
+};
+
+__device__ __forceinline__ void bam_cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bam_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bam_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bam_ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void bam_ldmatrix_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D (fp32, 16 x 8) += A (fp16, 16 x 16, row) * B (fp16, 16 x 8, col)
+__device__ __forceinline__ void bam_mma(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t bam_pack(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128, 3) batch_attn_mma_kernel(const __grid_constant__ BatchAttnParams p) {
+    using Cfg = BamCfg<HD>;
+    constexpr int KSTEPS = HD / 16, NT = HD / 8;
+    extern __shared__ __align__(128) uint8_t bam_smem[];
+    __shared__ int is_last;
+
+    const int row = blockIdx.z;
+    if (row >= p.ctl->n_rows) return;
+    const int slot = p.ctl->row_slot[row];
+    const int* table = p.tables + (size_t)slot * p.table_stride;
+    const int kvh = blockIdx.x, split = blockIdx.y, S = p.n_splits;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int grp = p.n_head / p.n_kv_heads;
+    const int L = p.st[slot].pos + 1;
+    const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
+    const int active = min(n_pages, S);
+    if (split >= active) return;
+    const int my_pages = (n_pages - split + S - 1) / S;              // pages of this CTA: split, split + S, ...
+    const int w_pages = (my_pages - warp + 3) / 4;                   // ... of which this warp takes every fourth
+
+    uint8_t* wbuf = bam_smem + (size_t)warp * Cfg::WARP_BYTES;
+
+    // Q fragments: rows = the group's query heads (g < grp), pre-scaled, fp16.  Rows 8..15 of the MMA tile stay zero.
+    uint32_t qa[KSTEPS][2];
+    {
+        const float* q = p.q + ((size_t)row * p.n_head + (size_t)kvh * grp + g) * HD;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+            if (g < grp) {
+                lo = *reinterpret_cast<const float2*>(q + ks * 16 + 2 * t);
+                hi = *reinterpret_cast<const float2*>(q + ks * 16 + 8 + 2 * t);
+            }
+            qa[ks][0] = bam_pack(lo.x * p.scale, lo.y * p.scale);
+            qa[ks][1] = bam_pack(hi.x * p.scale, hi.y * p.scale);
+        }
+    }
+    float o[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    float m_run = -INFINITY, l_run = 0.f;
+
+    auto issue = [&](int j) {          // page j of this warp -> buffer j & 1 (K then V), 16-byte chunks swizzled by the row
+        const int pg = split + (warp + 4 * j) * S;
+        const size_t off = ((size_t)table[pg] * p.n_kv_heads + kvh) * (size_t)(KV_PAGE_TOKENS * HD);
+        const uint8_t* ksrc = reinterpret_cast<const uint8_t*>(p.k_cache + off);
+        const uint8_t* vsrc = reinterpret_cast<const uint8_t*>(p.v_cache + off);
+        const uint32_t kdst = smem_u32(wbuf + (size_t)(j & 1) * 2 * Cfg::PAGE_BYTES), vdst = kdst + Cfg::PAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < Cfg::PAGE_BYTES / 16 / 32; ++i) {
+            const int ci = i * 32 + lane, r = ci / Cfg::CHUNKS_PER_ROW, c = ci % Cfg::CHUNKS_PER_ROW;
+            const uint32_t d = (uint32_t)(r * Cfg::ROW_BYTES + ((c ^ (r & 7)) << 4));
+            bam_cp_async16(kdst + d, ksrc + (size_t)ci * 16);
+            bam_cp_async16(vdst + d, vsrc + (size_t)ci * 16);
+        }
+        bam_commit();
+    };
+    if (w_pages > 0) issue(0);
+    for (int j = 0; j < w_pages; ++j) {
+        if (j + 1 < w_pages) { issue(j + 1); bam_wait<1>(); } else { bam_wait<0>(); }
+        __syncwarp();
+        const uint32_t kb = smem_u32(wbuf + (size_t)(j & 1) * 2 * Cfg::PAGE_BYTES), vb = kb + Cfg::PAGE_BYTES;
+        const int pg = split + (warp + 4 * j) * S;
+        const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
+        // ---- S = Q K^T : two n-tiles (positions 0-7, 8-15) ----
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            // matrices: (pos 0-7, dims k0..+7), (pos 0-7, dims k0+8..+15), (pos 8-15, k0..+7), (pos 8-15, k0+8..+15)
+            const int m = lane >> 3, pos = (lane & 7) + 8 * (m >> 1), chunk = 2 * ks + (m & 1);
+            uint32_t b0, b1, b2, b3;
+            bam_ldmatrix_x4(kb + (uint32_t)(pos * Cfg::ROW_BYTES + ((chunk ^ (pos & 7)) << 4)), b0, b1, b2, b3);
+            bam_mma(s0, qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);
+            bam_mma(s1, qa[ks][0], 0u, qa[ks][1], 0u, b2, b3);
+        }
+        // ---- online softmax of row g (query head g): this thread holds columns 2t, 2t+1 of both n-tiles ----
+        float v0 = (2 * t < npos) ? s0[0] : -INFINITY, v1 = (2 * t + 1 < npos) ? s0[1] : -INFINITY;
+        float v2 = (8 + 2 * t < npos) ? s1[0] : -INFINITY, v3 = (9 + 2 * t < npos) ? s1[1] : -INFINITY;
+        float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run, mx);                       // npos >= 1: finite
+        const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+        const float p0 = expf(v0 - m_new), p1 = expf(v1 - m_new), p2 = expf(v2 - m_new), p3 = expf(v3 - m_new);      // exp(-inf) = 0
+        float ps = (p0 + p1) + (p2 + p3);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+        l_run = l_run * corr + ps;
+        m_run = m_new;
+        // P as the A operand of the second MMA (rows 8..15 zero): k = positions
+        const uint32_t pa0 = bam_pack(p0, p1), pa2 = bam_pack(p2, p3);
+        // ---- O = O * corr + P V ----
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { o[n][0] *= corr; o[n][1] *= corr; }
+#pragma unroll
+        for (int n2 = 0; n2 < NT / 2; ++n2) {
+            // transposed loads: (pos 0-7, dims n0..+7), (pos 8-15, n0..+7), (pos 0-7, n0+8..+15), (pos 8-15, n0+8..+15)
+            const int m = lane >> 3, pos = (lane & 7) + 8 * (m & 1), chunk = 2 * n2 + (m >> 1);
+            uint32_t b0, b1, b2, b3;
+            bam_ldmatrix_x4_t(vb + (uint32_t)(pos * Cfg::ROW_BYTES + ((chunk ^ (pos & 7)) << 4)), b0, b1, b2, b3);
+            bam_mma(o[2 * n2], pa0, 0u, pa2, 0u, b0, b1);
+            bam_mma(o[2 * n2 + 1], pa0, 0u, pa2, 0u, b2, b3);
+        }
+        __syncwarp();                                                 // every lane is done with this buffer before it is refilled
+    }
+
+    // ---- merge the four warps (each holds (m, l, O) of heads g < grp over ITS pages), then the splits ----
+    // (each warp writes its partial over its OWN page buffers -- it is done with them -- and reads the others' after the barrier)
+    if (g < grp) {
+        float* mw = reinterpret_cast<float*>(wbuf) + (size_t)g * (HD + 2);
+        if (t == 0) { mw[HD] = m_run; mw[HD + 1] = l_run; }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { mw[8 * n + 2 * t] = o[n][0]; mw[8 * n + 2 * t + 1] = o[n][1]; }
+    }
+    __syncthreads();
+    const size_t pbase = ((size_t)row * p.n_head + (size_t)kvh * grp) * S;      // partial slots of this KV head's first query head
+    for (int e = threadIdx.x; e < grp * HD; e += 128) {
+        const int h = e / HD, d = e % HD;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, reinterpret_cast<const float*>(bam_smem + (size_t)w * Cfg::WARP_BYTES)[(size_t)h * (HD + 2) + HD]);
+        float den = 0.f, acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float* mw = reinterpret_cast<const float*>(bam_smem + (size_t)w * Cfg::WARP_BYTES) + (size_t)h * (HD + 2);
+            const float wgt = (mw[HD] == -INFINITY) ? 0.f : expf(mw[HD] - M);
+            den += wgt * mw[HD + 1];
+            acc += wgt * mw[d];
+        }
+        if (active == 1) {
+            p.out16[((size_t)row * p.n_head + (size_t)kvh * grp + h) * HD + d] = __float2half_rn(acc / den);
+        } else {
+            p.part_o[(pbase + (size_t)h * S + split) * HD + d] = acc;
+            if (d == 0) {
+                p.part_ml[(pbase + (size_t)h * S + split) * 2] = M;
+                p.part_ml[(pbase + (size_t)h * S + split) * 2 + 1] = den;
+            }
+        }
+    }
+    if (active == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* ctr = p.counters + (size_t)row * p.n_kv_heads + kvh;
+        unsigned ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(ctr) : "memory");
+        is_last = (ticket == (unsigned)active - 1);
+        if (is_last) *ctr = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    for (int e = threadIdx.x; e < grp * HD; e += 128) {              // splits in order: the result does not depend on who came last
+        const int h = e / HD, d = e % HD;
+        const size_t pb = pbase + (size_t)h * S;
+        float M = -INFINITY;
+        for (int s2 = 0; s2 < active; ++s2) M = fmaxf(M, __ldcg(p.part_ml + (pb + s2) * 2));
+        float den = 0.f, acc = 0.f;
+        for (int s2 = 0; s2 < active; ++s2) {
+            const float wgt = expf(__ldcg(p.part_ml + (pb + s2) * 2) - M);
+            den += wgt * __ldcg(p.part_ml + (pb + s2) * 2 + 1);
+            acc += wgt * __ldcg(p.part_o + (pb + s2) * HD + d);
+        }
+        p.out16[((size_t)row * p.n_head + (size_t)kvh * grp + h) * HD + d] = __float2half_rn(acc / den);
+    }
+}
+
 // Greedy rows: one CTA per row scans the row's logits once (max / lowest argmax / sum of exponentials, the single-sequence
 // sampler's arithmetic: ties go to the lowest index; logprob = -log(sum exp(l - max))) and advances the row's StepState.
-constexpr int BS_THREADS = 1024;
+constexpr int BS_THREADS = 512;
+constexpr int BS_PARTS = BATCH_SAMPLE_PARTS;
+constexpr int BS_ROW_FLOATS = BATCH_SAMPLE_ROW_FLOATS;
 struct BCand { float m; int i; float s; };
 __device__ __forceinline__ BCand bcand_merge(BCand a, BCand b) {
     if (b.m > a.m || (b.m == a.m && b.i < a.i)) { const BCand t = a; a = b; b = t; }
@@ -189,17 +405,22 @@ __device__ __forceinline__ BCand bcand_merge(BCand a, BCand b) {
 }
 __global__ void __launch_bounds__(BS_THREADS) batch_sample_greedy_kernel(const float* __restrict__ logits, int n_vocab,
                                                                          const BatchCtl* __restrict__ ctl, StepState* __restrict__ stv,
-                                                                         int* __restrict__ out_ids, float* __restrict__ out_lps, int max_out) {
-    const int row = blockIdx.x;
+                                                                         int* __restrict__ out_ids, float* __restrict__ out_lps, int max_out,
+                                                                         float* __restrict__ scratch) {
+    // grid (row, part): BS_PARTS CTAs scan a row's logits (one CTA per row left 32 CTAs walking 513 KB each: 73 us of a step);
+    // the last one of a row (atomic ticket) merges the parts IN PART ORDER and advances the row's state
+    const int row = blockIdx.x, part = blockIdx.y;
     if (row >= ctl->n_rows) return;
     const int slot = ctl->row_slot[row];
     StepState* st = stv + slot;
     if (st->temperature > 0.f) return;               // sampled rows: the seeded top-k sampler runs on them after this kernel
     __shared__ BCand sc[BS_THREADS / 32];
+    __shared__ int is_last;
     const float* lg = logits + (size_t)row * n_vocab;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n_vocab + BS_PARTS - 1) / BS_PARTS, i0 = part * per, i1 = min(n_vocab, i0 + per);
     BCand c{-INFINITY, 0x7fffffff, 0.f};
-    for (int i = tid; i < n_vocab; i += BS_THREADS) {
+    for (int i = i0 + tid; i < i1; i += BS_THREADS) {
         const float v = lg[i];
         if (v > c.m) {                               // ascending indices per thread: strict > keeps the lowest on ties
             c.s = (c.m == -INFINITY ? 0.f : c.s * expf(c.m - v)) + 1.f;
@@ -216,9 +437,23 @@ __global__ void __launch_bounds__(BS_THREADS) batch_sample_greedy_kernel(const f
     }
     if (lane == 0) sc[warp] = c;
     __syncthreads();
-    if (tid != 0) return;
-    BCand t = sc[0];
-    for (int w = 1; w < BS_THREADS / 32; ++w) t = bcand_merge(t, sc[w]);
+    float* rs = scratch + (size_t)row * BS_ROW_FLOATS;      // [BS_PARTS][m, i, s] + ticket
+    if (tid == 0) {
+        BCand t = sc[0];
+        for (int w = 1; w < BS_THREADS / 32; ++w) t = bcand_merge(t, sc[w]);
+        rs[part * 3] = t.m;
+        reinterpret_cast<int*>(rs)[part * 3 + 1] = t.i;
+        rs[part * 3 + 2] = t.s;
+        __threadfence();
+        unsigned ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(reinterpret_cast<unsigned*>(rs) + 3 * BS_PARTS) : "memory");
+        is_last = ticket == (unsigned)BS_PARTS - 1;
+        if (is_last) reinterpret_cast<unsigned*>(rs)[3 * BS_PARTS] = 0;
+    }
+    __syncthreads();
+    if (!is_last || tid != 0) return;
+    BCand t{__ldcg(rs), __ldcg(reinterpret_cast<const int*>(rs) + 1), __ldcg(rs + 2)};
+    for (int k = 1; k < BS_PARTS; ++k) t = bcand_merge(t, BCand{__ldcg(rs + 3 * k), __ldcg(reinterpret_cast<const int*>(rs) + 3 * k + 1), __ldcg(rs + 3 * k + 2)});
     if (st->done) return;
     const int out_idx = st->out_idx;
     if (out_idx < max_out) {
@@ -279,14 +514,29 @@ cudaError_t batch_gather_tokens_launch(const BatchCtl* ctl, const StepState* st,
 cudaError_t batch_rope_kv_launch(const float* qkv, int bucket, const BatchCtl* ctl, const StepState* st, const int* tables, int table_stride,
                                  int n_head, int n_kv, int hd, const float* cos_t, const float* sin_t, float* q_out, __half* k_cache,
                                  __half* v_cache, cudaStream_t s) {
-    batch_rope_kv_kernel<<<bucket, 256, 0, s>>>(qkv, ctl, st, tables, table_stride, n_head, n_kv, hd, cos_t, sin_t, q_out, k_cache, v_cache);
+    const int slices = std::max(1, std::min(8, ((n_head + n_kv) * hd / 2 + 255) / 256));
+    batch_rope_kv_kernel<<<dim3((unsigned)bucket, (unsigned)slices), 256, 0, s>>>(qkv, ctl, st, tables, table_stride, n_head, n_kv, hd, cos_t, sin_t, q_out,
+                                                                                   k_cache, v_cache);
     return cudaGetLastError();
+}
+
+cudaError_t batch_attn_configure() {
+    cudaError_t e = cudaFuncSetAttribute(batch_attn_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BamCfg<128>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(batch_attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BamCfg<64>::SMEM);
+    return e;
 }
 
 cudaError_t batch_attn_launch(const BatchAttnParams& p, int bucket, cudaStream_t s) {
     const int grp = p.n_head / p.n_kv_heads;
     if (grp < 1 || grp > B_MAX_GRP || p.n_head % p.n_kv_heads || p.n_splits < 1 || p.n_splits > 32) return cudaErrorInvalidValue;
     const dim3 grid((unsigned)p.n_kv_heads, (unsigned)p.n_splits, (unsigned)bucket);
+    static const bool use_mma = []() { const char* e = getenv("GL_BATCH_ATTN_MMA"); return !(e && e[0] == '0'); }();
+    if (use_mma) {       // tensor-core kernel (default); GL_BATCH_ATTN_MMA=0 keeps the scalar one for A/B runs
+        if (p.head_dim == 128) batch_attn_mma_kernel<128><<<grid, 128, BamCfg<128>::SMEM, s>>>(p);
+        else if (p.head_dim == 64) batch_attn_mma_kernel<64><<<grid, 128, BamCfg<64>::SMEM, s>>>(p);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    }
     if (p.head_dim == 128) batch_attn_kernel<4><<<grid, 32 * grp, 0, s>>>(p);
     else if (p.head_dim == 64) batch_attn_kernel<2><<<grid, 32 * grp, 0, s>>>(p);
     else return cudaErrorInvalidValue;
@@ -294,8 +544,8 @@ cudaError_t batch_attn_launch(const BatchAttnParams& p, int bucket, cudaStream_t
 }
 
 cudaError_t batch_sample_greedy_launch(const float* logits, int n_vocab, int bucket, const BatchCtl* ctl, StepState* st, int* out_ids,
-                                       float* out_lps, int max_out, cudaStream_t s) {
-    batch_sample_greedy_kernel<<<bucket, BS_THREADS, 0, s>>>(logits, n_vocab, ctl, st, out_ids, out_lps, max_out);
+                                       float* out_lps, int max_out, float* scratch, cudaStream_t s) {
+    batch_sample_greedy_kernel<<<dim3((unsigned)bucket, BS_PARTS), BS_THREADS, 0, s>>>(logits, n_vocab, ctl, st, out_ids, out_lps, max_out, scratch);
     return cudaGetLastError();
 }
 

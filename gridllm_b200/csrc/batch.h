@@ -55,12 +55,15 @@ cudaError_t batch_gather_tokens_launch(const BatchCtl* ctl, const StepState* st,
 cudaError_t batch_rope_kv_launch(const float* qkv, int bucket, const BatchCtl* ctl, const StepState* st, const int* tables, int table_stride,
                                  int n_head, int n_kv, int hd, const float* cos_t, const float* sin_t, float* q_out, __half* k_cache,
                                  __half* v_cache, cudaStream_t s);
+cudaError_t batch_attn_configure();      // opt in to the tensor-core attention kernel's dynamic shared memory (once per device)
 cudaError_t batch_attn_launch(const BatchAttnParams& p, int bucket, cudaStream_t s);
 // greedy rows (temperature 0): argmax + log-softmax of the winner over logits [bucket][n_vocab]; advances the row's StepState
 // and writes out_ids / out_lps [slot][max_out] exactly like the single-sequence sampler.  Rows with temperature > 0 are skipped
 // (the host launches the seeded top-k sampler on them).
+constexpr int BATCH_SAMPLE_PARTS = 8;                                   // CTAs per row
+constexpr int BATCH_SAMPLE_ROW_FLOATS = 3 * BATCH_SAMPLE_PARTS + 1;     // scratch per row: per part (max, argmax, sum exp) + a ticket; zero at first
 cudaError_t batch_sample_greedy_launch(const float* logits, int n_vocab, int bucket, const BatchCtl* ctl, StepState* st, int* out_ids,
-                                       float* out_lps, int max_out, cudaStream_t s);
+                                       float* out_lps, int max_out, float* scratch /*[MAX_BATCH][BATCH_SAMPLE_ROW_FLOATS]*/, cudaStream_t s);
 // out[r] = {token, logprob, done, pos} of row r after its sampler ran
 cudaError_t batch_collect_launch(const BatchCtl* ctl, const StepState* st, const float* out_lps, int max_out, BatchOut* out, int bucket,
                                  cudaStream_t s);

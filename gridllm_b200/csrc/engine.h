@@ -212,7 +212,7 @@ private:
     StepState* bst_ = nullptr;                        // [MAX_BATCH]
     int* btables_ = nullptr;                          // [MAX_BATCH][n_pages_]
     int *bids_ = nullptr, *bout_ids_ = nullptr;
-    float *bx_ = nullptr, *bqkv_ = nullptr, *bq_ = nullptr, *blogits_ = nullptr, *bfirst_logits_ = nullptr, *bout_lp_ = nullptr, *bpart_o_ = nullptr, *bpart_ml_ = nullptr;
+    float *bx_ = nullptr, *bqkv_ = nullptr, *bq_ = nullptr, *blogits_ = nullptr, *bfirst_logits_ = nullptr, *bout_lp_ = nullptr, *bpart_o_ = nullptr, *bpart_ml_ = nullptr, *bsample_scratch_ = nullptr;
     __half *bxn16_ = nullptr, *battn16_ = nullptr, *bh16_ = nullptr;
     unsigned* bcounters_ = nullptr;
     BatchOut* bout_ = nullptr;

@@ -78,6 +78,7 @@ Status Engine::pack_qgemm(const std::vector<const GGUFTensor*>& src, int mode, Q
     CU(cudaMemcpy(out.tile_off, toff.data(), (size_t)out.n_tiles * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(out.tile_type, ttype.data(), (size_t)out.n_tiles, cudaMemcpyHostToDevice));
     CU(cudaMemset(out.counters, 0, (size_t)out.n_tiles * 4));
+    out.describe(toff.data(), ttype.data());
     return {};
 }
 
@@ -139,6 +140,7 @@ Status Engine::ensure_batch_state() {
         return e;
     };
     const size_t R = MAX_BATCH;
+    CU(batch_attn_configure());
     CU(dalloc((void**)&bctl_, sizeof(BatchCtl)));
     CU(dalloc((void**)&btables_, R * n_pages_ * 4));
     CU(dalloc((void**)&bids_, R * 4));
@@ -156,6 +158,7 @@ Status Engine::ensure_batch_state() {
     CU(dalloc((void**)&bpart_o_, R * n_head_ * 16 * hd_ * 4));
     CU(dalloc((void**)&bpart_ml_, R * n_head_ * 16 * 2 * 4));
     CU(dalloc((void**)&bcounters_, R * n_kv_ * 4));
+    CU(dalloc((void**)&bsample_scratch_, R * BATCH_SAMPLE_ROW_FLOATS * 4));
     // the lm_head as a 16-bit matrix (the layer matrices already have their copy: build_prefill_weights)
     CU(dalloc(&head16_, (size_t)n_vocab_ * n_embd_ * 2));
     CU(dequant_rows_launch(output_.w, output_.type, output_.rows, output_.cols, output_.row_stride, output_.tile_rows, head16_, n_embd_, 0, 0, false,
@@ -382,7 +385,7 @@ Status Engine::seq_open_many(const int32_t* ids, const int32_t* offs, int n_seq,
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(bctl_, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_);
             last_rows_.clear();
             const int bucket = bucket_of(P);
-            if (ce == cudaSuccess) ce = batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, stream_);
+            if (ce == cudaSuccess) ce = batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, bsample_scratch_, stream_);
             for (int i = 0; i < P && ce == cudaSuccess; ++i) {
                 const int slot = pslots[i];
                 if (slots_[slot].sampler != 0) {
@@ -514,7 +517,7 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
     }
     CU(batch_rmsnorm_launch(bx_, output_norm_, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
     CU(linear(bxn16_, head16_, blogits_, n_vocab_, n_embd_, n_vocab_, GEMM_EPI_F32, use_q ? &qhead_ : nullptr));
-    CU(batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, s)); ++nl;
+    CU(batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, bsample_scratch_, s)); ++nl;
     if (n_launch) *n_launch = nl;
     return {};
 }

@@ -39,27 +39,33 @@ namespace gl {
 
 namespace {
 
-constexpr int QG_THREADS = 14 * 32;
-constexpr int QG_RAW_STRIDE = 27648;                 // >= 26 880, multiple of 1024
-constexpr int QG_A_SLOTS = 4;                        // operand-tile ring = the four K-steps of one qtile
+constexpr int QG_THREADS = 15 * 32;
+constexpr int QG_A_SLOTS = 6;                        // operand-tile ring: 1.5 qtiles, so the unpack warps never wait for the MMAs of the qtile before
+constexpr int QG_ACT_UNITS = 2;                      // activation ring: the four [NB x 64] boxes of two qtiles
+constexpr size_t QG_SMEM = 227 * 1024;               // the whole opt-in shared memory; the raw ring takes what the other two leave
 
 template <int NB> struct QCfg {
-    static constexpr int STAGES = NB <= 32 ? 3 : 2;
     static constexpr int B_TILE = NB * 128;          // activations [NB rows x 64] fp16, 128-byte swizzle
-    static constexpr int STAGE_BYTES = QG_RAW_STRIDE + 4 * B_TILE;
+    static constexpr int ACT_BYTES = QG_ACT_UNITS * 4 * B_TILE;
+    static constexpr int A_BYTES = QG_A_SLOTS * QG_A_TILE_BYTES;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int RAW_BUDGET = (int)QG_SMEM - 1024 /* alignment */ - BAR_BYTES - ACT_BYTES - A_BYTES;
     static constexpr int TMEM_COLS = 2 * NB < 32 ? 32 : 2 * NB;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (size_t)QG_A_SLOTS * QG_A_TILE_BYTES + 1024 /* alignment */ + 512 /* barriers */;
 };
+constexpr int QG_MAX_RAW_STAGES = 6;
 
 struct QParams {
     CUtensorMap tb;              // activations: dims {K, rows_alloc}, box {64, NB}, 128-byte swizzle
     const uint8_t* w;
-    const uint64_t* tile_off;
+    const uint64_t* tile_off;    // per-tile tables: only when the GEMM's tiles are not "type0 up to tile_split, then type1"
     const uint8_t* tile_type;
     unsigned* counters;
     float* partial;              // [grid][2][NB * 128]
     void* c;
     int ldc, epi, n, n_tiles, nkb;
+    int type0, type1, tile_split;          // tiles [0, tile_split) are type0, the rest type1 (Q | K | V with a Q6_K V); tile_split = n_tiles when uniform
+    unsigned long long off_split;          // byte offset of tile tile_split
+    int raw_stride, raw_stages;            // raw ring geometry: stride = the largest qtile of this GEMM (18 432 or 27 648)
 };
 
 __device__ __forceinline__ void tma_load_2d_q(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -103,6 +109,17 @@ __device__ __forceinline__ long long q_range_start(int c, long long U, int G) { 
 // largest c with range_start(c) <= x
 __device__ __forceinline__ int q_owner_of(long long x, long long U, int G) { return (int)(((x + 1) * G + U - 1) / U) - 1; }
 
+// type and byte offset of a tile: arithmetic for the common shapes (no dependent global loads in front of the first TMA)
+__device__ __forceinline__ int q_tile_type(const QParams& p, int tile) {
+    if (p.tile_type != nullptr) return __ldg(p.tile_type + tile);
+    return tile < p.tile_split ? p.type0 : p.type1;
+}
+__device__ __forceinline__ unsigned long long q_tile_off(const QParams& p, int tile) {
+    if (p.tile_off != nullptr) return __ldg(p.tile_off + tile);
+    return tile < p.tile_split ? (unsigned long long)tile * p.nkb * (unsigned)qg_qtile_bytes(p.type0)
+                               : p.off_split + (unsigned long long)(tile - p.tile_split) * p.nkb * (unsigned)qg_qtile_bytes(p.type1);
+}
+
 template <int NB>
 __device__ __forceinline__ void q_epilogue(const QParams& p, int n, int lane, const float* v) {
     if (p.epi == GEMM_EPI_SILU) {
@@ -136,15 +153,18 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     using Cfg = QCfg<NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* stages = smem;                                                   // [STAGES][raw | 4 activation tiles]
-    uint8_t* a_ring = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;          // [4][128 x 64 fp16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)QG_A_SLOTS * QG_A_TILE_BYTES);
-    uint64_t* stage_full = bars;                       // [STAGES]  producer (tx bytes)     -> unpack warps, MMA issuer
-    uint64_t* stage_empty = stage_full + Cfg::STAGES;  // [STAGES]  8 unpack warps + 1 commit -> producer
-    uint64_t* a_full = stage_empty + Cfg::STAGES;      // [4]       4 unpack warps            -> MMA issuer
-    uint64_t* a_empty = a_full + QG_A_SLOTS;           // [4]       commit                    -> unpack warps
-    uint64_t* acc_full = a_empty + QG_A_SLOTS;         // [2]       commit                    -> epilogue
-    uint64_t* acc_empty = acc_full + 2;                // [2]       4 epilogue warps          -> MMA issuer
+    uint8_t* a_ring = smem;                                                   // [6][128 x 64 fp16]        unpack warps -> tensor core
+    uint8_t* act_ring = a_ring + Cfg::A_BYTES;                                // [2][4][NB x 64 fp16]      TMA (L2)     -> tensor core
+    uint8_t* raw_ring = act_ring + Cfg::ACT_BYTES;                            // [raw_stages][raw_stride]  TMA (HBM)    -> unpack warps
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (QG_SMEM - 1024 - Cfg::BAR_BYTES));
+    uint64_t* raw_full = bars;                               // [6]  producer (tx bytes)  -> unpack warps
+    uint64_t* raw_empty = raw_full + QG_MAX_RAW_STAGES;      // [6]  8 unpack warps       -> producer
+    uint64_t* act_full = raw_empty + QG_MAX_RAW_STAGES;      // [2]  producer (tx bytes)  -> MMA issuer
+    uint64_t* act_empty = act_full + QG_ACT_UNITS;           // [2]  commit               -> activation producer
+    uint64_t* a_full = act_empty + QG_ACT_UNITS;             // [6]  4 unpack warps       -> MMA issuer
+    uint64_t* a_empty = a_full + QG_A_SLOTS;                 // [6]  commit               -> unpack warps
+    uint64_t* acc_full = a_empty + QG_A_SLOTS;               // [2]  commit               -> epilogue
+    uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps     -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     int* flag = reinterpret_cast<int*>(tmem_slot + 1);                        // "this CTA finishes the shared tile"
 
@@ -152,10 +172,12 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     const int G = gridDim.x, cta = blockIdx.x;
     const long long U = (long long)p.n_tiles * p.nkb;
     const long long u0 = q_range_start(cta, U, G), u1 = q_range_start(cta + 1, U, G);
+    const int R = p.raw_stages;
 
-    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
+    if (warp == 14 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], 9); }
+        for (int i = 0; i < QG_MAX_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 8); }
+        for (int i = 0; i < QG_ACT_UNITS; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
         for (int i = 0; i < QG_A_SLOTS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_mbar_init();
@@ -171,18 +193,29 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== producer =====
+            // ===== weight producer: one 1-D bulk copy per qtile, as far ahead as the raw ring is deep =====
             for (long long u = u0; u < u1; ++u) {
-                const int i = (int)(u - u0), s = i % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
+                const int i = (int)(u - u0), s = i % R;
+                const uint32_t ph = (uint32_t)(i / R) & 1u;
                 const int tile = (int)(u / p.nkb), kb = (int)(u % p.nkb);
-                const uint32_t qb = (uint32_t)qg_qtile_bytes(p.tile_type[tile]);
-                uint8_t* st = stages + (size_t)s * Cfg::STAGE_BYTES;
-                mbar_wait(&stage_empty[s], ph ^ 1u);
-                mbar_expect_tx(&stage_full[s], qb + 4u * Cfg::B_TILE);
-                tma_load_1d(st, p.w + p.tile_off[tile] + (size_t)kb * qb, qb, &stage_full[s]);
+                const uint32_t qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
+                mbar_wait(&raw_empty[s], ph ^ 1u);
+                mbar_expect_tx(&raw_full[s], qb);
+                tma_load_1d(raw_ring + (size_t)s * p.raw_stride, p.w + q_tile_off(p, tile) + (size_t)kb * qb, qb, &raw_full[s]);
+            }
+        }
+    } else if (warp == 14) {
+        if (lane == 0) {
+            // ===== activation producer: the four [NB x 64] boxes of a qtile's K range (L2-resident), two qtiles deep =====
+            for (long long u = u0; u < u1; ++u) {
+                const int i = (int)(u - u0), s = i % QG_ACT_UNITS;
+                const uint32_t ph = (uint32_t)(i / QG_ACT_UNITS) & 1u;
+                const int kb = (int)(u % p.nkb);
+                uint8_t* st = act_ring + (size_t)s * 4 * Cfg::B_TILE;
+                mbar_wait(&act_empty[s], ph ^ 1u);
+                mbar_expect_tx(&act_full[s], 4u * Cfg::B_TILE);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) tma_load_2d_q(st + QG_RAW_STRIDE + kk * Cfg::B_TILE, &p.tb, kb * QG_COLS + kk * QG_KSTEP, 0, &stage_full[s]);
+                for (int kk = 0; kk < 4; ++kk) tma_load_2d_q(st + kk * Cfg::B_TILE, &p.tb, kb * QG_COLS + kk * QG_KSTEP, 0, &act_full[s]);
             }
         }
     } else if (warp == 1) {
@@ -199,23 +232,23 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                 q_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NB);
                 for (int j = 0; j < n_kb; ++j, ++u) {
-                    const int i = (int)(u - u0), s = i % Cfg::STAGES;
-                    const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-                    mbar_wait(&stage_full[s], ph);                   // the activation tiles of this stage have landed
+                    const int i = (int)(u - u0), sa = i % QG_ACT_UNITS;
+                    mbar_wait(&act_full[sa], (uint32_t)(i / QG_ACT_UNITS) & 1u);      // the activation boxes of this qtile have landed
                     q_fence_after();
-                    const uint32_t sb = smem_u32(stages + (size_t)s * Cfg::STAGE_BYTES + QG_RAW_STRIDE);
+                    const uint32_t sb = smem_u32(act_ring + (size_t)sa * 4 * Cfg::B_TILE);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        mbar_wait(&a_full[kk], (uint32_t)i & 1u);    // the unpack warps have written operand tile kk of this qtile
+                        const int g = 4 * i + kk, slot = g % QG_A_SLOTS;
+                        mbar_wait(&a_full[slot], (uint32_t)(g / QG_A_SLOTS) & 1u);    // the unpack warps have written this operand tile
                         q_fence_after();
-                        const uint64_t adesc = q_desc_sw128(smem_u32(a_ring + (size_t)kk * QG_A_TILE_BYTES));
+                        const uint64_t adesc = q_desc_sw128(smem_u32(a_ring + (size_t)slot * QG_A_TILE_BYTES));
                         const uint64_t bdesc = q_desc_sw128(sb + (uint32_t)(kk * Cfg::B_TILE));
 #pragma unroll
                         for (int k = 0; k < QG_KSTEP / 16; ++k)
                             q_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | kk | k) ? 1u : 0u);
-                        q_commit(&a_empty[kk]);                       // operand tile kk may be overwritten once these MMAs have read it
+                        q_commit(&a_empty[slot]);                     // the slot may be overwritten once these MMAs have read it
                     }
-                    q_commit(&stage_empty[s]);                        // ... and the stage's activation tiles
+                    q_commit(&act_empty[sa]);                         // ... and the qtile's activation boxes
                     if (j == n_kb - 1) q_commit(&acc_full[buf]);
                 }
             }
@@ -224,24 +257,27 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         // ===== unpack warps: thread (row r, half h) =====
         const int t = (warp - 2) * 32 + lane, r = t & 127, h = t >> 7;
         for (long long u = u0; u < u1; ++u) {
-            const int i = (int)(u - u0), s = i % Cfg::STAGES;
-            const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-            const int type = p.tile_type[(int)(u / p.nkb)];
-            const uint8_t* raw = stages + (size_t)s * Cfg::STAGE_BYTES;
-            mbar_wait(&stage_full[s], ph);
+            const int i = (int)(u - u0), s = i % R;
+            const uint32_t ph = (uint32_t)(i / R) & 1u;
+            const int type = q_tile_type(p, (int)(u / p.nkb));
+            const uint8_t* raw = raw_ring + (size_t)s * p.raw_stride;
+            mbar_wait(&raw_full[s], ph);
             qg_dequant_thread(
-                type, raw, r, h, [&](int kk) { return a_ring + (size_t)kk * QG_A_TILE_BYTES; },
-                [&](int kk) { mbar_wait(&a_empty[kk], ((uint32_t)i & 1u) ^ 1u); },          // the MMAs of the previous qtile have read slot kk
+                type, raw, r, h, [&](int kk) { return a_ring + (size_t)((4 * i + kk) % QG_A_SLOTS) * QG_A_TILE_BYTES; },
+                [&](int kk) {                                                                  // the MMAs that last read this slot are done
+                    const int g = 4 * i + kk;
+                    mbar_wait(&a_empty[g % QG_A_SLOTS], ((uint32_t)(g / QG_A_SLOTS) & 1u) ^ 1u);
+                },
                 [&](int kk) {
                     fence_proxy_async();                                                      // generic-proxy stores -> visible to the tensor core
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[kk]);
+                    if (lane == 0) mbar_arrive(&a_full[(4 * i + kk) % QG_A_SLOTS]);
                 });
             __syncwarp();
-            if (lane == 0) mbar_arrive(&stage_empty[s]);                                      // this warp has read all it needs of the raw bytes
+            if (lane == 0) mbar_arrive(&raw_empty[s]);                                        // this warp has read all it needs of the raw bytes
         }
     } else {
-        // ===== epilogue warps =====
+        // ===== epilogue warps (10..13) =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int nl = q * 32 + lane;                                 // row inside the tile
         int seg = 0;
@@ -282,12 +318,23 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             const int finish = *flag;
             named_bar_sync(1, 128);                                   // everyone has read the flag before the next shared tile rewrites it
             if (!finish) continue;
+            // sum in CTA order (deterministic); two contributors per round trip: their loads are independent
 #pragma unroll
             for (int b = 0; b < NB; ++b) v[b] = 0.f;
-            for (int c = c_first; c <= c_last; ++c) {
-                const float* part = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS);
+            int c = c_first;
+            for (; c + 1 <= c_last; c += 2) {
+                const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + nl;
+                const float* pb = p.partial + ((size_t)(c + 1) * 2) * (NB * QG_ROWS) + nl;
+                float ta[NB], tb2[NB];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) v[b] += __ldcg(part + b * QG_ROWS + nl);
+                for (int b = 0; b < NB; ++b) { ta[b] = __ldcg(pa + b * QG_ROWS); tb2[b] = __ldcg(pb + b * QG_ROWS); }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) v[b] = (v[b] + ta[b]) + tb2[b];
+            }
+            if (c <= c_last) {
+                const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + nl;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) v[b] += __ldcg(pa + b * QG_ROWS);
             }
             q_epilogue<NB>(p, n, lane, v);
         }
@@ -335,8 +382,10 @@ EncodeTiledFnQ encode_fn_q() {
 }
 
 template <int NB>
-cudaError_t launch_nb(const QParams& qp, int grid, cudaStream_t s) {
-    qgemm_kernel<NB><<<grid, QG_THREADS, QCfg<NB>::SMEM, s>>>(qp);
+cudaError_t launch_nb(QParams& qp, int grid, cudaStream_t s) {
+    qp.raw_stages = std::min(QG_MAX_RAW_STAGES, QCfg<NB>::RAW_BUDGET / qp.raw_stride);
+    if (qp.raw_stages < 2) return cudaErrorInvalidValue;
+    qgemm_kernel<NB><<<grid, QG_THREADS, QG_SMEM, s>>>(qp);
     return cudaGetLastError();
 }
 
@@ -346,9 +395,9 @@ size_t qgemm_partial_floats(int nb) { return (size_t)QGEMM_MAX_GRID * 2 * nb * Q
 bool qgemm_batch_ok(int nb) { return nb == 16 || nb == 32 || nb == 64; }
 
 cudaError_t qgemm_configure() {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCfg<16>::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(qgemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCfg<32>::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(qgemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCfg<64>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qgemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qgemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QG_SMEM);
     return e;
 }
 
@@ -405,7 +454,13 @@ cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows
     if (fn(&qp.tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(act), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    qp.w = wt.w; qp.tile_off = wt.tile_off; qp.tile_type = wt.tile_type; qp.counters = wt.counters; qp.partial = partial;
+    qp.w = wt.w; qp.counters = wt.counters; qp.partial = partial;
+    // tile addressing: arithmetic when the tiles are "type0, then type1" (every Llama GEMM: uniform, or Q | K | V with another V
+    // type); the per-tile tables only for anything else
+    qp.type0 = wt.type0; qp.type1 = wt.type1; qp.tile_split = wt.tile_split; qp.off_split = wt.off_split;
+    qp.tile_off = wt.two_segment ? nullptr : wt.tile_off;
+    qp.tile_type = wt.two_segment ? nullptr : wt.tile_type;
+    qp.raw_stride = wt.has_q6k ? QG_Q6K_BYTES + 768 : QG_Q4K_BYTES;      // 27 648 / 18 432: multiples of 1024
     qp.c = c; qp.ldc = ldc; qp.epi = epi; qp.n = wt.n; qp.n_tiles = wt.n_tiles; qp.nkb = wt.nkb;
     const long long U = (long long)wt.n_tiles * wt.nkb;
     const int grid = (int)std::min<long long>(std::min(n_sm, QGEMM_MAX_GRID), U);

@@ -19,6 +19,23 @@ struct QGemmWeights {
     int k = 0;                        // input features, multiple of 256
     int n_tiles = 0, nkb = 0;
     uint64_t bytes = 0;               // bytes of the stream = the GGUF bytes of the matrix
+    // "tiles [0, tile_split) are type0, the rest type1": lets the kernel compute a tile's type and offset instead of loading them
+    bool two_segment = false, has_q6k = false;
+    int type0 = 0, type1 = 0, tile_split = 0;
+    uint64_t off_split = 0;
+    void describe(const uint64_t* toff_host, const uint8_t* ttype_host) {
+        type0 = ttype_host[0];
+        tile_split = n_tiles;
+        type1 = type0;
+        off_split = 0;
+        has_q6k = false;
+        two_segment = true;
+        for (int t = 0; t < n_tiles; ++t) {
+            if (ttype_host[t] == 14) has_q6k = true;
+            if (tile_split == n_tiles && ttype_host[t] != type0) { tile_split = t; type1 = ttype_host[t]; off_split = toff_host[t]; }
+            else if (tile_split != n_tiles && ttype_host[t] != type1) two_segment = false;
+        }
+    }
 };
 
 // source of rows for the load-time packer: a matrix in NATIVE GGUF row layout on the device

@@ -229,7 +229,9 @@ QG_FN void qg_dequant_thread(int type, const uint8_t* raw, int r, int h, ATileOf
         }
     } else {
         const QgU4 scw = qg_ld128(raw + 12 * QG_PLANE + r * 16);
-        const uint32_t scs[4] = {scw.x, scw.y, scw.z, scw.w};
+        // this thread's eight scales (columns 128h..128h+127): two words picked by h, then indexed by compile-time constants only
+        // (a 4-word array indexed by a run-time h is a local-memory array: every scale a round trip through L1)
+        const uint32_t scs2[2] = {h ? scw.z : scw.x, h ? scw.w : scw.y};
         const float d = half_bits_to_float(qg_ld16(raw + 13 * QG_PLANE + r * 2));
 #pragma unroll
         for (int kk2 = 0; kk2 < 2; ++kk2) {
@@ -246,8 +248,8 @@ QG_FN void qg_dequant_thread(int type, const uint8_t* raw, int r, int h, ATileOf
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     // columns 32j + 8t .. +7: 16-column sub-block g = 2j + t/2 (scale byte g), high bits in half-word t&1 of word 2jj + t/2
-                    const int g = 2 * j + (t >> 1);
-                    const int sc = (int)(int8_t)((scs[g >> 2] >> (8 * (g & 3))) & 0xFF);
+                    // 16-column sub-block g = 8h + 4kk2 + 2jj + t/2: word kk2 of this thread's pair, byte 2jj + t/2
+                    const int sc = (int)(int8_t)((scs2[kk2] >> (8 * (2 * jj + (t >> 1)))) & 0xFF);
                     const QH2 s2 = qh2_set(d * (float)sc);
                     const uint32_t hw = hwords[2 * jj + (t >> 1)];
                     uint32_t o[4];
