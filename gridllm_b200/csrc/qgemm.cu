@@ -9,23 +9,27 @@
 // (16 cycles of tcgen05 against ~800 cycles of HBM time per qtile and SM), so the tensor pipe idles and the CUDA cores'
 // job -- ~2.3 lane-operations per weight to unpack nibbles into fp16 -- is what has to keep up with the memory pipe.
 //
-// Shape of the kernel (persistent, one CTA per SM, 14 warps, hand-written PTX; layouts and the per-thread unpack program in
+// Shape of the kernel (persistent, one CTA per SM, 24 warps, hand-written PTX; layouts and the per-thread unpack program in
 // qgemm_layout.h, which the CPU suite runs bit for bit):
 //   the weights of a GEMM are a stream of QTILES (128 rows x 256 columns, one contiguous 18 / 26 KB range each); the U = tiles x
 //   K-blocks qtiles are dealt to the G CTAs as contiguous ranges [c U / G, (c+1) U / G) ("stream-K": perfect balance for every
 //   shape -- 32 tiles x 16 blocks on 148 SMs as well as 1002 x 16 -- and every CTA streams ONE contiguous byte range);
-//   warp 0 / one lane : producer -- per qtile one 1-D TMA bulk copy of the raw bytes plus four 2-D TMA boxes of the activations
-//                       [B x 64] fp16 (L2-resident) into a 2-3 stage ring;
-//   warps 2..9        : unpack -- thread (row, half) turns 128 columns of its row into sixteen 16-byte chunks of the four
-//                       128-byte-swizzled operand tiles [128 x 64] fp16 of the qtile (conflict-free 128-bit loads and stores),
-//                       fence.proxy.async, mbarrier arrive;
-//   warp 1 / one lane : MMA issuer -- per K-step four tcgen05.mma.cta_group::1.kind::f16 (M 128 = weight rows, N = B, K 16) on
-//                       shared-memory descriptors, accumulator [128 lanes x B columns] fp32 in TENSOR MEMORY, double-buffered
-//                       across output tiles; tcgen05.commit hands operand tiles / stages / accumulators on;
-//   warps 10..13      : epilogue -- tcgen05.ld, then either the fused epilogue (fp32 store, residual add, SiLU*mul -> fp16) or,
-//                       for an output tile whose K range is shared with neighbouring CTAs, a partial to scratch + atomic
-//                       ticket; the last contributor adds the partials IN CTA ORDER (deterministic) and runs the epilogue.
-// SASS to look for: UTCHMMA (tcgen05.mma), UBLKCP (1-D bulk copy), UTMALDG (2-D TMA), LDTM (tcgen05.ld), UTCBAR (commit).
+//   warp 0 / one lane : weight producer -- per qtile one 1-D TMA bulk copy of the raw bytes into a 6-8 stage ring (all the
+//                       shared memory the activations leave: 110-190 KB in flight per SM);
+//   warp 2 / one lane : activation producer -- four 2-D TMA boxes [B x 64] fp16 per qtile (L2-resident), two qtiles deep;
+//   warps 4..19       : unpack -- thread (row, K-step) turns 64 columns of its row into 32 packed half2 REGISTERS and writes them
+//                       with one tcgen05.st.32x32b.x32 into TENSOR MEMORY: the A operand [128 lanes x 32 columns] of that K-step
+//                       (ring of 8 K-steps = 256 TMEM columns).  The dequantised weights never touch shared memory: the only
+//                       shared-memory traffic per qtile is the raw bytes (in, out) and the activations;
+//   warp 1 / one lane : MMA issuer -- per K-step four tcgen05.mma.cta_group::1.kind::f16 with A FROM TMEM and B = the activation
+//                       box in shared memory (M 128 = weight rows, N = B, K 16), accumulator [128 lanes x B columns] fp32 in
+//                       TMEM, double-buffered across output tiles; tcgen05.commit hands K-step slots / boxes / accumulators on;
+//   warps 20..23      : epilogue -- tcgen05.ld 16 batch columns at a time, then either the fused epilogue (fp32 store, residual
+//                       add, SiLU*mul -> fp16) or, for an output tile whose K range is shared with neighbouring CTAs, a partial to
+//                       scratch + atomic ticket; the last contributor adds the partials IN CTA ORDER (deterministic) and runs
+//                       the epilogue.
+// SASS to look for: UTCHMMA (tcgen05.mma), STTM (tcgen05.st), LDTM (tcgen05.ld), UBLKCP (1-D bulk copy), UTMALDG (2-D TMA),
+// UTCBAR (commit).
 #include <cuda.h>
 #include <algorithm>
 #include <cstdlib>
@@ -39,20 +43,20 @@ namespace gl {
 
 namespace {
 
-constexpr int QG_THREADS = 15 * 32;
-constexpr int QG_A_SLOTS = 6;                        // operand-tile ring: 1.5 qtiles, so the unpack warps never wait for the MMAs of the qtile before
-constexpr int QG_ACT_UNITS = 2;                      // activation ring: the four [NB x 64] boxes of two qtiles
-constexpr size_t QG_SMEM = 227 * 1024;               // the whole opt-in shared memory; the raw ring takes what the other two leave
+constexpr int QG_THREADS = 24 * 32;
+constexpr int QG_W_UNPACK0 = 4, QG_N_UNPACK = 16, QG_W_EPI0 = 20;
+constexpr int QG_A_UNITS = 2;                        // operand ring: the A operand (TMEM, 4 K-steps x 32 columns) and the activation boxes (shared memory) of two qtiles
+constexpr int QG_A_COL0 = 128;                       // TMEM columns [0, 128): two accumulators of up to 64; [128, 384): the A ring
+constexpr int QG_TMEM_COLS = 512;                    // power of two >= 384 (one CTA per SM: nobody else wants the rest)
+constexpr size_t QG_SMEM = 227 * 1024;               // the whole opt-in shared memory; the raw ring takes what the activations leave
 
 template <int NB> struct QCfg {
     static constexpr int B_TILE = NB * 128;          // activations [NB rows x 64] fp16, 128-byte swizzle
-    static constexpr int ACT_BYTES = QG_ACT_UNITS * 4 * B_TILE;
-    static constexpr int A_BYTES = QG_A_SLOTS * QG_A_TILE_BYTES;
+    static constexpr int ACT_BYTES = QG_A_UNITS * 4 * B_TILE;
     static constexpr int BAR_BYTES = 512;
-    static constexpr int RAW_BUDGET = (int)QG_SMEM - 1024 /* alignment */ - BAR_BYTES - ACT_BYTES - A_BYTES;
-    static constexpr int TMEM_COLS = 2 * NB < 32 ? 32 : 2 * NB;
+    static constexpr int RAW_BUDGET = (int)QG_SMEM - 1024 /* alignment */ - BAR_BYTES - ACT_BYTES;
 };
-constexpr int QG_MAX_RAW_STAGES = 6;
+constexpr int QG_MAX_RAW_STAGES = 8;
 
 struct QParams {
     CUtensorMap tb;              // activations: dims {K, rows_alloc}, box {64, NB}, 128-byte swizzle
@@ -73,18 +77,35 @@ __device__ __forceinline__ void tma_load_2d_q(void* dst, const CUtensorMap* map,
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ bool q_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void q_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void q_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void q_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void q_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem: 128 lanes x 8 columns of two fp16] x B[smem descriptor]: the ".ts" form of the instruction
+__device__ __forceinline__ void q_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// 32 lanes x 32 columns: thread t of the warp writes its 32 registers to columns [col, col + 32) of lane (lane base + t)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* w) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]),
+          "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]),
+          "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 // K-major operand tile, 128-byte swizzle, rows of 64 fp16 (8-row atoms of 1024 B): the descriptor prefill_tc5.cu uses
 __device__ __forceinline__ uint64_t q_desc_sw128(uint32_t smem_addr) {
@@ -120,31 +141,36 @@ __device__ __forceinline__ unsigned long long q_tile_off(const QParams& p, int t
                                : p.off_split + (unsigned long long)(tile - p.tile_split) * p.nkb * (unsigned)qg_qtile_bytes(p.type1);
 }
 
-template <int NB>
-__device__ __forceinline__ void q_epilogue(const QParams& p, int n, int lane, const float* v) {
+// fused epilogue of 16 batch columns [b0, b0 + 16) of output feature n (v[i] = C[b0 + i][n])
+__device__ __forceinline__ void q_epilogue16(const QParams& p, int n, int lane, int b0, const float* v) {
     if (p.epi == GEMM_EPI_SILU) {
         // weight rows are interleaved [8 gate | 8 up] at load: lane l of a 16-lane group holds gate (l < 8) or up (l >= 8) of
         // hidden column (n / 16) * 8 + l % 8
         __half* out = reinterpret_cast<__half*>(p.c);
         const int hcol = (n >> 4) * 8 + (n & 7);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
+        for (int b = 0; b < 16; ++b) {
             const float up = __shfl_xor_sync(0xffffffffu, v[b], 8);
             if ((lane & 8) == 0 && n < p.n) {
                 const float g = v[b];
-                out[(size_t)b * p.ldc + hcol] = __float2half_rn((g / (1.0f + expf(-g))) * up);
+                out[(size_t)(b0 + b) * p.ldc + hcol] = __float2half_rn((g / (1.0f + expf(-g))) * up);
             }
         }
         return;
     }
     if (n >= p.n) return;
-    float* out = reinterpret_cast<float*>(p.c) + n;
+    float* out = reinterpret_cast<float*>(p.c) + (size_t)b0 * p.ldc + n;
     if (p.epi == GEMM_EPI_ADD_F32) {
+        // all sixteen loads first: written as load / add / store per element the compiler must keep them in order (it cannot
+        // prove the rows distinct), and sixteen L2 round trips in a row are 15 us per launch
+        float old[16];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) out[(size_t)b * p.ldc] += v[b];
+        for (int b = 0; b < 16; ++b) old[b] = __ldcg(out + (size_t)b * p.ldc);
+#pragma unroll
+        for (int b = 0; b < 16; ++b) out[(size_t)b * p.ldc] = old[b] + v[b];
     } else {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) out[(size_t)b * p.ldc] = v[b];
+        for (int b = 0; b < 16; ++b) out[(size_t)b * p.ldc] = v[b];
     }
 }
 
@@ -153,37 +179,34 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     using Cfg = QCfg<NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* a_ring = smem;                                                   // [6][128 x 64 fp16]        unpack warps -> tensor core
-    uint8_t* act_ring = a_ring + Cfg::A_BYTES;                                // [2][4][NB x 64 fp16]      TMA (L2)     -> tensor core
+    uint8_t* act_ring = smem;                                                 // [2][4][NB x 64 fp16]      TMA (L2)     -> tensor core
     uint8_t* raw_ring = act_ring + Cfg::ACT_BYTES;                            // [raw_stages][raw_stride]  TMA (HBM)    -> unpack warps
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (QG_SMEM - 1024 - Cfg::BAR_BYTES));
-    uint64_t* raw_full = bars;                               // [6]  producer (tx bytes)  -> unpack warps
-    uint64_t* raw_empty = raw_full + QG_MAX_RAW_STAGES;      // [6]  8 unpack warps       -> producer
-    uint64_t* act_full = raw_empty + QG_MAX_RAW_STAGES;      // [2]  producer (tx bytes)  -> MMA issuer
-    uint64_t* act_empty = act_full + QG_ACT_UNITS;           // [2]  commit               -> activation producer
-    uint64_t* a_full = act_empty + QG_ACT_UNITS;             // [6]  4 unpack warps       -> MMA issuer
-    uint64_t* a_empty = a_full + QG_A_SLOTS;                 // [6]  commit               -> unpack warps
-    uint64_t* acc_full = a_empty + QG_A_SLOTS;               // [2]  commit               -> epilogue
-    uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps     -> MMA issuer
+    uint64_t* raw_full = bars;                               // [8]  producer (tx bytes)                     -> unpack warps
+    uint64_t* raw_empty = raw_full + QG_MAX_RAW_STAGES;      // [8]  16 unpack warps                         -> producer
+    uint64_t* unit_full = raw_empty + QG_MAX_RAW_STAGES;     // [2]  16 unpack warps + activations (tx bytes) -> MMA issuer
+    uint64_t* unit_empty = unit_full + QG_A_UNITS;           // [2]  commit                                  -> unpack warps, activation producer
+    uint64_t* acc_full = unit_empty + QG_A_UNITS;            // [2]  commit                                  -> epilogue
+    uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps                        -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     int* flag = reinterpret_cast<int*>(tmem_slot + 1);                        // "this CTA finishes the shared tile"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
-    const long long U = (long long)p.n_tiles * p.nkb;
-    const long long u0 = q_range_start(cta, U, G), u1 = q_range_start(cta + 1, U, G);
+    const int nkb = p.nkb;
+    const int U = p.n_tiles * nkb;                                            // < 2^31 / 148 for every matrix of these models
+    const int u0 = (int)q_range_start(cta, U, G), u1 = (int)q_range_start(cta + 1, U, G);
     const int R = p.raw_stages;
 
-    if (warp == 14 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
+    if (warp == 2 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < QG_MAX_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 8); }
-        for (int i = 0; i < QG_ACT_UNITS; ++i) { mbar_init(&act_full[i], 1); mbar_init(&act_empty[i], 1); }
-        for (int i = 0; i < QG_A_SLOTS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < QG_MAX_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], QG_N_UNPACK); }
+        for (int i = 0; i < QG_A_UNITS; ++i) { mbar_init(&unit_full[i], QG_N_UNPACK + 1); mbar_init(&unit_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_mbar_init();
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(QG_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     q_fence_before();
@@ -194,120 +217,140 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             // ===== weight producer: one 1-D bulk copy per qtile, as far ahead as the raw ring is deep =====
-            for (long long u = u0; u < u1; ++u) {
-                const int i = (int)(u - u0), s = i % R;
-                const uint32_t ph = (uint32_t)(i / R) & 1u;
-                const int tile = (int)(u / p.nkb), kb = (int)(u % p.nkb);
-                const uint32_t qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
+            int tile = u0 / nkb, kb = u0 - tile * nkb, s = 0;
+            uint32_t ph = 0;
+            uint32_t qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
+            const uint8_t* src = p.w + q_tile_off(p, tile) + (size_t)kb * qb;
+            for (int u = u0; u < u1; ++u) {
                 mbar_wait(&raw_empty[s], ph ^ 1u);
                 mbar_expect_tx(&raw_full[s], qb);
-                tma_load_1d(raw_ring + (size_t)s * p.raw_stride, p.w + q_tile_off(p, tile) + (size_t)kb * qb, qb, &raw_full[s]);
-            }
-        }
-    } else if (warp == 14) {
-        if (lane == 0) {
-            // ===== activation producer: the four [NB x 64] boxes of a qtile's K range (L2-resident), two qtiles deep =====
-            for (long long u = u0; u < u1; ++u) {
-                const int i = (int)(u - u0), s = i % QG_ACT_UNITS;
-                const uint32_t ph = (uint32_t)(i / QG_ACT_UNITS) & 1u;
-                const int kb = (int)(u % p.nkb);
-                uint8_t* st = act_ring + (size_t)s * 4 * Cfg::B_TILE;
-                mbar_wait(&act_empty[s], ph ^ 1u);
-                mbar_expect_tx(&act_full[s], 4u * Cfg::B_TILE);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) tma_load_2d_q(st + kk * Cfg::B_TILE, &p.tb, kb * QG_COLS + kk * QG_KSTEP, 0, &act_full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            // instruction descriptor: D = F32, A / B = F16, both K-major, N = NB, M = 128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int seg = 0;
-            for (long long u = u0; u < u1; ++seg) {
-                const int kb_lo = (int)(u % p.nkb);
-                const int n_kb = (int)min((long long)(p.nkb - kb_lo), u1 - u);
-                const int buf = seg & 1;
-                mbar_wait(&acc_empty[buf], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
-                q_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NB);
-                for (int j = 0; j < n_kb; ++j, ++u) {
-                    const int i = (int)(u - u0), sa = i % QG_ACT_UNITS;
-                    mbar_wait(&act_full[sa], (uint32_t)(i / QG_ACT_UNITS) & 1u);      // the activation boxes of this qtile have landed
-                    q_fence_after();
-                    const uint32_t sb = smem_u32(act_ring + (size_t)sa * 4 * Cfg::B_TILE);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int g = 4 * i + kk, slot = g % QG_A_SLOTS;
-                        mbar_wait(&a_full[slot], (uint32_t)(g / QG_A_SLOTS) & 1u);    // the unpack warps have written this operand tile
-                        q_fence_after();
-                        const uint64_t adesc = q_desc_sw128(smem_u32(a_ring + (size_t)slot * QG_A_TILE_BYTES));
-                        const uint64_t bdesc = q_desc_sw128(sb + (uint32_t)(kk * Cfg::B_TILE));
-#pragma unroll
-                        for (int k = 0; k < QG_KSTEP / 16; ++k)
-                            q_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | kk | k) ? 1u : 0u);
-                        q_commit(&a_empty[slot]);                     // the slot may be overwritten once these MMAs have read it
+                tma_load_1d(raw_ring + (size_t)s * p.raw_stride, src, qb, &raw_full[s]);
+                src += qb;
+                if (++s == R) { s = 0; ph ^= 1u; }
+                if (++kb == nkb) {                                            // next output tile: its type may differ (Q | K | V)
+                    kb = 0;
+                    ++tile;
+                    if (u + 1 < u1) {
+                        qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
+                        src = p.w + q_tile_off(p, tile);
                     }
-                    q_commit(&act_empty[sa]);                         // ... and the qtile's activation boxes
-                    if (j == n_kb - 1) q_commit(&acc_full[buf]);
                 }
             }
         }
-    } else if (warp < 10) {
-        // ===== unpack warps: thread (row r, half h) =====
-        const int t = (warp - 2) * 32 + lane, r = t & 127, h = t >> 7;
-        for (long long u = u0; u < u1; ++u) {
-            const int i = (int)(u - u0), s = i % R;
-            const uint32_t ph = (uint32_t)(i / R) & 1u;
-            const int type = q_tile_type(p, (int)(u / p.nkb));
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ===== activation producer: the four [NB x 64] boxes of a qtile's K range (L2-resident), two qtiles deep =====
+            int kb = u0 % nkb;
+            for (int u = u0; u < u1; ++u) {
+                const int i = u - u0, s = i & 1;
+                uint8_t* st = act_ring + (size_t)s * 4 * Cfg::B_TILE;
+                mbar_wait(&unit_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(&unit_full[s], 4u * Cfg::B_TILE);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) tma_load_2d_q(st + kk * Cfg::B_TILE, &p.tb, kb * QG_COLS + kk * QG_KSTEP, 0, &unit_full[s]);
+                if (++kb == nkb) kb = 0;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // The WHOLE warp walks the loop with warp-uniform values and one elected lane issues: written as `if (lane == 0) { ... }`
+        // the compiler cannot keep the operands in uniform registers and wraps every tcgen05 instruction in a convert-to-uniform
+        // loop (ELECT / 4 x R2UR / UTCHMMA / BRA.U.ANY: ~15 dependent instructions per MMA).  One thread then needed ~4 000 cycles for
+        // the 16 MMAs, 5 commits and 5 waits of a qtile -- and that, not HBM or the unpack warps, set the pace of the kernel
+        // (profiles/r02_qgemm_notes.md).  One wait, 16 MMAs and one commit per qtile now.
+        // instruction descriptor: D = F32, A / B = F16, both K-major, N = NB, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t act_u32 = __shfl_sync(0xffffffffu, smem_u32(act_ring), 0);
+        int seg = 0, kb_lo = u0 % nkb;
+        for (int u = u0; u < u1; ++seg) {
+            const int n_kb = min(nkb - kb_lo, u1 - u);
+            kb_lo = 0;
+            const int buf = seg & 1;
+            mbar_wait(&acc_empty[buf], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
+            const uint32_t tmem_d = tb + (uint32_t)(buf * NB);
+            for (int j = 0; j < n_kb; ++j, ++u) {
+                const int i = u - u0, sa = i & 1;
+                mbar_wait(&unit_full[sa], (uint32_t)(i >> 1) & 1u);   // A operand in TMEM (16 unpack warps) and activation boxes (TMA) are there
+                q_fence_after();
+                const uint32_t ta = tb + (uint32_t)(QG_A_COL0 + sa * 128);
+                const uint64_t bdesc = q_desc_sw128(act_u32 + (uint32_t)(sa * 4 * Cfg::B_TILE));
+                if (q_elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)                   // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of B
+                            q_mma_f16_ts(tmem_d, ta + (uint32_t)(kk * 32 + k * 8), bdesc + (uint64_t)(kk * (Cfg::B_TILE >> 4) + 2 * k), idesc,
+                                         (kk | k) ? 1u : (j ? 1u : 0u));
+                    q_commit(&unit_empty[sa]);                        // TMEM slot and activation boxes may be overwritten once these MMAs are done
+                    if (j == n_kb - 1) q_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= QG_W_UNPACK0 && warp < QG_W_EPI0) {
+        // ===== unpack warps: thread (row r, K-step kk); the warp's TMEM lane quarter (warp % 4) is r / 32 =====
+        const int t = (warp - QG_W_UNPACK0) * 32 + lane, r = t & 127, kk = t >> 7;
+        const uint32_t ta0 = tmem_base + ((uint32_t)(r & ~31) << 16) + (uint32_t)(QG_A_COL0 + kk * 32);
+        int tile = u0 / nkb, kb = u0 - tile * nkb, s = 0;
+        uint32_t ph = 0;
+        int type = q_tile_type(p, tile);
+        for (int u = u0; u < u1; ++u) {
+            const int i = u - u0;
             const uint8_t* raw = raw_ring + (size_t)s * p.raw_stride;
             mbar_wait(&raw_full[s], ph);
-            qg_dequant_thread(
-                type, raw, r, h, [&](int kk) { return a_ring + (size_t)((4 * i + kk) % QG_A_SLOTS) * QG_A_TILE_BYTES; },
-                [&](int kk) {                                                                  // the MMAs that last read this slot are done
-                    const int g = 4 * i + kk;
-                    mbar_wait(&a_empty[g % QG_A_SLOTS], ((uint32_t)(g / QG_A_SLOTS) & 1u) ^ 1u);
-                },
-                [&](int kk) {
-                    fence_proxy_async();                                                      // generic-proxy stores -> visible to the tensor core
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[(4 * i + kk) % QG_A_SLOTS]);
-                });
+            uint32_t w[32];
+            qg_dequant_kstep(type, raw, r, kk, [&](int c, QgU4 v) { w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w; });
             __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[s]);                                        // this warp has read all it needs of the raw bytes
+            if (lane == 0) mbar_arrive(&raw_empty[s]);                // this warp has read all it needs of the raw bytes
+            // the 32 words sit in registers: only now does the thread need the TMEM slot (the MMAs of two qtiles ago are done)
+            mbar_wait(&unit_empty[i & 1], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            q_fence_after();
+            tmem_st_32x32(ta0 + (uint32_t)((i & 1) * 128), w);
+            q_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&unit_full[i & 1]);
+            if (++s == R) { s = 0; ph ^= 1u; }
+            if (++kb == nkb) { kb = 0; ++tile; if (u + 1 < u1) type = q_tile_type(p, tile); }
         }
-    } else {
-        // ===== epilogue warps (10..13) =====
+    } else if (warp >= QG_W_EPI0) {
+        // ===== epilogue warps =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int nl = q * 32 + lane;                                 // row inside the tile
         int seg = 0;
-        for (long long u = u0; u < u1; ++seg) {
-            const int tile = (int)(u / p.nkb), kb_lo = (int)(u % p.nkb);
-            const int n_kb = (int)min((long long)(p.nkb - kb_lo), u1 - u);
+        int tile = u0 / nkb, kb_lo = u0 - tile * nkb;
+        for (int u = u0; u < u1; ++seg, ++tile) {
+            const int n_kb = min(nkb - kb_lo, u1 - u);
+            kb_lo = 0;
             u += n_kb;
             const int buf = seg & 1;
+            const int n = tile * QG_ROWS + nl;
+            const bool whole = n_kb == nkb;                           // the whole K range of this tile is ours
+            // shared tile: partial -> scratch, ticket; the last contributor sums the partials in CTA order
+            const int t0 = tile * nkb;
+            const int c_first = whole ? cta : q_owner_of(t0, U, G), c_last = whole ? cta : q_owner_of(t0 + nkb - 1, U, G);
+            float* mine = p.partial + ((size_t)cta * 2 + (cta == c_first ? 1 : 0)) * (NB * QG_ROWS) + nl;
             mbar_wait(&acc_full[buf], (uint32_t)(seg >> 1) & 1u);
             q_fence_after();
-            float v[NB];
 #pragma unroll
-            for (int c = 0; c < NB / 16; ++c) tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NB + c * 16), v + c * 16);
-            q_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);              // the accumulator half is in registers: the next tile may start
-            const int n = tile * QG_ROWS + nl;
-            if (n_kb == p.nkb) {                                      // the whole K range of this tile is ours
-                q_epilogue<NB>(p, n, lane, v);
-                continue;
+            for (int c = 0; c < NB / 16; ++c) {
+                float v[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NB + c * 16), v);
+                if (c == NB / 16 - 1) {
+                    q_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);      // the accumulator has been read: the tile after next may start
+                }
+                if (whole) q_epilogue16(p, n, lane, c * 16, v);
+                else {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) mine[(c * 16 + b) * QG_ROWS] = v[b];
+                }
             }
-            // shared tile: partial -> scratch, ticket; the last contributor sums the partials in CTA order
-            const long long t0 = (long long)tile * p.nkb;
-            const int c_first = q_owner_of(t0, U, G), c_last = q_owner_of(t0 + p.nkb - 1, U, G);
-            float* mine = p.partial + ((size_t)cta * 2 + (cta == c_first ? 1 : 0)) * (NB * QG_ROWS);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) mine[b * QG_ROWS + nl] = v[b];
+            if (whole) continue;
             __threadfence();
             named_bar_sync(1, 128);
-            if (warp == 10 && lane == 0) {
+            if (warp == QG_W_EPI0 && lane == 0) {
                 unsigned ticket;
                 asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.counters + tile) : "memory");
                 const int last = ticket == (unsigned)(c_last - c_first);
@@ -318,30 +361,34 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             const int finish = *flag;
             named_bar_sync(1, 128);                                   // everyone has read the flag before the next shared tile rewrites it
             if (!finish) continue;
-            // sum in CTA order (deterministic); two contributors per round trip: their loads are independent
+            // sum in CTA order (deterministic); sixteen batch columns at a time, two contributors per round trip
+#pragma unroll 1
+            for (int b0 = 0; b0 < NB; b0 += 16) {
+                float v[16];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) v[b] = 0.f;
-            int c = c_first;
-            for (; c + 1 <= c_last; c += 2) {
-                const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + nl;
-                const float* pb = p.partial + ((size_t)(c + 1) * 2) * (NB * QG_ROWS) + nl;
-                float ta[NB], tb2[NB];
+                for (int b = 0; b < 16; ++b) v[b] = 0.f;
+                int c = c_first;
+                for (; c + 1 <= c_last; c += 2) {
+                    const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + (size_t)b0 * QG_ROWS + nl;
+                    const float* pb = p.partial + ((size_t)(c + 1) * 2) * (NB * QG_ROWS) + (size_t)b0 * QG_ROWS + nl;
+                    float ta[16], tb2[16];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) { ta[b] = __ldcg(pa + b * QG_ROWS); tb2[b] = __ldcg(pb + b * QG_ROWS); }
+                    for (int b = 0; b < 16; ++b) { ta[b] = __ldcg(pa + b * QG_ROWS); tb2[b] = __ldcg(pb + b * QG_ROWS); }
 #pragma unroll
-                for (int b = 0; b < NB; ++b) v[b] = (v[b] + ta[b]) + tb2[b];
+                    for (int b = 0; b < 16; ++b) v[b] = (v[b] + ta[b]) + tb2[b];
+                }
+                if (c <= c_last) {
+                    const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + (size_t)b0 * QG_ROWS + nl;
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) v[b] += __ldcg(pa + b * QG_ROWS);
+                }
+                q_epilogue16(p, n, lane, b0, v);
             }
-            if (c <= c_last) {
-                const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + nl;
-#pragma unroll
-                for (int b = 0; b < NB; ++b) v[b] += __ldcg(pa + b * QG_ROWS);
-            }
-            q_epilogue<NB>(p, n, lane, v);
         }
     }
     q_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(QG_TMEM_COLS) : "memory");
 }
 
 // ---- load time: native GGUF rows -> QG qtile stream -----------------------------------------------------------------------

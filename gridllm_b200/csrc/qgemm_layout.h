@@ -11,8 +11,9 @@
 //   plane  : inside a qtile the fields of the 128 super-blocks are regrouped into planes of [128 rows][16 B], so that the 32
 //            lanes of a warp (32 consecutive rows) read 512 contiguous bytes per 128-bit load -- no bank conflicts, no 2-byte
 //            aligned 210-byte records
-//   K-step : 64 columns = one tcgen05 operand tile [128 rows x 64] fp16 (16 KB, 128-byte swizzle); a qtile is 4 K-steps
-//   chunk  : 8 consecutive columns of one row = one 16-byte store into the operand tile
+//   K-step : 64 columns = one tcgen05 A operand [128 rows x 64] fp16 -- kept in TENSOR MEMORY (lane = row, 32 columns of two
+//            fp16 each), written by the unpack warps with tcgen05.st, never staged in shared memory; a qtile is 4 K-steps
+//   chunk  : 8 consecutive columns of one row = four packed half2 words
 //
 // QG layouts (a lossless permutation of the GGUF bits; pack_block() below is the definition):
 //   Q4_K qtile : [hdr  : 128 x 16 B]  d, dmin, scales[12] of each row's block, verbatim
@@ -50,17 +51,12 @@ constexpr int QG_KSTEP = 64;                 // columns of one operand tile
 constexpr int QG_PLANE = QG_ROWS * 16;       // bytes of one plane
 constexpr int QG_Q4K_BYTES = 9 * QG_PLANE;                       // 18 432
 constexpr int QG_Q6K_BYTES = 13 * QG_PLANE + QG_ROWS * 2;        // 26 880
-constexpr int QG_A_TILE_BYTES = QG_ROWS * QG_KSTEP * 2;          // 16 384
 
 GL_HD int qg_qtile_bytes(int type) { return type == 12 ? QG_Q4K_BYTES : type == 14 ? QG_Q6K_BYTES : 0; }
 GL_HD bool qg_type_ok(int type) { return type == 12 || type == 14; }
 
 // nibble position of column i (0..7) inside a 32-bit word
 GL_HD int qg_nib_pos(int i) { return (i >> 1) + 4 * (i & 1); }
-
-// byte offset of chunk c (0..7) of row r (0..127) inside a [128 x 64] fp16 operand tile with the 128-byte swizzle TMA and
-// tcgen05 use for K-major operands: 8-row atoms of 1024 B, the 16-byte chunk index XORed with the row index inside the atom
-GL_HD int qg_a_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
 
 // ---- load time (device kernel in qgemm.cu; the host check runs the same code): one GGUF super-block of tile row r -> its
 // 16-byte words in the planes of the qtile image.  Every (row, plane) word is written exactly once, by the thread that owns the row.
@@ -172,22 +168,15 @@ QG_FN void qg_q6k_word(uint32_t lo, uint32_t hi16, QH2 s2, uint32_t out[4]) {
     }
 }
 
-// ---- the per-thread program of the kernel's dequantisation warps -------------------------------------------------------------
-// Thread (row r, half h) turns columns 128h..128h+127 of row r's super-block into 16 chunks: K-steps 2h and 2h+1, chunks 0..7 each.
-// `raw` is the qtile image in shared memory, `a_tiles` the base of FOUR consecutive operand tiles (K-steps 0..3 of this qtile;
-// the kernel passes the ring slots' addresses through a_tile_of(kstep)).  The host check calls it with plain arrays.
 struct QgU4 { uint32_t x, y, z, w; };
 
-// 128-bit loads / stores of the program: SHARED-memory instructions on the device (the kernel only ever passes shared-memory
-// pointers; a generic-address load would cost an address-space lookup per access), plain memory on the host
+// 128-bit loads of the program: SHARED-memory instructions on the device (the kernel only ever passes shared-memory pointers; a
+// generic-address load would cost an address-space lookup per access), plain memory on the host
 #if defined(__CUDACC__)
 QG_FN QgU4 qg_ld128(const uint8_t* p) {
     QgU4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
     return v;
-}
-QG_FN void qg_st128(uint8_t* p, QgU4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 QG_FN uint16_t qg_ld16(const uint8_t* p) {
     uint16_t v;
@@ -196,68 +185,58 @@ QG_FN uint16_t qg_ld16(const uint8_t* p) {
 }
 #else
 QG_FN QgU4 qg_ld128(const uint8_t* p) { QgU4 v; memcpy(&v, p, 16); return v; }
-QG_FN void qg_st128(uint8_t* p, QgU4 v) { memcpy(p, &v, 16); }
 QG_FN uint16_t qg_ld16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 #endif
 
-template <typename ATileOf, typename BeforeKStep, typename AfterKStep>
-QG_FN void qg_dequant_thread(int type, const uint8_t* raw, int r, int h, ATileOf a_tile_of, BeforeKStep before, AfterKStep after) {
+// ---- the per-thread program of the kernel's unpack warps -------------------------------------------------------------------
+// Thread (row r, K-step kk) turns columns 64kk..64kk+63 of row r's super-block into 8 chunks of 8 fp16 (four packed half2 words
+// each) and hands them to `store(c, words)`, c = 0..7 in column order.  The kernel collects the 32 words in registers and writes
+// them to TENSOR MEMORY (the A operand of the MMA: lane = row, column = k / 2); the host check writes them to a plain array.
+// `raw` is the qtile image (shared memory on the device).
+template <typename StoreChunk>
+QG_FN void qg_dequant_kstep(int type, const uint8_t* raw, int r, int kk, StoreChunk store) {
     if (type == 12) {
         const QgU4 hdr = qg_ld128(raw + r * 16);
         const float d = half_bits_to_float((uint16_t)(hdr.x & 0xFFFF)), dmin = half_bits_to_float((uint16_t)(hdr.x >> 16));
 #pragma unroll
-        for (int kk2 = 0; kk2 < 2; ++kk2) {
-            const int kk = 2 * h + kk2;
-            before(kk);
-            uint8_t* tile = a_tile_of(kk);
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * kk + jj;                                                  // sub-block of 32 columns
+            int sc, mn;
+            qg_q4k_scale_min(j, hdr.y, hdr.z, hdr.w, sc, mn);
+            const QH2 s2 = qh2_set(d * (float)sc), nm2 = qh2_set(-(dmin * (float)mn));
+            const QgU4 q = qg_ld128(raw + (1 + j) * QG_PLANE + r * 16);
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = 2 * kk + jj;
-                int sc, mn;
-                qg_q4k_scale_min(j, hdr.y, hdr.z, hdr.w, sc, mn);
-                const QH2 s2 = qh2_set(d * (float)sc), nm2 = qh2_set(-(dmin * (float)mn));
-                const QgU4 q = qg_ld128(raw + (1 + j) * QG_PLANE + r * 16);
-                const uint32_t words[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    uint32_t o[4];
-                    qg_q4k_word(words[t], s2, nm2, o);
-                    qg_st128(tile + qg_a_off(r, jj * 4 + t), QgU4{o[0], o[1], o[2], o[3]});
-                }
+            for (int t = 0; t < 4; ++t) {
+                uint32_t o[4];
+                qg_q4k_word(words[t], s2, nm2, o);
+                store(jj * 4 + t, QgU4{o[0], o[1], o[2], o[3]});
             }
-            after(kk);
         }
     } else {
         const QgU4 scw = qg_ld128(raw + 12 * QG_PLANE + r * 16);
-        // this thread's eight scales (columns 128h..128h+127): two words picked by h, then indexed by compile-time constants only
-        // (a 4-word array indexed by a run-time h is a local-memory array: every scale a round trip through L1)
-        const uint32_t scs2[2] = {h ? scw.z : scw.x, h ? scw.w : scw.y};
+        // the four scales of this K-step (16-column sub-blocks 4kk..4kk+3) are ONE word of the row's sixteen: picked by kk with
+        // selects, then indexed by compile-time constants only (an array indexed at run time would live in local memory)
+        const uint32_t sc4 = kk == 0 ? scw.x : kk == 1 ? scw.y : kk == 2 ? scw.z : scw.w;
         const float d = half_bits_to_float(qg_ld16(raw + 13 * QG_PLANE + r * 2));
+        const QgU4 hq = qg_ld128(raw + (8 + kk) * QG_PLANE + r * 16);                   // high bits of columns 64kk..64kk+63
+        const uint32_t hwords[4] = {hq.x, hq.y, hq.z, hq.w};
 #pragma unroll
-        for (int kk2 = 0; kk2 < 2; ++kk2) {
-            const int kk = 2 * h + kk2;
-            before(kk);
-            uint8_t* tile = a_tile_of(kk);
-            const QgU4 hq = qg_ld128(raw + (8 + kk) * QG_PLANE + r * 16);      // high bits of columns 64kk..64kk+63
-            const uint32_t hwords[4] = {hq.x, hq.y, hq.z, hq.w};
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * kk + jj;                                                  // 32-column group
+            const QgU4 q = qg_ld128(raw + j * QG_PLANE + r * 16);
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = 2 * kk + jj;                                                             // 32-column group
-                const QgU4 q = qg_ld128(raw + j * QG_PLANE + r * 16);
-                const uint32_t words[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    // columns 32j + 8t .. +7: 16-column sub-block g = 2j + t/2 (scale byte g), high bits in half-word t&1 of word 2jj + t/2
-                    // 16-column sub-block g = 8h + 4kk2 + 2jj + t/2: word kk2 of this thread's pair, byte 2jj + t/2
-                    const int sc = (int)(int8_t)((scs2[kk2] >> (8 * (2 * jj + (t >> 1)))) & 0xFF);
-                    const QH2 s2 = qh2_set(d * (float)sc);
-                    const uint32_t hw = hwords[2 * jj + (t >> 1)];
-                    uint32_t o[4];
-                    qg_q6k_word(words[t], (t & 1) ? (hw >> 16) : (hw & 0xFFFFu), s2, o);
-                    qg_st128(tile + qg_a_off(r, jj * 4 + t), QgU4{o[0], o[1], o[2], o[3]});
-                }
+            for (int t = 0; t < 4; ++t) {
+                // columns 32j + 8t .. +7: 16-column sub-block 4kk + 2jj + t/2 (byte 2jj + t/2 of sc4), high bits in half-word t & 1
+                // of word 2jj + t/2
+                const int sc = (int)(int8_t)((sc4 >> (8 * (2 * jj + (t >> 1)))) & 0xFF);
+                const QH2 s2 = qh2_set(d * (float)sc);
+                const uint32_t hw = hwords[2 * jj + (t >> 1)];
+                uint32_t o[4];
+                qg_q6k_word(words[t], (t & 1) ? (hw >> 16) : (hw & 0xFFFFu), s2, o);
+                store(jj * 4 + t, QgU4{o[0], o[1], o[2], o[3]});
             }
-            after(kk);
         }
     }
 }

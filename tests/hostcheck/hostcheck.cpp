@@ -174,22 +174,16 @@ extern "C" int hc_qg_dequant(int type, const uint8_t* blocks /*[128][block bytes
     std::vector<uint8_t> qt((size_t)qg_qtile_bytes(type) + 64, 0xAB);     // poison: every byte must be written by the packer
     for (int r = 0; r < QG_ROWS; ++r) qg_pack_block(type, blocks + (size_t)r * bb, qt.data(), r);
     *qtile_bytes = qg_qtile_bytes(type);
-    alignas(16) static uint8_t tiles[4 * QG_A_TILE_BYTES];
-    memset(tiles, 0xCD, sizeof tiles);
-    int order_ok = 1, last[2] = {-1, -1};
-    for (int h = 0; h < 2; ++h)
+    std::vector<int> written((size_t)QG_ROWS * QG_COLS / 8, 0);
+    for (int kk = 0; kk < 4; ++kk)                                           // the kernel's 512 unpack threads: (row, K-step)
         for (int r = 0; r < QG_ROWS; ++r)
-            qg_dequant_thread(type, qt.data(), r, h, [&](int kk) { return tiles + (size_t)kk * QG_A_TILE_BYTES; },
-                              [&](int kk) { if (kk / 2 != h) order_ok = 0; last[h] = kk; }, [&](int) {});
-    if (!order_ok) return -2;
-    for (int r = 0; r < QG_ROWS; ++r)
-        for (int col = 0; col < QG_COLS; ++col) {
-            const int kk = col / QG_KSTEP, c = (col % QG_KSTEP) / 8, i = col % 8;
-            // what the tensor core reads as element (row r, k = col % 64) of K-step kk: the chunk sits at chunk slot c ^ (r & 7)
-            const uint8_t* p = tiles + (size_t)kk * QG_A_TILE_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((c ^ (r & 7)) << 4) + 2 * i;
-            uint16_t v;
-            memcpy(&v, p, 2);
-            out[(size_t)r * QG_COLS + col] = v;
-        }
+            qg_dequant_kstep(type, qt.data(), r, kk, [&](int c, QgU4 v) {
+                // chunk c of K-step kk = columns 64kk + 8c .. +7 of row r: words in column order, two fp16 per word (low half first) --
+                // exactly what tcgen05.st puts into TMEM columns 4c .. 4c+3 of the row's lane
+                memcpy(out + (size_t)r * QG_COLS + 64 * kk + 8 * c, &v, 16);
+                ++written[((size_t)r * QG_COLS + 64 * kk + 8 * c) / 8];
+            });
+    for (int w : written)
+        if (w != 1) return -2;                                               // every chunk exactly once
     return 0;
 }
