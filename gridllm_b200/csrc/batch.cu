@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256) batch_rope_kv_kernel(const float* __restr
                                                             int n_head, int n_kv, int hd, const float* __restrict__ cos_t,
                                                             const float* __restrict__ sin_t, float* __restrict__ q_out,
                                                             __half* __restrict__ k_cache, __half* __restrict__ v_cache) {
+    pdl_launch_dependents();                        // the next kernel of the step may start its own prologue (qgemm: its weight stream)
+    pdl_wait();                                     // ... while this one waits here for the QKV rows
     const int r = blockIdx.x;
     if (r >= ctl->n_rows) return;
     const int slot = ctl->row_slot[r];
@@ -197,8 +199,9 @@ template <int HD> struct BamCfg {
     static constexpr int ROW_BYTES = HD * 2;
     static constexpr int PAGE_BYTES = KV_PAGE_TOKENS * ROW_BYTES;
     static constexpr int CHUNKS_PER_ROW = ROW_BYTES / 16;
-    static constexpr int WARP_BYTES = 2 /*buffers*/ * 2 /*K, V*/ * PAGE_BYTES;
-    static constexpr size_t SMEM = (size_t)4 * WARP_BYTES;       // 64 KB (head_dim 128): three CTAs per SM; the merge reuses the page buffers
+    static constexpr int NBUF = 3;                               // pages in flight per warp: two ahead of the one being multiplied
+    static constexpr int WARP_BYTES = NBUF * 2 /*K, V*/ * PAGE_BYTES;
+    static constexpr size_t SMEM = (size_t)4 * WARP_BYTES;       // 96 KB (head_dim 128): two CTAs per SM; the merge reuses the page buffers
     static_assert(8 * (HD + 2) * 4 <= WARP_BYTES, "a warp's (m, l, O) of 8 heads must fit its own page buffers");
 };
 
@@ -225,12 +228,14 @@ __device__ __forceinline__ uint32_t bam_pack(float lo, float hi) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(128, 3) batch_attn_mma_kernel(const __grid_constant__ BatchAttnParams p) {
+__global__ void __launch_bounds__(128, 2) batch_attn_mma_kernel(const __grid_constant__ BatchAttnParams p) {
     using Cfg = BamCfg<HD>;
     constexpr int KSTEPS = HD / 16, NT = HD / 8;
     extern __shared__ __align__(128) uint8_t bam_smem[];
     __shared__ int is_last;
 
+    pdl_launch_dependents();
+    pdl_wait();                                     // q and the newest K / V rows come from the kernel before
     const int row = blockIdx.z;
     if (row >= p.ctl->n_rows) return;
     const int slot = p.ctl->row_slot[row];
@@ -267,12 +272,12 @@ __global__ void __launch_bounds__(128, 3) batch_attn_mma_kernel(const __grid_con
     for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
     float m_run = -INFINITY, l_run = 0.f;
 
-    auto issue = [&](int j) {          // page j of this warp -> buffer j & 1 (K then V), 16-byte chunks swizzled by the row
+    auto issue = [&](int j) {          // page j of this warp -> buffer j % NBUF (K then V), 16-byte chunks swizzled by the row
         const int pg = split + (warp + 4 * j) * S;
         const size_t off = ((size_t)table[pg] * p.n_kv_heads + kvh) * (size_t)(KV_PAGE_TOKENS * HD);
         const uint8_t* ksrc = reinterpret_cast<const uint8_t*>(p.k_cache + off);
         const uint8_t* vsrc = reinterpret_cast<const uint8_t*>(p.v_cache + off);
-        const uint32_t kdst = smem_u32(wbuf + (size_t)(j & 1) * 2 * Cfg::PAGE_BYTES), vdst = kdst + Cfg::PAGE_BYTES;
+        const uint32_t kdst = smem_u32(wbuf + (size_t)(j % Cfg::NBUF) * 2 * Cfg::PAGE_BYTES), vdst = kdst + Cfg::PAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < Cfg::PAGE_BYTES / 16 / 32; ++i) {
             const int ci = i * 32 + lane, r = ci / Cfg::CHUNKS_PER_ROW, c = ci % Cfg::CHUNKS_PER_ROW;
@@ -282,11 +287,16 @@ __global__ void __launch_bounds__(128, 3) batch_attn_mma_kernel(const __grid_con
         }
         bam_commit();
     };
-    if (w_pages > 0) issue(0);
+    // a page costs a full HBM round trip (~1 us under load) and ~0.3 us of math: with ONE page ahead a warp is latency-bound
+    // (1.2 us per page, r02 run D); two ahead keep the memory pipe of the warp busy.  One commit group per page, empty when the
+    // warp has run out of pages, so that wait_group<NBUF - 1> always means "page j has landed".
+#pragma unroll
+    for (int j = 0; j < Cfg::NBUF - 1; ++j) { if (j < w_pages) issue(j); else bam_commit(); }
     for (int j = 0; j < w_pages; ++j) {
-        if (j + 1 < w_pages) { issue(j + 1); bam_wait<1>(); } else { bam_wait<0>(); }
+        if (j + Cfg::NBUF - 1 < w_pages) issue(j + Cfg::NBUF - 1); else bam_commit();
+        bam_wait<Cfg::NBUF - 1>();
         __syncwarp();
-        const uint32_t kb = smem_u32(wbuf + (size_t)(j & 1) * 2 * Cfg::PAGE_BYTES), vb = kb + Cfg::PAGE_BYTES;
+        const uint32_t kb = smem_u32(wbuf + (size_t)(j % Cfg::NBUF) * 2 * Cfg::PAGE_BYTES), vb = kb + Cfg::PAGE_BYTES;
         const int pg = split + (warp + 4 * j) * S;
         const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
         // ---- S = Q K^T : two n-tiles (positions 0-7, 8-15) ----
@@ -489,6 +499,8 @@ __global__ void __launch_bounds__(MAX_BATCH) batch_collect_kernel(const BatchCtl
 
 __global__ void __launch_bounds__(256) batch_rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, int n, float eps,
                                                             __half* __restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x;
     __shared__ float red[8];
     const float* xr = x + (size_t)r * n;
@@ -504,7 +516,29 @@ __global__ void __launch_bounds__(256) batch_rmsnorm_kernel(const float* __restr
     for (int i = threadIdx.x; i < n; i += 256) yr[i] = __float2half_rn((xr[i] * rstd) * w[i]);
 }
 
+// launch with the programmatic-dependent-launch attribute: the kernel may become resident while its predecessor in the stream
+// is still running and blocks in pdl_wait() before it touches anything (GL_BATCH_PDL=0: plain stream order, for A/B runs)
+template <typename... Args>
+cudaError_t launch_dep(void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = batch_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 }  // namespace
+
+bool batch_pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("GL_BATCH_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 cudaError_t batch_gather_tokens_launch(const BatchCtl* ctl, const StepState* st, int* ids, int bucket, cudaStream_t s) {
     batch_gather_tokens_kernel<<<1, MAX_BATCH, 0, s>>>(ctl, st, ids, bucket);
@@ -515,9 +549,8 @@ cudaError_t batch_rope_kv_launch(const float* qkv, int bucket, const BatchCtl* c
                                  int n_head, int n_kv, int hd, const float* cos_t, const float* sin_t, float* q_out, __half* k_cache,
                                  __half* v_cache, cudaStream_t s) {
     const int slices = std::max(1, std::min(8, ((n_head + n_kv) * hd / 2 + 255) / 256));
-    batch_rope_kv_kernel<<<dim3((unsigned)bucket, (unsigned)slices), 256, 0, s>>>(qkv, ctl, st, tables, table_stride, n_head, n_kv, hd, cos_t, sin_t, q_out,
-                                                                                   k_cache, v_cache);
-    return cudaGetLastError();
+    return launch_dep(batch_rope_kv_kernel, dim3((unsigned)bucket, (unsigned)slices), dim3(256), 0, s, qkv, ctl, st, tables, table_stride, n_head, n_kv, hd,
+                      cos_t, sin_t, q_out, k_cache, v_cache);
 }
 
 cudaError_t batch_attn_configure() {
@@ -532,10 +565,9 @@ cudaError_t batch_attn_launch(const BatchAttnParams& p, int bucket, cudaStream_t
     const dim3 grid((unsigned)p.n_kv_heads, (unsigned)p.n_splits, (unsigned)bucket);
     static const bool use_mma = []() { const char* e = getenv("GL_BATCH_ATTN_MMA"); return !(e && e[0] == '0'); }();
     if (use_mma) {       // tensor-core kernel (default); GL_BATCH_ATTN_MMA=0 keeps the scalar one for A/B runs
-        if (p.head_dim == 128) batch_attn_mma_kernel<128><<<grid, 128, BamCfg<128>::SMEM, s>>>(p);
-        else if (p.head_dim == 64) batch_attn_mma_kernel<64><<<grid, 128, BamCfg<64>::SMEM, s>>>(p);
-        else return cudaErrorInvalidValue;
-        return cudaGetLastError();
+        if (p.head_dim == 128) return launch_dep(batch_attn_mma_kernel<128>, grid, dim3(128), (size_t)BamCfg<128>::SMEM, s, p);
+        if (p.head_dim == 64) return launch_dep(batch_attn_mma_kernel<64>, grid, dim3(128), (size_t)BamCfg<64>::SMEM, s, p);
+        return cudaErrorInvalidValue;
     }
     if (p.head_dim == 128) batch_attn_kernel<4><<<grid, 32 * grp, 0, s>>>(p);
     else if (p.head_dim == 64) batch_attn_kernel<2><<<grid, 32 * grp, 0, s>>>(p);
@@ -557,8 +589,7 @@ cudaError_t batch_collect_launch(const BatchCtl* ctl, const StepState* st, const
 
 cudaError_t batch_rmsnorm_launch(const float* x, const float* w, int rows, int n, float eps, __half* y, cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
-    batch_rmsnorm_kernel<<<rows, 256, 0, s>>>(x, w, n, eps, y);
-    return cudaGetLastError();
+    return launch_dep(batch_rmsnorm_kernel, dim3((unsigned)rows), dim3(256), 0, s, x, w, n, eps, y);
 }
 
 }  // namespace gl

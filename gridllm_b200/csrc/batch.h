@@ -49,6 +49,7 @@ struct BatchAttnParams {
     float scale;
 };
 
+bool batch_pdl_enabled();              // GL_BATCH_PDL (default on): the per-layer kernels of the step use programmatic dependent launch
 // ids[r] = token of row r's sequence (0 for rows beyond n_rows, so that padded rows stay finite)
 cudaError_t batch_gather_tokens_launch(const BatchCtl* ctl, const StepState* st, int* ids, int bucket, cudaStream_t s);
 // QKV rows fp32 [bucket x (qd + 2 kvd)]: RoPE at each row's own position, q out fp32, K / V appended to the row's own pages

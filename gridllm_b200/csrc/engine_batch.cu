@@ -34,11 +34,13 @@ Status failb(int code, const std::string& m) { return Status{code, m}; }
         if (!_s.ok()) return _s; \
     } while (0)
 
-int attn_splits_for(int bucket, int n_kv) {
-    // enough CTAs to fill the machine a few times over; every split costs a partial + a merge, so no more than that
-    int s = 1;
-    while (s < 16 && n_kv * bucket * s < 512) s <<= 1;
-    return s;
+int attn_splits_for(int bucket, int n_kv, int n_sm) {
+    // ONE wave of CTAs: the tensor-core kernel keeps two CTAs per SM resident (96 KB of page buffers each), and a second,
+    // mostly empty wave costs as much as the first (B = 32 with 2 splits: 512 CTAs on 444 slots took 28.8 us against 11 us of
+    // KV traffic).  Within one wave, as many splits as fit: every split shortens the per-warp chain of dependent page loads.
+    const int slots = 2 * n_sm;
+    int s = slots / std::max(1, n_kv * bucket);
+    return std::max(1, std::min(16, s));
 }
 }  // namespace
 
@@ -497,7 +499,7 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
     };
     CU(batch_gather_tokens_launch(bctl_, bst_, bids_, bucket, s)); ++nl;
     CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, bids_, bucket, bx_, s)); ++nl;
-    const int splits = attn_splits_for(bucket, n_kv_);
+    const int splits = attn_splits_for(bucket, n_kv_, sm_count_);
     for (int il = 0; il < n_layer_; ++il) {
         const LayerWeights& L = layers_[il];
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;

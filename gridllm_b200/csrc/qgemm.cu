@@ -35,6 +35,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "batch.h"
 #include "common.cuh"
 #include "qgemm.h"
 #include "qgemm_layout.h"
@@ -214,6 +215,9 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     q_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Programmatic dependent launch: everything up to here, the weight stream and the unpacking of the first two qtiles need
+    // nothing from the kernel before -- only the activations (read) and C / the split-tile scratch (written) do.
+    pdl_launch_dependents();
     if (warp == 0) {
         if (lane == 0) {
             // ===== weight producer: one 1-D bulk copy per qtile, as far ahead as the raw ring is deep =====
@@ -241,6 +245,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         if (lane == 0) {
             // ===== activation producer: the four [NB x 64] boxes of a qtile's K range (L2-resident), two qtiles deep =====
             int kb = u0 % nkb;
+            pdl_wait();                                               // the activations are the output of the kernel before
             for (int u = u0; u < u1; ++u) {
                 const int i = u - u0, s = i & 1;
                 uint8_t* st = act_ring + (size_t)s * 4 * Cfg::B_TILE;
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         const int nl = q * 32 + lane;                                 // row inside the tile
         int seg = 0;
         int tile = u0 / nkb, kb_lo = u0 - tile * nkb;
+        pdl_wait();                                                   // C, the scratch and the tickets may still be in use by the kernel before
         for (int u = u0; u < u1; ++seg, ++tile) {
             const int n_kb = min(nkb - kb_lo, u1 - u);
             kb_lo = 0;
@@ -432,8 +438,17 @@ template <int NB>
 cudaError_t launch_nb(QParams& qp, int grid, cudaStream_t s) {
     qp.raw_stages = std::min(QG_MAX_RAW_STAGES, QCfg<NB>::RAW_BUDGET / qp.raw_stride);
     if (qp.raw_stages < 2) return cudaErrorInvalidValue;
-    qgemm_kernel<NB><<<grid, QG_THREADS, QG_SMEM, s>>>(qp);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(QG_THREADS);
+    cfg.dynamicSmemBytes = QG_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = batch_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, qgemm_kernel<NB>, qp);
 }
 
 }  // namespace

@@ -21,11 +21,11 @@
 //                                   = columns 32j+8t..+7, column i of the eight at nibble position NIB_POS[i]
 //   Q6_K qtile : [lo_j : 128 x 16 B, j = 0..7]  low nibbles of columns 32j..32j+31, same word / nibble order
 //                [hi_k : 128 x 16 B, k = 0..3]  the 2 high bits of columns 64k..64k+63: four 32-bit words, word u = columns
-//                                   64k+16u..+15; low half-word = the first eight columns, high half-word the second eight;
-//                                   in a half-word, pair p = columns (2p, 2p+1): bits [2p, 2p+1] and [8+2p, 8+2p+1]
+//                                   64k+16u..+15; of a pair of columns (2p, 2p+1) the first lives in the low 16-bit half, the
+//                                   second in the high half, at bit qg_q6k_hi_pos(second eight?, p) -- see there
 //                [sc   : 128 x 16 B]  int8 scales[16], verbatim       [d : 128 x 2 B]
-//   NIB_POS = {0, 4, 1, 5, 2, 6, 3, 7}: (w >> 4p) & 0x000F000F then holds columns (2p, 2p+1) in its two 16-bit halves -- one
-//   logic op away from a half2 via the 0x6400 exponent trick (1024 + q is exact in fp16).
+//   NIB_POS = {0, 4, 1, 5, 2, 6, 3, 7}: columns (2p, 2p+1) are the same nibble of the word's two 16-bit halves -- one logic op
+//   away from a half2 via the exponent trick (1024 + q, or 64 + q for a nibble at bits 4..7, is exact in fp16).
 //
 // Dequantised value (what the tensor core multiplies), in fp16 arithmetic with one rounding per step:
 //   Q4_K : w = fma(q, s, -m),  s = fp16(d * sc), m = fp16(dmin * mn)         (GGUF: d*sc*q - dmin*mn)
@@ -57,6 +57,13 @@ GL_HD bool qg_type_ok(int type) { return type == 12 || type == 14; }
 
 // nibble position of column i (0..7) inside a 32-bit word
 GL_HD int qg_nib_pos(int i) { return (i >> 1) + 4 * (i & 1); }
+
+// Q6_K high bits: bit position (inside its 16-bit half) of the 2-bit field of pair p of the FIRST (A) / SECOND (B) eight columns
+// of a 16-column hi word.  A's fields sit where the exponent trick wants them ([4,5] under 1024, [8,9] under 64) or two bits
+// above (pairs 2, 3: one shared >> 2); B's take the remaining bits and one shift each.
+GL_HD int qg_q6k_hi_pos(int second_eight, int p) {
+    return second_eight ? (p == 0 ? 12 : p == 1 ? 14 : p == 2 ? 0 : 2) : (p == 0 ? 4 : p == 1 ? 8 : p == 2 ? 6 : 10);
+}
 
 // ---- load time (device kernel in qgemm.cu; the host check runs the same code): one GGUF super-block of tile row r -> its
 // 16-byte words in the planes of the qtile image.  Every (row, plane) word is written exactly once, by the thread that owns the row.
@@ -95,9 +102,10 @@ GL_HD void qg_pack_block(int type, const uint8_t* blk, uint8_t* qtile, int r) {
             for (int cc = 0; cc < 64; ++cc) {
                 const int e = 64 * k + cc, h = e >> 7, rr = e & 127;
                 const uint32_t qh = (uint32_t)(blk[128 + h * 32 + (rr & 31)] >> (2 * (rr >> 5))) & 3u;
-                // word cc/16, half-word (cc%16)/8, pair p = (cc%8)/2, first / second of the pair
-                const int i = cc & 7, p = i >> 1, second = i & 1, halfword = (cc & 15) >> 3;
-                w[cc >> 4] |= qh << (16 * halfword + 8 * second + 2 * p);
+                // word cc/16; first / second eight columns of its sixteen; pair p = (cc%8)/2; the pair's first column in the low
+                // 16-bit half, its second in the high half (like the nibbles)
+                const int i = cc & 7;
+                w[cc >> 4] |= qh << (16 * (i & 1) + qg_q6k_hi_pos((cc & 15) >> 3, i >> 1));
             }
             qg_store_word(qtile + (8 + k) * QG_PLANE + r * 16, w);
         }
@@ -132,7 +140,30 @@ inline QH2 qh2_fma(QH2 a, QH2 b, QH2 c) {
 }
 #endif
 
-constexpr uint32_t QG_MAGIC = 0x64006400u;     // fp16 1024.0 in both halves: (1024 | q) is the exact fp16 value 1024 + q for q < 1024
+// The exponent trick: OR-ing a small integer into the mantissa of a suitable fp16 constant gives base + integer EXACTLY --
+//   bits [0, 6) under 0x6400 (1024.0, one unit per mantissa step):  1024 + q
+//   bits [4, 10) under 0x5400 (64.0, 1/16 per mantissa step):         64 + (bits >> 4)
+// so the nibble at bits 4..7 of a word needs no shift, and a word of eight nibbles costs ONE shift (>> 8) and four logic ops.
+constexpr uint32_t QG_MAGIC = 0x64006400u, QG_MAGIC_HI = 0x54005400u;
+constexpr uint32_t QG_NIB_LO = 0x000F000Fu, QG_NIB_HI = 0x00F000F0u;
+
+// (a & b) | c  and  a | (b & c): one LOP3 each on the device (written as separate & and | the compiler emits two when both
+// constants are immediates; the unpack warps are bound by exactly this pipe)
+#if defined(__CUDACC__)
+QG_FN uint32_t qg_and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+QG_FN uint32_t qg_or_and(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xF8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#else
+inline uint32_t qg_and_or(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | c; }
+inline uint32_t qg_or_and(uint32_t a, uint32_t b, uint32_t c) { return a | (b & c); }
+#endif
 
 // Q4_K scale / min of sub-block j from the three scale words (bytes 0..3, 4..7, 8..11 of scales[12])
 GL_HD void qg_q4k_scale_min(int j, uint32_t s0, uint32_t s1, uint32_t s2, int& sc, int& mn) {
@@ -146,26 +177,34 @@ GL_HD void qg_q4k_scale_min(int j, uint32_t s0, uint32_t s1, uint32_t s2, int& s
     }
 }
 
-// One 32-bit word of eight Q4_K nibbles -> four half2 (columns 0-1, 2-3, 4-5, 6-7): fma(q, s, -m)
+// One 32-bit word of eight Q4_K nibbles -> four half2 (columns 0-1, 2-3, 4-5, 6-7): fma(q, s, -m).
+// 1 shift + 4 logic ops (alu pipe), 4 subtractions + 4 fma (fma pipe) for eight weights.
 QG_FN void qg_q4k_word(uint32_t w, QH2 s2, QH2 nm2, uint32_t out[4]) {
-    const QH2 k1024 = qh2_bits(QG_MAGIC);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const QH2 q = qh2_sub(qh2_bits(((w >> (4 * p)) & 0x000F000Fu) | QG_MAGIC), k1024);
-        out[p] = qh2_to_bits(qh2_fma(q, s2, nm2));
-    }
+    const QH2 k1024 = qh2_bits(QG_MAGIC), k64 = qh2_bits(QG_MAGIC_HI);
+    const uint32_t w8 = w >> 8;
+    out[0] = qh2_to_bits(qh2_fma(qh2_sub(qh2_bits(qg_and_or(w, QG_NIB_LO, QG_MAGIC)), k1024), s2, nm2));
+    out[1] = qh2_to_bits(qh2_fma(qh2_sub(qh2_bits(qg_and_or(w, QG_NIB_HI, QG_MAGIC_HI)), k64), s2, nm2));
+    out[2] = qh2_to_bits(qh2_fma(qh2_sub(qh2_bits(qg_and_or(w8, QG_NIB_LO, QG_MAGIC)), k1024), s2, nm2));
+    out[3] = qh2_to_bits(qh2_fma(qh2_sub(qh2_bits(qg_and_or(w8, QG_NIB_HI, QG_MAGIC_HI)), k64), s2, nm2));
 }
 
-// One 32-bit word of eight Q6_K low nibbles + its 16 bits of high pairs -> four half2: (q - 32) * s
-// s2a / s2b: the scales of the first / second four columns are the same 16-column sub-block, so one scale per word
-QG_FN void qg_q6k_word(uint32_t lo, uint32_t hi16, QH2 s2, uint32_t out[4]) {
-    const QH2 k1056 = qh2_bits(0x64206420u);                        // 1024 + 32
-    const uint32_t x4 = ((hi16 & 0xFFu) | ((hi16 & 0xFF00u) << 8)) << 4;      // first-of-pair bits -> [4,5]+2p, second-of-pair -> [20,21]+2p
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const uint32_t q = ((lo >> (4 * p)) & 0x000F000Fu) | ((x4 >> (2 * p)) & 0x00300030u) | QG_MAGIC;
-        out[p] = qh2_to_bits(qh2_mul(qh2_sub(qh2_bits(q), k1056), s2));
-    }
+// One 32-bit word of eight Q6_K low nibbles + the hi word of its 16-column group -> four half2: (q - 32) * s
+// (the eight columns are one half of a 16-column sub-block: one scale)
+template <int SECOND>
+QG_FN void qg_q6k_word(uint32_t lo, uint32_t hw, QH2 s2, uint32_t out[4]) {
+    const QH2 k1056 = qh2_bits(0x64206420u), k96 = qh2_bits(0x56005600u);      // 1024 + 32, 64 + 32
+    const uint32_t lo8 = lo >> 8;
+    uint32_t h0, h1, h2, h3;
+    if (SECOND) { h0 = hw >> 8; h1 = hw >> 6; h2 = hw << 4; h3 = hw << 6; }
+    else { h0 = hw; h1 = hw; h2 = hw >> 2; h3 = h2; }
+    const uint32_t q0 = qg_or_and(qg_and_or(lo, QG_NIB_LO, QG_MAGIC), h0, 0x00300030u);
+    const uint32_t q1 = qg_or_and(qg_and_or(lo, QG_NIB_HI, QG_MAGIC_HI), h1, 0x03000300u);
+    const uint32_t q2 = qg_or_and(qg_and_or(lo8, QG_NIB_LO, QG_MAGIC), h2, 0x00300030u);
+    const uint32_t q3 = qg_or_and(qg_and_or(lo8, QG_NIB_HI, QG_MAGIC_HI), h3, 0x03000300u);
+    out[0] = qh2_to_bits(qh2_mul(qh2_sub(qh2_bits(q0), k1056), s2));
+    out[1] = qh2_to_bits(qh2_mul(qh2_sub(qh2_bits(q1), k96), s2));
+    out[2] = qh2_to_bits(qh2_mul(qh2_sub(qh2_bits(q2), k1056), s2));
+    out[3] = qh2_to_bits(qh2_mul(qh2_sub(qh2_bits(q3), k96), s2));
 }
 
 struct QgU4 { uint32_t x, y, z, w; };
@@ -234,7 +273,8 @@ QG_FN void qg_dequant_kstep(int type, const uint8_t* raw, int r, int kk, StoreCh
                 const QH2 s2 = qh2_set(d * (float)sc);
                 const uint32_t hw = hwords[2 * jj + (t >> 1)];
                 uint32_t o[4];
-                qg_q6k_word(words[t], (t & 1) ? (hw >> 16) : (hw & 0xFFFFu), s2, o);
+                if (t & 1) qg_q6k_word<1>(words[t], hw, s2, o);
+                else qg_q6k_word<0>(words[t], hw, s2, o);
                 store(jj * 4 + t, QgU4{o[0], o[1], o[2], o[3]});
             }
         }
