@@ -98,6 +98,15 @@ __device__ __forceinline__ void q_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 // 32 lanes x 32 columns: thread t of the warp writes its 32 registers to columns [col, col + 32) of lane (lane base + t)
+__device__ __forceinline__ void tmem_st_32x32_nowait(uint32_t taddr, const uint32_t* w) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]),
+          "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]),
+          "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* w) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
@@ -184,8 +193,8 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     uint8_t* raw_ring = act_ring + Cfg::ACT_BYTES;                            // [raw_stages][raw_stride]  TMA (HBM)    -> unpack warps
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (QG_SMEM - 1024 - Cfg::BAR_BYTES));
     uint64_t* raw_full = bars;                               // [8]  producer (tx bytes)                     -> unpack warps
-    uint64_t* raw_empty = raw_full + QG_MAX_RAW_STAGES;      // [8]  16 unpack warps                         -> producer
-    uint64_t* unit_full = raw_empty + QG_MAX_RAW_STAGES;     // [2]  16 unpack warps + activations (tx bytes) -> MMA issuer
+    uint64_t* raw_empty = raw_full + QG_MAX_RAW_STAGES;      // [8]  8 unpack warps (one group)             -> producer
+    uint64_t* unit_full = raw_empty + QG_MAX_RAW_STAGES;     // [2]  8 unpack warps + activations (tx bytes)  -> MMA issuer
     uint64_t* unit_empty = unit_full + QG_A_UNITS;           // [2]  commit                                  -> unpack warps, activation producer
     uint64_t* acc_full = unit_empty + QG_A_UNITS;            // [2]  commit                                  -> epilogue
     uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps                        -> MMA issuer
@@ -201,8 +210,8 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
 
     if (warp == 2 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < QG_MAX_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], QG_N_UNPACK); }
-        for (int i = 0; i < QG_A_UNITS; ++i) { mbar_init(&unit_full[i], QG_N_UNPACK + 1); mbar_init(&unit_empty[i], 1); }
+        for (int i = 0; i < QG_MAX_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], QG_N_UNPACK / 2); }
+        for (int i = 0; i < QG_A_UNITS; ++i) { mbar_init(&unit_full[i], QG_N_UNPACK / 2 + 1); mbar_init(&unit_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_mbar_init();
     }
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             const uint32_t tmem_d = tb + (uint32_t)(buf * NB);
             for (int j = 0; j < n_kb; ++j, ++u) {
                 const int i = u - u0, sa = i & 1;
-                mbar_wait(&unit_full[sa], (uint32_t)(i >> 1) & 1u);   // A operand in TMEM (16 unpack warps) and activation boxes (TMA) are there
+                mbar_wait(&unit_full[sa], (uint32_t)(i >> 1) & 1u);   // A operand in TMEM (one unpack group) and activation boxes (TMA) are there
                 q_fence_after();
                 const uint32_t ta = tb + (uint32_t)(QG_A_COL0 + sa * 128);
                 const uint64_t bdesc = q_desc_sw128(act_u32 + (uint32_t)(sa * 4 * Cfg::B_TILE));
@@ -294,29 +303,42 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             }
         }
     } else if (warp >= QG_W_UNPACK0 && warp < QG_W_EPI0) {
-        // ===== unpack warps: thread (row r, K-step kk); the warp's TMEM lane quarter (warp % 4) is r / 32 =====
-        const int t = (warp - QG_W_UNPACK0) * 32 + lane, r = t & 127, kk = t >> 7;
-        const uint32_t ta0 = tmem_base + ((uint32_t)(r & ~31) << 16) + (uint32_t)(QG_A_COL0 + kk * 32);
-        int tile = u0 / nkb, kb = u0 - tile * nkb, s = 0;
-        uint32_t ph = 0;
-        int type = q_tile_type(p, tile);
-        for (int u = u0; u < u1; ++u) {
-            const int i = u - u0;
+        // ===== unpack warps: two groups of eight; group g owns the qtiles i = g (mod 2) of the CTA's range and slot g of the
+        // operand ring.  Thread (row r, half h) of a group turns 128 columns of its row into two K-steps (2 x 32 registers, two
+        // tcgen05.st).  Two qtiles are therefore in flight at once, and a warp pays the fixed latencies of an iteration (barrier
+        // polls, tcgen05.wait::st, arrive -> MMA -> commit round trip) once per 128 columns: with all sixteen warps on the SAME
+        // qtile the kernel ran at one warp-iteration (~0.9 us) per qtile whatever the arithmetic (Q4_K and Q6_K alike, run I).
+        // The warp's TMEM lane quarter (warp % 4) is r / 32.
+        const int t = (warp - QG_W_UNPACK0) * 32 + lane, grp = t >> 8, r = t & 127, h = (t >> 7) & 1;
+        const uint32_t ta0 = tmem_base + ((uint32_t)(r & ~31) << 16) + (uint32_t)(QG_A_COL0 + grp * 128 + h * 64);
+        int tile = (u0 + grp) / nkb, kb = (u0 + grp) - tile * nkb, s = grp % R;
+        uint32_t ph = (uint32_t)(grp / R) & 1u, n = 0;
+        int type = q_tile_type(p, min(tile, p.n_tiles - 1));
+        for (int u = u0 + grp; u < u1; u += 2, ++n) {
             const uint8_t* raw = raw_ring + (size_t)s * p.raw_stride;
             mbar_wait(&raw_full[s], ph);
             uint32_t w[32];
-            qg_dequant_kstep(type, raw, r, kk, [&](int c, QgU4 v) { w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w; });
+            qg_dequant_kstep(type, raw, r, 2 * h, [&](int c, QgU4 v) { w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w; });
+            // the first 32 words sit in registers: only now does the thread need its TMEM slot (the MMAs of this group's previous
+            // qtile are done)
+            mbar_wait(&unit_empty[grp], (n & 1u) ^ 1u);
+            q_fence_after();
+            tmem_st_32x32_nowait(ta0, w);
+            qg_dequant_kstep(type, raw, r, 2 * h + 1, [&](int c, QgU4 v) { w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w; });
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[s]);                // this warp has read all it needs of the raw bytes
-            // the 32 words sit in registers: only now does the thread need the TMEM slot (the MMAs of two qtiles ago are done)
-            mbar_wait(&unit_empty[i & 1], ((uint32_t)(i >> 1) & 1u) ^ 1u);
-            q_fence_after();
-            tmem_st_32x32(ta0 + (uint32_t)((i & 1) * 128), w);
+            tmem_st_32x32_nowait(ta0 + 32, w);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             q_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&unit_full[i & 1]);
-            if (++s == R) { s = 0; ph ^= 1u; }
-            if (++kb == nkb) { kb = 0; ++tile; if (u + 1 < u1) type = q_tile_type(p, tile); }
+            if (lane == 0) mbar_arrive(&unit_full[grp]);
+            s += 2;
+            if (s >= R) { s -= R; ph ^= 1u; }
+            kb += 2;
+            if (kb >= nkb) {
+                do { kb -= nkb; ++tile; } while (kb >= nkb);
+                if (u + 2 < u1) type = q_tile_type(p, tile);
+            }
         }
     } else if (warp >= QG_W_EPI0) {
         // ===== epilogue warps =====
