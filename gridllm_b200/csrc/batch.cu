@@ -272,9 +272,18 @@ __global__ void __launch_bounds__(128, 2) batch_attn_mma_kernel(const __grid_con
     for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
     float m_run = -INFINITY, l_run = 0.f;
 
+    // physical pages of this warp's pages, 32 at a time: lane l holds the entry of page j0 + l.  Looked up inside issue() the
+    // entry was a dependent global load in front of every page's copies (a third of the kernel's stall samples, r02 run J).
+    int tbl = 0;
+    auto load_tbl = [&](int j0) {
+        const int j = j0 + lane;
+        tbl = j < w_pages ? table[split + (warp + 4 * j) * S] : 0;
+    };
+    load_tbl(0);
     auto issue = [&](int j) {          // page j of this warp -> buffer j % NBUF (K then V), 16-byte chunks swizzled by the row
-        const int pg = split + (warp + 4 * j) * S;
-        const size_t off = ((size_t)table[pg] * p.n_kv_heads + kvh) * (size_t)(KV_PAGE_TOKENS * HD);
+        if ((j & 31) == 0 && j > 0) load_tbl(j);
+        const int phys = __shfl_sync(0xffffffffu, tbl, j & 31);
+        const size_t off = ((size_t)phys * p.n_kv_heads + kvh) * (size_t)(KV_PAGE_TOKENS * HD);
         const uint8_t* ksrc = reinterpret_cast<const uint8_t*>(p.k_cache + off);
         const uint8_t* vsrc = reinterpret_cast<const uint8_t*>(p.v_cache + off);
         const uint32_t kdst = smem_u32(wbuf + (size_t)(j % Cfg::NBUF) * 2 * Cfg::PAGE_BYTES), vdst = kdst + Cfg::PAGE_BYTES;

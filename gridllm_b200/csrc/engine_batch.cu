@@ -71,7 +71,7 @@ Status Engine::pack_qgemm(const std::vector<const GGUFTensor*>& src, int mode, Q
     std::vector<uint64_t> toff(out.n_tiles);
     std::vector<uint8_t> ttype(out.n_tiles);
     CU(qgemm_pack_launch(qs, (int)src.size(), mode, k, out.w, toff.data(), ttype.data(), stream_));
-    CU(cudaMalloc((void**)&out.tile_off, (size_t)out.n_tiles * 8));
+    CU(cudaMalloc((void**)&out.tile_off, (size_t)out.n_tiles * 4));
     allocs_.push_back(out.tile_off);
     CU(cudaMalloc((void**)&out.tile_type, (size_t)out.n_tiles + 16));
     allocs_.push_back(out.tile_type);

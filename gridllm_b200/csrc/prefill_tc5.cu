@@ -62,6 +62,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 }
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool tc5_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc5_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -217,34 +222,41 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            // instruction descriptor: D = F32, A / B = F16 or BF16, both K-major, N = 128, M = 128
-            const uint32_t fmt = p.bf16 ? 1u : 0u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            int st = 0;
-            uint32_t ph = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&acc_empty[buf], aph ^ 1u);      // the epilogue has drained this half (free on its first use)
+        // ===== MMA issuer =====
+        // The whole warp walks the loop with warp-uniform values and ONE ELECTED lane issues: inside `if (lane == 0)` the
+        // compiler cannot keep descriptors and addresses in uniform registers and wraps every tcgen05 instruction in a
+        // convert-to-uniform loop (ELECT / R2UR / UTCHMMA / BRA.U.ANY); written this way an MMA is two uniform adds and the
+        // instruction (found on the batched decode GEMM, where the issuer's own instruction stream set the pace: qgemm.cu).
+        // instruction descriptor: D = F32, A / B = F16 or BF16, both K-major, N = BN, M = 128
+        const uint32_t fmt = p.bf16 ? 1u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+        int st = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&acc_empty[buf], aph ^ 1u);      // the epilogue has drained this half (free on its first use)
+            tc5_fence_after();
+            const uint32_t tmem_d = tb + (uint32_t)(buf * BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&full[st], ph);
                 tc5_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(&full[st], ph);
-                    tc5_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
+                const uint32_t sa = smem0 + (uint32_t)(st * STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
+                if (tc5_elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advancing K inside the swizzle atom: +32 bytes = +2 in the descriptor's 16-byte address units
-                        tc5_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        tc5_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : (kb ? 1u : 0u));
                     }
                     tc5_commit(&empty[st]);                       // the stage is free once these MMAs have read it
                     if (kb == nk - 1) tc5_commit(&acc_full[buf]); // ... and the accumulator is complete
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
         }
     } else {

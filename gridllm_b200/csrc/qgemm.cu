@@ -24,10 +24,11 @@
 //   warp 1 / one lane : MMA issuer -- per K-step four tcgen05.mma.cta_group::1.kind::f16 with A FROM TMEM and B = the activation
 //                       box in shared memory (M 128 = weight rows, N = B, K 16), accumulator [128 lanes x B columns] fp32 in
 //                       TMEM, double-buffered across output tiles; tcgen05.commit hands K-step slots / boxes / accumulators on;
-//   warps 20..23      : epilogue -- tcgen05.ld 16 batch columns at a time, then either the fused epilogue (fp32 store, residual
-//                       add, SiLU*mul -> fp16) or, for an output tile whose K range is shared with neighbouring CTAs, a partial to
-//                       scratch + atomic ticket; the last contributor adds the partials IN CTA ORDER (deterministic) and runs
-//                       the epilogue.
+//   warps 20..23      : epilogue -- tcgen05.ld 16 batch columns at a time, then the fused epilogue (fp32 store, residual add,
+//                       SiLU*mul -> fp16).  An output tile whose K range is shared with neighbouring CTAs is finished by the
+//                       lowest-numbered of them (its part of the tile is the END of its range, the others' the START of theirs):
+//                       the others store their partial to scratch and count themselves in, the finisher adds the partials IN
+//                       CTA ORDER (deterministic) to its accumulator and runs the epilogue.
 // SASS to look for: UTCHMMA (tcgen05.mma), STTM (tcgen05.st), LDTM (tcgen05.ld), UBLKCP (1-D bulk copy), UTMALDG (2-D TMA),
 // UTCBAR (commit).
 #include <cuda.h>
@@ -65,13 +66,18 @@ struct QParams {
     const uint64_t* tile_off;    // per-tile tables: only when the GEMM's tiles are not "type0 up to tile_split, then type1"
     const uint8_t* tile_type;
     unsigned* counters;
-    float* partial;              // [grid][2][NB * 128]
+    float* partial;              // [grid][NB * 128]: a CTA's part of the tile it shares with lower-numbered CTAs
     void* c;
     int ldc, epi, n, n_tiles, nkb;
     int type0, type1, tile_split;          // tiles [0, tile_split) are type0, the rest type1 (Q | K | V with a Q6_K V); tile_split = n_tiles when uniform
     unsigned long long off_split;          // byte offset of tile tile_split
     int raw_stride, raw_stages;            // raw ring geometry: stride = the largest qtile of this GEMM (18 432 or 27 648)
+    unsigned long long* trace;             // GL_QGEMM_TRACE=1: [grid][QG_TRACE_SLOTS] %globaltimer stamps of this launch (tools/qgemm_trace.py); else null
 };
+constexpr int QG_TRACE_SLOTS = 10, QG_TRACE_LAUNCHES = 1024;
+__device__ __forceinline__ void q_stamp(const QParams& p, int slot) {
+    if (p.trace) p.trace[(size_t)blockIdx.x * QG_TRACE_SLOTS + slot] = globaltimer_ns();
+}
 
 __device__ __forceinline__ void tma_load_2d_q(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
@@ -199,11 +205,11 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     uint64_t* acc_full = unit_empty + QG_A_UNITS;            // [2]  commit                                  -> epilogue
     uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps                        -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    int* flag = reinterpret_cast<int*>(tmem_slot + 1);                        // "this CTA finishes the shared tile"
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     const int nkb = p.nkb;
+    if (threadIdx.x == 0) q_stamp(p, 0);                                      // CTA entry
     const int U = p.n_tiles * nkb;                                            // < 2^31 / 148 for every matrix of these models
     const int u0 = (int)q_range_start(cta, U, G), u1 = (int)q_range_start(cta + 1, U, G);
     const int R = p.raw_stages;
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     __syncthreads();
     q_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) q_stamp(p, 1);                                      // barriers, tensor memory ready
 
     // Programmatic dependent launch: everything up to here, the weight stream and the unpacking of the first two qtiles need
     // nothing from the kernel before -- only the activations (read) and C / the split-tile scratch (written) do.
@@ -238,6 +245,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                 mbar_wait(&raw_empty[s], ph ^ 1u);
                 mbar_expect_tx(&raw_full[s], qb);
                 tma_load_1d(raw_ring + (size_t)s * p.raw_stride, src, qb, &raw_full[s]);
+                if (u == u0) q_stamp(p, 2);                                   // first weight copy issued
                 src += qb;
                 if (++s == R) { s = 0; ph ^= 1u; }
                 if (++kb == nkb) {                                            // next output tile: its type may differ (Q | K | V)
@@ -255,6 +263,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             // ===== activation producer: the four [NB x 64] boxes of a qtile's K range (L2-resident), two qtiles deep =====
             int kb = u0 % nkb;
             pdl_wait();                                               // the activations are the output of the kernel before
+            q_stamp(p, 8);                                                    // the kernel before has completed
             for (int u = u0; u < u1; ++u) {
                 const int i = u - u0, s = i & 1;
                 uint8_t* st = act_ring + (size_t)s * 4 * Cfg::B_TILE;
@@ -302,6 +311,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                 __syncwarp();
             }
         }
+        if (lane == 0) q_stamp(p, 9);                                         // last MMA issued
     } else if (warp >= QG_W_UNPACK0 && warp < QG_W_EPI0) {
         // ===== unpack warps: two groups of eight; group g owns the qtiles i = g (mod 2) of the CTA's range and slot g of the
         // operand ring.  Thread (row r, half h) of a group turns 128 columns of its row into two K-steps (2 x 32 registers, two
@@ -317,6 +327,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         for (int u = u0 + grp; u < u1; u += 2, ++n) {
             const uint8_t* raw = raw_ring + (size_t)s * p.raw_stride;
             mbar_wait(&raw_full[s], ph);
+            if (n == 0 && t == 0) q_stamp(p, 3);                              // first qtile has landed
             uint32_t w[32];
             qg_dequant_kstep(type, raw, r, 2 * h, [&](int c, QgU4 v) { w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w; });
             // the first 32 words sit in registers: only now does the thread need its TMEM slot (the MMAs of this group's previous
@@ -340,6 +351,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                 if (u + 2 < u1) type = q_tile_type(p, tile);
             }
         }
+        if ((t & 255) == 0) q_stamp(p, 4 + grp);                              // this group has unpacked its last qtile
     } else if (warp >= QG_W_EPI0) {
         // ===== epilogue warps =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
@@ -354,12 +366,49 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             const int buf = seg & 1;
             const int n = tile * QG_ROWS + nl;
             const bool whole = n_kb == nkb;                           // the whole K range of this tile is ours
-            // shared tile: partial -> scratch, ticket; the last contributor sums the partials in CTA order
+            // Shared tile.  Its FIRST units are the END of CTA c_first's range, its later units the START of the ranges of
+            // c_first + 1 .. c_last: those CTAs store their part to scratch and count themselves in; c_first gets there last (or
+            // together with the CTAs whose whole range lies inside the tile), so it is the designated finisher -- it keeps its own
+            // part in tensor memory, adds the others' (CTA order: deterministic) and runs the epilogue.  It polls the counter and
+            // fetches the partials while its own MMAs are still running.  (All CTAs of the grid are resident -- one per SM -- and
+            // nobody waits for a lower-numbered CTA, so the wait cannot deadlock.)  Two alternatives were measured and dropped:
+            // "last to arrive finishes" (ticket; the finisher then starts the exchange only after its own part: +4 us per launch,
+            // run L) and "all K contributors finish a slice each" (two shared tiles per CTA, each a chain of five global round trips
+            // at the very end: +6 us, run N).
             const int t0 = tile * nkb;
             const int c_first = whole ? cta : q_owner_of(t0, U, G), c_last = whole ? cta : q_owner_of(t0 + nkb - 1, U, G);
-            float* mine = p.partial + ((size_t)cta * 2 + (cta == c_first ? 1 : 0)) * (NB * QG_ROWS) + nl;
+            const bool finisher = !whole && cta == c_first;
+            float* mine = p.partial + (size_t)cta * (NB * QG_ROWS) + nl;
+            constexpr bool PRE = NB <= 32;                            // the others' sum fits the registers beside the accumulator chunk
+            float ps[PRE ? NB : 1];
+            if (finisher) {
+                if (warp == QG_W_EPI0 && lane == 0) {
+                    const unsigned need = (unsigned)(c_last - c_first);
+                    unsigned got;
+                    while (true) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(p.counters + tile) : "memory");
+                        if (got >= need) break;
+                        __nanosleep(32);
+                    }
+                    p.counters[tile] = 0;                             // ready for the next launch (everybody has counted in)
+                }
+                named_bar_sync(1, 128);
+                if (PRE) {
+#pragma unroll
+                    for (int b = 0; b < (PRE ? NB : 1); ++b) ps[b] = 0.f;
+                    for (int c = c_first + 1; c <= c_last; ++c) {
+                        const float* pc = p.partial + (size_t)c * (NB * QG_ROWS) + nl;
+                        float tv[PRE ? NB : 1];
+#pragma unroll
+                        for (int b = 0; b < (PRE ? NB : 1); ++b) tv[b] = __ldcg(pc + b * QG_ROWS);
+#pragma unroll
+                        for (int b = 0; b < (PRE ? NB : 1); ++b) ps[b] += tv[b];
+                    }
+                }
+            }
             mbar_wait(&acc_full[buf], (uint32_t)(seg >> 1) & 1u);
             q_fence_after();
+            if (u >= u1 && warp == QG_W_EPI0 && lane == 0) q_stamp(p, 6);     // last accumulator complete
 #pragma unroll
             for (int c = 0; c < NB / 16; ++c) {
                 float v[16];
@@ -370,49 +419,32 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);      // the accumulator has been read: the tile after next may start
                 }
                 if (whole) q_epilogue16(p, n, lane, c * 16, v);
-                else {
+                else if (finisher) {
+                    if (PRE) {
+#pragma unroll
+                        for (int b = 0; b < 16; ++b) v[b] += ps[PRE ? c * 16 + b : 0];
+                    } else {
+                        for (int cc = c_first + 1; cc <= c_last; ++cc) {
+                            const float* pc = p.partial + (size_t)cc * (NB * QG_ROWS) + (size_t)(c * 16) * QG_ROWS + nl;
+                            float tv[16];
+#pragma unroll
+                            for (int b = 0; b < 16; ++b) tv[b] = __ldcg(pc + b * QG_ROWS);
+#pragma unroll
+                            for (int b = 0; b < 16; ++b) v[b] += tv[b];
+                        }
+                    }
+                    q_epilogue16(p, n, lane, c * 16, v);
+                } else {
 #pragma unroll
                     for (int b = 0; b < 16; ++b) mine[(c * 16 + b) * QG_ROWS] = v[b];
                 }
             }
-            if (whole) continue;
+            if (whole || finisher) continue;
             __threadfence();
             named_bar_sync(1, 128);
-            if (warp == QG_W_EPI0 && lane == 0) {
-                unsigned ticket;
-                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.counters + tile) : "memory");
-                const int last = ticket == (unsigned)(c_last - c_first);
-                if (last) p.counters[tile] = 0;                       // ready for the next launch
-                *flag = last;
-            }
-            named_bar_sync(1, 128);
-            const int finish = *flag;
-            named_bar_sync(1, 128);                                   // everyone has read the flag before the next shared tile rewrites it
-            if (!finish) continue;
-            // sum in CTA order (deterministic); sixteen batch columns at a time, two contributors per round trip
-#pragma unroll 1
-            for (int b0 = 0; b0 < NB; b0 += 16) {
-                float v[16];
-#pragma unroll
-                for (int b = 0; b < 16; ++b) v[b] = 0.f;
-                int c = c_first;
-                for (; c + 1 <= c_last; c += 2) {
-                    const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + (size_t)b0 * QG_ROWS + nl;
-                    const float* pb = p.partial + ((size_t)(c + 1) * 2) * (NB * QG_ROWS) + (size_t)b0 * QG_ROWS + nl;
-                    float ta[16], tb2[16];
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) { ta[b] = __ldcg(pa + b * QG_ROWS); tb2[b] = __ldcg(pb + b * QG_ROWS); }
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) v[b] = (v[b] + ta[b]) + tb2[b];
-                }
-                if (c <= c_last) {
-                    const float* pa = p.partial + ((size_t)c * 2 + (c == c_first ? 1 : 0)) * (NB * QG_ROWS) + (size_t)b0 * QG_ROWS + nl;
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) v[b] += __ldcg(pa + b * QG_ROWS);
-                }
-                q_epilogue16(p, n, lane, b0, v);
-            }
+            if (warp == QG_W_EPI0 && lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
         }
+        if (warp == QG_W_EPI0 && lane == 0) q_stamp(p, 7);                    // epilogue done
     }
     q_fence_before();
     __syncthreads();
@@ -474,6 +506,23 @@ cudaError_t launch_nb(QParams& qp, int grid, cudaStream_t s) {
 }
 
 }  // namespace
+
+// ---- GL_QGEMM_TRACE=1: per-launch, per-CTA %globaltimer stamps (profiling aid; tools/qgemm_trace.py reads them back) ----
+namespace {
+unsigned long long* g_trace = nullptr;
+int g_trace_launch = 0;
+bool trace_on() {
+    static const bool on = []() { const char* e = getenv("GL_QGEMM_TRACE"); return e && e[0] == '1'; }();
+    return on;
+}
+}  // namespace
+extern "C" int gl_dbg_qgemm_trace(unsigned long long* out, int max_launches, int reset) {
+    const int n = std::min(std::min(g_trace_launch, QG_TRACE_LAUNCHES), max_launches);
+    if (out && g_trace && n > 0) cudaMemcpy(out, g_trace, (size_t)n * QGEMM_MAX_GRID * QG_TRACE_SLOTS * 8, cudaMemcpyDeviceToHost);
+    const int total = g_trace_launch;
+    if (reset) { g_trace_launch = 0; if (g_trace) cudaMemset(g_trace, 0, (size_t)QG_TRACE_LAUNCHES * QGEMM_MAX_GRID * QG_TRACE_SLOTS * 8); }
+    return std::min(total, QG_TRACE_LAUNCHES);
+}
 
 size_t qgemm_partial_floats(int nb) { return (size_t)QGEMM_MAX_GRID * 2 * nb * QG_ROWS; }
 bool qgemm_batch_ok(int nb) { return nb == 16 || nb == 32 || nb == 64; }
@@ -548,6 +597,14 @@ cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows
     qp.c = c; qp.ldc = ldc; qp.epi = epi; qp.n = wt.n; qp.n_tiles = wt.n_tiles; qp.nkb = wt.nkb;
     const long long U = (long long)wt.n_tiles * wt.nkb;
     const int grid = (int)std::min<long long>(std::min(n_sm, QGEMM_MAX_GRID), U);
+    if (trace_on()) {       // NOTE: a captured graph keeps the slot of the capture: trace with plain launches (gl_time_batch_step's warm pass)
+        if (!g_trace) {
+            if (cudaMalloc((void**)&g_trace, (size_t)QG_TRACE_LAUNCHES * QGEMM_MAX_GRID * QG_TRACE_SLOTS * 8) != cudaSuccess) return cudaErrorMemoryAllocation;
+            cudaMemset(g_trace, 0, (size_t)QG_TRACE_LAUNCHES * QGEMM_MAX_GRID * QG_TRACE_SLOTS * 8);
+        }
+        if (g_trace_launch < QG_TRACE_LAUNCHES) qp.trace = g_trace + (size_t)g_trace_launch * QGEMM_MAX_GRID * QG_TRACE_SLOTS;
+        ++g_trace_launch;
+    }
     if (nb == 16) return launch_nb<16>(qp, grid, s);
     if (nb == 32) return launch_nb<32>(qp, grid, s);
     return launch_nb<64>(qp, grid, s);

@@ -14,7 +14,7 @@ struct QGemmWeights {
     uint8_t* w = nullptr;             // qtile stream
     uint64_t* tile_off = nullptr;     // device [n_tiles]: byte offset of a tile's first qtile
     uint8_t* tile_type = nullptr;     // device [n_tiles]: ggml type of the tile's rows (12 Q4_K / 14 Q6_K)
-    unsigned* counters = nullptr;     // device [n_tiles]: split-tile tickets, zero between launches
+    unsigned* counters = nullptr;     // device [n_tiles]: parts of a split tile stored so far, zero between launches
     int n = 0;                        // output features (rows of the matrix), multiple of 128
     int k = 0;                        // input features, multiple of 256
     int n_tiles = 0, nkb = 0;
