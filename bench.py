@@ -547,16 +547,19 @@ def run_config3(args, N, path, rank, local_rank, world, dist, timed, peaks, extr
         for w in workers:
             await w.stop()
         ok = sum(1 for j in jobs if "result" in sched.results.get(j["id"], {}))
+        errs = [str(sched.results.get(j["id"], {}).get("error")) for j in jobs if "result" not in sched.results.get(j["id"], {})]
         chunks = sum(sched.stream_chunks.get(j["id"], 0) for j in jobs)
         used = sorted(set(sched.assigned.values()))
         ttft = [sched.first_chunk_at[j["id"]] - sched.submitted_at[j["id"]] for j in jobs if j["id"] in sched.first_chunk_at]
         return {"wall": wall, "ok": ok, "chunks": chunks, "workers_used": used, "ticks": sched.ticks, "n": len(jobs),
-                "ttft_median_s": statistics.median(ttft) if ttft else None}
+                "ttft_median_s": statistics.median(ttft) if ttft else None, "first_error": errs[0] if errs else None}
 
     loop = asyncio.new_event_loop()
     for w in range(min(args.warmup, 1) + 0):                          # one warm pass captures the graphs of every bucket it meets
         r = loop.run_until_complete(run_step(1000 + w, 0.0))
         log(f"[bench] config3 warm pass: {r['ok']}/{r['n']} requests in {r['wall']:.2f} s, counters {engines[0].batch_counters()}")
+        if r["ok"] != r["n"]:            # fail NOW and loudly: a worker that answers every job with an error is not a slow worker
+            raise SystemExit(f"[bench] config3: {r['n'] - r['ok']} of {r['n']} warm-up requests failed: {r.get('first_error')}")
     for e in engines:
         e.batch_counters(reset=True)
 

@@ -253,20 +253,33 @@ __global__ void __launch_bounds__(128, 2) batch_attn_mma_kernel(const __grid_con
     uint8_t* wbuf = bam_smem + (size_t)warp * Cfg::WARP_BYTES;
 
     // Q fragments: rows = the group's query heads (g < grp), pre-scaled, fp16.  Rows 8..15 of the MMA tile stay zero.
+    // Fused mode: the raw q row is rotated here (a thread's two elements per k-step half are one adjacent RoPE pair).
+    const bool fused = p.qkv != nullptr;
+    const float* cs = fused ? p.cos_t + (size_t)(L - 1) * (HD / 2) : nullptr;
+    const float* sn = fused ? p.sin_t + (size_t)(L - 1) * (HD / 2) : nullptr;
     uint32_t qa[KSTEPS][2];
     {
-        const float* q = p.q + ((size_t)row * p.n_head + (size_t)kvh * grp + g) * HD;
+        const float* q = fused ? p.qkv + (size_t)row * p.ld_qkv + ((size_t)kvh * grp + g) * HD
+                               : p.q + ((size_t)row * p.n_head + (size_t)kvh * grp + g) * HD;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
             float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
             if (g < grp) {
                 lo = *reinterpret_cast<const float2*>(q + ks * 16 + 2 * t);
                 hi = *reinterpret_cast<const float2*>(q + ks * 16 + 8 + 2 * t);
+                if (fused) {
+                    const float c0 = cs[ks * 8 + t], s0 = sn[ks * 8 + t], c1 = cs[ks * 8 + 4 + t], s1 = sn[ks * 8 + 4 + t];
+                    lo = make_float2(lo.x * c0 - lo.y * s0, lo.x * s0 + lo.y * c0);
+                    hi = make_float2(hi.x * c1 - hi.y * s1, hi.x * s1 + hi.y * c1);
+                }
             }
             qa[ks][0] = bam_pack(lo.x * p.scale, lo.y * p.scale);
             qa[ks][1] = bam_pack(hi.x * p.scale, hi.y * p.scale);
         }
     }
+    // the newest position's K / V rows: who owns its page?
+    const int pg_new = (L - 1) / KV_PAGE_TOKENS, tok_new = (L - 1) % KV_PAGE_TOKENS;
+    const int j_new = (fused && pg_new % S == split && ((pg_new - split) / S) % 4 == warp) ? ((pg_new - split) / S) / 4 : -1;
     float o[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
@@ -308,6 +321,31 @@ __global__ void __launch_bounds__(128, 2) batch_attn_mma_kernel(const __grid_con
         const uint32_t kb = smem_u32(wbuf + (size_t)(j % Cfg::NBUF) * 2 * Cfg::PAGE_BYTES), vb = kb + Cfg::PAGE_BYTES;
         const int pg = split + (warp + 4 * j) * S;
         const int npos = min(KV_PAGE_TOKENS, L - pg * KV_PAGE_TOKENS);
+        if (j == j_new) {
+            // this page holds the position of THIS step: its K / V rows are still in the QKV buffer.  Lane l owns elements 4l..4l+3
+            // (two RoPE pairs) of both rows: rotate K, round to fp16, patch the copy in shared memory, and write the cache.
+            static_assert(HD == 128 || HD == 64, "lane -> 4 elements of the row");
+            if (lane * 4 < HD) {
+                const float* kr = p.qkv + (size_t)row * p.ld_qkv + (size_t)p.n_head * HD + (size_t)kvh * HD + lane * 4;
+                const float* vr = kr + (size_t)p.n_kv_heads * HD;
+                const float4 kx = *reinterpret_cast<const float4*>(kr), vx = *reinterpret_cast<const float4*>(vr);
+                const float c0 = cs[lane * 2], s0 = sn[lane * 2], c1 = cs[lane * 2 + 1], s1 = sn[lane * 2 + 1];
+                uint2 kw, vw;
+                kw.x = bam_pack(kx.x * c0 - kx.y * s0, kx.x * s0 + kx.y * c0);
+                kw.y = bam_pack(kx.z * c1 - kx.w * s1, kx.z * s1 + kx.w * c1);
+                vw.x = bam_pack(vx.x, vx.y);
+                vw.y = bam_pack(vx.z, vx.w);
+                const int chunk = lane >> 1;
+                const uint32_t d = (uint32_t)(tok_new * Cfg::ROW_BYTES + ((chunk ^ (tok_new & 7)) << 4) + (lane & 1) * 8);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(kb + d), "r"(kw.x), "r"(kw.y) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + d), "r"(vw.x), "r"(vw.y) : "memory");
+                const int phys_new = table[pg];
+                const size_t off = (((size_t)phys_new * p.n_kv_heads + kvh) * KV_PAGE_TOKENS + tok_new) * HD + lane * 4;
+                *reinterpret_cast<uint2*>(const_cast<__half*>(p.k_cache) + off) = kw;
+                *reinterpret_cast<uint2*>(const_cast<__half*>(p.v_cache) + off) = vw;
+            }
+            __syncwarp();
+        }
         // ---- S = Q K^T : two n-tiles (positions 0-7, 8-15) ----
         float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -568,11 +606,21 @@ cudaError_t batch_attn_configure() {
     return e;
 }
 
+static bool batch_attn_use_mma() {
+    static const bool on = []() { const char* e = getenv("GL_BATCH_ATTN_MMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+bool batch_attn_fuses_rope(int head_dim) {
+    static const bool on = []() { const char* e = getenv("GL_BATCH_FUSE_ROPE"); return !(e && e[0] == '0'); }();
+    return on && batch_attn_use_mma() && (head_dim == 128 || head_dim == 64);
+}
+
 cudaError_t batch_attn_launch(const BatchAttnParams& p, int bucket, cudaStream_t s) {
     const int grp = p.n_head / p.n_kv_heads;
     if (grp < 1 || grp > B_MAX_GRP || p.n_head % p.n_kv_heads || p.n_splits < 1 || p.n_splits > 32) return cudaErrorInvalidValue;
     const dim3 grid((unsigned)p.n_kv_heads, (unsigned)p.n_splits, (unsigned)bucket);
-    static const bool use_mma = []() { const char* e = getenv("GL_BATCH_ATTN_MMA"); return !(e && e[0] == '0'); }();
+    const bool use_mma = batch_attn_use_mma();
+    if (p.qkv != nullptr && !use_mma) return cudaErrorInvalidValue;          // only the tensor-core kernel rotates and appends
     if (use_mma) {       // tensor-core kernel (default); GL_BATCH_ATTN_MMA=0 keeps the scalar one for A/B runs
         if (p.head_dim == 128) return launch_dep(batch_attn_mma_kernel<128>, grid, dim3(128), (size_t)BamCfg<128>::SMEM, s, p);
         if (p.head_dim == 64) return launch_dep(batch_attn_mma_kernel<64>, grid, dim3(128), (size_t)BamCfg<64>::SMEM, s, p);

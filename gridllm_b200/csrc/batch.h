@@ -34,7 +34,14 @@ struct BatchOut {
 };
 
 struct BatchAttnParams {
-    const float* q;                      // [rows][n_head][head_dim] fp32, rotated
+    const float* q;                      // [rows][n_head][head_dim] fp32, rotated (null when the kernel rotates itself: qkv below)
+    // fused RoPE + KV append (tensor-core kernel only): the raw QKV rows of the step.  The CTA rotates its own query heads; the
+    // warp that owns the page of the newest position rotates that K row, converts the V row, patches its shared-memory copy of
+    // the page and writes both rows to the cache.  One kernel and one dependent launch less per layer.
+    const float* qkv;                    // [rows][ld_qkv] fp32: q | k | v, or null
+    int ld_qkv;
+    const float* cos_t;                  // [pos][head_dim / 2]
+    const float* sin_t;
     const __half* k_cache;               // layer base, [page][kv][16][hd]
     const __half* v_cache;
     const int* tables;                   // [MAX_BATCH slots][table_stride] logical -> physical page
@@ -58,6 +65,7 @@ cudaError_t batch_rope_kv_launch(const float* qkv, int bucket, const BatchCtl* c
                                  __half* v_cache, cudaStream_t s);
 cudaError_t batch_attn_configure();      // opt in to the tensor-core attention kernel's dynamic shared memory (once per device)
 cudaError_t batch_attn_launch(const BatchAttnParams& p, int bucket, cudaStream_t s);
+bool batch_attn_fuses_rope(int head_dim);    // tensor-core kernel in use (GL_BATCH_ATTN_MMA != 0) and GL_BATCH_FUSE_ROPE != 0
 // greedy rows (temperature 0): argmax + log-softmax of the winner over logits [bucket][n_vocab]; advances the row's StepState
 // and writes out_ids / out_lps [slot][max_out] exactly like the single-sequence sampler.  Rows with temperature > 0 are skipped
 // (the host launches the seeded top-k sampler on them).

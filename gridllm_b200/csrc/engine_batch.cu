@@ -71,7 +71,7 @@ Status Engine::pack_qgemm(const std::vector<const GGUFTensor*>& src, int mode, Q
     std::vector<uint64_t> toff(out.n_tiles);
     std::vector<uint8_t> ttype(out.n_tiles);
     CU(qgemm_pack_launch(qs, (int)src.size(), mode, k, out.w, toff.data(), ttype.data(), stream_));
-    CU(cudaMalloc((void**)&out.tile_off, (size_t)out.n_tiles * 4));
+    CU(cudaMalloc((void**)&out.tile_off, (size_t)out.n_tiles * 8));
     allocs_.push_back(out.tile_off);
     CU(cudaMalloc((void**)&out.tile_type, (size_t)out.n_tiles + 16));
     allocs_.push_back(out.tile_type);
@@ -500,15 +500,21 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
     CU(batch_gather_tokens_launch(bctl_, bst_, bids_, bucket, s)); ++nl;
     CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, bids_, bucket, bx_, s)); ++nl;
     const int splits = attn_splits_for(bucket, n_kv_, sm_count_);
+    const bool fuse_rope = batch_attn_fuses_rope(hd_);
     for (int il = 0; il < n_layer_; ++il) {
         const LayerWeights& L = layers_[il];
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         CU(batch_rmsnorm_launch(bx_, L.attn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
         CU(linear(bxn16_, L.wqkv16, bqkv_, ldq, n_embd_, ldq, GEMM_EPI_F32, use_q ? &qlayers_[il].qkv : nullptr));
-        CU(batch_rope_kv_launch(bqkv_, bucket, bctl_, bst_, btables_, n_pages_, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, bq_, kc, vc, s)); ++nl;
         BatchAttnParams a{};
-        a.q = bq_; a.k_cache = kc; a.v_cache = vc; a.tables = btables_; a.table_stride = n_pages_; a.st = bst_; a.ctl = bctl_;
+        if (fuse_rope) {        // the attention kernel rotates q itself and appends the step's K / V rows (batch.h)
+            a.q = nullptr; a.qkv = bqkv_; a.ld_qkv = ldq; a.cos_t = rope_cos_; a.sin_t = rope_sin_;
+        } else {
+            CU(batch_rope_kv_launch(bqkv_, bucket, bctl_, bst_, btables_, n_pages_, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, bq_, kc, vc, s)); ++nl;
+            a.q = bq_;
+        }
+        a.k_cache = kc; a.v_cache = vc; a.tables = btables_; a.table_stride = n_pages_; a.st = bst_; a.ctl = bctl_;
         a.out16 = battn16_; a.part_o = bpart_o_; a.part_ml = bpart_ml_; a.counters = bcounters_;
         a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = splits; a.scale = scale;
         CU(batch_attn_launch(a, bucket, s)); ++nl;
