@@ -56,6 +56,7 @@ template <int NB> struct QCfg {
     static constexpr int B_TILE = NB * 128;          // activations [NB rows x 64] fp16, 128-byte swizzle
     static constexpr int ACT_BYTES = QG_A_UNITS * 4 * B_TILE;
     static constexpr int BAR_BYTES = 512;
+    static constexpr int CK_BYTES = 2 * 4 * NB * 32 * 4;       // cluster mode: two rounds x four source ranks x [NB columns][32 rows] fp32
     static constexpr int RAW_BUDGET = (int)QG_SMEM - 1024 /* alignment */ - BAR_BYTES - ACT_BYTES;
 };
 constexpr int QG_MAX_RAW_STAGES = 8;
@@ -72,6 +73,7 @@ struct QParams {
     int type0, type1, tile_split;          // tiles [0, tile_split) are type0, the rest type1 (Q | K | V with a Q6_K V); tile_split = n_tiles when uniform
     unsigned long long off_split;          // byte offset of tile tile_split
     int raw_stride, raw_stages;            // raw ring geometry: stride = the largest qtile of this GEMM (18 432 or 27 648)
+    int ck_s;                              // 0: stream-K over the whole grid; 4: clusters of four CTAs share tiles, K split in quarters
     unsigned long long* trace;             // GL_QGEMM_TRACE=1: [grid][QG_TRACE_SLOTS] %globaltimer stamps of this launch (tools/qgemm_trace.py); else null
 };
 constexpr int QG_TRACE_SLOTS = 10, QG_TRACE_LAUNCHES = 1024;
@@ -190,13 +192,59 @@ __device__ __forceinline__ void q_epilogue16(const QParams& p, int n, int lane, 
     }
 }
 
+// ---- the CTA's sequence of qtiles ------------------------------------------------------------------------------------------------
+// stream-K   : a contiguous range of the GEMM's U = tiles x K-blocks units: (tile, kb) advances kb-first through whole tiles;
+// cluster    : (QParams::ck_s = 4) the four CTAs of a thread-block cluster share output tiles: rank r owns K-blocks
+//              [r nkb / 4, (r + 1) nkb / 4) of the tiles cluster, cluster + n_clusters, ... -- tile-aligned split-K, the partials
+//              meet in DISTRIBUTED SHARED MEMORY (below) instead of going through L2.
+struct QWalk {
+    int n;                       // units of this CTA
+    int tile0, kb0;              // first unit
+    int kb_begin, kb_end;        // K-block range of every segment after the first
+    int tile_step;
+    __device__ __forceinline__ void advance(int& tile, int& kb, int steps) const {
+        kb += steps;
+        while (kb >= kb_end) { kb -= kb_end - kb_begin; tile += tile_step; }
+    }
+};
+__device__ __forceinline__ uint32_t q_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t q_mapa(uint32_t local_smem_addr, uint32_t rank) {      // the same location in CTA `rank` of the cluster
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void q_st_cluster_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void q_arrive_cluster(uint32_t cluster_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+__device__ __forceinline__ void q_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();
+    }
+}
+constexpr int QG_CK = 4;                                       // cluster size of the tile-aligned split-K mode
+
 template <int NB>
 __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_constant__ QParams p) {
     using Cfg = QCfg<NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* act_ring = smem;                                                 // [2][4][NB x 64 fp16]      TMA (L2)     -> tensor core
-    uint8_t* raw_ring = act_ring + Cfg::ACT_BYTES;                            // [raw_stages][raw_stride]  TMA (HBM)    -> unpack warps
+    float* recv = reinterpret_cast<float*>(act_ring + Cfg::ACT_BYTES);        // cluster mode: [2 rounds][4 ranks][NB][32 rows] partial slices
+    uint8_t* raw_ring = act_ring + Cfg::ACT_BYTES + (p.ck_s ? Cfg::CK_BYTES : 0);   // [raw_stages][raw_stride]  TMA (HBM) -> unpack warps
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (QG_SMEM - 1024 - Cfg::BAR_BYTES));
     uint64_t* raw_full = bars;                               // [8]  producer (tx bytes)                     -> unpack warps
     uint64_t* raw_empty = raw_full + QG_MAX_RAW_STAGES;      // [8]  8 unpack warps (one group)             -> producer
@@ -204,21 +252,35 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     uint64_t* unit_empty = unit_full + QG_A_UNITS;           // [2]  commit                                  -> unpack warps, activation producer
     uint64_t* acc_full = unit_empty + QG_A_UNITS;            // [2]  commit                                  -> epilogue
     uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps                        -> MMA issuer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* recv_bar = acc_empty + 2;                      // [2]  cluster mode: 4 ranks' epilogue warps    -> this rank's epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     const int nkb = p.nkb;
     if (threadIdx.x == 0) q_stamp(p, 0);                                      // CTA entry
     const int U = p.n_tiles * nkb;                                            // < 2^31 / 148 for every matrix of these models
-    const int u0 = (int)q_range_start(cta, U, G), u1 = (int)q_range_start(cta + 1, U, G);
+    const bool ck = p.ck_s != 0;
+    const int rank = ck ? (int)q_cluster_rank() : 0, cluster = cta / QG_CK;
+    QWalk wk;
+    int u0 = 0;
+    if (!ck) {
+        u0 = (int)q_range_start(cta, U, G);
+        const int u1 = (int)q_range_start(cta + 1, U, G);
+        wk.n = u1 - u0; wk.tile0 = u0 / nkb; wk.kb0 = u0 - wk.tile0 * nkb; wk.kb_begin = 0; wk.kb_end = nkb; wk.tile_step = 1;
+    } else {
+        const int n_clusters = G / QG_CK;
+        const int rounds = cluster < p.n_tiles ? (p.n_tiles - cluster + n_clusters - 1) / n_clusters : 0;
+        wk.kb_begin = rank * nkb / QG_CK; wk.kb_end = (rank + 1) * nkb / QG_CK;
+        wk.n = rounds * (wk.kb_end - wk.kb_begin); wk.tile0 = cluster; wk.kb0 = wk.kb_begin; wk.tile_step = n_clusters;
+    }
     const int R = p.raw_stages;
 
     if (warp == 2 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tb) : "memory");
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < QG_MAX_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], QG_N_UNPACK / 2); }
         for (int i = 0; i < QG_A_UNITS; ++i) { mbar_init(&unit_full[i], QG_N_UNPACK / 2 + 1); mbar_init(&unit_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&recv_bar[i], QG_CK); }
         fence_mbar_init();
     }
     if (warp == 3) {
@@ -228,6 +290,10 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     q_fence_before();
     __syncthreads();
     q_fence_after();
+    if (ck) {       // nobody may arrive on a peer's barrier before that peer has initialised it
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) q_stamp(p, 1);                                      // barriers, tensor memory ready
 
@@ -237,41 +303,37 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             // ===== weight producer: one 1-D bulk copy per qtile, as far ahead as the raw ring is deep =====
-            int tile = u0 / nkb, kb = u0 - tile * nkb, s = 0;
-            uint32_t ph = 0;
-            uint32_t qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
-            const uint8_t* src = p.w + q_tile_off(p, tile) + (size_t)kb * qb;
-            for (int u = u0; u < u1; ++u) {
+            int tile = wk.tile0, kb = wk.kb0, s = 0, cur = -1;
+            uint32_t ph = 0, qb = 0;
+            const uint8_t* base = nullptr;
+            for (int i = 0; i < wk.n; ++i) {
+                if (tile != cur) {                                            // next output tile: its type may differ (Q | K | V)
+                    cur = tile;
+                    qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
+                    base = p.w + q_tile_off(p, tile);
+                }
                 mbar_wait(&raw_empty[s], ph ^ 1u);
                 mbar_expect_tx(&raw_full[s], qb);
-                tma_load_1d(raw_ring + (size_t)s * p.raw_stride, src, qb, &raw_full[s]);
-                if (u == u0) q_stamp(p, 2);                                   // first weight copy issued
-                src += qb;
+                tma_load_1d(raw_ring + (size_t)s * p.raw_stride, base + (size_t)kb * qb, qb, &raw_full[s]);
+                if (i == 0) q_stamp(p, 2);                                    // first weight copy issued
                 if (++s == R) { s = 0; ph ^= 1u; }
-                if (++kb == nkb) {                                            // next output tile: its type may differ (Q | K | V)
-                    kb = 0;
-                    ++tile;
-                    if (u + 1 < u1) {
-                        qb = (uint32_t)qg_qtile_bytes(q_tile_type(p, tile));
-                        src = p.w + q_tile_off(p, tile);
-                    }
-                }
+                wk.advance(tile, kb, 1);
             }
         }
     } else if (warp == 2) {
         if (lane == 0) {
             // ===== activation producer: the four [NB x 64] boxes of a qtile's K range (L2-resident), two qtiles deep =====
-            int kb = u0 % nkb;
+            int tile = wk.tile0, kb = wk.kb0;
             pdl_wait();                                               // the activations are the output of the kernel before
             q_stamp(p, 8);                                                    // the kernel before has completed
-            for (int u = u0; u < u1; ++u) {
-                const int i = u - u0, s = i & 1;
+            for (int i = 0; i < wk.n; ++i) {
+                const int s = i & 1;
                 uint8_t* st = act_ring + (size_t)s * 4 * Cfg::B_TILE;
                 mbar_wait(&unit_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(&unit_full[s], 4u * Cfg::B_TILE);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) tma_load_2d_q(st + kk * Cfg::B_TILE, &p.tb, kb * QG_COLS + kk * QG_KSTEP, 0, &unit_full[s]);
-                if (++kb == nkb) kb = 0;
+                wk.advance(tile, kb, 1);
             }
         }
     } else if (warp == 1) {
@@ -285,15 +347,15 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         const uint32_t idesc = (1u << 4) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t act_u32 = __shfl_sync(0xffffffffu, smem_u32(act_ring), 0);
-        int seg = 0, kb_lo = u0 % nkb;
-        for (int u = u0; u < u1; ++seg) {
-            const int n_kb = min(nkb - kb_lo, u1 - u);
-            kb_lo = 0;
+        int seg = 0, kb = wk.kb0;
+        for (int i = 0; i < wk.n; ++seg) {
+            const int n_kb = min(wk.kb_end - kb, wk.n - i);
+            kb = wk.kb_begin;
             const int buf = seg & 1;
             mbar_wait(&acc_empty[buf], ((uint32_t)(seg >> 1) & 1u) ^ 1u);
             const uint32_t tmem_d = tb + (uint32_t)(buf * NB);
-            for (int j = 0; j < n_kb; ++j, ++u) {
-                const int i = u - u0, sa = i & 1;
+            for (int j = 0; j < n_kb; ++j, ++i) {
+                const int sa = i & 1;
                 mbar_wait(&unit_full[sa], (uint32_t)(i >> 1) & 1u);   // A operand in TMEM (one unpack group) and activation boxes (TMA) are there
                 q_fence_after();
                 const uint32_t ta = tb + (uint32_t)(QG_A_COL0 + sa * 128);
@@ -313,18 +375,18 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         }
         if (lane == 0) q_stamp(p, 9);                                         // last MMA issued
     } else if (warp >= QG_W_UNPACK0 && warp < QG_W_EPI0) {
-        // ===== unpack warps: two groups of eight; group g owns the qtiles i = g (mod 2) of the CTA's range and slot g of the
+        // ===== unpack warps: two groups of eight; group g owns the qtiles i = g (mod 2) of the CTA's sequence and slot g of the
         // operand ring.  Thread (row r, half h) of a group turns 128 columns of its row into two K-steps (2 x 32 registers, two
         // tcgen05.st).  Two qtiles are therefore in flight at once, and a warp pays the fixed latencies of an iteration (barrier
-        // polls, tcgen05.wait::st, arrive -> MMA -> commit round trip) once per 128 columns: with all sixteen warps on the SAME
-        // qtile the kernel ran at one warp-iteration (~0.9 us) per qtile whatever the arithmetic (Q4_K and Q6_K alike, run I).
-        // The warp's TMEM lane quarter (warp % 4) is r / 32.
+        // polls, tcgen05.wait::st, arrive -> MMA -> commit round trip) once per 128 columns.  The warp's TMEM lane quarter
+        // (warp % 4) is r / 32.
         const int t = (warp - QG_W_UNPACK0) * 32 + lane, grp = t >> 8, r = t & 127, h = (t >> 7) & 1;
         const uint32_t ta0 = tmem_base + ((uint32_t)(r & ~31) << 16) + (uint32_t)(QG_A_COL0 + grp * 128 + h * 64);
-        int tile = (u0 + grp) / nkb, kb = (u0 + grp) - tile * nkb, s = grp % R;
+        int tile = wk.tile0, kb = wk.kb0, s = grp % R, cur = -1, type = 12;
+        if (grp) wk.advance(tile, kb, 1);
         uint32_t ph = (uint32_t)(grp / R) & 1u, n = 0;
-        int type = q_tile_type(p, min(tile, p.n_tiles - 1));
-        for (int u = u0 + grp; u < u1; u += 2, ++n) {
+        for (int i = grp; i < wk.n; i += 2, ++n) {
+            if (tile != cur) { cur = tile; type = q_tile_type(p, tile); }
             const uint8_t* raw = raw_ring + (size_t)s * p.raw_stride;
             mbar_wait(&raw_full[s], ph);
             if (n == 0 && t == 0) q_stamp(p, 3);                              // first qtile has landed
@@ -345,25 +407,64 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             if (lane == 0) mbar_arrive(&unit_full[grp]);
             s += 2;
             if (s >= R) { s -= R; ph ^= 1u; }
-            kb += 2;
-            if (kb >= nkb) {
-                do { kb -= nkb; ++tile; } while (kb >= nkb);
-                if (u + 2 < u1) type = q_tile_type(p, tile);
-            }
+            wk.advance(tile, kb, 2);
         }
         if ((t & 255) == 0) q_stamp(p, 4 + grp);                              // this group has unpacked its last qtile
     } else if (warp >= QG_W_EPI0) {
         // ===== epilogue warps =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int nl = q * 32 + lane;                                 // row inside the tile
-        int seg = 0;
-        int tile = u0 / nkb, kb_lo = u0 - tile * nkb;
+        int seg = 0, tile = wk.tile0, kb = wk.kb0;
         pdl_wait();                                                   // C, the scratch and the tickets may still be in use by the kernel before
-        for (int u = u0; u < u1; ++seg, ++tile) {
-            const int n_kb = min(nkb - kb_lo, u1 - u);
-            kb_lo = 0;
-            u += n_kb;
+        for (int i = 0; i < wk.n; ++seg, tile += wk.tile_step) {
+            const int n_kb = min(wk.kb_end - kb, wk.n - i);
+            kb = wk.kb_begin;
+            i += n_kb;
             const int buf = seg & 1;
+            if (ck) {
+                // ---- cluster mode: this CTA's accumulator is one K-quarter of the tile.  Warp q holds rows 32q..32q+31 of it: they
+                // belong to the slice rank q finishes, so the warp stores them straight into rank q's shared memory (slot = own rank)
+                // and counts itself in on rank q's barrier; then the four warps reduce the slice this rank owns (ranks in order:
+                // deterministic) and run the epilogue.  One DSMEM hop instead of store -> fence -> signal -> poll -> load through L2.
+                constexpr int SLOT = NB * 32;                          // floats of one source rank's slice: [NB columns][32 rows]
+                constexpr int CPT = NB / 4;                            // batch columns per thread in the reduction: warp q takes columns q CPT ..
+                const int par = seg & 1;
+                const int n = tile * QG_ROWS + rank * 32 + lane;       // the output feature this thread finishes
+                float old[CPT];
+                if (p.epi == GEMM_EPI_ADD_F32) {                       // the residual's old values: requested before anything is waited for
+#pragma unroll
+                    for (int b = 0; b < CPT; ++b) old[b] = n < p.n ? __ldcg(reinterpret_cast<const float*>(p.c) + (size_t)(q * CPT + b) * p.ldc + n) : 0.f;
+                }
+                mbar_wait(&acc_full[buf], (uint32_t)(seg >> 1) & 1u);
+                q_fence_after();
+                if (i >= wk.n && warp == QG_W_EPI0 && lane == 0) q_stamp(p, 6);
+                const uint32_t dst = q_mapa(smem_u32(recv + (size_t)(par * QG_CK + rank) * SLOT), (uint32_t)q) + (uint32_t)lane * 4u;
+#pragma unroll
+                for (int c = 0; c < NB / 16; ++c) {
+                    float v[16];
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NB + c * 16), v);
+                    if (c == NB / 16 - 1) {
+                        q_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) q_st_cluster_f32(dst + (uint32_t)((c * 16 + b) * 32 * 4), v[b]);
+                }
+                __syncwarp();
+                if (lane == 0) q_arrive_cluster(q_mapa(smem_u32(&recv_bar[par]), (uint32_t)q));
+                q_wait_cluster(&recv_bar[par], (uint32_t)(seg >> 1) & 1u);
+                const float* mine = recv + (size_t)par * QG_CK * SLOT + (size_t)(q * CPT) * 32 + lane;
+                float* out = reinterpret_cast<float*>(p.c) + (size_t)(q * CPT) * p.ldc + n;
+#pragma unroll
+                for (int b = 0; b < CPT; ++b) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int src = 0; src < QG_CK; ++src) v += mine[(size_t)src * SLOT + b * 32];
+                    if (n < p.n) out[(size_t)b * p.ldc] = p.epi == GEMM_EPI_ADD_F32 ? old[b] + v : v;
+                }
+                continue;
+            }
             const int n = tile * QG_ROWS + nl;
             const bool whole = n_kb == nkb;                           // the whole K range of this tile is ours
             // Shared tile.  Its FIRST units are the END of CTA c_first's range, its later units the START of the ranges of
@@ -408,7 +509,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
             }
             mbar_wait(&acc_full[buf], (uint32_t)(seg >> 1) & 1u);
             q_fence_after();
-            if (u >= u1 && warp == QG_W_EPI0 && lane == 0) q_stamp(p, 6);     // last accumulator complete
+            if (i >= wk.n && warp == QG_W_EPI0 && lane == 0) q_stamp(p, 6);   // last accumulator complete
 #pragma unroll
             for (int c = 0; c < NB / 16; ++c) {
                 float v[16];
@@ -488,20 +589,67 @@ EncodeTiledFnQ encode_fn_q() {
     return fn;
 }
 
+// clusters of four CTAs (227 KB of shared memory each) the device can keep resident at once, per kernel variant
 template <int NB>
-cudaError_t launch_nb(QParams& qp, int grid, cudaStream_t s) {
-    qp.raw_stages = std::min(QG_MAX_RAW_STAGES, QCfg<NB>::RAW_BUDGET / qp.raw_stride);
+int max_clusters_nb() {
+    static const int n = []() {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(QGEMM_MAX_GRID / QG_CK * QG_CK));
+        cfg.blockDim = dim3(QG_THREADS);
+        cfg.dynamicSmemBytes = QG_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = QG_CK; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int k = 0;
+        if (cudaOccupancyMaxActiveClusters(&k, qgemm_kernel<NB>, &cfg) != cudaSuccess) { cudaGetLastError(); k = 0; }
+        return k;
+    }();
+    return n;
+}
+bool cluster_mode_enabled() {
+    static const bool on = []() { const char* e = getenv("GL_QGEMM_CLUSTER"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <int NB>
+cudaError_t launch_nb(QParams& qp, int grid, int n_sm, cudaStream_t s) {
+    // Tile-aligned split-K inside clusters of four for the GEMMs whose tiles are FEW and DEEP (QKV,
+    // attn_output, ffn_down: 32-48 tiles of 16-56 K-blocks on 148 SMs).  Under stream-K every such tile is shared by 4-6 CTAs
+    // that all finish at the same moment, and the partial sums cross L2 on the critical path (7-10 us per launch, run M);
+    // a cluster exchanges them through distributed shared memory.  Everything else (gate/up, lm_head: hundreds of tiles, at
+    // most two CTAs per tile, the second one early) stays stream-K.
+    qp.ck_s = 0;
+    if (cluster_mode_enabled() && qp.epi != GEMM_EPI_SILU && qp.nkb >= QG_CK) {
+        const int cap = std::min(max_clusters_nb<NB>(), std::min(n_sm, QGEMM_MAX_GRID) / QG_CK);
+        const int n_clusters = std::min(cap, qp.n_tiles);
+        if (n_clusters > 0 && qp.n_tiles <= 2 * n_clusters) {           // the two receive buffers cover two rounds
+            qp.ck_s = QG_CK;
+            grid = n_clusters * QG_CK;
+        }
+    }
+    qp.raw_stages = std::min(QG_MAX_RAW_STAGES, (QCfg<NB>::RAW_BUDGET - (qp.ck_s ? QCfg<NB>::CK_BYTES : 0)) / qp.raw_stride);
     if (qp.raw_stages < 2) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(QG_THREADS);
     cfg.dynamicSmemBytes = QG_SMEM;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (batch_pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (qp.ck_s) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = QG_CK; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = batch_pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, qgemm_kernel<NB>, qp);
 }
 
@@ -605,9 +753,9 @@ cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows
         if (g_trace_launch < QG_TRACE_LAUNCHES) qp.trace = g_trace + (size_t)g_trace_launch * QGEMM_MAX_GRID * QG_TRACE_SLOTS;
         ++g_trace_launch;
     }
-    if (nb == 16) return launch_nb<16>(qp, grid, s);
-    if (nb == 32) return launch_nb<32>(qp, grid, s);
-    return launch_nb<64>(qp, grid, s);
+    if (nb == 16) return launch_nb<16>(qp, grid, n_sm, s);
+    if (nb == 32) return launch_nb<32>(qp, grid, n_sm, s);
+    return launch_nb<64>(qp, grid, n_sm, s);
 }
 
 }  // namespace gl
