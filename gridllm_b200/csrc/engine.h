@@ -212,6 +212,8 @@ private:
     StepState* bst_ = nullptr;                        // [MAX_BATCH]
     int* btables_ = nullptr;                          // [MAX_BATCH][n_pages_]
     int *bids_ = nullptr, *bout_ids_ = nullptr;
+    static constexpr int BSSQ_PARTS = 512;       // 32-row slices of the residual stream the folded RMSNorm can sum (n_embd <= 16 384)
+    float* bssq_[2] = {nullptr, nullptr};
     float *bx_ = nullptr, *bqkv_ = nullptr, *bq_ = nullptr, *blogits_ = nullptr, *bfirst_logits_ = nullptr, *bout_lp_ = nullptr, *bpart_o_ = nullptr, *bpart_ml_ = nullptr, *bsample_scratch_ = nullptr;
     __half *bxn16_ = nullptr, *battn16_ = nullptr, *bh16_ = nullptr;
     unsigned* bcounters_ = nullptr;

@@ -160,6 +160,7 @@ Status Engine::ensure_batch_state() {
     CU(dalloc((void**)&bpart_o_, R * n_head_ * 16 * hd_ * 4));
     CU(dalloc((void**)&bpart_ml_, R * n_head_ * 16 * 2 * 4));
     CU(dalloc((void**)&bcounters_, R * n_kv_ * 4));
+    for (int i = 0; i < 2; ++i) CU(dalloc((void**)&bssq_[i], (size_t)BSSQ_PARTS * 64 * 4));      // folded RMSNorm: per-slice sums of squares
     CU(dalloc((void**)&bsample_scratch_, R * BATCH_SAMPLE_ROW_FLOATS * 4));
     // the lm_head as a 16-bit matrix (the layer matrices already have their copy: build_prefill_weights)
     CU(dalloc(&head16_, (size_t)n_vocab_ * n_embd_ * 2));
@@ -486,16 +487,34 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
     // resident 16-bit copy otherwise (models with other tensor types, or 65..128 rows, where the step is tensor-bound anyway)
     const bool use_q = have_qg_ && bucket <= 64;
     const int nb = std::max(16, bucket);
-    auto linear = [&](const void* a, const void* w, void* c, int n, int k, int ldc, int epi, const QGemmWeights* qw) -> cudaError_t {
+    auto linear = [&](const void* a, const void* w, void* c, int n, int k, int ldc, int epi, const QGemmWeights* qw,
+                      const QGemmNorm* norm = nullptr) -> cudaError_t {
         if (use_q) {
             ++nl;
-            return qgemm_launch(*qw, (const __half*)a, MAX_BATCH, nb, c, ldc, epi, qpartial_, sm_count_, s);
+            return qgemm_launch(*qw, (const __half*)a, MAX_BATCH, nb, c, ldc, epi, qpartial_, sm_count_, s, norm);
         }
         GemmParams g{};
         g.a = a; g.b = w; g.c = c; g.m = bucket; g.n = n; g.k = k; g.lda = k; g.ldb = k; g.ldc = ldc;
         g.batch = 1; g.b_batch_div = 1; g.epi = epi;
         ++nl;
         return gemm_tc5_supported(g) ? gemm_tc5_launch(g, MAX_BATCH, false, s) : gemm_tn_launch(g, false, s);
+    };
+    // RMSNorm folded into the GEMMs around it (qgemm.h, QGemmNorm): the residual-add GEMMs write the next GEMM's activation rows
+    // (x * gamma / 16, fp16) and the per-slice sums of squares; the GEMM behind the norm scales its accumulator by 16 / rms.
+    // Only the first norm of the step (behind the embedding gather) is still a kernel.
+    static const bool fold_env = []() { const char* e = getenv("GL_BATCH_FOLD_NORM"); return !(e && e[0] == '0'); }();
+    const bool fold = use_q && fold_env && bssq_[0] != nullptr && qgemm_uses_cluster(qlayers_[0].o, nb, GEMM_EPI_ADD_F32, sm_count_) &&
+                      qgemm_uses_cluster(qlayers_[0].down, nb, GEMM_EPI_ADD_F32, sm_count_) && n_embd_ / 128 * 4 <= BSSQ_PARTS;
+    const int ssq_parts = n_embd_ / 128 * 4;
+    auto produce = [&](const float* gamma, float* ssq) {
+        QGemmNorm nm{};
+        nm.gamma_next = gamma; nm.xg_out = bxn16_; nm.ldxg = n_embd_; nm.ssq_out = ssq;
+        return nm;
+    };
+    auto consume = [&](const float* ssq) {
+        QGemmNorm nm{};
+        nm.ssq_in = ssq; nm.ssq_parts = ssq_parts; nm.n_norm = n_embd_; nm.eps = eps_;
+        return nm;
     };
     CU(batch_gather_tokens_launch(bctl_, bst_, bids_, bucket, s)); ++nl;
     CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, bids_, bucket, bx_, s)); ++nl;
@@ -505,8 +524,12 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
         const LayerWeights& L = layers_[il];
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
-        CU(batch_rmsnorm_launch(bx_, L.attn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
-        CU(linear(bxn16_, L.wqkv16, bqkv_, ldq, n_embd_, ldq, GEMM_EPI_F32, use_q ? &qlayers_[il].qkv : nullptr));
+        const bool folded_in = fold && il > 0;                           // this layer's attn_norm came out of the ffn_down GEMM before
+        if (!folded_in) { CU(batch_rmsnorm_launch(bx_, L.attn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl; }
+        {
+            const QGemmNorm nm = consume(bssq_[1]);
+            CU(linear(bxn16_, L.wqkv16, bqkv_, ldq, n_embd_, ldq, GEMM_EPI_F32, use_q ? &qlayers_[il].qkv : nullptr, folded_in ? &nm : nullptr));
+        }
         BatchAttnParams a{};
         if (fuse_rope) {        // the attention kernel rotates q itself and appends the step's K / V rows (batch.h)
             a.q = nullptr; a.qkv = bqkv_; a.ld_qkv = ldq; a.cos_t = rope_cos_; a.sin_t = rope_sin_;
@@ -518,13 +541,25 @@ Status Engine::enqueue_batch_step(cudaStream_t s, int bucket, int* n_launch) {
         a.out16 = battn16_; a.part_o = bpart_o_; a.part_ml = bpart_ml_; a.counters = bcounters_;
         a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = splits; a.scale = scale;
         CU(batch_attn_launch(a, bucket, s)); ++nl;
-        CU(linear(battn16_, L.wo16, bx_, n_embd_, qd, n_embd_, GEMM_EPI_ADD_F32, use_q ? &qlayers_[il].o : nullptr));
-        CU(batch_rmsnorm_launch(bx_, L.ffn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
-        CU(linear(bxn16_, L.wgu16, bh16_, 2 * n_ff_, n_embd_, n_ff_, GEMM_EPI_SILU, use_q ? &qlayers_[il].gu : nullptr));
-        CU(linear(bh16_, L.wd16, bx_, n_embd_, n_ff_, n_embd_, GEMM_EPI_ADD_F32, use_q ? &qlayers_[il].down : nullptr));
+        {
+            const QGemmNorm nm = produce(L.ffn_norm, bssq_[0]);
+            CU(linear(battn16_, L.wo16, bx_, n_embd_, qd, n_embd_, GEMM_EPI_ADD_F32, use_q ? &qlayers_[il].o : nullptr, fold ? &nm : nullptr));
+        }
+        if (!fold) { CU(batch_rmsnorm_launch(bx_, L.ffn_norm, bucket, n_embd_, eps_, bxn16_, s)); ++nl; }
+        {
+            const QGemmNorm nm = consume(bssq_[0]);
+            CU(linear(bxn16_, L.wgu16, bh16_, 2 * n_ff_, n_embd_, n_ff_, GEMM_EPI_SILU, use_q ? &qlayers_[il].gu : nullptr, fold ? &nm : nullptr));
+        }
+        {
+            const QGemmNorm nm = produce(il + 1 < n_layer_ ? layers_[il + 1].attn_norm : output_norm_, bssq_[1]);
+            CU(linear(bh16_, L.wd16, bx_, n_embd_, n_ff_, n_embd_, GEMM_EPI_ADD_F32, use_q ? &qlayers_[il].down : nullptr, fold ? &nm : nullptr));
+        }
     }
-    CU(batch_rmsnorm_launch(bx_, output_norm_, bucket, n_embd_, eps_, bxn16_, s)); ++nl;
-    CU(linear(bxn16_, head16_, blogits_, n_vocab_, n_embd_, n_vocab_, GEMM_EPI_F32, use_q ? &qhead_ : nullptr));
+    if (!fold) { CU(batch_rmsnorm_launch(bx_, output_norm_, bucket, n_embd_, eps_, bxn16_, s)); ++nl; }
+    {
+        const QGemmNorm nm = consume(bssq_[1]);
+        CU(linear(bxn16_, head16_, blogits_, n_vocab_, n_embd_, n_vocab_, GEMM_EPI_F32, use_q ? &qhead_ : nullptr, fold ? &nm : nullptr));
+    }
     CU(batch_sample_greedy_launch(blogits_, n_vocab_, bucket, bctl_, bst_, bout_ids_, bout_lp_, max_out_, bsample_scratch_, s)); ++nl;
     if (n_launch) *n_launch = nl;
     return {};

@@ -55,7 +55,7 @@ constexpr size_t QG_SMEM = 227 * 1024;               // the whole opt-in shared 
 template <int NB> struct QCfg {
     static constexpr int B_TILE = NB * 128;          // activations [NB rows x 64] fp16, 128-byte swizzle
     static constexpr int ACT_BYTES = QG_A_UNITS * 4 * B_TILE;
-    static constexpr int BAR_BYTES = 512;
+    static constexpr int BAR_BYTES = 1536;         // mbarriers, TMEM address, folded-RMSNorm scratch (64 + 128 floats)
     static constexpr int CK_BYTES = 2 * 4 * NB * 32 * 4;       // cluster mode: two rounds x four source ranks x [NB columns][32 rows] fp32
     static constexpr int RAW_BUDGET = (int)QG_SMEM - 1024 /* alignment */ - BAR_BYTES - ACT_BYTES;
 };
@@ -74,6 +74,14 @@ struct QParams {
     unsigned long long off_split;          // byte offset of tile tile_split
     int raw_stride, raw_stages;            // raw ring geometry: stride = the largest qtile of this GEMM (18 432 or 27 648)
     int ck_s;                              // 0: stream-K over the whole grid; 4: clusters of four CTAs share tiles, K split in quarters
+    // folded RMSNorm (qgemm.h, QGemmNorm)
+    const float* gamma_next;
+    __half* xg_out;
+    int ldxg;
+    float* ssq_out;
+    const float* ssq_in;
+    int ssq_parts, n_norm;
+    float eps;
     unsigned long long* trace;             // GL_QGEMM_TRACE=1: [grid][QG_TRACE_SLOTS] %globaltimer stamps of this launch (tools/qgemm_trace.py); else null
 };
 constexpr int QG_TRACE_SLOTS = 10, QG_TRACE_LAUNCHES = 1024;
@@ -160,7 +168,11 @@ __device__ __forceinline__ unsigned long long q_tile_off(const QParams& p, int t
 }
 
 // fused epilogue of 16 batch columns [b0, b0 + 16) of output feature n (v[i] = C[b0 + i][n])
-__device__ __forceinline__ void q_epilogue16(const QParams& p, int n, int lane, int b0, const float* v) {
+__device__ __forceinline__ void q_epilogue16(const QParams& p, int n, int lane, int b0, float* v, const float* inv) {
+    if (inv != nullptr) {                // folded RMSNorm: the activations carried x * gamma / 16, the token's 16 / rms comes here
+#pragma unroll
+        for (int b = 0; b < 16; ++b) v[b] *= inv[b0 + b];
+    }
     if (p.epi == GEMM_EPI_SILU) {
         // weight rows are interleaved [8 gate | 8 up] at load: lane l of a 16-lane group holds gate (l < 8) or up (l >= 8) of
         // hidden column (n / 16) * 8 + l % 8
@@ -254,6 +266,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
     uint64_t* acc_empty = acc_full + 2;                      // [2]  4 epilogue warps                        -> MMA issuer
     uint64_t* recv_bar = acc_empty + 2;                      // [2]  cluster mode: 4 ranks' epilogue warps    -> this rank's epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_bar + 2);
+    float* inv_s = reinterpret_cast<float*>(tmem_slot + 2);  // [64] folded RMSNorm: 16 / rms of every token of the step
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -416,6 +429,34 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
         const int nl = q * 32 + lane;                                 // row inside the tile
         int seg = 0, tile = wk.tile0, kb = wk.kb0;
         pdl_wait();                                                   // C, the scratch and the tickets may still be in use by the kernel before
+        const float* inv = nullptr;
+        if (p.ssq_in != nullptr) {
+            // folded RMSNorm, consumer side: token b's sum of squares = the parts the GEMM before wrote, added in part order by ONE
+            // thread per token (every CTA computes the same 64 numbers; the loads hit L2 and hide behind the first qtiles)
+            const int et = threadIdx.x - QG_W_EPI0 * 32;
+            constexpr int GROUPS = 128 / NB;                          // threads per token: each sums every GROUPS-th part
+            const int b = et % NB, g = et / NB;
+            float acc = 0.f;
+            for (int pt = g; pt < p.ssq_parts; pt += GROUPS * 8) {    // eight loads in flight per thread and round trip
+                float t8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t8[k] = pt + k * GROUPS < p.ssq_parts ? __ldcg(p.ssq_in + (size_t)(pt + k * GROUPS) * 64 + b) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += t8[k];
+            }
+            float* red = inv_s + 64;                                  // [GROUPS][NB] partial sums
+            red[g * NB + b] = acc;
+            named_bar_sync(1, 128);
+            if (et < NB) {
+                float ss = 0.f;
+#pragma unroll
+                for (int k = 0; k < GROUPS; ++k) ss += red[k * NB + et];
+                // the parts hold sums of x^2; the activations carried x * gamma * PRESCALE
+                inv_s[et] = rsqrtf(ss / (float)p.n_norm + p.eps) * (1.0f / QGEMM_NORM_PRESCALE);
+            }
+            named_bar_sync(1, 128);
+            inv = inv_s;
+        }
         for (int i = 0; i < wk.n; ++seg, tile += wk.tile_step) {
             const int n_kb = min(wk.kb_end - kb, wk.n - i);
             kb = wk.kb_begin;
@@ -430,6 +471,8 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                 constexpr int CPT = NB / 4;                            // batch columns per thread in the reduction: warp q takes columns q CPT ..
                 const int par = seg & 1;
                 const int n = tile * QG_ROWS + rank * 32 + lane;       // the output feature this thread finishes
+                const bool fold = p.xg_out != nullptr;                 // folded RMSNorm, producer side (this GEMM adds to the residual)
+                const float gam = fold && n < p.n ? __ldg(p.gamma_next + n) * QGEMM_NORM_PRESCALE : 0.f;
                 float old[CPT];
                 if (p.epi == GEMM_EPI_ADD_F32) {                       // the residual's old values: requested before anything is waited for
 #pragma unroll
@@ -456,12 +499,32 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                 q_wait_cluster(&recv_bar[par], (uint32_t)(seg >> 1) & 1u);
                 const float* mine = recv + (size_t)par * QG_CK * SLOT + (size_t)(q * CPT) * 32 + lane;
                 float* out = reinterpret_cast<float*>(p.c) + (size_t)(q * CPT) * p.ldc + n;
+                const int hcol = (n >> 4) * 8 + (n & 7);               // SiLU*mul: rows are [8 gate | 8 up] groups, lane ^ 8 is the partner
 #pragma unroll
                 for (int b = 0; b < CPT; ++b) {
                     float v = 0.f;
 #pragma unroll
                     for (int src = 0; src < QG_CK; ++src) v += mine[(size_t)src * SLOT + b * 32];
-                    if (n < p.n) out[(size_t)b * p.ldc] = p.epi == GEMM_EPI_ADD_F32 ? old[b] + v : v;
+                    if (inv != nullptr) v *= inv[q * CPT + b];
+                    if (p.epi == GEMM_EPI_SILU) {
+                        const float up = __shfl_xor_sync(0xffffffffu, v, 8);
+                        if ((lane & 8) == 0 && n < p.n)
+                            reinterpret_cast<__half*>(p.c)[(size_t)(q * CPT + b) * p.ldc + hcol] = __float2half_rn((v / (1.0f + expf(-v))) * up);
+                        continue;
+                    }
+                    const float xn = p.epi == GEMM_EPI_ADD_F32 ? old[b] + v : v;
+                    if (n < p.n) out[(size_t)b * p.ldc] = xn;
+                    if (fold) {
+                        if (n < p.n) p.xg_out[(size_t)(q * CPT + b) * p.ldxg + n] = __float2half_rn(xn * gam);
+                        // sum of squares of this slice's 32 rows for token q CPT + b: lanes in a fixed butterfly order
+                        float sq = n < p.n ? xn * xn : 0.f;
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                        if (lane == 0) p.ssq_out[(size_t)(tile * QG_CK + rank) * 64 + q * CPT + b] = sq;
+                    }
                 }
                 continue;
             }
@@ -519,7 +582,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);      // the accumulator has been read: the tile after next may start
                 }
-                if (whole) q_epilogue16(p, n, lane, c * 16, v);
+                if (whole) q_epilogue16(p, n, lane, c * 16, v, inv);
                 else if (finisher) {
                     if (PRE) {
 #pragma unroll
@@ -534,7 +597,7 @@ __global__ void __launch_bounds__(QG_THREADS, 1) qgemm_kernel(const __grid_const
                             for (int b = 0; b < 16; ++b) v[b] += tv[b];
                         }
                     }
-                    q_epilogue16(p, n, lane, c * 16, v);
+                    q_epilogue16(p, n, lane, c * 16, v, inv);
                 } else {
 #pragma unroll
                     for (int b = 0; b < 16; ++b) mine[(c * 16 + b) * QG_ROWS] = v[b];
@@ -615,16 +678,18 @@ bool cluster_mode_enabled() {
 
 template <int NB>
 cudaError_t launch_nb(QParams& qp, int grid, int n_sm, cudaStream_t s) {
-    // Tile-aligned split-K inside clusters of four for the GEMMs whose tiles are FEW and DEEP (QKV,
-    // attn_output, ffn_down: 32-48 tiles of 16-56 K-blocks on 148 SMs).  Under stream-K every such tile is shared by 4-6 CTAs
-    // that all finish at the same moment, and the partial sums cross L2 on the critical path (7-10 us per launch, run M);
-    // a cluster exchanges them through distributed shared memory.  Everything else (gate/up, lm_head: hundreds of tiles, at
-    // most two CTAs per tile, the second one early) stays stream-K.
+    // Tile-aligned split-K inside clusters of four.  Under stream-K a tile of QKV / attn_output / ffn_down (32-48 tiles of 16-56
+    // K-blocks on 148 SMs) is shared by 4-6 CTAs that all finish at the same moment, and the partial sums cross L2 on the
+    // critical path (7-10 us per launch, run M); a cluster exchanges them through distributed shared memory, and with many tiles
+    // per cluster (gate/up, lm_head) every exchange but the last hides behind the next tile's main loop.  Stream-K remains for
+    // matrices with fewer than four K-blocks per row and for GL_QGEMM_CLUSTER=0.
     qp.ck_s = 0;
-    if (cluster_mode_enabled() && qp.epi != GEMM_EPI_SILU && qp.nkb >= QG_CK) {
+    if (cluster_mode_enabled() && qp.nkb >= QG_CK) {                     // the same rule as qgemm_uses_cluster()
         const int cap = std::min(max_clusters_nb<NB>(), std::min(n_sm, QGEMM_MAX_GRID) / QG_CK);
         const int n_clusters = std::min(cap, qp.n_tiles);
-        if (n_clusters > 0 && qp.n_tiles <= 2 * n_clusters) {           // the two receive buffers cover two rounds
+        if (n_clusters > 0) {
+            // Any number of rounds on two receive buffers: a rank sends round r only after its own wait for round r - 1, which
+            // needs every peer's round r - 1 arrival, and a peer arrives for r - 1 only after it has read round r - 2.
             qp.ck_s = QG_CK;
             grid = n_clusters * QG_CK;
         }
@@ -721,8 +786,16 @@ cudaError_t qgemm_pack_launch(const QGemmSource* src, int nsrc, int mode, int k,
     return e;
 }
 
+bool qgemm_uses_cluster(const QGemmWeights& wt, int nb, int epi, int n_sm) {
+    (void)epi;
+    if (!cluster_mode_enabled() || wt.nkb < QG_CK) return false;
+    const int mc = nb == 16 ? max_clusters_nb<16>() : nb == 32 ? max_clusters_nb<32>() : max_clusters_nb<64>();
+    const int cap = std::min(mc, std::min(n_sm, QGEMM_MAX_GRID) / QG_CK);
+    return std::min(cap, wt.n_tiles) > 0;
+}
+
 cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows_alloc, int nb, void* c, int ldc, int epi, float* partial,
-                         int n_sm, cudaStream_t s) {
+                         int n_sm, cudaStream_t s, const QGemmNorm* norm) {
     if (!qgemm_batch_ok(nb) || act_rows_alloc < nb || !wt.w || (wt.k % QG_COLS) || ((uintptr_t)act % 16)) return cudaErrorInvalidValue;
     if (epi != GEMM_EPI_F32 && epi != GEMM_EPI_ADD_F32 && epi != GEMM_EPI_SILU) return cudaErrorInvalidValue;
     EncodeTiledFnQ fn = encode_fn_q();
@@ -743,6 +816,12 @@ cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows
     qp.tile_type = wt.two_segment ? nullptr : wt.tile_type;
     qp.raw_stride = wt.has_q6k ? QG_Q6K_BYTES + 768 : QG_Q4K_BYTES;      // 27 648 / 18 432: multiples of 1024
     qp.c = c; qp.ldc = ldc; qp.epi = epi; qp.n = wt.n; qp.n_tiles = wt.n_tiles; qp.nkb = wt.nkb;
+    if (norm != nullptr) {
+        if (norm->xg_out != nullptr && !(epi == GEMM_EPI_ADD_F32 && qgemm_uses_cluster(wt, nb, epi, n_sm) && norm->gamma_next && norm->ssq_out))
+            return cudaErrorInvalidValue;                                // the producer side exists in the cluster epilogue only
+        qp.gamma_next = norm->gamma_next; qp.xg_out = norm->xg_out; qp.ldxg = norm->ldxg; qp.ssq_out = norm->ssq_out;
+        qp.ssq_in = norm->ssq_in; qp.ssq_parts = norm->ssq_parts; qp.n_norm = norm->n_norm; qp.eps = norm->eps;
+    }
     const long long U = (long long)wt.n_tiles * wt.nkb;
     const int grid = (int)std::min<long long>(std::min(n_sm, QGEMM_MAX_GRID), U);
     if (trace_on()) {       // NOTE: a captured graph keeps the slot of the capture: trace with plain launches (gl_time_batch_step's warm pass)

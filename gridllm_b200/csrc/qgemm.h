@@ -43,6 +43,24 @@ struct QGemmSource { const uint8_t* w; int type; int rows; };
 
 constexpr int QGEMM_MAX_GRID = 148;
 
+// RMSNorm folded into the GEMMs around it (no separate kernel, no launch boundary):
+//   the residual-add GEMM in front of a norm (attn_output, ffn_down) also writes xg[b][n] = fp16(x_new[b][n] * gamma[n] / 16) -- the
+//   NEXT GEMM's activation rows, scaled by the norm's weights but not yet by 1 / rms -- and, per (32-row slice, token), the sum
+//   of x_new^2 (`ssq_out`, [parts][64]);  the GEMM behind the norm (QKV, gate/up, lm_head) multiplies its accumulator by
+//   16 / sqrt(sum of the parts / n_norm + eps) per token: W (g x / rms) = (W (g x)) / rms.  The parts are summed in a fixed order.
+//   Producer side needs the cluster mode of the kernel (qgemm_uses_cluster); otherwise the engine keeps the stand-alone kernel.
+struct QGemmNorm {
+    const float* gamma_next = nullptr;   // producer: weights of the norm BEHIND this GEMM's output, [n]
+    __half* xg_out = nullptr;            // producer: [>= nb rows][ldxg] fp16
+    int ldxg = 0;
+    float* ssq_out = nullptr;            // producer: [n_tiles * 4][64]
+    const float* ssq_in = nullptr;       // consumer: the parts written by the GEMM before; null = activations are already normalised
+    int ssq_parts = 0;
+    int n_norm = 0;                      // consumer: width of the normalised vector (n_embd)
+    float eps = 0.f;
+};
+constexpr float QGEMM_NORM_PRESCALE = 1.0f / 16.0f;
+
 size_t qgemm_partial_floats(int nb);          // floats of split-tile scratch a launch with nb batch columns may use
 cudaError_t qgemm_configure();                // opt in to the kernel's dynamic shared memory (once per device)
 bool qgemm_batch_ok(int nb);                  // nb in {16, 32, 64}
@@ -54,6 +72,8 @@ cudaError_t qgemm_pack_launch(const QGemmSource* src, int nsrc, int mode, int k,
 // C[b][n] (+)= sum_k act[b][k] * W[n][k] for b < nb batch rows.  act: fp16 [>= 128 rows][k] (rows beyond the batch are
 // read but their results never stored); epi as GemmEpilogue (F32, ADD_F32, SILU with C fp16 [.. x n/2]).
 cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows_alloc, int nb, void* c, int ldc, int epi, float* partial,
-                         int n_sm, cudaStream_t s);
+                         int n_sm, cudaStream_t s, const QGemmNorm* norm = nullptr);
+// will qgemm_launch run this GEMM in cluster mode (tile-aligned split-K inside clusters of four)?
+bool qgemm_uses_cluster(const QGemmWeights& wt, int nb, int epi, int n_sm);
 
 }  // namespace gl

@@ -287,6 +287,9 @@ class LlamaShape:
 TINY = LlamaShape("tiny-llama-synth", 2, 256, 4, 2, 512, 512, 10000.0, 1e-5, 512)
 # second tiny shape with n_ff that is not a power of two and GQA 4:1, head_dim 128 like Llama-3
 TINY128 = LlamaShape("tiny128-llama-synth", 2, 512, 4, 1, 768, 1024, 500000.0, 1e-5, 1024)
+# four K-blocks per row and 8-12 output tiles per GEMM: the smallest shape on which the batched step's quantised GEMMs take their
+# cluster path (tile-aligned split-K, folded RMSNorm) -- the 256 / 512-wide models above run the stream-K path only
+MID = LlamaShape("mid-llama-synth", 2, 1024, 8, 2, 2048, 1024, 500000.0, 1e-5, 1024)
 TINYLLAMA_1B = LlamaShape("tinyllama-1.1b-synth", 22, 2048, 32, 4, 5632, 32000, 10000.0, 1e-5, 2048)
 LLAMA3_8B = LlamaShape("llama3-8b-synth", 32, 4096, 32, 8, 14336, 128256, 500000.0, 1e-5, 8192)
 MISTRAL_7B = LlamaShape("mistral-7b-synth", 32, 4096, 32, 8, 14336, 32000, 10000.0, 1e-5, 8192)

@@ -52,6 +52,15 @@ def tiny128_gguf(tmp_models):
 
 
 @pytest.fixture(scope="session")
+def mid_gguf(tmp_models):
+    """2-layer d=1024 Llama (head_dim 128, GQA 4:1, n_ff 2048): wide enough for the cluster path of the batched GEMMs."""
+    from oracle import gguf_synth as S
+    p = str(tmp_models / "mid_q4km.gguf")
+    S.build_model(p, S.MID, "q4_k_m", seed=2468)
+    return p
+
+
+@pytest.fixture(scope="session")
 def tiny_q8_gguf(tmp_models):
     from oracle import gguf_synth as S
     p = str(tmp_models / "tiny_q8.gguf")

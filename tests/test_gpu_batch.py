@@ -53,7 +53,7 @@ def _check_against_oracle(ref, ids, lps, logits, tag):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("fixture", ["tiny_gguf", "tiny128_gguf"])
+@pytest.mark.parametrize("fixture", ["tiny_gguf", "tiny128_gguf", "mid_gguf"])
 def test_every_sequence_of_a_batch_matches_the_oracle(fixture, mode, request):
     from oracle import llama_oracle as O
     path = request.getfixturevalue(fixture)
