@@ -671,6 +671,14 @@ int max_clusters_nb() {
     }();
     return n;
 }
+// Cluster mode pays where tiles are few and deep.  With many tiles per cluster (gate/up: 7 rounds, lm_head: 31) it LOST to
+// stream-K on the measurement (run S: gate/up 28 -> 32 us, lm_head 92 -> 138 us): 132 of 148 SMs hold a cluster, the rounds
+// quantise (7 x 4 qtiles against 24.2), and a 4-qtile segment per tile leaves the accumulator hand-off no slack.  Default: at
+// most two rounds (QKV, attn_output, ffn_down of the Llama shapes); GL_QGEMM_CLUSTER_ROUNDS overrides.
+int cluster_max_rounds() {
+    static const int r = []() { const char* e = getenv("GL_QGEMM_CLUSTER_ROUNDS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    return r;
+}
 bool cluster_mode_enabled() {
     static const bool on = []() { const char* e = getenv("GL_QGEMM_CLUSTER"); return !(e && e[0] == '0'); }();
     return on;
@@ -680,14 +688,14 @@ template <int NB>
 cudaError_t launch_nb(QParams& qp, int grid, int n_sm, cudaStream_t s) {
     // Tile-aligned split-K inside clusters of four.  Under stream-K a tile of QKV / attn_output / ffn_down (32-48 tiles of 16-56
     // K-blocks on 148 SMs) is shared by 4-6 CTAs that all finish at the same moment, and the partial sums cross L2 on the
-    // critical path (7-10 us per launch, run M); a cluster exchanges them through distributed shared memory, and with many tiles
-    // per cluster (gate/up, lm_head) every exchange but the last hides behind the next tile's main loop.  Stream-K remains for
-    // matrices with fewer than four K-blocks per row and for GL_QGEMM_CLUSTER=0.
+    // critical path (7-10 us per launch, run M); a cluster exchanges them through distributed shared memory.  Stream-K remains
+    // for GEMMs with many tiles per cluster (gate/up, lm_head: cluster_max_rounds()), for matrices with fewer than four K-blocks
+    // per row and for GL_QGEMM_CLUSTER=0.
     qp.ck_s = 0;
     if (cluster_mode_enabled() && qp.nkb >= QG_CK) {                     // the same rule as qgemm_uses_cluster()
         const int cap = std::min(max_clusters_nb<NB>(), std::min(n_sm, QGEMM_MAX_GRID) / QG_CK);
         const int n_clusters = std::min(cap, qp.n_tiles);
-        if (n_clusters > 0) {
+        if (n_clusters > 0 && qp.n_tiles <= cluster_max_rounds() * n_clusters) {
             // Any number of rounds on two receive buffers: a rank sends round r only after its own wait for round r - 1, which
             // needs every peer's round r - 1 arrival, and a peer arrives for r - 1 only after it has read round r - 2.
             qp.ck_s = QG_CK;
@@ -791,7 +799,8 @@ bool qgemm_uses_cluster(const QGemmWeights& wt, int nb, int epi, int n_sm) {
     if (!cluster_mode_enabled() || wt.nkb < QG_CK) return false;
     const int mc = nb == 16 ? max_clusters_nb<16>() : nb == 32 ? max_clusters_nb<32>() : max_clusters_nb<64>();
     const int cap = std::min(mc, std::min(n_sm, QGEMM_MAX_GRID) / QG_CK);
-    return std::min(cap, wt.n_tiles) > 0;
+    const int n_clusters = std::min(cap, wt.n_tiles);
+    return n_clusters > 0 && wt.n_tiles <= cluster_max_rounds() * n_clusters;
 }
 
 cudaError_t qgemm_launch(const QGemmWeights& wt, const __half* act, int act_rows_alloc, int nb, void* c, int ldc, int epi, float* partial,
