@@ -180,6 +180,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
     prefill_tc5_ = env_int("GL_PREFILL_TC5", 1) != 0;
+    prefill_flash_ = env_int("GL_PREFILL_FLASH", 1) != 0;
 
     std::string err = gguf_.open(path);
     if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);
@@ -229,6 +230,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(gemv_configure());
     CU(prefill_configure());
     CU(gemm_tc5_configure());
+    CU(flash_prefill_configure());
 
     // ---- weights -> HBM -------------------------------------------------------------------------
     ST(upload_matrix(*te, tok_embd_, /*native=*/true));

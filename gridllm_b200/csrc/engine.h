@@ -141,6 +141,7 @@ private:
     int smem_kb_ = 224, attn_splits_ = 16;
     int prefill_mode_ = 0, prefill_min_ = 8;
     bool have_w16_ = false, prefill_bf16_ = false, prefill_tc5_ = true;
+    bool prefill_flash_ = true;     // fused prompt attention (prefill_attn.cu); GL_PREFILL_FLASH=0: the three-launch path, for A/B runs
     // prefill scratch (grown on demand)
     int pf_cap_ = 0;
     float *pf_x_ = nullptr, *pf_qkv_ = nullptr, *pf_s_ = nullptr;

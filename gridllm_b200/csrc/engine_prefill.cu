@@ -74,14 +74,14 @@ Status Engine::ensure_prefill_scratch(int t_pad) {
     const size_t T = (size_t)t_pad;
     CU(alloc((void**)&pf_x_, T * n_embd_ * 4));
     CU(alloc((void**)&pf_qkv_, T * (qd + 2 * kvd) * 4));
-    CU(alloc((void**)&pf_s_, (size_t)n_head_ * T * T * 4));
+    if (!prefill_flash_) CU(alloc((void**)&pf_s_, (size_t)n_head_ * T * T * 4));      // scores exist in HBM on the three-launch path only
     CU(alloc((void**)&pf_xn_, T * n_embd_ * 2));
     CU(alloc((void**)&pf_attn_, T * qd * 2));
     CU(alloc((void**)&pf_h_, T * n_ff_ * 2));
     CU(alloc((void**)&pf_q_, T * qd * 2));
     CU(alloc((void**)&pf_k_, T * kvd * 2));
     CU(alloc((void**)&pf_vt_, (size_t)kvd * T * 2));
-    CU(alloc((void**)&pf_p_, (size_t)n_head_ * T * T * 2));
+    if (!prefill_flash_) CU(alloc((void**)&pf_p_, (size_t)n_head_ * T * T * 2));
     pf_cap_ = t_pad;
     return {};
 }
@@ -101,6 +101,8 @@ Status Engine::prefill_batched(int n, int* n_launch) {
     };
     CU(embed_rows_launch(tok_embd_.w, tok_embd_.type, n_embd_, tok_embd_.row_stride, prompt_ids_, T, pf_x_, s)); ++nl;
     const float scale = 1.0f / std::sqrt((float)hd_);
+    PrefillSegs segs{};
+    segs.n = 1; segs.start[0] = 0; segs.len[0] = T; segs.table[0] = page_table_;
     for (int il = 0; il < n_layer_; ++il) {
         const LayerWeights& L = layers_[il];
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
@@ -112,21 +114,27 @@ Status Engine::prefill_batched(int n, int* n_launch) {
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
             CU(linear(g)); ++nl;
         }
-        CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, tp, s)); ++nl;
-        {   // S[h] = Q_h K_kvh^T
-            GemmParams g{};
-            g.a = pf_q_; g.b = pf_k_; g.c = pf_s_; g.m = T; g.n = T; g.k = hd_; g.lda = qd; g.ldb = kvd; g.ldc = tp;
-            g.batch = n_head_; g.a_batch_stride = hd_; g.b_batch_stride = hd_; g.b_batch_div = grp; g.c_batch_stride = (long long)tp * tp;
-            g.epi = GEMM_EPI_F32; g.causal_skip = 1;
-            CU(gemm_tn_launch(g, false, s)); ++nl;
-        }
-        CU(softmax_causal_launch(pf_s_, n_head_, T, tp, scale, pf_p_, s)); ++nl;
-        {   // O[:, h] = P[h] V_kvh   (B = V^T rows = head dims)
-            GemmParams g{};
-            g.a = pf_p_; g.b = pf_vt_; g.c = pf_attn_; g.m = T; g.n = hd_; g.k = TP; g.lda = tp; g.ldb = tp; g.ldc = qd;
-            g.batch = n_head_; g.a_batch_stride = (long long)tp * tp; g.b_batch_stride = (long long)hd_ * tp; g.b_batch_div = grp; g.c_batch_stride = hd_;
-            g.epi = GEMM_EPI_T16; g.causal_k = 1;
-            CU(gemm_tn_launch(g, false, s)); ++nl;
+        if (prefill_flash_) {
+            // RoPE + split + cache append, then ONE fused attention launch (prefill_attn.cu): scores stay on the SM
+            CU(rope_split_segs_launch(pf_qkv_, TP, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, tp, segs, s)); ++nl;
+            CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s)); ++nl;
+        } else {
+            CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, tp, s)); ++nl;
+            {   // S[h] = Q_h K_kvh^T
+                GemmParams g{};
+                g.a = pf_q_; g.b = pf_k_; g.c = pf_s_; g.m = T; g.n = T; g.k = hd_; g.lda = qd; g.ldb = kvd; g.ldc = tp;
+                g.batch = n_head_; g.a_batch_stride = hd_; g.b_batch_stride = hd_; g.b_batch_div = grp; g.c_batch_stride = (long long)tp * tp;
+                g.epi = GEMM_EPI_F32; g.causal_skip = 1;
+                CU(gemm_tn_launch(g, false, s)); ++nl;
+            }
+            CU(softmax_causal_launch(pf_s_, n_head_, T, tp, scale, pf_p_, s)); ++nl;
+            {   // O[:, h] = P[h] V_kvh   (B = V^T rows = head dims)
+                GemmParams g{};
+                g.a = pf_p_; g.b = pf_vt_; g.c = pf_attn_; g.m = T; g.n = hd_; g.k = TP; g.lda = tp; g.ldb = tp; g.ldc = qd;
+                g.batch = n_head_; g.a_batch_stride = (long long)tp * tp; g.b_batch_stride = (long long)hd_ * tp; g.b_batch_div = grp; g.c_batch_stride = hd_;
+                g.epi = GEMM_EPI_T16; g.causal_k = 1;
+                CU(gemm_tn_launch(g, false, s)); ++nl;
+            }
         }
         {
             GemmParams g{};
@@ -186,6 +194,27 @@ Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
             CU(linear(g)); ++nl;
         }
+        if (prefill_flash_) {
+            // the whole pack: one RoPE / split launch and one fused attention launch per PF_MAX_SEGS sequences
+            for (size_t c0 = 0; c0 < starts.size(); c0 += PF_MAX_SEGS) {
+                PrefillSegs segs{};
+                segs.n = (int)std::min<size_t>(PF_MAX_SEGS, starts.size() - c0);
+                int row_lo = starts[c0], row_hi = row_lo;
+                for (int i = 0; i < segs.n; ++i) {
+                    segs.start[i] = starts[c0 + i];
+                    segs.len[i] = lens[c0 + i];
+                    segs.table[i] = tables ? (*tables)[c0 + i] : nullptr;
+                    row_hi = std::max(row_hi, segs.start[i] + (segs.len[i] + 127) / 128 * 128);
+                }
+                if (c0 + PF_MAX_SEGS >= starts.size()) row_hi = std::max(row_hi, TP);      // trailing rows of the pack are zeroed too
+                // the kernel indexes rows of the pack absolutely: shift the segment starts to the chunk's first row
+                PrefillSegs rs = segs;
+                for (int i = 0; i < rs.n; ++i) rs.start[i] -= row_lo;
+                CU(rope_split_segs_launch(pf_qkv_ + (size_t)row_lo * ldq, row_hi - row_lo, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_ + (size_t)row_lo * qd,
+                                          pf_k_ + (size_t)row_lo * kvd, pf_vt_ + row_lo, kc, vc, tp, rs, s)); ++nl;
+                CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s)); ++nl;
+            }
+        } else
         for (size_t i = 0; i < starts.size(); ++i) {
             const int r0 = starts[i], len = lens[i], lp = (len + 127) / 128 * 128;
             // RoPE at positions 0..len-1 of THIS sequence; V^T columns r0.. of the pack-wide [kvd][tp] matrix; no cache

@@ -42,6 +42,24 @@ cudaError_t rmsnorm_rows_launch(const float* x, const float* w, int rows, int ro
 cudaError_t rope_split_launch(const float* qkv, int t_rows, int t_pad, int pos0, int n_head, int n_kv, int hd, const float* cos_t,
                               const float* sin_t, __half* qo, __half* ko, __half* vt, __half* k_cache, __half* v_cache,
                               const int* page_table, int vt_ld /* row stride of vt; k_cache may be null (nothing cached) */, cudaStream_t s);
+// ---- fused prompt attention (prefill_attn.cu) --------------------------------------------------------------------
+// The sequences of one pass: sequence i owns rows [start[i], start[i] + len[i]) of the packed activation matrix (starts at
+// 128-row boundaries); table[i] = its KV page table on the device (null: nothing is cached).
+constexpr int PF_MAX_SEGS = 32;
+struct PrefillSegs {
+    int n;
+    int start[PF_MAX_SEGS];
+    int len[PF_MAX_SEGS];
+    const int* table[PF_MAX_SEGS];
+};
+cudaError_t flash_prefill_configure();
+bool flash_prefill_supported(int hd);
+// out[rows][n_head * hd] = causal softmax(q k^T * scale) v per sequence and head; q / k rows, vt = V^T [n_kv * hd][vt_ld]
+cudaError_t flash_prefill_launch(const __half* q, const __half* k, const __half* vt, __half* out, const PrefillSegs& segs, int n_head, int n_kv,
+                                 int hd, int vt_ld, float scale, cudaStream_t s);
+// rope_split for every sequence of a pack in one launch (rows_pad = rows of the pack, padding rows are zeroed)
+cudaError_t rope_split_segs_launch(const float* qkv, int rows_pad, int n_head, int n_kv, int hd, const float* cos_t, const float* sin_t, __half* qo,
+                                   __half* ko, __half* vt, __half* k_cache, __half* v_cache, int vt_ld, const PrefillSegs& segs, cudaStream_t s);
 cudaError_t softmax_causal_launch(const float* sc, int n_head, int t_rows, int t_pad, float scale, __half* p, cudaStream_t s);
 cudaError_t embed_rows_launch(const uint8_t* w, int type, int cols, int row_bytes, const int* ids, int t_rows, float* x, cudaStream_t s);
 

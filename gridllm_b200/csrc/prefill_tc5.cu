@@ -38,9 +38,14 @@ constexpr int ACC_BUFS = 2;
 // Output tile 128 x BN.  BN = 128: 6 stages of 32 KB, accumulators in 256 of the SM's 512 TMEM columns.  BN = 256: 4 stages of
 // 48 KB, accumulators in all 512 columns -- each K-step then stages 48 KB for 128 x 256 x 64 MACs (96 B per MMA cycle instead
 // of 128): the L2 -> shared-memory feed, not the tensor pipe, is what limits the 128 x 128 tile (tensor pipe active 46 %, run 59).
-template <int BN> struct Tc5Cfg {
-    static constexpr int STAGES = BN == 128 ? 6 : 4;
-    static constexpr int TILE_B_BYTES = BN * BK * 2;
+// PAIR = 2: two CTAs on the two SMs of a TPC (a cluster of two) share one 256 x BN tile -- tcgen05.mma.cta_group::2, M 256: each CTA
+// stages its own 128 rows of A and HALF of the B tile (BN / 2 weight rows), the tensor cores of both SMs read both halves of B.
+// Per SM and K-step that is 32 KB staged for 128 x 256 x 64 MACs instead of 48 KB: the shared-memory port (TMA writes + operand
+// reads), which is what limits the one-CTA 128 x 256 tile, carries 128 B per MMA cycle instead of 192, and 6 stages fit.
+template <int BN, int PAIR> struct Tc5Cfg {
+    static constexpr int B_ROWS = BN / PAIR;                     // rows of B this CTA stages
+    static constexpr int STAGES = (BN == 128 || PAIR == 2) ? 6 : 4;
+    static constexpr int TILE_B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
     static constexpr int TMEM_COLS = ACC_BUFS * BN;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
@@ -79,6 +84,46 @@ __device__ __forceinline__ void tc5_mma_f16(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA pair (cta_group::2) -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc5_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tc5_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the same shared-memory location in CTA 0 of the pair: bit 24 of a shared::cluster address is the rank inside the pair
+constexpr uint32_t TC5_PEER_MASK = 0xFEFFFFFFu;
+// TMA of a CTA of a pair: the bytes land in THIS CTA's shared memory, the transaction count on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar) & TC5_PEER_MASK), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// commit of the pair's MMAs: one arrival on the mbarrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc5_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc5_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrival on the mbarrier at this offset in the LEADER's shared memory (from either CTA of the pair)
+__device__ __forceinline__ void tc5_arrive_leader(uint64_t* bar) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(0u));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
 // K-major operand tile, 128-byte swizzle, rows of 64 16-bit elements (one swizzle atom = 8 rows x 128 B = 1024 B):
 // start address, stride between 8-row groups = 1024 B, descriptor version 1 (sm_100), layout SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -158,24 +203,27 @@ __device__ __forceinline__ void epilogue_row(const Tc5Params& p, int row, int co
     }
 }
 
-template <int BN>
+template <int BN, int PAIR>
 __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ Tc5Params p) {
-    constexpr int STAGES = Tc5Cfg<BN>::STAGES, TILE_B_BYTES = Tc5Cfg<BN>::TILE_B_BYTES, STAGE_BYTES = Tc5Cfg<BN>::STAGE_BYTES;
-    constexpr int TMEM_COLS = Tc5Cfg<BN>::TMEM_COLS;
-    (void)TILE_B_BYTES;
+    using Cfg = Tc5Cfg<BN, PAIR>;
+    constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, B_ROWS = Cfg::B_ROWS;
+    constexpr int TMEM_COLS = Cfg::TMEM_COLS;
+    constexpr int TM = BM * PAIR;                     // rows of the tile a CTA (pair) owns
     extern __shared__ uint8_t smem_raw[];
     // 128-byte-swizzled tiles must sit on 1024-byte boundaries
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;          // [ACC_BUFS] MMA issuer -> epilogue
-    uint64_t* acc_empty = acc_full + ACC_BUFS;    // [ACC_BUFS] epilogue (4 warps) -> MMA issuer
+    uint64_t* acc_empty = acc_full + ACC_BUFS;    // [ACC_BUFS] epilogue (4 warps per CTA) -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_BUFS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR == 2 ? (int)tc5_cluster_rank() : 0;      // CTA inside the pair; rank 0 issues the MMAs
+    const int worker = (int)blockIdx.x / PAIR, n_workers = (int)gridDim.x / PAIR;
     // M tiles are the fast grid dimension: the (few) CTAs that share a weight tile run back to back and find it in L2
     // (N-major order re-read every weight byte from DRAM once per M tile: 943 MB for the 235 MB gate/up matrix, run 39)
-    const int tiles_m = (p.m + BM - 1) / BM, tiles_n = (p.n + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
+    const int tiles_m = (p.m + TM - 1) / TM, tiles_n = (p.n + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
     const int nk = (p.k + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -189,16 +237,22 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
         }
         for (int i = 0; i < ACC_BUFS; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_empty[i], 4 * PAIR);
         }
         fence_mbar_init();
     }
-    if (warp == 2) {   // one warp allocates the accumulator's TMEM columns and publishes the base address
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 2) {   // one warp (of each CTA of a pair) allocates the accumulator's TMEM columns and publishes the base address
+        if constexpr (PAIR == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc5_fence_before();
     __syncthreads();
+    if constexpr (PAIR == 2) tc5_cluster_sync();      // the peer's barriers exist before anything signals them
     tc5_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -207,64 +261,80 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
             // ===== TMA producer: the ring runs on across tile boundaries =====
             int st = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            for (int tile = worker; tile < n_tiles; tile += n_workers) {
+                const int m0 = (tile % tiles_m) * TM + rank * BM, n0 = (tile / tiles_m) * BN + rank * B_ROWS;
                 for (int kb = 0; kb < nk; ++kb) {
                     mbar_wait(&empty[st], ph ^ 1u);
                     uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
-                    mbar_expect_tx(&full[st], STAGE_BYTES);
-                    tma_load_2d(sa, &p.ta, kb * BK, m0, &full[st]);
+                    if constexpr (PAIR == 2) {
+                        // both CTAs' boxes are counted on the leader's barrier (armed by the leader alone: the phase cannot
+                        // complete before its arrival, however early the peer's bytes land)
+                        if (rank == 0) mbar_expect_tx(&full[st], 2 * STAGE_BYTES);
+                        tma_load_2d_pair(sa, &p.ta, kb * BK, m0, &full[st]);
+                        tma_load_2d_pair(sa + TILE_A_BYTES, &p.tb, kb * BK, n0, &full[st]);
+                    } else {
+                        mbar_expect_tx(&full[st], STAGE_BYTES);
+                        tma_load_2d(sa, &p.ta, kb * BK, m0, &full[st]);
 #pragma unroll
-                    for (int h = 0; h < BN / 128; ++h)      // the tensor map's box is 128 rows: a 256-row B tile is two boxes, 16 KB apart
-                        tma_load_2d(sa + TILE_A_BYTES + h * (128 * BK * 2), &p.tb, kb * BK, n0 + h * 128, &full[st]);
+                        for (int h = 0; h < BN / 128; ++h)      // the tensor map's box is 128 rows: a 256-row B tile is two boxes, 16 KB apart
+                            tma_load_2d(sa + TILE_A_BYTES + h * (128 * BK * 2), &p.tb, kb * BK, n0 + h * 128, &full[st]);
+                    }
                     if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer (of a pair: the leader's) =====
         // The whole warp walks the loop with warp-uniform values and ONE ELECTED lane issues: inside `if (lane == 0)` the
         // compiler cannot keep descriptors and addresses in uniform registers and wraps every tcgen05 instruction in a
         // convert-to-uniform loop (ELECT / R2UR / UTCHMMA / BRA.U.ANY); written this way an MMA is two uniform adds and the
         // instruction (found on the batched decode GEMM, where the issuer's own instruction stream set the pace: qgemm.cu).
-        // instruction descriptor: D = F32, A / B = F16 or BF16, both K-major, N = BN, M = 128
-        const uint32_t fmt = p.bf16 ? 1u : 0u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-        int st = 0;
-        uint32_t ph = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(&acc_empty[buf], aph ^ 1u);      // the epilogue has drained this half (free on its first use)
-            tc5_fence_after();
-            const uint32_t tmem_d = tb + (uint32_t)(buf * BN);
-            for (int kb = 0; kb < nk; ++kb) {
-                mbar_wait(&full[st], ph);
+        // instruction descriptor: D = F32, A / B = F16 or BF16, both K-major, N = BN, M = 128 (pair: 256)
+        if (rank == 0) {
+            const uint32_t fmt = p.bf16 ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            int st = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int tile = worker; tile < n_tiles; tile += n_workers, ++it) {
+                const int buf = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&acc_empty[buf], aph ^ 1u);      // the epilogue(s) have drained this half (free on its first use)
                 tc5_fence_after();
-                const uint32_t sa = smem0 + (uint32_t)(st * STAGE_BYTES);
-                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
-                if (tc5_elect_one()) {
+                const uint32_t tmem_d = tb + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&full[st], ph);
+                    tc5_fence_after();
+                    const uint32_t sa = smem0 + (uint32_t)(st * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + TILE_A_BYTES);
+                    if (tc5_elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advancing K inside the swizzle atom: +32 bytes = +2 in the descriptor's 16-byte address units
-                        tc5_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : (kb ? 1u : 0u));
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advancing K inside the swizzle atom: +32 bytes = +2 in the descriptor's 16-byte address units
+                            if constexpr (PAIR == 2) tc5_mma_f16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : (kb ? 1u : 0u));
+                            else tc5_mma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : (kb ? 1u : 0u));
+                        }
+                        if constexpr (PAIR == 2) {
+                            tc5_commit_pair(&empty[st]);                       // both CTAs' stages are free once these MMAs have read them
+                            if (kb == nk - 1) tc5_commit_pair(&acc_full[buf]); // ... and both halves of the accumulator are complete
+                        } else {
+                            tc5_commit(&empty[st]);                       // the stage is free once these MMAs have read it
+                            if (kb == nk - 1) tc5_commit(&acc_full[buf]); // ... and the accumulator is complete
+                        }
                     }
-                    tc5_commit(&empty[st]);                       // the stage is free once these MMAs have read it
-                    if (kb == nk - 1) tc5_commit(&acc_full[buf]); // ... and the accumulator is complete
+                    __syncwarp();
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++st == STAGES) { st = 0; ph ^= 1u; }
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> global (each CTA of a pair: its own 128 rows) =====
         const int q = warp & 3;                      // the TMEM lane quarter this warp may access
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int tile = worker; tile < n_tiles; tile += n_workers, ++it) {
+            const int m0 = (tile % tiles_m) * TM + rank * BM, n0 = (tile / tiles_m) * BN;
             const int buf = it & 1;
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
             tc5_fence_after();
@@ -281,13 +351,18 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
             }
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp's quarter of the accumulator half is in registers / memory
+            if (lane == 0) {                          // this warp's quarter of the accumulator half is in registers / memory
+                if constexpr (PAIR == 2) tc5_arrive_leader(&acc_empty[buf]);
+                else mbar_arrive(&acc_empty[buf]);
+            }
         }
     }
     tc5_fence_before();
     __syncthreads();
+    if constexpr (PAIR == 2) tc5_cluster_sync();      // neither CTA frees tensor memory the pair's MMAs may still write
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if constexpr (PAIR == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -320,8 +395,9 @@ bool make_map(CUtensorMap* map, const void* base, int rows, int k, int ld, bool 
 }  // namespace
 
 cudaError_t gemm_tc5_configure() {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<128>::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc5_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<256>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<128, 1>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc5_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<256, 1>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc5_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Cfg<256, 2>::SMEM);
     return e;
 }
 
@@ -349,12 +425,40 @@ cudaError_t gemm_tc5_launch(const GemmParams& p, int a_rows_alloc, bool bf16, cu
     bool wide = p.m > 128 && p.n >= 512 && 2 * waves(t256) <= waves(t128) + (waves(t128) > 6 ? 1 : 0);
     if (force_bn == 128) wide = false;
     if (force_bn == 256) wide = p.n >= 256;
+    // CTA pairs (cta_group::2, 256 x 256 tiles on two SMs) where they do not cost whole waves: time in units of one 128 x 128 tile
+    // on one SM.  GL_TC5_PAIR = 0 never, 1 (default) by this rule, 2 whenever the shape allows it (tests, A/B runs).
+    const int pair_mode = []() { const char* e = getenv("GL_TC5_PAIR"); return e ? atoi(e) : 1; }();      // read per launch: tests flip it inside one process
+    const int t_pair = ((p.m + 255) / 256) * ((p.n + 255) / 256);
+    const int cost_single = wide ? 2 * waves(t256) : waves(t128);
+    const int cost_pair = 2 * ((t_pair + n_sm / 2 - 1) / (n_sm / 2));
+    if (p.m > 128 && p.n >= 256 && (pair_mode == 2 || (pair_mode == 1 && cost_pair <= cost_single))) {
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(TC5_THREADS);
+        cfg.dynamicSmemBytes = Tc5Cfg<256, 2>::SMEM;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        // pairs that can be resident at once (one per TPC unless the device says otherwise): the persistent grid is that wide
+        static const int max_pairs = [&]() {
+            cudaLaunchConfig_t q = cfg;
+            q.gridDim = dim3((unsigned)(2 * (n_sm / 2)));
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc5_kernel<256, 2>, &q) != cudaSuccess || n < 1) { cudaGetLastError(); n = n_sm / 2; }
+            return std::min(n, n_sm / 2);
+        }();
+        const int pairs = std::max(1, std::min(t_pair, max_pairs));
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        return cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<256, 2>, tp);
+    }
     if (wide) {
         const dim3 grid((unsigned)(persist ? std::min(t256, n_sm) : t256));
-        gemm_tc5_kernel<256><<<grid, TC5_THREADS, Tc5Cfg<256>::SMEM, s>>>(tp);
+        gemm_tc5_kernel<256, 1><<<grid, TC5_THREADS, Tc5Cfg<256, 1>::SMEM, s>>>(tp);
     } else {
         const dim3 grid((unsigned)(persist ? std::min(t128, n_sm) : t128));
-        gemm_tc5_kernel<128><<<grid, TC5_THREADS, Tc5Cfg<128>::SMEM, s>>>(tp);
+        gemm_tc5_kernel<128, 1><<<grid, TC5_THREADS, Tc5Cfg<128, 1>::SMEM, s>>>(tp);
     }
     return cudaGetLastError();
 }

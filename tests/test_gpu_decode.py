@@ -213,6 +213,52 @@ def test_batched_prefill_many_tiles_per_sm(wide_ffn_gguf, n_tok, monkeypatch):
     assert np.abs(lb - l2).max() <= 1e-2 * scale
 
 
+@pytest.mark.parametrize("fixture", ["tiny_gguf", "tiny128_gguf"])          # head dim 64 and 128
+@pytest.mark.parametrize("n_tok", [37, 200, 300])
+def test_fused_prompt_attention_equals_three_launch_path(fixture, n_tok, request, monkeypatch):
+    """prefill_attn.cu (scores on the SM, online softmax) against the path it replaces (Q K^T GEMM -> causal softmax -> P V GEMM,
+    GL_PREFILL_FLASH=0): same q / k / v bits in, P rounded to fp16 in both; stated tolerance 2e-3 * max|logit|."""
+    from oracle import llama_oracle as O
+    path = request.getfixturevalue(fixture)
+    m = O.load_gguf(path)
+    toks = np.random.Generator(np.random.PCG64(4000 + n_tok)).integers(0, m.n_vocab - 3, size=n_tok)
+    monkeypatch.setenv("GL_PREFILL_FLASH", "1")
+    e1 = _engine(path, prefill_mode=0)
+    l1 = e1.prefill(toks)
+    nxt = int(np.argmax(l1))
+    d1, _, _ = e1.decode_step(nxt)                      # the KV rows the fused RoPE / split launch cached
+    e1.close()
+    monkeypatch.setenv("GL_PREFILL_FLASH", "0")
+    e0 = _engine(path, prefill_mode=0)
+    l0 = e0.prefill(toks)
+    d0, _, _ = e0.decode_step(nxt)
+    e0.close()
+    scale = np.abs(l0).max()
+    assert np.isfinite(l1).all()
+    assert np.abs(l1 - l0).max() <= 2e-3 * scale, (fixture, n_tok, np.abs(l1 - l0).max(), scale)
+    assert np.abs(d1 - d0).max() <= 2e-3 * np.abs(d0).max()
+
+
+@pytest.mark.parametrize("n_tok", [129, 300, 520])
+def test_cta_pair_gemm_equals_single_cta_gemm(wide_ffn_gguf, n_tok, monkeypatch):
+    """tcgen05.mma.cta_group::2 (256 x 256 tiles on two SMs, GL_TC5_PAIR=2: wherever the shape allows) against the one-CTA kernel: same operands, same K
+    order per output element.  Ragged M: the pair's second CTA owns rows past the prompt in the last tile."""
+    from oracle import llama_oracle as O
+    m = O.load_gguf(wide_ffn_gguf)
+    toks = np.random.Generator(np.random.PCG64(6000 + n_tok)).integers(0, m.n_vocab - 3, size=n_tok)
+    out = {}
+    for mode in ("2", "0"):                               # 2 = pairs whenever the shape allows, 0 = never
+        monkeypatch.setenv("GL_TC5_PAIR", mode)
+        e = _engine(wide_ffn_gguf, prefill_mode=0, max_ctx=1024)
+        for _ in range(2):
+            e.kv_reset()
+            out[mode] = e.prefill(toks)
+        e.close()
+    scale = np.abs(out["0"]).max()
+    assert np.isfinite(out["2"]).all()
+    assert np.abs(out["2"] - out["0"]).max() <= 1e-5 * scale, (n_tok, np.abs(out["2"] - out["0"]).max(), scale)
+
+
 def test_generate_with_batched_prefill(tiny128_gguf):
     from oracle import llama_oracle as O
     m = O.load_gguf(tiny128_gguf)
