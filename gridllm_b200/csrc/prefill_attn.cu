@@ -249,50 +249,65 @@ __global__ void __launch_bounds__(FA_THREADS, 2) flash_prefill_kernel(const __gr
 template <int HD> constexpr int fa_smem_bytes() { return FA_BM * HD * 2 + 2 * (FA_BN * HD * 2 + HD * FA_BN * 2); }
 
 // QKV fp32 rows of a PACK -> RoPE -> Q, K (16-bit rows), V^T columns, + each sequence's own fp16 cache pages.
-// One launch for the whole pack: block = row of the pack; the rows between a sequence's end and its 128-row boundary are
-// written as zeros (finite operands for the padded tiles).
+// One launch for the whole pack: block = EIGHT consecutive rows of the pack (sequences start on 128-row boundaries, so a block
+// never straddles two of them); the rows between a sequence's end and its 128-row boundary are written as zeros (finite
+// operands for the padded tiles).  Eight rows per block make the V^T store one 16-byte write per (head dim, block) instead of
+// eight 2-byte writes a row stride apart (the per-row version moved 16 x the bytes it stored).
+constexpr int RS_ROWS = 8;
 __global__ void __launch_bounds__(256) rope_split_segs_kernel(const float* __restrict__ qkv, int n_head, int n_kv, int hd,
                                                               const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                               __half* __restrict__ qo, __half* __restrict__ ko, __half* __restrict__ vt,
                                                               __half* __restrict__ k_cache, __half* __restrict__ v_cache, int vt_ld,
                                                               const __grid_constant__ PrefillSegs segs) {
-    const int t = blockIdx.x;
+    const int t0 = blockIdx.x * RS_ROWS;
     const int qd = n_head * hd, kvd = n_kv * hd, ld = qd + 2 * kvd;
     int seq = -1;
     for (int i = 0; i < segs.n; ++i) {
         const int lp = (segs.len[i] + 127) / 128 * 128;
-        if (t >= segs.start[i] && t < segs.start[i] + lp) seq = i;
+        if (t0 >= segs.start[i] && t0 < segs.start[i] + lp) seq = i;
     }
-    const int pos = seq >= 0 ? t - segs.start[seq] : 0;
-    if (seq < 0 || pos >= segs.len[seq]) {
-        for (int i = threadIdx.x; i < qd; i += 256) qo[(size_t)t * qd + i] = __float2half_rn(0.f);
-        for (int i = threadIdx.x; i < kvd; i += 256) { ko[(size_t)t * kvd + i] = __float2half_rn(0.f); vt[(size_t)i * vt_ld + t] = __float2half_rn(0.f); }
-        return;
-    }
-    const float* row = qkv + (size_t)t * ld;
-    const int* page_table = segs.table[seq];
+    const int pos0 = seq >= 0 ? t0 - segs.start[seq] : 0;
+    const int n_valid = seq >= 0 ? max(0, min(RS_ROWS, segs.len[seq] - pos0)) : 0;      // rows pos0 .. pos0 + n_valid - 1 are tokens
+    const int* page_table = seq >= 0 ? segs.table[seq] : nullptr;
     const bool cache = k_cache != nullptr && page_table != nullptr;
-    const int page = cache ? page_table[pos / KV_PAGE_TOKENS] : 0, tok = pos % KV_PAGE_TOKENS;
-    for (int i = threadIdx.x; i < (qd + kvd) / 2; i += 256) {
-        const int r = 2 * i;
-        const int d = r % hd;
-        const float c = cos_t[(size_t)pos * (hd / 2) + d / 2], s = sin_t[(size_t)pos * (hd / 2) + d / 2];
-        const float a = row[r], b = row[r + 1];
-        const float o0 = a * c - b * s, o1 = a * s + b * c;
-        if (r < qd) {
-            *reinterpret_cast<__half2*>(qo + (size_t)t * qd + r) = __floats2half2_rn(o0, o1);
-        } else {
-            const int rk = r - qd, kvh = rk / hd;
-            const __half2 hk = __floats2half2_rn(o0, o1);
-            *reinterpret_cast<__half2*>(ko + (size_t)t * kvd + rk) = hk;
-            if (cache) *reinterpret_cast<__half2*>(k_cache + (((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d) = hk;
+    for (int j = 0; j < RS_ROWS; ++j) {
+        const int t = t0 + j, pos = pos0 + j;
+        if (j >= n_valid) {
+            for (int i = threadIdx.x; i < qd / 2; i += 256) *reinterpret_cast<__half2*>(qo + (size_t)t * qd + 2 * i) = __floats2half2_rn(0.f, 0.f);
+            for (int i = threadIdx.x; i < kvd / 2; i += 256) *reinterpret_cast<__half2*>(ko + (size_t)t * kvd + 2 * i) = __floats2half2_rn(0.f, 0.f);
+            continue;
+        }
+        const float* row = qkv + (size_t)t * ld;
+        const int page = cache ? page_table[pos / KV_PAGE_TOKENS] : 0, tok = pos % KV_PAGE_TOKENS;
+        for (int i = threadIdx.x; i < (qd + kvd) / 2; i += 256) {
+            const int r = 2 * i;
+            const int d = r % hd;
+            const float c = cos_t[(size_t)pos * (hd / 2) + d / 2], s = sin_t[(size_t)pos * (hd / 2) + d / 2];
+            const float2 ab = *reinterpret_cast<const float2*>(row + r);
+            const float o0 = ab.x * c - ab.y * s, o1 = ab.x * s + ab.y * c;
+            if (r < qd) {
+                *reinterpret_cast<__half2*>(qo + (size_t)t * qd + r) = __floats2half2_rn(o0, o1);
+            } else {
+                const int rk = r - qd, kvh = rk / hd;
+                const __half2 hk = __floats2half2_rn(o0, o1);
+                *reinterpret_cast<__half2*>(ko + (size_t)t * kvd + rk) = hk;
+                if (cache) *reinterpret_cast<__half2*>(k_cache + (((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d) = hk;
+            }
         }
     }
+    // V: thread = head-dim column, the block's eight tokens side by side in V^T
     for (int i = threadIdx.x; i < kvd; i += 256) {
-        const __half hv = __float2half_rn(row[qd + kvd + i]);
-        vt[(size_t)i * vt_ld + t] = hv;
-        const int kvh = i / hd, d = i % hd;
-        if (cache) v_cache[(((size_t)page * n_kv + kvh) * KV_PAGE_TOKENS + tok) * hd + d] = hv;
+        __align__(16) __half hv[RS_ROWS];
+#pragma unroll
+        for (int j = 0; j < RS_ROWS; ++j) hv[j] = __float2half_rn(j < n_valid ? qkv[(size_t)(t0 + j) * ld + qd + kvd + i] : 0.f);
+        *reinterpret_cast<uint4*>(vt + (size_t)i * vt_ld + t0) = *reinterpret_cast<const uint4*>(hv);
+        if (cache) {
+            const int kvh = i / hd, d = i % hd;
+            for (int j = 0; j < n_valid; ++j) {
+                const int pos = pos0 + j;
+                v_cache[(((size_t)page_table[pos / KV_PAGE_TOKENS] * n_kv + kvh) * KV_PAGE_TOKENS + pos % KV_PAGE_TOKENS) * hd + d] = hv[j];
+            }
+        }
     }
 }
 
@@ -327,8 +342,9 @@ cudaError_t flash_prefill_launch(const __half* q, const __half* k, const __half*
 
 cudaError_t rope_split_segs_launch(const float* qkv, int rows_pad, int n_head, int n_kv, int hd, const float* cos_t, const float* sin_t, __half* qo,
                                    __half* ko, __half* vt, __half* k_cache, __half* v_cache, int vt_ld, const PrefillSegs& segs, cudaStream_t s) {
-    if (segs.n < 1 || segs.n > PF_MAX_SEGS || rows_pad < 1 || (hd & 1)) return cudaErrorInvalidValue;
-    rope_split_segs_kernel<<<rows_pad, 256, 0, s>>>(qkv, n_head, n_kv, hd, cos_t, sin_t, qo, ko, vt, k_cache, v_cache, vt_ld, segs);
+    // rows come in whole blocks of eight; the V^T store is 16 bytes wide
+    if (segs.n < 1 || segs.n > PF_MAX_SEGS || rows_pad < 1 || (rows_pad % RS_ROWS) || (hd & 1) || (vt_ld & 7) || ((uintptr_t)vt & 15)) return cudaErrorInvalidValue;
+    rope_split_segs_kernel<<<rows_pad / RS_ROWS, 256, 0, s>>>(qkv, n_head, n_kv, hd, cos_t, sin_t, qo, ko, vt, k_cache, v_cache, vt_ld, segs);
     return cudaGetLastError();
 }
 

@@ -88,18 +88,22 @@ class NativeInferenceService:
     OLLAMA_SAMPLING_DEFAULTS = {"temperature": 0.8, "top_k": 40, "top_p": 0.9}
 
     def __init__(self, models: Dict[str, str], device: int = 0, max_ctx: int = 0,
-                 sampling_defaults: Optional[Dict[str, Any]] = None, apply_template: bool = False, max_batch: int = 0, **engine_kw):
+                 sampling_defaults: Optional[Dict[str, Any]] = None, apply_template: bool = False, max_batch: int = 0,
+                 jinja_templates: bool = True, **engine_kw):
         """models: Ollama-style model name -> GGUF path.
         sampling_defaults: options a request inherits when it does not carry them.  None = greedy (temperature 0, the
         BASELINE.json configuration); pass OLLAMA_SAMPLING_DEFAULTS to behave like an Ollama worker for such requests.
         apply_template: frame generate / completion prompts as one user turn of the model's chat template (with
         metadata.system as the system turn) unless metadata.raw, as Ollama does; default False = raw prompts.
         max_batch: > 1 turns on continuous batching: concurrent generate* calls become sequences of
-        one engine and are decoded together, one batched step per token (gridllm_b200/batching.py); 0 / 1 = one request at a time."""
+        one engine and are decoded together, one batched step per token (gridllm_b200/batching.py); 0 / 1 = one request at a time.
+        jinja_templates: render tokenizer.chat_template as Jinja for chat requests (default); False = family framing only."""
         self._sampling_defaults = dict(sampling_defaults or {})
         # Ollama wraps the prompt of /api/generate and /v1/completions in the model's template (system + prompt as one user
         # turn) unless the request says raw [external]; off by default: the prompt text is tokenised as it is
         self._apply_template = bool(apply_template)
+        # chat messages are framed by RENDERING the GGUF's tokenizer.chat_template (Jinja); False = by template family only
+        self._jinja = bool(jinja_templates)
         self._paths = dict(models)
         self._device = device
         self._max_ctx = max_ctx
@@ -216,15 +220,68 @@ class NativeInferenceService:
             return np.concatenate([np.asarray(ctx, dtype=np.int32), np.asarray(new, dtype=np.int32)])
         return eng.tokenize(text or "", add_bos=True, parse_special=False)
 
+    @staticmethod
+    def _control_text(eng: N.Engine, tid) -> str:
+        """the vocabulary text of a (control) token: gl_token_piece renders control tokens as nothing (what a stream wants), so
+        the text is found by asking the tokenizer which known spelling parses to this id"""
+        try:
+            if tid is None or int(tid) < 0:
+                return ""
+            txt = eng.token_piece(int(tid)).decode("utf-8", "replace")
+            if txt:
+                return txt
+            for cand in ("<|begin_of_text|>", "<|end_of_text|>", "<|eot_id|>", "<s>", "</s>", "<|im_start|>", "<|im_end|>",
+                         "<|endoftext|>", "<bos>", "<eos>", "<|startoftext|>"):
+                ids = eng.tokenize(cand, add_bos=False, parse_special=True)
+                if len(ids) == 1 and int(ids[0]) == int(tid):
+                    return cand
+        except Exception:
+            pass
+        return ""
+
+    def _render_jinja(self, eng: N.Engine, tmpl: str, messages: List[Dict[str, Any]]) -> Optional[str]:
+        """tokenizer.chat_template interpreted as what it is -- a Jinja program -- the way Ollama's runner and Hugging Face
+        `apply_chat_template` do [external]: sandboxed environment, `messages`, `add_generation_prompt = True`, `bos_token` /
+        `eos_token` (the GGUF's own token texts) and `raise_exception`.  None when the template cannot be rendered (a construct
+        outside Jinja, a variable the host does not supply, a role the template refuses): the caller falls back to the
+        template FAMILY.  A leading BOS text is dropped: the tokenizer adds the BOS id itself."""
+        try:
+            import jinja2
+            from jinja2.sandbox import ImmutableSandboxedEnvironment
+        except Exception:
+            return None
+        try:
+            key = (id(eng), tmpl)
+            cache = self.__dict__.setdefault("_tmpl_cache", {})
+            if key not in cache:
+                env = ImmutableSandboxedEnvironment(trim_blocks=True, lstrip_blocks=True, undefined=jinja2.StrictUndefined)
+
+                def raise_exception(msg):
+                    raise jinja2.exceptions.TemplateError(msg)
+                env.globals["raise_exception"] = raise_exception
+
+                cache[key] = (env.from_string(tmpl), self._control_text(eng, getattr(eng.info, "bos_id", -1)), self._control_text(eng, getattr(eng.info, "eos_id", -1)))
+            t, bos, eos = cache[key]
+            out = t.render(messages=[dict(m) for m in messages], add_generation_prompt=True, bos_token=bos, eos_token=eos)
+            if bos and out.startswith(bos):
+                out = out[len(bos):]
+            return out if out else None
+        except Exception:
+            return None
+
     def _chat_prompt(self, eng: N.Engine, messages: List[Dict[str, Any]]) -> str:
-        """messages -> prompt text.  The GGUF's chat template is not interpreted (it is Jinja); its FAMILY is recognised from
-        the markers it contains -- what llama.cpp's template detection does [external] -- and the family's framing applied:
-        Llama-3 headers (also the default without a template), ChatML, Llama-2 / Mistral [INST].  The gateway's own /api/chat
-        flattening ("role: content\n...assistant:", ollama.ts:367-370) reaches generate*, not this method."""
+        """messages -> prompt text.  The GGUF's chat template is rendered as Jinja (`_render_jinja`); where that is not possible
+        its FAMILY is recognised from the markers it contains -- what llama.cpp's template detection does [external] -- and the
+        family's framing applied: Llama-3 headers (also the default without a template), ChatML, Llama-2 / Mistral [INST].
+        The gateway's own /api/chat flattening ("role: content\n...assistant:", ollama.ts:367-370) reaches generate*, not this method."""
         try:
             tmpl = eng.chat_template or ""
         except Exception:
             tmpl = ""
+        if tmpl and self._jinja:
+            rendered = self._render_jinja(eng, tmpl, messages)
+            if rendered is not None:
+                return rendered
         msgs = [(m.get("role", "user"), m.get("content", "")) for m in messages]
         if "<|im_start|>" in tmpl:                       # ChatML
             return "".join(f"<|im_start|>{r}\n{c}<|im_end|>\n" for r, c in msgs) + "<|im_start|>assistant\n"

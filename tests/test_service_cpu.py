@@ -133,7 +133,8 @@ def test_workers_shard_requests_like_the_scheduler(tiny_gguf, hostcheck_lib, mon
         assert sched.results[f"job-{i}"]["result"]["token_ids"] == [int(t) for t in ref["ids"]]
 
 
-def test_chat_framing_follows_the_template_family(svc):
+def test_chat_framing_follows_the_template_family(svc, monkeypatch):
+    monkeypatch.setattr(svc, "_jinja", False)               # the fallback path: template FAMILY from its markers
     eng = svc._engine("tiny:latest")
     msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "hi"}, {"role": "assistant", "content": "hello"},
             {"role": "user", "content": "bye"}]
@@ -155,6 +156,50 @@ def test_chat_framing_follows_the_template_family(svc):
         def chat_template(self):
             raise RuntimeError("boom")
     assert svc._chat_prompt(Broken(), msgs[1:2]).startswith("<|start_header_id|>user<|end_header_id|>\n\nhi<|eot_id|>")
+
+
+LLAMA3_TEMPLATE = ("{% set loop_messages = messages %}{% for message in loop_messages %}{% set content = '<|start_header_id|>' + message['role'] + "
+                   "'<|end_header_id|>\n\n'+ message['content'] | trim + '<|eot_id|>' %}{% if loop.index0 == 0 %}{% set content = bos_token + content %}"
+                   "{% endif %}{{ content }}{% endfor %}{% if add_generation_prompt %}{{ '<|start_header_id|>assistant<|end_header_id|>\n\n' }}{% endif %}")
+CHATML_TEMPLATE = ("{% for message in messages %}{{'<|im_start|>' + message['role'] + '\n' + message['content'] + '<|im_end|>' + '\n'}}{% endfor %}"
+                   "{% if add_generation_prompt %}{{ '<|im_start|>assistant\n' }}{% endif %}")
+MISTRAL_TEMPLATE = ("{{ bos_token }}{% for message in messages %}{% if (message['role'] == 'user') != (loop.index0 % 2 == 0) %}"
+                    "{{ raise_exception('Conversation roles must alternate user/assistant/user/assistant/...') }}{% endif %}"
+                    "{% if message['role'] == 'user' %}{{ '[INST] ' + message['content'] + ' [/INST]' }}{% elif message['role'] == 'assistant' %}"
+                    "{{ message['content'] + eos_token}}{% else %}{{ raise_exception('Only user and assistant roles are supported!') }}{% endif %}{% endfor %}")
+
+
+def test_chat_template_is_rendered_as_jinja(svc):
+    """tokenizer.chat_template is a Jinja program: the host renders it (messages, add_generation_prompt, bos_token / eos_token from
+    the GGUF's own vocabulary, raise_exception) as Ollama's runner and HF apply_chat_template do [external]; the published Llama-3,
+    ChatML and Mistral templates give their documented framings, and a template that refuses the conversation falls back to its family."""
+    pytest.importorskip("jinja2")
+    eng = svc._engine("tiny:latest")
+    bos, eos = svc._control_text(eng, eng.info.bos_id), svc._control_text(eng, eng.info.eos_id)
+    assert bos and eos                                       # control tokens have a spelling even though they stream as nothing
+    msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "  hi  "}, {"role": "assistant", "content": "hello"},
+            {"role": "user", "content": "bye"}]
+    eng.chat_template = LLAMA3_TEMPLATE
+    p = svc._chat_prompt(eng, msgs)
+    # content is trimmed by the template itself ("| trim"); the leading BOS text is left to the tokenizer
+    assert p == ("<|start_header_id|>system<|end_header_id|>\n\nbe brief<|eot_id|><|start_header_id|>user<|end_header_id|>\n\nhi<|eot_id|>"
+                 "<|start_header_id|>assistant<|end_header_id|>\n\nhello<|eot_id|><|start_header_id|>user<|end_header_id|>\n\nbye<|eot_id|>"
+                 "<|start_header_id|>assistant<|end_header_id|>\n\n")
+    assert not p.startswith(bos)
+    ids = eng.tokenize(p, add_bos=True, parse_special=True)
+    assert int(ids[0]) == eng.info.bos_id and int(ids[1]) != eng.info.bos_id
+    eng.chat_template = CHATML_TEMPLATE
+    assert svc._chat_prompt(eng, msgs) == ("<|im_start|>system\nbe brief<|im_end|>\n<|im_start|>user\n  hi  <|im_end|>\n<|im_start|>assistant\nhello<|im_end|>\n"
+                                           "<|im_start|>user\nbye<|im_end|>\n<|im_start|>assistant\n")
+    eng.chat_template = MISTRAL_TEMPLATE
+    assert svc._chat_prompt(eng, msgs[1:]) == "[INST]   hi   [/INST]hello" + eos + "[INST] bye [/INST]"
+    # the Mistral template refuses a system role (raise_exception): the family framing folds it into the first user turn
+    assert svc._chat_prompt(eng, msgs) == "[INST] be brief\n\n  hi   [/INST] hello</s>[INST] bye [/INST]"
+    # family only, on request
+    svc._jinja = False
+    eng.chat_template = CHATML_TEMPLATE.replace("{% if add_generation_prompt %}", "{% if false %}")
+    assert svc._chat_prompt(eng, msgs[:2]).endswith("<|im_start|>assistant\n")
+    svc._jinja = True
 
 
 def test_generate_prompts_can_be_framed_like_ollama(tiny_gguf, hostcheck_lib, monkeypatch):

@@ -1,6 +1,7 @@
-"""Prompt-attention probe on the GPU box: the Llama-3-8B-shaped model's batched prefill with the fused attention kernel
-(prefill_attn.cu) and with the three-launch path (GL_PREFILL_FLASH=0), at 512 and 2048 prompt tokens: device time of the
-prompt pass and agreement of the first generated token's logits."""
+"""Prompt-pass probe on the GPU box: the Llama-3-8B-shaped model's batched prefill under a list of switch settings
+(PROBE_VARIANTS="GL_PREFILL_FLASH=1;GL_PREFILL_FLASH=0" by default: the fused attention kernel of prefill_attn.cu against the
+three-launch path; "GL_TC5_PAIR=1;GL_TC5_PAIR=0": CTA-pair GEMM against the one-CTA kernel), at the prompt lengths given on the
+command line: device time of the prompt pass and agreement of the first generated token's logits with the first variant's."""
 import json
 import os
 import sys
@@ -21,20 +22,22 @@ def main():
     for T in lens:
         prompt = np.random.Generator(np.random.PCG64(1000 + T)).integers(0, 128000, size=T)
         ref = None
-        for flash in ("1", "0"):
-            os.environ["GL_PREFILL_FLASH"] = flash
+        for var in os.environ.get("PROBE_VARIANTS", "GL_PREFILL_FLASH=1;GL_PREFILL_FLASH=0").split(";"):
+            for kv in var.split(","):
+                k, v = kv.split("=")
+                os.environ[k] = v
             e = N.Engine(path, max_ctx=T + 16)
             best = 1e9
             for _ in range(3):
                 g = e.generate(prompt, num_predict=2, ignore_eos=True, want_logits=True)
                 best = min(best, g.stats.prompt_eval_duration_ns / 1e6)
             lg = e.last_logits(0).copy()
-            out = {"tokens": T, "flash": flash, "prefill_ms": round(best, 3), "launches": int(g.stats.kernel_launches), "ids": g.ids[:2].tolist(),
+            out = {"tokens": T, "variant": var, "prefill_ms": round(best, 3), "launches": int(g.stats.kernel_launches), "ids": g.ids[:2].tolist(),
                    "finite": bool(np.isfinite(lg).all())}
             if ref is None:
                 ref = lg
             else:
-                out["max_abs_diff_vs_flash"] = float(np.abs(lg - ref).max())
+                out["max_abs_diff_vs_first"] = float(np.abs(lg - ref).max())
                 out["max_abs_logit"] = float(np.abs(ref).max())
             print(json.dumps(out), flush=True)
             e.close()
