@@ -19,7 +19,21 @@ namespace {
 constexpr int TILE_PAGES = 4;
 constexpr int MAX_GRP = 8;
 
-template <int DPL>   // dims per lane = head_dim / 32
+constexpr int MAX_CL = 16;          // splits of one KV head in one thread-block cluster (cluster mode)
+
+__device__ __forceinline__ uint32_t attn_mapa(uint32_t local_smem_addr, uint32_t rank) {      // the same location in CTA `rank` of the cluster
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+    return ra;
+}
+
+// CL = false: partials through global memory, merged by the last CTA of each KV head (atomic ticket).
+// CL = true : the n_splits CTAs of a KV head are ONE thread-block cluster.  Every split sends each rank the slice of its partial
+//             output that rank owns (st.shared::cluster into the rank's receive buffer: distributed shared memory) with its
+//             (max, sum); one cluster barrier; every rank merges its slice of the head group's output -- no global round trip,
+//             no ticket, and the merge is spread over the cluster (the ticket path: partial store 0.9 us + ticket 0.8 us + the
+//             last CTA's 32 partial loads 2.0 us per layer, profiles/r01_run59_perop_timeline.log).
+template <int DPL, bool CL>   // dims per lane = head_dim / 32
 __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_constant__ AttnParams p) {
     constexpr int HD = DPL * 32;
     constexpr int PAGE_ELEMS = KV_PAGE_TOKENS * HD;
@@ -28,6 +42,8 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     __shared__ __align__(128) __half vs[TILE_PAGES * PAGE_ELEMS];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int is_last;
+    __shared__ __align__(16) float rx_o[CL ? MAX_CL : 1][CL ? 128 : 4];      // [split][this rank's slice of the group's output]
+    __shared__ __align__(8) float rx_ml[CL ? MAX_CL : 1][2];                 // [split](max, sum) of the head the slice belongs to
 
     const int kvh = blockIdx.x, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,8 +104,8 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     for (int d = 0; d < DPL; ++d) q[d] *= p.scale;
     const int n_pages = (L + KV_PAGE_TOKENS - 1) / KV_PAGE_TOKENS;
     const int active = min(n_pages, S);
-    if (split >= active) return;                    // (then nothing was staged either: final_pages <= n_pages)
-    const int my_pages = (n_pages - split + S - 1) / S;
+    if (!CL && split >= active) return;             // (then nothing was staged either: final_pages <= n_pages)
+    const int my_pages = split < active ? (n_pages - split + S - 1) / S : 0;      // cluster mode: idle splits stay for the barrier
 
     float m_run = -INFINITY, l_run = 0.f;
     uint32_t ph = 0;
@@ -130,6 +146,35 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
     }
 
     if (tr) tr[2] = globaltimer_ns();
+    if constexpr (CL) {
+        const int G = grp * HD, slice = G / S;      // rank r merges outputs [r * slice, (r + 1) * slice) of this KV head's group
+        if (split < active) {
+            const int f = warp * HD + lane * DPL;   // this lane's dims in the group's flat output
+            const uint32_t dst = attn_mapa(smem_u32(&rx_o[split][f % slice]), (uint32_t)(f / slice));
+            if (DPL == 4) asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o[0]), "f"(o[1]), "f"(o[DPL - 2]), "f"(o[DPL - 1]) : "memory");
+            else asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(o[0]), "f"(o[1]) : "memory");
+            const int per_head = HD / slice;        // ranks that hold slices of this warp's head
+            if (lane < per_head) {
+                const uint32_t dml = attn_mapa(smem_u32(&rx_ml[split][0]), (uint32_t)(warp * per_head + lane));
+                asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dml), "f"(m_run), "f"(l_run) : "memory");
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        const int t = threadIdx.x;
+        if (t < slice) {
+            float M = -INFINITY;
+            for (int sp = 0; sp < active; ++sp) M = fmaxf(M, rx_ml[sp][0]);
+            float acc = 0.f, den = 0.f;
+            for (int sp = 0; sp < active; ++sp) {   // splits in order: deterministic
+                const float w = expf(rx_ml[sp][0] - M);
+                den += w * rx_ml[sp][1];
+                acc += w * rx_o[sp][t];
+            }
+            p.out[(size_t)kvh * G + split * slice + t] = acc / den;
+        }
+        return;
+    }
     if (active == 1) {
         const float inv = 1.0f / l_run;
         float* out = p.out + (size_t)head * HD + lane * DPL;
@@ -164,21 +209,52 @@ __global__ void __launch_bounds__(32 * MAX_GRP) attn_decode_kernel(const __grid_
 
 }  // namespace
 
+// cluster mode needs: 8 or 16 splits (16 = a non-portable cluster size), and a slice of the group's output per rank that lies
+// inside one head and is at least one lane's dims wide
+bool attn_cluster_ok(int n_head, int n_kv_heads, int head_dim, int n_splits) {
+    if (n_kv_heads < 1 || n_head % n_kv_heads || (n_splits != 8 && n_splits != 16)) return false;
+    const int grp = n_head / n_kv_heads, G = grp * head_dim;
+    if (grp > MAX_GRP || G % n_splits) return false;
+    const int slice = G / n_splits, dpl = head_dim / 32;
+    return slice <= head_dim && head_dim % slice == 0 && slice % dpl == 0 && slice <= 32 * grp && slice <= 128;
+}
+
+cudaError_t attn_decode_configure() {
+    cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<4, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_decode_kernel<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return e;
+}
+
 cudaError_t attn_decode_launch(const AttnParams& p, bool pdl, cudaStream_t s) {
     const int grp = p.n_head / p.n_kv_heads;
     if (grp < 1 || grp > MAX_GRP || p.n_head % p.n_kv_heads || p.n_splits < 1 || p.n_splits > 32) return cudaErrorInvalidValue;
+    if (p.cluster && !attn_cluster_ok(p.n_head, p.n_kv_heads, p.head_dim, p.n_splits)) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)p.n_kv_heads, (unsigned)p.n_splits);
     cfg.blockDim = dim3(32u * grp);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.cluster) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = (unsigned)p.n_splits; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    if (p.head_dim == 128) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<4>, p);
-    if (p.head_dim == 64) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<2>, p);
+    cfg.numAttrs = na;
+    if (p.cluster) {
+        if (p.head_dim == 128) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<4, true>, p);
+        if (p.head_dim == 64) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<2, true>, p);
+        return cudaErrorInvalidValue;
+    }
+    if (p.head_dim == 128) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<4, false>, p);
+    if (p.head_dim == 64) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<2, false>, p);
     return cudaErrorInvalidValue;
 }
 

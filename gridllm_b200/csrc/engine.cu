@@ -177,10 +177,13 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     sampler_pdl_ = env_int("GL_SAMPLER_PDL", 0) != 0;
     greedy_pdl_ = env_int("GL_GREEDY_PDL", 0) != 0;
     attn_splits_ = std::max(1, std::min(32, env_int("GL_ATTN_SPLITS", 32)));
+    attn_cluster_ = env_int("GL_ATTN_CLUSTER", 0) != 0;      // the splits of a KV head as one thread-block cluster (attention.cu); needs 8 / 16 splits
+    if (attn_cluster_ && attn_splits_ != 8 && attn_splits_ != 16) attn_splits_ = 16;
     prefill_mode_ = env_int("GL_PREFILL", opts ? opts->prefill_mode : 0);
     prefill_min_ = env_int("GL_PREFILL_MIN", 8);
     prefill_tc5_ = env_int("GL_PREFILL_TC5", 1) != 0;
     prefill_flash_ = env_int("GL_PREFILL_FLASH", 1) != 0;
+    prefill_fuse_rope_ = env_int("GL_PREFILL_FUSE_ROPE", 1) != 0;
 
     std::string err = gguf_.open(path);
     if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);
@@ -231,6 +234,8 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(prefill_configure());
     CU(gemm_tc5_configure());
     CU(flash_prefill_configure());
+    CU(attn_decode_configure());
+    if (attn_cluster_ && !attn_cluster_ok(n_head_, n_kv_, hd_, attn_splits_)) attn_cluster_ = false;      // shapes the slices do not fit: the ticket path
 
     // ---- weights -> HBM -------------------------------------------------------------------------
     ST(upload_matrix(*te, tok_embd_, /*native=*/true));
@@ -547,6 +552,7 @@ Status Engine::enqueue_step(cudaStream_t s, bool with_head, bool keep_logits, in
             a.q = q_; a.k_cache = kc; a.v_cache = vc; a.page_table = page_table_; a.n_table = n_pages_; a.st = st_; a.out = attn_;
             a.part_o = part_o_; a.part_ml = part_ml_; a.counters = counters_;
             a.n_head = n_head_; a.n_kv_heads = n_kv_; a.head_dim = hd_; a.n_splits = attn_splits_; a.scale = scale;
+            a.cluster = attn_cluster_ ? 1 : 0;
             a.trace = perop_trace_ ? perop_trace_ + 16 * (size_t)std::min(*n_launch, PEROP_TRACE_LAUNCHES - 1) : nullptr;
             CU(attn_decode_launch(a, pdl && fused_, s));
             ++*n_launch;

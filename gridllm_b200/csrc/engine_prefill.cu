@@ -108,15 +108,24 @@ Status Engine::prefill_batched(int n, int* n_launch) {
         __half* kc = kcache_ + (size_t)il * kv_layer_elems_;
         __half* vc = vcache_ + (size_t)il * kv_layer_elems_;
         CU(rmsnorm_rows_launch(pf_x_, L.attn_norm, T, TP, n_embd_, eps_, pf_xn_, bf, s)); ++nl;
+        bool roped = false;
         {
             GemmParams g{};
             g.a = pf_xn_; g.b = L.wqkv16; g.c = pf_qkv_; g.m = T; g.n = ldq; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = ldq;
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
-            CU(linear(g)); ++nl;
+            RopeSplitArgs ra{rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, n_head_, n_kv_, hd_, tp, segs};
+            if (prefill_flash_ && prefill_fuse_rope_ && prefill_tc5_) {
+                // RoPE + split + cache append in the projection's own epilogue: the fp32 QKV matrix never exists (rows T .. TP of
+                // the normalised activations are zeros; the epilogue writes them as padding rows)
+                GemmParams gr = g;
+                gr.epi = GEMM_EPI_ROPE_SPLIT; gr.rope = &ra; gr.m = TP;
+                if (gemm_tc5_supported(gr)) { CU(gemm_tc5_launch(gr, tp, bf, s)); ++nl; roped = true; }
+            }
+            if (!roped) { CU(linear(g)); ++nl; }
         }
         if (prefill_flash_) {
-            // RoPE + split + cache append, then ONE fused attention launch (prefill_attn.cu): scores stay on the SM
-            CU(rope_split_segs_launch(pf_qkv_, TP, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, tp, segs, s)); ++nl;
+            // (RoPE + split + cache append, then) ONE fused attention launch (prefill_attn.cu): scores stay on the SM
+            if (!roped) { CU(rope_split_segs_launch(pf_qkv_, TP, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, tp, segs, s)); ++nl; }
             CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s)); ++nl;
         } else {
             CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, tp, s)); ++nl;
@@ -188,11 +197,24 @@ Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<
         __half* kc = tables ? kcache_ + (size_t)il * kv_layer_elems_ : nullptr;      // gl_seq_open_many: each sequence's K / V rows go
         __half* vc = tables ? vcache_ + (size_t)il * kv_layer_elems_ : nullptr;      // to its own pages; embeddings cache nothing
         CU(rmsnorm_rows_launch(pf_x_, L.attn_norm, TP, TP, n_embd_, eps_, pf_xn_, bf, s)); ++nl;
+        bool roped = false;
         {
             GemmParams g{};
             g.a = pf_xn_; g.b = L.wqkv16; g.c = pf_qkv_; g.m = TP; g.n = ldq; g.k = n_embd_; g.lda = n_embd_; g.ldb = n_embd_; g.ldc = ldq;
             g.batch = 1; g.b_batch_div = 1; g.epi = GEMM_EPI_F32;
-            CU(linear(g)); ++nl;
+            RopeSplitArgs ra{rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, n_head_, n_kv_, hd_, tp, {}};
+            if (prefill_flash_ && prefill_fuse_rope_ && prefill_tc5_ && starts.size() <= (size_t)PF_MAX_SEGS) {
+                ra.segs.n = (int)starts.size();
+                for (int i = 0; i < ra.segs.n; ++i) {
+                    ra.segs.start[i] = starts[i];
+                    ra.segs.len[i] = lens[i];
+                    ra.segs.table[i] = tables ? (*tables)[i] : nullptr;
+                }
+                GemmParams gr = g;
+                gr.epi = GEMM_EPI_ROPE_SPLIT; gr.rope = &ra;
+                if (gemm_tc5_supported(gr)) { CU(gemm_tc5_launch(gr, tp, bf, s)); ++nl; roped = true; }
+            }
+            if (!roped) { CU(linear(g)); ++nl; }
         }
         if (prefill_flash_) {
             // the whole pack: one RoPE / split launch and one fused attention launch per PF_MAX_SEGS sequences
@@ -208,10 +230,12 @@ Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<
                 }
                 if (c0 + PF_MAX_SEGS >= starts.size()) row_hi = std::max(row_hi, TP);      // trailing rows of the pack are zeroed too
                 // the kernel indexes rows of the pack absolutely: shift the segment starts to the chunk's first row
-                PrefillSegs rs = segs;
-                for (int i = 0; i < rs.n; ++i) rs.start[i] -= row_lo;
-                CU(rope_split_segs_launch(pf_qkv_ + (size_t)row_lo * ldq, row_hi - row_lo, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_ + (size_t)row_lo * qd,
-                                          pf_k_ + (size_t)row_lo * kvd, pf_vt_ + row_lo, kc, vc, tp, rs, s)); ++nl;
+                if (!roped) {
+                    PrefillSegs rs = segs;
+                    for (int i = 0; i < rs.n; ++i) rs.start[i] -= row_lo;
+                    CU(rope_split_segs_launch(pf_qkv_ + (size_t)row_lo * ldq, row_hi - row_lo, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_ + (size_t)row_lo * qd,
+                                              pf_k_ + (size_t)row_lo * kvd, pf_vt_ + row_lo, kc, vc, tp, rs, s)); ++nl;
+                }
                 CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s)); ++nl;
             }
         } else

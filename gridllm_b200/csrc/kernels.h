@@ -117,8 +117,11 @@ struct AttnParams {
     int n_head, n_kv_heads, head_dim, n_splits;
     float scale;
     unsigned long long* trace;   // optional (GL_TRACE=1): [2 CTAs][8] %globaltimer stamps
+    int cluster;            // 1: the splits of a KV head form one thread-block cluster and merge through distributed shared memory
 };
 cudaError_t attn_decode_launch(const AttnParams& p, bool pdl, cudaStream_t s);
+cudaError_t attn_decode_configure();
+bool attn_cluster_ok(int n_head, int n_kv_heads, int head_dim, int n_splits);
 
 struct SampleParams {
     const float* logits;

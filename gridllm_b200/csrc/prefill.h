@@ -11,6 +11,29 @@ enum GemmEpilogue : int {
     GEMM_EPI_ADD_F32 = 1,  // C fp32 += acc                 (residual add in place)
     GEMM_EPI_T16 = 2,      // C 16-bit = acc
     GEMM_EPI_SILU = 3,     // B rows interleaved [8 gate | 8 up]: C16[m][col] = silu(gate) * up
+    GEMM_EPI_ROPE_SPLIT = 4,  // the QKV projection: RoPE on the q / k columns, 16-bit Q / K rows, V^T columns, fp16 cache pages (tcgen05 path only)
+};
+
+// The sequences of one prompt pass: sequence i owns rows [start[i], start[i] + len[i]) of the packed activation matrix (starts at
+// 128-row boundaries); table[i] = its KV page table on the device (null: nothing is cached).
+constexpr int PF_MAX_SEGS = 32;
+struct PrefillSegs {
+    int n;
+    int start[PF_MAX_SEGS];
+    int len[PF_MAX_SEGS];
+    const int* table[PF_MAX_SEGS];
+};
+// what GEMM_EPI_ROPE_SPLIT writes instead of C (the arguments of rope_split_segs_launch, which it replaces)
+struct RopeSplitArgs {
+    const float* cos_t;
+    const float* sin_t;
+    __half* q;          // [rows][n_head * hd]
+    __half* k;          // [rows][n_kv * hd]
+    __half* vt;         // [n_kv * hd][vt_ld]
+    __half* k_cache;    // this layer's pages, or null
+    __half* v_cache;
+    int n_head, n_kv, hd, vt_ld;
+    PrefillSegs segs;
 };
 
 // C[M x N] = A[M x K] * B[N x K]^T, 16-bit inputs (fp16 or bf16), fp32 accumulate; strides in ELEMENTS.
@@ -28,6 +51,7 @@ struct GemmParams {
     int epi;
     int causal_skip;           // 1: skip tiles entirely above the diagonal (S = Q K^T)
     int causal_k;              // 1: limit K to the last row of the tile + 1 (O = P V, P lower-triangular)
+    const RopeSplitArgs* rope; // GEMM_EPI_ROPE_SPLIT: where the rotated / split rows go (host pointer, copied into the launch)
 };
 
 cudaError_t prefill_configure();   // per device: opt in to the GEMM's dynamic shared memory
@@ -43,15 +67,6 @@ cudaError_t rope_split_launch(const float* qkv, int t_rows, int t_pad, int pos0,
                               const float* sin_t, __half* qo, __half* ko, __half* vt, __half* k_cache, __half* v_cache,
                               const int* page_table, int vt_ld /* row stride of vt; k_cache may be null (nothing cached) */, cudaStream_t s);
 // ---- fused prompt attention (prefill_attn.cu) --------------------------------------------------------------------
-// The sequences of one pass: sequence i owns rows [start[i], start[i] + len[i]) of the packed activation matrix (starts at
-// 128-row boundaries); table[i] = its KV page table on the device (null: nothing is cached).
-constexpr int PF_MAX_SEGS = 32;
-struct PrefillSegs {
-    int n;
-    int start[PF_MAX_SEGS];
-    int len[PF_MAX_SEGS];
-    const int* table[PF_MAX_SEGS];
-};
 cudaError_t flash_prefill_configure();
 bool flash_prefill_supported(int hd);
 // out[rows][n_head * hd] = causal softmax(q k^T * scale) v per sequence and head; q / k rows, vt = V^T [n_kv * hd][vt_ld]

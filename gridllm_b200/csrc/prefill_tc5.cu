@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "kernels.h"
 #include "prefill.h"
 
 namespace gl {
@@ -58,6 +59,7 @@ struct Tc5Params {
     int m, n, k, ldc;
     int epi;
     int bf16;
+    RopeSplitArgs rope;  // GEMM_EPI_ROPE_SPLIT only
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -203,6 +205,62 @@ __device__ __forceinline__ void epilogue_row(const Tc5Params& p, int row, int co
     }
 }
 
+// GEMM_EPI_ROPE_SPLIT: 32 consecutive columns of one row of the QKV projection, straight from the accumulator -- what the
+// stand-alone RoPE / split kernel did after a round trip of the fp32 QKV matrix through HBM (50 MB written + 50 MB read per
+// layer at 2 048 rows).  pos < 0: a padding row (zeros: finite operands for the padded attention tiles).  The q / k / v
+// regions and the heads are multiples of 32 columns wide, so a chunk never straddles two of them.
+__device__ __forceinline__ void epilogue_rope_split(const RopeSplitArgs& a, int row, int pos, const int* page_table, int col0, const uint32_t* v) {
+    const int qd = a.n_head * a.hd, kvd = a.n_kv * a.hd;
+    const bool cache = pos >= 0 && a.k_cache != nullptr && page_table != nullptr;
+    size_t cache_off = 0;
+    if (cache) {
+        const int kvcol = col0 < qd + kvd ? col0 - qd : col0 - qd - kvd;      // (only used for the k / v regions)
+        cache_off = (((size_t)__ldg(page_table + pos / KV_PAGE_TOKENS) * a.n_kv + (kvcol >= 0 ? kvcol / a.hd : 0)) * KV_PAGE_TOKENS + pos % KV_PAGE_TOKENS) * a.hd +
+                    (kvcol >= 0 ? kvcol % a.hd : 0);
+    }
+    if (col0 < qd + kvd) {
+        __align__(16) __half2 o[16];
+        if (pos >= 0) {
+            const int d0 = col0 % a.hd;
+            const float4* c4 = reinterpret_cast<const float4*>(a.cos_t + (size_t)pos * (a.hd / 2) + d0 / 2);
+            const float4* s4 = reinterpret_cast<const float4*>(a.sin_t + (size_t)pos * (a.hd / 2) + d0 / 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
+                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float x0 = __uint_as_float(v[8 * i + 2 * e]), x1 = __uint_as_float(v[8 * i + 2 * e + 1]);
+                    o[4 * i + e] = __floats2half2_rn(x0 * cc[e] - x1 * ss[e], x0 * ss[e] + x1 * cc[e]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __floats2half2_rn(0.f, 0.f);
+        }
+        __half* dst = col0 < qd ? a.q + (size_t)row * qd + col0 : a.k + (size_t)row * kvd + (col0 - qd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(o)[i];
+        if (cache && col0 >= qd) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(a.k_cache + cache_off)[i] = reinterpret_cast<const uint4*>(o)[i];
+        }
+    } else {
+        // V: the warp's 32 lanes are 32 consecutive rows = 64 contiguous bytes of one V^T row per store instruction
+        const int c0 = col0 - qd - kvd;
+        __align__(16) __half hv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            hv[j] = __float2half_rn(pos >= 0 ? __uint_as_float(v[j]) : 0.f);
+            a.vt[(size_t)(c0 + j) * a.vt_ld + row] = hv[j];
+        }
+        if (cache) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(a.v_cache + cache_off)[i] = reinterpret_cast<const uint4*>(hv)[i];
+        }
+    }
+}
+
 template <int BN, int PAIR>
 __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ Tc5Params p) {
     using Cfg = Tc5Cfg<BN, PAIR>;
@@ -339,13 +397,25 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) gemm_tc5_kernel(const __grid_c
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
             tc5_fence_after();
             const int row = m0 + q * 32 + lane;
+            int pos = -1;                               // GEMM_EPI_ROPE_SPLIT: the row's position inside its sequence (-1: padding)
+            const int* page_table = nullptr;
+            if (p.epi == GEMM_EPI_ROPE_SPLIT) {
+                for (int i = 0; i < p.rope.segs.n; ++i) {
+                    const int st = p.rope.segs.start[i], ln = p.rope.segs.len[i];
+                    if (row >= st && row < st + (ln + 127) / 128 * 128) {
+                        pos = row - st < ln ? row - st : -1;
+                        page_table = p.rope.segs.table[i];
+                    }
+                }
+            }
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
                 const int col0 = n0 + c * 32;
                 if (row < p.m && col0 < p.n) {
-                    if (p.bf16) epilogue_row<__nv_bfloat16>(p, row, col0, v);
+                    if (p.epi == GEMM_EPI_ROPE_SPLIT) epilogue_rope_split(p.rope, row, pos, page_table, col0, v);
+                    else if (p.bf16) epilogue_row<__nv_bfloat16>(p, row, col0, v);
                     else epilogue_row<__half>(p, row, col0, v);
                 }
             }
@@ -403,6 +473,10 @@ cudaError_t gemm_tc5_configure() {
 
 bool gemm_tc5_supported(const GemmParams& p) {
     // plain (un-batched, non-causal) TN GEMMs whose rows TMA can address: 16-byte aligned bases and row strides
+    if (p.epi == GEMM_EPI_ROPE_SPLIT) {
+        const RopeSplitArgs* r = p.rope;
+        if (!r || (r->hd % 32) || p.n != (r->n_head + 2 * r->n_kv) * r->hd || (p.m % 128) || (r->vt_ld & 7) || r->segs.n < 1 || r->segs.n > PF_MAX_SEGS) return false;
+    }
     return p.batch == 1 && !p.causal_skip && !p.causal_k && (p.lda % 8) == 0 && (p.ldb % 8) == 0 && (p.k % 8) == 0 &&
            ((uintptr_t)p.a % 16) == 0 && ((uintptr_t)p.b % 16) == 0 && (p.epi != GEMM_EPI_SILU || (p.n % 16) == 0);
 }
@@ -413,6 +487,7 @@ cudaError_t gemm_tc5_launch(const GemmParams& p, int a_rows_alloc, bool bf16, cu
     Tc5Params tp{};
     if (!make_map(&tp.ta, p.a, a_rows_alloc, p.k, p.lda, bf16) || !make_map(&tp.tb, p.b, p.n, p.k, p.ldb, bf16)) return cudaErrorInvalidValue;
     tp.c = p.c; tp.m = p.m; tp.n = p.n; tp.k = p.k; tp.ldc = p.ldc; tp.epi = p.epi; tp.bf16 = bf16 ? 1 : 0;
+    if (p.epi == GEMM_EPI_ROPE_SPLIT) tp.rope = *p.rope;
     // persistent grid: one CTA per SM walks the tiles, M tiles fastest (the CTAs that share a weight tile run together)
     static const int n_sm = []() { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
     static const bool persist = []() { const char* e = getenv("GL_TC5_PERSIST"); return !(e && e[0] == '0'); }();

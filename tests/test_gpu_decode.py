@@ -239,6 +239,31 @@ def test_fused_prompt_attention_equals_three_launch_path(fixture, n_tok, request
     assert np.abs(d1 - d0).max() <= 2e-3 * np.abs(d0).max()
 
 
+@pytest.mark.parametrize("fixture", ["tiny_gguf", "tiny128_gguf"])
+@pytest.mark.parametrize("n_tok", [37, 300])
+def test_rope_split_in_the_qkv_epilogue_equals_the_kernel(fixture, n_tok, request, monkeypatch):
+    """GEMM_EPI_ROPE_SPLIT (RoPE, Q / K / V^T split and the fp16 cache append out of the QKV projection's accumulator) against
+    the stand-alone kernel reading the fp32 QKV matrix (GL_PREFILL_FUSE_ROPE=0): same arithmetic on the same accumulators --
+    2e-3 * max|logit| covers a different fused-multiply-add contraction; the decode step that follows reads the cached K / V."""
+    from oracle import llama_oracle as O
+    path = request.getfixturevalue(fixture)
+    m = O.load_gguf(path)
+    toks = np.random.Generator(np.random.PCG64(7000 + n_tok)).integers(0, m.n_vocab - 3, size=n_tok)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GL_PREFILL_FUSE_ROPE", mode)
+        e = _engine(path, prefill_mode=0)
+        lg = e.prefill(toks)
+        nxt = int(np.argmax(lg)) if mode == "1" else out["1"][2]
+        dg, _, _ = e.decode_step(nxt)
+        out[mode] = (lg, dg, nxt)
+        e.close()
+    scale = np.abs(out["0"][0]).max()
+    assert np.isfinite(out["1"][0]).all() and np.isfinite(out["1"][1]).all()
+    assert np.abs(out["1"][0] - out["0"][0]).max() <= 2e-3 * scale, (fixture, n_tok, np.abs(out["1"][0] - out["0"][0]).max(), scale)
+    assert np.abs(out["1"][1] - out["0"][1]).max() <= 2e-3 * np.abs(out["0"][1]).max()
+
+
 @pytest.mark.parametrize("n_tok", [129, 300, 520])
 def test_cta_pair_gemm_equals_single_cta_gemm(wide_ffn_gguf, n_tok, monkeypatch):
     """tcgen05.mma.cta_group::2 (256 x 256 tiles on two SMs, GL_TC5_PAIR=2: wherever the shape allows) against the one-CTA kernel: same operands, same K
@@ -294,6 +319,44 @@ def test_long_context_decode(tiny128_gguf):
         lg = e.last_logits(i)
         assert np.isfinite(lg).all()
         assert np.abs(lg - ref["logits"][i]).max() <= 1e-2 * np.abs(ref["logits"][i]).max(), i
+        if g.ids[i] != ref["ids"][i]:
+            assert ref["margins"][i] <= 5e-2
+            break
+    e.close()
+
+
+@pytest.mark.parametrize("fixture", ["tiny_gguf", "tiny128_gguf"])          # GQA group 2 / head dim 64 and group 4 / head dim 128
+@pytest.mark.parametrize("splits", [8, 16])
+def test_cluster_attention_matches_oracle(fixture, splits, request, monkeypatch):
+    """GL_ATTN_CLUSTER=1: the splits of a KV head are one thread-block cluster (8 portable, 16 opt-in) and merge their partials
+    through distributed shared memory instead of global partials + an atomic ticket.  Short contexts (idle splits still join the
+    cluster barrier), a page boundary, and a context of more pages than one staging tile per split; same tolerances as the
+    ticket path."""
+    from oracle import llama_oracle as O
+    path = request.getfixturevalue(fixture)
+    m = O.load_gguf(path)
+    monkeypatch.setenv("GL_ATTN_CLUSTER", "1")
+    monkeypatch.setenv("GL_ATTN_SPLITS", str(splits))
+    e = _engine(path)
+    orc = O.LlamaOracle(m, act="i16", kv_f16=True)
+    toks = np.random.Generator(np.random.PCG64(1000)).integers(0, m.n_vocab - 3, size=40)
+    for i, t in enumerate(toks):
+        logits, am, lp = e.decode_step(int(t))
+        ref = orc.step(int(t))
+        assert np.isfinite(logits).all()
+        assert np.abs(logits - ref).max() <= 2e-3 * np.abs(ref).max(), (fixture, splits, i)
+    e.close()
+    # 700 cached positions = 44 pages: 3 - 6 pages per split, i.e. a second staging tile at 8 splits (the 512-context model: 450)
+    n_long = 700 if fixture == "tiny128_gguf" else 450
+    e = _engine(path, max_ctx=1024 if fixture == "tiny128_gguf" else 512)
+    orc = O.LlamaOracle(m, act="exact", kv_f16=True)
+    prompt = np.random.Generator(np.random.PCG64(78)).integers(0, m.n_vocab - 3, size=n_long)
+    ref = orc.generate(prompt, 12)
+    g = e.generate(prompt, num_predict=12, ignore_eos=True, want_logits=True)
+    for i in range(12):
+        lg = e.last_logits(i)
+        assert np.isfinite(lg).all()
+        assert np.abs(lg - ref["logits"][i]).max() <= 1e-2 * np.abs(ref["logits"][i]).max(), (fixture, splits, i)
         if g.ids[i] != ref["ids"][i]:
             assert ref["margins"][i] <= 5e-2
             break
