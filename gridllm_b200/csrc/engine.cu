@@ -184,6 +184,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     prefill_tc5_ = env_int("GL_PREFILL_TC5", 1) != 0;
     prefill_flash_ = env_int("GL_PREFILL_FLASH", 1) != 0;
     prefill_fuse_rope_ = env_int("GL_PREFILL_FUSE_ROPE", 1) != 0;
+    prefill_attn_tc5_ = env_int("GL_PREFILL_ATTN_TC5", 0) != 0;
 
     std::string err = gguf_.open(path);
     if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);
@@ -234,6 +235,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     CU(prefill_configure());
     CU(gemm_tc5_configure());
     CU(flash_prefill_configure());
+    CU(flash_tc5_configure());
     CU(attn_decode_configure());
     if (attn_cluster_ && !attn_cluster_ok(n_head_, n_kv_, hd_, attn_splits_)) attn_cluster_ = false;      // shapes the slices do not fit: the ticket path
 

@@ -126,7 +126,9 @@ Status Engine::prefill_batched(int n, int* n_launch) {
         if (prefill_flash_) {
             // (RoPE + split + cache append, then) ONE fused attention launch (prefill_attn.cu): scores stay on the SM
             if (!roped) { CU(rope_split_segs_launch(pf_qkv_, TP, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, tp, segs, s)); ++nl; }
-            CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s)); ++nl;
+            if (prefill_attn_tc5_ && flash_tc5_supported(hd_)) CU(flash_tc5_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, tp, scale, s));
+            else CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s));
+            ++nl;
         } else {
             CU(rope_split_launch(pf_qkv_, T, tp, 0, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_, pf_k_, pf_vt_, kc, vc, page_table_, tp, s)); ++nl;
             {   // S[h] = Q_h K_kvh^T
@@ -236,7 +238,9 @@ Status Engine::prefill_packed(const std::vector<int>& starts, const std::vector<
                     CU(rope_split_segs_launch(pf_qkv_ + (size_t)row_lo * ldq, row_hi - row_lo, n_head_, n_kv_, hd_, rope_cos_, rope_sin_, pf_q_ + (size_t)row_lo * qd,
                                               pf_k_ + (size_t)row_lo * kvd, pf_vt_ + row_lo, kc, vc, tp, rs, s)); ++nl;
                 }
-                CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s)); ++nl;
+                if (prefill_attn_tc5_ && flash_tc5_supported(hd_)) CU(flash_tc5_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, tp, scale, s));
+                else CU(flash_prefill_launch(pf_q_, pf_k_, pf_vt_, (__half*)pf_attn_, segs, n_head_, n_kv_, hd_, tp, scale, s));
+                ++nl;
             }
         } else
         for (size_t i = 0; i < starts.size(); ++i) {

@@ -72,6 +72,12 @@ bool flash_prefill_supported(int hd);
 // out[rows][n_head * hd] = causal softmax(q k^T * scale) v per sequence and head; q / k rows, vt = V^T [n_kv * hd][vt_ld]
 cudaError_t flash_prefill_launch(const __half* q, const __half* k, const __half* vt, __half* out, const PrefillSegs& segs, int n_head, int n_kv,
                                  int hd, int vt_ld, float scale, cudaStream_t s);
+// the same on tcgen05 (prefill_attn_tc5.cu; head dim 128): scores, probabilities and the output accumulator in tensor memory.
+// rows_alloc = rows of q / k (columns of vt) that exist in memory (TMA reads beyond them as zeros)
+cudaError_t flash_tc5_configure();
+bool flash_tc5_supported(int hd);
+cudaError_t flash_tc5_launch(const __half* q, const __half* k, const __half* vt, __half* out, const PrefillSegs& segs, int n_head, int n_kv, int hd,
+                             int vt_ld, int rows_alloc, float scale, cudaStream_t s);
 // rope_split for every sequence of a pack in one launch (rows_pad = rows of the pack, padding rows are zeroed)
 cudaError_t rope_split_segs_launch(const float* qkv, int rows_pad, int n_head, int n_kv, int hd, const float* cos_t, const float* sin_t, __half* qo,
                                    __half* ko, __half* vt, __half* k_cache, __half* v_cache, int vt_ld, const PrefillSegs& segs, cudaStream_t s);

@@ -239,6 +239,28 @@ def test_fused_prompt_attention_equals_three_launch_path(fixture, n_tok, request
     assert np.abs(d1 - d0).max() <= 2e-3 * np.abs(d0).max()
 
 
+@pytest.mark.parametrize("n_tok", [37, 128, 300, 700])
+def test_tcgen05_prompt_attention_equals_the_mma_sync_kernel(tiny128_gguf, n_tok, monkeypatch):
+    """prefill_attn_tc5.cu (S, P and O in tensor memory, tcgen05.mma with the probabilities as the TMEM A operand,
+    GL_PREFILL_ATTN_TC5=1) against prefill_attn.cu's mma.sync kernel on the same q / k / v bits: both round P to fp16 and sum the
+    rounded values; KV tiles are 128 instead of 64 rows, so the online-softmax rescaling points differ -- 2e-3 * max|logit|.
+    1 .. 6 query tiles: one KV tile (diagonal only), both TMEM score buffers in use, the third tile re-using the first buffer."""
+    from oracle import llama_oracle as O
+    m = O.load_gguf(tiny128_gguf)
+    toks = np.random.Generator(np.random.PCG64(8000 + n_tok)).integers(0, m.n_vocab - 3, size=n_tok)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GL_PREFILL_ATTN_TC5", mode)
+        e = _engine(tiny128_gguf, prefill_mode=0, max_ctx=1024)
+        for _ in range(2):                                   # twice: barriers / TMEM are set up per launch
+            e.kv_reset()
+            out[mode] = e.prefill(toks)
+        e.close()
+    scale = np.abs(out["0"]).max()
+    assert np.isfinite(out["1"]).all()
+    assert np.abs(out["1"] - out["0"]).max() <= 2e-3 * scale, (n_tok, np.abs(out["1"] - out["0"]).max(), scale)
+
+
 @pytest.mark.parametrize("fixture", ["tiny_gguf", "tiny128_gguf"])
 @pytest.mark.parametrize("n_tok", [37, 300])
 def test_rope_split_in_the_qkv_epilogue_equals_the_kernel(fixture, n_tok, request, monkeypatch):
