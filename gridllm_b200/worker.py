@@ -112,8 +112,14 @@ class NativeWorker:
 
     async def drain(self) -> None:
         """wait for the jobs this worker holds (max_concurrent > 1 runs them as tasks)"""
+        # A task that has finished leaves `_tasks` through its done-callback, which runs one loop iteration AFTER the task completes.
+        # gather() of tasks that are all done already returns a completed future and awaiting it does not yield: without the explicit
+        # pruning and the sleep(0) below this loop spun for ever when drain() was entered in that one-iteration window (found on two
+        # GPUs with the 1 s dispatch tick: the event loop never got to run the callbacks).
         while self._tasks:
             await asyncio.gather(*list(self._tasks), return_exceptions=True)
+            self._tasks = {t for t in self._tasks if not t.done()}
+            await asyncio.sleep(0)
 
     async def stop(self) -> None:
         await self.drain()

@@ -377,6 +377,27 @@ def test_num_predict_minus_one_runs_until_the_context_is_full(svc):
     assert res["eval_count"] == eng.info.n_ctx - len(ids) and res["done_reason"] == "length"
 
 
+@pytest.mark.timeout(30)
+def test_drain_does_not_spin_on_tasks_that_finished_a_moment_ago(svc):
+    """NativeWorker.drain() entered while a job task is done but its done-callback (which removes it from the worker's task set) has
+    not run yet: gather() of finished tasks completes without yielding, so the loop must prune and yield itself -- it used to spin
+    for ever (bench.py --workload config3 --gpus 2, 1 s dispatch tick)."""
+    from gridllm_b200.worker import LocalBus, NativeWorker
+    w = NativeWorker("b200-0", svc, LocalBus(), max_concurrent=4)
+
+    async def go():
+        async def job():
+            return None
+        t = asyncio.get_running_loop().create_task(job())
+        w._tasks.add(t)
+        t.add_done_callback(w._tasks.discard)
+        await asyncio.sleep(0)          # the task's only step and this coroutine's resumption run in the same loop iteration
+        assert t.done() and t in w._tasks
+        await w.drain()
+        assert not w._tasks
+    _run(go())
+
+
 # ---- continuous batching on the host side (gridllm_b200/batching.py): concurrent requests share the engine's batched step ----
 @pytest.fixture()
 def bsvc(tiny_gguf, hostcheck_lib, monkeypatch):
