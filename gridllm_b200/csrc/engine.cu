@@ -184,7 +184,7 @@ Status Engine::load(const std::string& path, int device, const gl_engine_opts* o
     prefill_tc5_ = env_int("GL_PREFILL_TC5", 1) != 0;
     prefill_flash_ = env_int("GL_PREFILL_FLASH", 1) != 0;
     prefill_fuse_rope_ = env_int("GL_PREFILL_FUSE_ROPE", 1) != 0;
-    prefill_attn_tc5_ = env_int("GL_PREFILL_ATTN_TC5", 0) != 0;
+    prefill_attn_tc5_ = env_int("GL_PREFILL_ATTN_TC5", 1) != 0;      // head dim 128; head dim 64 takes the mma.sync kernel
 
     std::string err = gguf_.open(path);
     if (!err.empty()) return fail(err.find("cannot open") == 0 ? GL_ERR_IO : GL_ERR_FORMAT, err);

@@ -143,7 +143,7 @@ private:
     int prefill_mode_ = 0, prefill_min_ = 8;
     bool have_w16_ = false, prefill_bf16_ = false, prefill_tc5_ = true;
     bool prefill_fuse_rope_ = true;  // RoPE / split / cache append in the QKV GEMM's epilogue (GL_PREFILL_FUSE_ROPE=0: the stand-alone kernel)
-    bool prefill_attn_tc5_ = false;  // the fused prompt attention on tcgen05 / tensor memory (prefill_attn_tc5.cu, head dim 128); GL_PREFILL_ATTN_TC5
+    bool prefill_attn_tc5_ = true;   // the fused prompt attention on tcgen05 / tensor memory (prefill_attn_tc5.cu, head dim 128); GL_PREFILL_ATTN_TC5
     bool prefill_flash_ = true;     // fused prompt attention (prefill_attn.cu); GL_PREFILL_FLASH=0: the three-launch path, for A/B runs
     // prefill scratch (grown on demand)
     int pf_cap_ = 0;

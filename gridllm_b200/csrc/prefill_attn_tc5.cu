@@ -240,19 +240,19 @@ __global__ void __launch_bounds__(TA_THREADS, 1) flash_tc5_kernel(const __grid_c
             ta_fence_after();
             const bool diag = (j == n_kt - 1);
             const int col0 = j * TA_BN;
-            // pass 1: the row's maximum over the tile
+            // the row's 128 scores are read from tensor memory ONCE (its read port moves 64 B per cycle: two passes over the tile
+            // cost as many cycles as the tile's 16 MMAs) and stay in registers for the maximum and the exponentials
+            uint32_t v[128];
+            ta_ld32(ts, v);
+            ta_ld32(ts + 32u, v + 32);
+            ta_ld32(ts + 64u, v + 64);
+            ta_ld32(ts + 96u, v + 96);
+            ta_wait_ld();
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[64];
-                ta_ld32(ts + (uint32_t)(c * 64), v);
-                ta_ld32(ts + (uint32_t)(c * 64 + 32), v + 32);
-                ta_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 64; ++e) {
-                    const float s = __uint_as_float(v[e]);
-                    if (!diag || col0 + c * 64 + e <= row) mx = fmaxf(mx, s);
-                }
+            for (int e = 0; e < 128; ++e) {
+                const float s = __uint_as_float(v[e]);
+                if (!diag || col0 + e <= row) mx = fmaxf(mx, s);
             }
             // column 0 of the first tile is never masked: the maximum is finite from the first tile on
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
@@ -263,33 +263,28 @@ __global__ void __launch_bounds__(TA_THREADS, 1) flash_tc5_kernel(const __grid_c
                 ta_fence_after();
                 if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[64];
-                        ta_ld32(lane_base + TA_COL_O + (uint32_t)(c * 64), v);
-                        ta_ld32(lane_base + TA_COL_O + (uint32_t)(c * 64 + 32), v + 32);
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t ov[32];
+                        ta_ld32(lane_base + TA_COL_O + (uint32_t)(c * 32), ov);
                         ta_wait_ld();
 #pragma unroll
-                        for (int e = 0; e < 64; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
-                        ta_st32(lane_base + TA_COL_O + (uint32_t)(c * 64), v);
-                        ta_st32(lane_base + TA_COL_O + (uint32_t)(c * 64 + 32), v + 32);
+                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * corr);
+                        ta_st32(lane_base + TA_COL_O + (uint32_t)(c * 32), ov);
                     }
                 }
             }
             m_run = m_new;
-            // pass 2: P = exp2(s * scale - m) -> fp16 pairs over the first 64 columns of the same buffer; a 32-column chunk of P
-            // (64 positions) is stored after the 64 score columns it comes from have been read, and never past them
+            // P = exp2(s * scale - m) -> fp16 pairs, written over the first 64 columns of the same buffer (every score is in
+            // registers by now)
             float sum = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 2; ++c) {
-                uint32_t w[32], v[64];
-                ta_ld32(ts + (uint32_t)(c * 64), v);
-                ta_ld32(ts + (uint32_t)(c * 64 + 32), v + 32);
-                ta_wait_ld();
+                uint32_t w[32];
 #pragma unroll
                 for (int e = 0; e < 64; e += 2) {
                     const int cc = col0 + c * 64 + e;
-                    float p0 = ta_exp2(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_new));
-                    float p1 = ta_exp2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_new));
+                    float p0 = ta_exp2(fmaf(__uint_as_float(v[c * 64 + e]), p.scale_log2, -m_new));
+                    float p1 = ta_exp2(fmaf(__uint_as_float(v[c * 64 + e + 1]), p.scale_log2, -m_new));
                     if (diag) {
                         if (cc > row) p0 = 0.f;
                         if (cc + 1 > row) p1 = 0.f;
