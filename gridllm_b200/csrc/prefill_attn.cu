@@ -4,11 +4,10 @@
 // at 2 048 tokens) on the path behind OllamaService.generate*Response / generateEmbedding
 // (/root/reference/client/src/services/OllamaService.ts:142-145, 235-237, 633-636: the prompt-evaluation phase).
 //
-// Shape of the work: per (query head, 128-row query tile, sequence) one CTA of four warps, 32 query rows per warp.
-// Head dims are 64 / 128 and the KV tile is 64 rows, so one tile is M 128 x N 64 x K 128 + M 128 x N 128 x K 64 --
-// too small and too softmax-bound per tile for a tcgen05 pipeline to pay without a second softmax warpgroup; this
-// version keeps the accumulators in registers (mma.sync m16n8k16, fp32 accumulate) and spends its effort on what
-// the old path wasted: HBM traffic and launches.  K rows [kv][hd] and V^T rows [hd][kv] (what rope_split writes) are
+// Shape of the work: per (query head, 128-row query tile, sequence) one CTA of four warps, 32 query rows per warp,
+// KV tiles of 64 rows.  This version keeps the accumulators in registers (mma.sync m16n8k16, fp32 accumulate) and
+// spends its effort on what the old path wasted: HBM traffic and launches.  It serves head dim 64 and is the A/B
+// partner of the tcgen05 kernel (prefill_attn_tc5.cu, head dim 128: scores, probabilities and output in tensor memory).  K rows [kv][hd] and V^T rows [hd][kv] (what rope_split writes) are
 // both "n-major with k contiguous", i.e. the B operand of a TN product: plain ldmatrix for both products, no
 // transposes.  cp.async double buffering of the K / V^T tiles, XOR-swizzled shared memory, 96 KB per CTA at head dim
 // 128: two CTAs per SM.  A pack of sequences (block-diagonal causal attention, section 4.7 of DESIGN.md) is one launch:
@@ -55,16 +54,12 @@ __device__ __forceinline__ float fa_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ uint32_t fa_pack(float lo, float hi) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
 // tile of 64-column rows (128 B): 16-byte chunk c of row r lives at chunk c ^ (r & 7)
 __device__ __forceinline__ uint32_t fa_swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 template <int HD>
 __global__ void __launch_bounds__(FA_THREADS, 2) flash_prefill_kernel(const __grid_constant__ FlashParams p) {
-    constexpr int NSUB = HD / 64;                     // 64-column sub-tiles of a [rows][HD] tile
+    // a [rows][HD] tile is HD / 64 sub-tiles of 64 columns (one 128-byte swizzle row each)
     constexpr int Q_BYTES = FA_BM * HD * 2;
     constexpr int K_BYTES = FA_BN * HD * 2;
     constexpr int V_BYTES = HD * FA_BN * 2;

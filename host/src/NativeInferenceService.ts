@@ -57,12 +57,28 @@ export class NativeInferenceService {
 	private samplingDefaults: Record<string, number> = process.env.GRIDLLM_SAMPLING === "ollama" ? { temperature: 0.8, top_k: 40, top_p: 0.9 } : {};
 	private applyTemplate = process.env.GRIDLLM_APPLY_TEMPLATE === "1";
 
-	// messages -> prompt text.  The GGUF's chat template is Jinja and is not interpreted: its FAMILY is recognised from the
-	// markers it contains (gl_chat_template) -- Llama-3 headers (also the default), ChatML, Llama-2 / Mistral [INST] -- and
-	// that family's framing applied; identical to gridllm_b200/service.py::_chat_prompt.
+	// Optional Jinja renderer for tokenizer.chat_template: (template, variables) -> text, e.g. `(t, v) => new Template(t).render(v)`
+	// from @huggingface/jinja.  gridllm_b200/service.py renders the template with sandboxed jinja2 (messages, add_generation_prompt,
+	// bos_token / eos_token, raise_exception) and falls back to the family framing below when that fails; this twin does the same
+	// when a renderer is injected, and uses the family framing alone otherwise (no Jinja engine is vendored here).
+	public renderTemplate?: (template: string, vars: Record<string, unknown>) => string;
+	public bosText = "";      // texts of the BOS / EOS control tokens for the template (the vocabulary's spelling)
+	public eosText = "";
+
+	// messages -> prompt text.  With a renderer: the GGUF's chat template interpreted as the Jinja program it is.  Otherwise (or
+	// when rendering throws) its FAMILY is recognised from the markers it contains (gl_chat_template) -- Llama-3 headers (also the
+	// default), ChatML, Llama-2 / Mistral [INST] -- and that family's framing applied; same order as gridllm_b200/service.py::_chat_prompt.
 	private chatPrompt(e: unknown, messages: Array<{ role: string; content: string }>): string {
 		let tmpl = "";
 		try { tmpl = native.chatTemplate(e) || ""; } catch { tmpl = ""; }
+		if (tmpl && this.renderTemplate) {
+			try {
+				let out = this.renderTemplate(tmpl, { messages, add_generation_prompt: true, bos_token: this.bosText, eos_token: this.eosText,
+					raise_exception: (m: string) => { throw new Error(m); } });
+				if (this.bosText && out.startsWith(this.bosText)) out = out.slice(this.bosText.length);      // the tokenizer adds the BOS id itself
+				if (out) return out;
+			} catch { /* a template this conversation does not fit: the family framing */ }
+		}
 		const msgs = messages.map((m) => [m.role ?? "user", m.content ?? ""] as [string, string]);
 		if (tmpl.includes("<|im_start|>"))
 			return msgs.map(([r, c]) => `<|im_start|>${r}\n${c}<|im_end|>\n`).join("") + "<|im_start|>assistant\n";
