@@ -13,7 +13,8 @@ config4: 32 x 2048 prompt tokens; config5: 1 250 documents / 8 = the share of on
   e2e          the same metric through the reference-facing call with HOST buffers (C ABI / NativeWorker), wall clock
   roofline     dominant kernel: algorithmic bytes (or flops) / measured device time vs the measured peak (MEASURED_PEAKS.json)
   cpu_baseline the C restatement of the reference's CPU path (oracle/c/llama_cpu.c: ggml-style int8-activation integer dots,
-               batched prompt pass) on the host cores, a bounded sample of the same workload
+               batched prompt pass) on the host cores, a bounded sample of the same workload (rank 0, N = 1 only; the 8B-shape
+               parity pre-flight of config2 likewise runs on the N = 1 line)
 `--impl reference` times only that CPU restatement, really -- model loaded once, thread count chosen once, every step a
 measured bounded sample -- and prints the same metric / unit / config as the native arm.  (The reference's own engine, an
 un-vendored Ollama/llama.cpp behind HTTP, cannot be installed here: no node / ollama / network -- DESIGN.md section 2.)
@@ -374,7 +375,7 @@ def main():
                 "data": "synthetic", "config": config, "e2e": out["e2e"], "gpu_launches": out["gpu_launches"], "roofline": out["roofline"],
                 "clocks": out["clocks"]}
         line.update(out.get("extra", {}))
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:                # the contract: the cpu_baseline leg on rank 0 at N = 1 only
             # the CPU leg runs in its own process (the reference arm of this same file, two measured samples after a warm one): the
             # engines are gone by now, and an OpenMP runtime started inside a process that has run CUDA, asyncio and a batch-runner
             # thread has been seen to stall for minutes -- a separate process cannot
@@ -448,7 +449,12 @@ def run_config2(args, N, path, rank, local_rank, world, dist, timed, peaks, extr
     eng = N.Engine(path, device=local_rank, max_ctx=1024)
     info = eng.info
     pre = None
-    if rank == 0 and not args.no_preflight:
+    # At N > 1 every rank runs the same kernels on the same model as the N = 1 line of the same tree, which carries the check; the
+    # C restatement also competes with the other ranks for the host cores there (66 s at N = 2 against 9 s at N = 1, run Y), so the
+    # multi-rank lines skip it unless GL_BENCH_PREFLIGHT_MULTI=1.
+    if world > 1 and os.environ.get("GL_BENCH_PREFLIGHT_MULTI", "0") != "1":
+        pre = {"skipped": "world > 1: the N = 1 line of the same tree carries the 8B-shape parity check (GL_BENCH_PREFLIGHT_MULTI=1 runs it here too)"}
+    elif rank == 0 and not args.no_preflight:
         t0 = time.time()
         pre = preflight_8b_parity(eng, path)
         pre["seconds"] = round(time.time() - t0, 1)
