@@ -251,17 +251,24 @@ class NativeInferenceService:
         except Exception:
             return None
         try:
-            key = (id(eng), tmpl)
-            cache = self.__dict__.setdefault("_tmpl_cache", {})
-            if key not in cache:
+            cache = self.__dict__.setdefault("_tmpl_cache", {})       # compiled templates, by template text
+            if tmpl not in cache:
                 env = ImmutableSandboxedEnvironment(trim_blocks=True, lstrip_blocks=True, undefined=jinja2.StrictUndefined)
 
                 def raise_exception(msg):
                     raise jinja2.exceptions.TemplateError(msg)
                 env.globals["raise_exception"] = raise_exception
-
-                cache[key] = (env.from_string(tmpl), self._control_text(eng, getattr(eng.info, "bos_id", -1)), self._control_text(eng, getattr(eng.info, "eos_id", -1)))
-            t, bos, eos = cache[key]
+                cache[tmpl] = env.from_string(tmpl)
+            t = cache[tmpl]
+            # the BOS / EOS spellings belong to the engine's vocabulary: kept on the engine object, not beside the template
+            ctrl = getattr(eng, "_gl_ctrl_text", None)
+            if ctrl is None:
+                ctrl = (self._control_text(eng, getattr(eng.info, "bos_id", -1)), self._control_text(eng, getattr(eng.info, "eos_id", -1)))
+                try:
+                    eng._gl_ctrl_text = ctrl
+                except Exception:
+                    pass
+            bos, eos = ctrl
             out = t.render(messages=[dict(m) for m in messages], add_generation_prompt=True, bos_token=bos, eos_token=eos)
             if bos and out.startswith(bos):
                 out = out[len(bos):]
