@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <queue>
 
 namespace gl {
 
@@ -159,7 +160,43 @@ bool Tokenizer::load(const GGUFFile& f) {
     ok_ = false;
     const GGUFValue* toks = f.find("tokenizer.ggml.tokens");
     if (!toks || toks->arr_s.empty()) return false;
-    if (f.get_s("tokenizer.ggml.model", "") != "gpt2") return false;
+    const std::string model = f.get_s("tokenizer.ggml.model", "");
+    if (model == "llama") {
+        // SentencePiece BPE (Llama-2 / Mistral): pieces + scores; no pre-tokeniser, no merges list
+        const GGUFValue* sc = f.find("tokenizer.ggml.scores");
+        if (!sc || sc->arr_f.size() != toks->arr_s.size()) return false;
+        tokens_ = toks->arr_s;
+        scores_.assign(sc->arr_f.begin(), sc->arr_f.end());
+        const GGUFValue* ty = f.find("tokenizer.ggml.token_type");
+        types_.assign(tokens_.size(), 1);
+        if (ty && ty->arr_i.size() == tokens_.size())
+            for (size_t i = 0; i < tokens_.size(); ++i) types_[i] = (int)ty->arr_i[i];
+        tok2id_.reserve(tokens_.size() * 2);
+        for (size_t i = 0; i < tokens_.size(); ++i) tok2id_.emplace(tokens_[i], (int32_t)i);
+        for (int b = 0; b < 256; ++b) byte_tok_[b] = -1;
+        for (size_t i = 0; i < tokens_.size(); ++i) {
+            const std::string& t = tokens_[i];
+            if (types_[i] == 6 && t.size() == 6 && t.compare(0, 3, "<0x") == 0 && t[5] == '>') {
+                auto hex = [](char c) { return c >= '0' && c <= '9' ? c - '0' : (c >= 'A' && c <= 'F' ? c - 'A' + 10 : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : -1)); };
+                const int hi = hex(t[3]), lo = hex(t[4]);
+                if (hi >= 0 && lo >= 0) byte_tok_[hi * 16 + lo] = (int32_t)i;
+            }
+        }
+        bos = (int)f.get_u("tokenizer.ggml.bos_token_id", 1);
+        eos = (int)f.get_u("tokenizer.ggml.eos_token_id", 2);
+        unk_ = (int)f.get_u("tokenizer.ggml.unknown_token_id", 0);
+        eot = (int)f.get_u("tokenizer.ggml.eot_token_id", (uint64_t)-1);
+        add_bos_default = f.get_u("tokenizer.ggml.add_bos_token", 1) != 0;
+        add_space_prefix_ = f.get_u("tokenizer.ggml.add_space_prefix", 1) != 0;
+        chat_template = f.get_s("tokenizer.chat_template", "");
+        for (size_t i = 0; i < tokens_.size(); ++i)
+            if (types_[i] == 3 || types_[i] == 4) specials_.emplace_back(tokens_[i], (int32_t)i);
+        std::sort(specials_.begin(), specials_.end(), [](auto& a, auto& b) { return a.first.size() > b.first.size(); });
+        spm_ = true;
+        ok_ = true;
+        return true;
+    }
+    if (model != "gpt2") return false;
     // Only the llama-bpe ("llama3") pre-tokeniser split is restated here.  Other byte-level BPE files that are also
     // general.architecture == llama (tekken, smollm, deepseek-llm, ... -- each has its own split regex in llama.cpp [external])
     // would tokenise silently wrong, so they load WITHOUT a tokenizer: text requests fail with a message, token-id requests work.
@@ -238,11 +275,14 @@ std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos, bo
     if (add_bos && bos >= 0) out.push_back(bos);
     // split on control tokens first
     std::vector<std::pair<std::string, int32_t>> parts;   // (text, -1) or ("", special id)
-    if (parse_special && !specials_.empty()) {
+    // control pieces (token type 3) are recognised in the text only with parse_special; user-defined pieces (type 4) always, as whole
+    // pieces -- the rule of llama.cpp's special-token partition and of sentencepiece's user_defined_symbols [external]
+    if (!specials_.empty()) {
         size_t i = 0, start = 0;
         while (i < text.size()) {
             bool hit = false;
             for (auto& sp : specials_) {
+                if (!parse_special && types_[sp.second] == 3) continue;
                 if (!sp.first.empty() && text.compare(i, sp.first.size(), sp.first) == 0) {
                     if (i > start) parts.emplace_back(text.substr(start, i - start), -1);
                     parts.emplace_back(std::string(), sp.second);
@@ -258,6 +298,18 @@ std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos, bo
     } else {
         parts.emplace_back(text, -1);
     }
+    if (spm_) {
+        // a fragment that starts the text or follows a control token is prefixed with a space (what llama.cpp's SPM path and
+        // sentencepiece's add_dummy_prefix do [external]); spaces become U+2581 inside spm_text
+        bool prev_special = true;
+        for (auto& pr : parts) {
+            if (pr.second >= 0) { out.push_back(pr.second); prev_special = true; continue; }
+            if (pr.first.empty()) continue;                          // the empty text has no pieces (not even the prefix)
+            spm_text((add_space_prefix_ && prev_special) ? " " + pr.first : pr.first, out);
+            prev_special = false;
+        }
+        return out;
+    }
     for (auto& pr : parts) {
         if (pr.second >= 0) { out.push_back(pr.second); continue; }
         for (auto& w : llama3_pretokenize(pr.first)) {
@@ -269,9 +321,79 @@ std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos, bo
     return out;
 }
 
+// SentencePiece BPE over one fragment (restating llm_tokenizer_spm of llama.cpp / the BPE model of sentencepiece [external]): the
+// fragment's UTF-8 characters are the initial symbols; the adjacent pair whose concatenation is a piece with the HIGHEST score is merged
+// first (ties: the leftmost pair), until no adjacent pair forms a piece; a symbol that is not a piece falls back to its bytes (<0xXX>).
+void Tokenizer::spm_text(const std::string& raw, std::vector<int32_t>& out) const {
+    std::string text;
+    text.reserve(raw.size() + 8);
+    for (char c : raw) {
+        if (c == ' ') text += "\xE2\x96\x81";      // U+2581
+        else text += c;
+    }
+    struct Sym { int prev, next; size_t off, n; };
+    std::vector<Sym> sym;
+    for (size_t i = 0; i < text.size();) {
+        const unsigned char c = (unsigned char)text[i];
+        size_t n = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+        if (i + n > text.size()) n = text.size() - i;
+        sym.push_back(Sym{(int)sym.size() - 1, (int)sym.size() + 1, i, n});
+        i += n;
+    }
+    if (sym.empty()) return;
+    sym.back().next = -1;
+    struct Bigram { int left, right; float score; size_t size; };
+    auto worse = [](const Bigram& a, const Bigram& b) { return a.score < b.score || (a.score == b.score && a.left > b.left); };
+    std::priority_queue<Bigram, std::vector<Bigram>, decltype(worse)> queue(worse);
+    auto try_add = [&](int l, int r) {
+        if (l < 0 || r < 0) return;
+        const std::string t = text.substr(sym[l].off, sym[l].n + sym[r].n);
+        auto it = tok2id_.find(t);
+        if (it == tok2id_.end() || (size_t)it->second >= scores_.size()) return;
+        queue.push(Bigram{l, r, scores_[it->second], t.size()});
+    };
+    for (int i = 1; i < (int)sym.size(); ++i) try_add(i - 1, i);
+    while (!queue.empty()) {
+        const Bigram b = queue.top();
+        queue.pop();
+        Sym& l = sym[b.left];
+        Sym& r = sym[b.right];
+        if (l.n == 0 || r.n == 0 || l.n + r.n != b.size) continue;      // one of the two was merged away since this entry was queued
+        l.n += r.n;
+        r.n = 0;
+        l.next = r.next;
+        if (r.next >= 0) sym[r.next].prev = b.left;
+        try_add(l.prev, b.left);
+        try_add(b.left, l.next);
+    }
+    for (int i = 0; i >= 0; i = sym[i].next) {
+        const std::string t = text.substr(sym[i].off, sym[i].n);
+        auto it = tok2id_.find(t);
+        if (it != tok2id_.end()) { out.push_back(it->second); continue; }
+        for (unsigned char c : t) {
+            if (byte_tok_[c] >= 0) out.push_back(byte_tok_[c]);
+            else if (unk_ >= 0) out.push_back(unk_);
+        }
+    }
+}
+
 std::string Tokenizer::piece(int32_t id) const {
     if (!ok_ || id < 0 || id >= (int)tokens_.size()) return {};
     if (types_[id] == 3) return {};     // control tokens render as nothing
+    if (spm_) {
+        if (types_[id] == 6) {          // byte-fallback piece: the byte itself (maybe half a character: the host holds it back)
+            for (int b = 0; b < 256; ++b)
+                if (byte_tok_[b] == id) return std::string(1, (char)b);
+            return {};
+        }
+        std::string out;
+        const std::string& t = tokens_[id];
+        for (size_t i = 0; i < t.size();) {
+            if (t.compare(i, 3, "\xE2\x96\x81") == 0) { out += ' '; i += 3; }
+            else out += t[i++];
+        }
+        return out;
+    }
     std::string out;
     for (auto& ch : utf8_chars(tokens_[id])) {
         auto it = cp2byte_.find(utf8_decode1(ch));
@@ -284,6 +406,8 @@ std::string Tokenizer::piece(int32_t id) const {
 std::string Tokenizer::decode(const int32_t* ids, int n) const {
     std::string out;
     for (int i = 0; i < n; ++i) out += piece(ids[i]);
+    // SPM: the space the encoder put in front of a text that starts the sequence is not part of the text
+    if (spm_ && add_space_prefix_ && !out.empty() && out[0] == ' ') out.erase(0, 1);
     return out;
 }
 

@@ -1,9 +1,10 @@
 // Byte-level BPE tokenizer driven by GGUF metadata (tokenizer.ggml.{model,tokens,merges,...}).
 // In the reference the tokenizer lives inside Ollama; OllamaService only ever ships prompt TEXT
 // (/root/reference/client/src/services/OllamaService.ts:101-104, 190-195), so a native worker needs
-// its own.  Supports tokenizer.ggml.model == "gpt2" (Llama-3 family).  The pre-tokeniser is the
-// llama-bpe split over Unicode code points (general categories L* / N* from generated tables -- tools/gen_unicode_ranges.py --
-// and White_Space).
+// its own.  Supports tokenizer.ggml.model == "gpt2" (Llama-3 family: byte-level BPE; the pre-tokeniser is the
+// llama-bpe split over Unicode code points -- general categories L* / N* from generated tables, tools/gen_unicode_ranges.py,
+// and White_Space) and tokenizer.ggml.model == "llama" (Llama-2 / Mistral family, BASELINE config 5's model: SentencePiece BPE
+// -- pieces with scores, U+2581 for spaces, <0xXX> byte fallback).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -31,7 +32,13 @@ public:
 
 private:
     void bpe_word(const std::string& word_u, std::vector<int32_t>& out) const;
+    void spm_text(const std::string& text, std::vector<int32_t>& out) const;      // one raw-text fragment, SentencePiece BPE
     bool ok_ = false;
+    bool spm_ = false;                                // tokenizer.ggml.model == "llama"
+    bool add_space_prefix_ = true;                    // SPM: a fragment that starts the text or follows a control token gets a leading space
+    int unk_ = -1;
+    std::vector<float> scores_;                       // SPM: merge priority of every piece
+    int32_t byte_tok_[256];                           // SPM: <0xXX> byte-fallback pieces (-1: absent)
     bool ignore_merges_ = false;                      // pre-tokens found whole in the vocabulary skip the merge loop
     std::vector<std::string> tokens_;                 // in "unicode-escaped bytes" form (GPT-2)
     std::vector<int> types_;

@@ -136,3 +136,89 @@ def test_pretokeniser_unicode_fuzz(hostcheck_lib):
         text = "".join(rng.choice(cands, size=int(rng.integers(1, 12))))
         ref = [p for p, _ in split.pre_tokenize_str(text)]
         assert _hc_pretokenize(hostcheck_lib, text) == ref, repr(text)
+
+
+# ---- SentencePiece BPE (tokenizer.ggml.model == "llama": Llama-2 / Mistral, the model family of BASELINE config 5) -----------------
+@pytest.fixture(scope="module")
+def spm_vocab(tmp_path_factory):
+    """A SentencePiece BPE model trained here on synthetic text (byte fallback, dummy prefix, identity normalisation, [INST] / [/INST]
+    as user-defined symbols -- the shape of the Llama-2 / Mistral tokenizers) and the vocabulary-only GGUF a converter would write for
+    it: pieces, scores, token types, bos / eos / unk ids, add_space_prefix."""
+    spm = pytest.importorskip("sentencepiece")
+    import io
+    import random
+    from oracle import gguf_synth as S
+    rnd = random.Random(1)
+    words = ["the", "quick", "brown", "fox", "jumps", "over", "lazy", "dog", "hello", "world", "rain", "in", "spain", "stays", "mainly", "plain",
+             "naïve", "café", "日本語", "テスト", "emoji", "data", "model", "token", "embedding", "worker", "scheduler", "gpu", "kernel", "Straße",
+             "über", "zwölf", "1234", "42", "3.14", "(paren)", "semi;colon", "new\nline"]
+    lines = [" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 12))) for _ in range(4000)]
+    model = io.BytesIO()
+    spm.SentencePieceTrainer.train(sentence_iterator=iter(lines), model_writer=model, vocab_size=600, model_type="bpe", byte_fallback=True,
+                                   character_coverage=0.995, bos_id=1, eos_id=2, unk_id=0, pad_id=-1, normalization_rule_name="identity",
+                                   add_dummy_prefix=True, remove_extra_whitespaces=False, minloglevel=2, user_defined_symbols=["[INST]", "[/INST]"])
+    sp = spm.SentencePieceProcessor(model_proto=model.getvalue())
+    n = sp.get_piece_size()
+    toks = [sp.id_to_piece(i) for i in range(n)]
+    types = [2 if sp.is_unknown(i) else 3 if sp.is_control(i) else 6 if sp.is_byte(i) else 4 if toks[i] in ("[INST]", "[/INST]") else 1 for i in range(n)]
+    g = S.GGUFFile()
+    g.add_str("general.architecture", "llama")
+    g.add_str("tokenizer.ggml.model", "llama")
+    g.add_arr("tokenizer.ggml.tokens", S._STR, toks)
+    g.add_arr("tokenizer.ggml.scores", S._F32, [sp.get_score(i) for i in range(n)])
+    g.add_arr("tokenizer.ggml.token_type", S._I32, types)
+    g.add_u32("tokenizer.ggml.bos_token_id", 1)
+    g.add_u32("tokenizer.ggml.eos_token_id", 2)
+    g.add_u32("tokenizer.ggml.unknown_token_id", 0)
+    g.add_bool("tokenizer.ggml.add_bos_token", True)
+    g.add_bool("tokenizer.ggml.add_space_prefix", True)
+    path = str(tmp_path_factory.mktemp("spm") / "spm_vocab.gguf")
+    g.write(path)
+    return path, sp
+
+
+def _spm_ids(lib, path, text, bos=0, special=0):
+    ids = np.zeros(8192, dtype=np.int32)
+    n = lib.hc_tokenize(path.encode(), text.encode(), bos, special, ids.ctypes.data_as(ctypes.c_void_p), 8192)
+    assert n >= 0, n
+    return ids[:n].tolist()
+
+
+def test_sentencepiece_bpe_matches_the_sentencepiece_library(hostcheck_lib, spm_vocab):
+    """tokenizer.cpp's SentencePiece path (highest-score adjacent pair first, U+2581 for spaces, the dummy prefix, <0xXX> byte fallback)
+    against the `sentencepiece` library on the same model: curated strings (multiple / leading / trailing spaces, accents, CJK, an
+    emoji and letters outside the model's alphabet -> byte pieces, digits, punctuation, newlines, the empty string) and 400 random
+    ones; ids equal, and the text comes back from the ids."""
+    import random
+    path, sp = spm_vocab
+    tests = ["hello world", "the quick brown fox", " leading space", "two  spaces", "trailing ", "naïve café über Straße", "日本語のテスト",
+             "emoji 😀 zzz qqq", "1234 42 3.14", "new\nline\ttab", "", "a", "zwölfzwölf hello,world!(paren)", "   ", "\n"]
+    rnd = random.Random(7)
+    alphabet = list("abcdefghijklmnopqrstuvwxyz    \n.,;!()äöüß日本語テスト1234567890😀")
+    tests += ["".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 48))) for _ in range(400)]
+    out = ctypes.create_string_buffer(1 << 16)
+    for t in tests:
+        ours, ref = _spm_ids(hostcheck_lib, path, t), sp.encode(t)
+        assert ours == ref, (t, ours, ref)
+        if t:
+            a = np.asarray(ours, dtype=np.int32)
+            k = hostcheck_lib.hc_detokenize(path.encode(), a.ctypes.data_as(ctypes.c_void_p), len(ours), out, 1 << 16)
+            assert k >= 0 and out.raw[:k].decode("utf-8") == sp.decode(ref) == t
+    assert _spm_ids(hostcheck_lib, path, "hello", bos=1) == [1] + sp.encode("hello")          # BOS id, then the prefixed text
+
+
+def test_sentencepiece_control_and_user_defined_pieces(hostcheck_lib, spm_vocab):
+    """Mistral's [INST] framing: with parse_special the markers are single pieces and the text after a marker gets the space prefix
+    again (what llama.cpp's SPM path does [external]); without it they are spelled out piece by piece."""
+    path, sp = spm_vocab
+    inst, inst_end = sp.piece_to_id("[INST]"), sp.piece_to_id("[/INST]")
+    ids = _spm_ids(hostcheck_lib, path, "[INST] hello world [/INST]", bos=1, special=1)
+    assert ids[0] == 1 and ids[1] == inst and ids[-1] == inst_end
+    assert ids[2:-1] == sp.encode(" hello world ")             # the fragment " hello world " behind a marker: prefixed again
+    # user-defined pieces are whole pieces with or without parse_special; the text behind one is a new fragment and gets the space
+    # prefix again -- llama.cpp's rule (Ollama's tokenizer), where sentencepiece itself would not re-prefix; control pieces need
+    # parse_special
+    assert _spm_ids(hostcheck_lib, path, "a [INST] b", bos=0, special=0) == sp.encode("a ") + [inst] + sp.encode(" b")
+    eos_text = sp.id_to_piece(2)
+    plain = _spm_ids(hostcheck_lib, path, "a" + eos_text, bos=0, special=0)
+    assert 2 not in plain and _spm_ids(hostcheck_lib, path, "a" + eos_text, bos=0, special=1)[-1] == 2
