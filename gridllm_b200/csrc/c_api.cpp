@@ -181,6 +181,18 @@ int gl_token_piece(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32
     return GL_OK;
 }
 
+int gl_token_text(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32_t* len_out) {
+    if (!e || !len_out) return bad("gl_token_text: null argument");
+    const gl::Tokenizer& t = e->impl->tokenizer();
+    if (!t.ok()) { *len_out = 0; return GL_OK; }
+    const std::string tx = t.text(id);
+    *len_out = (int32_t)tx.size();
+    if (!buf) return GL_OK;
+    if ((int32_t)tx.size() > cap) { gl::set_last_error("gl_token_text: output buffer too small"); return GL_ERR_INVALID; }
+    std::memcpy(buf, tx.data(), tx.size());
+    return GL_OK;
+}
+
 int gl_batch_counters(gl_engine* e, uint64_t out[8], int32_t reset) {
     if (!e || !out) return bad("gl_batch_counters: null argument");
     e->impl->batch_counters(out, reset != 0);

@@ -403,6 +403,12 @@ std::string Tokenizer::piece(int32_t id) const {
     return out;
 }
 
+std::string Tokenizer::text(int32_t id) const {
+    if (!ok_ || id < 0 || id >= (int)tokens_.size()) return {};
+    if (types_[id] == 3 || types_[id] == 4) return tokens_[id];      // control / user-defined pieces are stored as they are written
+    return piece(id);
+}
+
 std::string Tokenizer::decode(const int32_t* ids, int n) const {
     std::string out;
     for (int i = 0; i < n; ++i) out += piece(ids[i]);

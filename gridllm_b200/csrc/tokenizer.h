@@ -25,6 +25,7 @@ public:
     std::vector<int32_t> encode(const std::string& text, bool add_bos, bool parse_special) const;
     std::string decode(const int32_t* ids, int n) const;
     std::string piece(int32_t id) const;     // raw bytes of one token ("" for control tokens)
+    std::string text(int32_t id) const;      // the vocabulary's spelling of a token, control tokens included (chat templates)
     int n_vocab() const { return (int)tokens_.size(); }
     int bos = -1, eos = -1, eot = -1;
     bool add_bos_default = true;

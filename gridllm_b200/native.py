@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "GL_OK", -1: "GL_ERR_INVALID", -2: "GL_ERR_IO", -3: "GL_ERR_F
 ABI_SYMBOLS = [
     "gl_abi_version", "gl_last_error", "gl_device_count", "gl_engine_create", "gl_engine_destroy",
     "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_chat_template", "gl_generate", "gl_embed", "gl_last_logits", "gl_sample_logits",
-    "gl_seq_open", "gl_seq_open_many", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_batch_counters", "gl_time_batch_step",
+    "gl_seq_open", "gl_seq_open_many", "gl_batch_step", "gl_seq_close", "gl_seq_logits", "gl_seq_stats", "gl_token_piece", "gl_token_text", "gl_batch_counters", "gl_time_batch_step",
     "gl_gemv", "gl_gemv_model_tensor", "gl_rmsnorm", "gl_decode_step", "gl_kv_reset", "gl_position",
     "gl_prefill", "gl_time_decode",
 ]
@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
     lib.gl_seq_logits.argtypes = [vp, i32, f32p, i32]
     lib.gl_seq_stats.argtypes = [vp, i32, C.POINTER(GenStats)]
     lib.gl_token_piece.argtypes = [vp, i32, C.c_char_p, i32, i32p]
+    lib.gl_token_text.argtypes = [vp, i32, C.c_char_p, i32, i32p]
     lib.gl_batch_counters.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     lib.gl_time_batch_step.argtypes = [vp, i32, i32, i32, f32p, i32p, C.POINTER(C.c_uint64)]
     lib.gl_gemv.argtypes = [vp, C.c_int, vp, i32, i32, f32p, f32p, i32, f32p]
@@ -296,6 +297,14 @@ class Engine:
         n = C.c_int32(0)
         _check(self._lib.gl_token_piece(self._h, int(tid), buf, 256, C.byref(n)))
         return buf.raw[: n.value]
+
+    def token_text(self, tid: int) -> str:
+        """the vocabulary's spelling of a token, control tokens included ('' when the model has no tokenizer): bos_token / eos_token
+        of a chat template"""
+        buf = C.create_string_buffer(512)
+        n = C.c_int32(0)
+        _check(self._lib.gl_token_text(self._h, int(tid), buf, 512, C.byref(n)))
+        return buf.raw[: n.value].decode("utf-8", "replace")
 
     def batch_counters(self, reset: bool = False) -> dict:
         out = (C.c_uint64 * 8)()

@@ -222,11 +222,17 @@ class NativeInferenceService:
 
     @staticmethod
     def _control_text(eng: N.Engine, tid) -> str:
-        """the vocabulary text of a (control) token: gl_token_piece renders control tokens as nothing (what a stream wants), so
-        the text is found by asking the tokenizer which known spelling parses to this id"""
+        """the vocabulary text of a (control) token: gl_token_text where the engine has it; gl_token_piece renders control tokens
+        as nothing (what a stream wants), so for an engine without the call the text is found by asking the tokenizer which known
+        spelling parses to this id"""
         try:
             if tid is None or int(tid) < 0:
                 return ""
+            tt = getattr(eng, "token_text", None)              # gl_token_text: the spelling straight from the vocabulary
+            if tt is not None:
+                txt = tt(int(tid))
+                if txt:
+                    return txt
             txt = eng.token_piece(int(tid)).decode("utf-8", "replace")
             if txt:
                 return txt

@@ -12,6 +12,7 @@
 //   generate(engine, Int32Array prompt, {numPredict, ignoreEos, stopIds}, onToken|null) -> Promise<{ids, logprobs, stats}>
 //   embed(engine, Int32Array ids, Int32Array offsets) -> Promise<{embeddings: Float32Array, stats}>
 //   chatTemplate(engine) -> string   (tokenizer.chat_template of the GGUF; the TS host picks the message framing from it)
+//   tokenText(engine, id) -> string  (the vocabulary's spelling of a token, control tokens included: bos_token / eos_token of a template)
 //   seqOpen(engine, Int32Array prompt, {numPredict, ...}) -> Promise<number>      \  continuous batching:
 //   batchStep(engine) -> Promise<Array<{slot, id, logprob, done, piece}>>          |  every job the worker holds is a sequence;
 //   seqClose(engine, slot) ; seqStats(engine, slot) -> stats                      /  one batched step serves all of them
@@ -349,6 +350,21 @@ napi_value ChatTemplate(napi_env env, napi_callback_info info) {
     return out;
 }
 
+// the vocabulary's spelling of a token, control tokens included: bos_token / eos_token of a chat template (gl_token_text)
+napi_value TokenText(napi_env env, napi_callback_info info) {
+    size_t argc = 2;
+    napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    gl_engine* e = unwrap(env, argv[0]);
+    int32_t id = -1, len = 0;
+    NAPI_OK(napi_get_value_int32(env, argv[1], &id));
+    char buf[512];
+    if (gl_token_text(e, id, buf, (int32_t)sizeof buf, &len) != GL_OK) return throw_gl(env, "gl_token_text");
+    napi_value out;
+    NAPI_OK(napi_create_string_utf8(env, buf, (size_t)len, &out));
+    return out;
+}
+
 void read_sample_opts(napi_env env, napi_value o, gl_sample_opts& so, std::vector<int32_t>& stop_ids) {
     napi_value v;
     so.num_predict = 128;
@@ -521,6 +537,7 @@ napi_value Init(napi_env env, napi_value exports) {
         {"detokenize", nullptr, Detokenize, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"embed", nullptr, Embed, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"chatTemplate", nullptr, ChatTemplate, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"tokenText", nullptr, TokenText, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"seqOpen", nullptr, SeqOpen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"batchStep", nullptr, BatchStep, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"seqClose", nullptr, SeqClose, nullptr, nullptr, nullptr, napi_default, nullptr},

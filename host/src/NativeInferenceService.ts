@@ -62,8 +62,8 @@ export class NativeInferenceService {
 	// bos_token / eos_token, raise_exception) and falls back to the family framing below when that fails; this twin does the same
 	// when a renderer is injected, and uses the family framing alone otherwise (no Jinja engine is vendored here).
 	public renderTemplate?: (template: string, vars: Record<string, unknown>) => string;
-	public bosText = "";      // texts of the BOS / EOS control tokens for the template (the vocabulary's spelling)
-	public eosText = "";
+	public bosText = "";      // texts of the BOS / EOS control tokens for the template: native.tokenText(engine, info.bosId / eosId)
+	public eosText = "";      // (filled when the engine is created)
 
 	// messages -> prompt text.  With a renderer: the GGUF's chat template interpreted as the Jinja program it is.  Otherwise (or
 	// when rendering throws) its FAMILY is recognised from the markers it contains (gl_chat_template) -- Llama-3 headers (also the

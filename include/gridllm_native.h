@@ -165,6 +165,10 @@ int  gl_seq_logits(gl_engine* e, int32_t slot, float* out, int32_t n_vocab);
 int  gl_seq_stats(gl_engine* e, int32_t slot, gl_gen_stats* stats);
 /* the bytes of one token as gl_generate's callback would hand them over (may be an incomplete UTF-8 sequence) */
 int  gl_token_piece(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32_t* len_out);
+/* the vocabulary's own spelling of a token, control tokens included ("<|begin_of_text|>", "</s>", ...; *len_out = 0 without a
+ * tokenizer): what a chat template's bos_token / eos_token must be rendered with (generateChat*Response, OllamaService.ts:353-599).
+ * gl_token_piece renders control tokens as nothing, which is what a stream wants and a template cannot use. */
+int  gl_token_text(const gl_engine* e, int32_t id, char* buf, int32_t cap, int32_t* len_out);
 /* engine-wide batching counters since creation (or the last reset): out[0] batched steps, [1] sum over steps of sequences in
  * the step, [2] device ns of those steps, [3] device ns of the prefills of gl_seq_open, [4] prompt tokens prefilled,
  * [5] sequences opened, [6] kernel launches, [7] reserved.  reset != 0 zeroes them after reading. */

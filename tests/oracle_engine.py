@@ -146,6 +146,15 @@ class OracleEngine:
     def token_piece(self, tid):
         return self._bytes([tid])
 
+    def token_text(self, tid):
+        """gl_token_text: the vocabulary's spelling, control tokens included (the double reads it from the GGUF metadata)"""
+        toks = getattr(self, "_vocab_texts", None)
+        if toks is None:
+            import gguf                                   # gguf-py, the ggml project's own reader
+            f = gguf.GGUFReader(self.path).fields.get("tokenizer.ggml.tokens")
+            toks = self._vocab_texts = [bytes(f.parts[i]).decode("utf-8", "replace") for i in f.data] if f is not None else []
+        return toks[tid] if 0 <= tid < len(toks) else ""
+
     def embed(self, seqs):
         if any(len(s) > self.info.n_ctx for s in seqs):
             raise RuntimeError("GL_ERR_CONTEXT: sequence exceeds the engine context")

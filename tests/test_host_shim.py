@@ -19,7 +19,7 @@ def test_napi_shim_type_checks():
 def test_shim_binds_the_hot_path_entry_points():
     src = open(os.path.join(ROOT, "host", "napi", "addon.cc")).read()
     for sym in ("gl_engine_create", "gl_engine_destroy", "gl_engine_info", "gl_tokenize", "gl_detokenize", "gl_generate", "gl_embed",
-                "gl_device_count", "gl_last_error", "gl_chat_template", "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_stats", "gl_token_piece"):
+                "gl_device_count", "gl_last_error", "gl_chat_template", "gl_seq_open", "gl_batch_step", "gl_seq_close", "gl_seq_stats", "gl_token_piece", "gl_token_text"):
         assert sym + "(" in src, sym
     ts = open(os.path.join(ROOT, "host", "src", "NativeInferenceService.ts")).read()
     for method in ("checkHealth", "getAvailableModels", "validateModel", "generateResponse", "generateStreamResponse", "generateChatResponse",
