@@ -400,7 +400,8 @@ def gpt2_byte_to_unicode() -> Dict[int, str]:
 def build_model(path: str, shape: LlamaShape, recipe: str = "q4_k_m", seed: int = 1234,
                 mode: str = "quantize", gain: float = 1.0, with_vocab: bool = True,
                 arch: str = "llama", rope_freqs: Optional[np.ndarray] = None,
-                rope_scaling: Optional[Tuple[str, float]] = None, pre: str = "llama-bpe") -> Dict[str, object]:
+                rope_scaling: Optional[Tuple[str, float]] = None, pre: str = "llama-bpe",
+                spm_vocab: Optional[Dict[str, object]] = None) -> Dict[str, object]:
     """Write a synthetic Llama-architecture GGUF.
 
     mode="quantize": fp32 master weights N(0, gain^2/fan_in) (embedding N(0,1), norm weights
@@ -409,6 +410,9 @@ def build_model(path: str, shape: LlamaShape, recipe: str = "q4_k_m", seed: int 
     mode="random":   raw random well-formed blocks (fast; for Llama-3-8B shaped benches).
     rope_freqs:   per-pair frequency factors written as rope_freqs.weight F32[head_dim/2] (what the Llama-3.1 converter emits).
     rope_scaling: (type, factor) -> {arch}.rope.scaling.type / .factor.   pre: tokenizer.ggml.pre.
+    spm_vocab:    a SentencePiece vocabulary instead of the synthetic byte-level BPE one (tokenizer.ggml.model = "llama", the
+                  Llama-2 / Mistral family): {"tokens": [...], "scores": [...], "types": [...], "bos": id, "eos": id, "unk": id,
+                  "chat_template": str or None}; shape.n_vocab must equal len(tokens).
     Returns {"bytes": file size, "n_params": ..., "weights_bytes": matrix payload}.
     """
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -432,7 +436,20 @@ def build_model(path: str, shape: LlamaShape, recipe: str = "q4_k_m", seed: int 
     if rope_scaling is not None:
         g.add_str(f"{arch}.rope.scaling.type", rope_scaling[0])
         g.add_f32(f"{arch}.rope.scaling.factor", rope_scaling[1])
-    if with_vocab:
+    if spm_vocab is not None:
+        assert len(spm_vocab["tokens"]) == shape.n_vocab, (len(spm_vocab["tokens"]), shape.n_vocab)
+        g.add_str("tokenizer.ggml.model", "llama")
+        g.add_arr("tokenizer.ggml.tokens", _STR, list(spm_vocab["tokens"]))
+        g.add_arr("tokenizer.ggml.scores", _F32, list(spm_vocab["scores"]))
+        g.add_arr("tokenizer.ggml.token_type", _I32, list(spm_vocab["types"]))
+        g.add_u32("tokenizer.ggml.bos_token_id", int(spm_vocab["bos"]))
+        g.add_u32("tokenizer.ggml.eos_token_id", int(spm_vocab["eos"]))
+        g.add_u32("tokenizer.ggml.unknown_token_id", int(spm_vocab["unk"]))
+        g.add_bool("tokenizer.ggml.add_bos_token", True)
+        g.add_bool("tokenizer.ggml.add_space_prefix", True)
+        if spm_vocab.get("chat_template"):
+            g.add_str("tokenizer.chat_template", str(spm_vocab["chat_template"]))
+    elif with_vocab:
         toks, merges, types = synth_vocab(shape.n_vocab)
         g.add_str("tokenizer.ggml.model", "gpt2")
         g.add_str("tokenizer.ggml.pre", pre)

@@ -24,6 +24,18 @@ class OracleEngine:
         self.m = O.load_gguf(gguf_path)
         self.info = SimpleNamespace(has_tokenizer=1, n_vocab=self.m.n_vocab, n_embd=self.m.n_embd, n_params=int(1e6), quantization=b"Q4_K_M", n_ctx=int(max_ctx) if max_ctx else 512,
                                     eos_id=self.m.n_vocab - 2, eot_id=self.m.n_vocab - 1, bos_id=self.m.n_vocab - 3)
+        try:                                     # bos / eos / eot ids as the file states them (a SentencePiece vocabulary keeps them at 1 / 2)
+            import gguf
+            fields = gguf.GGUFReader(gguf_path).fields
+
+            def _u(key, dflt):
+                f = fields.get(key)
+                return int(f.parts[-1][0]) if f is not None else dflt
+            self.info.bos_id = _u("tokenizer.ggml.bos_token_id", self.info.bos_id)
+            self.info.eos_id = _u("tokenizer.ggml.eos_token_id", self.info.eos_id)
+            self.info.eot_id = _u("tokenizer.ggml.eot_token_id", -1 if fields.get("tokenizer.ggml.scores") is not None else self.info.eot_id)
+        except Exception:
+            pass
         self.calls = []
         self.chat_template = ""
         self.max_batch = int(kw.get("max_batch", 0) or 0)

@@ -202,6 +202,56 @@ def test_chat_template_is_rendered_as_jinja(svc):
     svc._jinja = True
 
 
+def test_mistral_family_text_goes_through_sentencepiece_and_its_template(tmp_path, hostcheck_lib, monkeypatch):
+    """BASELINE config 5's model family end to end on the host side: a GGUF whose tokenizer is SentencePiece BPE
+    (tokenizer.ggml.model = "llama") -- document TEXT reaches the engine as the ids the `sentencepiece` library gives, the
+    embeddings come back one per document, and a chat request is framed by the published Mistral template ([INST] ... [/INST],
+    `eos_token` spelled as the vocabulary spells it) before it is tokenised."""
+    spm = pytest.importorskip("sentencepiece")
+    pytest.importorskip("jinja2")
+    import io
+    import random
+    import oracle_engine
+    from gridllm_b200 import service as SV
+    from oracle import gguf_synth as S
+    rnd = random.Random(3)
+    words = ["the", "quick", "brown", "fox", "hello", "world", "embedding", "worker", "scheduler", "document", "query", "gpu", "naïve", "café"]
+    lines = [" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 10))) for _ in range(2000)]
+    model = io.BytesIO()
+    spm.SentencePieceTrainer.train(sentence_iterator=iter(lines), model_writer=model, vocab_size=400, model_type="bpe", byte_fallback=True,
+                                   bos_id=1, eos_id=2, unk_id=0, pad_id=-1, normalization_rule_name="identity", add_dummy_prefix=True,
+                                   remove_extra_whitespaces=False, minloglevel=2, user_defined_symbols=["[INST]", "[/INST]"])
+    sp = spm.SentencePieceProcessor(model_proto=model.getvalue())
+    n = sp.get_piece_size()
+    toks = [sp.id_to_piece(i) for i in range(n)]
+    types = [2 if sp.is_unknown(i) else 3 if sp.is_control(i) else 6 if sp.is_byte(i) else 4 if toks[i] in ("[INST]", "[/INST]") else 1 for i in range(n)]
+    shape = S.LlamaShape("tiny-mistral-synth", 2, 256, 4, 2, 512, n, 10000.0, 1e-5, 512)
+    path = str(tmp_path / "tiny_mistral.gguf")
+    S.build_model(path, shape, "q8_0", seed=11, spm_vocab={"tokens": toks, "scores": [sp.get_score(i) for i in range(n)], "types": types,
+                                                            "bos": 1, "eos": 2, "unk": 0, "chat_template": MISTRAL_TEMPLATE})
+    oracle_engine.use_hostcheck(hostcheck_lib)
+    monkeypatch.setattr(SV.N, "Engine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(SV.N, "device_count", lambda: 1)
+    s = SV.NativeInferenceService({"mistral:tiny": path})
+    eng = s._engine("mistral:tiny")
+    assert eng.info.bos_id == 1 and eng.info.eos_id == 2
+    docs = ["the quick brown fox", "hello world, naïve café", "an unseen wörd ✓"]
+    for d in docs:
+        assert list(eng.tokenize(d, add_bos=True)) == [1] + sp.encode(d)
+    res = _run(s.generateEmbedding({"id": "e1", "model": "mistral:tiny", "input": docs, "metadata": {"requestType": "embedding"}}))
+    emb = np.asarray(res["embeddings"])
+    assert emb.shape == (3, 256) and np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-4) and res["prompt_eval_count"] == sum(1 + len(sp.encode(d)) for d in docs)
+    # chat: the template is rendered (eos_token = "</s>" from the vocabulary), then tokenised with the markers as single pieces
+    eng.chat_template = MISTRAL_TEMPLATE
+    msgs = [{"role": "user", "content": "hello world"}, {"role": "assistant", "content": "the fox"}, {"role": "user", "content": "quick query"}]
+    prompt = s._chat_prompt(eng, msgs)
+    assert prompt == "[INST] hello world [/INST]the fox</s>[INST] quick query [/INST]"
+    ids = list(eng.tokenize(prompt, add_bos=True, parse_special=True))
+    inst, inst_end = sp.piece_to_id("[INST]"), sp.piece_to_id("[/INST]")
+    assert ids[0] == 1 and ids.count(inst) == 2 and ids.count(inst_end) == 2 and ids.count(2) == 1
+    s.close()
+
+
 def test_generate_prompts_can_be_framed_like_ollama(tiny_gguf, hostcheck_lib, monkeypatch):
     """apply_template=True: /api/generate-style prompts become one user turn of the model's template (metadata.system as the
     system turn) unless metadata.raw; the default service tokenises the prompt text as it is"""
